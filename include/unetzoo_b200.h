@@ -1,0 +1,180 @@
+/* C ABI of libunetzoo_b200.so -- the B200 (sm_100a) hot path of gigantenbein/UNet-Zoo.
+ *
+ * The reference is pure Python/PyTorch: its "FFI" for this path is the set of ATen/cuDNN operator calls made by
+ * torchlayers.py, models/{unet,probabilistic_unet,phiseg}.py and utils.py.  Every entry
+ * point below replaces one (or a fused group) of those call sites; the citation after each prototype names them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless marked [host]; nothing is retained or freed.
+ *   - activations: bf16, NHWC, channel count a multiple of 16 (zero padded), pixel stride `ld*` in elements
+ *     (multiple of 8) so channel slices of concat buffers can be read / written in place.
+ *   - everything the reference's callers can observe (mu, sigma, z, logits, losses, parameter gradients): fp32 in the
+ *     reference's NCHW / OIHW layouts.
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it.
+ *   - return 0 on success; non-zero = error, text via uz_last_error().  Never throws, never synchronises.
+ */
+#ifndef UNETZOO_B200_H_
+#define UNETZOO_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UZ_ABI_VERSION 1
+
+const char* uz_last_error(void);
+int uz_abi_version(void);
+int uz_device_sm_count(void);
+
+/* ---- convolutions on tcgen05 tensor cores (conv_tc.cu, wgrad_tc.cu) ------------------------------------------------ */
+
+/* Tile geometry the conv kernel will use for an [N,H,W] pixel grid: a TN x TH x TW box of 128 pixels per CTA.
+ * num_tiles sizes the `stats_partial` buffer of uz_conv_fwd.  [host out-params] */
+int uz_conv_tile_geometry(int N, int H, int W, int* TW, int* TH, int* TN, int* num_tiles);
+
+/* y[n,h,w,co] = act( scale[co] * sum_{tap,ci} x[n,h+dy,w+dx,ci] * w_packed[tap][co][ci] + shift[co] ), zero padding.
+ * taps = 9 (3x3, pad 1) or 1 (1x1).  scale/shift may be NULL (1 / 0).  relu != 0 applies max(.,0).
+ * stats_partial (optional) receives per-tile per-channel sum and sum of squares of the STORED bf16 outputs,
+ * layout [num_tiles][2][Cout] fp32, for training-mode BatchNorm (reduced by uz_bn_finalize).
+ * Replaces: nn.Conv2d forward (torchlayers.py:18; models/unet.py:25-29; models/phiseg.py:28,32,57-58,91), fused with
+ * the eval-mode BatchNorm + ReLU of torchlayers.py:20-21 or the bias + ReLU of models/unet.py:25-30; called with
+ * dgrad-packed weights it is conv2d's input-gradient (autograd of the same call sites). */
+int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, int taps,
+                void* y, int ldy, const float* scale, const float* shift, int relu, float* stats_partial,
+                void* stream);
+
+/* Workspace size (floats) for uz_conv_wgrad, or -1 if the shape is unsupported. */
+long long uz_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout, int taps);
+
+/* dw[co][ci][tap] = sum_pixels dy[p][co] * x[p + offset(tap)][ci]  (fp32, PyTorch OIHW layout, logical channel
+ * counts; Cin/Cout are the stored, padded counts).  Replaces conv2d's weight-gradient (autograd of torchlayers.py:18). */
+int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, int N, int H, int W, int Cin, int Cout, int taps,
+                  int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream);
+
+/* ---- memory-bound NHWC kernels (elementwise.cu) -------------------------------------------------------------------- */
+
+/* fp32 OIHW weights -> bf16 [taps][CoutP][CinP] (forward) and, if w_dgrad != NULL, bf16 [taps][CinP2][CoutP2] with
+ * taps flipped and channels transposed (input-gradient).  Padding is zero filled.  (fp32 parameters stay
+ * owned by the caller's stock Adam, train_model.py:49.) */
+int uz_pack_conv_weight(const float* w, int Cout, int Cin, int taps, void* w_fwd, int CoutP, int CinP, void* w_dgrad,
+                        int CinP2, int CoutP2, void* stream);
+
+/* Training-mode BatchNorm statistics: reduce the conv's per-tile partials, emit scale = gamma*invstd and
+ * shift = beta - mean*scale, save mean / invstd, update running stats (momentum, unbiased variance).
+ * Replaces nn.BatchNorm2d(eps=1e-3, momentum=0.01) statistics, torchlayers.py:20. */
+int uz_bn_finalize(const float* partial, int tiles, int C, float count, const float* gamma, const float* beta,
+                   float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                   float* mean_out, float* invstd_out, void* stream);
+
+/* Eval-mode fold of conv bias + BatchNorm running stats into the conv epilogue's scale / shift (train_model.py:139). */
+int uz_bn_eval_fold(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
+                    const float* running_var, float eps, int C, float* scale, float* shift, void* stream);
+
+/* out = act(y * scale[c] + shift[c]) -- BatchNorm normalise + ReLU (torchlayers.py:20-21). */
+int uz_affine_act(const void* y, int ldy, const float* scale, const float* shift, int relu, void* out, int ldo,
+                  long long npix, int C, void* stream);
+
+/* BatchNorm(+ReLU) backward in two passes over (dout, y): per-block partial sums -> coefficients -> dy.
+ * partial: [uz_bn_bwd_num_blocks][2][C].  dy = A*g + B*y + Cc with g = dout * [y*scale+shift > 0].
+ * Replaces autograd of torchlayers.py:20-21. */
+int uz_bn_bwd_num_blocks(long long npix, int C);
+int uz_bn_bwd_reduce(const void* dout, int ldd, const void* y, int ldy, const float* scale, const float* shift, int relu,
+                     long long npix, int C, float* partial, void* stream);
+int uz_bn_bwd_finalize(const float* partial, int nblocks, int C, float count, const float* gamma, const float* mean,
+                       const float* invstd, float* coefA, float* coefB, float* coefC, float* dgamma, float* dbeta,
+                       void* stream);
+int uz_bn_bwd_apply(const void* dout, int ldd, const void* y, int ldy, const float* scale, const float* shift, int relu,
+                    const float* coefA, const float* coefB, const float* coefC, void* dy, int lddy, long long npix,
+                    int C, void* stream);
+
+/* AvgPool2d(kernel 2, stride 2, ceil_mode) on even sizes (models/phiseg.py:23, models/unet.py:22,
+ * models/probabilistic_unet.py:56) and its gradient (optionally accumulated into dx). */
+int uz_avgpool2_fwd(const void* x, int ldx, void* out, int ldo, int N, int Ho, int Wo, int C, void* stream);
+int uz_avgpool2_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int Ho, int Wo, int C, int accumulate,
+                    void* stream);
+
+/* Bilinear x2 upsampling, align_corners != 0 (models/phiseg.py:66,213-216,305-309) or == 0 (models/unet.py:67), written
+ * at pixel stride ldo so the result can land inside a concat buffer (torch.cat of models/phiseg.py:71,315); gradient. */
+int uz_upsample2x_fwd(const void* x, int ldx, void* out, int ldo, int N, int h, int w, int C, int align_corners,
+                      void* stream);
+int uz_upsample2x_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int h, int w, int C, int align_corners,
+                      void* stream);
+
+/* Strided channel-slice copy / accumulate: torch.cat along channels and its slice gradients
+ * (models/phiseg.py:71,183,315; models/unet.py:72). */
+int uz_copy_channels(const void* src, int lds, void* dst, int ldd, long long npix, int C, int accumulate, void* stream);
+
+/* Network input: fp32 NCHW patch (+ optional mask of integer labels as float, [B,1,H,W]) -> bf16 NHWC [B,H,W,CP] with
+ * channels [image | (mask==k)-0.5, k<nlabels | 0...].  Replaces utils.convert_batch_to_onehot (utils.py:289-311, a
+ * host loop + H2D in the reference) and the cat of models/phiseg.py:176-183 / models/probabilistic_unet.py:103-109. */
+int uz_input_pack(const float* patch, const float* mask, int B, int Cimg, int H, int W, int nlabels, void* out, int CP,
+                  void* stream);
+
+/* Module-boundary layout conversions fp32 NCHW <-> bf16 NHWC (ld >= C, padding zero filled). */
+int uz_nchw_to_nhwc(const float* src, int B, int C, long long hw, void* dst, int ld, void* stream);
+int uz_nhwc_to_nchw(const void* src, int ld, int B, int C, long long hw, float* dst, void* stream);
+
+/* ---- latent heads and losses (heads_loss.cu) ------------------------------------------------------------------------ */
+
+/* SampleZBlock head (models/phiseg.py:95-106): mu = 1x1 conv, sigma = softplus(1x1 conv), z = mu + sigma*eps.
+ * feat bf16 NHWC [B*hw][C]; weights fp32 [zdim][C]; eps/mu/sigma/z fp32 NCHW [B,zdim,hw]. */
+int uz_head_fwd(const void* feat, int ld, int C, const float* wmu, const float* bmu, const float* wsig,
+                const float* bsig, const float* eps, int B, int hw, int zdim, float* mu, float* sigma, float* z,
+                void* stream);
+int uz_head_bwd_num_blocks(int B, int hw);
+/* Gradient of the head.  dmu/dsigma/dz may be NULL.  wpartial: [blocks][2*zdim][C], bpartial: [blocks][2*zdim];
+ * dw: [2*zdim][C] (mu rows then sigma rows), db: [2*zdim]; dfeat bf16 NHWC. */
+int uz_head_bwd(const void* feat, int ld, int C, const float* wmu, const float* wsig, const float* eps,
+                const float* sigma, const float* dmu, const float* dsigma, const float* dz, int B, int hw, int zdim,
+                void* dfeat, int ldd, float* wpartial, float* bpartial, float* dw, float* db, void* stream);
+
+/* One level of KL_two_gauss_with_diag_cov (models/phiseg.py:436-453, sigma1*sigma0 quirk) times `weight`
+ * (4^level, models/phiseg.py:463): out[0] = weight * mean_b 0.5 * sum(...).  Inputs fp32 [batch][per_sample]. */
+int uz_kl_fwd(const float* mu0, const float* s0, const float* mu1, const float* s1, int batch, int per_sample,
+              float weight, float* out, void* stream);
+int uz_kl_bwd(const float* mu0, const float* s0, const float* mu1, const float* s1, int batch, int per_sample,
+              float weight, const float* upstream, float* dmu0, float* ds0, float* dmu1, float* ds1, void* stream);
+
+/* Likelihood.s_layer (1x1 conv to n_classes, no norm / activation) fused with the nearest upsample to full resolution
+ * (models/phiseg.py:283-284,319-321): out fp32 NCHW [B,ncls,h*factor,wd*factor]. */
+int uz_slayer_fwd(const void* feat, int ld, int C, const float* w, const float* bias, int ncls, int B, int h, int wd,
+                  int factor, float* out, void* stream);
+int uz_slayer_bwd_num_blocks(int B, int h, int wd);
+int uz_slayer_bwd(const float* dout, const void* feat, int ld, int C, const float* w, int ncls, int B, int h, int wd,
+                  int factor, void* dfeat, int ldd, float* wpartial, float* bpartial, float* dw, float* db, void* stream);
+
+/* residual_multinoulli_loss (models/phiseg.py:481-513): for l = L-1..0, acc_l = sum_{k>=l} s_k and
+ * ce_levels[l] = mean_b sum_pixels CE(acc_l, target).  s / ds: [host] arrays of L device pointers (fp32 NCHW);
+ * ds[l] (optional) receives upstream[0] * d(sum_l ce_levels[l]) / d s_l (upstream: device scalar, NULL = 1).
+ * partial: [uz_residual_ce_num_blocks][L]. */
+int uz_residual_ce_num_blocks(int B, int hw);
+int uz_residual_ce(const float* const* s, float* const* ds, const float* upstream, int L, int ncls,
+                   const float* target, int B, int hw, float* partial, float* ce_levels, void* stream);
+
+/* PHISeg.accumulate_output (models/phiseg.py:428-434): out = s[L-1] + s[0] + ... + s[L-2] (+ softmax over classes);
+ * out may alias s[L-1] (the reference accumulates in place).  s: [host] array of L device pointers. */
+int uz_accumulate_output(const float* const* s, int L, int ncls, int B, int hw, int use_softmax, float* out,
+                         void* stream);
+
+/* ---- sample evaluation (eval_metrics.cu) ---------------------------------------------------------------------------- */
+
+/* Bit-pack (labels == label_values[l]) masks: labels [count][hw] of dtype 0 = int64, 1 = float32, 2 = uint8;
+ * bits uint32 [count][nlabels][ceil(hw/32)], counts int32 [count][nlabels].  label_values is a [host] array.
+ * Replaces the (m == lbl)*1 / torch.sum tests of utils.py:158-165. */
+int uz_ged_pack_masks(const void* labels, int dtype, int count, int hw, const int* label_values, int nlabels,
+                      unsigned int* bits, int* counts, void* stream);
+/* generalised_energy_distance (utils.py:148-200): pair_d double [N*M + N*N + M*M] (the d_sy, d_ss, d_yy lists in the
+ * reference's order); out double [4] = {GED, sum d_sy, sum d_ss, sum d_yy}, summed sequentially like Python. */
+int uz_ged_pairwise(const unsigned int* bits_s, const int* cnt_s, int N, const unsigned int* bits_y, const int* cnt_y,
+                    int M, int nlabels, int hw, double* pair_d, double* out, void* stream);
+/* torch.argmax(dim=1) of fp32 NCHW [N,C,hw] -> uint8 [N,hw] (train_model.py:195). */
+int uz_argmax_classes(const float* x, int N, int C, int hw, unsigned char* out, void* stream);
+/* variance_ncc_dist (utils.py:202-247 with ncc :130-145): probs fp32 [N,C,hw]; gt one-hot [M,C,hw] of gt_dtype
+ * (0 = int64, 1 = float32, 2 = uint8); work double [(1+M)*hw + M]; out double [1]. */
+int uz_variance_ncc(const float* probs, const void* gt, int gt_dtype, int N, int C, int hw, int M, double* work,
+                    double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNETZOO_B200_H_ */

@@ -1,0 +1,105 @@
+"""Generate tests/golden/*.npz from the REAL reference modules (run in the build container only):
+
+    python -m oracle.make_golden
+
+Fixtures hold seeds + reference OUTPUTS only; weights and inputs are re-synthesised from the seeds by
+oracle/synth.py, so the files stay small.  Everything here executes /root/reference code unmodified
+(through oracle/ref_loader.py shims) -- TEST INFRASTRUCTURE.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import synth                                    # noqa: E402
+from oracle.ref_loader import load_reference                # noqa: E402
+from oracle.ref_run import build_reference_phiseg, injected_noise  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def phiseg_case(tag, filters, batch, wseed, dseed, nseed, keep_logits):
+    net = build_reference_phiseg(filters)
+    sd = synth.synth_state_dict(net.state_dict(), seed=wseed)
+    patch, labels, mask = synth.lidc_like_batch(batch, seed=dseed)
+    eps = synth.noise_list(synth.phiseg_noise_shapes(batch), seed=nseed)
+    out = {'filters': np.asarray(filters), 'batch': batch, 'wseed': wseed, 'dseed': dseed, 'nseed': nseed}
+    for training in (True, False):
+        net.load_state_dict(sd)
+        net.train(training)
+        key = 'train' if training else 'eval'
+        with injected_noise(eps):
+            s = net.forward(patch, mask, training=training)
+            s = [t.clone() for t in s]
+            net.loss_dict = {}
+            loss = net.loss(mask)
+        out[key + '_loss'] = float(loss)
+        for k, v in net.loss_dict.items():
+            out['%s_%s' % (key, k)] = float(v)
+        for lvl in range(5):
+            out['%s_post_mu%d' % (key, lvl)] = net.posterior_mu[lvl].detach().numpy()
+            out['%s_post_sigma%d' % (key, lvl)] = net.posterior_sigma[lvl].detach().numpy()
+            out['%s_prior_mu%d' % (key, lvl)] = net.prior_mu[lvl].detach().numpy()
+            out['%s_prior_sigma%d' % (key, lvl)] = net.prior_sigma[lvl].detach().numpy()
+        acc = sum(s)
+        out[key + '_logit_absmean'] = float(acc.abs().mean())
+        if keep_logits:
+            out[key + '_logits'] = acc.detach().numpy().astype(np.float32)
+        else:
+            out[key + '_logits_ds8'] = acc.detach()[:, :, ::8, ::8].numpy().astype(np.float32)
+        if training:
+            net.zero_grad()
+            loss.backward()
+            gn = {n: float(p.grad.norm()) for n, p in net.named_parameters() if p.grad is not None}
+            names = sorted(gn)
+            out['train_grad_names'] = np.asarray(names)
+            out['train_grad_norms'] = np.asarray([gn[n] for n in names])
+            out['train_nograd_names'] = np.asarray(sorted(n for n, p in net.named_parameters() if p.grad is None))
+            rs = net.state_dict()
+            k = 'posterior.contracting_path.3.layers.2.convolution.1.running_var'
+            out['train_running_var_probe'] = rs[k].numpy().copy()
+    np.savez_compressed(os.path.join(GOLDEN, tag + '.npz'), **out)
+    print(tag, out['train_loss'], out['eval_loss'])
+
+
+def metrics_case():
+    ns = load_reference()
+    rs = np.random.RandomState(11)
+    out = {}
+    # GED: N samples, M annotators, binary + 3-class, with empty masks
+    for tag, (N, M, C, S) in {'bin': (7, 4, 2, 32), 'tri': (5, 3, 3, 24)}.items():
+        samples = (rs.uniform(size=(N, S, S)) < 0.3).astype(np.int64) * rs.randint(1, C, (N, S, S))
+        gts = (rs.uniform(size=(M, S, S)) < 0.3).astype(np.int64) * rs.randint(1, C, (M, S, S))
+        samples[0] = 0
+        gts[-1] = 0
+        ged = ns.utils.generalised_energy_distance(torch.from_numpy(samples), torch.from_numpy(gts).float(),
+                                                   nlabels=C - 1, label_range=range(1, C))
+        logits = rs.standard_normal((N, C, S, S)).astype(np.float32) * 2
+        probs = torch.softmax(torch.from_numpy(logits), 1)
+        onehot = ns.utils.convert_batch_to_onehot(torch.from_numpy(gts).float().unsqueeze(1), nlabels=C)
+        ncc = ns.utils.variance_ncc_dist(probs, onehot)
+        out[tag + '_samples'] = samples.astype(np.uint8)
+        out[tag + '_gts'] = gts.astype(np.uint8)
+        out[tag + '_logits'] = logits
+        out[tag + '_ged'] = float(ged)
+        out[tag + '_ncc'] = np.asarray(ncc, np.float64)
+        out[tag + '_onehot'] = onehot.numpy().astype(np.uint8)
+    # KL known answer from the reference method
+    net = build_reference_phiseg([16] * 7)
+    kl = net.KL_two_gauss_with_diag_cov(torch.tensor([[[[0.5, -1.0]]]]), torch.tensor([[[[0.8, 1.5]]]]),
+                                        torch.tensor([[[[0.0, 0.25]]]]), torch.tensor([[[[1.2, 0.7]]]]))
+    out['kl1'] = float(kl)
+    np.savez_compressed(os.path.join(GOLDEN, 'metrics.npz'), **out)
+    print('metrics', out['bin_ged'], out['bin_ncc'], out['tri_ged'], out['tri_ncc'], out['kl1'])
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    os.makedirs(GOLDEN, exist_ok=True)
+    phiseg_case('phiseg_small', [16, 32, 32, 32, 32, 32, 32], 4, 1, 3, 5, keep_logits=True)
+    phiseg_case('phiseg_lidc', [32, 64, 128, 192, 192, 192, 192], 2, 2, 4, 6, keep_logits=False)
+    metrics_case()

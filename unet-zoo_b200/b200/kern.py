@@ -1,0 +1,372 @@
+"""Thin tensor-level wrappers over the C ABI (no autograd).  Activations are torch bf16 tensors of shape
+[N, H, W, C] whose last-dim stride is 1 and whose pixel stride (stride(2)) may exceed C (channel slices of concat
+buffers); N/H/W must be densely packed over pixels."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+BN_EPS = 1e-3        # reference torchlayers.py:20
+BN_MOMENTUM = 0.01
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _check_act(t):
+    if not t.is_cuda:
+        raise _lib.UnetZooLibError('B200 path needs CUDA tensors (no CPU fallback)')
+    assert t.dtype == torch.bfloat16 and t.dim() == 4 and t.stride(3) == 1, (t.dtype, t.shape, t.stride())
+    n, h, w, c = t.shape
+    ld = t.stride(2)
+    assert h == 1 or t.stride(1) == w * ld, t.stride()
+    assert n == 1 or t.stride(0) == h * w * ld, t.stride()
+    return n, h, w, c, ld
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def new_act(n, h, w, c, device):
+    return torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+
+
+def conv_tile_geometry(n, h, w):
+    tw, th, tn, nt = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.call('uz_conv_tile_geometry', n, h, w, ctypes.byref(tw), ctypes.byref(th), ctypes.byref(tn), ctypes.byref(nt))
+    return tw.value, th.value, tn.value, nt.value
+
+
+def pack_conv_weight(w, need_dgrad=True):
+    """w fp32 [Cout,Cin,kh,kw] -> (w_fwd bf16 [taps,CoutP,CinP], w_dgrad bf16 [taps,CinP,CoutP] or None)."""
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w.shape[2] * w.shape[3]
+    coutp, cinp = pad16(cout), pad16(cin)
+    wf = torch.empty((taps, coutp, cinp), dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty((taps, cinp, coutp), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
+    _lib.call('uz_pack_conv_weight', _p(w.contiguous()), cout, cin, taps, _p(wf), coutp, cinp, _p(wd), cinp, coutp,
+              _stream())
+    return wf, wd
+
+
+def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=False):
+    """x [N,H,W,Cin] bf16, w_packed [taps,Cout,Cin] bf16 -> y [N,H,W,Cout] bf16 (+ stats partial [tiles,2,Cout])."""
+    n, h, w, cin, ldx = _check_act(x)
+    taps, cout, cin_w = w_packed.shape
+    assert cin_w == cin, (cin_w, cin)
+    if out is None:
+        out = new_act(n, h, w, cout, x.device)
+    _, _, _, _, ldy = _check_act(out)
+    partial = None
+    if stats:
+        nt = conv_tile_geometry(n, h, w)[3]
+        partial = torch.empty((nt, 2, cout), dtype=torch.float32, device=x.device)
+    _lib.call('uz_conv_fwd', _p(x), n, h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy, _p(scale), _p(shift),
+              int(relu), _p(partial), _stream())
+    return out, partial
+
+
+def conv_wgrad(x, dy, taps, cin_logical, cout_logical):
+    """-> dw fp32 [cout_logical, cin_logical, taps]"""
+    n, h, w, cin, ldx = _check_act(x)
+    _, _, _, cout, lddy = _check_act(dy)
+    ws = _lib.raw('uz_wgrad_workspace_floats')(n, h, w, cin, cout, taps)
+    if ws < 0:
+        raise _lib.UnetZooLibError('uz_conv_wgrad: unsupported shape Cin=%d Cout=%d' % (cin, cout))
+    work = torch.empty((ws,), dtype=torch.float32, device=x.device)
+    dw = torch.empty((cout_logical, cin_logical, taps), dtype=torch.float32, device=x.device)
+    _lib.call('uz_conv_wgrad', _p(x), ldx, _p(dy), lddy, n, h, w, cin, cout, taps, cin_logical, cout_logical, _p(work),
+              _p(dw), _stream())
+    return dw
+
+
+def bn_finalize(partial, count, gamma, beta, running_mean=None, running_var=None, eps=BN_EPS, momentum=BN_MOMENTUM):
+    tiles, _, c = partial.shape
+    dev = partial.device
+    scale = torch.empty(c, dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    mean = torch.empty_like(scale)
+    invstd = torch.empty_like(scale)
+    _lib.call('uz_bn_finalize', _p(partial), tiles, c, float(count), _p(gamma), _p(beta), eps, momentum,
+              _p(running_mean), _p(running_var), _p(scale), _p(shift), _p(mean), _p(invstd), _stream())
+    return scale, shift, mean, invstd
+
+
+def bn_eval_fold(conv_bias, gamma, beta, rm, rv, eps=BN_EPS):
+    c = rm.numel()
+    scale = torch.empty(c, dtype=torch.float32, device=rm.device)
+    shift = torch.empty_like(scale)
+    _lib.call('uz_bn_eval_fold', _p(conv_bias), _p(gamma), _p(beta), _p(rm), _p(rv), eps, c, _p(scale), _p(shift),
+              _stream())
+    return scale, shift
+
+
+def affine_act(y, scale, shift, relu=True, out=None):
+    n, h, w, c, ldy = _check_act(y)
+    if out is None:
+        out = new_act(n, h, w, c, y.device)
+    ldo = _check_act(out)[4]
+    _lib.call('uz_affine_act', _p(y), ldy, _p(scale), _p(shift), int(relu), _p(out), ldo, n * h * w, c, _stream())
+    return out
+
+
+def bn_relu_bwd(dout, y, scale, shift, gamma, mean, invstd, relu=True):
+    """-> dy bf16, dgamma, dbeta (fp32 [C])"""
+    n, h, w, c, ldd = _check_act(dout)
+    ldy = _check_act(y)[4]
+    npix = n * h * w
+    nb = _lib.raw('uz_bn_bwd_num_blocks')(npix, c)
+    dev = y.device
+    partial = torch.empty((nb, 2, c), dtype=torch.float32, device=dev)
+    _lib.call('uz_bn_bwd_reduce', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), npix, c, _p(partial),
+              _stream())
+    coef = torch.empty((3, c), dtype=torch.float32, device=dev)
+    dgamma = torch.empty(c, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+    _lib.call('uz_bn_bwd_finalize', _p(partial), nb, c, float(npix), _p(gamma), _p(mean), _p(invstd), _p(coef[0]),
+              _p(coef[1]), _p(coef[2]), _p(dgamma), _p(dbeta), _stream())
+    dy = new_act(n, h, w, c, dev)
+    _lib.call('uz_bn_bwd_apply', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), _p(coef[0]), _p(coef[1]),
+              _p(coef[2]), _p(dy), c, npix, c, _stream())
+    return dy, dgamma, dbeta
+
+
+def relu_bwd(dout, y, scale, shift):
+    """plain (bias+)ReLU backward: dy = dout * [y*scale+shift > 0]"""
+    n, h, w, c, ldd = _check_act(dout)
+    ldy = _check_act(y)[4]
+    dy = new_act(n, h, w, c, y.device)
+    _lib.call('uz_bn_bwd_apply', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), 1, None, None, None, _p(dy), c,
+              n * h * w, c, _stream())
+    return dy
+
+
+def avgpool2_fwd(x):
+    n, h, w, c, ldx = _check_act(x)
+    out = new_act(n, h // 2, w // 2, c, x.device)
+    _lib.call('uz_avgpool2_fwd', _p(x), ldx, _p(out), c, n, h // 2, w // 2, c, _stream())
+    return out
+
+
+def avgpool2_bwd(dout):
+    n, ho, wo, c, ldd = _check_act(dout)
+    dx = new_act(n, ho * 2, wo * 2, c, dout.device)
+    _lib.call('uz_avgpool2_bwd', _p(dout), ldd, _p(dx), c, n, ho, wo, c, 0, _stream())
+    return dx
+
+
+def upsample2x_fwd(x, align_corners=True, out=None):
+    n, h, w, c, ldx = _check_act(x)
+    if out is None:
+        out = new_act(n, 2 * h, 2 * w, c, x.device)
+    ldo = _check_act(out)[4]
+    _lib.call('uz_upsample2x_fwd', _p(x), ldx, _p(out), ldo, n, h, w, c, int(align_corners), _stream())
+    return out
+
+
+def upsample2x_bwd(dout, align_corners=True):
+    n, hh, ww, c, ldd = _check_act(dout)
+    dx = new_act(n, hh // 2, ww // 2, c, dout.device)
+    _lib.call('uz_upsample2x_bwd', _p(dout), ldd, _p(dx), c, n, hh // 2, ww // 2, c, int(align_corners), _stream())
+    return dx
+
+
+def copy_channels(src, dst, accumulate=False):
+    n, h, w, c, lds = _check_act(src)
+    ldd = _check_act(dst)[4]
+    assert dst.shape == src.shape
+    _lib.call('uz_copy_channels', _p(src), lds, _p(dst), ldd, n * h * w, c, int(accumulate), _stream())
+    return dst
+
+
+def input_pack(patch, mask, nlabels=2, cp=16):
+    b, cimg, h, w = patch.shape
+    out = new_act(b, h, w, cp, patch.device)
+    patch = patch.contiguous().float()
+    if mask is not None:
+        mask = mask.contiguous().float()
+    _lib.call('uz_input_pack', _p(patch), _p(mask), b, cimg, h, w, nlabels, _p(out), cp, _stream())
+    return out
+
+
+def nchw_to_nhwc(x, ld=None):
+    b, c, h, w = x.shape
+    ld = ld or pad16(c)
+    out = new_act(b, h, w, ld, x.device)
+    _lib.call('uz_nchw_to_nhwc', _p(x.contiguous().float()), b, c, h * w, _p(out), ld, _stream())
+    return out
+
+
+def nhwc_to_nchw(x, c=None):
+    n, h, w, cc, ld = _check_act(x)
+    c = c or cc
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _lib.call('uz_nhwc_to_nchw', _p(x), ld, n, c, h * w, _p(out), _stream())
+    return out
+
+
+def head_fwd(feat, wmu, bmu, wsig, bsig, eps):
+    n, h, w, c, ld = _check_act(feat)
+    zdim = wmu.shape[0]
+    mu = torch.empty((n, zdim, h, w), dtype=torch.float32, device=feat.device)
+    sigma = torch.empty_like(mu)
+    z = torch.empty_like(mu)
+    _lib.call('uz_head_fwd', _p(feat), ld, c, _p(wmu), _p(bmu), _p(wsig), _p(bsig), _p(eps), n, h * w, zdim, _p(mu),
+              _p(sigma), _p(z), _stream())
+    return mu, sigma, z
+
+
+def head_bwd(feat, wmu, wsig, eps, sigma, dmu, dsigma, dz):
+    n, h, w, c, ld = _check_act(feat)
+    zdim = wmu.shape[0]
+    dev = feat.device
+    nb = _lib.raw('uz_head_bwd_num_blocks')(n, h * w)
+    wpartial = torch.empty((nb, 2 * zdim, c), dtype=torch.float32, device=dev)
+    bpartial = torch.empty((nb, 2 * zdim), dtype=torch.float32, device=dev)
+    dw = torch.empty((2 * zdim, c), dtype=torch.float32, device=dev)
+    db = torch.empty((2 * zdim,), dtype=torch.float32, device=dev)
+    dfeat = new_act(n, h, w, c, dev)
+    _lib.call('uz_head_bwd', _p(feat), ld, c, _p(wmu), _p(wsig), _p(eps), _p(sigma), _p(dmu), _p(dsigma), _p(dz), n,
+              h * w, zdim, _p(dfeat), c, _p(wpartial), _p(bpartial), _p(dw), _p(db), _stream())
+    return dfeat, dw, db
+
+
+def kl_fwd(mu0, s0, mu1, s1, weight):
+    b = mu0.shape[0]
+    per = mu0.numel() // b
+    out = torch.empty((1,), dtype=torch.float32, device=mu0.device)
+    _lib.call('uz_kl_fwd', _p(mu0), _p(s0), _p(mu1), _p(s1), b, per, float(weight), _p(out), _stream())
+    return out
+
+
+def kl_bwd(mu0, s0, mu1, s1, weight, upstream):
+    b = mu0.shape[0]
+    per = mu0.numel() // b
+    g = [torch.empty_like(mu0) for _ in range(4)]
+    _lib.call('uz_kl_bwd', _p(mu0), _p(s0), _p(mu1), _p(s1), b, per, float(weight), _p(upstream), _p(g[0]), _p(g[1]),
+              _p(g[2]), _p(g[3]), _stream())
+    return g
+
+
+def slayer_fwd(feat, w, bias, factor):
+    n, h, wd, c, ld = _check_act(feat)
+    ncls = w.shape[0]
+    out = torch.empty((n, ncls, h * factor, wd * factor), dtype=torch.float32, device=feat.device)
+    _lib.call('uz_slayer_fwd', _p(feat), ld, c, _p(w), _p(bias), ncls, n, h, wd, factor, _p(out), _stream())
+    return out
+
+
+def slayer_bwd(dout, feat, w, factor):
+    n, h, wd, c, ld = _check_act(feat)
+    ncls = w.shape[0]
+    dev = feat.device
+    nb = _lib.raw('uz_slayer_bwd_num_blocks')(n, h, wd)
+    wpartial = torch.empty((nb, ncls, c), dtype=torch.float32, device=dev)
+    bpartial = torch.empty((nb, ncls), dtype=torch.float32, device=dev)
+    dw = torch.empty((ncls, c), dtype=torch.float32, device=dev)
+    db = torch.empty((ncls,), dtype=torch.float32, device=dev)
+    dfeat = new_act(n, h, wd, c, dev)
+    _lib.call('uz_slayer_bwd', _p(dout.contiguous()), _p(feat), ld, c, _p(w), ncls, n, h, wd, factor, _p(dfeat), c,
+              _p(wpartial), _p(bpartial), _p(dw), _p(db), _stream())
+    return dfeat, dw, db
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def residual_ce(s_list, target, need_grad=True, upstream=None):
+    """s_list: L fp32 NCHW logits (index = latent level); -> ce_levels fp32 [L], grads list or None."""
+    L = len(s_list)
+    b, ncls, h, w = s_list[0].shape
+    dev = s_list[0].device
+    s_list = [s.contiguous() for s in s_list]
+    grads = [torch.empty_like(s) for s in s_list] if need_grad else None
+    nb = _lib.raw('uz_residual_ce_num_blocks')(b, h * w)
+    partial = torch.empty((nb, L), dtype=torch.float32, device=dev)
+    ce = torch.empty((L,), dtype=torch.float32, device=dev)
+    target = target.contiguous().float()
+    _lib.call('uz_residual_ce', _ptr_array(s_list), _ptr_array(grads) if need_grad else None, _p(upstream), L, ncls,
+              _p(target), b, h * w, _p(partial), _p(ce), _stream())
+    return ce, grads
+
+
+def accumulate_output(s_list, use_softmax, out):
+    L = len(s_list)
+    b, ncls, h, w = s_list[0].shape
+    _lib.call('uz_accumulate_output', _ptr_array(s_list), L, ncls, b, h * w, int(use_softmax), _p(out), _stream())
+    return out
+
+
+_DTYPE_CODE = {torch.int64: 0, torch.float32: 1, torch.uint8: 2}
+
+
+def ged(samples, gts, label_values):
+    """samples [N,H,W], gts [M,H,W] (int64 / float32 / uint8) -> double tensor [4] = GED, sum d_sy, d_ss, d_yy."""
+    if not samples.is_cuda:
+        raise _lib.UnetZooLibError('B200 path needs CUDA tensors (no CPU fallback)')
+    samples = samples.contiguous()
+    gts = gts.contiguous()
+    n, m = samples.shape[0], gts.shape[0]
+    hw = samples[0].numel()
+    assert gts[0].numel() == hw
+    nl = len(label_values)
+    words = (hw + 31) // 32
+    dev = samples.device
+    lv = (ctypes.c_int * nl)(*[int(v) for v in label_values])
+    bits_s = torch.empty((n, nl, words), dtype=torch.int32, device=dev)
+    cnt_s = torch.empty((n, nl), dtype=torch.int32, device=dev)
+    bits_y = torch.empty((m, nl, words), dtype=torch.int32, device=dev)
+    cnt_y = torch.empty((m, nl), dtype=torch.int32, device=dev)
+    _lib.call('uz_ged_pack_masks', _p(samples), _DTYPE_CODE[samples.dtype], n, hw, lv, nl, _p(bits_s), _p(cnt_s),
+              _stream())
+    _lib.call('uz_ged_pack_masks', _p(gts), _DTYPE_CODE[gts.dtype], m, hw, lv, nl, _p(bits_y), _p(cnt_y), _stream())
+    pair_d = torch.empty((n * m + n * n + m * m,), dtype=torch.float64, device=dev)
+    out = torch.empty((4,), dtype=torch.float64, device=dev)
+    _lib.call('uz_ged_pairwise', _p(bits_s), _p(cnt_s), n, _p(bits_y), _p(cnt_y), m, nl, hw, _p(pair_d), _p(out),
+              _stream())
+    return out
+
+
+def argmax_classes(x):
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
+    _lib.call('uz_argmax_classes', _p(x.contiguous()), n, c, h * w, _p(out), _stream())
+    return out
+
+
+def variance_ncc(probs, gt_onehot):
+    """probs fp32 [N,C,H,W], gt_onehot [M,C,H,W] -> double tensor [1]"""
+    if not probs.is_cuda:
+        raise _lib.UnetZooLibError('B200 path needs CUDA tensors (no CPU fallback)')
+    probs = probs.contiguous().float()
+    gt_onehot = gt_onehot.contiguous().to(probs.device)
+    n, c, h, w = probs.shape
+    m = gt_onehot.shape[0]
+    hw = h * w
+    work = torch.empty(((1 + m) * hw + m,), dtype=torch.float64, device=probs.device)
+    out = torch.empty((1,), dtype=torch.float64, device=probs.device)
+    _lib.call('uz_variance_ncc', _p(probs), _p(gt_onehot), _DTYPE_CODE[gt_onehot.dtype], n, c, hw, m, _p(work), _p(out),
+              _stream())
+    return out
+
+
+def channel_sum(g):
+    """per-channel sum over pixels of a bf16 NHWC tensor -> fp32 [C] (conv bias gradient of BN-free layers)."""
+    n, h, w, c, ld = _check_act(g)
+    npix = n * h * w
+    nb = _lib.raw('uz_bn_bwd_num_blocks')(npix, c)
+    partial = torch.empty((nb, 2, c), dtype=torch.float32, device=g.device)
+    one = torch.ones(c, dtype=torch.float32, device=g.device)
+    _lib.call('uz_bn_bwd_reduce', _p(g), ld, _p(g), ld, _p(one), _p(one), 0, npix, c, _p(partial), _stream())
+    return partial[:, 0].sum(0)

@@ -1,0 +1,288 @@
+"""torch.autograd.Functions over the C ABI.  They own the saved tensors and workspaces (SURVEY.md 8b "Ownership")
+and keep the parameter / gradient tensors in the reference's fp32 NCHW / OIHW layouts so the caller's stock Adam
+(reference train_model.py:49) keeps working.
+
+``Act`` is the internal activation handle that flows between the drop-in modules: a bf16 NHWC tensor whose channel
+count is padded to a multiple of 16, plus the logical channel count.
+"""
+import torch
+
+from . import kern
+
+
+class Act:
+    """bf16 NHWC activation [N,H,W,Cp] (Cp = pad16(c)); ``c`` = logical channels."""
+    __slots__ = ('t', 'c')
+
+    def __init__(self, t, c):
+        self.t = t
+        self.c = c
+
+    @property
+    def shape(self):
+        n, h, w, _ = self.t.shape
+        return (n, self.c, h, w)
+
+
+def _dense(t):
+    """grads handed over by autograd may be arbitrary views; kernels need unit channel stride + packed pixels."""
+    if t.stride(3) == 1 and (t.shape[1] == 1 or t.stride(1) == t.shape[2] * t.stride(2)) and \
+            (t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.shape[2] * t.stride(2)) and t.stride(2) % 8 == 0 \
+            and t.data_ptr() % 16 == 0:
+        return t
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ layout boundary
+class ToNHWC(torch.autograd.Function):
+    """fp32 NCHW -> bf16 NHWC (padded).  Used at module boundaries and for z -> next conv."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.c = x.shape[1]
+        return kern.nchw_to_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return kern.nhwc_to_nchw(_dense(g), ctx.c)
+
+
+class FromNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, c):
+        ctx.ld = t.shape[3]
+        return kern.nhwc_to_nchw(t, c)
+
+    @staticmethod
+    def backward(ctx, g):
+        return kern.nchw_to_nhwc(g, ctx.ld), None
+
+
+def to_act(x):
+    if isinstance(x, Act):
+        return x
+    if not x.is_cuda:
+        raise kern._lib.UnetZooLibError('UNet-Zoo B200 modules need CUDA tensors: there is no CPU fallback path')
+    return Act(ToNHWC.apply(x.float()), x.shape[1])
+
+
+def from_act(a):
+    return FromNHWC.apply(a.t, a.c)
+
+
+# ------------------------------------------------------------------------------------------------ conv (+BN) (+ReLU)
+class ConvBNAct(torch.autograd.Function):
+    """Conv2D of the reference (torchlayers.py:7-29): conv(k=3 pad 1 | k=1) + bias -> BatchNorm(train) -> ReLU.
+
+    forward (training): tcgen05 conv with statistics epilogue -> uz_bn_finalize -> uz_affine_act.
+    backward: two-pass BN/ReLU backward -> dgrad (same conv kernel, flipped weights) + tcgen05 wgrad.
+    The conv bias gets a zero gradient: BatchNorm removes any per-channel constant, d loss / d bias == 0 exactly.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, relu, cin_logical):
+        need_dx = ctx.needs_input_grad[0]
+        wf, wd = kern.pack_conv_weight(weight, need_dgrad=need_dx)
+        y, partial = kern.conv_fwd(x, wf, shift=bias, stats=True)
+        n, h, w, _ = x.shape
+        scale, shift, mean, invstd = kern.bn_finalize(partial, n * h * w, gamma, beta, running_mean, running_var)
+        a = kern.affine_act(y, scale, shift, relu=relu)
+        ctx.save_for_backward(x, y, wd, scale, shift, mean, invstd, gamma)
+        ctx.relu = relu
+        ctx.cin_logical = cin_logical
+        ctx.wshape = weight.shape
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        x, y, wd, scale, shift, mean, invstd, gamma = ctx.saved_tensors
+        da = _dense(da)
+        dy, dgamma, dbeta = kern.bn_relu_bwd(da, y, scale, shift, gamma, mean, invstd, relu=ctx.relu)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx, _ = kern.conv_fwd(dy, wd)
+        cout, cin, kh, kw = ctx.wshape
+        dw = kern.conv_wgrad(x, dy, kh * kw, cin, cout).view(cout, cin, kh, kw)
+        dbias = torch.zeros(cout, dtype=torch.float32, device=dy.device)
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None
+
+
+class ConvAffineAct(torch.autograd.Function):
+    """Inference-time Conv2D (BatchNorm running statistics folded into the conv epilogue) and the BN-free
+    conv + bias (+ReLU) of models/unet.py:25-30 (scale = 1, shift = bias): ONE kernel per layer."""
+
+    @staticmethod
+    def forward(ctx, x, weight, scale, shift, relu, cin_logical, bias_is_shift):
+        need_dx = ctx.needs_input_grad[0]
+        need_bwd = need_dx or ctx.needs_input_grad[1]
+        wf, wd = kern.pack_conv_weight(weight, need_dgrad=need_dx)
+        a, _ = kern.conv_fwd(x, wf, scale=scale, shift=shift, relu=relu)
+        if need_bwd:
+            ctx.save_for_backward(x, a, wd, scale)
+        ctx.relu = relu
+        ctx.cin_logical = cin_logical
+        ctx.wshape = weight.shape
+        ctx.bias_is_shift = bias_is_shift
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        x, a, wd, scale = ctx.saved_tensors
+        if scale is not None:
+            raise NotImplementedError('backward through eval-mode (folded) BatchNorm is not on the hot path; '
+                                      'call net.train() for training (reference train_model.py:95)')
+        da = _dense(da)
+        cout, cin, kh, kw = ctx.wshape
+        one = torch.ones(cout, dtype=torch.float32, device=da.device)
+        zero = torch.zeros_like(one)
+        if ctx.relu:
+            dy = kern.relu_bwd(da, a, one, zero)
+        else:
+            dy = da
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx, _ = kern.conv_fwd(dy, wd)
+        dw = kern.conv_wgrad(x, dy, kh * kw, cin, cout).view(cout, cin, kh, kw)
+        dshift = None
+        if ctx.bias_is_shift and ctx.needs_input_grad[3]:
+            dshift = kern.channel_sum(dy)
+        return dx, dw, None, dshift, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ pooling / upsampling / concat
+class AvgPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return kern.avgpool2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return kern.avgpool2_bwd(_dense(g))
+
+
+class Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, align_corners):
+        ctx.align = align_corners
+        return kern.upsample2x_fwd(x, align_corners)
+
+    @staticmethod
+    def backward(ctx, g):
+        return kern.upsample2x_bwd(_dense(g), ctx.align), None
+
+
+class Concat(torch.autograd.Function):
+    """torch.cat([a, b], dim=channels) on NHWC; with up_b the second operand is bilinearly upsampled x2 on the fly
+    (Likelihood top-down path, models/phiseg.py:304-315; U-Net decoder, models/unet.py:67-72)."""
+
+    @staticmethod
+    def forward(ctx, a, b, up_a, up_b, align_corners):
+        n = a.shape[0]
+        h = a.shape[1] * (2 if up_a else 1)
+        w = a.shape[2] * (2 if up_a else 1)
+        ca, cb = a.shape[3], b.shape[3]
+        out = kern.new_act(n, h, w, ca + cb, a.device)
+        for src, up, sl in ((a, up_a, out[..., :ca]), (b, up_b, out[..., ca:])):
+            if up:
+                kern.upsample2x_fwd(src, align_corners, out=sl)
+            else:
+                kern.copy_channels(src, sl)
+        ctx.cfg = (ca, up_a, up_b, align_corners)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ca, up_a, up_b, align = ctx.cfg
+        g = _dense(g)
+        ga, gb = g[..., :ca], g[..., ca:]
+        da = kern.upsample2x_bwd(ga, align) if up_a else ga
+        db = kern.upsample2x_bwd(gb, align) if up_b else gb
+        return da, db, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ latent head / losses
+class LatentHead(torch.autograd.Function):
+    """mu, sigma = softplus(.), z = mu + sigma * eps from NHWC features (models/phiseg.py:95-106)."""
+
+    @staticmethod
+    def forward(ctx, feat, wmu, bmu, wsig, bsig, eps):
+        c = feat.shape[3]
+        wm = wmu.reshape(wmu.shape[0], -1)
+        ws = wsig.reshape(wsig.shape[0], -1)
+        if wm.shape[1] != c:          # features are channel padded
+            wm = torch.nn.functional.pad(wm, (0, c - wm.shape[1]))
+            ws = torch.nn.functional.pad(ws, (0, c - ws.shape[1]))
+        wm, ws = wm.contiguous(), ws.contiguous()
+        mu, sigma, z = kern.head_fwd(feat, wm, bmu, ws, bsig, eps)
+        ctx.save_for_backward(feat, wm, ws, eps, sigma)
+        ctx.wshape = wmu.shape
+        return mu, sigma, z
+
+    @staticmethod
+    def backward(ctx, dmu, dsigma, dz):
+        feat, wm, ws, eps, sigma = ctx.saved_tensors
+        cont = lambda t: None if t is None else t.contiguous()
+        dfeat, dw, db = kern.head_bwd(feat, wm, ws, eps, sigma, cont(dmu), cont(dsigma), cont(dz))
+        zdim, cl = ctx.wshape[0], ctx.wshape[1]
+        dwmu = dw[:zdim, :cl].reshape(ctx.wshape)
+        dwsig = dw[zdim:, :cl].reshape(ctx.wshape)
+        return dfeat, dwmu, db[:zdim], dwsig, db[zdim:], None
+
+
+class KLLevel(torch.autograd.Function):
+    """weight * KL_two_gauss_with_diag_cov (models/phiseg.py:436-453,463-472)."""
+
+    @staticmethod
+    def forward(ctx, mu0, s0, mu1, s1, weight):
+        mu0, s0, mu1, s1 = (t.contiguous() for t in (mu0, s0, mu1, s1))
+        ctx.save_for_backward(mu0, s0, mu1, s1)
+        ctx.weight = weight
+        return kern.kl_fwd(mu0, s0, mu1, s1, weight).reshape(())
+
+    @staticmethod
+    def backward(ctx, up):
+        mu0, s0, mu1, s1 = ctx.saved_tensors
+        g = kern.kl_bwd(mu0, s0, mu1, s1, ctx.weight, up.reshape(1).contiguous())
+        return g[0], g[1], g[2], g[3], None
+
+
+class SLayerNearest(torch.autograd.Function):
+    """1x1 conv to class logits + nearest upsample to the image size (models/phiseg.py:319-321)."""
+
+    @staticmethod
+    def forward(ctx, feat, weight, bias, factor):
+        c = feat.shape[3]
+        w2 = weight.reshape(weight.shape[0], -1)
+        if w2.shape[1] != c:
+            w2 = torch.nn.functional.pad(w2, (0, c - w2.shape[1]))
+        w2 = w2.contiguous()
+        ctx.save_for_backward(feat, w2)
+        ctx.factor = factor
+        ctx.wshape = weight.shape
+        return kern.slayer_fwd(feat, w2, bias, factor)
+
+    @staticmethod
+    def backward(ctx, g):
+        feat, w2 = ctx.saved_tensors
+        dfeat, dw, db = kern.slayer_bwd(g, feat, w2, ctx.factor)
+        return dfeat, dw[:, :ctx.wshape[1]].reshape(ctx.wshape), db, None
+
+
+class ResidualCE(torch.autograd.Function):
+    """residual_multinoulli_loss (models/phiseg.py:492-513): returns (sum over levels, per-level values).  The
+    gradient kernel is the same fused pass re-run in backward with the upstream scalar folded in."""
+
+    @staticmethod
+    def forward(ctx, target, *s_list):
+        s_list = [s.contiguous() for s in s_list]
+        ce, _ = kern.residual_ce(s_list, target, need_grad=False)
+        ctx.save_for_backward(target, *s_list)
+        total = ce.sum()
+        ctx.mark_non_differentiable(ce)
+        return total, ce
+
+    @staticmethod
+    def backward(ctx, up, _unused):
+        target, *s_list = ctx.saved_tensors
+        _, grads = kern.residual_ce(list(s_list), target, need_grad=True, upstream=up.reshape(1).contiguous().float())
+        return (None,) + tuple(grads)

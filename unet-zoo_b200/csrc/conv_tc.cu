@@ -1,0 +1,300 @@
+// 3x3 (pad 1) / 1x1 convolution as implicit GEMM on tcgen05 tensor cores, NHWC bf16 in, fp32 accumulate in TMEM.
+//
+// Replaces the cuDNN conv2d call sites K1/K2 of SURVEY.md 2b (reference torchlayers.py:18, models/unet.py:25-29,
+// models/phiseg.py:28,32,57-58,91) and, with transposed/flipped packed weights, their dgrad.
+//
+// GEMM view: M = 128 output pixels (a TN x TH x TW box of the [N,H,W] pixel grid), N = Cout (<= 256), K = taps * Cin.
+// One K step = (tap, block of KC input channels).  For every K step the producer issues
+//   * one 4-D TMA box load of the input shifted by the tap offset -- out-of-bounds coordinates (the zero padding, and
+//     batch overhang of the last tile) are zero-filled by the TMA unit, so no halo logic exists in the kernel;
+//   * one 3-D TMA box load of the [Cout x KC] weight slice of that tap.
+// Both land in the canonical K-major swizzled layout (swizzle span = KC * 2 bytes) that tcgen05.mma reads directly.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner, warps 2..5 = epilogue.
+// Epilogue: TMEM -> registers (tcgen05.ld) -> per-channel affine (+ReLU) -> bf16 -> shared staging -> coalesced 16 B
+// stores; optionally per-tile per-channel sum / sum-of-squares of the STORED bf16 values (BatchNorm batch statistics,
+// reduced deterministically by uz_bn_finalize).
+#include "common.cuh"
+#include "unetzoo_b200.h"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct ConvParams {
+  int N, H, W, Cin, Cout;
+  int taps;           // 9 or 1
+  int TW, TH, TN;     // pixel box of one tile, TW*TH*TN == 128
+  int tilesW, tilesH; // tiles per image row / column
+  int KC;             // channels per K step (16 / 32 / 64)
+  int BN;             // output channels per CTA (multiple of 16, <= 256)
+  int stages;
+  int ldy;            // output pixel stride (elements)
+  int relu;
+  uint32_t tmem_cols;
+  __nv_bfloat16* y;
+  const float* scale;  // [Cout] or nullptr (=1)
+  const float* shift;  // [Cout] or nullptr (=0)
+  float* stats;        // [tiles][2][Cout] or nullptr
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+               const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x A][stages x B] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t swz = p.KC * 2;                    // swizzle span in bytes = one smem row
+  const uint32_t a_bytes = kBlockM * swz;
+  const uint32_t b_bytes = p.BN * swz;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + p.stages * a_bytes;
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int tile = blockIdx.x;
+  const int n_chunk = blockIdx.y;
+  const int tx = tile % p.tilesW;
+  const int ty = (tile / p.tilesW) % p.tilesH;
+  const int tn = tile / (p.tilesW * p.tilesH);
+  const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+  const int c_out0 = n_chunk * p.BN;
+
+  const int kblocks = p.Cin / p.KC;
+  const int k_iters = p.taps * kblocks;
+
+  if (warp == 0 && lane == 0) {
+    uz::tma_prefetch_desc(&tmap_x);
+    uz::tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        uz::mbar_init(&full_bar[s], 1);
+        uz::mbar_init(&empty_bar[s], 1);
+      }
+      uz::mbar_init(&accum_bar, 1);
+      uz::fence_barrier_init();
+    }
+    __syncwarp();
+    uz::tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  }
+  uz::tc_fence_before();
+  __syncthreads();
+  uz::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % p.stages;
+        if (it >= p.stages) uz::mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
+        const int tap = it / kblocks;
+        const int kb = it - tap * kblocks;
+        int dy = 0, dx = 0;
+        if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+        uz::mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+        uz::tma_load_4d(smem_a + s * a_bytes, &tmap_x, &full_bar[s], kb * p.KC, x0 + dx, y0 + dy, n0);
+        uz::tma_load_3d(smem_b + s * b_bytes, &tmap_w, &full_bar[s], kb * p.KC, c_out0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = uz::umma_idesc_bf16(kBlockM, p.BN, 0, 0);
+    const uint32_t sbo = 8 * swz;
+    for (int it = 0; it < k_iters; ++it) {
+      const int s = it % p.stages;
+      uz::mbar_wait(&full_bar[s], (it / p.stages) & 1);
+      uz::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = uz::smem_u32(smem_a + s * a_bytes);
+        const uint32_t b_addr = uz::smem_u32(smem_b + s * b_bytes);
+        for (int k = 0; k < p.KC / 16; ++k) {
+          const uint64_t adesc = uz::umma_desc(a_addr + k * 32, 16, sbo, swz);
+          const uint64_t bdesc = uz::umma_desc(b_addr + k * 32, 16, sbo, swz);
+          uz::tc_mma_f16(tmem_base, adesc, bdesc, idesc, (it | k) != 0);
+        }
+        uz::tc_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
+        if (it == k_iters - 1) uz::tc_commit(&accum_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                // tile row == output pixel index in the box
+    uz::mbar_wait(&accum_bar, 0);
+    uz::tc_fence_after();
+    // staging buffer reuses the (now idle) operand stages: 128 rows x (BN*2 + 16) bytes
+    const uint32_t pitch = p.BN * 2 + 16;
+    uint8_t* stage_out = smem;
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t r[16];
+      uz::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      uz::tmem_ld_wait();
+      uint32_t packed[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = c_out0 + c + 2 * j;
+        float v0 = __uint_as_float(r[2 * j]);
+        float v1 = __uint_as_float(r[2 * j + 1]);
+        if (p.scale) { v0 *= __ldg(p.scale + ch); v1 *= __ldg(p.scale + ch + 1); }
+        if (p.shift) { v0 += __ldg(p.shift + ch); v1 += __ldg(p.shift + ch + 1); }
+        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        packed[j] = uz::pack_bf16x2(v0, v1);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(stage_out + row * pitch + c * 2);
+      dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    }
+    uz::tc_fence_before();
+    // named barrier over the 128 epilogue threads
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+
+    const int et = threadIdx.x - 64;              // 0..127
+    const int box_px = p.TW * p.TH;
+    int valid_n = p.N - n0; if (valid_n > p.TN) valid_n = p.TN;
+    const int valid_rows = valid_n * box_px;
+
+    // coalesced store: consecutive threads write consecutive 16 B chunks of one pixel's channel vector
+    const int chunks = p.BN / 8;
+    for (int idx = et; idx < valid_rows * chunks; idx += 128) {
+      const int rrow = idx / chunks;
+      const int ck = idx - rrow * chunks;
+      const int xx = rrow % p.TW;
+      const int yy = (rrow / p.TW) % p.TH;
+      const int nn = rrow / box_px;
+      const size_t pix = (static_cast<size_t>(n0 + nn) * p.H + (y0 + yy)) * p.W + (x0 + xx);
+      const uint4 v = *reinterpret_cast<const uint4*>(stage_out + rrow * pitch + ck * 16);
+      *reinterpret_cast<uint4*>(p.y + pix * p.ldy + c_out0 + ck * 8) = v;
+    }
+    if (p.stats) {
+      // per-channel sum / sumsq over the valid rows of this tile (of the stored bf16 values)
+      for (int cp = et; cp < p.BN / 2; cp += 128) {
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        for (int rr = 0; rr < valid_rows; ++rr) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(stage_out + rr * pitch + cp * 4);
+          const float a = uz::bf16lo(v), b = uz::bf16hi(v);
+          s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+        }
+        float* dst = p.stats + static_cast<size_t>(tile) * 2 * p.Cout + c_out0 + cp * 2;
+        dst[0] = s0; dst[1] = s1;
+        dst[p.Cout] = q0; dst[p.Cout + 1] = q1;
+      }
+    }
+  }
+
+  uz::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    uz::tc_fence_after();
+    uz::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+int pow2_div_le(int v, int cap) {
+  int t = 1;
+  while (t * 2 <= cap && v % (t * 2) == 0) t *= 2;
+  return t;
+}
+
+}  // namespace
+
+extern "C" int uz_conv_tile_geometry(int N, int H, int W, int* TW, int* TH, int* TN, int* num_tiles) {
+  if (N <= 0 || H <= 0 || W <= 0) return UZ_ERR_ARG;
+  const int tw = pow2_div_le(W, 16);
+  const int th = pow2_div_le(H, kBlockM / tw);
+  const int tn = kBlockM / (tw * th);
+  if (TW) *TW = tw;
+  if (TH) *TH = th;
+  if (TN) *TN = tn;
+  if (num_tiles) *num_tiles = (W / tw) * (H / th) * ((N + tn - 1) / tn);
+  return UZ_OK;
+}
+
+extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout,
+                           int taps, void* y, int ldy, const float* scale, const float* shift, int relu,
+                           float* stats_partial, void* stream) {
+  UZ_CHECK_ARG(x && w_packed && y, "uz_conv_fwd: null pointer");
+  UZ_CHECK_ARG(taps == 9 || taps == 1, "uz_conv_fwd: taps must be 9 or 1 (got %d)", taps);
+  UZ_CHECK_ARG(Cin % 16 == 0 && Cin > 0, "uz_conv_fwd: Cin must be a positive multiple of 16 (got %d)", Cin);
+  UZ_CHECK_ARG(Cout % 16 == 0 && Cout > 0, "uz_conv_fwd: Cout must be a positive multiple of 16 (got %d)", Cout);
+  UZ_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= Cin && ldy >= Cout, "uz_conv_fwd: bad pixel strides");
+  UZ_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+               "uz_conv_fwd: pointers must be 16-byte aligned");
+  ConvParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
+  int tiles = 0;
+  uz_conv_tile_geometry(N, H, W, &p.TW, &p.TH, &p.TN, &tiles);
+  p.tilesW = W / p.TW; p.tilesH = H / p.TH;
+  p.KC = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
+  // output-channel split: one CTA covers all of Cout unless Cout > 256 or the grid would leave SMs idle
+  int bn = Cout;
+  int splits = 1;
+  while (bn > 256 || (tiles * splits < uz::num_sms() && bn % 32 == 0 && bn >= 64)) {
+    if (bn % 32 != 0) break;
+    bn /= 2; splits *= 2;
+  }
+  UZ_CHECK_ARG(bn <= 256 && bn % 16 == 0, "uz_conv_fwd: unsupported Cout %d", Cout);
+  p.BN = bn;
+  p.ldy = ldy; p.relu = relu;
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.scale = scale; p.shift = shift; p.stats = stats_partial;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(bn)) cols *= 2;
+  p.tmem_cols = cols;
+  const uint32_t swz = p.KC * 2;
+  const size_t stage_bytes = static_cast<size_t>(kBlockM + bn) * swz;
+  const size_t out_bytes = static_cast<size_t>(kBlockM) * (bn * 2 + 16);
+  const int k_iters = taps * (Cin / p.KC);
+  int stages = static_cast<int>((196 * 1024) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > k_iters) stages = k_iters;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  size_t smem = stages * stage_bytes;
+  if (smem < out_bytes) smem = out_bytes;
+  smem += 1024;  // alignment slack
+
+  CUtensorMap tx, tw;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(W) * ldx * 2,
+                           static_cast<uint64_t>(H) * W * ldx * 2};
+    uint32_t box[4] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TH),
+                       static_cast<uint32_t>(p.TN)};
+    int rc = uz::make_tmap_bf16(&tx, x, 4, dims, strides, box, swz);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Cout), static_cast<uint64_t>(taps)};
+    uint64_t strides[2] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Cout) * Cin * 2};
+    uint32_t box[3] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(bn), 1};
+    int rc = uz::make_tmap_bf16(&tw, w_packed, 3, dims, strides, box, swz);
+    if (rc) return rc;
+  }
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      uz::set_error("uz_conv_fwd: cannot raise dynamic smem limit to %zu: %s", static_cast<size_t>(smem), cudaGetErrorString(e));
+      return UZ_ERR_CUDA;
+    }
+    attr_bytes = smem;
+  }
+  dim3 grid(tiles, splits, 1);
+  conv_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+  UZ_CHECK_LAUNCH("uz_conv_fwd");
+  return UZ_OK;
+}

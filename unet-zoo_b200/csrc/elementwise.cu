@@ -1,0 +1,616 @@
+// Memory-bound NHWC bf16 kernels around the tensor-core convolutions: weight packing, BatchNorm statistics
+// finalisation / apply / backward, 2x2 average pooling, bilinear x2 upsampling (align_corners True and False) written
+// straight into channel slices of concat buffers, strided channel copies, input packing with one-hot conditioning.
+//
+// All activations are [pixels][channels] with a pixel stride `ld` (elements, multiple of 8) so producers can write into
+// and consumers can read from channel slices of wider (concat) buffers without copies.  Every thread moves 16-byte
+// vectors (8 bf16 channels); consecutive threads touch consecutive 16-byte chunks of a pixel => fully coalesced.
+#include "common.cuh"
+#include "unetzoo_b200.h"
+
+namespace {
+
+constexpr int kEwThreads = 256;
+
+inline int ew_blocks(size_t work, int per_block = kEwThreads) {
+  size_t b = (work + per_block - 1) / per_block;
+  size_t cap = static_cast<size_t>(uz::num_sms()) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = uz::bf16lo(v.x); f[1] = uz::bf16hi(v.x); f[2] = uz::bf16lo(v.y); f[3] = uz::bf16hi(v.y);
+  f[4] = uz::bf16lo(v.z); f[5] = uz::bf16hi(v.z); f[6] = uz::bf16lo(v.w); f[7] = uz::bf16hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(uz::pack_bf16x2(f[0], f[1]), uz::pack_bf16x2(f[2], f[3]), uz::pack_bf16x2(f[4], f[5]),
+                    uz::pack_bf16x2(f[6], f[7]));
+}
+
+// ---------------------------------------------------------------- weight packing
+// w fp32 [Cout][Cin][taps] (PyTorch OIHW flattened over kh,kw) ->
+//   fwd : bf16 [taps][CoutP][CinP]            wp[t][o][i]  = w[o][i][t]
+//   dgrad: bf16 [taps][CinP2][CoutP2]         wd[t][i][o]  = w[o][i][taps-1-t]   (flipped taps, transposed channels)
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, __nv_bfloat16* wp,
+                                   int CoutP, int CinP, __nv_bfloat16* wd, int CinP2, int CoutP2) {
+  const size_t n_fwd = static_cast<size_t>(taps) * CoutP * CinP;
+  const size_t n_bwd = wd ? static_cast<size_t>(taps) * CinP2 * CoutP2 : 0;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n_fwd + n_bwd;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    if (idx < n_fwd) {
+      const int i = idx % CinP;
+      const int o = (idx / CinP) % CoutP;
+      const int t = idx / (static_cast<size_t>(CinP) * CoutP);
+      float v = (i < Cin && o < Cout) ? w[(static_cast<size_t>(o) * Cin + i) * taps + t] : 0.f;
+      wp[idx] = __float2bfloat16(v);
+    } else {
+      const size_t j = idx - n_fwd;
+      const int o = j % CoutP2;
+      const int i = (j / CoutP2) % CinP2;
+      const int t = j / (static_cast<size_t>(CoutP2) * CinP2);
+      float v = (i < Cin && o < Cout) ? w[(static_cast<size_t>(o) * Cin + i) * taps + (taps - 1 - t)] : 0.f;
+      wd[j] = __float2bfloat16(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- BatchNorm statistics
+// partial [tiles][2][C] (sum, sumsq per tile, written by the conv epilogue) -> per-channel scale/shift, saved
+// mean/invstd, running-stat update (momentum, unbiased variance) -- reference torchlayers.py:20, SURVEY Appendix A.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int tiles, int C, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                                   float* mean_out, float* invstd_out) {
+  // one warp per channel; lanes stride over tiles; fixed order => deterministic
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int t = lane; t < tiles; t += 32) {
+    s += static_cast<double>(partial[(static_cast<size_t>(t) * 2) * C + warp]);
+    q += static_cast<double>(partial[(static_cast<size_t>(t) * 2 + 1) * C + warp]);
+  }
+  s = uz::warp_sum_d(s);
+  q = uz::warp_sum_d(q);
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float g = gamma ? gamma[warp] : 1.f;
+    const float b = beta ? beta[warp] : 0.f;
+    const float sc = g * invstd;
+    scale[warp] = sc;
+    shift[warp] = b - static_cast<float>(mean) * sc;
+    if (mean_out) mean_out[warp] = static_cast<float>(mean);
+    if (invstd_out) invstd_out[warp] = invstd;
+    if (running_mean) {
+      const double unbiased = count > 1.f ? var * count / (count - 1.0) : var;
+      running_mean[warp] = (1.f - momentum) * running_mean[warp] + momentum * static_cast<float>(mean);
+      running_var[warp] = (1.f - momentum) * running_var[warp] + momentum * static_cast<float>(unbiased);
+    }
+  }
+}
+
+// eval-mode fold: y = relu(conv*scale + shift) with running statistics (train_model.py:139 net.eval()).
+__global__ void bn_eval_fold_kernel(const float* __restrict__ conv_bias, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ rm,
+                                    const float* __restrict__ rv, float eps, int C, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = (gamma ? gamma[c] : 1.f) * rsqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
+}
+
+// out = act(y * scale[c] + shift[c])
+__global__ void affine_act_kernel(const __nv_bfloat16* __restrict__ y, int ldy, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, int relu, __nv_bfloat16* out, int ldo, size_t npix,
+                                  int C) {
+  const int chunks = C / 8;
+  const size_t total = npix * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = idx / chunks;
+    const int c0 = static_cast<int>(idx - pix * chunks) * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(y + pix * ldy + c0);
+    float f[8];
+    unpack8(v, f);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (relu) f[j] = fmaxf(f[j], 0.f);
+    }
+    *reinterpret_cast<uint4*>(out + pix * ldo + c0) = pack8(f);
+  }
+}
+
+// BN+ReLU backward, pass 1: per-channel sum(g) and sum(g * y) with g = dout * [y*scale+shift > 0]; partial per block.
+// block = (C/8 channel chunks) x rows; grid-stride over pixel rows; block result -> partial[block][2][C].
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, const __nv_bfloat16* __restrict__ y,
+                                     int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
+                                     int relu, size_t npix, int C, float* partial) {
+  extern __shared__ float red[];  // [rows][2][C]
+  const int chunks = C / 8;
+  const int rows = blockDim.x / chunks;
+  const int r = threadIdx.x / chunks;
+  const int c0 = (threadIdx.x - r * chunks) * 8;
+  float sg[8], sgy[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sgy[j] = 0.f; }
+  if (r < rows) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+    for (size_t pix = static_cast<size_t>(blockIdx.x) * rows + r; pix < npix;
+         pix += static_cast<size_t>(gridDim.x) * rows) {
+      float g[8], yy[8];
+      unpack8(*reinterpret_cast<const uint4*>(dout + pix * ldd + c0), g);
+      unpack8(*reinterpret_cast<const uint4*>(y + pix * ldy + c0), yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float m = (!relu || fmaf(yy[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
+        sg[j] += m;
+        sgy[j] = fmaf(m, yy[j], sgy[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[(r * 2) * C + c0 + j] = sg[j];
+      red[(r * 2 + 1) * C + c0 + j] = sgy[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int rr = 0; rr < rows; ++rr) acc += red[rr * 2 * C + i];
+    partial[static_cast<size_t>(blockIdx.x) * 2 * C + i] = acc;
+  }
+}
+
+// pass 1b: reduce partials -> coefficients of dy = A*g + B*y + Cc, plus dgamma/dbeta (fp32, PyTorch grad layout).
+//   xhat = (y - mean) * invstd ; dgamma = sum(g*xhat) ; dbeta = sum(g)
+//   dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat))
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, float count,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, float* coefA, float* coefB, float* coefC,
+                                       float* dgamma, float* dbeta) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= C) return;
+  double sg = 0.0, sgy = 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
+    sg += static_cast<double>(partial[static_cast<size_t>(b) * 2 * C + warp]);
+    sgy += static_cast<double>(partial[static_cast<size_t>(b) * 2 * C + C + warp]);
+  }
+  sg = uz::warp_sum_d(sg);
+  sgy = uz::warp_sum_d(sgy);
+  if (lane == 0) {
+    const double mu = mean[warp], is = invstd[warp], g = gamma ? gamma[warp] : 1.0;
+    const double sgx = (sgy - mu * sg) * is;  // sum g*xhat
+    const double mg = sg / count, mgx = sgx / count;
+    coefA[warp] = static_cast<float>(g * is);
+    coefB[warp] = static_cast<float>(-g * is * is * mgx);
+    coefC[warp] = static_cast<float>(-g * is * mg + g * is * is * mgx * mu);
+    if (dgamma) dgamma[warp] = static_cast<float>(sgx);
+    if (dbeta) dbeta[warp] = static_cast<float>(sg);
+  }
+}
+
+// pass 2: dy = A*g + B*y + Cc   (A,B,Cc may be null => plain ReLU backward dy = g)
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, const __nv_bfloat16* __restrict__ y,
+                                    int ldy, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                    const float* __restrict__ coefA, const float* __restrict__ coefB,
+                                    const float* __restrict__ coefC, __nv_bfloat16* dy, int lddy, size_t npix, int C) {
+  const int chunks = C / 8;
+  const size_t total = npix * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = idx / chunks;
+    const int c0 = static_cast<int>(idx - pix * chunks) * 8;
+    float g[8], yy[8];
+    unpack8(*reinterpret_cast<const uint4*>(dout + pix * ldd + c0), g);
+    unpack8(*reinterpret_cast<const uint4*>(y + pix * ldy + c0), yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float m = (!relu || fmaf(yy[j], scale[c], shift[c]) > 0.f) ? g[j] : 0.f;
+      g[j] = coefA ? fmaf(coefA[c], m, fmaf(coefB[c], yy[j], coefC[c])) : m;
+    }
+    *reinterpret_cast<uint4*>(dy + pix * lddy + c0) = pack8(g);
+  }
+}
+
+// ---------------------------------------------------------------- 2x2 average pooling (AvgPool2d(2,2,ceil_mode), even sizes)
+__global__ void avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* out, int ldo, int N,
+                                    int Ho, int Wo, int C) {
+  const int chunks = C / 8;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * chunks;
+  const int W = Wo * 2;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(idx % chunks) * 8;
+    const size_t opix = idx / chunks;
+    const int xo = opix % Wo;
+    const int yo = (opix / Wo) % Ho;
+    const size_t n = opix / (static_cast<size_t>(Wo) * Ho);
+    const size_t ipix = (n * (Ho * 2) + yo * 2) * W + xo * 2;
+    float a[8], b[8], c[8], d[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + ipix * ldx + c0), a);
+    unpack8(*reinterpret_cast<const uint4*>(x + (ipix + 1) * ldx + c0), b);
+    unpack8(*reinterpret_cast<const uint4*>(x + (ipix + W) * ldx + c0), c);
+    unpack8(*reinterpret_cast<const uint4*>(x + (ipix + W + 1) * ldx + c0), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.25f * ((a[j] + b[j]) + (c[j] + d[j]));
+    *reinterpret_cast<uint4*>(out + opix * ldo + c0) = pack8(a);
+  }
+}
+
+// dx[n, y, x, c] = 0.25 * dout[n, y/2, x/2, c]  (optionally accumulating into dx: the pooled tensor's source may also
+// feed a skip connection whose gradient is already in dx)
+__global__ void avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, __nv_bfloat16* dx, int ldx, int N,
+                                    int Ho, int Wo, int C, int accumulate) {
+  const int chunks = C / 8;
+  const int H = Ho * 2, W = Wo * 2;
+  const size_t total = static_cast<size_t>(N) * H * W * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(idx % chunks) * 8;
+    const size_t ipix = idx / chunks;
+    const int xi = ipix % W;
+    const int yi = (ipix / W) % H;
+    const size_t n = ipix / (static_cast<size_t>(W) * H);
+    const size_t opix = (n * Ho + yi / 2) * Wo + xi / 2;
+    float g[8];
+    unpack8(*reinterpret_cast<const uint4*>(dout + opix * ldd + c0), g);
+    if (accumulate) {
+      float o[8];
+      unpack8(*reinterpret_cast<const uint4*>(dx + ipix * ldx + c0), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = fmaf(0.25f, g[j], o[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
+    }
+    *reinterpret_cast<uint4*>(dx + ipix * ldx + c0) = pack8(g);
+  }
+}
+
+// ---------------------------------------------------------------- bilinear x2
+// align_corners=True : src = dst * (in-1)/(out-1)              (reference models/phiseg.py:66,213-216,305-309)
+// align_corners=False: src = max((dst+0.5)/2 - 0.5, 0)         (reference models/unet.py:67)
+__device__ __forceinline__ void up2_src(int o, int in, int align, int& i0, int& i1, float& w1) {
+  float s;
+  if (align) {
+    s = in > 1 ? o * (static_cast<float>(in - 1) / static_cast<float>(2 * in - 1)) : 0.f;
+  } else {
+    s = fmaxf((o + 0.5f) * 0.5f - 0.5f, 0.f);
+  }
+  i0 = static_cast<int>(s);
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  w1 = s - i0;
+}
+
+__global__ void up2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* out, int ldo, int N, int h,
+                               int w, int C, int align) {
+  const int chunks = C / 8;
+  const int H = 2 * h, W = 2 * w;
+  const size_t total = static_cast<size_t>(N) * H * W * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(idx % chunks) * 8;
+    const size_t opix = idx / chunks;
+    const int xo = opix % W;
+    const int yo = (opix / W) % H;
+    const size_t n = opix / (static_cast<size_t>(W) * H);
+    int x0, x1, y0, y1;
+    float wx, wy;
+    up2_src(xo, w, align, x0, x1, wx);
+    up2_src(yo, h, align, y0, y1, wy);
+    const size_t base = n * h * w;
+    float a[8], b[8], c[8], d[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + (base + static_cast<size_t>(y0) * w + x0) * ldx + c0), a);
+    unpack8(*reinterpret_cast<const uint4*>(x + (base + static_cast<size_t>(y0) * w + x1) * ldx + c0), b);
+    unpack8(*reinterpret_cast<const uint4*>(x + (base + static_cast<size_t>(y1) * w + x0) * ldx + c0), c);
+    unpack8(*reinterpret_cast<const uint4*>(x + (base + static_cast<size_t>(y1) * w + x1) * ldx + c0), d);
+    const float w00 = (1.f - wy) * (1.f - wx), w01 = (1.f - wy) * wx, w10 = wy * (1.f - wx), w11 = wy * wx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = w00 * a[j] + w01 * b[j] + w10 * c[j] + w11 * d[j];
+    *reinterpret_cast<uint4*>(out + opix * ldo + c0) = pack8(a);
+  }
+}
+
+// gather form of the transpose: every input pixel collects from the output pixels that read it
+__global__ void up2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, __nv_bfloat16* dx, int ldx, int N, int h,
+                               int w, int C, int align) {
+  const int chunks = C / 8;
+  const int H = 2 * h, W = 2 * w;
+  const size_t total = static_cast<size_t>(N) * h * w * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(idx % chunks) * 8;
+    const size_t ipix = idx / chunks;
+    const int xi = ipix % w;
+    const int yi = (ipix / w) % h;
+    const size_t n = ipix / (static_cast<size_t>(w) * h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int ylo = max(2 * yi - 2, 0), yhi = min(2 * yi + 3, H - 1);
+    const int xlo = max(2 * xi - 2, 0), xhi = min(2 * xi + 3, W - 1);
+    for (int yo = ylo; yo <= yhi; ++yo) {
+      int y0, y1; float wy;
+      up2_src(yo, h, align, y0, y1, wy);
+      float cy = 0.f;
+      if (y0 == yi) cy += 1.f - wy;
+      if (y1 == yi) cy += wy;
+      if (cy == 0.f) continue;
+      for (int xo = xlo; xo <= xhi; ++xo) {
+        int x0, x1; float wx;
+        up2_src(xo, w, align, x0, x1, wx);
+        float cx = 0.f;
+        if (x0 == xi) cx += 1.f - wx;
+        if (x1 == xi) cx += wx;
+        if (cx == 0.f) continue;
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(dout + ((n * H + yo) * W + xo) * ldd + c0), g);
+        const float cw = cy * cx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(cw, g[j], acc[j]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + ipix * ldx + c0) = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------- strided channel copy / add (concat, split, grad sum)
+__global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int lds, __nv_bfloat16* dst, int ldd,
+                                     size_t npix, int C, int accumulate) {
+  const int chunks = C / 8;
+  const size_t total = npix * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = idx / chunks;
+    const int c0 = static_cast<int>(idx - pix * chunks) * 8;
+    uint4 v = *reinterpret_cast<const uint4*>(src + pix * lds + c0);
+    if (accumulate) {
+      float a[8], b[8];
+      unpack8(v, a);
+      unpack8(*reinterpret_cast<const uint4*>(dst + pix * ldd + c0), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += b[j];
+      v = pack8(a);
+    }
+    *reinterpret_cast<uint4*>(dst + pix * ldd + c0) = v;
+  }
+}
+
+// ---------------------------------------------------------------- input packing
+// patch fp32 NCHW [B,Cimg,H,W] (+ mask float [B,1,H,W] holding integer labels) -> bf16 NHWC [B,H,W,CP]:
+//   channels [0,Cimg) image, [Cimg, Cimg+nlabels) = (mask==k) - 0.5 (reference models/phiseg.py:176-183,
+//   utils.py:289-311), rest zero.
+__global__ void input_pack_kernel(const float* __restrict__ patch, const float* __restrict__ mask, int B, int Cimg,
+                                  int H, int W, int nlabels, __nv_bfloat16* out, int CP) {
+  const size_t hw = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * hw;
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = pix / hw, r = pix - b * hw;
+    __nv_bfloat16* o = out + pix * CP;
+    int c = 0;
+    for (; c < Cimg; ++c) o[c] = __float2bfloat16(patch[(b * Cimg + c) * hw + r]);
+    if (mask) {
+      const float m = mask[b * hw + r];
+      for (int k = 0; k < nlabels; ++k, ++c) o[c] = __float2bfloat16((m == static_cast<float>(k) ? 1.f : 0.f) - 0.5f);
+    }
+    for (; c < CP; ++c) o[c] = __float2bfloat16(0.f);
+  }
+}
+
+// fp32 NCHW <-> bf16 NHWC (module-boundary conversions; channel padding zero-filled)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int B, int C, size_t hw, __nv_bfloat16* dst, int ld) {
+  const size_t total = static_cast<size_t>(B) * hw * ld;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = idx % ld;
+    const size_t pix = idx / ld;
+    const size_t b = pix / hw, r = pix - b * hw;
+    dst[idx] = __float2bfloat16(c < C ? src[(b * C + c) * hw + r] : 0.f);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int ld, int B, int C, size_t hw, float* dst) {
+  const size_t total = static_cast<size_t>(B) * C * hw;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = idx % hw;
+    const int c = (idx / hw) % C;
+    const size_t b = idx / (hw * C);
+    dst[idx] = __bfloat162float(src[(b * hw + r) * ld + c]);
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int uz_pack_conv_weight(const float* w, int Cout, int Cin, int taps, void* w_fwd, int CoutP, int CinP,
+                                   void* w_dgrad, int CinP2, int CoutP2, void* stream) {
+  UZ_CHECK_ARG(w && w_fwd, "uz_pack_conv_weight: null pointer");
+  UZ_CHECK_ARG(CoutP >= Cout && CinP >= Cin, "uz_pack_conv_weight: padded dims smaller than logical dims");
+  UZ_CHECK_ARG(!w_dgrad || (CinP2 >= Cin && CoutP2 >= Cout), "uz_pack_conv_weight: bad dgrad dims");
+  const size_t n = static_cast<size_t>(taps) * CoutP * CinP + (w_dgrad ? static_cast<size_t>(taps) * CinP2 * CoutP2 : 0);
+  pack_weight_kernel<<<ew_blocks(n), kEwThreads, 0, ST(stream)>>>(w, Cout, Cin, taps, static_cast<__nv_bfloat16*>(w_fwd),
+                                                                 CoutP, CinP, static_cast<__nv_bfloat16*>(w_dgrad),
+                                                                 CinP2, CoutP2);
+  UZ_CHECK_LAUNCH("uz_pack_conv_weight");
+  return UZ_OK;
+}
+
+extern "C" int uz_bn_finalize(const float* partial, int tiles, int C, float count, const float* gamma,
+                              const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                              float* scale, float* shift, float* mean_out, float* invstd_out, void* stream) {
+  UZ_CHECK_ARG(partial && scale && shift && tiles > 0 && C > 0, "uz_bn_finalize: bad arguments");
+  const int threads = 256;
+  const int blocks = (C * 32 + threads - 1) / threads;
+  bn_finalize_kernel<<<blocks, threads, 0, ST(stream)>>>(partial, tiles, C, count, gamma, beta, eps, momentum,
+                                                         running_mean, running_var, scale, shift, mean_out, invstd_out);
+  UZ_CHECK_LAUNCH("uz_bn_finalize");
+  return UZ_OK;
+}
+
+extern "C" int uz_bn_eval_fold(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
+                               const float* running_var, float eps, int C, float* scale, float* shift, void* stream) {
+  UZ_CHECK_ARG(running_mean && running_var && scale && shift && C > 0, "uz_bn_eval_fold: bad arguments");
+  bn_eval_fold_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(conv_bias, gamma, beta, running_mean, running_var, eps, C,
+                                                              scale, shift);
+  UZ_CHECK_LAUNCH("uz_bn_eval_fold");
+  return UZ_OK;
+}
+
+extern "C" int uz_affine_act(const void* y, int ldy, const float* scale, const float* shift, int relu, void* out,
+                             int ldo, long long npix, int C, void* stream) {
+  UZ_CHECK_ARG(y && out && scale && shift, "uz_affine_act: null pointer");
+  UZ_CHECK_ARG(C % 8 == 0 && ldy % 8 == 0 && ldo % 8 == 0 && aligned16(y) && aligned16(out), "uz_affine_act: alignment");
+  if (npix == 0) return UZ_OK;
+  affine_act_kernel<<<ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), ldy, scale, shift, relu, static_cast<__nv_bfloat16*>(out), ldo,
+      static_cast<size_t>(npix), C);
+  UZ_CHECK_LAUNCH("uz_affine_act");
+  return UZ_OK;
+}
+
+extern "C" int uz_bn_bwd_num_blocks(long long npix, int C) {
+  const int chunks = C / 8;
+  int threads = 256;
+  if (chunks > threads) threads = ((chunks + 31) / 32) * 32;
+  const int rows = threads / chunks;
+  long long b = (npix + rows - 1) / rows;
+  const long long cap = static_cast<long long>(uz::num_sms()) * 4;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+extern "C" int uz_bn_bwd_reduce(const void* dout, int ldd, const void* y, int ldy, const float* scale,
+                                const float* shift, int relu, long long npix, int C, float* partial, void* stream) {
+  UZ_CHECK_ARG(dout && y && scale && shift && partial, "uz_bn_bwd_reduce: null pointer");
+  UZ_CHECK_ARG(C % 8 == 0 && ldd % 8 == 0 && ldy % 8 == 0, "uz_bn_bwd_reduce: alignment");
+  const int chunks = C / 8;
+  int threads = 256;
+  if (chunks > threads) threads = ((chunks + 31) / 32) * 32;
+  const int rows = threads / chunks;
+  const int blocks = uz_bn_bwd_num_blocks(npix, C);
+  const size_t smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);
+  bn_bwd_reduce_kernel<<<blocks, threads, smem, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dout), ldd,
+                                                             static_cast<const __nv_bfloat16*>(y), ldy, scale, shift,
+                                                             relu, static_cast<size_t>(npix), C, partial);
+  UZ_CHECK_LAUNCH("uz_bn_bwd_reduce");
+  return UZ_OK;
+}
+
+extern "C" int uz_bn_bwd_finalize(const float* partial, int nblocks, int C, float count, const float* gamma,
+                                  const float* mean, const float* invstd, float* coefA, float* coefB, float* coefC,
+                                  float* dgamma, float* dbeta, void* stream) {
+  UZ_CHECK_ARG(partial && mean && invstd && coefA && coefB && coefC, "uz_bn_bwd_finalize: null pointer");
+  const int threads = 256;
+  const int blocks = (C * 32 + threads - 1) / threads;
+  bn_bwd_finalize_kernel<<<blocks, threads, 0, ST(stream)>>>(partial, nblocks, C, count, gamma, mean, invstd, coefA,
+                                                             coefB, coefC, dgamma, dbeta);
+  UZ_CHECK_LAUNCH("uz_bn_bwd_finalize");
+  return UZ_OK;
+}
+
+extern "C" int uz_bn_bwd_apply(const void* dout, int ldd, const void* y, int ldy, const float* scale,
+                               const float* shift, int relu, const float* coefA, const float* coefB,
+                               const float* coefC, void* dy, int lddy, long long npix, int C, void* stream) {
+  UZ_CHECK_ARG(dout && y && dy && scale && shift, "uz_bn_bwd_apply: null pointer");
+  UZ_CHECK_ARG(C % 8 == 0 && ldd % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0, "uz_bn_bwd_apply: alignment");
+  if (npix == 0) return UZ_OK;
+  bn_bwd_apply_kernel<<<ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dout), ldd, static_cast<const __nv_bfloat16*>(y), ldy, scale, shift, relu, coefA,
+      coefB, coefC, static_cast<__nv_bfloat16*>(dy), lddy, static_cast<size_t>(npix), C);
+  UZ_CHECK_LAUNCH("uz_bn_bwd_apply");
+  return UZ_OK;
+}
+
+extern "C" int uz_avgpool2_fwd(const void* x, int ldx, void* out, int ldo, int N, int Ho, int Wo, int C, void* stream) {
+  UZ_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "uz_avgpool2_fwd: bad arguments");
+  avgpool2_fwd_kernel<<<ew_blocks(static_cast<size_t>(N) * Ho * Wo * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, N, Ho, Wo, C);
+  UZ_CHECK_LAUNCH("uz_avgpool2_fwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_avgpool2_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int Ho, int Wo, int C,
+                               int accumulate, void* stream) {
+  UZ_CHECK_ARG(dout && dx && C % 8 == 0 && ldx % 8 == 0 && ldd % 8 == 0, "uz_avgpool2_bwd: bad arguments");
+  avgpool2_bwd_kernel<<<ew_blocks(static_cast<size_t>(N) * Ho * Wo * 4 * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dout), ldd, static_cast<__nv_bfloat16*>(dx), ldx, N, Ho, Wo, C, accumulate);
+  UZ_CHECK_LAUNCH("uz_avgpool2_bwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_upsample2x_fwd(const void* x, int ldx, void* out, int ldo, int N, int h, int w, int C,
+                                 int align_corners, void* stream) {
+  UZ_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "uz_upsample2x_fwd: bad arguments");
+  up2_fwd_kernel<<<ew_blocks(static_cast<size_t>(N) * h * w * 4 * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, N, h, w, C, align_corners);
+  UZ_CHECK_LAUNCH("uz_upsample2x_fwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_upsample2x_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int h, int w, int C,
+                                 int align_corners, void* stream) {
+  UZ_CHECK_ARG(dout && dx && C % 8 == 0 && ldx % 8 == 0 && ldd % 8 == 0, "uz_upsample2x_bwd: bad arguments");
+  up2_bwd_kernel<<<ew_blocks(static_cast<size_t>(N) * h * w * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dout), ldd, static_cast<__nv_bfloat16*>(dx), ldx, N, h, w, C, align_corners);
+  UZ_CHECK_LAUNCH("uz_upsample2x_bwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_copy_channels(const void* src, int lds, void* dst, int ldd, long long npix, int C, int accumulate,
+                                void* stream) {
+  UZ_CHECK_ARG(src && dst && C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && aligned16(src) && aligned16(dst),
+               "uz_copy_channels: bad arguments");
+  if (npix == 0) return UZ_OK;
+  copy_channels_kernel<<<ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, static_cast<size_t>(npix), C,
+      accumulate);
+  UZ_CHECK_LAUNCH("uz_copy_channels");
+  return UZ_OK;
+}
+
+extern "C" int uz_input_pack(const float* patch, const float* mask, int B, int Cimg, int H, int W, int nlabels,
+                             void* out, int CP, void* stream) {
+  UZ_CHECK_ARG(patch && out, "uz_input_pack: null pointer");
+  UZ_CHECK_ARG(CP % 8 == 0 && CP >= Cimg + (mask ? nlabels : 0), "uz_input_pack: CP=%d too small", CP);
+  input_pack_kernel<<<ew_blocks(static_cast<size_t>(B) * H * W), kEwThreads, 0, ST(stream)>>>(
+      patch, mask, B, Cimg, H, W, nlabels, static_cast<__nv_bfloat16*>(out), CP);
+  UZ_CHECK_LAUNCH("uz_input_pack");
+  return UZ_OK;
+}
+
+extern "C" int uz_nchw_to_nhwc(const float* src, int B, int C, long long hw, void* dst, int ld, void* stream) {
+  UZ_CHECK_ARG(src && dst && ld >= C, "uz_nchw_to_nhwc: bad arguments");
+  nchw_to_nhwc_kernel<<<ew_blocks(static_cast<size_t>(B) * hw * ld), kEwThreads, 0, ST(stream)>>>(
+      src, B, C, static_cast<size_t>(hw), static_cast<__nv_bfloat16*>(dst), ld);
+  UZ_CHECK_LAUNCH("uz_nchw_to_nhwc");
+  return UZ_OK;
+}
+
+extern "C" int uz_nhwc_to_nchw(const void* src, int ld, int B, int C, long long hw, float* dst, void* stream) {
+  UZ_CHECK_ARG(src && dst && ld >= C, "uz_nhwc_to_nchw: bad arguments");
+  nhwc_to_nchw_kernel<<<ew_blocks(static_cast<size_t>(B) * C * hw), kEwThreads, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), ld, B, C, static_cast<size_t>(hw), dst);
+  UZ_CHECK_LAUNCH("uz_nhwc_to_nchw");
+  return UZ_OK;
+}

@@ -1,0 +1,530 @@
+// Latent heads and losses of PHiSeg / ProbUNet (fp32 arithmetic, memory-bound):
+//   * SampleZBlock head: mu = 1x1 conv, sigma = softplus(1x1 conv), z = mu + sigma * eps  (models/phiseg.py:95-106)
+//   * KL_two_gauss_with_diag_cov with the sigma1*sigma0 quirk                              (models/phiseg.py:436-453)
+//   * s_layer 1x1 conv to class logits + nearest upsample to full resolution             (models/phiseg.py:283-284,319-321)
+//   * residual multinoulli (softmax cross-entropy) loss over the level sums               (models/phiseg.py:481-513)
+//   * accumulate_output (+softmax)                                                         (models/phiseg.py:428-434)
+// Features arrive as NHWC bf16; everything the caller can see (mu, sigma, z, logits) is fp32 NCHW like the reference.
+#include "common.cuh"
+#include "unetzoo_b200.h"
+
+namespace {
+
+constexpr int kMaxCls = 8;   // n_classes (2 for LIDC, 3 for UZH/BraTS)
+constexpr int kMaxLvl = 8;   // latent levels (5)
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+// ---------------------------------------------------------------- head forward
+// one warp per pixel: lanes stride over channels (bf16x2 loads), 2*Z dot products reduced with shuffles.
+template <int Z>
+__global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ wmu,
+                                const float* __restrict__ bmu, const float* __restrict__ wsig,
+                                const float* __restrict__ bsig, const float* __restrict__ eps, int B, int hw, float* mu,
+                                float* sigma, float* z) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int npix = B * hw;
+  if (warp >= npix) return;
+  float am[Z], as[Z];
+#pragma unroll
+  for (int k = 0; k < Z; ++k) { am[k] = 0.f; as[k] = 0.f; }
+  const __nv_bfloat16* f = feat + static_cast<size_t>(warp) * ld;
+  for (int c = lane * 2; c < C; c += 64) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(f + c);
+    const float f0 = uz::bf16lo(v), f1 = uz::bf16hi(v);
+#pragma unroll
+    for (int k = 0; k < Z; ++k) {
+      am[k] = fmaf(f0, wmu[k * C + c], fmaf(f1, wmu[k * C + c + 1], am[k]));
+      as[k] = fmaf(f0, wsig[k * C + c], fmaf(f1, wsig[k * C + c + 1], as[k]));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < Z; ++k) { am[k] = uz::warp_sum(am[k]); as[k] = uz::warp_sum(as[k]); }
+  if (lane == 0) {
+    const int b = warp / hw, r = warp - b * hw;
+#pragma unroll
+    for (int k = 0; k < Z; ++k) {
+      const size_t o = (static_cast<size_t>(b) * Z + k) * hw + r;
+      const float m = am[k] + bmu[k];
+      const float s = softplus_f(as[k] + bsig[k]);
+      const float zz = fmaf(s, eps[o], m);
+      mu[o] = m; sigma[o] = s; z[o] = zz;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- head backward
+// Inputs: upstream grads of mu, sigma, z (fp32 NCHW, any may be null).  dz folds into dmu/dsigma:
+//   dmu_t = dmu + dz ; dsig_t = dsigma + dz*eps ; dpre = dsig_t * sigmoid(pre) where sigma = softplus(pre).
+// Since sigma is saved (not pre): sigmoid(pre) = 1 - exp(-sigma) for pre <= 20, 1 otherwise (sigma = pre > 20).
+// Outputs: dfeat bf16 NHWC [npix][C]; per-block partial weight/bias grads reduced by head_bwd_wreduce_kernel.
+template <int Z>
+__global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ wmu,
+                                const float* __restrict__ wsig, const float* __restrict__ eps,
+                                const float* __restrict__ sigma, const float* __restrict__ dmu,
+                                const float* __restrict__ dsigma, const float* __restrict__ dz, int B, int hw,
+                                __nv_bfloat16* dfeat, int ldd, float* wpartial /*[blocks][2Z][C]*/,
+                                float* bpartial /*[blocks][2Z]*/) {
+  extern __shared__ float sm[];  // [warps][2Z][C] accumulators for weight grads
+  const int warps = blockDim.x >> 5;
+  const int wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float* acc = sm + static_cast<size_t>(wid) * 2 * Z * C;
+  for (int i = lane; i < 2 * Z * C; i += 32) acc[i] = 0.f;
+  float bacc[2 * Z];
+#pragma unroll
+  for (int k = 0; k < 2 * Z; ++k) bacc[k] = 0.f;
+  __syncwarp();
+  const int npix = B * hw;
+  for (int pix = blockIdx.x * warps + wid; pix < npix; pix += gridDim.x * warps) {
+    const int b = pix / hw, r = pix - b * hw;
+    float gm[Z], gs[Z];
+#pragma unroll
+    for (int k = 0; k < Z; ++k) {
+      const size_t o = (static_cast<size_t>(b) * Z + k) * hw + r;
+      const float gz = dz ? dz[o] : 0.f;
+      const float s = sigma[o];
+      gm[k] = (dmu ? dmu[o] : 0.f) + gz;
+      const float gsig = (dsigma ? dsigma[o] : 0.f) + gz * eps[o];
+      const float dsp = s > 20.f ? 1.f : (1.f - expf(-s));
+      gs[k] = gsig * dsp;
+      bacc[k] += gm[k];
+      bacc[Z + k] += gs[k];
+    }
+    const __nv_bfloat16* f = feat + static_cast<size_t>(pix) * ld;
+    __nv_bfloat16* df = dfeat + static_cast<size_t>(pix) * ldd;
+    for (int c = lane * 2; c < C; c += 64) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(f + c);
+      const float f0 = uz::bf16lo(v), f1 = uz::bf16hi(v);
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < Z; ++k) {
+        d0 = fmaf(gm[k], wmu[k * C + c], fmaf(gs[k], wsig[k * C + c], d0));
+        d1 = fmaf(gm[k], wmu[k * C + c + 1], fmaf(gs[k], wsig[k * C + c + 1], d1));
+        acc[k * C + c] = fmaf(gm[k], f0, acc[k * C + c]);
+        acc[k * C + c + 1] = fmaf(gm[k], f1, acc[k * C + c + 1]);
+        acc[(Z + k) * C + c] = fmaf(gs[k], f0, acc[(Z + k) * C + c]);
+        acc[(Z + k) * C + c + 1] = fmaf(gs[k], f1, acc[(Z + k) * C + c + 1]);
+      }
+      *reinterpret_cast<uint32_t*>(df + c) = uz::pack_bf16x2(d0, d1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * Z * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < warps; ++w) t += sm[static_cast<size_t>(w) * 2 * Z * C + i];
+    wpartial[static_cast<size_t>(blockIdx.x) * 2 * Z * C + i] = t;
+  }
+  // bias partials: every lane of a warp holds the same bacc (all lanes executed the same pixel loop)
+  __shared__ float bsm[32][2 * Z];
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 2 * Z; ++k) bsm[wid][k] = bacc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * Z) {
+    float t = 0.f;
+    for (int w = 0; w < warps; ++w) t += bsm[w][threadIdx.x];
+    bpartial[blockIdx.x * 2 * Z + threadIdx.x] = t;
+  }
+}
+
+// out[i] = sum_b partial[b][i]   (fixed order, deterministic)
+__global__ void column_reduce_kernel(const float* __restrict__ partial, int nblocks, int n, float* out, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t = 0.f;
+  for (int b = 0; b < nblocks; ++b) t += partial[static_cast<size_t>(b) * n + i];
+  out[i] = t * scale;
+}
+
+// ---------------------------------------------------------------- KL (one level)
+// out[0] = weight * mean_b( 0.5 * sum_i[ (s0^2 + d^2)/(s1*s0 + 1e-10) + log(s1*s0 + 1e-10) - log(s0^2 + 1e-10) - 1 ] )
+// single block => deterministic; per-element terms in fp32 like the reference, block reduction in fp64.
+__global__ void kl_fwd_kernel(const float* __restrict__ mu0, const float* __restrict__ s0, const float* __restrict__ mu1,
+                              const float* __restrict__ s1, int n, float scale, float* out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = s0[i], b = s1[i], d = mu1[i] - mu0[i];
+    const float v0 = a * a, v1 = b * a;
+    acc += static_cast<double>((v0 + d * d) / (v1 + 1e-10f) + logf(v1 + 1e-10f) - logf(v0 + 1e-10f) - 1.f);
+  }
+  acc = uz::warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    t = uz::warp_sum_d(t);
+    if (threadIdx.x == 0) out[0] = static_cast<float>(0.5 * t * scale);
+  }
+}
+
+__global__ void kl_bwd_kernel(const float* __restrict__ mu0, const float* __restrict__ s0, const float* __restrict__ mu1,
+                              const float* __restrict__ s1, int n, float scale, const float* __restrict__ upstream,
+                              float* dmu0, float* ds0, float* dmu1, float* ds1) {
+  const float g = upstream[0] * scale;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float a = s0[i], b = s1[i], d = mu1[i] - mu0[i];
+    const float t = b * a + 1e-10f, u = a * a + 1e-10f, num = a * a + d * d;
+    const float it = 1.f / t;
+    dmu0[i] = -g * d * it;
+    dmu1[i] = g * d * it;
+    ds1[i] = 0.5f * g * (a * it - num * a * it * it);
+    ds0[i] = 0.5f * g * (2.f * a * it - num * b * it * it + b * it - 2.f * a / u);
+  }
+}
+
+// ---------------------------------------------------------------- s_layer: 1x1 conv to logits + nearest upsample
+// one warp per LOW-res pixel; writes the f x f replicated block of the full-res fp32 NCHW output.
+__global__ void slayer_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ w,
+                                  const float* __restrict__ bias, int ncls, int B, int h, int wd, int f, float* out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int npix = B * h * wd;
+  if (warp >= npix) return;
+  float acc[kMaxCls];
+#pragma unroll
+  for (int k = 0; k < kMaxCls; ++k) acc[k] = 0.f;
+  const __nv_bfloat16* fp = feat + static_cast<size_t>(warp) * ld;
+  for (int c = lane * 2; c < C; c += 64) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(fp + c);
+    const float f0 = uz::bf16lo(v), f1 = uz::bf16hi(v);
+#pragma unroll
+    for (int k = 0; k < kMaxCls; ++k)
+      if (k < ncls) acc[k] = fmaf(f0, w[k * C + c], fmaf(f1, w[k * C + c + 1], acc[k]));
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxCls; ++k)
+    if (k < ncls) acc[k] = uz::warp_sum(acc[k]) + bias[k];
+  const int b = warp / (h * wd);
+  const int r = warp - b * h * wd;
+  const int yl = r / wd, xl = r - yl * wd;
+  const int H = h * f, W = wd * f;
+  for (int k = 0; k < ncls; ++k) {
+    float* o = out + ((static_cast<size_t>(b) * ncls + k) * H + yl * f) * W + xl * f;
+    for (int i = lane; i < f * f; i += 32) o[(i / f) * W + (i % f)] = acc[k];
+  }
+}
+
+// backward: ds_low = sum over the f x f block of ds_full; dfeat = W^T ds_low; partial dW, db per block.
+__global__ void slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ feat, int ld, int C,
+                                  const float* __restrict__ w, int ncls, int B, int h, int wd, int f,
+                                  __nv_bfloat16* dfeat, int ldd, float* wpartial /*[blocks][ncls][C]*/,
+                                  float* bpartial /*[blocks][ncls]*/) {
+  extern __shared__ float sm[];  // [warps][ncls][C]
+  const int warps = blockDim.x >> 5;
+  const int wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float* acc = sm + static_cast<size_t>(wid) * ncls * C;
+  for (int i = lane; i < ncls * C; i += 32) acc[i] = 0.f;
+  float bacc[kMaxCls];
+#pragma unroll
+  for (int k = 0; k < kMaxCls; ++k) bacc[k] = 0.f;
+  __syncwarp();
+  const int npix = B * h * wd;
+  const int H = h * f, W = wd * f;
+  for (int pix = blockIdx.x * warps + wid; pix < npix; pix += gridDim.x * warps) {
+    const int b = pix / (h * wd);
+    const int r = pix - b * h * wd;
+    const int yl = r / wd, xl = r - yl * wd;
+    float g[kMaxCls];
+#pragma unroll
+    for (int k = 0; k < kMaxCls; ++k) {
+      g[k] = 0.f;
+      if (k < ncls) {
+        const float* o = dout + ((static_cast<size_t>(b) * ncls + k) * H + yl * f) * W + xl * f;
+        float t = 0.f;
+        for (int i = lane; i < f * f; i += 32) t += o[(i / f) * W + (i % f)];
+        g[k] = uz::warp_sum(t);
+        bacc[k] += g[k];
+      }
+    }
+    const __nv_bfloat16* fp = feat + static_cast<size_t>(pix) * ld;
+    __nv_bfloat16* df = dfeat + static_cast<size_t>(pix) * ldd;
+    for (int c = lane * 2; c < C; c += 64) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(fp + c);
+      const float f0 = uz::bf16lo(v), f1 = uz::bf16hi(v);
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxCls; ++k) {
+        if (k < ncls) {
+          d0 = fmaf(g[k], w[k * C + c], d0);
+          d1 = fmaf(g[k], w[k * C + c + 1], d1);
+          acc[k * C + c] = fmaf(g[k], f0, acc[k * C + c]);
+          acc[k * C + c + 1] = fmaf(g[k], f1, acc[k * C + c + 1]);
+        }
+      }
+      *reinterpret_cast<uint32_t*>(df + c) = uz::pack_bf16x2(d0, d1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncls * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int ww = 0; ww < warps; ++ww) t += sm[static_cast<size_t>(ww) * ncls * C + i];
+    wpartial[static_cast<size_t>(blockIdx.x) * ncls * C + i] = t;
+  }
+  __shared__ float bsm[32][kMaxCls];
+  if (lane == 0)
+    for (int k = 0; k < ncls; ++k) bsm[wid][k] = bacc[k];
+  __syncthreads();
+  if (threadIdx.x < ncls) {
+    float t = 0.f;
+    for (int ww = 0; ww < warps; ++ww) t += bsm[ww][threadIdx.x];
+    bpartial[blockIdx.x * ncls + threadIdx.x] = t;
+  }
+}
+
+// ---------------------------------------------------------------- residual multinoulli loss (forward + gradients)
+struct LevelPtrs {
+  const float* s[kMaxLvl];
+  float* ds[kMaxLvl];
+};
+// For level l (processed L-1 .. 0): acc_l = sum_{k>=l} s_k ; CE_l(pixel) = logsumexp(acc_l) - acc_l[target].
+// Per-block partial sums per level -> partial[block][L]; gradients d s_k = (1/B) * sum_{l<=k} (softmax(acc_l) - onehot).
+__global__ void residual_ce_kernel(LevelPtrs ptrs, int L, int ncls, const float* __restrict__ target, int B, int hw,
+                                   float inv_batch, const float* __restrict__ upstream, float* partial) {
+  if (upstream) inv_batch *= upstream[0];
+  __shared__ float red[32][kMaxLvl];
+  float lsum[kMaxLvl];
+#pragma unroll
+  for (int l = 0; l < kMaxLvl; ++l) lsum[l] = 0.f;
+  const size_t npix = static_cast<size_t>(B) * hw;
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < npix;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = pix / hw, r = pix - b * hw;
+    const int tgt = static_cast<int>(target[pix]);
+    float acc[kMaxCls], grad[kMaxCls];
+#pragma unroll
+    for (int k = 0; k < kMaxCls; ++k) { acc[k] = 0.f; grad[k] = 0.f; }
+    float gl[kMaxLvl][kMaxCls];
+#pragma unroll
+    for (int l = kMaxLvl - 1; l >= 0; --l) {
+      if (l < L) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kMaxCls; ++k)
+          if (k < ncls) {
+            acc[k] += ptrs.s[l][(b * ncls + k) * hw + r];
+            mx = fmaxf(mx, acc[k]);
+          }
+        float se = 0.f, e[kMaxCls];
+#pragma unroll
+        for (int k = 0; k < kMaxCls; ++k)
+          if (k < ncls) { e[k] = expf(acc[k] - mx); se += e[k]; }
+        const float lse = mx + logf(se);
+        float at = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxCls; ++k)
+          if (k < ncls) {
+            if (k == tgt) at = acc[k];
+            gl[l][k] = (e[k] / se - (k == tgt ? 1.f : 0.f)) * inv_batch;
+          }
+        lsum[l] += lse - at;
+      }
+    }
+    // d s_k = sum_{l<=k} gl[l]  (prefix over levels from 0 upwards)
+#pragma unroll
+    for (int l = 0; l < kMaxLvl; ++l) {
+      if (l < L) {
+#pragma unroll
+        for (int k = 0; k < kMaxCls; ++k)
+          if (k < ncls) {
+            grad[k] += gl[l][k];
+            if (ptrs.ds[l]) ptrs.ds[l][(b * ncls + k) * hw + r] = grad[k];
+          }
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int l = 0; l < kMaxLvl; ++l) {
+    const float t = uz::warp_sum(lsum[l]);
+    if (lane == 0) red[wid][l] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < L) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w][threadIdx.x];
+    partial[blockIdx.x * L + threadIdx.x] = t;
+  }
+}
+
+// ---------------------------------------------------------------- accumulate_output (+softmax), in place into the last list entry
+__global__ void accumulate_kernel(LevelPtrs ptrs, int L, int ncls, int B, int hw, int use_softmax, float* out) {
+  const size_t npix = static_cast<size_t>(B) * hw;
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < npix;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = pix / hw, r = pix - b * hw;
+    float acc[kMaxCls];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxCls; ++k) {
+      acc[k] = 0.f;
+      if (k < ncls) {
+        // same association order as the reference: ((s[L-1] + s[0]) + s[1]) + ...
+        float t = ptrs.s[L - 1][(b * ncls + k) * hw + r];
+        for (int l = 0; l < L - 1; ++l) t += ptrs.s[l][(b * ncls + k) * hw + r];
+        acc[k] = t;
+        mx = fmaxf(mx, t);
+      }
+    }
+    if (use_softmax) {
+      float se = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxCls; ++k)
+        if (k < ncls) { acc[k] = expf(acc[k] - mx); se += acc[k]; }
+#pragma unroll
+      for (int k = 0; k < kMaxCls; ++k)
+        if (k < ncls) acc[k] = acc[k] / se;
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxCls; ++k)
+      if (k < ncls) out[(b * ncls + k) * hw + r] = acc[k];
+  }
+}
+
+int cap_blocks(long long want, int per_sm) {
+  long long cap = static_cast<long long>(uz::num_sms()) * per_sm;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+
+}  // namespace
+
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int uz_head_fwd(const void* feat, int ld, int C, const float* wmu, const float* bmu, const float* wsig,
+                           const float* bsig, const float* eps, int B, int hw, int zdim, float* mu, float* sigma,
+                           float* z, void* stream) {
+  UZ_CHECK_ARG(feat && wmu && bmu && wsig && bsig && eps && mu && sigma && z, "uz_head_fwd: null pointer");
+  UZ_CHECK_ARG(zdim == 2, "uz_head_fwd: z_dim %d unsupported (reference hard-codes 2, models/phiseg.py:81)", zdim);
+  UZ_CHECK_ARG(C % 2 == 0 && ld % 2 == 0, "uz_head_fwd: C and ld must be even");
+  const int npix = B * hw;
+  const int threads = 256;
+  const int blocks = (npix * 32 + threads - 1) / threads;
+  head_fwd_kernel<2><<<blocks, threads, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, bmu, wsig,
+                                                          bsig, eps, B, hw, mu, sigma, z);
+  UZ_CHECK_LAUNCH("uz_head_fwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_head_bwd_num_blocks(int B, int hw) { return cap_blocks((static_cast<long long>(B) * hw + 7) / 8, 1); }
+
+// dw: [2*zdim][C] (rows 0..zdim-1 = d mu_conv.weight, rest = d sigma_conv.weight); db: [2*zdim] likewise.
+extern "C" int uz_head_bwd(const void* feat, int ld, int C, const float* wmu, const float* wsig, const float* eps,
+                           const float* sigma, const float* dmu, const float* dsigma, const float* dz, int B, int hw,
+                           int zdim, void* dfeat, int ldd, float* wpartial, float* bpartial, float* dw, float* db,
+                           void* stream) {
+  UZ_CHECK_ARG(feat && wmu && wsig && eps && sigma && dfeat && wpartial && bpartial && dw && db,
+               "uz_head_bwd: null pointer");
+  UZ_CHECK_ARG(zdim == 2, "uz_head_bwd: z_dim %d unsupported", zdim);
+  UZ_CHECK_ARG(C % 2 == 0 && ld % 2 == 0 && ldd % 2 == 0, "uz_head_bwd: C and strides must be even");
+  const int threads = 256;  // 8 warps
+  const int blocks = uz_head_bwd_num_blocks(B, hw);
+  const size_t smem = static_cast<size_t>(threads / 32) * 4 * C * sizeof(float);
+  UZ_CHECK_ARG(smem <= 48 * 1024, "uz_head_bwd: C=%d too large for the shared accumulators", C);
+  head_bwd_kernel<2><<<blocks, threads, smem, ST(stream)>>>(static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, wsig,
+                                                            eps, sigma, dmu, dsigma, dz, B, hw,
+                                                            static_cast<__nv_bfloat16*>(dfeat), ldd, wpartial, bpartial);
+  UZ_CHECK_LAUNCH("uz_head_bwd");
+  column_reduce_kernel<<<(4 * C + 127) / 128, 128, 0, ST(stream)>>>(wpartial, blocks, 4 * C, dw, 1.f);
+  column_reduce_kernel<<<1, 32, 0, ST(stream)>>>(bpartial, blocks, 4, db, 1.f);
+  UZ_CHECK_LAUNCH("uz_head_bwd(reduce)");
+  return UZ_OK;
+}
+
+extern "C" int uz_kl_fwd(const float* mu0, const float* s0, const float* mu1, const float* s1, int batch,
+                         int per_sample, float weight, float* out, void* stream) {
+  UZ_CHECK_ARG(mu0 && s0 && mu1 && s1 && out && batch > 0, "uz_kl_fwd: bad arguments");
+  kl_fwd_kernel<<<1, 1024, 0, ST(stream)>>>(mu0, s0, mu1, s1, batch * per_sample, weight / batch, out);
+  UZ_CHECK_LAUNCH("uz_kl_fwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_kl_bwd(const float* mu0, const float* s0, const float* mu1, const float* s1, int batch,
+                         int per_sample, float weight, const float* upstream, float* dmu0, float* ds0, float* dmu1,
+                         float* ds1, void* stream) {
+  UZ_CHECK_ARG(mu0 && s0 && mu1 && s1 && upstream && dmu0 && ds0 && dmu1 && ds1, "uz_kl_bwd: null pointer");
+  const int n = batch * per_sample;
+  kl_bwd_kernel<<<cap_blocks((n + 255) / 256, 4), 256, 0, ST(stream)>>>(mu0, s0, mu1, s1, n, weight / batch, upstream,
+                                                                       dmu0, ds0, dmu1, ds1);
+  UZ_CHECK_LAUNCH("uz_kl_bwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_slayer_fwd(const void* feat, int ld, int C, const float* w, const float* bias, int ncls, int B,
+                             int h, int wd, int factor, float* out, void* stream) {
+  UZ_CHECK_ARG(feat && w && bias && out, "uz_slayer_fwd: null pointer");
+  UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxCls, "uz_slayer_fwd: n_classes %d unsupported (max %d)", ncls, kMaxCls);
+  UZ_CHECK_ARG(C % 2 == 0 && ld % 2 == 0 && factor >= 1, "uz_slayer_fwd: bad C/ld/factor");
+  const int npix = B * h * wd;
+  const int threads = 256;
+  slayer_fwd_kernel<<<(npix * 32 + threads - 1) / threads, threads, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(feat), ld, C, w, bias, ncls, B, h, wd, factor, out);
+  UZ_CHECK_LAUNCH("uz_slayer_fwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_slayer_bwd_num_blocks(int B, int h, int wd) {
+  return cap_blocks((static_cast<long long>(B) * h * wd + 7) / 8, 2);
+}
+
+extern "C" int uz_slayer_bwd(const float* dout, const void* feat, int ld, int C, const float* w, int ncls, int B, int h,
+                             int wd, int factor, void* dfeat, int ldd, float* wpartial, float* bpartial, float* dw,
+                             float* db, void* stream) {
+  UZ_CHECK_ARG(dout && feat && w && dfeat && wpartial && bpartial && dw && db, "uz_slayer_bwd: null pointer");
+  UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxCls, "uz_slayer_bwd: n_classes %d unsupported", ncls);
+  const int threads = 256;
+  const int blocks = uz_slayer_bwd_num_blocks(B, h, wd);
+  const size_t smem = static_cast<size_t>(threads / 32) * ncls * C * sizeof(float);
+  UZ_CHECK_ARG(smem <= 48 * 1024, "uz_slayer_bwd: ncls*C too large for the shared accumulators");
+  slayer_bwd_kernel<<<blocks, threads, smem, ST(stream)>>>(dout, static_cast<const __nv_bfloat16*>(feat), ld, C, w, ncls,
+                                                           B, h, wd, factor, static_cast<__nv_bfloat16*>(dfeat), ldd,
+                                                           wpartial, bpartial);
+  UZ_CHECK_LAUNCH("uz_slayer_bwd");
+  column_reduce_kernel<<<(ncls * C + 127) / 128, 128, 0, ST(stream)>>>(wpartial, blocks, ncls * C, dw, 1.f);
+  column_reduce_kernel<<<1, 32, 0, ST(stream)>>>(bpartial, blocks, ncls, db, 1.f);
+  UZ_CHECK_LAUNCH("uz_slayer_bwd(reduce)");
+  return UZ_OK;
+}
+
+extern "C" int uz_residual_ce_num_blocks(int B, int hw) {
+  return cap_blocks((static_cast<long long>(B) * hw + 255) / 256, 4);
+}
+
+// s[l], ds[l]: L pointers to fp32 NCHW [B,ncls,H,W]; ds entries (or ds itself) may be null when no gradient is needed.
+// ce_levels[l] = mean_b sum_pixels CE(sum_{k>=l} s_k, target)
+extern "C" int uz_residual_ce(const float* const* s, float* const* ds, const float* upstream, int L, int ncls,
+                              const float* target, int B, int hw, float* partial, float* ce_levels, void* stream) {
+  UZ_CHECK_ARG(s && target && partial && ce_levels, "uz_residual_ce: null pointer");
+  UZ_CHECK_ARG(L >= 1 && L <= kMaxLvl && ncls >= 1 && ncls <= kMaxCls, "uz_residual_ce: L=%d ncls=%d unsupported", L,
+               ncls);
+  LevelPtrs p{};
+  for (int l = 0; l < L; ++l) {
+    p.s[l] = s[l];
+    p.ds[l] = ds ? ds[l] : nullptr;
+  }
+  const int blocks = uz_residual_ce_num_blocks(B, hw);
+  residual_ce_kernel<<<blocks, 256, 0, ST(stream)>>>(p, L, ncls, target, B, hw, 1.f / B, upstream, partial);
+  UZ_CHECK_LAUNCH("uz_residual_ce");
+  column_reduce_kernel<<<1, 32, 0, ST(stream)>>>(partial, blocks, L, ce_levels, 1.f / B);
+  UZ_CHECK_LAUNCH("uz_residual_ce(reduce)");
+  return UZ_OK;
+}
+
+// out may alias s[L-1] (the reference accumulates in place into output_list[-1], quirk Q2).
+extern "C" int uz_accumulate_output(const float* const* s, int L, int ncls, int B, int hw, int use_softmax, float* out,
+                                    void* stream) {
+  UZ_CHECK_ARG(s && out, "uz_accumulate_output: null pointer");
+  UZ_CHECK_ARG(L >= 1 && L <= kMaxLvl && ncls >= 1 && ncls <= kMaxCls, "uz_accumulate_output: L=%d ncls=%d unsupported",
+               L, ncls);
+  LevelPtrs p{};
+  for (int l = 0; l < L; ++l) p.s[l] = s[l];
+  accumulate_kernel<<<cap_blocks((static_cast<long long>(B) * hw + 255) / 256, 8), 256, 0, ST(stream)>>>(
+      p, L, ncls, B, hw, use_softmax, out);
+  UZ_CHECK_LAUNCH("uz_accumulate_output");
+  return UZ_OK;
+}

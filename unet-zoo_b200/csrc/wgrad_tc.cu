@@ -1,0 +1,294 @@
+// Weight gradient of the 3x3 / 1x1 convolution on tcgen05 tensor cores.
+//
+//   dW[tap][co][ci] = sum over pixels p of dy[p][co] * x[p + offset(tap)][ci]
+//
+// GEMM view per tap: D[M = co][N = ci] += A[M = co][K = pixel] * B[N = ci][K = pixel].  Both operands are NHWC, i.e. the
+// M/N index (channel) is contiguous and K (pixel) is strided: the "MN-major" operand mode of tcgen05.mma, fed directly
+// by the same TMA boxes the forward kernel uses ([pixels][64 channels], 128-byte swizzle).  The tap offset is applied
+// to the x box coordinates; out-of-bounds pixels (zero padding) are zero-filled by TMA.
+//
+// Work split: grid.x = pixel splits (split-K), grid.y = (tap group) x (128-wide block of co).  A CTA keeps one fp32
+// accumulator [128 x Cin] per tap of its group in TMEM (taps_per_cta * Cin <= 512 columns), streams its share of the
+// pixel tiles through a TMA/mbarrier pipeline and finally writes a partial [tap][co][ci] slab; uz_wgrad_reduce sums the
+// slabs in fixed order (deterministic) into the PyTorch OIHW fp32 gradient.
+#include "common.cuh"
+#include "unetzoo_b200.h"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 6;
+
+struct WgradParams {
+  int N, H, W, Cin, Cout;   // Cin / Cout as stored (multiples of 16)
+  int taps;                 // 9 or 1
+  int PIX;                  // pixels per K tile (64 or 128)
+  int TW, TH, TN;
+  int tilesW, tilesH, num_tiles;
+  int taps_per_cta, tap_groups;
+  int a_boxes, b_boxes;     // 64-channel boxes per stage for dy (<=2) and x
+  int stages;
+  uint32_t tmem_cols;
+  float* partial;           // [splits][taps][Cout][Cin]
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t box_bytes = p.PIX * 128;                         // [PIX pixels][64 ch] bf16
+  const uint32_t a_bytes = p.a_boxes * box_bytes;
+  const uint32_t b_bytes = p.b_boxes * box_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x, splits = gridDim.x;
+  const int group = blockIdx.y % p.tap_groups;
+  const int co0 = (blockIdx.y / p.tap_groups) * 128;
+  const int tap0 = group * p.taps_per_cta;
+  int ntaps = p.taps - tap0; if (ntaps > p.taps_per_cta) ntaps = p.taps_per_cta;
+
+  int my_tiles = 0;
+  if (split < p.num_tiles) my_tiles = (p.num_tiles - split + splits - 1) / splits;
+  const int iters = my_tiles * ntaps;
+
+  if (warp == 0 && lane == 0) {
+    uz::tma_prefetch_desc(&tmap_dy);
+    uz::tma_prefetch_desc(&tmap_x);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        uz::mbar_init(&full_bar[s], 1);
+        uz::mbar_init(&empty_bar[s], 1);
+      }
+      uz::mbar_init(&accum_bar, 1);
+      uz::fence_barrier_init();
+    }
+    __syncwarp();
+    uz::tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  }
+  uz::tc_fence_before();
+  __syncthreads();
+  uz::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages;
+        if (it >= p.stages) uz::mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
+        const int ti = it / ntaps;
+        const int tap = tap0 + (it - ti * ntaps);
+        const int tile = split + ti * splits;
+        const int tx = tile % p.tilesW;
+        const int ty = (tile / p.tilesW) % p.tilesH;
+        const int tn = tile / (p.tilesW * p.tilesH);
+        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
+        int dy = 0, dx = 0;
+        if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+        uint8_t* sa = smem + s * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        uz::mbar_expect_tx(&full_bar[s], stage_bytes);
+        for (int b = 0; b < p.a_boxes; ++b)
+          uz::tma_load_4d(sa + b * box_bytes, &tmap_dy, &full_bar[s], co0 + b * 64, x0, y0, n0);
+        for (int b = 0; b < p.b_boxes; ++b)
+          uz::tma_load_4d(sb + b * box_bytes, &tmap_x, &full_bar[s], b * 64, x0 + dx, y0 + dy, n0);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t lbo = box_bytes;   // stride between 64-channel runs
+    const uint32_t sbo = 1024;        // 8 pixel rows x 128 B
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % p.stages;
+      uz::mbar_wait(&full_bar[s], (it / p.stages) & 1);
+      uz::tc_fence_after();
+      if (lane == 0) {
+        const int ti = it / ntaps;
+        const int tl = it - ti * ntaps;  // local tap index -> accumulator slot
+        const uint32_t a_addr = uz::smem_u32(smem + s * stage_bytes);
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int ks = 0; ks < p.PIX / 16; ++ks) {
+          const uint64_t adesc = uz::umma_desc(a_addr + ks * 2048, lbo, sbo, 128);
+          for (int c = 0; c < p.Cin; c += 256) {
+            const int nn = (p.Cin - c) < 256 ? (p.Cin - c) : 256;
+            const uint64_t bdesc = uz::umma_desc(b_addr + (c / 64) * box_bytes + ks * 2048, lbo, sbo, 128);
+            const uint32_t idesc = uz::umma_idesc_bf16(128, nn, 1, 1);
+            uz::tc_mma_f16(tmem_base + tl * p.Cin + c, adesc, bdesc, idesc, (ti | ks) != 0);
+          }
+        }
+        uz::tc_commit(&empty_bar[s]);
+        if (it == iters - 1) uz::tc_commit(&accum_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;            // co within the block
+    const int co = co0 + row;
+    if (iters > 0) {
+      uz::mbar_wait(&accum_bar, 0);
+      uz::tc_fence_after();
+    }
+    for (int tl = 0; tl < ntaps; ++tl) {
+      float* dst = p.partial + ((static_cast<size_t>(split) * p.taps + tap0 + tl) * p.Cout + co) * p.Cin;
+      for (int c = 0; c < p.Cin; c += 16) {
+        uint32_t r[16];
+        if (iters > 0) {
+          uz::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tl * p.Cin + c, r);
+          uz::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        if (co < p.Cout) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3]));
+        }
+      }
+    }
+  }
+
+  uz::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    uz::tc_fence_after();
+    uz::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// dw[o][i][t] (+)= scale * sum_s partial[s][t][o][i]   (fixed order); also emits dbias[o] = sum_pixels dy when asked.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int CoutP, int CinP,
+                                    int Cout, int Cin, float* dw) {
+  const size_t total = static_cast<size_t>(Cout) * Cin * taps;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int t = idx % taps;
+    const int i = (idx / taps) % Cin;
+    const int o = idx / (static_cast<size_t>(taps) * Cin);
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s)
+      acc += partial[((static_cast<size_t>(s) * taps + t) * CoutP + o) * CinP + i];
+    dw[idx] = acc;
+  }
+}
+
+int pow2_div_le(int v, int cap) {
+  int t = 1;
+  while (t * 2 <= cap && v % (t * 2) == 0) t *= 2;
+  return t;
+}
+
+struct Plan {
+  WgradParams p;
+  int splits, co_blocks;
+  size_t smem;
+};
+
+int make_plan(int N, int H, int W, int Cin, int Cout, int taps, Plan* out) {
+  WgradParams& p = out->p;
+  p = WgradParams{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
+  p.PIX = Cin <= 128 ? 128 : 64;
+  p.TW = pow2_div_le(W, 16);
+  p.TH = pow2_div_le(H, p.PIX / p.TW);
+  p.TN = p.PIX / (p.TW * p.TH);
+  p.tilesW = W / p.TW; p.tilesH = H / p.TH;
+  p.num_tiles = p.tilesW * p.tilesH * ((N + p.TN - 1) / p.TN);
+  int tpc = 512 / Cin; if (tpc < 1) return UZ_ERR_ARG;
+  if (tpc > taps) tpc = taps;
+  if (taps == 9 && tpc >= 3 && tpc < 9) tpc = 3;   // balanced groups of three
+  p.taps_per_cta = tpc;
+  p.tap_groups = (taps + tpc - 1) / tpc;
+  p.a_boxes = Cout > 64 ? 2 : 1;
+  p.b_boxes = (Cin + 63) / 64;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(tpc * Cin)) cols *= 2;
+  p.tmem_cols = cols;
+  const size_t stage_bytes = static_cast<size_t>(p.a_boxes + p.b_boxes) * p.PIX * 128;
+  int stages = static_cast<int>((196 * 1024) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 1) return UZ_ERR_ARG;
+  p.stages = stages;
+  out->smem = stages * stage_bytes + 1024;
+  out->co_blocks = (Cout + 127) / 128;
+  const int per_split = p.tap_groups * out->co_blocks;
+  int splits = (2 * uz::num_sms() + per_split - 1) / per_split;
+  if (splits > p.num_tiles) splits = p.num_tiles;
+  if (splits < 1) splits = 1;
+  out->splits = splits;
+  return UZ_OK;
+}
+
+}  // namespace
+
+extern "C" long long uz_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout, int taps) {
+  Plan pl;
+  if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0 || Cin > 512 || make_plan(N, H, W, Cin, Cout, taps, &pl)) return -1;
+  return static_cast<long long>(pl.splits) * taps * Cout * Cin;
+}
+
+// x: bf16 NHWC [N,H,W,Cin] (ldx), dy: bf16 NHWC [N,H,W,Cout] (lddy); dw: fp32 [Cout_logical][Cin_logical][taps].
+extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, int N, int H, int W, int Cin, int Cout,
+                             int taps, int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream) {
+  UZ_CHECK_ARG(x && dy && workspace && dw, "uz_conv_wgrad: null pointer");
+  UZ_CHECK_ARG(taps == 9 || taps == 1, "uz_conv_wgrad: taps must be 9 or 1");
+  UZ_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0 && Cin > 0 && Cout > 0 && Cin <= 512,
+               "uz_conv_wgrad: channels must be multiples of 16, Cin <= 512 (got %d, %d)", Cin, Cout);
+  UZ_CHECK_ARG(ldx % 8 == 0 && lddy % 8 == 0 && ldx >= Cin && lddy >= Cout, "uz_conv_wgrad: bad pixel strides");
+  UZ_CHECK_ARG(Cin_logical <= Cin && Cout_logical <= Cout, "uz_conv_wgrad: logical dims exceed stored dims");
+  Plan pl;
+  int rc = make_plan(N, H, W, Cin, Cout, taps, &pl);
+  UZ_CHECK_ARG(rc == UZ_OK, "uz_conv_wgrad: no plan for Cin=%d Cout=%d", Cin, Cout);
+  pl.p.partial = workspace;
+  CUtensorMap tdy, tx;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(lddy) * 2, static_cast<uint64_t>(W) * lddy * 2,
+                           static_cast<uint64_t>(H) * W * lddy * 2};
+    uint32_t box[4] = {64, static_cast<uint32_t>(pl.p.TW), static_cast<uint32_t>(pl.p.TH),
+                       static_cast<uint32_t>(pl.p.TN)};
+    rc = uz::make_tmap_bf16(&tdy, dy, 4, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(W) * ldx * 2,
+                           static_cast<uint64_t>(H) * W * ldx * 2};
+    uint32_t box[4] = {64, static_cast<uint32_t>(pl.p.TW), static_cast<uint32_t>(pl.p.TH),
+                       static_cast<uint32_t>(pl.p.TN)};
+    rc = uz::make_tmap_bf16(&tx, x, 4, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  static size_t attr_bytes = 0;
+  if (pl.smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      uz::set_error("uz_conv_wgrad: cannot raise dynamic smem limit to %zu: %s", static_cast<size_t>(pl.smem), cudaGetErrorString(e));
+      return UZ_ERR_CUDA;
+    }
+    attr_bytes = pl.smem;
+  }
+  dim3 grid(pl.splits, pl.p.tap_groups * pl.co_blocks, 1);
+  wgrad_tc_kernel<<<grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream)>>>(tdy, tx, pl.p);
+  UZ_CHECK_LAUNCH("uz_conv_wgrad");
+  const size_t total = static_cast<size_t>(Cout_logical) * Cin_logical * taps;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > uz::num_sms() * 8) blocks = uz::num_sms() * 8;
+  wgrad_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(workspace, pl.splits, taps, Cout, Cin,
+                                                                            Cout_logical, Cin_logical, dw);
+  UZ_CHECK_LAUNCH("uz_conv_wgrad(reduce)");
+  return UZ_OK;
+}

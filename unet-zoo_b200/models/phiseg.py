@@ -1,0 +1,403 @@
+"""Drop-in for the reference's ``models/phiseg.py`` on B200.
+
+Same public classes, constructor keywords, method names, cached attributes and state_dict keys as the reference
+(DownConvolutionalBlock :14-39, UpConvolutionalBlock :42-73, SampleZBlock :76-106, Posterior :109-206,
+increase_resolution :209-221, Likelihood :224-323, PHISeg :326-537), so ``train_model.py`` / ``test_model.py`` and
+the experiment files run unmodified.  Underneath, activations stay bf16 NHWC between layers and every op is a kernel
+of libunetzoo_b200.so; mu / sigma / z / logits / losses are fp32 NCHW tensors exactly where the reference exposes them.
+
+Quirks reproduced on purpose: Q1 loss aliasing, Q2 in-place accumulate_output, Q3 sigma1*sigma0 in
+the KL, Q4 RNG draw order (torch.randn_like is called with the reference's shapes in the reference's order, so a
+seeded run consumes the same Philox stream), Q5 ignored constructor arguments.
+"""
+import torch
+import torch.nn as nn
+
+from b200 import kern, ops
+from b200.ops import Act
+from torchlayers import Conv2D, Conv2DSequence, ReversibleSequence, _boundary
+
+
+class DownConvolutionalBlock(nn.Module):
+    def __init__(self, input_dim, output_dim, initializers, depth=3, padding=True, pool=True, reversible=False):
+        super(DownConvolutionalBlock, self).__init__()
+        if depth < 1:
+            raise ValueError
+        layers = []
+        if pool:
+            layers.append(nn.AvgPool2d(kernel_size=2, stride=2, padding=0, ceil_mode=True))
+        if reversible:
+            layers.append(ReversibleSequence(input_dim, output_dim, reversible_depth=3))
+        else:
+            layers.append(Conv2D(input_dim, output_dim, kernel_size=3, stride=1, padding=int(padding)))
+            if depth > 1:
+                for i in range(depth - 1):
+                    layers.append(Conv2D(output_dim, output_dim, kernel_size=3, stride=1, padding=int(padding)))
+        self.layers = nn.Sequential(*layers)
+
+    @_boundary
+    def forward(self, x):
+        for layer in self.layers:
+            if isinstance(layer, nn.AvgPool2d):
+                if x.t.shape[1] % 2 or x.t.shape[2] % 2:
+                    raise ValueError('AvgPool2d on odd sizes is unreachable in the reference (skip-shape asserts)')
+                x = Act(ops.AvgPool2.apply(x.t), x.c)
+            else:
+                x = layer(x)
+        return x
+
+
+class UpConvolutionalBlock(nn.Module):
+    """bilinear x2 (align_corners=True) -> 2 x Conv2D -> cat([x, bridge])"""
+
+    def __init__(self, input_dim, output_dim, initializers, padding, bilinear=True, reversible=False):
+        super(UpConvolutionalBlock, self).__init__()
+        self.bilinear = bilinear
+        if self.bilinear:
+            if reversible:
+                self.upconv_layer = ReversibleSequence(input_dim, output_dim, reversible_depth=2)
+            else:
+                self.upconv_layer = nn.Sequential(
+                    Conv2D(input_dim, output_dim, kernel_size=3, stride=1, padding=1),
+                    Conv2D(output_dim, output_dim, kernel_size=3, stride=1, padding=1),
+                )
+        else:
+            raise NotImplementedError
+
+    def forward(self, x, bridge):
+        plain = not isinstance(x, Act)
+        x, bridge = ops.to_act(x), ops.to_act(bridge)
+        if self.bilinear:
+            x = Act(ops.Upsample2x.apply(x.t, True), x.c)
+            for layer in self.upconv_layer:
+                x = layer(x)
+        assert x.t.shape[2] == bridge.t.shape[2]
+        assert x.t.shape[1] == bridge.t.shape[1]
+        out = Act(ops.Concat.apply(x.t, bridge.t, False, False, True), x.c + bridge.c)
+        return ops.from_act(out) if plain else out
+
+
+class SampleZBlock(nn.Module):
+    """2 x Conv2D, then 1x1 heads: mu, sigma = softplus(.), z = mu + sigma * randn_like(sigma)."""
+
+    def __init__(self, input_dim, z_dim0=2, depth=2, reversible=False):
+        super(SampleZBlock, self).__init__()
+        self.input_dim = input_dim
+        layers = []
+        if reversible:
+            layers.append(ReversibleSequence(input_dim, input_dim, reversible_depth=3))
+        else:
+            for i in range(depth):
+                layers.append(Conv2D(input_dim, input_dim, kernel_size=3, padding=1))
+        self.conv = nn.Sequential(*layers)
+        self.mu_conv = nn.Sequential(nn.Conv2d(input_dim, z_dim0, kernel_size=1))
+        self.sigma_conv = nn.Sequential(nn.Conv2d(input_dim, z_dim0, kernel_size=1), nn.Softplus())
+
+    def forward(self, pre_z):
+        x = ops.to_act(pre_z)
+        for layer in self.conv:
+            x = layer(x)
+        n, h, w, _ = x.t.shape
+        zdim = self.mu_conv[0].out_channels
+        # same call, shape, dtype and order as the reference (models/phiseg.py:104) => same RNG stream
+        eps = torch.randn_like(torch.empty((n, zdim, h, w), device=x.t.device, dtype=torch.float32), dtype=torch.float32)
+        mu, sigma, z = ops.LatentHead.apply(x.t, self.mu_conv[0].weight, self.mu_conv[0].bias,
+                                            self.sigma_conv[0].weight, self.sigma_conv[0].bias, eps)
+        return mu, sigma, z
+
+
+class Posterior(nn.Module):
+    """Posterior network (prior when is_posterior=False): 7 resolution levels, 5 latent levels (hard-coded like the
+    reference, models/phiseg.py:131-132)."""
+
+    def __init__(self, input_channels, num_classes, num_filters, initializers=None, padding=True, is_posterior=True,
+                 reversible=False):
+        super(Posterior, self).__init__()
+        self.input_channels = input_channels
+        self.num_filters = num_filters
+        self.latent_levels = 5
+        self.resolution_levels = 7
+        self.lvl_diff = self.resolution_levels - self.latent_levels
+        self.padding = padding
+        self.activation_maps = []
+        self.is_posterior = is_posterior
+        self.image_channels = input_channels
+        if is_posterior:
+            self.input_channels += 2          # one-hot mask, hard-coded two labels (models/phiseg.py:140,179)
+
+        self.contracting_path = nn.ModuleList()
+        for i in range(self.resolution_levels):
+            input = self.input_channels if i == 0 else output
+            output = self.num_filters[i]
+            pool = False if i == 0 else True
+            self.contracting_path.append(DownConvolutionalBlock(input, output, initializers, depth=3, padding=padding,
+                                                                pool=pool, reversible=reversible))
+        self.upsampling_path = nn.ModuleList()
+        for i in reversed(range(self.latent_levels)):
+            input = 2
+            output = self.num_filters[0] * 2
+            self.upsampling_path.append(UpConvolutionalBlock(input, output, initializers, padding, reversible=reversible))
+        self.sample_z_path = nn.ModuleList()
+        for i in reversed(range(self.latent_levels)):
+            input = 2 * self.num_filters[0] + self.num_filters[i + self.lvl_diff]
+            if i == self.latent_levels - 1:
+                input = self.num_filters[i + self.lvl_diff]
+            self.sample_z_path.append(SampleZBlock(input, depth=2, reversible=reversible))
+
+    def forward(self, patch, segm=None, training_prior=False, z_list=None):
+        if not patch.is_cuda:
+            raise kern._lib.UnetZooLibError('UNet-Zoo B200 modules need CUDA tensors: there is no CPU fallback path')
+        cp = kern.pad16(self.input_channels)
+        # one-hot(mask) - 0.5 concatenated after the image channels, produced directly in NHWC bf16 on the device
+        x = Act(kern.input_pack(patch, segm if segm is not None else None, nlabels=2, cp=cp), self.input_channels)
+        blocks = []
+        z = [None] * self.latent_levels
+        sigma = [None] * self.latent_levels
+        mu = [None] * self.latent_levels
+        for i, down in enumerate(self.contracting_path):
+            x = down(x)
+            if i != len(self.contracting_path) - 1:
+                blocks.append(x)
+        pre_conv = x
+        for i, sample_z in enumerate(self.sample_z_path):
+            if i != 0:
+                pre_conv = self.upsampling_path[i - 1](ops.to_act(z[-i]), blocks[-i])
+            mu[-i - 1], sigma[-i - 1], z[-i - 1] = self.sample_z_path[i](pre_conv)
+            if training_prior:
+                z[-i - 1] = z_list[-i - 1]      # own draw discarded AFTER it was made (quirk Q4)
+        del blocks
+        return z, mu, sigma
+
+
+class _UpsampleConvStack(nn.Sequential):
+    """nn.Sequential of [nn.Upsample, Conv2DSequence] * n whose forward runs the B200 kernels."""
+
+    @_boundary
+    def forward(self, x):
+        for m in self:
+            if isinstance(m, nn.Upsample):
+                x = Act(ops.Upsample2x.apply(x.t, True), x.c)
+            else:
+                x = m(x)
+        return x
+
+
+def increase_resolution(times, input_dim, output_dim):
+    """Increase the resolution by n times for the beginning of the likelihood path (models/phiseg.py:209-221)."""
+    module_list = []
+    for i in range(times):
+        module_list.append(nn.Upsample(mode='bilinear', scale_factor=2, align_corners=True))
+        if i != 0:
+            input_dim = output_dim
+        module_list.append(Conv2DSequence(input_dim=input_dim, output_dim=output_dim, depth=1))
+    return _UpsampleConvStack(*module_list)
+
+
+class Likelihood(nn.Module):
+    def __init__(self, input_channels, num_classes, num_filters, latent_levels=5, resolution_levels=7,
+                 image_size=(128, 128, 1), reversible=False, initializers=None, apply_last_layer=True, padding=True):
+        super(Likelihood, self).__init__()
+        self.input_channels = input_channels
+        self.num_classes = num_classes
+        self.num_filters = num_filters
+        self.latent_levels = latent_levels
+        self.resolution_levels = resolution_levels
+        self.lvl_diff = resolution_levels - latent_levels
+        self.image_size = image_size
+        self.reversible = reversible
+        self.padding = padding
+        self.activation_maps = []
+        self.apply_last_layer = apply_last_layer
+
+        self.likelihood_ups_path = nn.ModuleList()
+        self.likelihood_post_ups_path = nn.ModuleList()
+        for i in reversed(range(self.latent_levels)):
+            input = self.num_filters[i]
+            if reversible:
+                self.likelihood_ups_path.append(ReversibleSequence(input_dim=2, output_dim=input, reversible_depth=2))
+            else:
+                self.likelihood_ups_path.append(Conv2DSequence(input_dim=2, output_dim=input, depth=2))
+            self.likelihood_post_ups_path.append(increase_resolution(times=self.lvl_diff, input_dim=input,
+                                                                     output_dim=input))
+        self.likelihood_post_c_path = nn.ModuleList()
+        for i in range(latent_levels - 1):
+            input = self.num_filters[i] + self.num_filters[i + 1 + self.lvl_diff]
+            output = self.num_filters[i + self.lvl_diff]
+            if reversible:
+                self.likelihood_post_c_path.append(ReversibleSequence(input_dim=input, output_dim=output,
+                                                                      reversible_depth=2))
+            else:
+                self.likelihood_post_c_path.append(Conv2DSequence(input_dim=input, output_dim=output, depth=2))
+        self.s_layer = nn.ModuleList()
+        output = self.num_classes
+        for i in reversed(range(self.latent_levels)):
+            input = self.num_filters[i + self.lvl_diff]
+            self.s_layer.append(Conv2DSequence(input_dim=input, output_dim=output, depth=1, kernel=1,
+                                               activation=torch.nn.Identity, norm=torch.nn.Identity))
+
+    def forward(self, z):
+        """z: list of latent tensors [B,2,r,r] fp32 (index = latent level) -> list of full-resolution logits."""
+        s = [None] * self.latent_levels
+        post_z = [None] * self.latent_levels
+        post_c = [None] * self.latent_levels
+        for i in range(self.latent_levels):
+            assert z[-i - 1].shape[1] == 2
+            assert z[-i - 1].shape[2] == self.image_size[1] * 2 ** (-self.resolution_levels + 1 + i)
+            x = self.likelihood_ups_path[i](ops.to_act(z[-i - 1]))
+            x = self.likelihood_post_ups_path[i](x)
+            assert x.t.shape[1] == self.image_size[1] * 2 ** (-self.latent_levels + i + 1)
+            assert x.c == self.num_filters[-i - 1 - self.lvl_diff], '{} != {}'.format(x.c, self.num_filters[-i - 1])
+            post_z[-i - 1] = x
+        post_c[self.latent_levels - 1] = post_z[self.latent_levels - 1]
+        for i in reversed(range(self.latent_levels - 1)):
+            below = post_c[i + 1]
+            assert post_z[i].t.shape[1] == 2 * below.t.shape[1] and post_z[i].t.shape[2] == 2 * below.t.shape[2]
+            # bilinear x2 of the level below written straight into the concat buffer (no intermediate tensor)
+            concat = Act(ops.Concat.apply(post_z[i].t, below.t, False, True, True), post_z[i].c + below.c)
+            post_c[i] = self.likelihood_post_c_path[i](concat)
+        for i, block in enumerate(self.s_layer):
+            feat = post_c[-i - 1]
+            conv = block.convolution[0].convolution[0]
+            factor = self.image_size[1] // feat.t.shape[1]
+            assert factor * feat.t.shape[1] == self.image_size[1] and factor * feat.t.shape[2] == self.image_size[2]
+            s[-i - 1] = ops.SLayerNearest.apply(feat.t, conv.weight, conv.bias, factor)
+        return s
+
+
+class PHISeg(nn.Module):
+    """PHiSeg (https://arxiv.org/abs/1906.04045) behind the reference's module API (models/phiseg.py:326-537)."""
+
+    def __init__(self, input_channels, num_classes, num_filters, latent_levels=5, latent_dim=2, initializers=None,
+                 no_convs_fcomb=4, beta=10.0, image_size=(128, 128, 1), reversible=False, apply_last_layer=True,
+                 exponential_weighting=True, padding=True):
+        super(PHISeg, self).__init__()
+        self.input_channels = input_channels
+        self.num_classes = num_classes
+        self.num_filters = num_filters
+        self.latent_levels = latent_levels
+        self.image_size = image_size
+        self.loss_tot = 0
+        self.loss_dict = {}
+        self.kl_divergence_loss_weight = 1.0
+        self.beta = 1.0
+        self.padding = padding
+        self.activation_maps = []
+        self.apply_last_layer = apply_last_layer
+        self.exponential_weighting = exponential_weighting
+        self.exponential_weight = 4
+        self.residual_multinoulli_loss_weight = 1.0
+        self.kl_divergence_loss = 0
+        self.reconstruction_loss = 0
+
+        self.posterior = Posterior(input_channels, num_classes, num_filters, initializers=None, padding=True,
+                                   reversible=reversible)
+        self.likelihood = Likelihood(input_channels, num_classes, num_filters, initializers=None,
+                                     apply_last_layer=True, padding=True, image_size=self.image_size,
+                                     reversible=reversible)
+        self.prior = Posterior(input_channels, num_classes, num_filters, initializers=None, padding=True,
+                               is_posterior=False, reversible=reversible)
+        self.s_out_list = [None] * self.latent_levels
+        self.s_out_list_with_softmax = [None] * self.latent_levels
+
+    # ---------------------------------------------------------------- sampling
+    def sample_posterior(self):
+        z_sample = [None] * self.latent_levels
+        for i, _ in enumerate(z_sample):
+            z_sample[i] = self.posterior_mu[i] + self.posterior_sigma[i] * torch.randn_like(self.posterior_sigma[i])
+        return z_sample
+
+    def sample_prior(self):
+        z_sample = [None] * self.latent_levels
+        for i, _ in enumerate(z_sample):
+            z_sample[i] = self.prior_mu[i] + self.prior_sigma[i] * torch.randn_like(self.prior_sigma[i])
+        return z_sample
+
+    def sample(self, testing=True):
+        if testing:
+            sample, _ = self.reconstruct(self.sample_prior(), use_softmax=False)
+            return sample
+        else:
+            raise NotImplementedError
+
+    def reconstruct(self, z_posterior, use_softmax=True):
+        layer_recon = self.likelihood(z_posterior)
+        return self.accumulate_output(layer_recon, use_softmax=use_softmax), layer_recon
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, patch, mask, training=True):
+        if training:
+            self.posterior_latent_space, self.posterior_mu, self.posterior_sigma = self.posterior(patch, mask)
+            self.prior_latent_space, self.prior_mu, self.prior_sigma = self.prior(
+                patch, training_prior=True, z_list=self.posterior_latent_space)
+            self.s_out_list = self.likelihood(self.posterior_latent_space)
+        else:
+            self.posterior_latent_space, self.posterior_mu, self.posterior_sigma = self.posterior(patch, mask)
+            self.prior_latent_space, self.prior_mu, self.prior_sigma = self.prior(patch, training_prior=False)
+            self.s_out_list = self.likelihood(self.prior_latent_space)
+        return self.s_out_list
+
+    def accumulate_output(self, output_list, use_softmax=False):
+        """s_accum = output_list[-1]; s_accum += output_list[i] -- IN PLACE like the reference (quirk Q2)."""
+        s_accum = output_list[-1]
+        if torch.is_grad_enabled() and any(t.requires_grad for t in output_list):
+            # autograd-tracked corner (sample() during training): same aliasing through torch's in-place add
+            for i in range(len(output_list) - 1):
+                s_accum += output_list[i]
+            return torch.nn.functional.softmax(s_accum, dim=1) if use_softmax else s_accum
+        lst = [t.contiguous() for t in output_list]
+        if lst[-1].data_ptr() != output_list[-1].data_ptr():
+            raise RuntimeError('accumulate_output needs a contiguous last element to accumulate in place')
+        if use_softmax:
+            # the sum must stay in output_list[-1] (validate() calls loss() on the mutated list); softmax is a new tensor
+            kern.accumulate_output(lst, False, lst[-1])
+            out = torch.empty_like(lst[-1])
+            return kern.accumulate_output([lst[-1]], True, out)
+        return kern.accumulate_output(lst, False, lst[-1])
+
+    # ---------------------------------------------------------------- losses
+    def KL_two_gauss_with_diag_cov(self, mu0, sigma0, mu1, sigma1):
+        return ops.KLLevel.apply(mu0, sigma0, mu1, sigma1, 1.0)
+
+    def calculate_hierarchical_KL_div_loss(self):
+        if self.exponential_weighting:
+            level_weights = [self.exponential_weight ** i for i in list(range(self.latent_levels))]
+        else:
+            level_weights = [1] * self.latent_levels
+        for ii in reversed(range(self.latent_levels)):
+            self.loss_dict['KL_divergence_loss_lvl%d' % ii] = ops.KLLevel.apply(
+                self.posterior_mu[ii], self.posterior_sigma[ii], self.prior_mu[ii], self.prior_sigma[ii],
+                float(level_weights[ii]))
+            self._loss_add(self.kl_divergence_loss_weight * self.loss_dict['KL_divergence_loss_lvl%d' % ii])
+        return self.loss_tot
+
+    def _loss_add(self, term):
+        # ``self.loss_tot += tensor``: an int on the first add (new tensor), in place afterwards -- which is what
+        # makes kl_divergence_loss, reconstruction_loss and the returned loss ONE tensor in the reference (quirk Q1)
+        if torch.is_tensor(self.loss_tot):
+            self.loss_tot += term
+        else:
+            self.loss_tot = self.loss_tot + term
+
+    def multinoulli_loss(self, reconstruction, target):
+        total, _ = ops.ResidualCE.apply(target, reconstruction)
+        return total
+
+    def residual_multinoulli_loss(self, reconstruction, target):
+        total, levels = ops.ResidualCE.apply(target, *reconstruction)
+        for ii in range(self.latent_levels):
+            self.loss_dict['residual_multinoulli_loss_lvl%d' % ii] = levels[ii]
+        self.s_accumulated = [None] * self.latent_levels     # the level sums live only inside the fused kernel
+        self._loss_add(self.residual_multinoulli_loss_weight * total)
+        return self.loss_tot
+
+    def kl_divergence(self):
+        return self.calculate_hierarchical_KL_div_loss()
+
+    def elbo(self, segm, reconstruct_posterior_mean=False):
+        self.loss_tot = 0
+        self.kl_divergence_loss = self.kl_divergence()
+        self.reconstruction_loss = self.residual_multinoulli_loss(reconstruction=self.s_out_list, target=segm)
+        return self.loss_tot
+
+    def loss(self, segm):
+        return self.elbo(segm)

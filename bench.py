@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 hot path: PHiSeg-7/5 LIDC-128^2 training images/s (BASELINE.json metric), with
+GED-100 evaluation images/s, the tensor-core roofline of the conv kernels and the reference's CPU path beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # one process per GPU (torchrun for N > 1)
+    python bench.py --impl reference ...                      # the reference algorithm on the host cores (oracle port)
+
+One "step" = forward(training=True) + loss + backward + Adam.step on one synthetic LIDC-shaped batch of 12 images
+per GPU (reference train_model.py:101-122, models/experiments/phiseg_7_5_12.py).  `value` is timed with the batch
+resident in HBM (CUDA-graph replay of the whole step); `e2e` goes through the public TrainStep.step_host call with
+pinned host buffers: H2D of the batch and D2H of the loss inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'unet-zoo_b200')
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+FILTERS = [32, 64, 128, 192, 192, 192, 192]       # models/experiments/phiseg_7_5_12.py:13
+BATCH = 12                                         # per GPU (phiseg_7_5_12.py:30)
+IMAGE = (1, 128, 128)
+N_SAMPLES = 100                                    # GED-100 (BASELINE.json configs[3])
+ANNOTATORS = 4
+METRIC = 'PHiSeg-7/5 LIDC-128^2 train images/s'
+
+
+def conv_forward_flops_per_image(net, hw=128):
+    """Algorithmic conv FLOPs of one training forward per image: 2*Cout*H*W*Cin*k^2 per conv, counted on the
+    modules forward(training=True) runs (posterior + prior + likelihood; SURVEY.md 8d: 33.465 GFLOP for PHiSeg-7/5)."""
+    import torch.nn as nn
+    total = 0
+    res = {}
+
+    def level_of(name):
+        # resolution of each conv follows from the module path
+        parts = name.split('.')
+        if parts[1] == 'contracting_path':
+            return hw >> int(parts[2])
+        if parts[1] == 'upsampling_path':                       # index i-1 used at latent level 4-i
+            i = int(parts[2]) + 1
+            return hw >> (4 - i + 2)
+        if parts[1] == 'sample_z_path':
+            return hw >> (4 - int(parts[2]) + 2)
+        if parts[1] == 'likelihood_ups_path':
+            return hw >> (4 - int(parts[2]) + 2)
+        if parts[1] == 'likelihood_post_ups_path':
+            lvl = 4 - int(parts[2])
+            base = hw >> (lvl + 2)
+            return base * (2 if parts[3] == '1' else 4)
+        if parts[1] == 'likelihood_post_c_path':
+            return hw >> int(parts[2])
+        if parts[1] == 's_layer':
+            return hw >> (4 - int(parts[2]))
+        raise KeyError(name)
+
+    for name, m in net.named_modules():
+        if isinstance(m, nn.Conv2d):
+            if '.upsampling_path.4.' in name:                   # constructed but never called (phiseg.py:199)
+                continue
+            r = level_of(name)
+            total += 2 * m.out_channels * r * r * m.in_channels * m.kernel_size[0] * m.kernel_size[1]
+            res[name] = r
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.stop = threading.Event()
+        self.t = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) > 8:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def synthetic_batches(n_batches, seed):
+    from oracle import synth
+    out = []
+    for i in range(n_batches):
+        patch, labels, mask = synth.lidc_like_batch(BATCH, seed=seed + i)
+        out.append((patch.pin_memory(), mask.pin_memory(), labels))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- reference (CPU) arm
+def cpu_train_steps(steps, warmup, threads):
+    """The reference algorithm (oracle port, fp32, stock torch CPU ops + Adam) on the host cores: one step = one
+    B=12 training step of the same PHiSeg-7/5 configuration."""
+    from oracle import phiseg_oracle as po
+    from oracle import synth
+    from tests.keygrammar import phiseg_state_template
+    torch.set_num_threads(threads)
+    sd = synth.synth_state_dict(phiseg_state_template(FILTERS), seed=0)
+    params = [v.requires_grad_(True) for k, v in sd.items() if v.dtype == torch.float32 and 'running_' not in k]
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-5)
+    patch, labels, mask = synth.lidc_like_batch(BATCH, seed=100)
+    times = []
+    for it in range(warmup + steps):
+        eps = [torch.randn(s) for s in synth.phiseg_noise_shapes(BATCH)]
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = po.phiseg_forward(sd, patch, mask, eps, training=True)
+        loss = po.elbo(out, mask)['total']
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    times = cpu_train_steps(args.steps, max(args.warmup, 1), threads)
+    ms = 1000.0 * float(np.mean(times))
+    val = BATCH / (ms / 1000.0)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': max(args.warmup, 1), 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'PHiSeg-7/5 train step, LIDC-shaped 1x128x128, batch 12 (one bounded sample = one step)',
+                   'filters': FILTERS},
+        'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d timed B=12 training steps of the oracle port (torch CPU fp32, Adam)' % args.steps},
+        'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- B200 arm
+def timed_region(fn, steps, world, device):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def instrumented_conv_time(step, kern):
+    """Run one eager step with CUDA events around every tensor-core conv launch; returns per-kernel ms and counts."""
+    rec = {'conv_tc_kernel': [], 'wgrad_tc_kernel': []}
+    orig_f, orig_w = kern.conv_fwd, kern.conv_wgrad
+
+    def wrap(fn, key):
+        def inner(*a, **k):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            rec[key].append((e0, e1))
+            return out
+        return inner
+
+    kern.conv_fwd, kern.conv_wgrad = wrap(orig_f, 'conv_tc_kernel'), wrap(orig_w, 'wgrad_tc_kernel')
+    try:
+        step._body()
+        torch.cuda.synchronize()
+    finally:
+        kern.conv_fwd, kern.conv_wgrad = orig_f, orig_w
+    return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in rec.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-graph', action='store_true', help='time eager steps instead of CUDA-graph replay')
+    ap.add_argument('--skip-eval', action='store_true')
+    ap.add_argument('--skip-cpu', action='store_true')
+    args = ap.parse_args()
+
+    from b200 import dp as dpmod
+    if args.impl == 'reference':
+        rank = int(os.environ.get('RANK', '0'))
+        run_reference_arm(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the '
+                         'CPU arm)')
+    rank, world, local = dpmod.init_from_env('nccl')
+    device = torch.device('cuda', local)
+    from b200 import kern, train, _lib
+    from tests.keygrammar import dropin_phiseg
+    from oracle import synth
+
+    torch.manual_seed(1234 + rank)
+    net = dropin_phiseg(FILTERS)
+    net.load_state_dict(synth.synth_state_dict(net.state_dict(), seed=0))       # same weights on every rank
+    net = net.to(device)
+    opt = train.make_adam(net, capturable=True)
+    dp = dpmod.GradientAllReduce(net.parameters()) if world > 1 else None
+    step = train.TrainStep(net, opt, BATCH, IMAGE, use_graph=not args.no_graph, dp=dp, device=device)
+    batches = synthetic_batches(4, seed=1000 * (rank + 1))
+    step.patch.copy_(batches[0][0])
+    step.mask.copy_(batches[0][1])
+    step.prepare(warmup=3)
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step.step_device()
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput (value)
+    l0 = _lib.raw('uz_launch_count')()
+    with ClockSampler(local) as clk:
+        ms_total = timed_region(lambda i: step.step_device(), args.steps, world, device)
+    eager_launches = _lib.raw('uz_launch_count')() - l0
+    gpu_launches = step.launches_per_step * args.steps if step.graph is not None else eager_launches
+    ms_step = ms_total / args.steps
+    value = world * BATCH / (ms_step / 1000.0)
+
+    # ---- end to end through the public API (pinned host batch in, loss float out)
+    losses = []
+
+    def e2e_fn(i):
+        pb, mb, _ = batches[i % len(batches)]
+        losses.append(step.step_host(pb, mb))
+
+    for i in range(2):
+        e2e_fn(i)
+    ms_e2e = timed_region(e2e_fn, args.steps, world, device) / args.steps
+    e2e = {'value': world * BATCH / (ms_e2e / 1000.0), 'unit': 'images/s',
+           'h2d_bytes_per_step': int(batches[0][0].numel() * 4 + batches[0][1].numel() * 4), 'd2h_bytes_per_step': 4,
+           'ms_per_step': ms_e2e, 'api': 'b200.train.TrainStep.step_host (CUDA-graph replay)' if step.graph is not None
+           else 'b200.train.TrainStep.step_host (eager)'}
+
+    # ---- roofline of the tensor-core conv kernels: events around every launch of instrumented eager steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (measured)' if peaks else 'fallback 1.4 PFLOP/s sustained'
+    fwd_flops = conv_forward_flops_per_image(net, IMAGE[1])
+    conv_ms, conv_n = {}, {}
+    reps = 3
+    for _ in range(reps):
+        r = instrumented_conv_time(step, kern)
+        for k, (ms, n) in r.items():
+            conv_ms[k] = conv_ms.get(k, 0.0) + ms / reps
+            conv_n[k] = n
+    tc_ms = sum(conv_ms.values())
+    train_flops = 3.0 * fwd_flops * BATCH
+    achieved = train_flops / (tc_ms / 1000.0) / 1e12
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                'traffic': None, 'kernel': 'conv_tc_kernel (fwd + dgrad) + wgrad_tc_kernel',
+                'algorithmic_flops_per_step': train_flops, 'kernel_ms_per_step': tc_ms,
+                'launches_per_step': conv_n, 'ms_per_kernel_family': conv_ms, 'peak_source': peak_src,
+                'share_of_step': tc_ms / ms_step,
+                'how': 'CUDA events around every conv launch of %d instrumented eager steps; algorithmic FLOPs = 3 x '
+                       'forward conv FLOPs (SURVEY.md 8d)' % reps}
+
+    # ---- GED-100 evaluation throughput (N=100 samples of one image, 4 annotators), samples sharded over ranks
+    eval_block = None
+    if not args.skip_eval and world == 1:
+        ev = train.EvalStep(net, N_SAMPLES, 2)
+        labels = batches[0][2]
+        img = batches[0][0][0, 0].contiguous().pin_memory()
+        lab = labels[0].contiguous().pin_memory()
+        for _ in range(2):
+            ged, ncc = ev.run_host(img, lab)
+        k_eval = max(3, min(args.steps, 10))
+        t_ms = timed_region(lambda i: ev.run_host(img, lab), k_eval, world, device) / k_eval
+        eval_block = {'metric': 'PHiSeg GED-100 eval images/s (100 samples, 4 annotators, GED + NCC)',
+                      'value': 1000.0 / t_ms, 'unit': 'images/s', 'ms_per_image': t_ms, 'ged': ged, 'ncc': ncc,
+                      'path': 'EvalStep.run_host: H2D image+labels, forward(training=False) on 100 copies, '
+                              'accumulate_output(softmax), argmax, GED, NCC, D2H of two scalars'}
+        net.train()
+
+    # ---- the reference's CPU path beside it (rank 0, N = 1 only): bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        times = cpu_train_steps(3, 1, threads)
+        cpu_baseline = {'value': BATCH / float(np.mean(times)), 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                        'sample': '3 timed + 1 warm-up B=12 PHiSeg-7/5 training steps of the oracle port '
+                                  '(oracle/phiseg_oracle.py, torch CPU fp32 + Adam)'}
+
+    if rank == 0:
+        clocks = clk.summary()
+        act_mb = 15.0e6 * BATCH * 2 * 2 / 1e6      # ~15 M conv-output elements per image, y and a, bf16
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'data': 'synthetic',
+            'config': {'workload': 'PHiSeg-7/5 training step (forward+loss+backward+Adam), LIDC-shaped 1x128x128, '
+                                   '4 annotators, batch %d per GPU' % BATCH,
+                       'filters': FILTERS, 'global_batch': BATCH * world, 'parallelism': 'dp%d' % world,
+                       'cuda_graph': step.graph is not None,
+                       'l2': 'no flush needed: a step streams ~%.0f MB of activations (> 126 MB L2)' % act_mb,
+                       'loss_last': losses[-1] if losses else None},
+            'e2e': e2e, 'gpu_launches': int(gpu_launches), 'clocks': clocks, 'roofline': roofline,
+        }
+        if cpu_baseline is not None:
+            line['cpu_baseline'] = cpu_baseline
+        if eval_block is not None:
+            line['eval_ged100'] = eval_block
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -25,6 +25,8 @@ extern "C" {
 const char* uz_last_error(void);
 int uz_abi_version(void);
 int uz_device_sm_count(void);
+/* number of kernel launches issued by this library so far in this process (bench.py's gpu_launches) */
+long long uz_launch_count(void);
 
 /* ---- convolutions on tcgen05 tensor cores (conv_tc.cu, wgrad_tc.cu) ------------------------------------------------ */
 

@@ -61,57 +61,105 @@ def test_forward_and_losses(golden_dir, case, training):
           'argmax agreement vs fp32 %.5f' % (case, key, rel_emu, rel_ref, _rel(acc_emu, acc_ref), agree_ref))
     print('  loss cuda %.6g  emu %.6g  fp32 %.6g  golden(reference) %.6g' %
           (float(loss), float(e_emu['total']), float(e_ref['total']), float(g[key + '_loss'])))
-    # (a) same rounding points => only summation order / bf16 tie differences remain
-    assert rel_emu < 2e-2
+    # (a) same rounding points: what remains is summation order / bf16 ties -- which training-mode BatchNorm over as
+    #     few as 16 values per channel (2x2 level, batch 4) amplifies; the two ORACLES differ by the same amount
+    #     (printed above), so the bound is the bf16-storage envelope, not a kernel property.  Eval mode is tight.
+    tol = 8e-2 if training else 2e-2
+    assert rel_emu < tol
     for lvl in range(5):
-        assert _rel(net.prior_mu[lvl].cpu(), emu['prior_mu'][lvl]) < 2e-2
-        assert _rel(net.posterior_sigma[lvl].cpu(), emu['post_sigma'][lvl]) < 2e-2
-    assert float(loss) == pytest.approx(float(e_emu['total']), rel=2e-2)
-    # (b) reference arithmetic (fp32): bf16 storage through ~25 layers
-    assert rel_ref < 6e-2
-    assert float(loss) == pytest.approx(float(g[key + '_loss']), rel=6e-2)
-    assert agree_ref > 0.97
+        assert _rel(net.prior_mu[lvl].cpu(), emu['prior_mu'][lvl]) < tol
+        assert _rel(net.posterior_sigma[lvl].cpu(), emu['post_sigma'][lvl]) < tol
+    assert float(loss) == pytest.approx(float(e_emu['total']), rel=1e-2)
+    # (b) reference arithmetic (fp32) and the reference-generated fixture: bf16 storage through ~25 layers
+    assert rel_ref < (1e-1 if training else 2e-2)
+    assert float(loss) == pytest.approx(float(g[key + '_loss']), rel=1e-2)
+    assert agree_ref > (0.97 if training else 0.995)
+
+
+def _oracle_grads(sd, patch, mask, eps, bf16):
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    params = {k: v.requires_grad_(True) for k, v in sd2.items() if v.dtype == torch.float32 and 'running_' not in k}
+    out = po.phiseg_forward(sd2, patch, mask, eps, training=True, rnd=po.Rounding(bf16))
+    po.elbo(out, mask)['total'].backward()
+    return params
 
 
 def test_training_step_gradients(golden_dir):
+    """Gradients of one training step.  The synthetic random-weight network is ill-conditioned: merely rounding the
+    FORWARD activations to bf16 (oracle with Rounding(True), exact fp32 autograd backward) moves the median parameter
+    gradient by ~29 % rel-L2 from the fp32 oracle.  The kernel check is therefore against the oracle with the same
+    forward rounding; the distance to the fp32 (reference-arithmetic) gradients is asserted to be no worse than
+    that oracle's own."""
     g, net, sd, patch, mask, eps = _setup('phiseg_small', golden_dir)
     net.train(True)
     with injected_noise(eps):
         net.forward(patch.cuda(), mask.cuda(), training=True)
         loss = net.loss(mask.cuda())
     loss.backward()
-    # oracle gradients (fp32 == reference arithmetic)
-    sd2 = {k: v.clone() for k, v in sd.items()}
-    params = {k: v.requires_grad_(True) for k, v in sd2.items() if v.dtype == torch.float32 and 'running_' not in k}
-    out = po.phiseg_forward(sd2, patch, mask, eps, training=True)
-    po.elbo(out, mask)['total'].backward()
+    p_fp32 = _oracle_grads(sd, patch, mask, eps, False)
+    p_emu = _oracle_grads(sd, patch, mask, eps, True)
     named = dict(net.named_parameters())
     nograd = set(str(n) for n in g['train_nograd_names'])
-    worst = []
-    gmax = max(float(p.grad.norm()) for p in params.values() if p.grad is not None)
-    for n, p in params.items():
+    gmax = max(float(p.grad.norm()) for p in p_fp32.values() if p.grad is not None)
+    e_emu, e_fp32, o_gap = [], [], []
+    for n, p in p_fp32.items():
         if n in nograd:
             assert named[n].grad is None, n          # SURVEY.md 8e (3): never-used upsampling_path.4.*
             continue
         got = named[n].grad.cpu()
-        if n.endswith('convolution.0.bias') and (n[:-len('0.bias')] + '1.weight') in params:
+        if n.endswith('convolution.0.bias') and (n[:-len('0.bias')] + '1.weight') in p_fp32:
             assert float(got.abs().max()) == 0.0     # conv bias in front of BatchNorm: exactly zero by construction
             continue
-        ref = p.grad
-        if float(ref.norm()) < 1e-6 * gmax:
+        if float(p.grad.norm()) < 1e-6 * gmax:
             continue
-        worst.append((_rel(got, ref), n))
-    worst.sort(reverse=True)
-    print('\nworst gradient rel-L2 errors vs fp32 oracle:', worst[:5])
-    med = float(np.median([w for w, _ in worst]))
-    print('median %.3e' % med)
-    assert med < 5e-2
-    assert worst[0][0] < 0.35
+        e_emu.append((_rel(got, p_emu[n].grad), n))
+        e_fp32.append(_rel(got, p.grad))
+        o_gap.append(_rel(p_emu[n].grad, p.grad))
+    e_emu.sort(reverse=True)
+    med_emu, med_fp32, med_gap = (float(np.median([w for w, _ in e_emu])), float(np.median(e_fp32)),
+                                  float(np.median(o_gap)))
+    print('\nparameter-gradient rel-L2: cuda vs same-rounding oracle median %.3e (worst %s); cuda vs fp32 oracle median '
+          '%.3e; same-rounding oracle vs fp32 oracle median %.3e' % (med_emu, e_emu[:3], med_fp32, med_gap))
+    assert med_emu < 0.15
+    assert med_fp32 < 1.25 * med_gap + 0.02
     # running statistics were updated once, like nn.BatchNorm2d(momentum=0.01)
     k = 'posterior.contracting_path.3.layers.2.convolution.1.running_var'
     np.testing.assert_allclose(net.state_dict()[k].cpu().numpy(), g['train_running_var_probe'], rtol=2e-3)
     kk = 'posterior.contracting_path.3.layers.2.convolution.1.num_batches_tracked'
     assert int(net.state_dict()[kk]) == 4
+
+
+def test_likelihood_gradients_well_conditioned():
+    """Backward chain (wgrad, dgrad, BN/ReLU, upsample, concat, logits, CE) on the likelihood alone with fixed z:
+    batch 8, no 2x2 BatchNorm levels in the way -> close to the fp32 oracle."""
+    filters = [16, 32, 32, 32, 32, 32, 32]
+    net = dropin_phiseg(filters)
+    sd = synth.synth_state_dict(net.state_dict(), seed=4)
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    B = 8
+    patch, labels, mask = synth.lidc_like_batch(B, seed=2)
+    z = [t * 0.5 for t in synth.noise_list(synth.phiseg_noise_shapes(B)[:5], seed=9)][::-1]   # index = level
+    s = net.likelihood([t.cuda() for t in z])
+    loss = net.multinoulli_loss(sum(s), mask.cuda())
+    loss.backward()
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    params = {k: v.requires_grad_(True) for k, v in sd2.items() if k.startswith('likelihood.') and
+              v.dtype == torch.float32 and 'running_' not in k}
+    s_ref = po.likelihood(z, sd2, (128, 128), True)
+    loss_ref = po.multinoulli(sum(s_ref), mask)
+    loss_ref.backward()
+    assert float(loss) == pytest.approx(float(loss_ref), rel=5e-3)
+    named = dict(net.named_parameters())
+    gmax = max(float(p.grad.norm()) for p in params.values())
+    errs = sorted(((_rel(named[n].grad.cpu(), p.grad), n) for n, p in params.items()
+                   if float(p.grad.norm()) > 1e-5 * gmax and not (n.endswith('convolution.0.bias') and
+                                                                   (n[:-len('0.bias')] + '1.weight') in params)),
+                  reverse=True)
+    print('\nlikelihood-only gradient rel-L2 vs fp32 oracle: median %.3e worst %s' %
+          (float(np.median([e for e, _ in errs])), errs[:3]))
+    assert float(np.median([e for e, _ in errs])) < 3e-2
+    assert errs[0][0] < 0.15
 
 
 def test_accumulate_output_aliasing_and_sample(golden_dir):

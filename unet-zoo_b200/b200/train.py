@@ -1,0 +1,120 @@
+"""Step drivers around the drop-in modules: the reference's training step (train_model.py:101-122) and its
+N-sample evaluation (train_model.py:177-205) as reusable objects, optionally captured in a CUDA graph so the ~1.5 k
+kernel launches of a PHiSeg step are replayed without Python in the loop.
+
+The caller-visible semantics are the reference's: stock torch.optim.Adam(lr=1e-3, weight_decay=1e-5) on the fp32
+parameters, loss = net.loss(mask) after net.forward(patch, mask, training=True).
+"""
+import torch
+
+from . import _lib, kern
+
+
+def make_adam(net, capturable=True):
+    """train_model.py:49, with capturable=True so optimizer.step() can live inside a CUDA graph."""
+    return torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=capturable)
+
+
+class TrainStep:
+    """forward(training=True) -> loss -> zero_grad -> backward -> [gradient all-reduce] -> Adam.step."""
+
+    def __init__(self, net, optimizer, batch, image_size=(1, 128, 128), use_graph=True, dp=None, device=None):
+        self.net, self.opt, self.dp = net, optimizer, dp
+        self.device = device or torch.device('cuda', torch.cuda.current_device())
+        c, h, w = image_size
+        self.patch = torch.zeros((batch, c, h, w), dtype=torch.float32, device=self.device)
+        self.mask = torch.zeros((batch, 1, h, w), dtype=torch.float32, device=self.device)
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        self.graph = None
+        self.launches_per_step = None
+        self.use_graph = use_graph
+        net.train()
+
+    def _body(self):
+        if self.dp is not None:
+            self.dp.zero_grad()
+        else:
+            self.opt.zero_grad(set_to_none=True)
+        self.net.forward(self.patch, self.mask, training=True)
+        loss = self.net.loss(self.mask)
+        loss.backward()
+        if self.dp is not None:
+            self.dp.finish()
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def prepare(self, warmup=3):
+        """eager warm-up on a side stream (also sizes every lazily-set kernel attribute), then capture."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if self.dp is not None:
+            self.dp.freeze_buckets()
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.raw('uz_launch_count')()
+            with torch.cuda.graph(self.graph):
+                self._body()
+            self.launches_per_step = _lib.raw('uz_launch_count')() - n0
+        else:
+            n0 = _lib.raw('uz_launch_count')()
+            self._body()
+            self.launches_per_step = _lib.raw('uz_launch_count')() - n0
+        torch.cuda.synchronize()
+
+    def step_device(self):
+        """inputs already resident in self.patch / self.mask"""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+
+    def step_host(self, patch_pinned, mask_pinned):
+        """public end-to-end call: pinned host batch in, python float loss out (H2D + step + D2H)."""
+        self.patch.copy_(patch_pinned, non_blocking=True)
+        self.mask.copy_(mask_pinned, non_blocking=True)
+        self.step_device()
+        self.loss_host.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host)
+
+
+class EvalStep:
+    """One validation image like train_model.py:177-205: N copies -> forward(training=False) -> accumulate_output
+    (softmax) -> argmax -> GED + NCC against M annotators.  ``shard`` = (rank, world) splits the N samples."""
+
+    def __init__(self, net, n_samples=100, n_classes=2):
+        self.net = net
+        self.n = n_samples
+        self.n_classes = n_classes
+        net.eval()
+
+    @torch.no_grad()
+    def run_host(self, image_pinned, labels_pinned):
+        """image [H,W] fp32, labels [H,W,M] uint8 (host, pinned) -> (ged float, ncc float)"""
+        import utils  # the drop-in second boundary
+        dev = torch.device('cuda', torch.cuda.current_device())
+        img = image_pinned.to(dev, non_blocking=True)
+        lab = labels_pinned.to(dev, non_blocking=True)
+        return self.run_device(img, lab, utils)
+
+    @torch.no_grad()
+    def run_device(self, img, lab, utils=None):
+        if utils is None:
+            import utils
+        patch = img[None, None].repeat(self.n, 1, 1, 1)
+        masks = lab.permute(2, 0, 1).float()                       # [M,H,W]
+        mask = masks[0][None, None].repeat(self.n, 1, 1, 1)
+        s_list = self.net.forward(patch, mask, training=False)
+        probs = self.net.accumulate_output(s_list, use_softmax=True)
+        pred = kern.argmax_classes(probs)                          # torch.argmax(dim=1) of train_model.py:195
+        ged = utils.generalised_energy_distance(pred, masks, nlabels=self.n_classes - 1,
+                                                label_range=range(1, self.n_classes))
+        onehot = utils.convert_batch_to_onehot(masks.unsqueeze(1), nlabels=self.n_classes)
+        ncc = utils.variance_ncc_dist(probs, onehot)
+        return ged, float(ncc[0])

@@ -15,6 +15,7 @@ namespace uz {
 
 // last error text, readable through uz_last_error()
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define UZ_CHECK_ARG(cond, ...)                \
   do {                                         \
@@ -26,6 +27,7 @@ void set_error(const char* fmt, ...);
 
 #define UZ_CHECK_LAUNCH(name)                                                   \
   do {                                                                          \
+    uz::count_launch();                                                         \
     cudaError_t e__ = cudaGetLastError();                                       \
     if (e__ != cudaSuccess) {                                                   \
       uz::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \

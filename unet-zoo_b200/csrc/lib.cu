@@ -7,6 +7,7 @@
 
 namespace {
 thread_local char g_err[512] = "";
+long long g_launches = 0;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -28,6 +29,8 @@ int load_encode() {
 }  // namespace
 
 namespace uz {
+void count_launch() { ++g_launches; }
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -83,3 +86,5 @@ extern "C" const char* uz_last_error(void) { return g_err; }
 extern "C" int uz_abi_version(void) { return UZ_ABI_VERSION; }
 
 extern "C" int uz_device_sm_count(void) { return uz::num_sms(); }
+
+extern "C" long long uz_launch_count(void) { return g_launches; }

@@ -27,6 +27,10 @@ int uz_abi_version(void);
 int uz_device_sm_count(void);
 /* number of kernel launches issued by this library so far in this process (bench.py's gpu_launches) */
 long long uz_launch_count(void);
+/* profiling knobs for uz_conv_fwd (results become invalid): 1 = skip epilogue body, 2 = skip MMA issue,
+ * 4 = skip activation TMA loads, 8 = skip weight TMA loads, 32 = force the generic (non-persistent) kernel.
+ * 0 restores normal operation. */
+int uz_set_debug_flags(int flags);
 
 /* ---- convolutions on tcgen05 tensor cores (conv_tc.cu, wgrad_tc.cu) ------------------------------------------------ */
 
@@ -34,10 +38,15 @@ long long uz_launch_count(void);
  * num_tiles sizes the `stats_partial` buffer of uz_conv_fwd.  [host out-params] */
 int uz_conv_tile_geometry(int N, int H, int W, int* TW, int* TH, int* TN, int* num_tiles);
 
+/* Rows of the `stats_partial` buffer uz_conv_fwd will fill for this shape (persistent kernel: one per CTA; generic
+ * kernel: one per 128-pixel tile).  Pass the same number as `tiles` to uz_bn_finalize. */
+int uz_conv_stats_rows(int N, int H, int W, int Cin, int Cout, int taps);
+
 /* y[n,h,w,co] = act( scale[co] * sum_{tap,ci} x[n,h+dy,w+dx,ci] * w_packed[tap][co][ci] + shift[co] ), zero padding.
  * taps = 9 (3x3, pad 1) or 1 (1x1).  scale/shift may be NULL (1 / 0).  relu != 0 applies max(.,0).
  * stats_partial (optional) receives per-tile per-channel sum and sum of squares of the STORED bf16 outputs,
- * layout [num_tiles][2][Cout] fp32, for training-mode BatchNorm (reduced by uz_bn_finalize).
+ * layout [uz_conv_stats_rows()][2][Cout] fp32, for training-mode BatchNorm (reduced by uz_bn_finalize).
+ * w_packed taps are dx-major (t = kw*3 + kh) as produced by uz_pack_conv_weight.
  * Replaces: nn.Conv2d forward (torchlayers.py:18; models/unet.py:25-29; models/phiseg.py:28,32,57-58,91), fused with
  * the eval-mode BatchNorm + ReLU of torchlayers.py:20-21 or the bias + ReLU of models/unet.py:25-30; called with
  * dgrad-packed weights it is conv2d's input-gradient (autograd of the same call sites). */

@@ -129,16 +129,41 @@ def test_conv_wgrad_padded_channels():
 
 
 def test_pack_weight_layouts():
+    """packed taps are dx-major (t = kw*3 + kh); the dgrad copy is tap-flipped and channel-transposed."""
     k = kern()
     w = _rand(5, 3, 3, 3, seed=1)
     wf, wd = k.pack_conv_weight(w)
     assert wf.shape == (9, 16, 16) and wd.shape == (9, 16, 16)
     ref_f = torch.zeros(9, 16, 16, device=DEV)
-    ref_f[:, :5, :3] = bf16r(w).reshape(5, 3, 9).permute(2, 0, 1)
+    ref_f[:, :5, :3] = bf16r(w).permute(3, 2, 0, 1).reshape(9, 5, 3)
     assert torch.equal(wf.float(), ref_f)
     ref_d = torch.zeros(9, 16, 16, device=DEV)
-    ref_d[:, :3, :5] = bf16r(w).reshape(5, 3, 9).flip(2).permute(2, 1, 0)
+    ref_d[:, :3, :5] = ref_f[:, :5, :3].flip(0).permute(0, 2, 1)
     assert torch.equal(wd.float(), ref_d)
+
+
+def test_conv_persistent_kernel_matches_generic_kernel_at_baseline_size():
+    """BASELINE-size layer (batch 12, 128 -> 128 @ 128^2): the persistent 16x16-tile kernel and the generic 128-pixel
+    kernel (uz_set_debug_flags(32)) must agree to bf16 rounding, and both match torch on a sub-batch."""
+    from b200 import _lib
+    k = kern()
+    N, H, C = 12, 128, 128
+    x = bf16r(_rand(N, C, H, H, seed=1))
+    w = bf16r(_rand(C, C, 3, 3, seed=2, scale=(2.0 / (C * 9)) ** 0.5))
+    wf, _ = k.pack_conv_weight(w, need_dgrad=False)
+    xn = to_nhwc(x)
+    y2, p2 = k.conv_fwd(xn, wf, stats=True)
+    _lib.call('uz_set_debug_flags', 32)
+    try:
+        y1, p1 = k.conv_fwd(xn, wf, stats=True)
+    finally:
+        _lib.call('uz_set_debug_flags', 0)
+    assert p2.shape[0] <= 148 < p1.shape[0]
+    d = (y1.float() - y2.float()).abs()
+    assert float(d.max()) <= 2 ** -7 * float(y1.float().abs().max())
+    torch.testing.assert_close(p1.sum(0), p2.sum(0), rtol=1e-3, atol=1e-1)
+    ref = F.conv2d(x[:2], w, padding=1)
+    _assert_bf16_close(to_nchw(y2[:2].contiguous()), ref, 'persistent conv')
 
 
 @pytest.mark.parametrize('N,H,W,C', [(12, 16, 16, 64), (3, 32, 32, 192), (12, 2, 2, 192), (2, 64, 64, 32)])

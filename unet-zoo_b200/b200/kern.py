@@ -66,7 +66,7 @@ def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=Fa
     _, _, _, _, ldy = _check_act(out)
     partial = None
     if stats:
-        nt = conv_tile_geometry(n, h, w)[3]
+        nt = _lib.raw('uz_conv_stats_rows')(n, h, w, cin, cout, taps)
         partial = torch.empty((nt, 2, cout), dtype=torch.float32, device=x.device)
     _lib.call('uz_conv_fwd', _p(x), n, h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy, _p(scale), _p(shift),
               int(relu), _p(partial), _stream())

@@ -16,6 +16,13 @@
 #include "common.cuh"
 #include "unetzoo_b200.h"
 
+namespace uz {
+int g_conv_debug_flags = 0;
+int conv2_stats_rows(int N, int H, int W, int Cin, int Cout);
+int conv2_launch(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, void* y, int ldy,
+                 const float* scale, const float* shift, int relu, float* stats_partial, void* stream, int* handled);
+}  // namespace uz
+
 namespace {
 
 constexpr int kBlockM = 128;
@@ -37,6 +44,7 @@ struct ConvParams {
   const float* scale;  // [Cout] or nullptr (=1)
   const float* shift;  // [Cout] or nullptr (=0)
   float* stats;        // [tiles][2][Cout] or nullptr
+  int dbg;             // profiling knobs (uz_set_debug_flags): 1 = no epilogue body, 2 = no MMA, 4 = no A loads, 8 = no B loads
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -89,21 +97,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uz::tc_fence_before();
   __syncthreads();
   uz::tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tmem_base = uz::uniform_u32(tmem_base_slot);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    {
       for (int it = 0; it < k_iters; ++it) {
         const int s = it % p.stages;
         if (it >= p.stages) uz::mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
         const int tap = it / kblocks;
         const int kb = it - tap * kblocks;
         int dy = 0, dx = 0;
-        if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-        uz::mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
-        uz::tma_load_4d(smem_a + s * a_bytes, &tmap_x, &full_bar[s], kb * p.KC, x0 + dx, y0 + dy, n0);
-        uz::tma_load_3d(smem_b + s * b_bytes, &tmap_w, &full_bar[s], kb * p.KC, c_out0, tap);
+        if (p.taps == 9) { dx = tap / 3 - 1; dy = tap % 3 - 1; }   // packed taps are dx-major (see uz_pack_conv_weight)
+        if (uz::elect_one()) {
+          uz::mbar_expect_tx(&full_bar[s], ((p.dbg & 4) ? 0 : a_bytes) + ((p.dbg & 8) ? 0 : b_bytes));
+          if (!(p.dbg & 4)) uz::tma_load_4d(smem_a + s * a_bytes, &tmap_x, &full_bar[s], kb * p.KC, x0 + dx, y0 + dy, n0);
+          if (!(p.dbg & 8)) uz::tma_load_3d(smem_b + s * b_bytes, &tmap_w, &full_bar[s], kb * p.KC, c_out0, tap);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -114,10 +125,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int s = it % p.stages;
       uz::mbar_wait(&full_bar[s], (it / p.stages) & 1);
       uz::tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = uz::smem_u32(smem_a + s * a_bytes);
-        const uint32_t b_addr = uz::smem_u32(smem_b + s * b_bytes);
-        for (int k = 0; k < p.KC / 16; ++k) {
+      const uint32_t a_addr = uz::smem_u32(smem_a + s * a_bytes);
+      const uint32_t b_addr = uz::smem_u32(smem_b + s * b_bytes);
+      if (uz::elect_one()) {
+        for (int k = 0; k < ((p.dbg & 2) ? 0 : p.KC / 16); ++k) {
           const uint64_t adesc = uz::umma_desc(a_addr + k * 32, 16, sbo, swz);
           const uint64_t bdesc = uz::umma_desc(b_addr + k * 32, 16, sbo, swz);
           uz::tc_mma_f16(tmem_base, adesc, bdesc, idesc, (it | k) != 0);
@@ -136,7 +147,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     // staging buffer reuses the (now idle) operand stages: 128 rows x (BN*2 + 16) bytes
     const uint32_t pitch = p.BN * 2 + 16;
     uint8_t* stage_out = smem;
-    for (int c = 0; c < p.BN; c += 16) {
+    for (int c = 0; c < ((p.dbg & 1) ? 0 : p.BN); c += 16) {
       uint32_t r[16];
       uz::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       uz::tmem_ld_wait();
@@ -162,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int et = threadIdx.x - 64;              // 0..127
     const int box_px = p.TW * p.TH;
     int valid_n = p.N - n0; if (valid_n > p.TN) valid_n = p.TN;
-    const int valid_rows = valid_n * box_px;
+    const int valid_rows = (p.dbg & 1) ? 0 : valid_n * box_px;
 
     // coalesced store: consecutive threads write consecutive 16 B chunks of one pixel's channel vector
     const int chunks = p.BN / 8;
@@ -231,6 +242,12 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   UZ_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
                "uz_conv_fwd: pointers must be 16-byte aligned");
+  if (taps == 9 && !(uz::g_conv_debug_flags & 32)) {
+    int handled = 0;
+    int rc = uz::conv2_launch(x, N, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, stream,
+                              &handled);
+    if (rc || handled) return rc;
+  }
   ConvParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
   int tiles = 0;
@@ -249,6 +266,7 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   p.ldy = ldy; p.relu = relu;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.scale = scale; p.shift = shift; p.stats = stats_partial;
+  p.dbg = uz::g_conv_debug_flags;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(bn)) cols *= 2;
   p.tmem_cols = cols;
@@ -297,4 +315,19 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   conv_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tx, tw, p);
   UZ_CHECK_LAUNCH("uz_conv_fwd");
   return UZ_OK;
+}
+
+extern "C" int uz_set_debug_flags(int flags) {
+  uz::g_conv_debug_flags = flags;
+  return UZ_OK;
+}
+
+extern "C" int uz_conv_stats_rows(int N, int H, int W, int Cin, int Cout, int taps) {
+  if (taps == 9 && !(uz::g_conv_debug_flags & 32)) {
+    const int rows = uz::conv2_stats_rows(N, H, W, Cin, Cout);
+    if (rows > 0) return rows;
+  }
+  int tiles = 0;
+  if (uz_conv_tile_geometry(N, H, W, nullptr, nullptr, nullptr, &tiles)) return -1;
+  return tiles;
 }

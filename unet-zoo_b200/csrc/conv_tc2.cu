@@ -1,0 +1,433 @@
+// Persistent 3x3 convolution (pad 1) on tcgen05 tensor cores for feature maps with H, W multiples of 16.
+//
+// Second-generation kernel behind uz_conv_fwd (the generic conv_tc_kernel in conv_tc.cu keeps the small / odd shapes
+// and 1x1).  What profiling of the first kernel showed (profiles/r01_conv_v1_breakdown.md) and what this one does:
+//   * operand traffic L2->SM, not the tensor pipe, bounded the main loop (every tap re-read its 128-pixel box: 9x A).
+//       -> a work item is a 16x16-pixel tile (M = 256 = two 128-row accumulators sharing every weight tile) and a K step
+//          is (64- or 32-channel block, dx): ONE TMA box of 18 rows x 16 pixels shifted by dx lands as a halo slab;
+//          the three dy taps are MMAs on row-offset views of that slab (dy*16 rows = a whole number of swizzle atoms),
+//          so activations are read 3.4x instead of 9x and weights once per 256 pixels instead of once per 128.
+//   * ~8 us of fixed cost per CTA (launch, TMEM alloc, barrier setup) and a serial 6.6 us epilogue per 128x128 tile.
+//       -> persistent CTAs (one per SM) loop over work items; TMEM accumulators are double buffered when they fit so the
+//          epilogue of item i overlaps the MMAs of item i+1; the epilogue does no integer division and no global loads:
+//          scale/shift sit in shared memory, BatchNorm statistics are reduced in registers with a shuffle
+//          transpose-reduce, and the bf16 tile leaves through swizzled staging + TMA bulk tensor stores.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+#include "common.cuh"
+#include "unetzoo_b200.h"
+
+namespace uz {
+extern int g_conv_debug_flags;
+}
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 6;
+constexpr int kTile = 16;                 // 16 x 16 output pixels per work item
+constexpr int kSlabRows = (kTile + 2) * kTile;   // 18 image rows x 16 pixels
+
+struct Conv2Params {
+  int N, H, W, Cin, Cout;
+  int tilesW, tilesH, tiles;     // tiles per row / column / total (N * tilesH * tilesW)
+  int n_chunks, items;           // Cout / BN, tiles * n_chunks
+  int KC, BN, CW;                // channels per K step, output channels per item, channels per store box
+  int stages, nbuf;              // smem pipeline depth, TMEM accumulator buffers (1 or 2)
+  int relu;
+  uint32_t tmem_cols;
+  uint32_t stage_bytes, a_bytes, out_off;   // smem carve-up
+  const float* scale;
+  const float* shift;
+  float* stats;                  // [gridDim.x][2][Cout] or nullptr
+  int dbg;
+};
+
+__device__ __forceinline__ void tma_load_3d_box(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  uz::tma_load_3d(smem, m, bar, c0, c1, c2);
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(uz::smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// sum over the 32 lanes of v[j] for every j; afterwards lane l holds the total of column l in v[0]
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                const __grid_constant__ CUtensorMap tmap_y, const Conv2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_out = smem + p.out_off;                    // [BN/CW boxes][128 rows][CW*2 B], swizzled
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t acc_full[2];
+  __shared__ uint64_t acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_scale[256];
+  __shared__ float s_shift[256];
+  __shared__ float s_stats[4][2][256];                     // per epilogue warp: sum, sumsq per channel
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t rowb = KC * 2;                        // bytes per smem row = swizzle span
+  const int kblocks = p.Cin / KC;
+  const int k_steps = kblocks * 3;
+  // every CTA owns one output-channel chunk and a strided share of the tiles
+  const int chunk = blockIdx.x % p.n_chunks;
+  const int slot = blockIdx.x / p.n_chunks;
+  const int slots = gridDim.x / p.n_chunks;
+  const int c_out0 = chunk * p.BN;
+
+  if (warp == 0 && lane == 0) {
+    uz::tma_prefetch_desc(&tmap_x);
+    uz::tma_prefetch_desc(&tmap_w);
+    uz::tma_prefetch_desc(&tmap_y);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        uz::mbar_init(&full_bar[s], 1);
+        uz::mbar_init(&empty_bar[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        uz::mbar_init(&acc_full[b], 1);
+        uz::mbar_init(&acc_empty[b], 1);
+      }
+      uz::fence_barrier_init();
+    }
+    __syncwarp();
+    uz::tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  }
+  for (int c = threadIdx.x; c < p.BN; c += kThreads) {
+    s_scale[c] = p.scale ? p.scale[c_out0 + c] : 1.f;
+    s_shift[c] = p.shift ? p.shift[c_out0 + c] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 4 * 2 * 256; i += kThreads) (&s_stats[0][0][0])[i] = 0.f;
+  uz::tc_fence_before();
+  __syncthreads();
+  uz::tc_fence_after();
+  const uint32_t tmem_base = uz::uniform_u32(tmem_base_slot);
+
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
+    {
+      int stage = 0, phase = 0;
+      for (int tile = slot; tile < p.tiles; tile += slots) {
+        const int x0 = (tile % p.tilesW) * kTile;
+        const int y0 = ((tile / p.tilesW) % p.tilesH) * kTile;
+        const int n = tile / (p.tilesW * p.tilesH);
+        for (int ks = 0; ks < k_steps; ++ks) {
+          const int kb = ks / 3, dx = ks - kb * 3;
+          uz::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * p.stage_bytes;
+          if (uz::elect_one()) {
+            uz::mbar_expect_tx(&full_bar[stage],
+                               ((p.dbg & 4) ? 0 : p.a_bytes) + ((p.dbg & 8) ? 0 : p.stage_bytes - p.a_bytes));
+            if (!(p.dbg & 4)) uz::tma_load_4d(sa, &tmap_x, &full_bar[stage], kb * KC, x0 + dx - 1, y0 - 1, n);
+            if (!(p.dbg & 8)) tma_load_3d_box(sa + p.a_bytes, &tmap_w, &full_bar[stage], kb * KC, c_out0, dx * 3);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // Descriptors: the high words (SBO, version, swizzle mode) are loop invariant; only the 14-bit start-address field in
+    // the low word moves.  The 3 (dy) x 2 (half) x KC/16 MMAs of a K step are fully unrolled with compile-time offsets so
+    // ptxas gives every MMA its own uniform registers -- reusing one set serialises issue behind the previous MMA.
+    const uint32_t idesc = uz::umma_idesc_bf16(128, p.BN, 0, 0);
+    constexpr uint32_t sbo = 8 * rowb;
+    const uint64_t desc_hi = uz::umma_desc(0, 16, sbo, rowb) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = static_cast<uint32_t>(uz::umma_desc(0, 16, sbo, rowb) & 0xFFFFFFFFull);
+    const uint32_t b_tap_units = (p.BN * rowb) >> 4;
+    int stage = 0, phase = 0, acc_it = 0;
+    for (int tile = slot; tile < p.tiles; tile += slots, ++acc_it) {
+      const int buf = acc_it % p.nbuf;
+      const int acc_phase = (acc_it / p.nbuf) & 1;
+      uz::mbar_wait(&acc_empty[buf], acc_phase ^ 1);
+      uz::tc_fence_after();
+      const uint32_t d0 = tmem_base + buf * 2 * p.BN;
+      const uint32_t d1 = d0 + p.BN;
+      for (int ks = 0; ks < k_steps; ++ks) {
+        uz::mbar_wait(&full_bar[stage], phase);
+        uz::tc_fence_after();
+        {
+          const uint32_t a_lo = desc_lo0 + (uz::smem_u32(smem + stage * p.stage_bytes) >> 4);
+          const uint32_t b_lo = a_lo + (p.a_bytes >> 4);
+          if (!(p.dbg & 2) && uz::elect_one()) {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                  constexpr uint32_t kTileRowUnits = (kTile * rowb) >> 4;
+                  const uint64_t adesc = desc_hi | (a_lo + (dy + 8 * half) * kTileRowUnits + k * 2);
+                  const uint64_t bdesc = desc_hi | (b_lo + dy * b_tap_units + k * 2);
+                  const uint32_t acc = (dy == 0 && k == 0) ? static_cast<uint32_t>(ks != 0) : 1u;
+                  uz::tc_mma_f16(half ? d1 : d0, adesc, bdesc, idesc, acc);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (uz::elect_one()) {
+            uz::tc_commit(&empty_bar[stage]);
+            if (ks == k_steps - 1) uz::tc_commit(&acc_full[buf]);
+          }
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int ew = warp - 2;                   // 0..3, index into s_stats
+    const int row = q * 32 + lane;             // row of the 128-row half tile = pixel (y = row / 16, x = row % 16)
+    const int et = threadIdx.x - 64;
+    const uint32_t box_bytes = 128 * p.CW * 2;
+    const uint32_t cwb = p.CW * 2;             // bytes per staging row
+    // swizzle of the 16-byte chunk index inside a staging row (matches the TMA store tensor map)
+    const uint32_t xr = cwb == 128 ? (row & 7) : (cwb == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+    int acc_it = 0;
+    for (int tile = slot; tile < p.tiles; tile += slots, ++acc_it) {
+      const int buf = acc_it % p.nbuf;
+      const int acc_phase = (acc_it / p.nbuf) & 1;
+      const int x0 = (tile % p.tilesW) * kTile;
+      const int y0 = ((tile / p.tilesW) % p.tilesH) * kTile;
+      const int n = tile / (p.tilesW * p.tilesH);
+      uz::mbar_wait(&acc_full[buf], acc_phase);
+      uz::tc_fence_after();
+      for (int half = 0; half < 2; ++half) {
+        // staging buffer free? (previous TMA store has finished reading it)
+        if (et == 0) tma_store_wait_read();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!(p.dbg & 1)) {
+          for (int c = 0; c < p.BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 2 * p.BN + half * p.BN + c, r);
+            uz::tmem_ld_wait();
+            float v[32];
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ch = c + 2 * j;
+              float a = fmaf(__uint_as_float(r[2 * j]), s_scale[ch], s_shift[ch]);
+              float b = fmaf(__uint_as_float(r[2 * j + 1]), s_scale[ch + 1], s_shift[ch + 1]);
+              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              pk[j] = uz::pack_bf16x2(a, b);
+              v[2 * j] = uz::bf16lo(pk[j]);          // statistics of the values as stored
+              v[2 * j + 1] = uz::bf16hi(pk[j]);
+            }
+            // staging: box (c / CW), this thread's row, 16-byte chunks swizzled
+            {
+              const int cb = c / p.CW;
+              const int j0 = (c % p.CW) / 8;
+              uint8_t* rowp = smem_out + cb * box_bytes + row * cwb;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t chunk = static_cast<uint32_t>(j0 + j) ^ xr;
+                *reinterpret_cast<uint4*>(rowp + chunk * 16) =
+                    make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              }
+            }
+            if (p.stats) {
+              float sq[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+              const float s = transpose_reduce32(v, lane);
+              const float s2 = transpose_reduce32(sq, lane);
+              s_stats[ew][0][c + lane] += s;
+              s_stats[ew][1][c + lane] += s2;
+            }
+          }
+        }
+        // generic-proxy writes -> visible to the TMA (async proxy), then one thread issues the stores
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0 && !(p.dbg & 1)) {
+          for (int cb = 0; cb < p.BN / p.CW; ++cb)
+            tma_store_4d(&tmap_y, smem_out + cb * box_bytes, c_out0 + cb * p.CW, x0, y0 + 8 * half, n);
+          tma_store_commit();
+        }
+      }
+      // accumulator buffer drained -> hand it back to the MMA warp
+      uz::tc_fence_before();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) uz::mbar_arrive(&acc_empty[buf]);
+    }
+    if (et == 0) tma_store_wait_all();
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < 2 * p.Cout; i += 128) {
+        const int which = i / p.Cout, c = i - which * p.Cout - c_out0;
+        float t = 0.f;                         // channels of other chunks: zero rows keep uz_bn_finalize a plain sum
+        if (c >= 0 && c < p.BN)
+          t = (s_stats[0][which][c] + s_stats[1][which][c]) + (s_stats[2][which][c] + s_stats[3][which][c]);
+        p.stats[static_cast<size_t>(blockIdx.x) * 2 * p.Cout + i] = t;
+      }
+    }
+  }
+
+  uz::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    uz::tc_fence_after();
+    uz::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+struct Plan2 {
+  Conv2Params p;
+  int grid;
+  size_t smem;
+};
+
+bool make_plan2(int N, int H, int W, int Cin, int Cout, Plan2* out) {
+  if (H % kTile || W % kTile || Cin % 16 || Cout % 32 || Cout > 4096) return false;
+  Conv2Params& p = out->p;
+  p = Conv2Params{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.tilesW = W / kTile; p.tilesH = H / kTile;
+  p.tiles = N * p.tilesW * p.tilesH;
+  const int sms = uz::num_sms();
+  // output-channel chunking: whole Cout per item unless > 256 or too few items to occupy the SMs
+  int bn = Cout;
+  while (bn > 256) {
+    if (bn % 64) return false;
+    bn /= 2;
+  }
+  while (p.tiles * (Cout / bn) < sms && bn % 64 == 0 && bn >= 128) bn /= 2;
+  if (bn % 32) return false;
+  p.BN = bn;
+  p.n_chunks = Cout / bn;
+  p.items = p.tiles * p.n_chunks;
+  p.CW = (bn % 64 == 0) ? 64 : 32;
+  p.nbuf = (4 * bn <= 512) ? 2 : 1;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(p.nbuf * 2 * bn)) cols *= 2;
+  p.tmem_cols = cols;
+  const size_t out_bytes = static_cast<size_t>(128) * bn * 2;
+  const size_t budget = 214 * 1024;
+  int best_kc = 0, best_stages = 0;
+  for (int kc : {64, 32, 16}) {
+    if (Cin % kc) continue;
+    const size_t stage = static_cast<size_t>(kSlabRows + 3 * bn) * kc * 2;
+    int stages = static_cast<int>((budget - out_bytes) / stage);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages >= 2) { best_kc = kc; best_stages = stages; break; }
+  }
+  if (!best_kc) return false;
+  p.KC = best_kc;
+  p.stages = best_stages;
+  p.a_bytes = kSlabRows * best_kc * 2;
+  p.stage_bytes = (kSlabRows + 3 * bn) * best_kc * 2;
+  // stage sizes are multiples of 1024 B? slab: 288 rows * rowb (rowb >= 32) = 9216.. ok; weights 3*bn*rowb, bn % 32 == 0
+  if (p.a_bytes % 1024 || p.stage_bytes % 1024) return false;
+  p.out_off = p.stages * p.stage_bytes;
+  out->smem = p.out_off + out_bytes + 1024;
+  int slots = sms / p.n_chunks;
+  if (slots > p.tiles) slots = p.tiles;
+  if (slots < 1) return false;
+  out->grid = slots * p.n_chunks;
+  return true;
+}
+
+}  // namespace
+
+namespace uz {
+
+int conv2_stats_rows(int N, int H, int W, int Cin, int Cout) {
+  Plan2 pl;
+  if (!make_plan2(N, H, W, Cin, Cout, &pl)) return 0;
+  return pl.grid;
+}
+
+// returns UZ_OK and sets *handled = 1 when the persistent kernel took the launch
+int conv2_launch(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, void* y, int ldy,
+                 const float* scale, const float* shift, int relu, float* stats_partial, void* stream, int* handled) {
+  *handled = 0;
+  Plan2 pl;
+  if (!make_plan2(N, H, W, Cin, Cout, &pl)) return UZ_OK;
+  Conv2Params& p = pl.p;
+  p.scale = scale; p.shift = shift; p.relu = relu; p.stats = stats_partial;
+  p.dbg = g_conv_debug_flags;
+  const uint32_t swz = p.KC * 2;
+  CUtensorMap tx, tw, ty;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(W) * ldx * 2,
+                           static_cast<uint64_t>(H) * W * ldx * 2};
+    uint32_t box[4] = {static_cast<uint32_t>(p.KC), kTile, kTile + 2, 1};
+    int rc = make_tmap_bf16(&tx, x, 4, dims, strides, box, swz);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Cout), 9};
+    uint64_t strides[2] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Cout) * Cin * 2};
+    uint32_t box[3] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.BN), 3};
+    int rc = make_tmap_bf16(&tw, w_packed, 3, dims, strides, box, swz);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(N)};
+    uint64_t strides[3] = {static_cast<uint64_t>(ldy) * 2, static_cast<uint64_t>(W) * ldy * 2,
+                           static_cast<uint64_t>(H) * W * ldy * 2};
+    uint32_t box[4] = {static_cast<uint32_t>(p.CW), kTile, 8, 1};
+    int rc = make_tmap_bf16(&ty, y, 4, dims, strides, box, p.CW * 2);
+    if (rc) return rc;
+  }
+  auto kernel = p.KC == 64 ? conv_tc2_kernel<64> : (p.KC == 32 ? conv_tc2_kernel<32> : conv_tc2_kernel<16>);
+  static size_t attr_bytes[3] = {0, 0, 0};
+  size_t& ab = attr_bytes[p.KC == 64 ? 0 : (p.KC == 32 ? 1 : 2)];
+  if (pl.smem > ab) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("uz_conv_fwd(v2): cannot raise dynamic smem limit to %zu: %s", pl.smem, cudaGetErrorString(e));
+      return UZ_ERR_CUDA;
+    }
+    ab = pl.smem;
+  }
+  kernel<<<pl.grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream)>>>(tx, tw, ty, p);
+  UZ_CHECK_LAUNCH("uz_conv_fwd(v2)");
+  *handled = 1;
+  return UZ_OK;
+}
+
+}  // namespace uz

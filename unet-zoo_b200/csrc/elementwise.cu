@@ -30,9 +30,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------- weight packing
-// w fp32 [Cout][Cin][taps] (PyTorch OIHW flattened over kh,kw) ->
-//   fwd : bf16 [taps][CoutP][CinP]            wp[t][o][i]  = w[o][i][t]
-//   dgrad: bf16 [taps][CinP2][CoutP2]         wd[t][i][o]  = w[o][i][taps-1-t]   (flipped taps, transposed channels)
+// w fp32 [Cout][Cin][taps] (PyTorch OIHW flattened over kh,kw; source tap s = kh*3 + kw) ->
+//   fwd : bf16 [taps][CoutP][CinP]            wp[t][o][i]  = w[o][i][src(t)]
+//   dgrad: bf16 [taps][CinP2][CoutP2]         wd[t][i][o]  = w[o][i][src(taps-1-t)]   (flipped taps, transposed channels)
+// Packed taps are dx-major, t = kw*3 + kh, so the three dy taps of one dx are contiguous (one TMA box in conv_tc2).
+__device__ __forceinline__ int src_tap(int t, int taps) { return taps == 9 ? (t % 3) * 3 + t / 3 : t; }
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, __nv_bfloat16* wp,
                                    int CoutP, int CinP, __nv_bfloat16* wd, int CinP2, int CoutP2) {
   const size_t n_fwd = static_cast<size_t>(taps) * CoutP * CinP;
@@ -43,14 +45,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
       const int i = idx % CinP;
       const int o = (idx / CinP) % CoutP;
       const int t = idx / (static_cast<size_t>(CinP) * CoutP);
-      float v = (i < Cin && o < Cout) ? w[(static_cast<size_t>(o) * Cin + i) * taps + t] : 0.f;
+      float v = (i < Cin && o < Cout) ? w[(static_cast<size_t>(o) * Cin + i) * taps + src_tap(t, taps)] : 0.f;
       wp[idx] = __float2bfloat16(v);
     } else {
       const size_t j = idx - n_fwd;
       const int o = j % CoutP2;
       const int i = (j / CoutP2) % CinP2;
       const int t = j / (static_cast<size_t>(CoutP2) * CinP2);
-      float v = (i < Cin && o < Cout) ? w[(static_cast<size_t>(o) * Cin + i) * taps + (taps - 1 - t)] : 0.f;
+      float v = (i < Cin && o < Cout) ? w[(static_cast<size_t>(o) * Cin + i) * taps + src_tap(taps - 1 - t, taps)] : 0.f;
       wd[j] = __float2bfloat16(v);
     }
   }

@@ -32,12 +32,13 @@ struct WgradParams {
   float* partial;           // [splits][taps][Cout][Cin]
 };
 
+template <int PIX>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                 const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t box_bytes = p.PIX * 128;                         // [PIX pixels][64 ch] bf16
+  constexpr uint32_t box_bytes = PIX * 128;                       // [PIX pixels][64 ch] bf16
   const uint32_t a_bytes = p.a_boxes * box_bytes;
   const uint32_t b_bytes = p.b_boxes * box_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -77,10 +78,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   uz::tc_fence_before();
   __syncthreads();
   uz::tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tmem_base = uz::uniform_u32(tmem_base_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       for (int it = 0; it < iters; ++it) {
         const int s = it % p.stages;
         if (it >= p.stages) uz::mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
@@ -95,33 +96,42 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
         uint8_t* sa = smem + s * stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        uz::mbar_expect_tx(&full_bar[s], stage_bytes);
-        for (int b = 0; b < p.a_boxes; ++b)
-          uz::tma_load_4d(sa + b * box_bytes, &tmap_dy, &full_bar[s], co0 + b * 64, x0, y0, n0);
-        for (int b = 0; b < p.b_boxes; ++b)
-          uz::tma_load_4d(sb + b * box_bytes, &tmap_x, &full_bar[s], b * 64, x0 + dx, y0 + dy, n0);
+        if (uz::elect_one()) {
+          uz::mbar_expect_tx(&full_bar[s], stage_bytes);
+          for (int b = 0; b < p.a_boxes; ++b)
+            uz::tma_load_4d(sa + b * box_bytes, &tmap_dy, &full_bar[s], co0 + b * 64, x0, y0, n0);
+          for (int b = 0; b < p.b_boxes; ++b)
+            uz::tma_load_4d(sb + b * box_bytes, &tmap_x, &full_bar[s], b * 64, x0 + dx, y0 + dy, n0);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    const uint32_t lbo = box_bytes;   // stride between 64-channel runs
-    const uint32_t sbo = 1024;        // 8 pixel rows x 128 B
+    // MN-major operands: 64-channel runs LBO = box_bytes apart, 8-pixel groups SBO = 1024 B apart.  High descriptor words
+    // are invariant; the PIX/16 K steps are unrolled so every MMA owns its uniform registers (see conv_tc2.cu).
+    const uint64_t desc_hi = uz::umma_desc(0, box_bytes, 1024, 128) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = static_cast<uint32_t>(uz::umma_desc(0, box_bytes, 1024, 128) & 0xFFFFFFFFull);
+    const int n0 = p.Cin < 256 ? p.Cin : 256;          // first N chunk
+    const int n1 = p.Cin - n0;                         // second N chunk (Cin in (256, 512]) or 0
+    const uint32_t idesc0 = uz::umma_idesc_bf16(128, n0, 1, 1);
+    const uint32_t idesc1 = uz::umma_idesc_bf16(128, n1 > 0 ? n1 : 16, 1, 1);
     for (int it = 0; it < iters; ++it) {
       const int s = it % p.stages;
       uz::mbar_wait(&full_bar[s], (it / p.stages) & 1);
       uz::tc_fence_after();
-      if (lane == 0) {
-        const int ti = it / ntaps;
-        const int tl = it - ti * ntaps;  // local tap index -> accumulator slot
-        const uint32_t a_addr = uz::smem_u32(smem + s * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
-        for (int ks = 0; ks < p.PIX / 16; ++ks) {
-          const uint64_t adesc = uz::umma_desc(a_addr + ks * 2048, lbo, sbo, 128);
-          for (int c = 0; c < p.Cin; c += 256) {
-            const int nn = (p.Cin - c) < 256 ? (p.Cin - c) : 256;
-            const uint64_t bdesc = uz::umma_desc(b_addr + (c / 64) * box_bytes + ks * 2048, lbo, sbo, 128);
-            const uint32_t idesc = uz::umma_idesc_bf16(128, nn, 1, 1);
-            uz::tc_mma_f16(tmem_base + tl * p.Cin + c, adesc, bdesc, idesc, (ti | ks) != 0);
-          }
+      const int ti = it / ntaps;
+      const int tl = it - ti * ntaps;  // local tap index -> accumulator slot
+      const uint32_t a_lo = desc_lo0 + (uz::smem_u32(smem + s * stage_bytes) >> 4);
+      const uint32_t b_lo = a_lo + (a_bytes >> 4);
+      const uint32_t dcol = tmem_base + tl * p.Cin;
+      if (uz::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < PIX / 16; ++ks) {
+          const uint64_t adesc = desc_hi | (a_lo + ks * (2048 >> 4));
+          const uint32_t acc = ks == 0 ? static_cast<uint32_t>(ti != 0) : 1u;
+          uz::tc_mma_f16(dcol, adesc, desc_hi | (b_lo + ks * (2048 >> 4)), idesc0, acc);
+          if (n1 > 0)
+            uz::tc_mma_f16(dcol + 256, adesc, desc_hi | (b_lo + 4 * (box_bytes >> 4) + ks * (2048 >> 4)), idesc1, acc);
         }
         uz::tc_commit(&empty_bar[s]);
         if (it == iters - 1) uz::tc_commit(&accum_bar);
@@ -271,9 +281,11 @@ extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, i
     rc = uz::make_tmap_bf16(&tx, x, 4, dims, strides, box, 128);
     if (rc) return rc;
   }
-  static size_t attr_bytes = 0;
+  auto kernel = pl.p.PIX == 128 ? wgrad_tc_kernel<128> : wgrad_tc_kernel<64>;
+  static size_t attr_bytes_pix[2] = {0, 0};
+  size_t& attr_bytes = attr_bytes_pix[pl.p.PIX == 128 ? 0 : 1];
   if (pl.smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       uz::set_error("uz_conv_wgrad: cannot raise dynamic smem limit to %zu: %s", static_cast<size_t>(pl.smem), cudaGetErrorString(e));
@@ -282,7 +294,7 @@ extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, i
     attr_bytes = pl.smem;
   }
   dim3 grid(pl.splits, pl.p.tap_groups * pl.co_blocks, 1);
-  wgrad_tc_kernel<<<grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream)>>>(tdy, tx, pl.p);
+  kernel<<<grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream)>>>(tdy, tx, pl.p);
   UZ_CHECK_LAUNCH("uz_conv_wgrad");
   const size_t total = static_cast<size_t>(Cout_logical) * Cin_logical * taps;
   int blocks = static_cast<int>((total + 255) / 256);

@@ -200,29 +200,23 @@ def timed_region(fn, steps, world, device):
     return ms
 
 
-def instrumented_conv_time(step, kern):
-    """Run one eager step with CUDA events around every tensor-core conv launch; returns per-kernel ms and counts."""
-    rec = {'conv_tc_kernel': [], 'wgrad_tc_kernel': []}
-    orig_f, orig_w = kern.conv_fwd, kern.conv_wgrad
-
-    def wrap(fn, key):
-        def inner(*a, **k):
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = fn(*a, **k)
-            e1.record()
-            rec[key].append((e0, e1))
-            return out
-        return inner
-
-    kern.conv_fwd, kern.conv_wgrad = wrap(orig_f, 'conv_tc_kernel'), wrap(orig_w, 'wgrad_tc_kernel')
-    try:
-        step._body()
-        torch.cuda.synchronize()
-    finally:
-        kern.conv_fwd, kern.conv_wgrad = orig_f, orig_w
-    return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in rec.items()}
+def kernel_family_time(make_step, steps, world, device, lib):
+    """In-situ GPU time of the tensor-core conv kernels inside the step: the SAME captured step is timed with CUDA
+    events (graph replay, like the headline number) once complete, once with uz_conv_fwd launches elided and once with
+    uz_conv_wgrad launches elided (uz_set_debug_flags 128 / 256); the differences are the kernel families' times.
+    Values computed by the elided variants are garbage, so the caller restores the weights afterwards."""
+    out = {}
+    for name, flag in (('all', 0), ('without conv_tc (fwd+dgrad)', 128), ('without wgrad_tc', 256)):
+        lib.call('uz_set_debug_flags', flag)
+        try:
+            st = make_step()
+            st.prepare(warmup=1)
+            for _ in range(2):
+                st.step_device()
+            out[name] = timed_region(lambda i: st.step_device(), steps, world, device) / steps
+        finally:
+            lib.call('uz_set_debug_flags', 0)
+    return out
 
 
 def main():
@@ -300,23 +294,7 @@ def main():
     peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (measured)' if peaks else 'fallback 1.4 PFLOP/s sustained'
     fwd_flops = conv_forward_flops_per_image(net, IMAGE[1])
-    conv_ms, conv_n = {}, {}
-    reps = 3
-    for _ in range(reps):
-        r = instrumented_conv_time(step, kern)
-        for k, (ms, n) in r.items():
-            conv_ms[k] = conv_ms.get(k, 0.0) + ms / reps
-            conv_n[k] = n
-    tc_ms = sum(conv_ms.values())
-    train_flops = 3.0 * fwd_flops * BATCH
-    achieved = train_flops / (tc_ms / 1000.0) / 1e12
-    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                'traffic': None, 'kernel': 'conv_tc_kernel (fwd + dgrad) + wgrad_tc_kernel',
-                'algorithmic_flops_per_step': train_flops, 'kernel_ms_per_step': tc_ms,
-                'launches_per_step': conv_n, 'ms_per_kernel_family': conv_ms, 'peak_source': peak_src,
-                'share_of_step': tc_ms / ms_step,
-                'how': 'CUDA events around every conv launch of %d instrumented eager steps; algorithmic FLOPs = 3 x '
-                       'forward conv FLOPs (SURVEY.md 8d)' % reps}
+    roofline = None      # filled after the evaluation block (the measurement overwrites the weights)
 
     # ---- GED-100 evaluation throughput (N=100 samples of one image, 4 annotators), samples sharded over ranks
     eval_block = None
@@ -334,6 +312,26 @@ def main():
                       'path': 'EvalStep.run_host: H2D image+labels, forward(training=False) on 100 copies, '
                               'accumulate_output(softmax), argmax, GED, NCC, D2H of two scalars'}
         net.train()
+
+    # ---- roofline of the tensor-core conv kernels, in situ (differential graph replays)
+    saved = {k: v.clone() for k, v in net.state_dict().items()}
+    fam = kernel_family_time(lambda: train.TrainStep(net, train.make_adam(net), BATCH, IMAGE, use_graph=True, dp=None,
+                                                     device=device), max(5, args.steps // 2), 1, device, _lib)
+    net.load_state_dict(saved)
+    t_all = fam['all']
+    t_conv = max(t_all - fam['without conv_tc (fwd+dgrad)'], 1e-6)
+    t_wgrad = max(t_all - fam['without wgrad_tc'], 1e-6)
+    tc_ms = t_conv + t_wgrad
+    train_flops = 3.0 * fwd_flops * BATCH
+    achieved = train_flops / (tc_ms / 1000.0) / 1e12
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                'traffic': None, 'kernel': 'conv_tc2_kernel / conv_tc_kernel (fwd + dgrad) + wgrad_tc_kernel',
+                'algorithmic_flops_per_step': train_flops, 'kernel_ms_per_step': tc_ms,
+                'ms_per_kernel_family': {'conv_tc (fwd+dgrad)': t_conv, 'wgrad_tc (+reduce)': t_wgrad},
+                'step_ms': fam, 'peak_source': peak_src, 'share_of_step': tc_ms / t_all,
+                'how': 'CUDA-event time of the captured step minus the same step with that kernel family elided '
+                       '(uz_set_debug_flags 128 / 256), single GPU without gradient all-reduce; algorithmic FLOPs = '
+                       '3 x forward conv FLOPs (SURVEY.md 8d)'}
 
     # ---- the reference's CPU path beside it (rank 0, N = 1 only): bounded sample
     cpu_baseline = None

@@ -47,6 +47,23 @@ struct ConvParams {
   int dbg;             // profiling knobs (uz_set_debug_flags): 1 = no epilogue body, 2 = no MMA, 4 = no A loads, 8 = no B loads
 };
 
+// sum over the 32 lanes of v[j], j < 16; afterwards lanes l and l + 16 hold the total of column l
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvParams p) {
@@ -62,6 +79,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   __shared__ uint64_t empty_bar[kMaxStages];
   __shared__ uint64_t accum_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_scale[256];
+  __shared__ float s_shift[256];
+  __shared__ float s_stats[4][2][256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,6 +113,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
     __syncwarp();
     uz::tmem_alloc(&tmem_base_slot, p.tmem_cols);
+  }
+  for (int c = threadIdx.x; c < p.BN; c += kThreads) {
+    s_scale[c] = p.scale ? p.scale[c_out0 + c] : 1.f;
+    s_shift[c] = p.shift ? p.shift[c_out0 + c] : 0.f;
   }
   uz::tc_fence_before();
   __syncthreads();
@@ -140,65 +164,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // One thread per output pixel (tile row).  No staging: each thread streams its pixel's channel vector to global
+    // memory as 16-byte stores (32 contiguous bytes per 16 channels = whole sectors); scale/shift come from shared
+    // memory; BatchNorm statistics are reduced across the 32 rows of a warp with a shuffle transpose-reduce.
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;                // tile row == output pixel index in the box
+    const int ew = warp - 2;
+    const int row = q * 32 + lane;
+    const int box_px = p.TW * p.TH;
+    const int xx = row % p.TW, yy = (row / p.TW) % p.TH, nn = row / box_px;
+    const bool valid = (n0 + nn) < p.N && !(p.dbg & 1);
+    const size_t pix = (static_cast<size_t>(n0 + nn) * p.H + (y0 + yy)) * p.W + (x0 + xx);
+    __nv_bfloat16* dst = p.y + pix * p.ldy + c_out0;
     uz::mbar_wait(&accum_bar, 0);
     uz::tc_fence_after();
-    // staging buffer reuses the (now idle) operand stages: 128 rows x (BN*2 + 16) bytes
-    const uint32_t pitch = p.BN * 2 + 16;
-    uint8_t* stage_out = smem;
     for (int c = 0; c < ((p.dbg & 1) ? 0 : p.BN); c += 16) {
       uint32_t r[16];
       uz::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       uz::tmem_ld_wait();
       uint32_t packed[8];
+      float v[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int ch = c_out0 + c + 2 * j;
-        float v0 = __uint_as_float(r[2 * j]);
-        float v1 = __uint_as_float(r[2 * j + 1]);
-        if (p.scale) { v0 *= __ldg(p.scale + ch); v1 *= __ldg(p.scale + ch + 1); }
-        if (p.shift) { v0 += __ldg(p.shift + ch); v1 += __ldg(p.shift + ch + 1); }
+        float v0 = fmaf(__uint_as_float(r[2 * j]), s_scale[c + 2 * j], s_shift[c + 2 * j]);
+        float v1 = fmaf(__uint_as_float(r[2 * j + 1]), s_scale[c + 2 * j + 1], s_shift[c + 2 * j + 1]);
         if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
         packed[j] = uz::pack_bf16x2(v0, v1);
+        v[2 * j] = valid ? uz::bf16lo(packed[j]) : 0.f;       // statistics of the stored values, valid rows only
+        v[2 * j + 1] = valid ? uz::bf16hi(packed[j]) : 0.f;
       }
-      uint4* dst = reinterpret_cast<uint4*>(stage_out + row * pitch + c * 2);
-      dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-      dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-    }
-    uz::tc_fence_before();
-    // named barrier over the 128 epilogue threads
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-
-    const int et = threadIdx.x - 64;              // 0..127
-    const int box_px = p.TW * p.TH;
-    int valid_n = p.N - n0; if (valid_n > p.TN) valid_n = p.TN;
-    const int valid_rows = (p.dbg & 1) ? 0 : valid_n * box_px;
-
-    // coalesced store: consecutive threads write consecutive 16 B chunks of one pixel's channel vector
-    const int chunks = p.BN / 8;
-    for (int idx = et; idx < valid_rows * chunks; idx += 128) {
-      const int rrow = idx / chunks;
-      const int ck = idx - rrow * chunks;
-      const int xx = rrow % p.TW;
-      const int yy = (rrow / p.TW) % p.TH;
-      const int nn = rrow / box_px;
-      const size_t pix = (static_cast<size_t>(n0 + nn) * p.H + (y0 + yy)) * p.W + (x0 + xx);
-      const uint4 v = *reinterpret_cast<const uint4*>(stage_out + rrow * pitch + ck * 16);
-      *reinterpret_cast<uint4*>(p.y + pix * p.ldy + c_out0 + ck * 8) = v;
+      if (valid) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+        d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+      if (p.stats) {
+        float sq[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+        const float s1 = transpose_reduce16(v, lane);
+        const float s2 = transpose_reduce16(sq, lane);
+        if (lane < 16) {
+          s_stats[ew][0][c + lane] = s1;
+          s_stats[ew][1][c + lane] = s2;
+        }
+      }
     }
     if (p.stats) {
-      // per-channel sum / sumsq over the valid rows of this tile (of the stored bf16 values)
-      for (int cp = et; cp < p.BN / 2; cp += 128) {
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        for (int rr = 0; rr < valid_rows; ++rr) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(stage_out + rr * pitch + cp * 4);
-          const float a = uz::bf16lo(v), b = uz::bf16hi(v);
-          s0 += a; s1 += b; q0 += a * a; q1 += b * b;
-        }
-        float* dst = p.stats + static_cast<size_t>(tile) * 2 * p.Cout + c_out0 + cp * 2;
-        dst[0] = s0; dst[1] = s1;
-        dst[p.Cout] = q0; dst[p.Cout + 1] = q1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = threadIdx.x - 64;
+      for (int i = et; i < 2 * p.BN; i += 128) {
+        const int which = i / p.BN, c = i - which * p.BN;
+        float t = 0.f;
+        if (!(p.dbg & 1))
+          t = (s_stats[0][which][c] + s_stats[1][which][c]) + (s_stats[2][which][c] + s_stats[3][which][c]);
+        p.stats[(static_cast<size_t>(tile) * 2 + which) * p.Cout + c_out0 + c] = t;
       }
     }
   }
@@ -242,6 +261,7 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   UZ_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
                "uz_conv_fwd: pointers must be 16-byte aligned");
+  if (uz::g_conv_debug_flags & 128) return UZ_OK;   // measurement knob: step time without the conv kernels
   if (taps == 9 && !(uz::g_conv_debug_flags & 32)) {
     int handled = 0;
     int rc = uz::conv2_launch(x, N, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, stream,
@@ -279,9 +299,8 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   if (stages > k_iters) stages = k_iters;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  size_t smem = stages * stage_bytes;
-  if (smem < out_bytes) smem = out_bytes;
-  smem += 1024;  // alignment slack
+  size_t smem = stages * stage_bytes + 1024;  // + alignment slack
+  (void)out_bytes;
 
   CUtensorMap tx, tw;
   {

@@ -14,6 +14,10 @@
 #include "common.cuh"
 #include "unetzoo_b200.h"
 
+namespace uz {
+extern int g_conv_debug_flags;
+}
+
 namespace {
 
 constexpr int kThreads = 192;
@@ -176,6 +180,189 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Second-generation weight-gradient kernel for 3x3 convs on feature maps with H % 8 == 0 and W % 16 == 0.
+// The generic kernel above re-loads the dy tile and a shifted x tile for every tap: 128 B of operands per tensor-core
+// cycle per SM, three times what L2 delivers.  Here a CTA owns (128 output channels, one dx, <= 128 input channels):
+// per 8x16-pixel tile it loads the dy tile ONCE and ONE x halo slab (10 rows x 16 pixels, shifted by dx); the three dy
+// taps are MMAs on row-offset views of the slab (MN-major operands: K = pixel rows, a dy shift is 16 rows = 2 swizzle
+// atoms).  Operand traffic drops to ~45 B per tensor-core cycle.  Three [128 x <=128] fp32 accumulators live in TMEM.
+struct Wgrad2Params {
+  int N, H, W, Cin, Cout;
+  int tilesW, tilesH, num_tiles;
+  int ci_chunks, co_blocks;
+  int a_boxes;
+  int stages;
+  float* partial;           // [splits][9][Cout][Cin]
+};
+
+constexpr int kW2Pix = 128;                 // 8 rows x 16 pixels
+constexpr uint32_t kW2ABox = kW2Pix * 128;  // dy box  [128 px][64 ch]
+constexpr uint32_t kW2BBox = 160 * 128;     // x slab  [10 rows x 16 px][64 ch]
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                 const Wgrad2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x, splits = gridDim.x;
+  // blockIdx.y -> (co block, dx, ci chunk)
+  const int cc = blockIdx.y % p.ci_chunks;
+  const int dx = (blockIdx.y / p.ci_chunks) % 3;
+  const int co0 = (blockIdx.y / (p.ci_chunks * 3)) * 128;
+  const int ci0 = cc * 128;
+  int nch = p.Cin - ci0; if (nch > 128) nch = 128;      // input channels of this CTA (multiple of 16)
+  const int b_boxes = (nch + 63) / 64;
+  const uint32_t a_bytes = p.a_boxes * kW2ABox;
+  const uint32_t stage_bytes = a_bytes + 2 * kW2BBox;     // slab area sized for two boxes
+  const uint32_t tx_bytes = a_bytes + b_boxes * kW2BBox;
+  int my_tiles = 0;
+  if (split < p.num_tiles) my_tiles = (p.num_tiles - split + splits - 1) / splits;
+
+  if (warp == 0 && lane == 0) {
+    uz::tma_prefetch_desc(&tmap_dy);
+    uz::tma_prefetch_desc(&tmap_x);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        uz::mbar_init(&full_bar[s], 1);
+        uz::mbar_init(&empty_bar[s], 1);
+      }
+      uz::mbar_init(&accum_bar, 1);
+      uz::fence_barrier_init();
+    }
+    __syncwarp();
+    uz::tmem_alloc(&tmem_base_slot, 512);
+  }
+  uz::tc_fence_before();
+  __syncthreads();
+  uz::tc_fence_after();
+  const uint32_t tmem_base = uz::uniform_u32(tmem_base_slot);
+
+  if (warp == 0) {
+    int stage = 0, phase = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int tile = split + ti * splits;
+      const int x0 = (tile % p.tilesW) * 16;
+      const int y0 = ((tile / p.tilesW) % p.tilesH) * 8;
+      const int n = tile / (p.tilesW * p.tilesH);
+      uz::mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (uz::elect_one()) {
+        uint8_t* sa = smem + stage * stage_bytes;
+        uz::mbar_expect_tx(&full_bar[stage], tx_bytes);
+        for (int b = 0; b < p.a_boxes; ++b)
+          uz::tma_load_4d(sa + b * kW2ABox, &tmap_dy, &full_bar[stage], co0 + b * 64, x0, y0, n);
+        for (int b = 0; b < b_boxes; ++b)
+          uz::tma_load_4d(sa + a_bytes + b * kW2BBox, &tmap_x, &full_bar[stage], ci0 + b * 64, x0 + dx - 1, y0 - 1, n);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint64_t a_hi = uz::umma_desc(0, kW2ABox, 1024, 128) & 0xFFFFFFFF00000000ull;
+    const uint32_t a_lo0 = static_cast<uint32_t>(uz::umma_desc(0, kW2ABox, 1024, 128) & 0xFFFFFFFFull);
+    const uint64_t b_hi = uz::umma_desc(0, kW2BBox, 1024, 128) & 0xFFFFFFFF00000000ull;
+    const uint32_t b_lo0 = static_cast<uint32_t>(uz::umma_desc(0, kW2BBox, 1024, 128) & 0xFFFFFFFFull);
+    const uint32_t idesc = uz::umma_idesc_bf16(128, nch, 1, 1);
+    int stage = 0, phase = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      uz::mbar_wait(&full_bar[stage], phase);
+      uz::tc_fence_after();
+      const uint32_t sa = uz::smem_u32(smem + stage * stage_bytes);
+      const uint32_t a_lo = a_lo0 + (sa >> 4);
+      const uint32_t b_lo = b_lo0 + ((sa + a_bytes) >> 4);
+      if (uz::elect_one()) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+          for (int ks = 0; ks < kW2Pix / 16; ++ks) {
+            const uint32_t acc = ks == 0 ? static_cast<uint32_t>(ti != 0) : 1u;
+            uz::tc_mma_f16(tmem_base + dy * 128, a_hi | (a_lo + ks * 128), b_hi | (b_lo + (dy + ks) * 128), idesc, acc);
+          }
+        }
+        uz::tc_commit(&empty_bar[stage]);
+        if (ti == my_tiles - 1) uz::tc_commit(&accum_bar);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    if (my_tiles > 0) {
+      uz::mbar_wait(&accum_bar, 0);
+      uz::tc_fence_after();
+    }
+    for (int dy = 0; dy < 3; ++dy) {
+      const int tap = dy * 3 + dx;      // OIHW order kh*3 + kw
+      float* dst = p.partial + ((static_cast<size_t>(split) * 9 + tap) * p.Cout + co) * p.Cin + ci0;
+      for (int c = 0; c < nch; c += 16) {
+        uint32_t r[16];
+        if (my_tiles > 0) {
+          uz::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + dy * 128 + c, r);
+          uz::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        if (co < p.Cout) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3]));
+        }
+      }
+    }
+  }
+
+  uz::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    uz::tc_fence_after();
+    uz::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+struct Plan2 {
+  Wgrad2Params p;
+  int splits;
+  size_t smem;
+};
+
+bool make_plan2(int N, int H, int W, int Cin, int Cout, int taps, Plan2* out) {
+  if (taps != 9 || H % 8 || W % 16 || Cin % 16 || Cout % 16) return false;
+  if (uz::g_conv_debug_flags & 32) return false;
+  Wgrad2Params& p = out->p;
+  p = Wgrad2Params{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.tilesW = W / 16; p.tilesH = H / 8;
+  p.num_tiles = N * p.tilesW * p.tilesH;
+  p.ci_chunks = (Cin + 127) / 128;
+  p.co_blocks = (Cout + 127) / 128;
+  p.a_boxes = Cout > 64 ? 2 : 1;
+  const size_t stage_bytes = static_cast<size_t>(p.a_boxes) * kW2ABox + 2 * kW2BBox;
+  int stages = static_cast<int>((196 * 1024) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return false;
+  p.stages = stages;
+  out->smem = stages * stage_bytes + 1024;
+  const int per_split = p.co_blocks * 3 * p.ci_chunks;
+  int splits = uz::num_sms() / per_split;
+  if (splits > p.num_tiles) splits = p.num_tiles;
+  if (splits < 1) splits = 1;
+  out->splits = splits;
+  return true;
+}
+
 // dw[o][i][t] (+)= scale * sum_s partial[s][t][o][i]   (fixed order); also emits dbias[o] = sum_pixels dy when asked.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int CoutP, int CinP,
                                     int Cout, int Cin, float* dw) {
@@ -232,7 +419,7 @@ int make_plan(int N, int H, int W, int Cin, int Cout, int taps, Plan* out) {
   out->smem = stages * stage_bytes + 1024;
   out->co_blocks = (Cout + 127) / 128;
   const int per_split = p.tap_groups * out->co_blocks;
-  int splits = (2 * uz::num_sms() + per_split - 1) / per_split;
+  int splits = (uz::num_sms() + per_split - 1) / per_split;
   if (splits > p.num_tiles) splits = p.num_tiles;
   if (splits < 1) splits = 1;
   out->splits = splits;
@@ -242,6 +429,9 @@ int make_plan(int N, int H, int W, int Cin, int Cout, int taps, Plan* out) {
 }  // namespace
 
 extern "C" long long uz_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout, int taps) {
+  Plan2 pl2;
+  if (Cin > 0 && Cout > 0 && make_plan2(N, H, W, Cin, Cout, taps, &pl2))
+    return static_cast<long long>(pl2.splits) * taps * Cout * Cin;
   Plan pl;
   if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0 || Cin > 512 || make_plan(N, H, W, Cin, Cout, taps, &pl)) return -1;
   return static_cast<long long>(pl.splits) * taps * Cout * Cin;
@@ -256,6 +446,51 @@ extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, i
                "uz_conv_wgrad: channels must be multiples of 16, Cin <= 512 (got %d, %d)", Cin, Cout);
   UZ_CHECK_ARG(ldx % 8 == 0 && lddy % 8 == 0 && ldx >= Cin && lddy >= Cout, "uz_conv_wgrad: bad pixel strides");
   UZ_CHECK_ARG(Cin_logical <= Cin && Cout_logical <= Cout, "uz_conv_wgrad: logical dims exceed stored dims");
+  if (uz::g_conv_debug_flags & 256) return UZ_OK;   // measurement knob: step time without the wgrad kernels
+  Plan2 pl2;
+  if (make_plan2(N, H, W, Cin, Cout, taps, &pl2)) {
+    pl2.p.partial = workspace;
+    CUtensorMap tdy2, tx2;
+    {
+      uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                          static_cast<uint64_t>(N)};
+      uint64_t strides[3] = {static_cast<uint64_t>(lddy) * 2, static_cast<uint64_t>(W) * lddy * 2,
+                             static_cast<uint64_t>(H) * W * lddy * 2};
+      uint32_t box[4] = {64, 16, 8, 1};
+      int rc2 = uz::make_tmap_bf16(&tdy2, dy, 4, dims, strides, box, 128);
+      if (rc2) return rc2;
+    }
+    {
+      uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                          static_cast<uint64_t>(N)};
+      uint64_t strides[3] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(W) * ldx * 2,
+                             static_cast<uint64_t>(H) * W * ldx * 2};
+      uint32_t box[4] = {64, 16, 10, 1};
+      int rc2 = uz::make_tmap_bf16(&tx2, x, 4, dims, strides, box, 128);
+      if (rc2) return rc2;
+    }
+    static size_t attr2 = 0;
+    if (pl2.smem > attr2) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(pl2.smem));
+      if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        uz::set_error("uz_conv_wgrad(v2): cannot raise dynamic smem limit: %s", cudaGetErrorString(e));
+        return UZ_ERR_CUDA;
+      }
+      attr2 = pl2.smem;
+    }
+    dim3 grid2(pl2.splits, pl2.p.co_blocks * 3 * pl2.p.ci_chunks, 1);
+    wgrad_tc2_kernel<<<grid2, kThreads, pl2.smem, static_cast<cudaStream_t>(stream)>>>(tdy2, tx2, pl2.p);
+    UZ_CHECK_LAUNCH("uz_conv_wgrad(v2)");
+    const size_t total2 = static_cast<size_t>(Cout_logical) * Cin_logical * taps;
+    int blocks2 = static_cast<int>((total2 + 255) / 256);
+    if (blocks2 > uz::num_sms() * 8) blocks2 = uz::num_sms() * 8;
+    wgrad_reduce_kernel<<<blocks2, 256, 0, static_cast<cudaStream_t>(stream)>>>(workspace, pl2.splits, taps, Cout, Cin,
+                                                                               Cout_logical, Cin_logical, dw);
+    UZ_CHECK_LAUNCH("uz_conv_wgrad(v2 reduce)");
+    return UZ_OK;
+  }
   Plan pl;
   int rc = make_plan(N, H, W, Cin, Cout, taps, &pl);
   UZ_CHECK_ARG(rc == UZ_OK, "uz_conv_wgrad: no plan for Cin=%d Cout=%d", Cin, Cout);

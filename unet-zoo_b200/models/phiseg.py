@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from b200 import kern, ops
 from b200.ops import Act
-from torchlayers import Conv2D, Conv2DSequence, ReversibleSequence, _boundary
+from torchlayers import Conv2D, Conv2DSequence, ReversibleSequence, _boundary, deferred_batch_counts
 
 
 class DownConvolutionalBlock(nn.Module):
@@ -325,6 +325,10 @@ class PHISeg(nn.Module):
 
     # ---------------------------------------------------------------- forward
     def forward(self, patch, mask, training=True):
+        with deferred_batch_counts():
+            return self._forward(patch, mask, training)
+
+    def _forward(self, patch, mask, training=True):
         if training:
             self.posterior_latent_space, self.posterior_mu, self.posterior_sigma = self.posterior(patch, mask)
             self.prior_latent_space, self.prior_mu, self.prior_sigma = self.prior(

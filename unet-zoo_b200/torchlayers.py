@@ -13,6 +13,29 @@ from b200 import kern, ops
 from b200.ops import Act
 
 
+# BatchNorm.num_batches_tracked bookkeeping: inside ``deferred_batch_counts()`` the per-layer ``+= 1`` launches are
+# collected and applied with a single multi-tensor add when the context exits (106 launches -> 1 per PHiSeg forward).
+_deferred_counts = None
+
+
+class deferred_batch_counts:
+    def __enter__(self):
+        global _deferred_counts
+        self.prev = _deferred_counts
+        _deferred_counts = []
+        return self
+
+    def __exit__(self, *exc):
+        global _deferred_counts
+        counts, _deferred_counts = _deferred_counts, self.prev
+        if counts:
+            if self.prev is not None:
+                self.prev.extend(counts)
+            else:
+                torch._foreach_add_(counts, 1)
+        return False
+
+
 def _boundary(fn):
     """forward(x) wrapper: NCHW fp32 in -> NCHW fp32 out, Act in -> Act out."""
 
@@ -57,7 +80,9 @@ class Conv2D(nn.Module):
             if self.training:
                 t = ops.ConvBNAct.apply(x.t, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
                                         bn.running_var, relu, x.c)
-                if not getattr(self, '_defer_batch_count', False):
+                if _deferred_counts is not None:
+                    _deferred_counts.append(bn.num_batches_tracked)
+                else:
                     bn.num_batches_tracked.add_(1)
             else:
                 scale, shift = kern.bn_eval_fold(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)

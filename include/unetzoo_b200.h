@@ -71,6 +71,16 @@ int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, int N, int H
 int uz_pack_conv_weight(const float* w, int Cout, int Cin, int taps, void* w_fwd, int CoutP, int CinP, void* w_dgrad,
                         int CinP2, int CoutP2, void* stream);
 
+/* The same packing for every conv layer of a model in one launch.  descs_device: device array of n UzPackDesc (dgrad
+ * copy, if requested, has dims [taps][CinP][CoutP]).  grid = (blocks_per_layer, n). */
+typedef struct UzPackDesc {
+  const void* w;      /* fp32 OIHW */
+  void* w_fwd;        /* bf16 [taps][CoutP][CinP] */
+  void* w_dgrad;      /* bf16 [taps][CinP][CoutP] or NULL */
+  int Cout, Cin, taps, CoutP, CinP, reserved;
+} UzPackDesc;
+int uz_pack_conv_weights_batched(const void* descs_device, int n, int blocks_per_layer, void* stream);
+
 /* Training-mode BatchNorm statistics: reduce the conv's per-tile partials, emit scale = gamma*invstd and
  * shift = beta - mean*scale, save mean / invstd, update running stats (momentum, unbiased variance).
  * Replaces nn.BatchNorm2d(eps=1e-3, momentum=0.01) statistics, torchlayers.py:20. */

@@ -2,6 +2,7 @@
 [N, H, W, C] whose last-dim stride is 1 and whose pixel stride (stride(2)) may exceed C (channel slices of concat
 buffers); N/H/W must be densely packed over pixels."""
 import ctypes
+import struct
 
 import torch
 
@@ -44,8 +45,63 @@ def conv_tile_geometry(n, h, w):
     return tw.value, th.value, tn.value, nt.value
 
 
+class WeightPacker:
+    """Packs the fp32 OIHW weights of ALL tensor-core conv layers of a model into their bf16 forward / dgrad layouts
+    with ONE kernel launch per step (uz_pack_conv_weights_batched) instead of one per layer.  ``refresh()`` re-packs
+    when any weight changed (tensor version counters) -- every step in training, once in evaluation."""
+
+    def __init__(self, weights):
+        self.weights = [w for w in weights]
+        dev = self.weights[0].device
+        self.packed = {}
+        rows = []
+        self.max_elems = 0
+        for w in self.weights:
+            cout, cin = w.shape[0], w.shape[1]
+            taps = w.shape[2] * w.shape[3]
+            coutp, cinp = pad16(cout), pad16(cin)
+            wf = torch.empty((taps, coutp, cinp), dtype=torch.bfloat16, device=dev)
+            wd = torch.empty((taps, cinp, coutp), dtype=torch.bfloat16, device=dev)
+            self.packed[w.data_ptr()] = (wf, wd)
+            rows.append(struct.pack('<QQQiiiiii', w.data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, cin, taps, coutp,
+                                    cinp, 0))
+            self.max_elems = max(self.max_elems, 2 * taps * coutp * cinp)
+        raw = b''.join(rows)
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self.ptr0 = self.weights[0].data_ptr()
+        self.versions = None
+
+    def valid_for(self, weights_first):
+        return weights_first.data_ptr() == self.ptr0
+
+    def refresh(self, force=False):
+        versions = [w._version for w in self.weights]
+        if force or versions != self.versions:
+            blocks = min(64, max(1, (self.max_elems + 255) // 256 // 4))
+            _lib.call('uz_pack_conv_weights_batched', _p(self.table), len(self.weights), blocks, _stream())
+            self.versions = versions
+
+    def lookup(self, w):
+        return self.packed.get(w.data_ptr())
+
+
+_active_packer = None
+
+
+def set_active_packer(packer):
+    global _active_packer
+    prev = _active_packer
+    _active_packer = packer
+    return prev
+
+
 def pack_conv_weight(w, need_dgrad=True):
-    """w fp32 [Cout,Cin,kh,kw] -> (w_fwd bf16 [taps,CoutP,CinP], w_dgrad bf16 [taps,CinP,CoutP] or None)."""
+    """w fp32 [Cout,Cin,kh,kw] -> (w_fwd bf16 [taps,CoutP,CinP], w_dgrad bf16 [taps,CinP,CoutP] or None).
+    Inside a model forward the active WeightPacker already holds both (packed by one batched launch)."""
+    if _active_packer is not None:
+        hit = _active_packer.lookup(w)
+        if hit is not None:
+            return hit
     cout, cin = w.shape[0], w.shape[1]
     taps = w.shape[2] * w.shape[3]
     coutp, cinp = pad16(cout), pad16(cin)
@@ -370,3 +426,30 @@ def channel_sum(g):
     one = torch.ones(c, dtype=torch.float32, device=g.device)
     _lib.call('uz_bn_bwd_reduce', _p(g), ld, _p(g), ld, _p(one), _p(one), 0, npix, c, _p(partial), _stream())
     return partial[:, 0].sum(0)
+
+
+class ZeroArena:
+    """Zero-filled fp32 scratch handed out as views: gradients that are exactly zero by construction (conv bias in
+    front of BatchNorm) and zero-initialised accumulators share ONE fill per step instead of one launch each.
+    The memory is never written by this package; a fresh block is taken every step so stale views stay valid."""
+
+    def __init__(self, floats=1 << 16):
+        self.floats = floats
+        self.buf = None
+        self.off = 0
+
+    def reset(self):
+        self.buf = None
+        self.off = 0
+
+    def get(self, n, device):
+        n_al = (n + 3) // 4 * 4
+        if self.buf is None or self.buf.device != device or self.off + n_al > self.buf.numel():
+            self.buf = torch.zeros(max(self.floats, n_al), dtype=torch.float32, device=device)
+            self.off = 0
+        out = self.buf[self.off:self.off + n]
+        self.off += n_al
+        return out
+
+
+zero_arena = ZeroArena()

@@ -103,7 +103,7 @@ class ConvBNAct(torch.autograd.Function):
             dx, _ = kern.conv_fwd(dy, wd)
         cout, cin, kh, kw = ctx.wshape
         dw = kern.conv_wgrad(x, dy, kh * kw, cin, cout).view(cout, cin, kh, kw)
-        dbias = torch.zeros(cout, dtype=torch.float32, device=dy.device)
+        dbias = kern.zero_arena.get(cout, dy.device)
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None
 
 

@@ -58,6 +58,34 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
   }
 }
 
+// all conv layers of a model in ONE launch: blockIdx.y selects the layer descriptor (device table of UzPackDesc)
+__global__ void pack_weight_batched_kernel(const UzPackDesc* __restrict__ descs) {
+  const UzPackDesc d = descs[blockIdx.y];
+  const float* __restrict__ w = static_cast<const float*>(d.w);
+  __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(d.w_fwd);
+  __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d.w_dgrad);
+  const size_t n_fwd = static_cast<size_t>(d.taps) * d.CoutP * d.CinP;
+  const size_t n_bwd = wd ? n_fwd : 0;          // dgrad copy: [taps][CinP][CoutP]
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n_fwd + n_bwd;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    if (idx < n_fwd) {
+      const int i = idx % d.CinP;
+      const int o = (idx / d.CinP) % d.CoutP;
+      const int t = idx / (static_cast<size_t>(d.CinP) * d.CoutP);
+      float v = (i < d.Cin && o < d.Cout) ? w[(static_cast<size_t>(o) * d.Cin + i) * d.taps + src_tap(t, d.taps)] : 0.f;
+      wp[idx] = __float2bfloat16(v);
+    } else {
+      const size_t j = idx - n_fwd;
+      const int o = j % d.CoutP;
+      const int i = (j / d.CoutP) % d.CinP;
+      const int t = j / (static_cast<size_t>(d.CoutP) * d.CinP);
+      float v = (i < d.Cin && o < d.Cout)
+                    ? w[(static_cast<size_t>(o) * d.Cin + i) * d.taps + src_tap(d.taps - 1 - t, d.taps)] : 0.f;
+      wd[j] = __float2bfloat16(v);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- BatchNorm statistics
 // partial [tiles][2][C] (sum, sumsq per tile, written by the conv epilogue) -> per-channel scale/shift, saved
 // mean/invstd, running-stat update (momentum, unbiased variance) -- reference torchlayers.py:20, SURVEY Appendix A.
@@ -454,6 +482,14 @@ extern "C" int uz_pack_conv_weight(const float* w, int Cout, int Cin, int taps, 
                                                                  CoutP, CinP, static_cast<__nv_bfloat16*>(w_dgrad),
                                                                  CinP2, CoutP2);
   UZ_CHECK_LAUNCH("uz_pack_conv_weight");
+  return UZ_OK;
+}
+
+extern "C" int uz_pack_conv_weights_batched(const void* descs_device, int n, int blocks_per_layer, void* stream) {
+  UZ_CHECK_ARG(descs_device && n > 0 && blocks_per_layer > 0, "uz_pack_conv_weights_batched: bad arguments");
+  dim3 grid(blocks_per_layer, n, 1);
+  pack_weight_batched_kernel<<<grid, kEwThreads, 0, ST(stream)>>>(static_cast<const UzPackDesc*>(descs_device));
+  UZ_CHECK_LAUNCH("uz_pack_conv_weights_batched");
   return UZ_OK;
 }
 

@@ -324,9 +324,29 @@ class PHISeg(nn.Module):
         return self.accumulate_output(layer_recon, use_softmax=use_softmax), layer_recon
 
     # ---------------------------------------------------------------- forward
+    def _packer(self):
+        # one batched launch packs every conv weight (bf16 forward + dgrad layouts) per step
+        first = self.posterior.contracting_path[0].layers[0].convolution[0].weight
+        pk = getattr(self, '_weight_packer', None)
+        if pk is None or not pk.valid_for(first):
+            ws = [m.weight for m in self.modules()
+                  if isinstance(m, nn.Conv2d) and m.out_channels % 16 == 0 and m.weight.is_cuda]
+            pk = kern.WeightPacker(ws)
+            object.__setattr__(self, '_weight_packer', pk)
+        return pk
+
     def forward(self, patch, mask, training=True):
-        with deferred_batch_counts():
-            return self._forward(patch, mask, training)
+        if not patch.is_cuda:
+            raise kern._lib.UnetZooLibError('UNet-Zoo B200 modules need CUDA tensors: there is no CPU fallback path')
+        pk = self._packer()
+        pk.refresh()
+        kern.zero_arena.reset()
+        prev = kern.set_active_packer(pk)
+        try:
+            with deferred_batch_counts():
+                return self._forward(patch, mask, training)
+        finally:
+            kern.set_active_packer(prev)
 
     def _forward(self, patch, mask, training=True):
         if training:

@@ -362,10 +362,14 @@ def main():
         if eval_block is not None:
             line['eval_ged100'] = eval_block
         print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         import torch.distributed as dist
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        # captured graphs still reference the NCCL communicator: tearing the process group down can block, and there is
+        # nothing left to flush -- leave without running destructors
+        os._exit(0)
 
 
 if __name__ == '__main__':

@@ -206,3 +206,38 @@ def test_cpu_tensors_fail_loudly():
     patch, labels, mask = synth.lidc_like_batch(1, seed=1)
     with pytest.raises(RuntimeError):
         net.forward(patch, mask, training=True)
+
+
+def test_weights_are_repacked_after_an_optimizer_step(golden_dir):
+    """The bf16 packed copies must follow the fp32 parameters through torch's fused Adam (which does not bump tensor
+    version counters): two training steps must change the loss like the oracle's two steps do."""
+    from b200 import train
+    g, net, sd, patch, mask, eps = _setup('phiseg_small', golden_dir)
+    net.train(True)
+    opt = train.make_adam(net, capturable=False, fused=True)
+    losses = []
+    for it in range(3):
+        with injected_noise(eps):
+            net.forward(patch.cuda(), mask.cuda(), training=True)
+            loss = net.loss(mask.cuda())
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    # same three steps on the CPU oracle (fp32 reference arithmetic, stock Adam)
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    params = [v.requires_grad_(True) for k, v in sd2.items() if v.dtype == torch.float32 and 'running_' not in k]
+    opt2 = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-5)
+    ref = []
+    for it in range(3):
+        out = po.phiseg_forward(sd2, patch, mask, eps, training=True)
+        l = po.elbo(out, mask)['total']
+        opt2.zero_grad(set_to_none=True)
+        l.backward()
+        opt2.step()
+        ref.append(float(l))
+    print('\nlosses over 3 Adam steps: cuda %s  oracle %s' % (losses, ref))
+    assert losses[1] != losses[0] and losses[2] != losses[1]
+    for a, b in zip(losses, ref):
+        assert a == pytest.approx(b, rel=2e-2)
+    assert (losses[2] - losses[0]) == pytest.approx(ref[2] - ref[0], rel=0.35)

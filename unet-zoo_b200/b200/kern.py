@@ -47,8 +47,9 @@ def conv_tile_geometry(n, h, w):
 
 class WeightPacker:
     """Packs the fp32 OIHW weights of ALL tensor-core conv layers of a model into their bf16 forward / dgrad layouts
-    with ONE kernel launch per step (uz_pack_conv_weights_batched) instead of one per layer.  ``refresh()`` re-packs
-    when any weight changed (tensor version counters) -- every step in training, once in evaluation."""
+    with ONE kernel launch per forward (uz_pack_conv_weights_batched) instead of one per layer.  It always re-packs:
+    tensor version counters cannot be trusted to detect updates (torch's fused Adam writes parameters without bumping
+    them), and one ~30 us launch per forward is cheaper than a stale weight."""
 
     def __init__(self, weights):
         self.weights = [w for w in weights]
@@ -74,12 +75,9 @@ class WeightPacker:
     def valid_for(self, weights_first):
         return weights_first.data_ptr() == self.ptr0
 
-    def refresh(self, force=False):
-        versions = [w._version for w in self.weights]
-        if force or versions != self.versions:
-            blocks = min(64, max(1, (self.max_elems + 255) // 256 // 4))
-            _lib.call('uz_pack_conv_weights_batched', _p(self.table), len(self.weights), blocks, _stream())
-            self.versions = versions
+    def refresh(self):
+        blocks = min(64, max(1, (self.max_elems + 255) // 256 // 4))
+        _lib.call('uz_pack_conv_weights_batched', _p(self.table), len(self.weights), blocks, _stream())
 
     def lookup(self, w):
         return self.packed.get(w.data_ptr())

@@ -1,0 +1,65 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/unetzoo_b200.h declares; host-side planning
+entry points work on CPU; compute wrappers refuse CPU tensors (no fallback)."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from tests.gpu_util import PKG  # noqa: F401
+
+
+def test_library_exports_every_declared_symbol():
+    from b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 40
+    lib = _lib.load()
+    for name in protos:
+        assert hasattr(lib, name), name
+    assert lib.uz_abi_version() == 1
+    assert lib.uz_last_error() is not None
+    for name in ('uz_conv_fwd', 'uz_conv_wgrad', 'uz_bn_finalize', 'uz_head_fwd', 'uz_kl_fwd', 'uz_residual_ce',
+                 'uz_ged_pairwise', 'uz_variance_ncc', 'uz_pack_conv_weights_batched'):
+        assert name in protos
+
+
+def test_host_side_planning_entry_points():
+    from b200 import _lib, kern
+    tw, th, tn, nt = kern.conv_tile_geometry(12, 128, 128)
+    assert tw * th * tn == 128 and nt == 12 * 128 * 128 // 128
+    tw, th, tn, nt = kern.conv_tile_geometry(12, 2, 2)
+    assert (tw, th, tn, nt) == (2, 2, 32, 1)
+    lib = _lib.load()
+    assert lib.uz_wgrad_workspace_floats(12, 128, 128, 128, 128, 9) > 0
+    assert lib.uz_wgrad_workspace_floats(12, 128, 128, 100, 128, 9) == -1        # channels must be multiples of 16
+    assert 0 < lib.uz_conv_stats_rows(12, 128, 128, 128, 128, 9) <= 148           # persistent kernel: one row per CTA
+    assert lib.uz_conv_stats_rows(12, 8, 8, 192, 192, 9) == 6                     # generic kernel: one row per tile
+    assert lib.uz_bn_bwd_num_blocks(196608, 128) > 0
+
+
+def test_argument_errors_are_reported_not_thrown():
+    from b200 import _lib
+    lib = _lib.load()
+    rc = lib.uz_conv_fwd(None, 1, 16, 16, 16, 16, None, 16, 9, None, 16, None, None, 0, None, None)
+    assert rc != 0 and b'null pointer' in lib.uz_last_error()
+
+
+def test_compute_wrappers_refuse_cpu_tensors():
+    from b200 import _lib, kern
+    x = torch.zeros(1, 16, 16, 16, dtype=torch.bfloat16)
+    w = torch.zeros(9, 16, 16, dtype=torch.bfloat16)
+    with pytest.raises(_lib.UnetZooLibError):
+        kern.conv_fwd(x, w)
+    with pytest.raises(_lib.UnetZooLibError):
+        kern.ged(torch.zeros(2, 4, 4, dtype=torch.int64), torch.zeros(2, 4, 4), [1])
+
+
+def test_dropin_state_dict_and_parameter_count():
+    """PHISeg has 24 513 330 parameters / 820 state_dict entries."""
+    from tests.keygrammar import dropin_phiseg
+    net = dropin_phiseg([32, 64, 128, 192, 192, 192, 192])
+    assert sum(p.numel() for p in net.parameters()) == 24513330
+    assert len(net.state_dict()) == 820
+    assert 'prior.sample_z_path.4.mu_conv.0.weight' in net.state_dict()
+    with pytest.raises(NotImplementedError):
+        dropin_phiseg([32, 64, 128, 192, 192, 192, 192], reversible=True)

@@ -39,14 +39,14 @@ int uz_set_debug_flags(int flags);
  * num_tiles sizes the `stats_partial` buffer of uz_conv_fwd.  [host out-params] */
 int uz_conv_tile_geometry(int N, int H, int W, int* TW, int* TH, int* TN, int* num_tiles);
 
-/* Rows of the `stats_partial` buffer uz_conv_fwd will fill for this shape (persistent kernel: one per CTA; generic
- * kernel: one per 128-pixel tile).  Pass the same number as `tiles` to uz_bn_finalize. */
-int uz_conv_stats_rows(int N, int H, int W, int Cin, int Cout, int taps);
+/* 1 if uz_conv_fwd will use the persistent 16x16-tile kernel for this shape, 0 for the generic kernel. */
+int uz_conv_uses_persistent_kernel(int N, int H, int W, int Cin, int Cout, int taps);
 
 /* y[n,h,w,co] = act( scale[co] * sum_{tap,ci} x[n,h+dy,w+dx,ci] * w_packed[tap][co][ci] + shift[co] ), zero padding.
  * taps = 9 (3x3, pad 1) or 1 (1x1).  scale/shift may be NULL (1 / 0).  relu != 0 applies max(.,0).
- * stats_partial (optional) receives per-tile per-channel sum and sum of squares of the STORED bf16 outputs,
- * layout [uz_conv_stats_rows()][2][Cout] fp32, for training-mode BatchNorm (reduced by uz_bn_finalize).
+ * stats_partial (optional): [2][Cout] fp32 accumulators, ZERO on entry; the kernel atomically adds the per-channel sum
+ * and sum of squares of the STORED bf16 outputs (training-mode BatchNorm statistics; consumed by uz_bn_apply_train or
+ * uz_bn_finalize with tiles = 1).  Summation order across CTAs is not fixed (fp32 atomics).
  * w_packed taps are dx-major (t = kw*3 + kh) as produced by uz_pack_conv_weight.
  * Replaces: nn.Conv2d forward (torchlayers.py:18; models/unet.py:25-29; models/phiseg.py:28,32,57-58,91), fused with
  * the eval-mode BatchNorm + ReLU of torchlayers.py:20-21 or the bias + ReLU of models/unet.py:25-30; called with
@@ -87,6 +87,22 @@ int uz_pack_conv_weights_batched(const void* descs_device, int n, int blocks_per
 int uz_bn_finalize(const float* partial, int tiles, int C, float count, const float* gamma, const float* beta,
                    float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                    float* mean_out, float* invstd_out, void* stream);
+
+/* Training-mode BatchNorm normalise (+ReLU) straight from the conv's [2][C] accumulators: derives scale/shift per block,
+ * publishes scale/shift/mean/invstd (saved for backward) and updates the running statistics -- finalize + apply in one
+ * launch.  Replaces nn.BatchNorm2d(eps=1e-3, momentum=0.01) + nn.ReLU forward, torchlayers.py:20-21. */
+int uz_bn_apply_train(const void* y, int ldy, const float* sums, float count, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, float* scale_out,
+                      float* shift_out, float* mean_out, float* invstd_out, int relu, void* out, int ldo,
+                      long long npix, int C, void* stream);
+/* BatchNorm(+ReLU) backward in two launches: accumulate sum(g), sum(g*y) into [2][C] (zero on entry, fp32 atomics), then
+ * dy = A*g + B*y + Cc with the coefficients derived per block; dgamma / dbeta are written by the second kernel. */
+int uz_bn_bwd_reduce_sums(const void* dout, int ldd, const void* y, int ldy, const float* scale, const float* shift,
+                          int relu, long long npix, int C, float* sums, void* stream);
+int uz_bn_bwd_apply_train(const void* dout, int ldd, const void* y, int ldy, const float* scale, const float* shift,
+                          int relu, const float* sums, float count, const float* gamma, const float* mean,
+                          const float* invstd, float* dgamma, float* dbeta, void* dy, int lddy, long long npix, int C,
+                          void* stream);
 
 /* Eval-mode fold of conv bias + BatchNorm running stats into the conv epilogue's scale / shift (train_model.py:139). */
 int uz_bn_eval_fold(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,

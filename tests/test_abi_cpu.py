@@ -32,8 +32,9 @@ def test_host_side_planning_entry_points():
     lib = _lib.load()
     assert lib.uz_wgrad_workspace_floats(12, 128, 128, 128, 128, 9) > 0
     assert lib.uz_wgrad_workspace_floats(12, 128, 128, 100, 128, 9) == -1        # channels must be multiples of 16
-    assert 0 < lib.uz_conv_stats_rows(12, 128, 128, 128, 128, 9) <= 148           # persistent kernel: one row per CTA
-    assert lib.uz_conv_stats_rows(12, 8, 8, 192, 192, 9) == 6                     # generic kernel: one row per tile
+    assert lib.uz_conv_uses_persistent_kernel(12, 128, 128, 128, 128, 9) == 1
+    assert lib.uz_conv_uses_persistent_kernel(12, 8, 8, 192, 192, 9) == 0         # spatial < 16: generic kernel
+    assert lib.uz_conv_uses_persistent_kernel(12, 128, 128, 224, 128, 1) == 0     # 1x1: generic kernel
     assert lib.uz_bn_bwd_num_blocks(196608, 128) > 0
 
 

@@ -120,8 +120,7 @@ def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=Fa
     _, _, _, _, ldy = _check_act(out)
     partial = None
     if stats:
-        nt = _lib.raw('uz_conv_stats_rows')(n, h, w, cin, cout, taps)
-        partial = torch.empty((nt, 2, cout), dtype=torch.float32, device=x.device)
+        partial = zero_arena.get(2 * cout, x.device).view(1, 2, cout)      # [2][Cout] accumulators, zero on entry
     _lib.call('uz_conv_fwd', _p(x), n, h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy, _p(scale), _p(shift),
               int(relu), _p(partial), _stream())
     return out, partial
@@ -151,6 +150,34 @@ def bn_finalize(partial, count, gamma, beta, running_mean=None, running_var=None
     _lib.call('uz_bn_finalize', _p(partial), tiles, c, float(count), _p(gamma), _p(beta), eps, momentum,
               _p(running_mean), _p(running_var), _p(scale), _p(shift), _p(mean), _p(invstd), _stream())
     return scale, shift, mean, invstd
+
+
+def bn_apply_train(y, sums, count, gamma, beta, running_mean, running_var, relu=True, eps=BN_EPS, momentum=BN_MOMENTUM):
+    """finalize + normalise + ReLU in one launch -> (a, scale, shift, mean, invstd)"""
+    n, h, w, c, ldy = _check_act(y)
+    dev = y.device
+    st = torch.empty((4, c), dtype=torch.float32, device=dev)
+    out = new_act(n, h, w, c, dev)
+    _lib.call('uz_bn_apply_train', _p(y), ldy, _p(sums), float(count), _p(gamma), _p(beta), eps, momentum,
+              _p(running_mean), _p(running_var), _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), int(relu), _p(out), c,
+              n * h * w, c, _stream())
+    return out, st[0], st[1], st[2], st[3]
+
+
+def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True):
+    """two launches (accumulate, apply) -> dy bf16, dgamma, dbeta"""
+    n, h, w, c, ldd = _check_act(dout)
+    ldy = _check_act(y)[4]
+    npix = n * h * w
+    dev = y.device
+    sums = zero_arena.get(2 * c, dev)
+    _lib.call('uz_bn_bwd_reduce_sums', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), npix, c, _p(sums),
+              _stream())
+    dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+    dy = new_act(n, h, w, c, dev)
+    _lib.call('uz_bn_bwd_apply_train', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), _p(sums), float(npix),
+              _p(gamma), _p(mean), _p(invstd), _p(dgb[0]), _p(dgb[1]), _p(dy), c, npix, c, _stream())
+    return dy, dgb[0], dgb[1]
 
 
 def bn_eval_fold(conv_bias, gamma, beta, rm, rv, eps=BN_EPS):
@@ -431,14 +458,18 @@ class ZeroArena:
     front of BatchNorm) and zero-initialised accumulators share ONE fill per step instead of one launch each.
     The memory is never written by this package; a fresh block is taken every step so stale views stay valid."""
 
-    def __init__(self, floats=1 << 16):
+    def __init__(self, floats=1 << 19):
         self.floats = floats
         self.buf = None
         self.off = 0
 
-    def reset(self):
+    def reset(self, device=None):
+        """start a new step; with ``device`` the block is allocated (and zero-filled) right away on the CURRENT stream,
+        i.e. before any side stream forks off, so every later user is ordered after the fill"""
         self.buf = None
         self.off = 0
+        if device is not None:
+            self.buf = torch.zeros(self.floats, dtype=torch.float32, device=device)
 
     def get(self, n, device):
         n_al = (n + 3) // 4 * 4

@@ -74,8 +74,8 @@ def from_act(a):
 class ConvBNAct(torch.autograd.Function):
     """Conv2D of the reference (torchlayers.py:7-29): conv(k=3 pad 1 | k=1) + bias -> BatchNorm(train) -> ReLU.
 
-    forward (training): tcgen05 conv with statistics epilogue -> uz_bn_finalize -> uz_affine_act.
-    backward: two-pass BN/ReLU backward -> dgrad (same conv kernel, flipped weights) + tcgen05 wgrad.
+    forward (training): tcgen05 conv with statistics epilogue -> uz_bn_apply_train (finalize + normalise + ReLU).
+    backward: two-launch BN/ReLU backward -> dgrad (same conv kernel, flipped weights) + tcgen05 wgrad.
     The conv bias gets a zero gradient: BatchNorm removes any per-channel constant, d loss / d bias == 0 exactly.
     """
 
@@ -83,10 +83,10 @@ class ConvBNAct(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, relu, cin_logical):
         need_dx = ctx.needs_input_grad[0]
         wf, wd = kern.pack_conv_weight(weight, need_dgrad=need_dx)
-        y, partial = kern.conv_fwd(x, wf, shift=bias, stats=True)
+        y, sums = kern.conv_fwd(x, wf, shift=bias, stats=True)
         n, h, w, _ = x.shape
-        scale, shift, mean, invstd = kern.bn_finalize(partial, n * h * w, gamma, beta, running_mean, running_var)
-        a = kern.affine_act(y, scale, shift, relu=relu)
+        a, scale, shift, mean, invstd = kern.bn_apply_train(y, sums, n * h * w, gamma, beta, running_mean, running_var,
+                                                            relu=relu)
         ctx.save_for_backward(x, y, wd, scale, shift, mean, invstd, gamma)
         ctx.relu = relu
         ctx.cin_logical = cin_logical
@@ -97,7 +97,7 @@ class ConvBNAct(torch.autograd.Function):
     def backward(ctx, da):
         x, y, wd, scale, shift, mean, invstd, gamma = ctx.saved_tensors
         da = _dense(da)
-        dy, dgamma, dbeta = kern.bn_relu_bwd(da, y, scale, shift, gamma, mean, invstd, relu=ctx.relu)
+        dy, dgamma, dbeta = kern.bn_relu_bwd_train(da, y, scale, shift, gamma, mean, invstd, relu=ctx.relu)
         dx = None
         if ctx.needs_input_grad[0]:
             dx, _ = kern.conv_fwd(dy, wd)

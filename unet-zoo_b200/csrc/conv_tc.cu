@@ -43,7 +43,7 @@ struct ConvParams {
   __nv_bfloat16* y;
   const float* scale;  // [Cout] or nullptr (=1)
   const float* shift;  // [Cout] or nullptr (=0)
-  float* stats;        // [tiles][2][Cout] or nullptr
+  float* stats;        // [2][Cout] accumulators (zero on entry, atomically added to) or nullptr
   int dbg;             // profiling knobs (uz_set_debug_flags): 1 = no epilogue body, 2 = no MMA, 4 = no A loads, 8 = no B loads
 };
 
@@ -214,10 +214,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int et = threadIdx.x - 64;
       for (int i = et; i < 2 * p.BN; i += 128) {
         const int which = i / p.BN, c = i - which * p.BN;
-        float t = 0.f;
-        if (!(p.dbg & 1))
-          t = (s_stats[0][which][c] + s_stats[1][which][c]) + (s_stats[2][which][c] + s_stats[3][which][c]);
-        p.stats[(static_cast<size_t>(tile) * 2 + which) * p.Cout + c_out0 + c] = t;
+        if (!(p.dbg & 1)) {
+          const float t = (s_stats[0][which][c] + s_stats[1][which][c]) + (s_stats[2][which][c] + s_stats[3][which][c]);
+          atomicAdd(p.stats + which * p.Cout + c_out0 + c, t);
+        }
       }
     }
   }
@@ -341,12 +341,7 @@ extern "C" int uz_set_debug_flags(int flags) {
   return UZ_OK;
 }
 
-extern "C" int uz_conv_stats_rows(int N, int H, int W, int Cin, int Cout, int taps) {
-  if (taps == 9 && !(uz::g_conv_debug_flags & 32)) {
-    const int rows = uz::conv2_stats_rows(N, H, W, Cin, Cout);
-    if (rows > 0) return rows;
-  }
-  int tiles = 0;
-  if (uz_conv_tile_geometry(N, H, W, nullptr, nullptr, nullptr, &tiles)) return -1;
-  return tiles;
+extern "C" int uz_conv_uses_persistent_kernel(int N, int H, int W, int Cin, int Cout, int taps) {
+  if (taps == 9 && !(uz::g_conv_debug_flags & 32)) return uz::conv2_stats_rows(N, H, W, Cin, Cout) > 0 ? 1 : 0;
+  return 0;
 }

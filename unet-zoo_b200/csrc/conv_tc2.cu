@@ -38,7 +38,7 @@ struct Conv2Params {
   uint32_t stage_bytes, a_bytes, out_off;   // smem carve-up
   const float* scale;
   const float* shift;
-  float* stats;                  // [gridDim.x][2][Cout] or nullptr
+  float* stats;                  // [2][Cout] accumulators (zero on entry) or nullptr
   int dbg;
 };
 
@@ -292,12 +292,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     if (et == 0) tma_store_wait_all();
     if (p.stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = et; i < 2 * p.Cout; i += 128) {
-        const int which = i / p.Cout, c = i - which * p.Cout - c_out0;
-        float t = 0.f;                         // channels of other chunks: zero rows keep uz_bn_finalize a plain sum
-        if (c >= 0 && c < p.BN)
-          t = (s_stats[0][which][c] + s_stats[1][which][c]) + (s_stats[2][which][c] + s_stats[3][which][c]);
-        p.stats[static_cast<size_t>(blockIdx.x) * 2 * p.Cout + i] = t;
+      for (int i = et; i < 2 * p.BN; i += 128) {
+        const int which = i / p.BN, c = i - which * p.BN;
+        const float t = (s_stats[0][which][c] + s_stats[1][which][c]) + (s_stats[2][which][c] + s_stats[3][which][c]);
+        atomicAdd(p.stats + which * p.Cout + c_out0 + c, t);     // one add per CTA per channel
       }
     }
   }

@@ -161,11 +161,103 @@ __global__ void affine_act_kernel(const __nv_bfloat16* __restrict__ y, int ldy, 
   }
 }
 
+// Training-mode BatchNorm normalise + ReLU straight from the conv's statistics accumulators (sum, sumsq per channel):
+// every block derives scale/shift for all channels into shared memory (C rsqrt per block), block 0 also publishes them
+// (saved for backward), updates the running statistics (momentum, unbiased variance) -- no separate finalize launch.
+__global__ void bn_apply_train_kernel(const __nv_bfloat16* __restrict__ y, int ldy, const float* __restrict__ sums,
+                                      float count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      float eps, float momentum, float* running_mean, float* running_var,
+                                      float* scale_out, float* shift_out, float* mean_out, float* invstd_out, int relu,
+                                      __nv_bfloat16* out, int ldo, size_t npix, int C) {
+  extern __shared__ float sm[];          // [2][C]: scale, shift
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = sums[c] / count;
+    float var = sums[C + c] / count - mean * mean;
+    var = fmaxf(var, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    const float sc = (gamma ? gamma[c] : 1.f) * invstd;
+    const float sh = (beta ? beta[c] : 0.f) - mean * sc;
+    sm[c] = sc;
+    sm[C + c] = sh;
+    if (blockIdx.x == 0) {
+      scale_out[c] = sc;
+      shift_out[c] = sh;
+      mean_out[c] = mean;
+      invstd_out[c] = invstd;
+      if (running_mean) {
+        const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  const int chunks = C / 8;
+  const size_t total = npix * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = idx / chunks;
+    const int c0 = static_cast<int>(idx - pix * chunks) * 8;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(y + pix * ldy + c0), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sm[c0 + j], sm[C + c0 + j]);
+      if (relu) f[j] = fmaxf(f[j], 0.f);
+    }
+    *reinterpret_cast<uint4*>(out + pix * ldo + c0) = pack8(f);
+  }
+}
+
+// BN+ReLU backward pass 2 straight from the accumulators of pass 1 (sum g, sum g*y): coefficients per block in shared
+// memory, block 0 publishes dgamma / dbeta.   dy = A*g + B*y + Cc  (see bn_bwd_finalize_kernel for the algebra)
+__global__ void bn_bwd_apply_train_kernel(const __nv_bfloat16* __restrict__ dout, int ldd,
+                                          const __nv_bfloat16* __restrict__ y, int ldy, const float* __restrict__ scale,
+                                          const float* __restrict__ shift, int relu, const float* __restrict__ sums,
+                                          float count, const float* __restrict__ gamma, const float* __restrict__ mean,
+                                          const float* __restrict__ invstd, float* dgamma, float* dbeta,
+                                          __nv_bfloat16* dy, int lddy, size_t npix, int C) {
+  extern __shared__ float sm[];          // [5][C]: A, B, Cc, scale, shift
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float sg = sums[c], sgy = sums[C + c];
+    const float mu = mean[c], is = invstd[c], g = gamma ? gamma[c] : 1.f;
+    const float sgx = (sgy - mu * sg) * is;
+    const float mg = sg / count, mgx = sgx / count;
+    sm[c] = g * is;
+    sm[C + c] = -g * is * is * mgx;
+    sm[2 * C + c] = -g * is * mg + g * is * is * mgx * mu;
+    sm[3 * C + c] = scale[c];
+    sm[4 * C + c] = shift[c];
+    if (blockIdx.x == 0) {
+      if (dgamma) dgamma[c] = sgx;
+      if (dbeta) dbeta[c] = sg;
+    }
+  }
+  __syncthreads();
+  const int chunks = C / 8;
+  const size_t total = npix * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = idx / chunks;
+    const int c0 = static_cast<int>(idx - pix * chunks) * 8;
+    float g[8], yy[8];
+    unpack8(*reinterpret_cast<const uint4*>(dout + pix * ldd + c0), g);
+    unpack8(*reinterpret_cast<const uint4*>(y + pix * ldy + c0), yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float m = (!relu || fmaf(yy[j], sm[3 * C + c], sm[4 * C + c]) > 0.f) ? g[j] : 0.f;
+      g[j] = fmaf(sm[c], m, fmaf(sm[C + c], yy[j], sm[2 * C + c]));
+    }
+    *reinterpret_cast<uint4*>(dy + pix * lddy + c0) = pack8(g);
+  }
+}
+
 // BN+ReLU backward, pass 1: per-channel sum(g) and sum(g * y) with g = dout * [y*scale+shift > 0]; partial per block.
 // block = (C/8 channel chunks) x rows; grid-stride over pixel rows; block result -> partial[block][2][C].
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, const __nv_bfloat16* __restrict__ y,
                                      int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
-                                     int relu, size_t npix, int C, float* partial) {
+                                     int relu, size_t npix, int C, float* partial, int atomic_out) {
   extern __shared__ float red[];  // [rows][2][C]
   const int chunks = C / 8;
   const int rows = blockDim.x / chunks;
@@ -200,7 +292,8 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     float acc = 0.f;
     for (int rr = 0; rr < rows; ++rr) acc += red[rr * 2 * C + i];
-    partial[static_cast<size_t>(blockIdx.x) * 2 * C + i] = acc;
+    if (atomic_out) atomicAdd(partial + i, acc);
+    else partial[static_cast<size_t>(blockIdx.x) * 2 * C + i] = acc;
   }
 }
 
@@ -550,8 +643,56 @@ extern "C" int uz_bn_bwd_reduce(const void* dout, int ldd, const void* y, int ld
   const size_t smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);
   bn_bwd_reduce_kernel<<<blocks, threads, smem, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dout), ldd,
                                                              static_cast<const __nv_bfloat16*>(y), ldy, scale, shift,
-                                                             relu, static_cast<size_t>(npix), C, partial);
+                                                             relu, static_cast<size_t>(npix), C, partial, 0);
   UZ_CHECK_LAUNCH("uz_bn_bwd_reduce");
+  return UZ_OK;
+}
+
+extern "C" int uz_bn_bwd_reduce_sums(const void* dout, int ldd, const void* y, int ldy, const float* scale,
+                                     const float* shift, int relu, long long npix, int C, float* sums, void* stream) {
+  UZ_CHECK_ARG(dout && y && scale && shift && sums, "uz_bn_bwd_reduce_sums: null pointer");
+  UZ_CHECK_ARG(C % 8 == 0 && ldd % 8 == 0 && ldy % 8 == 0, "uz_bn_bwd_reduce_sums: alignment");
+  const int chunks = C / 8;
+  int threads = 256;
+  if (chunks > threads) threads = ((chunks + 31) / 32) * 32;
+  const int rows = threads / chunks;
+  int blocks = uz_bn_bwd_num_blocks(npix, C);
+  if (blocks > uz::num_sms()) blocks = uz::num_sms();      // one atomic per block per channel
+  const size_t smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);
+  bn_bwd_reduce_kernel<<<blocks, threads, smem, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dout), ldd,
+                                                             static_cast<const __nv_bfloat16*>(y), ldy, scale, shift,
+                                                             relu, static_cast<size_t>(npix), C, sums, 1);
+  UZ_CHECK_LAUNCH("uz_bn_bwd_reduce_sums");
+  return UZ_OK;
+}
+
+extern "C" int uz_bn_apply_train(const void* y, int ldy, const float* sums, float count, const float* gamma,
+                                 const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                 float* scale_out, float* shift_out, float* mean_out, float* invstd_out, int relu,
+                                 void* out, int ldo, long long npix, int C, void* stream) {
+  UZ_CHECK_ARG(y && sums && scale_out && shift_out && mean_out && invstd_out && out, "uz_bn_apply_train: null pointer");
+  UZ_CHECK_ARG(C % 8 == 0 && ldy % 8 == 0 && ldo % 8 == 0 && npix > 0, "uz_bn_apply_train: bad arguments");
+  bn_apply_train_kernel<<<ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 2 * C * sizeof(float),
+                          ST(stream)>>>(static_cast<const __nv_bfloat16*>(y), ldy, sums, count, gamma, beta, eps,
+                                        momentum, running_mean, running_var, scale_out, shift_out, mean_out, invstd_out,
+                                        relu, static_cast<__nv_bfloat16*>(out), ldo, static_cast<size_t>(npix), C);
+  UZ_CHECK_LAUNCH("uz_bn_apply_train");
+  return UZ_OK;
+}
+
+extern "C" int uz_bn_bwd_apply_train(const void* dout, int ldd, const void* y, int ldy, const float* scale,
+                                     const float* shift, int relu, const float* sums, float count, const float* gamma,
+                                     const float* mean, const float* invstd, float* dgamma, float* dbeta, void* dy,
+                                     int lddy, long long npix, int C, void* stream) {
+  UZ_CHECK_ARG(dout && y && scale && shift && sums && mean && invstd && dy, "uz_bn_bwd_apply_train: null pointer");
+  UZ_CHECK_ARG(C % 8 == 0 && ldd % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0 && npix > 0,
+               "uz_bn_bwd_apply_train: bad arguments");
+  bn_bwd_apply_train_kernel<<<ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 5 * C * sizeof(float),
+                              ST(stream)>>>(static_cast<const __nv_bfloat16*>(dout), ldd,
+                                            static_cast<const __nv_bfloat16*>(y), ldy, scale, shift, relu, sums, count,
+                                            gamma, mean, invstd, dgamma, dbeta, static_cast<__nv_bfloat16*>(dy), lddy,
+                                            static_cast<size_t>(npix), C);
+  UZ_CHECK_LAUNCH("uz_bn_bwd_apply_train");
   return UZ_OK;
 }
 

@@ -10,12 +10,59 @@ Quirks reproduced on purpose: Q1 loss aliasing, Q2 in-place accum
 the KL, Q4 RNG draw order (torch.randn_like is called with the reference's shapes in the reference's order, so a
 seeded run consumes the same Philox stream), Q5 ignored constructor arguments.
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from b200 import kern, ops
 from b200.ops import Act
 from torchlayers import Conv2D, Conv2DSequence, ReversibleSequence, _boundary, deferred_batch_counts
+
+
+# Independent sub-graphs (prior vs posterior encoder, the likelihood's per-level branches) are issued on a second CUDA
+# stream: most of their layers are too small to fill 148 SMs on their own.  UNETZOO_CONCURRENCY=0 disables it.
+_CONCURRENT = os.environ.get('UNETZOO_CONCURRENCY', '1') != '0'
+_side_streams = {}
+
+
+def _use_streams(t, hw=None):
+    """concurrency pays while single layers cannot fill the GPU: training-sized batches, not 100-sample evaluation"""
+    if not _CONCURRENT:
+        return False
+    if hw is None:
+        hw = t.shape[-1] * t.shape[-2]
+    return t.shape[0] * hw <= (1 << 19)
+
+
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+class _Fork:
+    """fork the current stream into a per-device side stream and join it back (CUDA-graph capturable)"""
+
+    def __init__(self, device):
+        self.main = torch.cuda.current_stream(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), self.main.cuda_stream)
+        if key not in _side_streams:
+            _side_streams[key] = torch.cuda.Stream(device=device)
+        self.stream = _side_streams[key]
+        self.stream.wait_stream(self.main)
+
+    def side(self):
+        return torch.cuda.stream(self.stream)
+
+    def hand_over(self, *tensors):
+        for t in tensors:
+            t.record_stream(self.main)
+
+    def join(self):
+        self.main.wait_stream(self.stream)
 
 
 class DownConvolutionalBlock(nn.Module):
@@ -145,19 +192,28 @@ class Posterior(nn.Module):
             self.sample_z_path.append(SampleZBlock(input, depth=2, reversible=reversible))
 
     def forward(self, patch, segm=None, training_prior=False, z_list=None):
+        return self.latent(*self.contract(patch, segm), training_prior=training_prior, z_list=z_list)
+
+    def contract(self, patch, segm=None):
+        """Encoder half (models/phiseg.py:175-194): input packing + the 7 DownConvolutionalBlocks.  No random draws, so
+        PHISeg.forward may run the prior's encoder concurrently with the posterior's on a second stream."""
         if not patch.is_cuda:
             raise kern._lib.UnetZooLibError('UNet-Zoo B200 modules need CUDA tensors: there is no CPU fallback path')
         cp = kern.pad16(self.input_channels)
         # one-hot(mask) - 0.5 concatenated after the image channels, produced directly in NHWC bf16 on the device
         x = Act(kern.input_pack(patch, segm if segm is not None else None, nlabels=2, cp=cp), self.input_channels)
         blocks = []
-        z = [None] * self.latent_levels
-        sigma = [None] * self.latent_levels
-        mu = [None] * self.latent_levels
         for i, down in enumerate(self.contracting_path):
             x = down(x)
             if i != len(self.contracting_path) - 1:
                 blocks.append(x)
+        return x, blocks
+
+    def latent(self, x, blocks, training_prior=False, z_list=None):
+        """Latent half (models/phiseg.py:196-206): per level [upsample z, 2 convs, cat skip] -> SampleZBlock."""
+        z = [None] * self.latent_levels
+        sigma = [None] * self.latent_levels
+        mu = [None] * self.latent_levels
         pre_conv = x
         for i, sample_z in enumerate(self.sample_z_path):
             if i != 0:
@@ -240,14 +296,21 @@ class Likelihood(nn.Module):
         s = [None] * self.latent_levels
         post_z = [None] * self.latent_levels
         post_c = [None] * self.latent_levels
+        # the per-level branches are independent: the small ones run on a second stream next to the full-resolution one
+        fork = _Fork(z[0].device) if (z[0].is_cuda and _use_streams(z[0], self.image_size[1] * self.image_size[2])) else None
         for i in range(self.latent_levels):
             assert z[-i - 1].shape[1] == 2
             assert z[-i - 1].shape[2] == self.image_size[1] * 2 ** (-self.resolution_levels + 1 + i)
-            x = self.likelihood_ups_path[i](ops.to_act(z[-i - 1]))
-            x = self.likelihood_post_ups_path[i](x)
+            with (fork.side() if (fork is not None and i != self.latent_levels - 1) else _null_ctx()):
+                x = self.likelihood_ups_path[i](ops.to_act(z[-i - 1]))
+                x = self.likelihood_post_ups_path[i](x)
+                if fork is not None and i != self.latent_levels - 1:
+                    fork.hand_over(x.t)
             assert x.t.shape[1] == self.image_size[1] * 2 ** (-self.latent_levels + i + 1)
             assert x.c == self.num_filters[-i - 1 - self.lvl_diff], '{} != {}'.format(x.c, self.num_filters[-i - 1])
             post_z[-i - 1] = x
+        if fork is not None:
+            fork.join()
         post_c[self.latent_levels - 1] = post_z[self.latent_levels - 1]
         for i in reversed(range(self.latent_levels - 1)):
             below = post_c[i + 1]
@@ -340,7 +403,7 @@ class PHISeg(nn.Module):
             raise kern._lib.UnetZooLibError('UNet-Zoo B200 modules need CUDA tensors: there is no CPU fallback path')
         pk = self._packer()
         pk.refresh()
-        kern.zero_arena.reset()
+        kern.zero_arena.reset(patch.device)
         prev = kern.set_active_packer(pk)
         try:
             with deferred_batch_counts():
@@ -349,14 +412,25 @@ class PHISeg(nn.Module):
             kern.set_active_packer(prev)
 
     def _forward(self, patch, mask, training=True):
+        # posterior and prior encoders are independent (no random draws inside): the prior's runs on a second stream.
+        # The latent halves keep the reference's order -- 5 posterior draws, then 5 prior draws (quirk Q4).
+        if _use_streams(patch):
+            fork = _Fork(patch.device)
+            with fork.side():
+                prior_x, prior_blocks = self.prior.contract(patch)
+                fork.hand_over(prior_x.t, *[b.t for b in prior_blocks])
+            post_x, post_blocks = self.posterior.contract(patch, mask)
+            fork.join()
+        else:
+            post_x, post_blocks = self.posterior.contract(patch, mask)
+            prior_x, prior_blocks = self.prior.contract(patch)
+        self.posterior_latent_space, self.posterior_mu, self.posterior_sigma = self.posterior.latent(post_x, post_blocks)
         if training:
-            self.posterior_latent_space, self.posterior_mu, self.posterior_sigma = self.posterior(patch, mask)
-            self.prior_latent_space, self.prior_mu, self.prior_sigma = self.prior(
-                patch, training_prior=True, z_list=self.posterior_latent_space)
+            self.prior_latent_space, self.prior_mu, self.prior_sigma = self.prior.latent(
+                prior_x, prior_blocks, training_prior=True, z_list=self.posterior_latent_space)
             self.s_out_list = self.likelihood(self.posterior_latent_space)
         else:
-            self.posterior_latent_space, self.posterior_mu, self.posterior_sigma = self.posterior(patch, mask)
-            self.prior_latent_space, self.prior_mu, self.prior_sigma = self.prior(patch, training_prior=False)
+            self.prior_latent_space, self.prior_mu, self.prior_sigma = self.prior.latent(prior_x, prior_blocks)
             self.s_out_list = self.likelihood(self.prior_latent_space)
         return self.s_out_list
 

@@ -238,7 +238,9 @@ def test_weights_are_repacked_after_an_optimizer_step(golden_dir):
         opt2.step()
         ref.append(float(l))
     print('\nlosses over 3 Adam steps: cuda %s  oracle %s' % (losses, ref))
-    assert losses[1] != losses[0] and losses[2] != losses[1]
+    # Adam's sign-like normalisation turns the 1e-7 run-to-run jitter of the atomically accumulated BatchNorm statistics
+    # into a few percent on this random-weight net after three steps; stale weights would leave the loss unchanged
+    assert losses[0] > losses[1] > losses[2]
     for a, b in zip(losses, ref):
-        assert a == pytest.approx(b, rel=2e-2)
-    assert (losses[2] - losses[0]) == pytest.approx(ref[2] - ref[0], rel=0.35)
+        assert a == pytest.approx(b, rel=8e-2)
+    assert (losses[2] - losses[0]) == pytest.approx(ref[2] - ref[0], rel=0.25)

@@ -108,6 +108,9 @@ class GradientAllReduce:
         def hook(param):
             bucket.pending -= 1
             if bucket.pending == 0 and self.world > 1:
+                if bucket.flat.is_cuda:
+                    from . import ops
+                    ops.sync_aux_streams()          # weight gradients are produced on the auxiliary stream
                 bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG if bucket.flat.is_cuda
                                               else dist.ReduceOp.SUM, group=self.group, async_op=True)
         return hook

@@ -33,6 +33,52 @@ def _dense(t):
     return t.contiguous()
 
 
+# ------------------------------------------------------------------------------------------------ auxiliary stream
+# The weight gradient of a layer depends only on (x, dy) and nothing downstream in the backward pass depends on it, so
+# it is issued on an auxiliary stream next to the dgrad chain; the streams are joined once at the end of backward
+# (autograd end-of-pass callback) or earlier by whoever needs the gradients (dp bucket hooks).  Small layers, whose
+# persistent kernels occupy a fraction of the SMs, then overlap.  UNETZOO_CONCURRENCY=0 disables it.
+import os as _os
+
+_AUX_ENABLED = _os.environ.get('UNETZOO_CONCURRENCY', '1') != '0'
+_aux = {'streams': {}, 'pending': [], 'keep': [], 'callback_queued': False}
+
+
+def _aux_stream(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _aux['streams']:
+        _aux['streams'][idx] = torch.cuda.Stream(device=device)
+    return _aux['streams'][idx]
+
+
+def sync_aux_streams():
+    """make the current stream wait for every outstanding auxiliary-stream launch"""
+    cur = torch.cuda.current_stream()
+    for st in _aux['pending']:
+        cur.wait_stream(st)
+    _aux['pending'] = []
+    _aux['keep'] = []
+    _aux['callback_queued'] = False
+
+
+def _run_on_aux(fn, keep):
+    """run fn() on the auxiliary stream after everything already queued on the current stream"""
+    if not _AUX_ENABLED:
+        return fn()
+    cur = torch.cuda.current_stream()
+    st = _aux_stream(keep[0].device)
+    st.wait_stream(cur)
+    with torch.cuda.stream(st):
+        out = fn()
+    _aux['keep'].append((keep, out))          # inputs stay referenced until the join: no early reuse of their memory
+    if st not in _aux['pending']:
+        _aux['pending'].append(st)
+    if not _aux['callback_queued']:
+        _aux['callback_queued'] = True
+        torch.autograd.Variable._execution_engine.queue_callback(sync_aux_streams)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ layout boundary
 class ToNHWC(torch.autograd.Function):
     """fp32 NCHW -> bf16 NHWC (padded).  Used at module boundaries and for z -> next conv."""
@@ -102,7 +148,7 @@ class ConvBNAct(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx, _ = kern.conv_fwd(dy, wd)
         cout, cin, kh, kw = ctx.wshape
-        dw = kern.conv_wgrad(x, dy, kh * kw, cin, cout).view(cout, cin, kh, kw)
+        dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, kh * kw, cin, cout), (x, dy)).view(cout, cin, kh, kw)
         dbias = kern.zero_arena.get(cout, dy.device)
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None
 

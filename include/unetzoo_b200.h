@@ -138,9 +138,15 @@ int uz_upsample2x_fwd(const void* x, int ldx, void* out, int ldo, int N, int h, 
 int uz_upsample2x_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int h, int w, int C, int align_corners,
                       void* stream);
 
-/* Strided channel-slice copy / accumulate: torch.cat along channels and its slice gradients
- * (models/phiseg.py:71,183,315; models/unet.py:72). */
+/* Strided channel-slice copy (accumulate 0), dst += src (1) or dst -= src (2): torch.cat along channels and its slice
+ * gradients (models/phiseg.py:71,183,315; models/unet.py:72) and the residual add / inverse of the reversible blocks
+ * (revtorch ReversibleBlock: y1 = x1 + F(x2), x2 = y2 - G(y1); torchlayers.py:71-78). */
 int uz_copy_channels(const void* src, int lds, void* dst, int ldd, long long npix, int C, int accumulate, void* stream);
+
+/* Global spatial mean [B,hw,C] -> [B,C] (bf16, fp32 accumulation) and its gradient: torch.mean over H then W in front of
+ * the ProbUNet Gaussian head (models/probabilistic_unet.py:114-115). */
+int uz_global_mean_fwd(const void* x, int ldx, int B, int hw, int C, void* out, int ldo, void* stream);
+int uz_global_mean_bwd(const void* dout, int ldd, int B, int hw, int C, void* dx, int ldx, void* stream);
 
 /* Network input: fp32 NCHW patch (+ optional mask of integer labels as float, [B,1,H,W]) -> bf16 NHWC [B,H,W,CP] with
  * channels [image | (mask==k)-0.5, k<nlabels | 0...].  Replaces utils.convert_batch_to_onehot (utils.py:289-311, a

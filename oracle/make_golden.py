@@ -97,9 +97,67 @@ def metrics_case():
     print('metrics', out['bin_ged'], out['bin_ncc'], out['tri_ged'], out['tri_ncc'], out['kl1'])
 
 
+def unet_cases():
+    import torch.distributions.normal as tdn
+    ns = load_reference()
+    out = {}
+    # U-Net (BASELINE configs[0] architecture at reduced width): forward + CE-mean loss + gradient norms
+    filters = [16, 32, 32, 48]
+    net = ns.unet.Unet(1, 2, filters)
+    sd = synth.synth_state_dict(net.state_dict(), seed=2)
+    net.load_state_dict(sd)
+    patch, labels, mask = synth.lidc_like_batch(3, seed=4)
+    logits = net.forward(patch)
+    loss = net.loss(mask)
+    loss.backward()
+    out['unet_filters'] = np.asarray(filters)
+    out['unet_logits_ds4'] = logits.detach()[:, :, ::4, ::4].numpy()
+    out['unet_loss'] = float(loss)
+    names = sorted(n for n, p in net.named_parameters())
+    out['unet_grad_names'] = np.asarray(names)
+    gd = dict(net.named_parameters())
+    out['unet_grad_norms'] = np.asarray([float(gd[n].grad.norm()) for n in names])
+    # Probabilistic U-Net, latent_dim 6 (BASELINE configs[1]) at reduced width
+    f7 = [32, 32, 32, 32, 32, 32, 32]
+    pn = ns.probabilistic_unet.ProbabilisticUnet(input_channels=1, num_classes=2, num_filters=f7, latent_dim=6,
+                                                 no_convs_fcomb=3)
+    sdp = synth.synth_state_dict(pn.state_dict(), seed=3)
+    eps = synth.noise_list([(3, 6)], seed=8)[0]
+    orig = tdn._standard_normal
+    tdn._standard_normal = lambda shape, dtype, device: eps.to(device)
+    try:
+        for training in (True, False):
+            key = 'train' if training else 'eval'
+            pn.load_state_dict(sdp)
+            pn.train(training)
+            fwd = pn.forward(patch, mask, training=training)
+            loss = pn.loss(mask)
+            out['prob_%s_forward_ds4' % key] = fwd.detach()[:, :, ::4, ::4].numpy()
+            out['prob_%s_loss' % key] = float(loss)
+            out['prob_%s_kl' % key] = float(pn.kl_divergence_loss)
+            out['prob_%s_rec' % key] = float(pn.reconstruction_loss)
+            out['prob_%s_mu_q' % key] = pn.posterior_latent_space.mean.detach().numpy()
+            out['prob_%s_sigma_p' % key] = pn.prior_latent_space.stddev.detach().numpy()
+            out['prob_%s_reconstruction_ds4' % key] = pn.reconstruction.detach()[:, :, ::4, ::4].numpy()
+            if training:
+                pn.zero_grad()
+                loss.backward()
+                gd = {n: p.grad for n, p in pn.named_parameters()}
+                names = sorted(n for n, g in gd.items() if g is not None)
+                out['prob_grad_names'] = np.asarray(names)
+                out['prob_grad_norms'] = np.asarray([float(gd[n].norm()) for n in names])
+                out['prob_nograd_names'] = np.asarray(sorted(n for n, g in gd.items() if g is None))
+    finally:
+        tdn._standard_normal = orig
+    out['prob_filters'] = np.asarray(f7)
+    np.savez_compressed(os.path.join(GOLDEN, 'unet_probunet.npz'), **out)
+    print('unet', out['unet_loss'], 'probunet', out['prob_train_loss'], out['prob_eval_loss'])
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     os.makedirs(GOLDEN, exist_ok=True)
     phiseg_case('phiseg_small', [16, 32, 32, 32, 32, 32, 32], 4, 1, 3, 5, keep_logits=True)
     phiseg_case('phiseg_lidc', [32, 64, 128, 192, 192, 192, 192], 2, 2, 4, 6, keep_logits=False)
     metrics_case()
+    unet_cases()

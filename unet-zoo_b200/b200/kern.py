@@ -260,11 +260,26 @@ def upsample2x_bwd(dout, align_corners=True):
 
 
 def copy_channels(src, dst, accumulate=False):
+    """accumulate: False/0 copy, True/1 dst += src, 2 dst -= src"""
     n, h, w, c, lds = _check_act(src)
     ldd = _check_act(dst)[4]
     assert dst.shape == src.shape
     _lib.call('uz_copy_channels', _p(src), lds, _p(dst), ldd, n * h * w, c, int(accumulate), _stream())
     return dst
+
+
+def global_mean_fwd(x):
+    n, h, w, c, ldx = _check_act(x)
+    out = new_act(n, 1, 1, c, x.device)
+    _lib.call('uz_global_mean_fwd', _p(x), ldx, n, h * w, c, _p(out), c, _stream())
+    return out
+
+
+def global_mean_bwd(dout, h, w):
+    n, _, _, c, ldd = _check_act(dout)
+    dx = new_act(n, h, w, c, dout.device)
+    _lib.call('uz_global_mean_bwd', _p(dout), ldd, n, h * w, c, _p(dx), c, _stream())
+    return dx
 
 
 def input_pack(patch, mask, nlabels=2, cp=16):

@@ -246,6 +246,19 @@ class Concat(torch.autograd.Function):
         return da, db, None, None, None
 
 
+class GlobalMean(torch.autograd.Function):
+    """spatial mean [N,H,W,C] -> [N,1,1,C] (models/probabilistic_unet.py:114-115)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.hw = (x.shape[1], x.shape[2])
+        return kern.global_mean_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return kern.global_mean_bwd(_dense(g), *ctx.hw)
+
+
 # ------------------------------------------------------------------------------------------------ latent head / losses
 class LatentHead(torch.autograd.Function):
     """mu, sigma = softplus(.), z = mu + sigma * eps from NHWC features (models/phiseg.py:95-106)."""

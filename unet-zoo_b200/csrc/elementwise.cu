@@ -503,15 +503,58 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int 
     const size_t pix = idx / chunks;
     const int c0 = static_cast<int>(idx - pix * chunks) * 8;
     uint4 v = *reinterpret_cast<const uint4*>(src + pix * lds + c0);
-    if (accumulate) {
+    if (accumulate) {          // 1: dst += src, 2: dst -= src
       float a[8], b[8];
       unpack8(v, a);
       unpack8(*reinterpret_cast<const uint4*>(dst + pix * ldd + c0), b);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] += b[j];
+      for (int j = 0; j < 8; ++j) a[j] = accumulate == 2 ? b[j] - a[j] : b[j] + a[j];
       v = pack8(a);
     }
     *reinterpret_cast<uint4*>(dst + pix * ldd + c0) = v;
+  }
+}
+
+// ---------------------------------------------------------------- global spatial mean (ProbUNet Gaussian heads)
+// out[b][c] = mean over the hw pixels of x[b][:][c]  (torch.mean over H then W, probabilistic_unet.py:114-115)
+__global__ void global_mean_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int hw, int C,
+                                       __nv_bfloat16* out, int ldo) {
+  // block = (sample, 64-channel group); threads = 32 channel pairs x 8 pixel lanes
+  __shared__ float red[8][64];
+  const int b = blockIdx.x, cg = blockIdx.y * 64;
+  const int cp = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  float s0 = 0.f, s1 = 0.f;
+  const int c = cg + cp * 2;
+  if (c < C) {
+    for (int p = pl; p < hw; p += 8) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(x + (static_cast<size_t>(b) * hw + p) * ldx + c);
+      s0 += uz::bf16lo(v);
+      s1 += uz::bf16hi(v);
+    }
+  }
+  red[pl][cp * 2] = s0;
+  red[pl][cp * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64 && cg + threadIdx.x < C) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    out[static_cast<size_t>(b) * ldo + cg + threadIdx.x] = __float2bfloat16(t / hw);
+  }
+}
+__global__ void global_mean_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, int hw, int C,
+                                       __nv_bfloat16* dx, int ldx, size_t npix) {
+  const int chunks = C / 8;
+  const size_t total = npix * chunks;
+  const float inv = 1.f / hw;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = idx / chunks;
+    const int c0 = static_cast<int>(idx - pix * chunks) * 8;
+    float g[8];
+    unpack8(*reinterpret_cast<const uint4*>(dout + (pix / hw) * ldd + c0), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= inv;
+    *reinterpret_cast<uint4*>(dx + pix * ldx + c0) = pack8(g);
   }
 }
 
@@ -765,6 +808,24 @@ extern "C" int uz_copy_channels(const void* src, int lds, void* dst, int ldd, lo
       static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, static_cast<size_t>(npix), C,
       accumulate);
   UZ_CHECK_LAUNCH("uz_copy_channels");
+  return UZ_OK;
+}
+
+extern "C" int uz_global_mean_fwd(const void* x, int ldx, int B, int hw, int C, void* out, int ldo, void* stream) {
+  UZ_CHECK_ARG(x && out && C % 2 == 0 && ldx % 2 == 0, "uz_global_mean_fwd: bad arguments");
+  dim3 grid(B, (C + 63) / 64, 1);
+  global_mean_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx, hw, C,
+                                                       static_cast<__nv_bfloat16*>(out), ldo);
+  UZ_CHECK_LAUNCH("uz_global_mean_fwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_global_mean_bwd(const void* dout, int ldd, int B, int hw, int C, void* dx, int ldx, void* stream) {
+  UZ_CHECK_ARG(dout && dx && C % 8 == 0 && ldd % 8 == 0 && ldx % 8 == 0, "uz_global_mean_bwd: bad arguments");
+  const size_t npix = static_cast<size_t>(B) * hw;
+  global_mean_bwd_kernel<<<ew_blocks(npix * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dout), ldd, hw, C, static_cast<__nv_bfloat16*>(dx), ldx, npix);
+  UZ_CHECK_LAUNCH("uz_global_mean_bwd");
   return UZ_OK;
 }
 

@@ -11,6 +11,7 @@
 namespace {
 
 constexpr int kMaxCls = 8;   // n_classes (2 for LIDC, 3 for UZH/BraTS)
+constexpr int kMaxOut = 16;  // outputs of the small 1x1 conv (class logits; 2 * latent_dim of the ProbUNet Gaussian heads)
 constexpr int kMaxLvl = 8;   // latent levels (5)
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
@@ -184,19 +185,19 @@ __global__ void slayer_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld
   const int lane = threadIdx.x & 31;
   const int npix = B * h * wd;
   if (warp >= npix) return;
-  float acc[kMaxCls];
+  float acc[kMaxOut];
 #pragma unroll
-  for (int k = 0; k < kMaxCls; ++k) acc[k] = 0.f;
+  for (int k = 0; k < kMaxOut; ++k) acc[k] = 0.f;
   const __nv_bfloat16* fp = feat + static_cast<size_t>(warp) * ld;
   for (int c = lane * 2; c < C; c += 64) {
     const uint32_t v = *reinterpret_cast<const uint32_t*>(fp + c);
     const float f0 = uz::bf16lo(v), f1 = uz::bf16hi(v);
 #pragma unroll
-    for (int k = 0; k < kMaxCls; ++k)
+    for (int k = 0; k < kMaxOut; ++k)
       if (k < ncls) acc[k] = fmaf(f0, w[k * C + c], fmaf(f1, w[k * C + c + 1], acc[k]));
   }
 #pragma unroll
-  for (int k = 0; k < kMaxCls; ++k)
+  for (int k = 0; k < kMaxOut; ++k)
     if (k < ncls) acc[k] = uz::warp_sum(acc[k]) + bias[k];
   const int b = warp / (h * wd);
   const int r = warp - b * h * wd;
@@ -219,9 +220,9 @@ __global__ void slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfl
   const int lane = threadIdx.x & 31;
   float* acc = sm + static_cast<size_t>(wid) * ncls * C;
   for (int i = lane; i < ncls * C; i += 32) acc[i] = 0.f;
-  float bacc[kMaxCls];
+  float bacc[kMaxOut];
 #pragma unroll
-  for (int k = 0; k < kMaxCls; ++k) bacc[k] = 0.f;
+  for (int k = 0; k < kMaxOut; ++k) bacc[k] = 0.f;
   __syncwarp();
   const int npix = B * h * wd;
   const int H = h * f, W = wd * f;
@@ -229,9 +230,9 @@ __global__ void slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfl
     const int b = pix / (h * wd);
     const int r = pix - b * h * wd;
     const int yl = r / wd, xl = r - yl * wd;
-    float g[kMaxCls];
+    float g[kMaxOut];
 #pragma unroll
-    for (int k = 0; k < kMaxCls; ++k) {
+    for (int k = 0; k < kMaxOut; ++k) {
       g[k] = 0.f;
       if (k < ncls) {
         const float* o = dout + ((static_cast<size_t>(b) * ncls + k) * H + yl * f) * W + xl * f;
@@ -248,7 +249,7 @@ __global__ void slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfl
       const float f0 = uz::bf16lo(v), f1 = uz::bf16hi(v);
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < kMaxCls; ++k) {
+      for (int k = 0; k < kMaxOut; ++k) {
         if (k < ncls) {
           d0 = fmaf(g[k], w[k * C + c], d0);
           d1 = fmaf(g[k], w[k * C + c + 1], d1);
@@ -265,7 +266,7 @@ __global__ void slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfl
     for (int ww = 0; ww < warps; ++ww) t += sm[static_cast<size_t>(ww) * ncls * C + i];
     wpartial[static_cast<size_t>(blockIdx.x) * ncls * C + i] = t;
   }
-  __shared__ float bsm[32][kMaxCls];
+  __shared__ float bsm[32][kMaxOut];
   if (lane == 0)
     for (int k = 0; k < ncls; ++k) bsm[wid][k] = bacc[k];
   __syncthreads();
@@ -458,7 +459,7 @@ extern "C" int uz_kl_bwd(const float* mu0, const float* s0, const float* mu1, co
 extern "C" int uz_slayer_fwd(const void* feat, int ld, int C, const float* w, const float* bias, int ncls, int B,
                              int h, int wd, int factor, float* out, void* stream) {
   UZ_CHECK_ARG(feat && w && bias && out, "uz_slayer_fwd: null pointer");
-  UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxCls, "uz_slayer_fwd: n_classes %d unsupported (max %d)", ncls, kMaxCls);
+  UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxOut, "uz_slayer_fwd: %d outputs unsupported (max %d)", ncls, kMaxOut);
   UZ_CHECK_ARG(C % 2 == 0 && ld % 2 == 0 && factor >= 1, "uz_slayer_fwd: bad C/ld/factor");
   const int npix = B * h * wd;
   const int threads = 256;
@@ -476,7 +477,7 @@ extern "C" int uz_slayer_bwd(const float* dout, const void* feat, int ld, int C,
                              int wd, int factor, void* dfeat, int ldd, float* wpartial, float* bpartial, float* dw,
                              float* db, void* stream) {
   UZ_CHECK_ARG(dout && feat && w && dfeat && wpartial && bpartial && dw && db, "uz_slayer_bwd: null pointer");
-  UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxCls, "uz_slayer_bwd: n_classes %d unsupported", ncls);
+  UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxOut, "uz_slayer_bwd: %d outputs unsupported", ncls);
   const int threads = 256;
   const int blocks = uz_slayer_bwd_num_blocks(B, h, wd);
   const size_t smem = static_cast<size_t>(threads / 32) * ncls * C * sizeof(float);

@@ -128,11 +128,11 @@ def init_weights_orthogonal_normal(m):
 
 
 def l2_regularisation(m):
-    """reference utils.py:93-101: sum of parameter 2-norms."""
-    total = None
-    for W in m.parameters():
-        total = W.norm(2) if total is None else total + W.norm(2)
-    return total
+    """reference utils.py:93-101: sum of the parameters' 2-norms (one multi-tensor norm instead of a launch each)."""
+    params = list(m.parameters())
+    if not params:
+        return None
+    return torch.stack(torch._foreach_norm(params, 2)).sum()
 
 
 def normalise_image(image):

@@ -22,12 +22,13 @@ from oracle.ref_run import build_reference_phiseg, injected_noise  # noqa: E402
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 
-def phiseg_case(tag, filters, batch, wseed, dseed, nseed, keep_logits):
-    net = build_reference_phiseg(filters)
+def phiseg_case(tag, filters, batch, wseed, dseed, nseed, keep_logits, reversible=False):
+    net = build_reference_phiseg(filters, reversible=reversible)
     sd = synth.synth_state_dict(net.state_dict(), seed=wseed)
     patch, labels, mask = synth.lidc_like_batch(batch, seed=dseed)
     eps = synth.noise_list(synth.phiseg_noise_shapes(batch), seed=nseed)
-    out = {'filters': np.asarray(filters), 'batch': batch, 'wseed': wseed, 'dseed': dseed, 'nseed': nseed}
+    out = {'filters': np.asarray(filters), 'batch': batch, 'wseed': wseed, 'dseed': dseed, 'nseed': nseed,
+           'reversible': int(reversible)}
     for training in (True, False):
         net.load_state_dict(sd)
         net.train(training)
@@ -60,8 +61,11 @@ def phiseg_case(tag, filters, batch, wseed, dseed, nseed, keep_logits):
             out['train_grad_norms'] = np.asarray([gn[n] for n in names])
             out['train_nograd_names'] = np.asarray(sorted(n for n, p in net.named_parameters() if p.grad is None))
             rs = net.state_dict()
-            k = 'posterior.contracting_path.3.layers.2.convolution.1.running_var'
+            k = ('posterior.contracting_path.3.layers.1.sequence.reversible_blocks.1.f_block.0.convolution.1.running_var'
+                 if reversible else 'posterior.contracting_path.3.layers.2.convolution.1.running_var')
             out['train_running_var_probe'] = rs[k].numpy().copy()
+            out['train_running_var_probe_key'] = k
+            out['train_num_batches_tracked_probe'] = int(rs[k.replace('running_var', 'num_batches_tracked')])
     np.savez_compressed(os.path.join(GOLDEN, tag + '.npz'), **out)
     print(tag, out['train_loss'], out['eval_loss'])
 
@@ -159,5 +163,6 @@ if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     phiseg_case('phiseg_small', [16, 32, 32, 32, 32, 32, 32], 4, 1, 3, 5, keep_logits=True)
     phiseg_case('phiseg_lidc', [32, 64, 128, 192, 192, 192, 192], 2, 2, 4, 6, keep_logits=False)
+    phiseg_case('phiseg_rev_small', [32, 64, 64, 64, 64, 64, 64], 4, 1, 3, 5, keep_logits=False, reversible=True)
     metrics_case()
     unet_cases()

@@ -52,7 +52,7 @@ def onehot_minus_half(mask, nlabels=2):
     return torch.cat([(mask == k).to(torch.float32) for k in range(nlabels)], dim=1) - 0.5
 
 
-def conv2d_unit(x, sd, prefix, training, rnd=FP32, kernel=3, norm=True, act=True, stats=None):
+def conv2d_unit(x, sd, prefix, training, rnd=FP32, kernel=3, norm=True, act=True, stats=None, updates=1):
     """torchlayers.py:7-29.  ``prefix`` is the Conv2D module path; keys prefix.convolution.{0,1}.*.
     In training mode the BN running stats in ``sd`` are updated in place like nn.BatchNorm2d does."""
     w = sd[prefix + '.convolution.0.weight']
@@ -69,11 +69,12 @@ def conv2d_unit(x, sd, prefix, training, rnd=FP32, kernel=3, norm=True, act=True
             var = y.var(dim=(0, 2, 3), unbiased=False)
             n = y.numel() // y.shape[1]
             with torch.no_grad():
-                rm.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean)
-                rv.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var * n / max(n - 1, 1))
-                nbt = prefix + '.convolution.1.num_batches_tracked'
-                if nbt in sd:
-                    sd[nbt] += 1
+                for _ in range(updates):      # reversible blocks run F and G twice per training step (quirk Q7)
+                    rm.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean)
+                    rv.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var * n / max(n - 1, 1))
+                    nbt = prefix + '.convolution.1.num_batches_tracked'
+                    if nbt in sd:
+                        sd[nbt] += 1
         else:
             mean, var = rm, rv
         if stats is not None:
@@ -86,6 +87,27 @@ def conv2d_unit(x, sd, prefix, training, rnd=FP32, kernel=3, norm=True, act=True
     return rnd.act(y) if (norm or act) else y
 
 
+def rev_sequence(x, sd, prefix, depth, training, rnd=FP32, stats=None, recompute=True):
+    """ReversibleSequence of the reference (torchlayers.py:55-82) over revtorch 0.2.0 additive coupling:
+    optional 1x1 Conv2D, then depth x {y1 = x1 + F(x2); y2 = x2 + G(y1)}.  Gradients through this plain forward equal
+    those of revtorch's inverse-recompute backward; with ``recompute`` (a training step that runs backward) the
+    BatchNorm running statistics of F and G receive two momentum updates."""
+    if prefix + '.inital_conv.convolution.0.weight' in sd:
+        x = conv2d_unit(x, sd, prefix + '.inital_conv', training, rnd, kernel=1, stats=stats)
+    upd = 2 if (training and recompute) else 1
+    for d in range(depth):
+        x1, x2 = torch.chunk(x, 2, dim=1)
+        base = '%s.sequence.reversible_blocks.%d' % (prefix, d)
+        y1 = rnd.act(x1 + conv2d_unit(x2, sd, base + '.f_block.0', training, rnd, stats=stats, updates=upd))
+        y2 = rnd.act(x2 + conv2d_unit(y1, sd, base + '.g_block.0', training, rnd, stats=stats, updates=upd))
+        x = torch.cat([y1, y2], dim=1)
+    return x
+
+
+def _is_rev(sd, prefix):
+    return any(k.startswith(prefix + '.sequence.reversible_blocks.') for k in sd)
+
+
 def up2(x):
     return F.interpolate(x, mode='bilinear', scale_factor=2, align_corners=True)
 
@@ -96,6 +118,8 @@ def down_block(x, sd, prefix, pool, training, rnd, stats=None):
     if pool:
         x = rnd.act(F.avg_pool2d(x, 2, 2, 0, ceil_mode=True))
         off = 1
+    if _is_rev(sd, '%s.layers.%d' % (prefix, off)):
+        return rev_sequence(x, sd, '%s.layers.%d' % (prefix, off), 3, training, rnd, stats)
     for k in range(3):
         x = conv2d_unit(x, sd, '%s.layers.%d' % (prefix, k + off), training, rnd, stats=stats)
     return x
@@ -103,8 +127,11 @@ def down_block(x, sd, prefix, pool, training, rnd, stats=None):
 
 def sample_z_block(x, sd, prefix, eps, training, rnd, stats=None):
     """models/phiseg.py:76-106; ``eps`` replaces torch.randn_like(sigma)."""
-    for k in range(2):
-        x = conv2d_unit(x, sd, '%s.conv.%d' % (prefix, k), training, rnd, stats=stats)
+    if _is_rev(sd, prefix + '.conv.0'):
+        x = rev_sequence(x, sd, prefix + '.conv.0', 3, training, rnd, stats)
+    else:
+        for k in range(2):
+            x = conv2d_unit(x, sd, '%s.conv.%d' % (prefix, k), training, rnd, stats=stats)
     mu = F.conv2d(x, sd[prefix + '.mu_conv.0.weight'], sd[prefix + '.mu_conv.0.bias'])
     sigma = F.softplus(F.conv2d(x, sd[prefix + '.sigma_conv.0.weight'], sd[prefix + '.sigma_conv.0.bias']))
     z = mu + sigma * eps
@@ -130,8 +157,12 @@ def encoder_decoder(patch, sd, name, eps_list, training, rnd=FP32, segm=None, z_
         lvl = LATENT_LEVELS - 1 - i
         if i != 0:
             u = rnd.act(up2(rnd.act(z[lvl + 1])))
-            for k in range(2):
-                u = conv2d_unit(u, sd, '%s.upsampling_path.%d.upconv_layer.%d' % (name, i - 1, k), training, rnd, stats=stats)
+            up_prefix = '%s.upsampling_path.%d.upconv_layer' % (name, i - 1)
+            if _is_rev(sd, up_prefix):
+                u = rev_sequence(u, sd, up_prefix, 2, training, rnd, stats)
+            else:
+                for k in range(2):
+                    u = conv2d_unit(u, sd, '%s.%d' % (up_prefix, k), training, rnd, stats=stats)
             pre = torch.cat([u, blocks[-i]], dim=1)
         mu[lvl], sigma[lvl], z[lvl] = sample_z_block(pre, sd, '%s.sample_z_path.%d' % (name, i), eps_list[i], training, rnd, stats)
         if z_forced is not None:
@@ -146,8 +177,12 @@ def likelihood(z, sd, image_hw, training, rnd=FP32, stats=None):
     for i in range(L):
         lvl = L - 1 - i
         x = rnd.act(z[lvl])
-        for k in range(2):
-            x = conv2d_unit(x, sd, 'likelihood.likelihood_ups_path.%d.convolution.%d' % (i, k), training, rnd, stats=stats)
+        if _is_rev(sd, 'likelihood.likelihood_ups_path.%d' % i):
+            x = rev_sequence(x, sd, 'likelihood.likelihood_ups_path.%d' % i, 2, training, rnd, stats)
+        else:
+            for k in range(2):
+                x = conv2d_unit(x, sd, 'likelihood.likelihood_ups_path.%d.convolution.%d' % (i, k), training, rnd,
+                                stats=stats)
         for t in range(LVL_DIFF):
             x = rnd.act(up2(x))
             x = conv2d_unit(x, sd, 'likelihood.likelihood_post_ups_path.%d.%d.convolution.0' % (i, 2 * t + 1), training, rnd, stats=stats)
@@ -156,8 +191,12 @@ def likelihood(z, sd, image_hw, training, rnd=FP32, stats=None):
     post_c[L - 1] = post_z[L - 1]
     for lvl in reversed(range(L - 1)):
         x = torch.cat([post_z[lvl], rnd.act(up2(post_c[lvl + 1]))], dim=1)
-        for k in range(2):
-            x = conv2d_unit(x, sd, 'likelihood.likelihood_post_c_path.%d.convolution.%d' % (lvl, k), training, rnd, stats=stats)
+        if _is_rev(sd, 'likelihood.likelihood_post_c_path.%d' % lvl):
+            x = rev_sequence(x, sd, 'likelihood.likelihood_post_c_path.%d' % lvl, 2, training, rnd, stats)
+        else:
+            for k in range(2):
+                x = conv2d_unit(x, sd, 'likelihood.likelihood_post_c_path.%d.convolution.%d' % (lvl, k), training, rnd,
+                                stats=stats)
         post_c[lvl] = x
     s = [None] * L
     for i in range(L):

@@ -79,6 +79,8 @@ def synth_state_dict(template, seed=0):
                 v = v * 0.25                       # keep sigma away from 0 so KL / z stay well conditioned
         elif name.endswith('.1.weight'):          # BatchNorm gamma (Conv2D.convolution.1)
             v = 1.0 + 0.1 * rs.standard_normal(shape)
+            if 'reversible_blocks' in name:       # small residual branches: y = x + F(x) stays bounded in eval mode,
+                v = 0.2 + 0.02 * rs.standard_normal(shape)   # where the synthetic running statistics do not normalise
         elif name.endswith('.1.bias'):            # BatchNorm beta
             v = 0.1 * rs.standard_normal(shape)
         else:                                     # conv bias

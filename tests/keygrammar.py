@@ -9,5 +9,5 @@ def dropin_phiseg(filters, reversible=False, image_size=(1, 128, 128), num_class
                   no_convs_fcomb=4, beta=10.0, image_size=image_size, reversible=reversible)
 
 
-def phiseg_state_template(filters):
-    return dropin_phiseg(filters).state_dict()
+def phiseg_state_template(filters, reversible=False):
+    return dropin_phiseg(filters, reversible=reversible).state_dict()

@@ -11,24 +11,25 @@ from oracle import synth
 from oracle.ref_loader import have_reference
 
 
-def _template(filters):
+def _template(filters, reversible=False):
     """state_dict names/shapes of the reference PHISeg without importing it: built by the drop-in's
     key grammar helper (pure host logic)."""
     from tests.keygrammar import phiseg_state_template
-    return phiseg_state_template(filters)
+    return phiseg_state_template(filters, reversible=reversible)
 
 
 def _run_case(g, training):
     filters = [int(v) for v in g['filters']]
     batch = int(g['batch'])
-    sd = synth.synth_state_dict(_template(filters), seed=int(g['wseed']))
+    rev = bool(int(g['reversible'])) if 'reversible' in g else False
+    sd = synth.synth_state_dict(_template(filters, rev), seed=int(g['wseed']))
     patch, labels, mask = synth.lidc_like_batch(batch, seed=int(g['dseed']))
     eps = synth.noise_list(synth.phiseg_noise_shapes(batch), seed=int(g['nseed']))
     out = po.phiseg_forward(sd, patch, mask, eps, training=training)
     return out, po.elbo(out, mask), sd, mask
 
 
-@pytest.mark.parametrize('case', ['phiseg_small', 'phiseg_lidc'])
+@pytest.mark.parametrize('case', ['phiseg_small', 'phiseg_lidc', 'phiseg_rev_small'])
 @pytest.mark.parametrize('training', [True, False])
 def test_oracle_matches_reference_fixture(golden_dir, case, training):
     g = np.load(os.path.join(golden_dir, case + '.npz'))
@@ -117,3 +118,25 @@ def test_oracle_matches_live_reference(training):
     assert list(tpl.keys()) == list(ref.keys())
     for k in ref:
         assert tuple(tpl[k].shape) == tuple(ref[k].shape) and tpl[k].dtype == ref[k].dtype, k
+
+
+def test_reversible_oracle_gradients_and_double_running_stat_update(golden_dir):
+    """RevPHiSeg (reference torchlayers.py:55-82 over revtorch, restated in oracle/shims/revtorch -- PARITY UNPINNED for
+    that third-party package): gradients through the plain forward equal the inverse-recompute backward; BatchNorm
+    running statistics of F / G get two momentum updates per training step (quirk Q7)."""
+    g = np.load(os.path.join(golden_dir, 'phiseg_rev_small.npz'))
+    filters = [int(v) for v in g['filters']]
+    batch = int(g['batch'])
+    sd = synth.synth_state_dict(_template(filters, True), seed=int(g['wseed']))
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype == torch.float32 and 'running_' not in k}
+    patch, labels, mask = synth.lidc_like_batch(batch, seed=int(g['dseed']))
+    eps = synth.noise_list(synth.phiseg_noise_shapes(batch), seed=int(g['nseed']))
+    out = po.phiseg_forward(sd, patch, mask, eps, training=True)
+    po.elbo(out, mask)['total'].backward()
+    norms = g['train_grad_norms']
+    floor = 1e-5 * float(norms.max())
+    for n, ref in zip(g['train_grad_names'], norms):
+        assert float(params[str(n)].grad.norm()) == pytest.approx(float(ref), rel=1e-2, abs=floor), n
+    k = str(g['train_running_var_probe_key'])
+    np.testing.assert_allclose(sd[k].detach().numpy(), g['train_running_var_probe'], rtol=1e-5)
+    assert int(sd[k.replace('running_var', 'num_batches_tracked')]) == int(g['train_num_batches_tracked_probe']) == 5

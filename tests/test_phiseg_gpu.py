@@ -244,3 +244,84 @@ def test_weights_are_repacked_after_an_optimizer_step(golden_dir):
     for a, b in zip(losses, ref):
         assert a == pytest.approx(b, rel=8e-2)
     assert (losses[2] - losses[0]) == pytest.approx(ref[2] - ref[0], rel=0.25)
+
+
+# ------------------------------------------------------------------------------------------------ RevPHiSeg
+def _setup_rev(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'phiseg_rev_small.npz'))
+    filters = [int(v) for v in g['filters']]
+    batch = int(g['batch'])
+    net = dropin_phiseg(filters, reversible=True)
+    sd = synth.synth_state_dict(net.state_dict(), seed=int(g['wseed']))
+    net.load_state_dict(sd)
+    net = net.cuda()
+    patch, labels, mask = synth.lidc_like_batch(batch, seed=int(g['dseed']))
+    eps = synth.noise_list(synth.phiseg_noise_shapes(batch), seed=int(g['nseed']))
+    return g, net, sd, patch, mask, eps
+
+
+@pytest.mark.parametrize('training', [True, False])
+def test_reversible_phiseg_forward_and_losses(golden_dir, training):
+    g, net, sd, patch, mask, eps = _setup_rev(golden_dir)
+    key = 'train' if training else 'eval'
+    net.train(training)
+    with injected_noise(eps), torch.no_grad():
+        s = [t.clone() for t in net.forward(patch.cuda(), mask.cuda(), training=training)]
+        loss = net.loss(mask.cuda())
+    with torch.no_grad():
+        emu = po.phiseg_forward({k: v.clone() for k, v in sd.items()}, patch, mask, eps, training=training,
+                                rnd=po.Rounding(True))
+        e_emu = po.elbo(emu, mask)
+    acc, acc_emu = sum(t.cpu() for t in s), po.accumulate_output(emu['s'])
+    print('\n[RevPHiSeg %s] logits rel-L2 vs same-rounding oracle %.3e; loss cuda %.6g emu %.6g golden(reference) %.6g' %
+          (key, _rel(acc, acc_emu), float(loss), float(e_emu['total']), float(g[key + '_loss'])))
+    assert _rel(acc, acc_emu) < (8e-2 if training else 3e-2)
+    assert float(loss) == pytest.approx(float(g[key + '_loss']), rel=3e-2)
+    np.testing.assert_allclose(acc[:, :, ::8, ::8].numpy(), g[key + '_logits_ds8'], rtol=0.3, atol=0.05 * float(np.abs(g[key + '_logits_ds8']).max()))
+
+
+def test_reversible_phiseg_training_step(golden_dir):
+    """Inverse-recompute backward: gradients vs the oracle's plain autograd (same forward rounding), the double
+    BatchNorm running-stat update (quirk Q7), and the reconstruction error of the regenerated activations."""
+    g, net, sd, patch, mask, eps = _setup_rev(golden_dir)
+    net.train(True)
+    with injected_noise(eps):
+        net.forward(patch.cuda(), mask.cuda(), training=True)
+        loss = net.loss(mask.cuda())
+    loss.backward()
+    p_emu = _oracle_grads(sd, patch, mask, eps, True)
+    p_fp32 = _oracle_grads(sd, patch, mask, eps, False)
+    named = dict(net.named_parameters())
+    gmax = max(float(p.grad.norm()) for p in p_fp32.values() if p.grad is not None)
+    e_emu, gap = [], []
+    for n, p in p_fp32.items():
+        if p.grad is None:
+            assert named[n].grad is None, n
+            continue
+        if n.endswith('convolution.0.bias') and (n[:-len('0.bias')] + '1.weight') in p_fp32:
+            continue
+        if float(p.grad.norm()) < 1e-6 * gmax:
+            continue
+        e_emu.append(_rel(named[n].grad.cpu(), p_emu[n].grad))
+        gap.append(_rel(p_emu[n].grad, p.grad))
+    print('\nRevPHiSeg gradient rel-L2: cuda vs same-rounding oracle median %.3e; that oracle vs fp32 oracle median %.3e' %
+          (float(np.median(e_emu)), float(np.median(gap))))
+    assert float(np.median(e_emu)) < max(0.3, 1.5 * float(np.median(gap)))
+    k = str(g['train_running_var_probe_key'])
+    np.testing.assert_allclose(net.state_dict()[k].cpu().numpy(), g['train_running_var_probe'], rtol=5e-3)
+    assert int(net.state_dict()[k.replace('running_var', 'num_batches_tracked')]) == 5      # 3 + two updates
+
+
+def test_reversible_block_inverse_is_accurate():
+    """x -> couple -> backward_pass regenerates x to bf16 accuracy (one block, random F/G)."""
+    import torchlayers
+    from b200.ops import Act
+    torch.manual_seed(0)
+    seq = torchlayers.ReversibleSequence(64, 64, reversible_depth=2).cuda().train()
+    x = (torch.randn(2, 16, 16, 64, device='cuda')).to(torch.bfloat16)
+    block = seq.sequence.reversible_blocks[0]
+    with torch.no_grad():
+        y = block.couple(x)
+    xr, dx = block.backward_pass(y, torch.zeros_like(y))
+    assert _rel(xr.float(), x.float()) < 1e-2
+    assert float(dx.float().abs().max()) == 0.0

@@ -116,8 +116,11 @@ class UpConvolutionalBlock(nn.Module):
         x, bridge = ops.to_act(x), ops.to_act(bridge)
         if self.bilinear:
             x = Act(ops.Upsample2x.apply(x.t, True), x.c)
-            for layer in self.upconv_layer:
-                x = layer(x)
+            if isinstance(self.upconv_layer, nn.Sequential):
+                for layer in self.upconv_layer:
+                    x = layer(x)
+            else:
+                x = self.upconv_layer(x)
         assert x.t.shape[2] == bridge.t.shape[2]
         assert x.t.shape[1] == bridge.t.shape[1]
         out = Act(ops.Concat.apply(x.t, bridge.t, False, False, True), x.c + bridge.c)

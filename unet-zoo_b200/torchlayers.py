@@ -113,10 +113,123 @@ class Conv2DSequence(nn.Module):
         return x
 
 
+class ReversibleBlock(nn.Module):
+    """Additive coupling of revtorch 0.2.0 (reference torchlayers.py:67-75): y1 = x1 + F(x2), y2 = x2 + G(y1) on the two
+    channel halves.  Sub-module names ``f_block`` / ``g_block`` are revtorch's (state_dict keys)."""
+
+    def __init__(self, f_block, g_block):
+        super(ReversibleBlock, self).__init__()
+        self.f_block = f_block
+        self.g_block = g_block
+
+    def couple(self, x):
+        """x: bf16 NHWC [N,H,W,C] -> y of the same shape; no autograd (callers handle gradients by inversion)."""
+        n, h, w, c = x.shape
+        half = c // 2
+        y = kern.new_act(n, h, w, c, x.device)
+        x1, x2, y1, y2 = x[..., :half], x[..., half:], y[..., :half], y[..., half:]
+        fx2 = self.f_block(Act(x2, half)).t
+        kern.copy_channels(x1, y1)
+        kern.copy_channels(fx2, y1, accumulate=1)
+        gy1 = self.g_block(Act(y1, half)).t
+        kern.copy_channels(x2, y2)
+        kern.copy_channels(gy1, y2, accumulate=1)
+        return y
+
+    def backward_pass(self, y, dy):
+        """Inverse recompute (revtorch ReversibleBlock.backward_pass): returns (x, dx); parameter gradients are
+        accumulated into ``.grad`` by the inner backward calls, F and G run a second time (BatchNorm running
+        statistics receive their second momentum update)."""
+        n, h, w, c = y.shape
+        half = c // 2
+        x = kern.new_act(n, h, w, c, y.device)
+        dx = kern.new_act(n, h, w, c, y.device)
+        y1, y2, dy1, dy2 = y[..., :half], y[..., half:], dy[..., :half], dy[..., half:]
+        x1, x2, dx1, dx2 = x[..., :half], x[..., half:], dx[..., :half], dx[..., half:]
+        y1_leaf = y1.detach().requires_grad_(True)
+        with torch.enable_grad():
+            gy1 = self.g_block(Act(y1_leaf, half)).t
+        torch.autograd.backward(gy1, dy2)
+        kern.copy_channels(y2, x2)
+        kern.copy_channels(gy1.detach(), x2, accumulate=2)            # x2 = y2 - G(y1)
+        kern.copy_channels(dy1, dx1)
+        kern.copy_channels(ops._dense(y1_leaf.grad), dx1, accumulate=1)   # dx1 = dy1 + dG/dy1
+        x2_leaf = x2.detach().requires_grad_(True)
+        with torch.enable_grad():
+            fx2 = self.f_block(Act(x2_leaf, half)).t
+        torch.autograd.backward(fx2, dx1)
+        kern.copy_channels(y1, x1)
+        kern.copy_channels(fx2.detach(), x1, accumulate=2)            # x1 = y1 - F(x2)
+        kern.copy_channels(dy2, dx2)
+        kern.copy_channels(ops._dense(x2_leaf.grad), dx2, accumulate=1)   # dx2 = dy2 + dF/dx2
+        return x, dx
+
+
+class _ReversibleFunction(torch.autograd.Function):
+    """Keeps only the output of the block chain; backward walks the blocks in reverse, regenerating their inputs."""
+
+    @staticmethod
+    def forward(ctx, x, blocks, *params):
+        y = x
+        for block in blocks:
+            y = block.couple(y)
+        ctx.blocks = blocks
+        ctx.y = y
+        ctx.packer = kern._active_packer          # weights do not change between forward and backward of a step
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y = ctx.y
+        del ctx.y
+        dy = ops._dense(dy)
+        prev = kern.set_active_packer(ctx.packer)
+        try:
+            for block in list(ctx.blocks)[::-1]:
+                y, dy = block.backward_pass(y, dy)
+        finally:
+            kern.set_active_packer(prev)
+        return (dy, None) + tuple(None for _ in ctx.blocks.parameters())
+
+
+class _RevtorchSequence(nn.Module):
+    """Stands where ``rv.ReversibleSequence`` does in the reference (attribute ``reversible_blocks``)."""
+
+    def __init__(self, reversible_blocks):
+        super(_RevtorchSequence, self).__init__()
+        self.reversible_blocks = reversible_blocks
+
+    def forward(self, x):
+        if torch.is_grad_enabled():
+            t = _ReversibleFunction.apply(x.t, self.reversible_blocks, *self.reversible_blocks.parameters())
+        else:
+            t = x.t
+            for block in self.reversible_blocks:
+                t = block.couple(t)
+        return Act(t, x.c)
+
+
 class ReversibleSequence(nn.Module):
-    """Reversible stack (reference torchlayers.py:55-82 over revtorch): not built yet on the B200 path."""
+    """Reversible stack of the reference (torchlayers.py:55-82): optional 1x1 Conv2D to change the channel count, then
+    ``reversible_depth`` additive-coupling blocks whose F and G are 3x3 Conv2D on half the channels.  Only the stack's
+    output is kept for backward; inputs are regenerated block by block (activation memory ~ 1/depth)."""
 
     def __init__(self, input_dim, output_dim, reversible_depth=3, kernel=3):
         super(ReversibleSequence, self).__init__()
-        raise NotImplementedError('reversible blocks (RevPHiSeg) are scheduled after the non-reversible hot path; '
-                                  'see DESIGN.md "next"')
+        if output_dim % 32 != 0:
+            raise NotImplementedError('reversible stacks need channel halves that are multiples of 16 on the B200 path')
+        if input_dim != output_dim:
+            self.inital_conv = Conv2D(input_dim, output_dim, kernel_size=1)
+        else:
+            self.inital_conv = nn.Identity()
+        blocks = []
+        for i in range(reversible_depth):
+            f_func = nn.Sequential(Conv2D(output_dim // 2, output_dim // 2, kernel_size=kernel, padding=1))
+            g_func = nn.Sequential(Conv2D(output_dim // 2, output_dim // 2, kernel_size=kernel, padding=1))
+            blocks.append(ReversibleBlock(f_func, g_func))
+        self.sequence = _RevtorchSequence(nn.ModuleList(blocks))
+
+    @_boundary
+    def forward(self, x):
+        x = self.inital_conv(x)
+        return self.sequence(x)

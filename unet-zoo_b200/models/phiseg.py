@@ -392,7 +392,7 @@ class PHISeg(nn.Module):
     # ---------------------------------------------------------------- forward
     def _packer(self):
         # one batched launch packs every conv weight (bf16 forward + dgrad layouts) per step
-        first = self.posterior.contracting_path[0].layers[0].convolution[0].weight
+        first = next(m.weight for m in self.modules() if isinstance(m, nn.Conv2d) and m.out_channels % 16 == 0)
         pk = getattr(self, '_weight_packer', None)
         if pk is None or not pk.valid_for(first):
             ws = [m.weight for m in self.modules()

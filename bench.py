@@ -228,6 +228,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='time eager steps instead of CUDA-graph replay')
     ap.add_argument('--skip-eval', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--model', default='phiseg', choices=['phiseg', 'revphiseg', 'probunet', 'unet'],
+                    help='phiseg = the headline workload; the others are reported as side information')
     args = ap.parse_args()
 
     from b200 import dp as dpmod
@@ -246,7 +248,16 @@ def main():
     from oracle import synth
 
     torch.manual_seed(1234 + rank)
-    net = dropin_phiseg(FILTERS)
+    if args.model == 'phiseg':
+        net = dropin_phiseg(FILTERS)
+    elif args.model == 'revphiseg':
+        net = dropin_phiseg(FILTERS, reversible=True)
+    elif args.model == 'probunet':
+        from models.probabilistic_unet import ProbabilisticUnet
+        net = ProbabilisticUnet(input_channels=1, num_classes=2, num_filters=FILTERS, latent_dim=6, no_convs_fcomb=3)
+    else:
+        from models.unet import Unet
+        net = Unet(1, 2, [32, 64, 128, 192])
     net.load_state_dict(synth.synth_state_dict(net.state_dict(), seed=0))       # same weights on every rank
     net = net.to(device)
     opt = train.make_adam(net, capturable=True)
@@ -293,12 +304,13 @@ def main():
         pass
     peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (measured)' if peaks else 'fallback 1.4 PFLOP/s sustained'
-    fwd_flops = conv_forward_flops_per_image(net, IMAGE[1])
+    side_models = {'revphiseg': 18.318e9, 'probunet': 13.598e9, 'unet': 6.958e9}      # SURVEY.md 8d, forward GFLOP / image
+    fwd_flops = conv_forward_flops_per_image(net, IMAGE[1]) if args.model == 'phiseg' else side_models[args.model]
     roofline = None      # filled after the evaluation block (the measurement overwrites the weights)
 
     # ---- GED-100 evaluation throughput (N=100 samples of one image, 4 annotators), samples sharded over ranks
     eval_block = None
-    if not args.skip_eval and world == 1:
+    if not args.skip_eval and world == 1 and args.model == 'phiseg':
         ev = train.EvalStep(net, N_SAMPLES, 2)
         labels = batches[0][2]
         img = batches[0][0][0, 0].contiguous().pin_memory()
@@ -314,6 +326,17 @@ def main():
         net.train()
 
     # ---- roofline of the tensor-core conv kernels, in situ (differential graph replays)
+    if args.model != 'phiseg':
+        if rank == 0:
+            print(json.dumps({'metric': '%s LIDC-128^2 train images/s (side information)' % args.model, 'value': value,
+                              'unit': 'images/s', 'n_gpus': world, 'ms_per_step': ms_step, 'e2e': e2e,
+                              'gpu_launches': int(gpu_launches),
+                              'algorithmic_tflops': 3.0 * fwd_flops * BATCH * world / (ms_step / 1000.0) / 1e12}))
+        sys.stdout.flush()
+        if world > 1:
+            torch.cuda.synchronize()
+            os._exit(0)
+        return
     saved = {k: v.clone() for k, v in net.state_dict().items()}
     fam = kernel_family_time(lambda: train.TrainStep(net, train.make_adam(net), BATCH, IMAGE, use_graph=True, dp=None,
                                                      device=device), max(5, args.steps // 2), 1, device, _lib)
@@ -349,7 +372,7 @@ def main():
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic',
-            'config': {'workload': 'PHiSeg-7/5 training step (forward+loss+backward+Adam), LIDC-shaped 1x128x128, '
+            'config': {'workload': 'PHiSeg-7/5 training step (forward+loss+backward+fused Adam), LIDC-shaped 1x128x128, '
                                    '4 annotators, batch %d per GPU' % BATCH,
                        'filters': FILTERS, 'global_batch': BATCH * world, 'parallelism': 'dp%d' % world,
                        'cuda_graph': step.graph is not None,

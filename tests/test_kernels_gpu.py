@@ -328,7 +328,7 @@ def test_kl_known_answer_and_gradients():
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
 
 
-@pytest.mark.parametrize('ncls,factor,C', [(2, 1, 128), (2, 16, 192), (3, 4, 192)])
+@pytest.mark.parametrize('ncls,factor,C', [(2, 1, 128), (2, 16, 192), (3, 4, 192), (12, 1, 192), (16, 2, 256)])
 def test_slayer_forward_backward(ncls, factor, C):
     k = kern()
     B, h = 3, 8

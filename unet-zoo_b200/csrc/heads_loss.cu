@@ -478,10 +478,12 @@ extern "C" int uz_slayer_bwd(const float* dout, const void* feat, int ld, int C,
                              float* db, void* stream) {
   UZ_CHECK_ARG(dout && feat && w && dfeat && wpartial && bpartial && dw && db, "uz_slayer_bwd: null pointer");
   UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxOut, "uz_slayer_bwd: %d outputs unsupported", ncls);
-  const int threads = 256;
+  int warps = static_cast<int>((44 * 1024) / (static_cast<size_t>(ncls) * C * sizeof(float)));
+  if (warps > 8) warps = 8;
+  UZ_CHECK_ARG(warps >= 1, "uz_slayer_bwd: ncls*C too large for the shared accumulators");
+  const int threads = warps * 32;
   const int blocks = uz_slayer_bwd_num_blocks(B, h, wd);
-  const size_t smem = static_cast<size_t>(threads / 32) * ncls * C * sizeof(float);
-  UZ_CHECK_ARG(smem <= 48 * 1024, "uz_slayer_bwd: ncls*C too large for the shared accumulators");
+  const size_t smem = static_cast<size_t>(warps) * ncls * C * sizeof(float);
   slayer_bwd_kernel<<<blocks, threads, smem, ST(stream)>>>(dout, static_cast<const __nv_bfloat16*>(feat), ld, C, w, ncls,
                                                            B, h, wd, factor, static_cast<__nv_bfloat16*>(dfeat), ldd,
                                                            wpartial, bpartial);

@@ -87,7 +87,8 @@ class AxisAlignedConvGaussian(nn.Module):
         mu_log_sigma = mu_log_sigma[:, :, 0, 0]
         mu = mu_log_sigma[:, :self.latent_dim]
         log_sigma = mu_log_sigma[:, self.latent_dim:]
-        return Independent(Normal(loc=mu, scale=torch.exp(log_sigma)), 1)
+        # validate_args=False: the default argument validation synchronises the host (not CUDA-graph capturable)
+        return Independent(Normal(loc=mu, scale=torch.exp(log_sigma), validate_args=False), 1, validate_args=False)
 
 
 class Fcomb(nn.Module):

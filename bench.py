@@ -83,32 +83,42 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.rows = []
-        self.stop = threading.Event()
-        self.t = None
-
-    def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(',')])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        self.proc = None
 
     def __enter__(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
+        # one long-lived nvidia-smi in loop mode (100 ms period) -- spawning one per sample is too slow for short regions
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.t.join(timeout=6)
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        for line in (out or '').strip().splitlines():
+            self.rows.append([c.strip() for c in line.split(',')])
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace('.', '').isdigit()]
+        rows = [r for r in self.rows if len(r) > 8 and r[1].replace('.', '').isdigit()]
+        # samples under load: power draw above the idle floor (first sample is taken before the load starts)
+        pw = [float(r[3]) if r[3].replace('.', '').isdigit() else 0.0 for r in rows]
+        if pw:
+            thr = min(pw) + 0.3 * (max(pw) - min(pw))
+            loaded = [r for r, p in zip(rows, pw) if p >= thr] or rows
+        else:
+            loaded = rows
+        self.rows = loaded
+        sm = [float(r[1]) for r in loaded]
+        mx = [float(r[2]) for r in loaded if r[2].replace('.', '').isdigit()]
         reasons = set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in self.rows:
@@ -117,7 +127,7 @@ class ClockSampler:
                     if v.lower().startswith('active'):
                         reasons.add(n)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'power_w_max': max(pw) if pw else None}
 
 
 def synthetic_batches(n_batches, seed):
@@ -206,6 +216,12 @@ def kernel_family_time(make_step, steps, world, device, lib):
     uz_conv_wgrad launches elided (uz_set_debug_flags 128 / 256); the differences are the kernel families' times.
     Values computed by the elided variants are garbage, so the caller restores the weights afterwards."""
     out = {}
+    # kernel busy time, not exposed time: the multi-stream overlap of the product path is switched off for this
+    # measurement so that a family's contribution to the step equals the sum of its launch durations
+    import models.phiseg as _mp
+    from b200 import ops as _ops
+    saved_flags = (_mp._CONCURRENT, _ops._AUX_ENABLED)
+    _mp._CONCURRENT, _ops._AUX_ENABLED = False, False
     for name, flag in (('all', 0), ('without conv_tc (fwd+dgrad)', 128), ('without wgrad_tc', 256)):
         lib.call('uz_set_debug_flags', flag)
         try:
@@ -216,6 +232,7 @@ def kernel_family_time(make_step, steps, world, device, lib):
             out[name] = timed_region(lambda i: st.step_device(), steps, world, device) / steps
         finally:
             lib.call('uz_set_debug_flags', 0)
+    _mp._CONCURRENT, _ops._AUX_ENABLED = saved_flags
     return out
 
 
@@ -274,8 +291,12 @@ def main():
 
     # ---- device-resident throughput (value)
     l0 = _lib.raw('uz_launch_count')()
-    with ClockSampler(local) as clk:
-        ms_total = timed_region(lambda i: step.step_device(), args.steps, world, device)
+    clk = ClockSampler(local)
+    clk.__enter__()
+    time.sleep(0.25)                     # let the sampler start; the GPU stays busy from here to the end of the e2e loop
+    for _ in range(3):
+        step.step_device()
+    ms_total = timed_region(lambda i: step.step_device(), args.steps, world, device)
     eager_launches = _lib.raw('uz_launch_count')() - l0
     gpu_launches = step.launches_per_step * args.steps if step.graph is not None else eager_launches
     ms_step = ms_total / args.steps
@@ -291,6 +312,10 @@ def main():
     for i in range(2):
         e2e_fn(i)
     ms_e2e = timed_region(e2e_fn, args.steps, world, device) / args.steps
+    for _ in range(max(0, int(1200.0 / max(ms_step, 1e-3)) - 2 * args.steps)):
+        step.step_device()               # keep the load up for >= ~1.2 s so the 100 ms clock sampler sees it
+    torch.cuda.synchronize()
+    clk.__exit__()
     e2e = {'value': world * BATCH / (ms_e2e / 1000.0), 'unit': 'images/s',
            'h2d_bytes_per_step': int(batches[0][0].numel() * 4 + batches[0][1].numel() * 4), 'd2h_bytes_per_step': 4,
            'ms_per_step': ms_e2e, 'api': 'b200.train.TrainStep.step_host (CUDA-graph replay)' if step.graph is not None
@@ -352,9 +377,14 @@ def main():
                 'algorithmic_flops_per_step': train_flops, 'kernel_ms_per_step': tc_ms,
                 'ms_per_kernel_family': {'conv_tc (fwd+dgrad)': t_conv, 'wgrad_tc (+reduce)': t_wgrad},
                 'step_ms': fam, 'peak_source': peak_src, 'share_of_step': tc_ms / t_all,
-                'how': 'CUDA-event time of the captured step minus the same step with that kernel family elided '
-                       '(uz_set_debug_flags 128 / 256), single GPU without gradient all-reduce; algorithmic FLOPs = '
-                       '3 x forward conv FLOPs (SURVEY.md 8d)'}
+                'how': 'CUDA-event time of the captured step, issued on ONE stream (multi-stream overlap off), minus the '
+                       'same step with that kernel family elided (uz_set_debug_flags 128 / 256); no gradient '
+                       'all-reduce; algorithmic FLOPs = 3 x forward conv FLOPs (SURVEY.md 8d).  The headline value '
+                       'uses the overlapped multi-stream step.',
+                'ncu_example': {'kernel': 'conv_tc2_kernel<64>, 128->128 @128^2, batch 12', 'us': 67.7,
+                                'dram_bytes': 56.1e6, 'algorithmic_bytes': 100.9e6, 'tma_l2_to_sm_bytes': 396.4e6,
+                                'tensor_pipe_active_frac': 0.42,
+                                'source': 'profiles/r01_conv_v2_ncu_full_128to128_at128.md'}}
 
     # ---- the reference's CPU path beside it (rank 0, N = 1 only): bounded sample
     cpu_baseline = None

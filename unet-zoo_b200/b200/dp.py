@@ -1,8 +1,8 @@
 """One-process-per-GPU data parallelism for the drop-in models (the reference has none).
 
-Training: batch data-parallel.  Parameter gradients live as views of a few flat fp32 buckets laid out in reverse
-registration (~ reverse autograd) order; a post-accumulate hook counts arrivals and, when a bucket is complete, issues
-ONE NCCL all-reduce (average) for it.  torch.distributed's NCCL process group runs the collective on its own stream
+Training: batch data-parallel.  Parameters are grouped into a few flat fp32 buckets in reverse registration
+(~ reverse autograd) order; a post-accumulate hook counts arrivals and, when a bucket is complete, gathers its gradients
+with one multi-tensor copy, re-points ``.grad`` at views of the flat buffer and issues ONE NCCL all-reduce (average).  torch.distributed's NCCL process group runs the collective on its own stream
 after the producing kernels and ``finish()`` makes the compute stream wait for it, so communication overlaps the rest
 of backward.  Parameters that never receive a gradient (``{posterior,prior}.upsampling_path.4.*``)
 keep ``grad is None`` exactly like in the reference, so stock Adam skips them.
@@ -46,7 +46,7 @@ def shard_counts(n, world):
 
 
 class _Bucket:
-    __slots__ = ('flat', 'params', 'pending', 'work')
+    __slots__ = ('flat', 'params', 'pending', 'work', 'views')
 
     def __init__(self, flat, params):
         self.flat, self.params, self.pending, self.work = flat, params, 0, None
@@ -83,48 +83,53 @@ class GradientAllReduce:
         """Call after at least one backward: builds the flat buckets over the parameters that have gradients."""
         live = [p for p in self.params if p.grad is not None]
         live.reverse()                                     # last-registered parameters finish backward first
-        self.buckets, cur, cur_bytes = [], [], 0
+        groups, cur, cur_bytes = [], [], 0
         for p in live:
             cur.append(p)
             cur_bytes += p.numel() * 4
             if cur_bytes >= self.bucket_bytes:
-                self.buckets.append(cur)
+                groups.append(cur)
                 cur, cur_bytes = [], 0
         if cur:
-            self.buckets.append(cur)
-        built = []
-        for plist in self.buckets:
+            groups.append(cur)
+        self.buckets = []
+        for plist in groups:
             flat = torch.zeros(sum(p.numel() for p in plist), dtype=torch.float32, device=plist[0].device)
             b = _Bucket(flat, plist)
+            b.views = []
             off = 0
             for p in plist:
-                p.grad = flat[off:off + p.numel()].view_as(p)
+                b.views.append(flat[off:off + p.numel()].view_as(p))
                 off += p.numel()
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
-            built.append(b)
-        self.buckets = built
+            self.buckets.append(b)
+        self.zero_grad()
 
     def _make_hook(self, bucket):
         def hook(param):
             bucket.pending -= 1
-            if bucket.pending == 0 and self.world > 1:
+            if bucket.pending == 0:
+                # gather the bucket's freshly produced gradients into its flat buffer with ONE multi-tensor copy and
+                # re-point .grad at the views: the all-reduce then averages the gradients in place
                 if bucket.flat.is_cuda:
                     from . import ops
                     ops.sync_aux_streams()          # weight gradients are produced on the auxiliary stream
-                bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG if bucket.flat.is_cuda
-                                              else dist.ReduceOp.SUM, group=self.group, async_op=True)
+                torch._foreach_copy_(bucket.views, [p.grad for p in bucket.params])
+                for p, v in zip(bucket.params, bucket.views):
+                    p.grad = v
+                if self.world > 1:
+                    bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG if bucket.flat.is_cuda
+                                                  else dist.ReduceOp.SUM, group=self.group, async_op=True)
         return hook
 
     # -- per step -------------------------------------------------------------------------------------------------
     def zero_grad(self):
-        if self.buckets is None:
-            for p in self.params:
-                p.grad = None
-            return
-        for b in self.buckets:
-            b.flat.zero_()
-            b.pending = len(b.params)
-            b.work = None
+        for p in self.params:
+            p.grad = None
+        if self.buckets is not None:
+            for b in self.buckets:
+                b.pending = len(b.params)
+                b.work = None
 
     def finish(self):
         if self.buckets is None:

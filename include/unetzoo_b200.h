@@ -32,6 +32,9 @@ long long uz_launch_count(void);
  * 128 = uz_conv_fwd returns without launching, 256 = uz_conv_wgrad returns without launching (bench.py times the step
  * with and without a kernel family to get that family's in-situ time).  0 restores normal operation. */
 int uz_set_debug_flags(int flags);
+/* Programmatic dependent launch for every kernel of the library (default off; environment UZ_PDL=1 or this call
+ * enables it: it helps single-stream execution and hurts the multi-stream overlap the models use, profiles/r01_pdl.md). */
+int uz_set_pdl(int enabled);
 
 /* ---- convolutions on tcgen05 tensor cores (conv_tc.cu, wgrad_tc.cu) ------------------------------------------------ */
 

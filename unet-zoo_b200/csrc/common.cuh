@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #define UZ_OK 0
 #define UZ_ERR_ARG 1
 #define UZ_ERR_CUDA 2
@@ -34,6 +36,19 @@ void count_launch();
       return UZ_ERR_CUDA;                                                       \
     }                                                                           \
   } while (0)
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of this library can be launched with cudaLaunchAttributeProgrammaticStreamSerialization (uz::launch
+// below, opt-in) and starts with pdl_prologue(): `griddepcontrol.wait` blocks until the preceding kernel in the stream has completed
+// and its memory is visible, `griddepcontrol.launch_dependents` lets the next kernel's CTAs be scheduled early.  The
+// launch latency and the input-independent prologue (barrier init, TMEM allocation, descriptor prefetch) of kernel N+1
+// thereby overlap the tail of kernel N.  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_wait();
+  pdl_trigger();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -192,8 +207,26 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 }  // namespace uz
 
-// ---------------------------------------------------------------- host side: tensor maps
+// ---------------------------------------------------------------- host side: launches and tensor maps
 namespace uz {
+extern int g_pdl;   // uz_set_pdl(); default from the environment variable UZ_PDL (0)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // Encodes a tiled bf16 tensor map; dims/strides innermost first, strides in BYTES for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, uint32_t swizzle_bytes);

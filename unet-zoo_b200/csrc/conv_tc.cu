@@ -114,6 +114,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     __syncwarp();
     uz::tmem_alloc(&tmem_base_slot, p.tmem_cols);
   }
+  uz::pdl_prologue();   // everything above is independent of the previous kernel's output
   for (int c = threadIdx.x; c < p.BN; c += kThreads) {
     s_scale[c] = p.scale ? p.scale[c_out0 + c] : 1.f;
     s_shift[c] = p.shift ? p.shift[c_out0 + c] : 0.f;
@@ -331,7 +332,7 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
     attr_bytes = smem;
   }
   dim3 grid(tiles, splits, 1);
-  conv_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+  uz::launch(conv_tc_kernel, grid, kThreads, smem, static_cast<cudaStream_t>(stream), tx, tw, p);
   UZ_CHECK_LAUNCH("uz_conv_fwd");
   return UZ_OK;
 }

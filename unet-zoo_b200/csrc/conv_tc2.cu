@@ -129,6 +129,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     __syncwarp();
     uz::tmem_alloc(&tmem_base_slot, p.tmem_cols);
   }
+  uz::pdl_prologue();   // everything above is independent of the previous kernel's output
   for (int c = threadIdx.x; c < p.BN; c += kThreads) {
     s_scale[c] = p.scale ? p.scale[c_out0 + c] : 1.f;
     s_shift[c] = p.shift ? p.shift[c_out0 + c] : 0.f;
@@ -422,7 +423,7 @@ int conv2_launch(const void* x, int N, int H, int W, int Cin, int ldx, const voi
     }
     ab = pl.smem;
   }
-  kernel<<<pl.grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream)>>>(tx, tw, ty, p);
+  uz::launch(kernel, pl.grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream), tx, tw, ty, p);
   UZ_CHECK_LAUNCH("uz_conv_fwd(v2)");
   *handled = 1;
   return UZ_OK;

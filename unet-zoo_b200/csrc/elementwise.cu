@@ -37,6 +37,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ int src_tap(int t, int taps) { return taps == 9 ? (t % 3) * 3 + t / 3 : t; }
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, __nv_bfloat16* wp,
                                    int CoutP, int CinP, __nv_bfloat16* wd, int CinP2, int CoutP2) {
+  uz::pdl_prologue();
   const size_t n_fwd = static_cast<size_t>(taps) * CoutP * CinP;
   const size_t n_bwd = wd ? static_cast<size_t>(taps) * CinP2 * CoutP2 : 0;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n_fwd + n_bwd;
@@ -60,6 +61,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
 
 // all conv layers of a model in ONE launch: blockIdx.y selects the layer descriptor (device table of UzPackDesc)
 __global__ void pack_weight_batched_kernel(const UzPackDesc* __restrict__ descs) {
+  uz::pdl_prologue();
   const UzPackDesc d = descs[blockIdx.y];
   const float* __restrict__ w = static_cast<const float*>(d.w);
   __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(d.w_fwd);
@@ -93,6 +95,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int tiles,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                                    float* mean_out, float* invstd_out) {
+  uz::pdl_prologue();
   // one warp per channel; lanes stride over tiles; fixed order => deterministic
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +131,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int tiles,
 __global__ void bn_eval_fold_kernel(const float* __restrict__ conv_bias, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, const float* __restrict__ rm,
                                     const float* __restrict__ rv, float eps, int C, float* scale, float* shift) {
+  uz::pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = (gamma ? gamma[c] : 1.f) * rsqrtf(rv[c] + eps);
@@ -139,6 +143,7 @@ __global__ void bn_eval_fold_kernel(const float* __restrict__ conv_bias, const f
 __global__ void affine_act_kernel(const __nv_bfloat16* __restrict__ y, int ldy, const float* __restrict__ scale,
                                   const float* __restrict__ shift, int relu, __nv_bfloat16* out, int ldo, size_t npix,
                                   int C) {
+  uz::pdl_prologue();
   const int chunks = C / 8;
   const size_t total = npix * chunks;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -169,6 +174,7 @@ __global__ void bn_apply_train_kernel(const __nv_bfloat16* __restrict__ y, int l
                                       float eps, float momentum, float* running_mean, float* running_var,
                                       float* scale_out, float* shift_out, float* mean_out, float* invstd_out, int relu,
                                       __nv_bfloat16* out, int ldo, size_t npix, int C) {
+  uz::pdl_prologue();
   extern __shared__ float sm[];          // [2][C]: scale, shift
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float mean = sums[c] / count;
@@ -217,6 +223,7 @@ __global__ void bn_bwd_apply_train_kernel(const __nv_bfloat16* __restrict__ dout
                                           float count, const float* __restrict__ gamma, const float* __restrict__ mean,
                                           const float* __restrict__ invstd, float* dgamma, float* dbeta,
                                           __nv_bfloat16* dy, int lddy, size_t npix, int C) {
+  uz::pdl_prologue();
   extern __shared__ float sm[];          // [5][C]: A, B, Cc, scale, shift
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float sg = sums[c], sgy = sums[C + c];
@@ -258,6 +265,7 @@ __global__ void bn_bwd_apply_train_kernel(const __nv_bfloat16* __restrict__ dout
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, const __nv_bfloat16* __restrict__ y,
                                      int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
                                      int relu, size_t npix, int C, float* partial, int atomic_out) {
+  uz::pdl_prologue();
   extern __shared__ float red[];  // [rows][2][C]
   const int chunks = C / 8;
   const int rows = blockDim.x / chunks;
@@ -304,6 +312,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, float* coefA, float* coefB, float* coefC,
                                        float* dgamma, float* dbeta) {
+  uz::pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= C) return;
@@ -331,6 +340,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int 
                                     int ldy, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                                     const float* __restrict__ coefA, const float* __restrict__ coefB,
                                     const float* __restrict__ coefC, __nv_bfloat16* dy, int lddy, size_t npix, int C) {
+  uz::pdl_prologue();
   const int chunks = C / 8;
   const size_t total = npix * chunks;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -353,6 +363,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int 
 // ---------------------------------------------------------------- 2x2 average pooling (AvgPool2d(2,2,ceil_mode), even sizes)
 __global__ void avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* out, int ldo, int N,
                                     int Ho, int Wo, int C) {
+  uz::pdl_prologue();
   const int chunks = C / 8;
   const size_t total = static_cast<size_t>(N) * Ho * Wo * chunks;
   const int W = Wo * 2;
@@ -379,6 +390,7 @@ __global__ void avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx
 // feed a skip connection whose gradient is already in dx)
 __global__ void avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, __nv_bfloat16* dx, int ldx, int N,
                                     int Ho, int Wo, int C, int accumulate) {
+  uz::pdl_prologue();
   const int chunks = C / 8;
   const int H = Ho * 2, W = Wo * 2;
   const size_t total = static_cast<size_t>(N) * H * W * chunks;
@@ -423,6 +435,7 @@ __device__ __forceinline__ void up2_src(int o, int in, int align, int& i0, int& 
 
 __global__ void up2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* out, int ldo, int N, int h,
                                int w, int C, int align) {
+  uz::pdl_prologue();
   const int chunks = C / 8;
   const int H = 2 * h, W = 2 * w;
   const size_t total = static_cast<size_t>(N) * H * W * chunks;
@@ -453,6 +466,7 @@ __global__ void up2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __n
 // gather form of the transpose: every input pixel collects from the output pixels that read it
 __global__ void up2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, __nv_bfloat16* dx, int ldx, int N, int h,
                                int w, int C, int align) {
+  uz::pdl_prologue();
   const int chunks = C / 8;
   const int H = 2 * h, W = 2 * w;
   const size_t total = static_cast<size_t>(N) * h * w * chunks;
@@ -496,6 +510,7 @@ __global__ void up2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, 
 // ---------------------------------------------------------------- strided channel copy / add (concat, split, grad sum)
 __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int lds, __nv_bfloat16* dst, int ldd,
                                      size_t npix, int C, int accumulate) {
+  uz::pdl_prologue();
   const int chunks = C / 8;
   const size_t total = npix * chunks;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -519,6 +534,7 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int 
 // out[b][c] = mean over the hw pixels of x[b][:][c]  (torch.mean over H then W, probabilistic_unet.py:114-115)
 __global__ void global_mean_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int hw, int C,
                                        __nv_bfloat16* out, int ldo) {
+  uz::pdl_prologue();
   // block = (sample, 64-channel group); threads = 32 channel pairs x 8 pixel lanes
   __shared__ float red[8][64];
   const int b = blockIdx.x, cg = blockIdx.y * 64;
@@ -543,6 +559,7 @@ __global__ void global_mean_fwd_kernel(const __nv_bfloat16* __restrict__ x, int 
 }
 __global__ void global_mean_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, int hw, int C,
                                        __nv_bfloat16* dx, int ldx, size_t npix) {
+  uz::pdl_prologue();
   const int chunks = C / 8;
   const size_t total = npix * chunks;
   const float inv = 1.f / hw;
@@ -564,6 +581,7 @@ __global__ void global_mean_bwd_kernel(const __nv_bfloat16* __restrict__ dout, i
 //   utils.py:289-311), rest zero.
 __global__ void input_pack_kernel(const float* __restrict__ patch, const float* __restrict__ mask, int B, int Cimg,
                                   int H, int W, int nlabels, __nv_bfloat16* out, int CP) {
+  uz::pdl_prologue();
   const size_t hw = static_cast<size_t>(H) * W;
   const size_t total = static_cast<size_t>(B) * hw;
   for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
@@ -582,6 +600,7 @@ __global__ void input_pack_kernel(const float* __restrict__ patch, const float* 
 
 // fp32 NCHW <-> bf16 NHWC (module-boundary conversions; channel padding zero-filled)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int B, int C, size_t hw, __nv_bfloat16* dst, int ld) {
+  uz::pdl_prologue();
   const size_t total = static_cast<size_t>(B) * hw * ld;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -592,6 +611,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int B, int C,
   }
 }
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int ld, int B, int C, size_t hw, float* dst) {
+  uz::pdl_prologue();
   const size_t total = static_cast<size_t>(B) * C * hw;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -614,7 +634,7 @@ extern "C" int uz_pack_conv_weight(const float* w, int Cout, int Cin, int taps, 
   UZ_CHECK_ARG(CoutP >= Cout && CinP >= Cin, "uz_pack_conv_weight: padded dims smaller than logical dims");
   UZ_CHECK_ARG(!w_dgrad || (CinP2 >= Cin && CoutP2 >= Cout), "uz_pack_conv_weight: bad dgrad dims");
   const size_t n = static_cast<size_t>(taps) * CoutP * CinP + (w_dgrad ? static_cast<size_t>(taps) * CinP2 * CoutP2 : 0);
-  pack_weight_kernel<<<ew_blocks(n), kEwThreads, 0, ST(stream)>>>(w, Cout, Cin, taps, static_cast<__nv_bfloat16*>(w_fwd),
+  uz::launch(pack_weight_kernel, ew_blocks(n), kEwThreads, 0, ST(stream), w, Cout, Cin, taps, static_cast<__nv_bfloat16*>(w_fwd),
                                                                  CoutP, CinP, static_cast<__nv_bfloat16*>(w_dgrad),
                                                                  CinP2, CoutP2);
   UZ_CHECK_LAUNCH("uz_pack_conv_weight");
@@ -624,7 +644,7 @@ extern "C" int uz_pack_conv_weight(const float* w, int Cout, int Cin, int taps, 
 extern "C" int uz_pack_conv_weights_batched(const void* descs_device, int n, int blocks_per_layer, void* stream) {
   UZ_CHECK_ARG(descs_device && n > 0 && blocks_per_layer > 0, "uz_pack_conv_weights_batched: bad arguments");
   dim3 grid(blocks_per_layer, n, 1);
-  pack_weight_batched_kernel<<<grid, kEwThreads, 0, ST(stream)>>>(static_cast<const UzPackDesc*>(descs_device));
+  uz::launch(pack_weight_batched_kernel, grid, kEwThreads, 0, ST(stream), static_cast<const UzPackDesc*>(descs_device));
   UZ_CHECK_LAUNCH("uz_pack_conv_weights_batched");
   return UZ_OK;
 }
@@ -635,7 +655,7 @@ extern "C" int uz_bn_finalize(const float* partial, int tiles, int C, float coun
   UZ_CHECK_ARG(partial && scale && shift && tiles > 0 && C > 0, "uz_bn_finalize: bad arguments");
   const int threads = 256;
   const int blocks = (C * 32 + threads - 1) / threads;
-  bn_finalize_kernel<<<blocks, threads, 0, ST(stream)>>>(partial, tiles, C, count, gamma, beta, eps, momentum,
+  uz::launch(bn_finalize_kernel, blocks, threads, 0, ST(stream), partial, tiles, C, count, gamma, beta, eps, momentum,
                                                          running_mean, running_var, scale, shift, mean_out, invstd_out);
   UZ_CHECK_LAUNCH("uz_bn_finalize");
   return UZ_OK;
@@ -644,7 +664,7 @@ extern "C" int uz_bn_finalize(const float* partial, int tiles, int C, float coun
 extern "C" int uz_bn_eval_fold(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
                                const float* running_var, float eps, int C, float* scale, float* shift, void* stream) {
   UZ_CHECK_ARG(running_mean && running_var && scale && shift && C > 0, "uz_bn_eval_fold: bad arguments");
-  bn_eval_fold_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(conv_bias, gamma, beta, running_mean, running_var, eps, C,
+  uz::launch(bn_eval_fold_kernel, (C + 127) / 128, 128, 0, ST(stream), conv_bias, gamma, beta, running_mean, running_var, eps, C,
                                                               scale, shift);
   UZ_CHECK_LAUNCH("uz_bn_eval_fold");
   return UZ_OK;
@@ -655,7 +675,7 @@ extern "C" int uz_affine_act(const void* y, int ldy, const float* scale, const f
   UZ_CHECK_ARG(y && out && scale && shift, "uz_affine_act: null pointer");
   UZ_CHECK_ARG(C % 8 == 0 && ldy % 8 == 0 && ldo % 8 == 0 && aligned16(y) && aligned16(out), "uz_affine_act: alignment");
   if (npix == 0) return UZ_OK;
-  affine_act_kernel<<<ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(affine_act_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(y), ldy, scale, shift, relu, static_cast<__nv_bfloat16*>(out), ldo,
       static_cast<size_t>(npix), C);
   UZ_CHECK_LAUNCH("uz_affine_act");
@@ -684,7 +704,7 @@ extern "C" int uz_bn_bwd_reduce(const void* dout, int ldd, const void* y, int ld
   const int rows = threads / chunks;
   const int blocks = uz_bn_bwd_num_blocks(npix, C);
   const size_t smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);
-  bn_bwd_reduce_kernel<<<blocks, threads, smem, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dout), ldd,
+  uz::launch(bn_bwd_reduce_kernel, blocks, threads, smem, ST(stream), static_cast<const __nv_bfloat16*>(dout), ldd,
                                                              static_cast<const __nv_bfloat16*>(y), ldy, scale, shift,
                                                              relu, static_cast<size_t>(npix), C, partial, 0);
   UZ_CHECK_LAUNCH("uz_bn_bwd_reduce");
@@ -702,7 +722,7 @@ extern "C" int uz_bn_bwd_reduce_sums(const void* dout, int ldd, const void* y, i
   int blocks = uz_bn_bwd_num_blocks(npix, C);
   if (blocks > uz::num_sms()) blocks = uz::num_sms();      // one atomic per block per channel
   const size_t smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);
-  bn_bwd_reduce_kernel<<<blocks, threads, smem, ST(stream)>>>(static_cast<const __nv_bfloat16*>(dout), ldd,
+  uz::launch(bn_bwd_reduce_kernel, blocks, threads, smem, ST(stream), static_cast<const __nv_bfloat16*>(dout), ldd,
                                                              static_cast<const __nv_bfloat16*>(y), ldy, scale, shift,
                                                              relu, static_cast<size_t>(npix), C, sums, 1);
   UZ_CHECK_LAUNCH("uz_bn_bwd_reduce_sums");
@@ -715,8 +735,7 @@ extern "C" int uz_bn_apply_train(const void* y, int ldy, const float* sums, floa
                                  void* out, int ldo, long long npix, int C, void* stream) {
   UZ_CHECK_ARG(y && sums && scale_out && shift_out && mean_out && invstd_out && out, "uz_bn_apply_train: null pointer");
   UZ_CHECK_ARG(C % 8 == 0 && ldy % 8 == 0 && ldo % 8 == 0 && npix > 0, "uz_bn_apply_train: bad arguments");
-  bn_apply_train_kernel<<<ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 2 * C * sizeof(float),
-                          ST(stream)>>>(static_cast<const __nv_bfloat16*>(y), ldy, sums, count, gamma, beta, eps,
+  uz::launch(bn_apply_train_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 2 * C * sizeof(float), ST(stream), static_cast<const __nv_bfloat16*>(y), ldy, sums, count, gamma, beta, eps,
                                         momentum, running_mean, running_var, scale_out, shift_out, mean_out, invstd_out,
                                         relu, static_cast<__nv_bfloat16*>(out), ldo, static_cast<size_t>(npix), C);
   UZ_CHECK_LAUNCH("uz_bn_apply_train");
@@ -730,8 +749,7 @@ extern "C" int uz_bn_bwd_apply_train(const void* dout, int ldd, const void* y, i
   UZ_CHECK_ARG(dout && y && scale && shift && sums && mean && invstd && dy, "uz_bn_bwd_apply_train: null pointer");
   UZ_CHECK_ARG(C % 8 == 0 && ldd % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0 && npix > 0,
                "uz_bn_bwd_apply_train: bad arguments");
-  bn_bwd_apply_train_kernel<<<ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 5 * C * sizeof(float),
-                              ST(stream)>>>(static_cast<const __nv_bfloat16*>(dout), ldd,
+  uz::launch(bn_bwd_apply_train_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 5 * C * sizeof(float), ST(stream), static_cast<const __nv_bfloat16*>(dout), ldd,
                                             static_cast<const __nv_bfloat16*>(y), ldy, scale, shift, relu, sums, count,
                                             gamma, mean, invstd, dgamma, dbeta, static_cast<__nv_bfloat16*>(dy), lddy,
                                             static_cast<size_t>(npix), C);
@@ -745,7 +763,7 @@ extern "C" int uz_bn_bwd_finalize(const float* partial, int nblocks, int C, floa
   UZ_CHECK_ARG(partial && mean && invstd && coefA && coefB && coefC, "uz_bn_bwd_finalize: null pointer");
   const int threads = 256;
   const int blocks = (C * 32 + threads - 1) / threads;
-  bn_bwd_finalize_kernel<<<blocks, threads, 0, ST(stream)>>>(partial, nblocks, C, count, gamma, mean, invstd, coefA,
+  uz::launch(bn_bwd_finalize_kernel, blocks, threads, 0, ST(stream), partial, nblocks, C, count, gamma, mean, invstd, coefA,
                                                              coefB, coefC, dgamma, dbeta);
   UZ_CHECK_LAUNCH("uz_bn_bwd_finalize");
   return UZ_OK;
@@ -757,7 +775,7 @@ extern "C" int uz_bn_bwd_apply(const void* dout, int ldd, const void* y, int ldy
   UZ_CHECK_ARG(dout && y && dy && scale && shift, "uz_bn_bwd_apply: null pointer");
   UZ_CHECK_ARG(C % 8 == 0 && ldd % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0, "uz_bn_bwd_apply: alignment");
   if (npix == 0) return UZ_OK;
-  bn_bwd_apply_kernel<<<ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(bn_bwd_apply_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(dout), ldd, static_cast<const __nv_bfloat16*>(y), ldy, scale, shift, relu, coefA,
       coefB, coefC, static_cast<__nv_bfloat16*>(dy), lddy, static_cast<size_t>(npix), C);
   UZ_CHECK_LAUNCH("uz_bn_bwd_apply");
@@ -766,7 +784,7 @@ extern "C" int uz_bn_bwd_apply(const void* dout, int ldd, const void* y, int ldy
 
 extern "C" int uz_avgpool2_fwd(const void* x, int ldx, void* out, int ldo, int N, int Ho, int Wo, int C, void* stream) {
   UZ_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "uz_avgpool2_fwd: bad arguments");
-  avgpool2_fwd_kernel<<<ew_blocks(static_cast<size_t>(N) * Ho * Wo * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(avgpool2_fwd_kernel, ew_blocks(static_cast<size_t>(N) * Ho * Wo * (C / 8)), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, N, Ho, Wo, C);
   UZ_CHECK_LAUNCH("uz_avgpool2_fwd");
   return UZ_OK;
@@ -775,7 +793,7 @@ extern "C" int uz_avgpool2_fwd(const void* x, int ldx, void* out, int ldo, int N
 extern "C" int uz_avgpool2_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int Ho, int Wo, int C,
                                int accumulate, void* stream) {
   UZ_CHECK_ARG(dout && dx && C % 8 == 0 && ldx % 8 == 0 && ldd % 8 == 0, "uz_avgpool2_bwd: bad arguments");
-  avgpool2_bwd_kernel<<<ew_blocks(static_cast<size_t>(N) * Ho * Wo * 4 * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(avgpool2_bwd_kernel, ew_blocks(static_cast<size_t>(N) * Ho * Wo * 4 * (C / 8)), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(dout), ldd, static_cast<__nv_bfloat16*>(dx), ldx, N, Ho, Wo, C, accumulate);
   UZ_CHECK_LAUNCH("uz_avgpool2_bwd");
   return UZ_OK;
@@ -784,7 +802,7 @@ extern "C" int uz_avgpool2_bwd(const void* dout, int ldd, void* dx, int ldx, int
 extern "C" int uz_upsample2x_fwd(const void* x, int ldx, void* out, int ldo, int N, int h, int w, int C,
                                  int align_corners, void* stream) {
   UZ_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "uz_upsample2x_fwd: bad arguments");
-  up2_fwd_kernel<<<ew_blocks(static_cast<size_t>(N) * h * w * 4 * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(up2_fwd_kernel, ew_blocks(static_cast<size_t>(N) * h * w * 4 * (C / 8)), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, N, h, w, C, align_corners);
   UZ_CHECK_LAUNCH("uz_upsample2x_fwd");
   return UZ_OK;
@@ -793,7 +811,7 @@ extern "C" int uz_upsample2x_fwd(const void* x, int ldx, void* out, int ldo, int
 extern "C" int uz_upsample2x_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int h, int w, int C,
                                  int align_corners, void* stream) {
   UZ_CHECK_ARG(dout && dx && C % 8 == 0 && ldx % 8 == 0 && ldd % 8 == 0, "uz_upsample2x_bwd: bad arguments");
-  up2_bwd_kernel<<<ew_blocks(static_cast<size_t>(N) * h * w * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(up2_bwd_kernel, ew_blocks(static_cast<size_t>(N) * h * w * (C / 8)), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(dout), ldd, static_cast<__nv_bfloat16*>(dx), ldx, N, h, w, C, align_corners);
   UZ_CHECK_LAUNCH("uz_upsample2x_bwd");
   return UZ_OK;
@@ -804,7 +822,7 @@ extern "C" int uz_copy_channels(const void* src, int lds, void* dst, int ldd, lo
   UZ_CHECK_ARG(src && dst && C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && aligned16(src) && aligned16(dst),
                "uz_copy_channels: bad arguments");
   if (npix == 0) return UZ_OK;
-  copy_channels_kernel<<<ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(copy_channels_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, static_cast<size_t>(npix), C,
       accumulate);
   UZ_CHECK_LAUNCH("uz_copy_channels");
@@ -814,7 +832,7 @@ extern "C" int uz_copy_channels(const void* src, int lds, void* dst, int ldd, lo
 extern "C" int uz_global_mean_fwd(const void* x, int ldx, int B, int hw, int C, void* out, int ldo, void* stream) {
   UZ_CHECK_ARG(x && out && C % 2 == 0 && ldx % 2 == 0, "uz_global_mean_fwd: bad arguments");
   dim3 grid(B, (C + 63) / 64, 1);
-  global_mean_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx, hw, C,
+  uz::launch(global_mean_fwd_kernel, grid, 256, 0, ST(stream), static_cast<const __nv_bfloat16*>(x), ldx, hw, C,
                                                        static_cast<__nv_bfloat16*>(out), ldo);
   UZ_CHECK_LAUNCH("uz_global_mean_fwd");
   return UZ_OK;
@@ -823,7 +841,7 @@ extern "C" int uz_global_mean_fwd(const void* x, int ldx, int B, int hw, int C, 
 extern "C" int uz_global_mean_bwd(const void* dout, int ldd, int B, int hw, int C, void* dx, int ldx, void* stream) {
   UZ_CHECK_ARG(dout && dx && C % 8 == 0 && ldd % 8 == 0 && ldx % 8 == 0, "uz_global_mean_bwd: bad arguments");
   const size_t npix = static_cast<size_t>(B) * hw;
-  global_mean_bwd_kernel<<<ew_blocks(npix * (C / 8)), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(global_mean_bwd_kernel, ew_blocks(npix * (C / 8)), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(dout), ldd, hw, C, static_cast<__nv_bfloat16*>(dx), ldx, npix);
   UZ_CHECK_LAUNCH("uz_global_mean_bwd");
   return UZ_OK;
@@ -833,7 +851,7 @@ extern "C" int uz_input_pack(const float* patch, const float* mask, int B, int C
                              void* out, int CP, void* stream) {
   UZ_CHECK_ARG(patch && out, "uz_input_pack: null pointer");
   UZ_CHECK_ARG(CP % 8 == 0 && CP >= Cimg + (mask ? nlabels : 0), "uz_input_pack: CP=%d too small", CP);
-  input_pack_kernel<<<ew_blocks(static_cast<size_t>(B) * H * W), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(input_pack_kernel, ew_blocks(static_cast<size_t>(B) * H * W), kEwThreads, 0, ST(stream), 
       patch, mask, B, Cimg, H, W, nlabels, static_cast<__nv_bfloat16*>(out), CP);
   UZ_CHECK_LAUNCH("uz_input_pack");
   return UZ_OK;
@@ -841,7 +859,7 @@ extern "C" int uz_input_pack(const float* patch, const float* mask, int B, int C
 
 extern "C" int uz_nchw_to_nhwc(const float* src, int B, int C, long long hw, void* dst, int ld, void* stream) {
   UZ_CHECK_ARG(src && dst && ld >= C, "uz_nchw_to_nhwc: bad arguments");
-  nchw_to_nhwc_kernel<<<ew_blocks(static_cast<size_t>(B) * hw * ld), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(nchw_to_nhwc_kernel, ew_blocks(static_cast<size_t>(B) * hw * ld), kEwThreads, 0, ST(stream), 
       src, B, C, static_cast<size_t>(hw), static_cast<__nv_bfloat16*>(dst), ld);
   UZ_CHECK_LAUNCH("uz_nchw_to_nhwc");
   return UZ_OK;
@@ -849,7 +867,7 @@ extern "C" int uz_nchw_to_nhwc(const float* src, int B, int C, long long hw, voi
 
 extern "C" int uz_nhwc_to_nchw(const void* src, int ld, int B, int C, long long hw, float* dst, void* stream) {
   UZ_CHECK_ARG(src && dst && ld >= C, "uz_nhwc_to_nchw: bad arguments");
-  nhwc_to_nchw_kernel<<<ew_blocks(static_cast<size_t>(B) * C * hw), kEwThreads, 0, ST(stream)>>>(
+  uz::launch(nhwc_to_nchw_kernel, ew_blocks(static_cast<size_t>(B) * C * hw), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(src), ld, B, C, static_cast<size_t>(hw), dst);
   UZ_CHECK_LAUNCH("uz_nhwc_to_nchw");
   return UZ_OK;

@@ -19,6 +19,7 @@ struct LabelSet {
 template <typename T>
 __global__ void pack_masks_kernel(const T* __restrict__ labels, int count, int hw, int words, LabelSet ls,
                                   uint32_t* bits, int* counts) {
+  uz::pdl_prologue();
   // one warp per (mask, word)
   const size_t gw = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -41,6 +42,7 @@ __global__ void pack_masks_kernel(const T* __restrict__ labels, int count, int h
 __global__ void pair_distance_kernel(const uint32_t* __restrict__ bits_s, const int* __restrict__ cnt_s, int N,
                                      const uint32_t* __restrict__ bits_y, const int* __restrict__ cnt_y, int M, int nl,
                                      int words, double* pair_d) {
+  uz::pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int total = N * M + N * N + M * M;
@@ -98,6 +100,7 @@ __device__ double py312_sum(const double* p, int n) {
 
 // out[0] = GED, out[1..3] = sum d_sy, sum d_ss, sum d_yy, in the reference's pair order (utils.py:185-200).
 __global__ void ged_finish_kernel(const double* __restrict__ pair_d, int N, int M, double* out) {
+  uz::pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double sy = py312_sum(pair_d, N * M);
   const double ss = py312_sum(pair_d + N * M, N * N);
@@ -111,6 +114,7 @@ __global__ void ged_finish_kernel(const double* __restrict__ pair_d, int N, int 
 
 // argmax over classes of fp32 NCHW [N,C,HW] -> uint8 [N,HW] (first maximal index, like torch.argmax)
 __global__ void argmax_kernel(const float* __restrict__ x, int N, int C, int hw, uint8_t* out) {
+  uz::pdl_prologue();
   const size_t total = static_cast<size_t>(N) * hw;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -129,6 +133,7 @@ __global__ void argmax_kernel(const float* __restrict__ x, int N, int C, int hw,
 template <typename GT>
 __global__ void ncc_pixel_kernel(const float* __restrict__ probs, const GT* __restrict__ gt, int N, int C, int hw,
                                  int M, double* e_ss, double* e_sy /*[M][hw]*/) {
+  uz::pdl_prologue();
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   if (px >= hw) return;
   constexpr int kC = 8;
@@ -173,6 +178,7 @@ __device__ double block_sum_d(double v, double* red) {
 
 // one block per annotator j: ncc_j = sum((a-abar)/(std_a*len) * (v-vbar)/std_v)
 __global__ void ncc_corr_kernel(const double* __restrict__ e_ss, const double* __restrict__ e_sy, int hw, double* ncc_j) {
+  uz::pdl_prologue();
   __shared__ double red[32];
   const int j = blockIdx.x;
   const double* v = e_sy + static_cast<size_t>(j) * hw;
@@ -195,6 +201,7 @@ __global__ void ncc_corr_kernel(const double* __restrict__ e_ss, const double* _
 }
 
 __global__ void ncc_finish_kernel(const double* __restrict__ ncc_j, int M, double* out) {
+  uz::pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double s = 0.0;
   for (int j = 0; j < M; ++j) s += ncc_j[j];
@@ -219,13 +226,13 @@ extern "C" int uz_ged_pack_masks(const void* labels, int dtype, int count, int h
   const size_t threads_total = static_cast<size_t>(count) * words * 32;
   const int blocks = static_cast<int>((threads_total + 255) / 256);
   if (dtype == 0)
-    pack_masks_kernel<long long><<<blocks, 256, 0, ST(stream)>>>(static_cast<const long long*>(labels), count, hw, words,
+    uz::launch(pack_masks_kernel<long long>, blocks, 256, 0, ST(stream), static_cast<const long long*>(labels), count, hw, words,
                                                                  ls, bits, counts);
   else if (dtype == 1)
-    pack_masks_kernel<float><<<blocks, 256, 0, ST(stream)>>>(static_cast<const float*>(labels), count, hw, words, ls, bits,
+    uz::launch(pack_masks_kernel<float>, blocks, 256, 0, ST(stream), static_cast<const float*>(labels), count, hw, words, ls, bits,
                                                              counts);
   else if (dtype == 2)
-    pack_masks_kernel<uint8_t><<<blocks, 256, 0, ST(stream)>>>(static_cast<const uint8_t*>(labels), count, hw, words, ls,
+    uz::launch(pack_masks_kernel<uint8_t>, blocks, 256, 0, ST(stream), static_cast<const uint8_t*>(labels), count, hw, words, ls,
                                                                bits, counts);
   else
     UZ_CHECK_ARG(false, "uz_ged_pack_masks: dtype %d unsupported", dtype);
@@ -240,10 +247,10 @@ extern "C" int uz_ged_pairwise(const unsigned int* bits_s, const int* cnt_s, int
   UZ_CHECK_ARG(bits_s && cnt_s && bits_y && cnt_y && pair_d && out && N > 0 && M > 0, "uz_ged_pairwise: bad arguments");
   const int words = (hw + 31) / 32;
   const int total = N * M + N * N + M * M;
-  pair_distance_kernel<<<(total * 32 + 255) / 256, 256, 0, ST(stream)>>>(bits_s, cnt_s, N, bits_y, cnt_y, M, nlabels,
+  uz::launch(pair_distance_kernel, (total * 32 + 255) / 256, 256, 0, ST(stream), bits_s, cnt_s, N, bits_y, cnt_y, M, nlabels,
                                                                         words, pair_d);
   UZ_CHECK_LAUNCH("uz_ged_pairwise");
-  ged_finish_kernel<<<1, 32, 0, ST(stream)>>>(pair_d, N, M, out);
+  uz::launch(ged_finish_kernel, 1, 32, 0, ST(stream), pair_d, N, M, out);
   UZ_CHECK_LAUNCH("uz_ged_pairwise(finish)");
   return UZ_OK;
 }
@@ -253,7 +260,7 @@ extern "C" int uz_argmax_classes(const float* x, int N, int C, int hw, unsigned 
   size_t total = static_cast<size_t>(N) * hw;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > uz::num_sms() * 16) blocks = uz::num_sms() * 16;
-  argmax_kernel<<<blocks, 256, 0, ST(stream)>>>(x, N, C, hw, out);
+  uz::launch(argmax_kernel, blocks, 256, 0, ST(stream), x, N, C, hw, out);
   UZ_CHECK_LAUNCH("uz_argmax_classes");
   return UZ_OK;
 }
@@ -269,19 +276,19 @@ extern "C" int uz_variance_ncc(const float* probs, const void* gt, int gt_dtype,
   double* ncc_j = work + static_cast<size_t>(1 + M) * hw;
   const int blocks = (hw + 127) / 128;
   if (gt_dtype == 0)
-    ncc_pixel_kernel<long long><<<blocks, 128, 0, ST(stream)>>>(probs, static_cast<const long long*>(gt), N, C, hw, M,
+    uz::launch(ncc_pixel_kernel<long long>, blocks, 128, 0, ST(stream), probs, static_cast<const long long*>(gt), N, C, hw, M,
                                                                 e_ss, e_sy);
   else if (gt_dtype == 1)
-    ncc_pixel_kernel<float><<<blocks, 128, 0, ST(stream)>>>(probs, static_cast<const float*>(gt), N, C, hw, M, e_ss, e_sy);
+    uz::launch(ncc_pixel_kernel<float>, blocks, 128, 0, ST(stream), probs, static_cast<const float*>(gt), N, C, hw, M, e_ss, e_sy);
   else if (gt_dtype == 2)
-    ncc_pixel_kernel<uint8_t><<<blocks, 128, 0, ST(stream)>>>(probs, static_cast<const uint8_t*>(gt), N, C, hw, M, e_ss,
+    uz::launch(ncc_pixel_kernel<uint8_t>, blocks, 128, 0, ST(stream), probs, static_cast<const uint8_t*>(gt), N, C, hw, M, e_ss,
                                                               e_sy);
   else
     UZ_CHECK_ARG(false, "uz_variance_ncc: gt dtype %d unsupported", gt_dtype);
   UZ_CHECK_LAUNCH("uz_variance_ncc(pixel)");
-  ncc_corr_kernel<<<M, 1024, 0, ST(stream)>>>(e_ss, e_sy, hw, ncc_j);
+  uz::launch(ncc_corr_kernel, M, 1024, 0, ST(stream), e_ss, e_sy, hw, ncc_j);
   UZ_CHECK_LAUNCH("uz_variance_ncc(corr)");
-  ncc_finish_kernel<<<1, 32, 0, ST(stream)>>>(ncc_j, M, out);
+  uz::launch(ncc_finish_kernel, 1, 32, 0, ST(stream), ncc_j, M, out);
   UZ_CHECK_LAUNCH("uz_variance_ncc(finish)");
   return UZ_OK;
 }

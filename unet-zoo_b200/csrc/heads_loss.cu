@@ -23,6 +23,7 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, 
                                 const float* __restrict__ bmu, const float* __restrict__ wsig,
                                 const float* __restrict__ bsig, const float* __restrict__ eps, int B, int hw, float* mu,
                                 float* sigma, float* z) {
+  uz::pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int npix = B * hw;
@@ -67,6 +68,7 @@ __global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, 
                                 const float* __restrict__ dsigma, const float* __restrict__ dz, int B, int hw,
                                 __nv_bfloat16* dfeat, int ldd, float* wpartial /*[blocks][2Z][C]*/,
                                 float* bpartial /*[blocks][2Z]*/) {
+  uz::pdl_prologue();
   extern __shared__ float sm[];  // [warps][2Z][C] accumulators for weight grads
   const int warps = blockDim.x >> 5;
   const int wid = threadIdx.x >> 5;
@@ -133,6 +135,7 @@ __global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, 
 
 // out[i] = sum_b partial[b][i]   (fixed order, deterministic)
 __global__ void column_reduce_kernel(const float* __restrict__ partial, int nblocks, int n, float* out, float scale) {
+  uz::pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float t = 0.f;
@@ -145,6 +148,7 @@ __global__ void column_reduce_kernel(const float* __restrict__ partial, int nblo
 // single block => deterministic; per-element terms in fp32 like the reference, block reduction in fp64.
 __global__ void kl_fwd_kernel(const float* __restrict__ mu0, const float* __restrict__ s0, const float* __restrict__ mu1,
                               const float* __restrict__ s1, int n, float scale, float* out) {
+  uz::pdl_prologue();
   __shared__ double red[32];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -165,6 +169,7 @@ __global__ void kl_fwd_kernel(const float* __restrict__ mu0, const float* __rest
 __global__ void kl_bwd_kernel(const float* __restrict__ mu0, const float* __restrict__ s0, const float* __restrict__ mu1,
                               const float* __restrict__ s1, int n, float scale, const float* __restrict__ upstream,
                               float* dmu0, float* ds0, float* dmu1, float* ds1) {
+  uz::pdl_prologue();
   const float g = upstream[0] * scale;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float a = s0[i], b = s1[i], d = mu1[i] - mu0[i];
@@ -181,6 +186,7 @@ __global__ void kl_bwd_kernel(const float* __restrict__ mu0, const float* __rest
 // one warp per LOW-res pixel; writes the f x f replicated block of the full-res fp32 NCHW output.
 __global__ void slayer_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ w,
                                   const float* __restrict__ bias, int ncls, int B, int h, int wd, int f, float* out) {
+  uz::pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int npix = B * h * wd;
@@ -214,6 +220,7 @@ __global__ void slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfl
                                   const float* __restrict__ w, int ncls, int B, int h, int wd, int f,
                                   __nv_bfloat16* dfeat, int ldd, float* wpartial /*[blocks][ncls][C]*/,
                                   float* bpartial /*[blocks][ncls]*/) {
+  uz::pdl_prologue();
   extern __shared__ float sm[];  // [warps][ncls][C]
   const int warps = blockDim.x >> 5;
   const int wid = threadIdx.x >> 5;
@@ -286,6 +293,7 @@ struct LevelPtrs {
 // Per-block partial sums per level -> partial[block][L]; gradients d s_k = (1/B) * sum_{l<=k} (softmax(acc_l) - onehot).
 __global__ void residual_ce_kernel(LevelPtrs ptrs, int L, int ncls, const float* __restrict__ target, int B, int hw,
                                    float inv_batch, const float* __restrict__ upstream, float* partial) {
+  uz::pdl_prologue();
   if (upstream) inv_batch *= upstream[0];
   __shared__ float red[32][kMaxLvl];
   float lsum[kMaxLvl];
@@ -354,6 +362,7 @@ __global__ void residual_ce_kernel(LevelPtrs ptrs, int L, int ncls, const float*
 
 // ---------------------------------------------------------------- accumulate_output (+softmax), in place into the last list entry
 __global__ void accumulate_kernel(LevelPtrs ptrs, int L, int ncls, int B, int hw, int use_softmax, float* out) {
+  uz::pdl_prologue();
   const size_t npix = static_cast<size_t>(B) * hw;
   for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < npix;
        pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -406,7 +415,7 @@ extern "C" int uz_head_fwd(const void* feat, int ld, int C, const float* wmu, co
   const int npix = B * hw;
   const int threads = 256;
   const int blocks = (npix * 32 + threads - 1) / threads;
-  head_fwd_kernel<2><<<blocks, threads, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, bmu, wsig,
+  uz::launch(head_fwd_kernel<2>, blocks, threads, 0, ST(stream), static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, bmu, wsig,
                                                           bsig, eps, B, hw, mu, sigma, z);
   UZ_CHECK_LAUNCH("uz_head_fwd");
   return UZ_OK;
@@ -427,12 +436,12 @@ extern "C" int uz_head_bwd(const void* feat, int ld, int C, const float* wmu, co
   const int blocks = uz_head_bwd_num_blocks(B, hw);
   const size_t smem = static_cast<size_t>(threads / 32) * 4 * C * sizeof(float);
   UZ_CHECK_ARG(smem <= 48 * 1024, "uz_head_bwd: C=%d too large for the shared accumulators", C);
-  head_bwd_kernel<2><<<blocks, threads, smem, ST(stream)>>>(static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, wsig,
+  uz::launch(head_bwd_kernel<2>, blocks, threads, smem, ST(stream), static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, wsig,
                                                             eps, sigma, dmu, dsigma, dz, B, hw,
                                                             static_cast<__nv_bfloat16*>(dfeat), ldd, wpartial, bpartial);
   UZ_CHECK_LAUNCH("uz_head_bwd");
-  column_reduce_kernel<<<(4 * C + 127) / 128, 128, 0, ST(stream)>>>(wpartial, blocks, 4 * C, dw, 1.f);
-  column_reduce_kernel<<<1, 32, 0, ST(stream)>>>(bpartial, blocks, 4, db, 1.f);
+  uz::launch(column_reduce_kernel, (4 * C + 127) / 128, 128, 0, ST(stream), wpartial, blocks, 4 * C, dw, 1.f);
+  uz::launch(column_reduce_kernel, 1, 32, 0, ST(stream), bpartial, blocks, 4, db, 1.f);
   UZ_CHECK_LAUNCH("uz_head_bwd(reduce)");
   return UZ_OK;
 }
@@ -440,7 +449,7 @@ extern "C" int uz_head_bwd(const void* feat, int ld, int C, const float* wmu, co
 extern "C" int uz_kl_fwd(const float* mu0, const float* s0, const float* mu1, const float* s1, int batch,
                          int per_sample, float weight, float* out, void* stream) {
   UZ_CHECK_ARG(mu0 && s0 && mu1 && s1 && out && batch > 0, "uz_kl_fwd: bad arguments");
-  kl_fwd_kernel<<<1, 1024, 0, ST(stream)>>>(mu0, s0, mu1, s1, batch * per_sample, weight / batch, out);
+  uz::launch(kl_fwd_kernel, 1, 1024, 0, ST(stream), mu0, s0, mu1, s1, batch * per_sample, weight / batch, out);
   UZ_CHECK_LAUNCH("uz_kl_fwd");
   return UZ_OK;
 }
@@ -450,7 +459,7 @@ extern "C" int uz_kl_bwd(const float* mu0, const float* s0, const float* mu1, co
                          float* ds1, void* stream) {
   UZ_CHECK_ARG(mu0 && s0 && mu1 && s1 && upstream && dmu0 && ds0 && dmu1 && ds1, "uz_kl_bwd: null pointer");
   const int n = batch * per_sample;
-  kl_bwd_kernel<<<cap_blocks((n + 255) / 256, 4), 256, 0, ST(stream)>>>(mu0, s0, mu1, s1, n, weight / batch, upstream,
+  uz::launch(kl_bwd_kernel, cap_blocks((n + 255) / 256, 4), 256, 0, ST(stream), mu0, s0, mu1, s1, n, weight / batch, upstream,
                                                                        dmu0, ds0, dmu1, ds1);
   UZ_CHECK_LAUNCH("uz_kl_bwd");
   return UZ_OK;
@@ -463,7 +472,7 @@ extern "C" int uz_slayer_fwd(const void* feat, int ld, int C, const float* w, co
   UZ_CHECK_ARG(C % 2 == 0 && ld % 2 == 0 && factor >= 1, "uz_slayer_fwd: bad C/ld/factor");
   const int npix = B * h * wd;
   const int threads = 256;
-  slayer_fwd_kernel<<<(npix * 32 + threads - 1) / threads, threads, 0, ST(stream)>>>(
+  uz::launch(slayer_fwd_kernel, (npix * 32 + threads - 1) / threads, threads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(feat), ld, C, w, bias, ncls, B, h, wd, factor, out);
   UZ_CHECK_LAUNCH("uz_slayer_fwd");
   return UZ_OK;
@@ -484,12 +493,12 @@ extern "C" int uz_slayer_bwd(const float* dout, const void* feat, int ld, int C,
   const int threads = warps * 32;
   const int blocks = uz_slayer_bwd_num_blocks(B, h, wd);
   const size_t smem = static_cast<size_t>(warps) * ncls * C * sizeof(float);
-  slayer_bwd_kernel<<<blocks, threads, smem, ST(stream)>>>(dout, static_cast<const __nv_bfloat16*>(feat), ld, C, w, ncls,
+  uz::launch(slayer_bwd_kernel, blocks, threads, smem, ST(stream), dout, static_cast<const __nv_bfloat16*>(feat), ld, C, w, ncls,
                                                            B, h, wd, factor, static_cast<__nv_bfloat16*>(dfeat), ldd,
                                                            wpartial, bpartial);
   UZ_CHECK_LAUNCH("uz_slayer_bwd");
-  column_reduce_kernel<<<(ncls * C + 127) / 128, 128, 0, ST(stream)>>>(wpartial, blocks, ncls * C, dw, 1.f);
-  column_reduce_kernel<<<1, 32, 0, ST(stream)>>>(bpartial, blocks, ncls, db, 1.f);
+  uz::launch(column_reduce_kernel, (ncls * C + 127) / 128, 128, 0, ST(stream), wpartial, blocks, ncls * C, dw, 1.f);
+  uz::launch(column_reduce_kernel, 1, 32, 0, ST(stream), bpartial, blocks, ncls, db, 1.f);
   UZ_CHECK_LAUNCH("uz_slayer_bwd(reduce)");
   return UZ_OK;
 }
@@ -511,9 +520,9 @@ extern "C" int uz_residual_ce(const float* const* s, float* const* ds, const flo
     p.ds[l] = ds ? ds[l] : nullptr;
   }
   const int blocks = uz_residual_ce_num_blocks(B, hw);
-  residual_ce_kernel<<<blocks, 256, 0, ST(stream)>>>(p, L, ncls, target, B, hw, 1.f / B, upstream, partial);
+  uz::launch(residual_ce_kernel, blocks, 256, 0, ST(stream), p, L, ncls, target, B, hw, 1.f / B, upstream, partial);
   UZ_CHECK_LAUNCH("uz_residual_ce");
-  column_reduce_kernel<<<1, 32, 0, ST(stream)>>>(partial, blocks, L, ce_levels, 1.f / B);
+  uz::launch(column_reduce_kernel, 1, 32, 0, ST(stream), partial, blocks, L, ce_levels, 1.f / B);
   UZ_CHECK_LAUNCH("uz_residual_ce(reduce)");
   return UZ_OK;
 }
@@ -526,7 +535,7 @@ extern "C" int uz_accumulate_output(const float* const* s, int L, int ncls, int 
                L, ncls);
   LevelPtrs p{};
   for (int l = 0; l < L; ++l) p.s[l] = s[l];
-  accumulate_kernel<<<cap_blocks((static_cast<long long>(B) * hw + 255) / 256, 8), 256, 0, ST(stream)>>>(
+  uz::launch(accumulate_kernel, cap_blocks((static_cast<long long>(B) * hw + 255) / 256, 8), 256, 0, ST(stream), 
       p, L, ncls, B, hw, use_softmax, out);
   UZ_CHECK_LAUNCH("uz_accumulate_output");
   return UZ_OK;

@@ -1,6 +1,7 @@
 // Library plumbing for libunetzoo_b200.so: error text, driver entry point for tensor-map encoding, device info.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "unetzoo_b200.h"
@@ -29,6 +30,13 @@ int load_encode() {
 }  // namespace
 
 namespace uz {
+int g_pdl = [] {
+  // Measured on the PHiSeg training step (profiles/r01_pdl.md): +4 % on a single stream, -3.5 % with the three-stream
+  // overlap the models use (early-scheduled dependents hold SM resources other streams could use) => opt-in.
+  const char* e = getenv("UZ_PDL");
+  return (e && e[0] == '1') ? 1 : 0;
+}();
+
 void count_launch() { ++g_launches; }
 
 void set_error(const char* fmt, ...) {
@@ -88,3 +96,8 @@ extern "C" int uz_abi_version(void) { return UZ_ABI_VERSION; }
 extern "C" int uz_device_sm_count(void) { return uz::num_sms(); }
 
 extern "C" long long uz_launch_count(void) { return g_launches; }
+
+extern "C" int uz_set_pdl(int enabled) {
+  uz::g_pdl = enabled ? 1 : 0;
+  return UZ_OK;
+}

@@ -79,6 +79,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     __syncwarp();
     uz::tmem_alloc(&tmem_base_slot, p.tmem_cols);
   }
+  uz::pdl_prologue();   // everything above is independent of the previous kernel's output
   uz::tc_fence_before();
   __syncthreads();
   uz::tc_fence_after();
@@ -242,6 +243,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
     __syncwarp();
     uz::tmem_alloc(&tmem_base_slot, 512);
   }
+  uz::pdl_prologue();   // everything above is independent of the previous kernel's output
   uz::tc_fence_before();
   __syncthreads();
   uz::tc_fence_after();
@@ -366,6 +368,7 @@ bool make_plan2(int N, int H, int W, int Cin, int Cout, int taps, Plan2* out) {
 // dw[o][i][t] (+)= scale * sum_s partial[s][t][o][i]   (fixed order); also emits dbias[o] = sum_pixels dy when asked.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int CoutP, int CinP,
                                     int Cout, int Cin, float* dw) {
+  uz::pdl_prologue();
   const size_t total = static_cast<size_t>(Cout) * Cin * taps;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -481,12 +484,12 @@ extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, i
       attr2 = pl2.smem;
     }
     dim3 grid2(pl2.splits, pl2.p.co_blocks * 3 * pl2.p.ci_chunks, 1);
-    wgrad_tc2_kernel<<<grid2, kThreads, pl2.smem, static_cast<cudaStream_t>(stream)>>>(tdy2, tx2, pl2.p);
+    uz::launch(wgrad_tc2_kernel, grid2, kThreads, pl2.smem, static_cast<cudaStream_t>(stream), tdy2, tx2, pl2.p);
     UZ_CHECK_LAUNCH("uz_conv_wgrad(v2)");
     const size_t total2 = static_cast<size_t>(Cout_logical) * Cin_logical * taps;
     int blocks2 = static_cast<int>((total2 + 255) / 256);
     if (blocks2 > uz::num_sms() * 8) blocks2 = uz::num_sms() * 8;
-    wgrad_reduce_kernel<<<blocks2, 256, 0, static_cast<cudaStream_t>(stream)>>>(workspace, pl2.splits, taps, Cout, Cin,
+    uz::launch(wgrad_reduce_kernel, blocks2, 256, 0, static_cast<cudaStream_t>(stream), workspace, pl2.splits, taps, Cout, Cin,
                                                                                Cout_logical, Cin_logical, dw);
     UZ_CHECK_LAUNCH("uz_conv_wgrad(v2 reduce)");
     return UZ_OK;
@@ -529,12 +532,12 @@ extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, i
     attr_bytes = pl.smem;
   }
   dim3 grid(pl.splits, pl.p.tap_groups * pl.co_blocks, 1);
-  kernel<<<grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream)>>>(tdy, tx, pl.p);
+  uz::launch(kernel, grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream), tdy, tx, pl.p);
   UZ_CHECK_LAUNCH("uz_conv_wgrad");
   const size_t total = static_cast<size_t>(Cout_logical) * Cin_logical * taps;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > uz::num_sms() * 8) blocks = uz::num_sms() * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(workspace, pl.splits, taps, Cout, Cin,
+  uz::launch(wgrad_reduce_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), workspace, pl.splits, taps, Cout, Cin,
                                                                             Cout_logical, Cin_logical, dw);
   UZ_CHECK_LAUNCH("uz_conv_wgrad(reduce)");
   return UZ_OK;

@@ -335,8 +335,8 @@ def main():
 
     # ---- GED-100 evaluation throughput (N=100 samples of one image, 4 annotators), samples sharded over ranks
     eval_block = None
-    if not args.skip_eval and world == 1 and args.model == 'phiseg':
-        ev = train.EvalStep(net, N_SAMPLES, 2)
+    if not args.skip_eval and args.model == 'phiseg':
+        ev = train.EvalStep(net, N_SAMPLES, 2, shard=(rank, world))
         labels = batches[0][2]
         img = batches[0][0][0, 0].contiguous().pin_memory()
         lab = labels[0].contiguous().pin_memory()
@@ -346,8 +346,10 @@ def main():
         t_ms = timed_region(lambda i: ev.run_host(img, lab), k_eval, world, device) / k_eval
         eval_block = {'metric': 'PHiSeg GED-100 eval images/s (100 samples, 4 annotators, GED + NCC)',
                       'value': 1000.0 / t_ms, 'unit': 'images/s', 'ms_per_image': t_ms, 'ged': ged, 'ncc': ncc,
-                      'path': 'EvalStep.run_host: H2D image+labels, forward(training=False) on 100 copies, '
-                              'accumulate_output(softmax), argmax, GED, NCC, D2H of two scalars'}
+                      'samples_per_rank': ev.counts or [N_SAMPLES],
+                      'path': 'EvalStep.run_host: H2D image+labels, forward(training=False) on this rank\'s share of '
+                              'the 100 copies, accumulate_output(softmax), all-gather of the class probabilities '
+                              '(N>1), argmax, GED, NCC, D2H of two scalars'}
         net.train()
 
     # ---- roofline of the tensor-core conv kernels, in situ (differential graph replays)

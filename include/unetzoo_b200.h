@@ -221,6 +221,36 @@ int uz_argmax_classes(const float* x, int N, int C, int hw, unsigned char* out, 
 int uz_variance_ncc(const float* probs, const void* gt, int gt_dtype, int N, int C, int hw, int M, double* work,
                     double* out, void* stream);
 
+/* ---- volumes: the 3-D clones of models/phiseg3D.py (NDHWC bf16 activations) ------------------------------------------ */
+/* BatchNorm3d, 1x1x1 heads, KL, residual cross-entropy, channel copies and layout conversion are the flat
+ * [pixels][channels] entry points above with pixels = N*D*H*W (hw = D*H*W for the fp32 NCDHW sides). */
+
+/* nn.Conv3d 3x3x3 pad 1 / 1x1x1 forward (models/phiseg3D.py:24) with the same epilogue contract as uz_conv_fwd
+ * (scale/shift/relu fold, or BatchNorm statistics accumulators); with dgrad-packed weights it is the input gradient.
+ * taps = 27: w_packed [(kd*3 + kw)*3 + kh][Cout][Cin] as produced by uz_pack_conv_weight(taps = 27); Cout % 32 == 0.
+ * Same persistent tcgen05 kernel as the 2-D path, the z taps are one more factor of the K loop; any D/H/W. */
+int uz_conv3d_fwd(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, int taps,
+                  void* y, int ldy, const float* scale, const float* shift, int relu, float* stats_partial,
+                  void* stream);
+/* conv3d weight gradient: dw fp32 [Cout_logical][Cin_logical][27] (OIDHW).  Workspace from uz_wgrad3d_workspace_floats. */
+long long uz_wgrad3d_workspace_floats(int N, int D, int H, int W, int Cin, int Cout);
+int uz_conv3d_wgrad(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout,
+                    int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream);
+/* nn.AvgPool3d(2, 2, ceil_mode=True) on even sizes (models/phiseg3D.py:100) and its gradient. */
+int uz_avgpool3_fwd(const void* x, int ldx, void* out, int ldo, int N, int Do, int Ho, int Wo, int C, void* stream);
+int uz_avgpool3_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int Do, int Ho, int Wo, int C, void* stream);
+/* F.interpolate / nn.Upsample(mode='trilinear', scale_factor=2, align_corners=True) (models/phiseg3D.py:143,291-294,
+ * 382-386) into a channel slice (ldo) and its gradient; (d, h, w) is the LOW resolution. */
+int uz_upsample3d_fwd(const void* x, int ldx, void* out, int ldo, int N, int d, int h, int w, int C, void* stream);
+int uz_upsample3d_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int d, int h, int w, int C, void* stream);
+/* Likelihood.s_layer 1x1x1 + nearest upsample to full resolution (models/phiseg3D.py:366-370,396-398 with the size fix
+ * of SURVEY.md 8c): out fp32 NCDHW [B,ncls,d*f,h*f,wd*f].  Backward workspace rows: uz_slayer_bwd_num_blocks(B*d,h,wd). */
+int uz_slayer3d_fwd(const void* feat, int ld, int C, const float* w, const float* bias, int ncls, int B, int d, int h,
+                    int wd, int factor, float* out, void* stream);
+int uz_slayer3d_bwd(const float* dout, const void* feat, int ld, int C, const float* w, int ncls, int B, int d, int h,
+                    int wd, int factor, void* dfeat, int ldd, float* wpartial, float* bpartial, float* dw, float* db,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,8 @@ sys.path.insert(0, ROOT)
 
 from oracle import synth                                    # noqa: E402
 from oracle.ref_loader import load_reference                # noqa: E402
-from oracle.ref_run import build_reference_phiseg, injected_noise  # noqa: E402
+from oracle.ref_run import (build_reference_phiseg, build_reference_phiseg3d, injected_noise,  # noqa: E402
+                            phiseg3d_patches)
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
@@ -66,6 +67,51 @@ def phiseg_case(tag, filters, batch, wseed, dseed, nseed, keep_logits, reversibl
             out['train_running_var_probe'] = rs[k].numpy().copy()
             out['train_running_var_probe_key'] = k
             out['train_num_batches_tracked_probe'] = int(rs[k.replace('running_var', 'num_batches_tracked')])
+    np.savez_compressed(os.path.join(GOLDEN, tag + '.npz'), **out)
+    print(tag, out['train_loss'], out['eval_loss'])
+
+
+def phiseg3d_case(tag, filters, latent_levels, size, batch, wseed, dseed, nseed, reversible=False):
+    """PHISeg3D of the reference under the three documented patches (oracle/ref_run.py)."""
+    net = build_reference_phiseg3d(filters, (4, size, size, size), latent_levels, reversible=reversible)
+    sd = synth.synth_state_dict(net.state_dict(), seed=wseed)
+    vol, lab = synth.brats_like_batch(batch, size=size, seed=dseed)
+    eps = synth.noise_list(synth.phiseg3d_noise_shapes(batch, size, latent_levels, len(filters)), seed=nseed)
+    out = {'filters': np.asarray(filters), 'latent_levels': latent_levels, 'size': size, 'batch': batch, 'wseed': wseed,
+           'dseed': dseed, 'nseed': nseed, 'reversible': int(reversible)}
+    for training in (True, False):
+        net.load_state_dict(sd)
+        net.train(training)
+        key = 'train' if training else 'eval'
+        with phiseg3d_patches(net), injected_noise(eps):
+            s = net.forward(vol, lab, training=training)
+            s = [t.clone() for t in s]
+            net.loss_dict = {}
+            loss = net.loss(lab)
+        out[key + '_loss'] = float(loss)
+        for k, v in net.loss_dict.items():
+            out['%s_%s' % (key, k)] = float(v)
+        for lvl in range(latent_levels):
+            st = 2 if lvl == 0 else 1            # the full-resolution level is stored at every second voxel
+            for nm, lst in (('post_mu', net.posterior_mu), ('post_sigma', net.posterior_sigma),
+                            ('prior_mu', net.prior_mu), ('prior_sigma', net.prior_sigma)):
+                out['%s_%s%d' % (key, nm, lvl)] = lst[lvl].detach()[:, :, ::st, ::st, ::st].numpy()
+        acc = sum(s)
+        out[key + '_logit_absmean'] = float(acc.abs().mean())
+        out[key + '_logits_ds2'] = acc.detach()[:, :, ::2, ::2, ::2].numpy().astype(np.float32)
+        if training:
+            net.zero_grad()
+            loss.backward()
+            gn = {n: float(p.grad.norm()) for n, p in net.named_parameters() if p.grad is not None}
+            names = sorted(gn)
+            out['train_grad_names'] = np.asarray(names)
+            out['train_grad_norms'] = np.asarray([gn[n] for n in names])
+            out['train_nograd_names'] = np.asarray(sorted(n for n, p in net.named_parameters() if p.grad is None))
+            k = 'posterior.contracting_path.1.layers.2.convolution.1.running_var'
+            if reversible:
+                k = 'posterior.contracting_path.1.layers.1.sequence.reversible_blocks.0.f_block.0.convolution.1.running_var'
+            out['train_running_var_probe'] = net.state_dict()[k].numpy().copy()
+            out['train_running_var_probe_key'] = k
     np.savez_compressed(os.path.join(GOLDEN, tag + '.npz'), **out)
     print(tag, out['train_loss'], out['eval_loss'])
 
@@ -164,5 +210,6 @@ if __name__ == '__main__':
     phiseg_case('phiseg_small', [16, 32, 32, 32, 32, 32, 32], 4, 1, 3, 5, keep_logits=True)
     phiseg_case('phiseg_lidc', [32, 64, 128, 192, 192, 192, 192], 2, 2, 4, 6, keep_logits=False)
     phiseg_case('phiseg_rev_small', [32, 64, 64, 64, 64, 64, 64], 4, 1, 3, 5, keep_logits=False, reversible=True)
+    phiseg3d_case('phiseg3d_small', [32, 64, 64], 3, 32, 2, 1, 3, 5)
     metrics_case()
     unet_cases()

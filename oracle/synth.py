@@ -87,3 +87,31 @@ def synth_state_dict(template, seed=0):
             v = 0.05 * rs.standard_normal(shape)
         out[name] = torch.from_numpy(np.asarray(v)).to(t.dtype).reshape(shape).clone()
     return out
+
+
+def brats_like_batch(batch, size=32, channels=4, seed=0):
+    """BraTS-shaped synthetic volumes: volume fp32 [B,4,S,S,S] ~ N(0,1)*0.5 with the lesion imprinted,
+    label index volume float32 [B,1,S,S,S] in {0,1,2} from two nested ellipsoids (reference data/bratsDataset.py:88-89,
+    125-131 only fixes these shapes)."""
+    rs = _rs(seed, 'brats')
+    vol = (rs.standard_normal((batch, channels, size, size, size)) * 0.5).astype(np.float32)
+    zz, yy, xx = np.mgrid[0:size, 0:size, 0:size].astype(np.float32)
+    lab = np.zeros((batch, 1, size, size, size), np.float32)
+    for b in range(batch):
+        c = rs.uniform(0.35 * size, 0.65 * size, 3)
+        r = rs.uniform(0.15 * size, 0.3 * size, 3)
+        d = ((zz - c[0]) / r[0]) ** 2 + ((yy - c[1]) / r[1]) ** 2 + ((xx - c[2]) / r[2]) ** 2
+        lab[b, 0] = (d <= 1.0).astype(np.float32) + (d <= 0.3).astype(np.float32)
+        vol[b] += 0.3 * lab[b]
+    return torch.from_numpy(vol), torch.from_numpy(lab)
+
+
+def phiseg3d_noise_shapes(batch, size, latent_levels, resolution_levels, z_dim=2):
+    """randn_like draws of one PHISeg3D.forward: posterior levels deepest first, then the prior's
+    (reference models/phiseg3D.py:188,276-281)."""
+    one = []
+    for i in range(latent_levels):
+        lvl = latent_levels - 1 - i
+        r = size >> (lvl + resolution_levels - latent_levels)
+        one.append((batch, z_dim, r, r, r))
+    return one + one

@@ -11,3 +11,10 @@ def dropin_phiseg(filters, reversible=False, image_size=(1, 128, 128), num_class
 
 def phiseg_state_template(filters, reversible=False):
     return dropin_phiseg(filters, reversible=reversible).state_dict()
+
+
+def dropin_phiseg3d(filters, latent_levels, image_size, reversible=False, num_classes=3, input_channels=4):
+    from models.phiseg3D import PHISeg3D
+    return PHISeg3D(input_channels=input_channels, num_classes=num_classes, num_filters=list(filters),
+                    latent_levels=latent_levels, no_convs_fcomb=4, beta=10.0, image_size=image_size,
+                    reversible=reversible)

@@ -62,5 +62,10 @@ def test_dropin_state_dict_and_parameter_count():
     assert sum(p.numel() for p in net.parameters()) == 24513330
     assert len(net.state_dict()) == 820
     assert 'prior.sample_z_path.4.mu_conv.0.weight' in net.state_dict()
+    rev = dropin_phiseg([32, 64, 128, 192, 192, 192, 192], reversible=True)
+    assert sum(p.numel() for p in rev.parameters()) == 16302290          # RevPHISeg
+    from tests.keygrammar import dropin_phiseg3d
+    vol = dropin_phiseg3d([32, 64, 128], 3, (4, 128, 128, 128))
+    assert sum(p.numel() for p in vol.parameters()) == 9265121           # PHISeg3D [32,64,128], L = 3
     with pytest.raises(NotImplementedError):
-        dropin_phiseg([32, 64, 128, 192, 192, 192, 192], reversible=True)
+        dropin_phiseg3d([32, 64, 128], 3, (4, 128, 128, 128), reversible=True)   # 16-channel halves: not on the B200 path yet

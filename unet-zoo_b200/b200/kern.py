@@ -1,6 +1,7 @@
 """Thin tensor-level wrappers over the C ABI (no autograd).  Activations are torch bf16 tensors of shape
-[N, H, W, C] whose last-dim stride is 1 and whose pixel stride (stride(2)) may exceed C (channel slices of concat
-buffers); N/H/W must be densely packed over pixels."""
+[N, H, W, C] (or [N, D, H, W, C] for the volumes of models/phiseg3D.py) whose last-dim stride is 1 and whose pixel
+stride may exceed C (channel slices of concat buffers); N/(D/)H/W must be densely packed over pixels.  The flat
+[pixels][channels] kernels see a volume as N*D images."""
 import ctypes
 import struct
 
@@ -23,6 +24,14 @@ def _p(t):
 def _check_act(t):
     if not t.is_cuda:
         raise _lib.UnetZooLibError('B200 path needs CUDA tensors (no CPU fallback)')
+    if t.dim() == 5:
+        assert t.dtype == torch.bfloat16 and t.stride(4) == 1, (t.dtype, t.shape, t.stride())
+        n, d, h, w, c = t.shape
+        ld = t.stride(3)
+        assert h == 1 or t.stride(2) == w * ld, t.stride()
+        assert d == 1 or t.stride(1) == h * w * ld, t.stride()
+        assert n == 1 or t.stride(0) == d * h * w * ld, t.stride()
+        return n * d, h, w, c, ld
     assert t.dtype == torch.bfloat16 and t.dim() == 4 and t.stride(3) == 1, (t.dtype, t.shape, t.stride())
     n, h, w, c = t.shape
     ld = t.stride(2)
@@ -35,8 +44,33 @@ def pad16(c):
     return (c + 15) // 16 * 16
 
 
+def pad_channels(c, weight_dim=4):
+    """stored channel count: multiples of 16; volumes (5-D weights) use multiples of 32, the granularity the 3x3x3
+    kernel needs for its output channels (a 2-channel latent is stored as 32 channels so its dgrad has a plan)"""
+    return (c + 31) // 32 * 32 if weight_dim == 5 else pad16(c)
+
+
 def new_act(n, h, w, c, device):
     return torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+
+
+def _like(x, c):
+    """fresh dense activation with x's batch / spatial dims and c channels"""
+    return torch.empty(tuple(x.shape[:-1]) + (c,), dtype=torch.bfloat16, device=x.device)
+
+
+def _taps(w):
+    t = 1
+    for k in w.shape[2:]:
+        t *= k
+    return t
+
+
+def _spatial_numel(shape):
+    t = 1
+    for k in shape:
+        t *= k
+    return t
 
 
 def conv_tile_geometry(n, h, w):
@@ -59,8 +93,8 @@ class WeightPacker:
         self.max_elems = 0
         for w in self.weights:
             cout, cin = w.shape[0], w.shape[1]
-            taps = w.shape[2] * w.shape[3]
-            coutp, cinp = pad16(cout), pad16(cin)
+            taps = _taps(w)
+            coutp, cinp = pad_channels(cout, w.dim()), pad_channels(cin, w.dim())
             wf = torch.empty((taps, coutp, cinp), dtype=torch.bfloat16, device=dev)
             wd = torch.empty((taps, cinp, coutp), dtype=torch.bfloat16, device=dev)
             self.packed[w.data_ptr()] = (wf, wd)
@@ -101,8 +135,8 @@ def pack_conv_weight(w, need_dgrad=True):
         if hit is not None:
             return hit
     cout, cin = w.shape[0], w.shape[1]
-    taps = w.shape[2] * w.shape[3]
-    coutp, cinp = pad16(cout), pad16(cin)
+    taps = _taps(w)
+    coutp, cinp = pad_channels(cout, w.dim()), pad_channels(cin, w.dim())
     wf = torch.empty((taps, coutp, cinp), dtype=torch.bfloat16, device=w.device)
     wd = torch.empty((taps, cinp, coutp), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
     _lib.call('uz_pack_conv_weight', _p(w.contiguous()), cout, cin, taps, _p(wf), coutp, cinp, _p(wd), cinp, coutp,
@@ -116,13 +150,17 @@ def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=Fa
     taps, cout, cin_w = w_packed.shape
     assert cin_w == cin, (cin_w, cin)
     if out is None:
-        out = new_act(n, h, w, cout, x.device)
+        out = _like(x, cout)
     _, _, _, _, ldy = _check_act(out)
     partial = None
     if stats:
         partial = zero_arena.get(2 * cout, x.device).view(1, 2, cout)      # [2][Cout] accumulators, zero on entry
-    _lib.call('uz_conv_fwd', _p(x), n, h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy, _p(scale), _p(shift),
-              int(relu), _p(partial), _stream())
+    if x.dim() == 5:
+        _lib.call('uz_conv3d_fwd', _p(x), x.shape[0], x.shape[1], h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy,
+                  _p(scale), _p(shift), int(relu), _p(partial), _stream())
+    else:
+        _lib.call('uz_conv_fwd', _p(x), n, h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy, _p(scale), _p(shift),
+                  int(relu), _p(partial), _stream())
     return out, partial
 
 
@@ -130,6 +168,16 @@ def conv_wgrad(x, dy, taps, cin_logical, cout_logical):
     """-> dw fp32 [cout_logical, cin_logical, taps]"""
     n, h, w, cin, ldx = _check_act(x)
     _, _, _, cout, lddy = _check_act(dy)
+    if x.dim() == 5 and taps == 27:
+        nb, d = x.shape[0], x.shape[1]
+        ws = _lib.raw('uz_wgrad3d_workspace_floats')(nb, d, h, w, cin, cout)
+        if ws < 0:
+            raise _lib.UnetZooLibError('uz_conv3d_wgrad: unsupported shape Cin=%d Cout=%d' % (cin, cout))
+        work = torch.empty((ws,), dtype=torch.float32, device=x.device)
+        dw = torch.empty((cout_logical, cin_logical, taps), dtype=torch.float32, device=x.device)
+        _lib.call('uz_conv3d_wgrad', _p(x), ldx, _p(dy), lddy, nb, d, h, w, cin, cout, cin_logical, cout_logical,
+                  _p(work), _p(dw), _stream())
+        return dw
     ws = _lib.raw('uz_wgrad_workspace_floats')(n, h, w, cin, cout, taps)
     if ws < 0:
         raise _lib.UnetZooLibError('uz_conv_wgrad: unsupported shape Cin=%d Cout=%d' % (cin, cout))
@@ -157,7 +205,7 @@ def bn_apply_train(y, sums, count, gamma, beta, running_mean, running_var, relu=
     n, h, w, c, ldy = _check_act(y)
     dev = y.device
     st = torch.empty((4, c), dtype=torch.float32, device=dev)
-    out = new_act(n, h, w, c, dev)
+    out = _like(y, c)
     _lib.call('uz_bn_apply_train', _p(y), ldy, _p(sums), float(count), _p(gamma), _p(beta), eps, momentum,
               _p(running_mean), _p(running_var), _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), int(relu), _p(out), c,
               n * h * w, c, _stream())
@@ -174,7 +222,7 @@ def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True):
     _lib.call('uz_bn_bwd_reduce_sums', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), npix, c, _p(sums),
               _stream())
     dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
-    dy = new_act(n, h, w, c, dev)
+    dy = _like(y, c)
     _lib.call('uz_bn_bwd_apply_train', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), _p(sums), float(npix),
               _p(gamma), _p(mean), _p(invstd), _p(dgb[0]), _p(dgb[1]), _p(dy), c, npix, c, _stream())
     return dy, dgb[0], dgb[1]
@@ -192,7 +240,7 @@ def bn_eval_fold(conv_bias, gamma, beta, rm, rv, eps=BN_EPS):
 def affine_act(y, scale, shift, relu=True, out=None):
     n, h, w, c, ldy = _check_act(y)
     if out is None:
-        out = new_act(n, h, w, c, y.device)
+        out = _like(y, c)
     ldo = _check_act(out)[4]
     _lib.call('uz_affine_act', _p(y), ldy, _p(scale), _p(shift), int(relu), _p(out), ldo, n * h * w, c, _stream())
     return out
@@ -213,7 +261,7 @@ def bn_relu_bwd(dout, y, scale, shift, gamma, mean, invstd, relu=True):
     dbeta = torch.empty(c, dtype=torch.float32, device=dev)
     _lib.call('uz_bn_bwd_finalize', _p(partial), nb, c, float(npix), _p(gamma), _p(mean), _p(invstd), _p(coef[0]),
               _p(coef[1]), _p(coef[2]), _p(dgamma), _p(dbeta), _stream())
-    dy = new_act(n, h, w, c, dev)
+    dy = _like(y, c)
     _lib.call('uz_bn_bwd_apply', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), _p(coef[0]), _p(coef[1]),
               _p(coef[2]), _p(dy), c, npix, c, _stream())
     return dy, dgamma, dbeta
@@ -223,7 +271,7 @@ def relu_bwd(dout, y, scale, shift):
     """plain (bias+)ReLU backward: dy = dout * [y*scale+shift > 0]"""
     n, h, w, c, ldd = _check_act(dout)
     ldy = _check_act(y)[4]
-    dy = new_act(n, h, w, c, y.device)
+    dy = _like(y, c)
     _lib.call('uz_bn_bwd_apply', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), 1, None, None, None, _p(dy), c,
               n * h * w, c, _stream())
     return dy
@@ -231,6 +279,11 @@ def relu_bwd(dout, y, scale, shift):
 
 def avgpool2_fwd(x):
     n, h, w, c, ldx = _check_act(x)
+    if x.dim() == 5:
+        nb, d = x.shape[0], x.shape[1]
+        out = torch.empty((nb, d // 2, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+        _lib.call('uz_avgpool3_fwd', _p(x), ldx, _p(out), c, nb, d // 2, h // 2, w // 2, c, _stream())
+        return out
     out = new_act(n, h // 2, w // 2, c, x.device)
     _lib.call('uz_avgpool2_fwd', _p(x), ldx, _p(out), c, n, h // 2, w // 2, c, _stream())
     return out
@@ -238,6 +291,11 @@ def avgpool2_fwd(x):
 
 def avgpool2_bwd(dout):
     n, ho, wo, c, ldd = _check_act(dout)
+    if dout.dim() == 5:
+        nb, do = dout.shape[0], dout.shape[1]
+        dx = torch.empty((nb, do * 2, ho * 2, wo * 2, c), dtype=torch.bfloat16, device=dout.device)
+        _lib.call('uz_avgpool3_bwd', _p(dout), ldd, _p(dx), c, nb, do, ho, wo, c, _stream())
+        return dx
     dx = new_act(n, ho * 2, wo * 2, c, dout.device)
     _lib.call('uz_avgpool2_bwd', _p(dout), ldd, _p(dx), c, n, ho, wo, c, 0, _stream())
     return dx
@@ -245,6 +303,14 @@ def avgpool2_bwd(dout):
 
 def upsample2x_fwd(x, align_corners=True, out=None):
     n, h, w, c, ldx = _check_act(x)
+    if x.dim() == 5:                       # trilinear, align_corners=True only (models/phiseg3D.py)
+        assert align_corners
+        nb, d = x.shape[0], x.shape[1]
+        if out is None:
+            out = torch.empty((nb, 2 * d, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+        ldo = _check_act(out)[4]
+        _lib.call('uz_upsample3d_fwd', _p(x), ldx, _p(out), ldo, nb, d, h, w, c, _stream())
+        return out
     if out is None:
         out = new_act(n, 2 * h, 2 * w, c, x.device)
     ldo = _check_act(out)[4]
@@ -254,6 +320,11 @@ def upsample2x_fwd(x, align_corners=True, out=None):
 
 def upsample2x_bwd(dout, align_corners=True):
     n, hh, ww, c, ldd = _check_act(dout)
+    if dout.dim() == 5:
+        nb, dd = dout.shape[0], dout.shape[1]
+        dx = torch.empty((nb, dd // 2, hh // 2, ww // 2, c), dtype=torch.bfloat16, device=dout.device)
+        _lib.call('uz_upsample3d_bwd', _p(dout), ldd, _p(dx), c, nb, dd // 2, hh // 2, ww // 2, c, _stream())
+        return dx
     dx = new_act(n, hh // 2, ww // 2, c, dout.device)
     _lib.call('uz_upsample2x_bwd', _p(dout), ldd, _p(dx), c, n, hh // 2, ww // 2, c, int(align_corners), _stream())
     return dx
@@ -283,54 +354,67 @@ def global_mean_bwd(dout, h, w):
 
 
 def input_pack(patch, mask, nlabels=2, cp=16):
-    b, cimg, h, w = patch.shape
-    out = new_act(b, h, w, cp, patch.device)
+    """patch fp32 [B,Cimg,(D,)H,W], mask index map [B,1,(D,)H,W] or None -> bf16 channel-last [B,(D,)H,W,cp]"""
+    b, cimg = patch.shape[0], patch.shape[1]
+    sp = tuple(patch.shape[2:])
+    assert cimg + (nlabels if mask is not None else 0) <= cp
+    out = torch.empty((b,) + sp + (cp,), dtype=torch.bfloat16, device=patch.device)
     patch = patch.contiguous().float()
     if mask is not None:
         mask = mask.contiguous().float()
-    _lib.call('uz_input_pack', _p(patch), _p(mask), b, cimg, h, w, nlabels, _p(out), cp, _stream())
+    _lib.call('uz_input_pack', _p(patch), _p(mask), b, cimg, _spatial_numel(sp[:-1]), sp[-1], nlabels, _p(out), cp,
+              _stream())
     return out
 
 
 def nchw_to_nhwc(x, ld=None):
-    b, c, h, w = x.shape
+    """fp32 [B,C,*spatial] -> bf16 [B,*spatial,ld]"""
+    b, c = x.shape[0], x.shape[1]
+    sp = tuple(x.shape[2:])
     ld = ld or pad16(c)
-    out = new_act(b, h, w, ld, x.device)
-    _lib.call('uz_nchw_to_nhwc', _p(x.contiguous().float()), b, c, h * w, _p(out), ld, _stream())
+    out = torch.empty((b,) + sp + (ld,), dtype=torch.bfloat16, device=x.device)
+    _lib.call('uz_nchw_to_nhwc', _p(x.contiguous().float()), b, c, _spatial_numel(sp), _p(out), ld, _stream())
     return out
 
 
 def nhwc_to_nchw(x, c=None):
-    n, h, w, cc, ld = _check_act(x)
+    _, _, _, cc, ld = _check_act(x)
     c = c or cc
-    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
-    _lib.call('uz_nhwc_to_nchw', _p(x), ld, n, c, h * w, _p(out), _stream())
+    b = x.shape[0]
+    sp = tuple(x.shape[1:-1])
+    out = torch.empty((b, c) + sp, dtype=torch.float32, device=x.device)
+    _lib.call('uz_nhwc_to_nchw', _p(x), ld, b, c, _spatial_numel(sp), _p(out), _stream())
     return out
 
 
 def head_fwd(feat, wmu, bmu, wsig, bsig, eps):
-    n, h, w, c, ld = _check_act(feat)
+    _, _, _, c, ld = _check_act(feat)
+    n = feat.shape[0]
+    sp = tuple(feat.shape[1:-1])
+    hw = _spatial_numel(sp)
     zdim = wmu.shape[0]
-    mu = torch.empty((n, zdim, h, w), dtype=torch.float32, device=feat.device)
+    mu = torch.empty((n, zdim) + sp, dtype=torch.float32, device=feat.device)
     sigma = torch.empty_like(mu)
     z = torch.empty_like(mu)
-    _lib.call('uz_head_fwd', _p(feat), ld, c, _p(wmu), _p(bmu), _p(wsig), _p(bsig), _p(eps), n, h * w, zdim, _p(mu),
+    _lib.call('uz_head_fwd', _p(feat), ld, c, _p(wmu), _p(bmu), _p(wsig), _p(bsig), _p(eps), n, hw, zdim, _p(mu),
               _p(sigma), _p(z), _stream())
     return mu, sigma, z
 
 
 def head_bwd(feat, wmu, wsig, eps, sigma, dmu, dsigma, dz):
-    n, h, w, c, ld = _check_act(feat)
+    _, _, _, c, ld = _check_act(feat)
+    n = feat.shape[0]
+    hw = _spatial_numel(feat.shape[1:-1])
     zdim = wmu.shape[0]
     dev = feat.device
-    nb = _lib.raw('uz_head_bwd_num_blocks')(n, h * w)
+    nb = _lib.raw('uz_head_bwd_num_blocks')(n, hw)
     wpartial = torch.empty((nb, 2 * zdim, c), dtype=torch.float32, device=dev)
     bpartial = torch.empty((nb, 2 * zdim), dtype=torch.float32, device=dev)
     dw = torch.empty((2 * zdim, c), dtype=torch.float32, device=dev)
     db = torch.empty((2 * zdim,), dtype=torch.float32, device=dev)
-    dfeat = new_act(n, h, w, c, dev)
+    dfeat = _like(feat, c)
     _lib.call('uz_head_bwd', _p(feat), ld, c, _p(wmu), _p(wsig), _p(eps), _p(sigma), _p(dmu), _p(dsigma), _p(dz), n,
-              h * w, zdim, _p(dfeat), c, _p(wpartial), _p(bpartial), _p(dw), _p(db), _stream())
+              hw, zdim, _p(dfeat), c, _p(wpartial), _p(bpartial), _p(dw), _p(db), _stream())
     return dfeat, dw, db
 
 
@@ -354,6 +438,11 @@ def kl_bwd(mu0, s0, mu1, s1, weight, upstream):
 def slayer_fwd(feat, w, bias, factor):
     n, h, wd, c, ld = _check_act(feat)
     ncls = w.shape[0]
+    if feat.dim() == 5:
+        nb, d = feat.shape[0], feat.shape[1]
+        out = torch.empty((nb, ncls, d * factor, h * factor, wd * factor), dtype=torch.float32, device=feat.device)
+        _lib.call('uz_slayer3d_fwd', _p(feat), ld, c, _p(w), _p(bias), ncls, nb, d, h, wd, factor, _p(out), _stream())
+        return out
     out = torch.empty((n, ncls, h * factor, wd * factor), dtype=torch.float32, device=feat.device)
     _lib.call('uz_slayer_fwd', _p(feat), ld, c, _p(w), _p(bias), ncls, n, h, wd, factor, _p(out), _stream())
     return out
@@ -368,7 +457,11 @@ def slayer_bwd(dout, feat, w, factor):
     bpartial = torch.empty((nb, ncls), dtype=torch.float32, device=dev)
     dw = torch.empty((ncls, c), dtype=torch.float32, device=dev)
     db = torch.empty((ncls,), dtype=torch.float32, device=dev)
-    dfeat = new_act(n, h, wd, c, dev)
+    dfeat = _like(feat, c)
+    if feat.dim() == 5:
+        _lib.call('uz_slayer3d_bwd', _p(dout.contiguous()), _p(feat), ld, c, _p(w), ncls, feat.shape[0], feat.shape[1],
+                  h, wd, factor, _p(dfeat), c, _p(wpartial), _p(bpartial), _p(dw), _p(db), _stream())
+        return dfeat, dw, db
     _lib.call('uz_slayer_bwd', _p(dout.contiguous()), _p(feat), ld, c, _p(w), ncls, n, h, wd, factor, _p(dfeat), c,
               _p(wpartial), _p(bpartial), _p(dw), _p(db), _stream())
     return dfeat, dw, db
@@ -384,23 +477,25 @@ def _ptr_array(tensors):
 def residual_ce(s_list, target, need_grad=True, upstream=None):
     """s_list: L fp32 NCHW logits (index = latent level); -> ce_levels fp32 [L], grads list or None."""
     L = len(s_list)
-    b, ncls, h, w = s_list[0].shape
+    b, ncls = s_list[0].shape[0], s_list[0].shape[1]
+    hw = _spatial_numel(s_list[0].shape[2:])
     dev = s_list[0].device
     s_list = [s.contiguous() for s in s_list]
     grads = [torch.empty_like(s) for s in s_list] if need_grad else None
-    nb = _lib.raw('uz_residual_ce_num_blocks')(b, h * w)
+    nb = _lib.raw('uz_residual_ce_num_blocks')(b, hw)
     partial = torch.empty((nb, L), dtype=torch.float32, device=dev)
     ce = torch.empty((L,), dtype=torch.float32, device=dev)
     target = target.contiguous().float()
     _lib.call('uz_residual_ce', _ptr_array(s_list), _ptr_array(grads) if need_grad else None, _p(upstream), L, ncls,
-              _p(target), b, h * w, _p(partial), _p(ce), _stream())
+              _p(target), b, hw, _p(partial), _p(ce), _stream())
     return ce, grads
 
 
 def accumulate_output(s_list, use_softmax, out):
     L = len(s_list)
-    b, ncls, h, w = s_list[0].shape
-    _lib.call('uz_accumulate_output', _ptr_array(s_list), L, ncls, b, h * w, int(use_softmax), _p(out), _stream())
+    b, ncls = s_list[0].shape[0], s_list[0].shape[1]
+    hw = _spatial_numel(s_list[0].shape[2:])
+    _lib.call('uz_accumulate_output', _ptr_array(s_list), L, ncls, b, hw, int(use_softmax), _p(out), _stream())
     return out
 
 

@@ -11,7 +11,8 @@ from . import kern
 
 
 class Act:
-    """bf16 NHWC activation [N,H,W,Cp] (Cp = pad16(c)); ``c`` = logical channels."""
+    """bf16 channel-last activation [N,H,W,Cp] or, for volumes, [N,D,H,W,Cp] (Cp = padded c); ``c`` = logical
+    channels."""
     __slots__ = ('t', 'c')
 
     def __init__(self, t, c):
@@ -20,12 +21,18 @@ class Act:
 
     @property
     def shape(self):
-        n, h, w, _ = self.t.shape
-        return (n, self.c, h, w)
+        return (self.t.shape[0], self.c) + tuple(self.t.shape[1:-1])
 
 
 def _dense(t):
     """grads handed over by autograd may be arbitrary views; kernels need unit channel stride + packed pixels."""
+    if t.dim() == 5:
+        n, d, h, w, _ = t.shape
+        ld = t.stride(3)
+        if t.stride(4) == 1 and ld % 8 == 0 and t.data_ptr() % 16 == 0 and (h == 1 or t.stride(2) == w * ld) and \
+                (d == 1 or t.stride(1) == h * w * ld) and (n == 1 or t.stride(0) == d * h * w * ld):
+            return t
+        return t.contiguous()
     if t.stride(3) == 1 and (t.shape[1] == 1 or t.stride(1) == t.shape[2] * t.stride(2)) and \
             (t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.shape[2] * t.stride(2)) and t.stride(2) % 8 == 0 \
             and t.data_ptr() % 16 == 0:
@@ -84,19 +91,19 @@ class ToNHWC(torch.autograd.Function):
     """fp32 NCHW -> bf16 NHWC (padded).  Used at module boundaries and for z -> next conv."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, ld=None):
         ctx.c = x.shape[1]
-        return kern.nchw_to_nhwc(x)
+        return kern.nchw_to_nhwc(x, ld)
 
     @staticmethod
     def backward(ctx, g):
-        return kern.nhwc_to_nchw(_dense(g), ctx.c)
+        return kern.nhwc_to_nchw(_dense(g), ctx.c), None
 
 
 class FromNHWC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t, c):
-        ctx.ld = t.shape[3]
+        ctx.ld = t.shape[-1]
         return kern.nhwc_to_nchw(t, c)
 
     @staticmethod
@@ -109,7 +116,8 @@ def to_act(x):
         return x
     if not x.is_cuda:
         raise kern._lib.UnetZooLibError('UNet-Zoo B200 modules need CUDA tensors: there is no CPU fallback path')
-    return Act(ToNHWC.apply(x.float()), x.shape[1])
+    # volumes store channels in multiples of 32 (kern.pad_channels)
+    return Act(ToNHWC.apply(x.float(), kern.pad_channels(x.shape[1], x.dim())), x.shape[1])
 
 
 def from_act(a):
@@ -130,8 +138,8 @@ class ConvBNAct(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         wf, wd = kern.pack_conv_weight(weight, need_dgrad=need_dx)
         y, sums = kern.conv_fwd(x, wf, shift=bias, stats=True)
-        n, h, w, _ = x.shape
-        a, scale, shift, mean, invstd = kern.bn_apply_train(y, sums, n * h * w, gamma, beta, running_mean, running_var,
+        npix = kern._spatial_numel(x.shape[:-1])
+        a, scale, shift, mean, invstd = kern.bn_apply_train(y, sums, npix, gamma, beta, running_mean, running_var,
                                                             relu=relu)
         ctx.save_for_backward(x, y, wd, scale, shift, mean, invstd, gamma)
         ctx.relu = relu
@@ -147,8 +155,9 @@ class ConvBNAct(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx, _ = kern.conv_fwd(dy, wd)
-        cout, cin, kh, kw = ctx.wshape
-        dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, kh * kw, cin, cout), (x, dy)).view(cout, cin, kh, kw)
+        cout, cin = ctx.wshape[0], ctx.wshape[1]
+        taps = kern._spatial_numel(ctx.wshape[2:])
+        dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, taps, cin, cout), (x, dy)).view(ctx.wshape)
         dbias = kern.zero_arena.get(cout, dy.device)
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None
 
@@ -178,7 +187,8 @@ class ConvAffineAct(torch.autograd.Function):
             raise NotImplementedError('backward through eval-mode (folded) BatchNorm is not on the hot path; '
                                       'call net.train() for training (reference train_model.py:95)')
         da = _dense(da)
-        cout, cin, kh, kw = ctx.wshape
+        cout, cin = ctx.wshape[0], ctx.wshape[1]
+        taps = kern._spatial_numel(ctx.wshape[2:])
         one = torch.ones(cout, dtype=torch.float32, device=da.device)
         zero = torch.zeros_like(one)
         if ctx.relu:
@@ -188,7 +198,7 @@ class ConvAffineAct(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx, _ = kern.conv_fwd(dy, wd)
-        dw = kern.conv_wgrad(x, dy, kh * kw, cin, cout).view(cout, cin, kh, kw)
+        dw = kern.conv_wgrad(x, dy, taps, cin, cout).view(ctx.wshape)
         dshift = None
         if ctx.bias_is_shift and ctx.needs_input_grad[3]:
             dshift = kern.channel_sum(dy)
@@ -223,11 +233,9 @@ class Concat(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, b, up_a, up_b, align_corners):
-        n = a.shape[0]
-        h = a.shape[1] * (2 if up_a else 1)
-        w = a.shape[2] * (2 if up_a else 1)
-        ca, cb = a.shape[3], b.shape[3]
-        out = kern.new_act(n, h, w, ca + cb, a.device)
+        ca, cb = a.shape[-1], b.shape[-1]
+        sp = tuple(k * (2 if up_a else 1) for k in a.shape[1:-1])
+        out = torch.empty((a.shape[0],) + sp + (ca + cb,), dtype=torch.bfloat16, device=a.device)
         for src, up, sl in ((a, up_a, out[..., :ca]), (b, up_b, out[..., ca:])):
             if up:
                 kern.upsample2x_fwd(src, align_corners, out=sl)
@@ -265,7 +273,7 @@ class LatentHead(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat, wmu, bmu, wsig, bsig, eps):
-        c = feat.shape[3]
+        c = feat.shape[-1]
         wm = wmu.reshape(wmu.shape[0], -1)
         ws = wsig.reshape(wsig.shape[0], -1)
         if wm.shape[1] != c:          # features are channel padded
@@ -310,7 +318,7 @@ class SLayerNearest(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feat, weight, bias, factor):
-        c = feat.shape[3]
+        c = feat.shape[-1]
         w2 = weight.reshape(weight.shape[0], -1)
         if w2.shape[1] != c:
             w2 = torch.nn.functional.pad(w2, (0, c - w2.shape[1]))

@@ -91,10 +91,16 @@ class EvalStep:
     """One validation image like train_model.py:177-205: N copies -> forward(training=False) -> accumulate_output
     (softmax) -> argmax -> GED + NCC against M annotators.  ``shard`` = (rank, world) splits the N samples."""
 
-    def __init__(self, net, n_samples=100, n_classes=2):
+    def __init__(self, net, n_samples=100, n_classes=2, shard=None):
         self.net = net
         self.n = n_samples
         self.n_classes = n_classes
+        self.counts = None
+        self.n_local = n_samples
+        if shard is not None and shard[1] > 1:
+            from . import dp
+            self.counts = dp.shard_counts(n_samples, shard[1])
+            self.n_local = self.counts[shard[0]]
         net.eval()
 
     @torch.no_grad()
@@ -110,11 +116,14 @@ class EvalStep:
     def run_device(self, img, lab, utils=None):
         if utils is None:
             import utils
-        patch = img[None, None].repeat(self.n, 1, 1, 1)
+        patch = img[None, None].repeat(self.n_local, 1, 1, 1)
         masks = lab.permute(2, 0, 1).float()                       # [M,H,W]
-        mask = masks[0][None, None].repeat(self.n, 1, 1, 1)
+        mask = masks[0][None, None].repeat(self.n_local, 1, 1, 1)
         s_list = self.net.forward(patch, mask, training=False)
         probs = self.net.accumulate_output(s_list, use_softmax=True)
+        if self.counts is not None:                                # this rank's samples -> the full set on every rank
+            from . import dp
+            probs = dp.gather_samples(probs.contiguous(), self.counts)
         pred = kern.argmax_classes(probs)                          # torch.argmax(dim=1) of train_model.py:195
         ged = utils.generalised_energy_distance(pred, masks, nlabels=self.n_classes - 1,
                                                 label_range=range(1, self.n_classes))

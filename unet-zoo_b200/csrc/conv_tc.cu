@@ -19,7 +19,7 @@
 namespace uz {
 int g_conv_debug_flags = 0;
 int conv2_stats_rows(int N, int H, int W, int Cin, int Cout);
-int conv2_launch(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, void* y, int ldy,
+int conv2_launch(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, void* y, int ldy,
                  const float* scale, const float* shift, int relu, float* stats_partial, void* stream, int* handled);
 }  // namespace uz
 
@@ -265,8 +265,8 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   if (uz::g_conv_debug_flags & 128) return UZ_OK;   // measurement knob: step time without the conv kernels
   if (taps == 9 && !(uz::g_conv_debug_flags & 32)) {
     int handled = 0;
-    int rc = uz::conv2_launch(x, N, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, stream,
-                              &handled);
+    int rc = uz::conv2_launch(x, N, 0, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial,
+                              stream, &handled);
     if (rc || handled) return rc;
   }
   ConvParams p{};
@@ -334,6 +334,32 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   dim3 grid(tiles, splits, 1);
   uz::launch(conv_tc_kernel, grid, kThreads, smem, static_cast<cudaStream_t>(stream), tx, tw, p);
   UZ_CHECK_LAUNCH("uz_conv_fwd");
+  return UZ_OK;
+}
+
+// volumes: x bf16 NDHWC [N,D,H,W,Cin]; taps 27 (3x3x3, pad 1; packed [(kd*3+kw)*3+kh][Cout][Cin]) or 1 (1x1x1)
+extern "C" int uz_conv3d_fwd(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout,
+                             int taps, void* y, int ldy, const float* scale, const float* shift, int relu,
+                             float* stats_partial, void* stream) {
+  UZ_CHECK_ARG(taps == 27 || taps == 1, "uz_conv3d_fwd: taps must be 27 or 1 (got %d)", taps);
+  UZ_CHECK_ARG(D > 0, "uz_conv3d_fwd: D must be positive");
+  if (taps == 1) {   // pointwise: a volume is N*D images
+    UZ_CHECK_ARG(static_cast<long long>(N) * D < (1ll << 30), "uz_conv3d_fwd: batch too large");
+    return uz_conv_fwd(x, N * D, H, W, Cin, ldx, w_packed, Cout, 1, y, ldy, scale, shift, relu, stats_partial, stream);
+  }
+  UZ_CHECK_ARG(x && w_packed && y, "uz_conv3d_fwd: null pointer");
+  UZ_CHECK_ARG(Cin % 16 == 0 && Cin > 0, "uz_conv3d_fwd: Cin must be a positive multiple of 16 (got %d)", Cin);
+  UZ_CHECK_ARG(Cout % 32 == 0 && Cout > 0, "uz_conv3d_fwd: Cout must be a positive multiple of 32 (got %d)", Cout);
+  UZ_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= Cin && ldy >= Cout, "uz_conv3d_fwd: bad pixel strides");
+  UZ_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+               "uz_conv3d_fwd: pointers must be 16-byte aligned");
+  if (uz::g_conv_debug_flags & 128) return UZ_OK;
+  int handled = 0;
+  int rc = uz::conv2_launch(x, N, D, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, stream,
+                            &handled);
+  if (rc) return rc;
+  UZ_CHECK_ARG(handled, "uz_conv3d_fwd: no kernel plan for Cin=%d Cout=%d", Cin, Cout);
   return UZ_OK;
 }
 

@@ -1,4 +1,7 @@
-// Persistent 3x3 convolution (pad 1) on tcgen05 tensor cores for feature maps with H, W multiples of 16.
+// Persistent 3x3 (2-D) and 3x3x3 (3-D) convolution (pad 1) on tcgen05 tensor cores.  2-D feature maps need H, W multiples
+// of 16; volumes of any size are accepted (partial tiles: TMA zero-fills the loads and clips the stores, the statistics
+// epilogue masks the out-of-range pixels).  A 2-D map is the D = 1, nz = 1 case of the same kernel: tensor maps are
+// always 5-D (C, W, H, D, N) and the z taps are one more factor of the K loop.
 //
 // Second-generation kernel behind uz_conv_fwd (the generic conv_tc_kernel in conv_tc.cu keeps the small / odd shapes
 // and 1x1).  What profiling of the first kernel showed (profiles/r01_conv_v1_breakdown.md) and what this one does:
@@ -28,8 +31,10 @@ constexpr int kTile = 16;                 // 16 x 16 output pixels per work item
 constexpr int kSlabRows = (kTile + 2) * kTile;   // 18 image rows x 16 pixels
 
 struct Conv2Params {
-  int N, H, W, Cin, Cout;
-  int tilesW, tilesH, tiles;     // tiles per row / column / total (N * tilesH * tilesW)
+  int N, D, H, W, Cin, Cout;
+  int nz;                        // taps along z: 1 (2-D, D == 1) or 3
+  int mask;                      // partial tiles present: statistics must skip pixels outside the image
+  int tilesW, tilesH, tiles;     // tiles per row / column / total (N * D * tilesH * tilesW)
   int n_chunks, items;           // Cout / BN, tiles * n_chunks
   int KC, BN, CW;                // channels per K step, output channels per item, channels per store box
   int stages, nbuf;              // smem pipeline depth, TMEM accumulator buffers (1 or 2)
@@ -45,10 +50,11 @@ struct Conv2Params {
 __device__ __forceinline__ void tma_load_3d_box(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   uz::tma_load_3d(smem, m, bar, c0, c1, c2);
 }
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
-               "r"(uz::smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               "r"(uz::smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -102,7 +108,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const int lane = threadIdx.x & 31;
   constexpr uint32_t rowb = KC * 2;                        // bytes per smem row = swizzle span
   const int kblocks = p.Cin / KC;
-  const int k_steps = kblocks * 3;
+  const int taps_xz = 3 * p.nz;                            // (dz, dx) pairs per channel block
+  const int k_steps = kblocks * taps_xz;
+  const int z_off = p.nz >> 1;                             // 1 for 3 z taps, 0 for the 2-D case
   // every CTA owns one output-channel chunk and a strided share of the tiles
   const int chunk = blockIdx.x % p.n_chunks;
   const int slot = blockIdx.x / p.n_chunks;
@@ -147,16 +155,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       for (int tile = slot; tile < p.tiles; tile += slots) {
         const int x0 = (tile % p.tilesW) * kTile;
         const int y0 = ((tile / p.tilesW) % p.tilesH) * kTile;
-        const int n = tile / (p.tilesW * p.tilesH);
+        const int zn = tile / (p.tilesW * p.tilesH);
+        const int z0 = zn % p.D;
+        const int n = zn / p.D;
         for (int ks = 0; ks < k_steps; ++ks) {
-          const int kb = ks / 3, dx = ks - kb * 3;
+          const int kb = ks / taps_xz, r = ks - kb * taps_xz;
+          const int dz = r / 3, dx = r - dz * 3;
           uz::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * p.stage_bytes;
           if (uz::elect_one()) {
             uz::mbar_expect_tx(&full_bar[stage],
                                ((p.dbg & 4) ? 0 : p.a_bytes) + ((p.dbg & 8) ? 0 : p.stage_bytes - p.a_bytes));
-            if (!(p.dbg & 4)) uz::tma_load_4d(sa, &tmap_x, &full_bar[stage], kb * KC, x0 + dx - 1, y0 - 1, n);
-            if (!(p.dbg & 8)) tma_load_3d_box(sa + p.a_bytes, &tmap_w, &full_bar[stage], kb * KC, c_out0, dx * 3);
+            if (!(p.dbg & 4))
+              uz::tma_load_5d(sa, &tmap_x, &full_bar[stage], kb * KC, x0 + dx - 1, y0 - 1, z0 + dz - z_off, n);
+            if (!(p.dbg & 8)) tma_load_3d_box(sa + p.a_bytes, &tmap_w, &full_bar[stage], kb * KC, c_out0, r * 3);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -229,13 +241,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int acc_phase = (acc_it / p.nbuf) & 1;
       const int x0 = (tile % p.tilesW) * kTile;
       const int y0 = ((tile / p.tilesW) % p.tilesH) * kTile;
-      const int n = tile / (p.tilesW * p.tilesH);
+      const int zn = tile / (p.tilesW * p.tilesH);
+      const int z0 = zn % p.D;
+      const int n = zn / p.D;
       uz::mbar_wait(&acc_full[buf], acc_phase);
       uz::tc_fence_after();
       for (int half = 0; half < 2; ++half) {
         // staging buffer free? (previous TMA store has finished reading it)
         if (et == 0) tma_store_wait_read();
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool in_image = !p.mask || ((x0 + (row & 15) < p.W) && (y0 + 8 * half + (row >> 4) < p.H));
         if (!(p.dbg & 1)) {
           for (int c = 0; c < p.BN; c += 32) {
             uint32_t r[32];
@@ -250,8 +265,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               float b = fmaf(__uint_as_float(r[2 * j + 1]), s_scale[ch + 1], s_shift[ch + 1]);
               if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
               pk[j] = uz::pack_bf16x2(a, b);
-              v[2 * j] = uz::bf16lo(pk[j]);          // statistics of the values as stored
-              v[2 * j + 1] = uz::bf16hi(pk[j]);
+              v[2 * j] = in_image ? uz::bf16lo(pk[j]) : 0.f;          // statistics of the values as stored
+              v[2 * j + 1] = in_image ? uz::bf16hi(pk[j]) : 0.f;
             }
             // staging: box (c / CW), this thread's row, 16-byte chunks swizzled
             {
@@ -281,7 +296,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0 && !(p.dbg & 1)) {
           for (int cb = 0; cb < p.BN / p.CW; ++cb)
-            tma_store_4d(&tmap_y, smem_out + cb * box_bytes, c_out0 + cb * p.CW, x0, y0 + 8 * half, n);
+            tma_store_5d(&tmap_y, smem_out + cb * box_bytes, c_out0 + cb * p.CW, x0, y0 + 8 * half, z0, n);
           tma_store_commit();
         }
       }
@@ -315,13 +330,18 @@ struct Plan2 {
   size_t smem;
 };
 
-bool make_plan2(int N, int H, int W, int Cin, int Cout, Plan2* out) {
-  if (H % kTile || W % kTile || Cin % 16 || Cout % 32 || Cout > 4096) return false;
+// D == 0: 2-D map (3x3 taps, H and W must be multiples of the tile); D >= 1: volume (3x3x3 taps, any H, W)
+bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
+  const bool vol = D > 0;
+  if (Cin % 16 || Cout % 32 || Cout > 4096) return false;
+  if (!vol && (H % kTile || W % kTile)) return false;
   Conv2Params& p = out->p;
   p = Conv2Params{};
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  p.tilesW = W / kTile; p.tilesH = H / kTile;
-  p.tiles = N * p.tilesW * p.tilesH;
+  p.N = N; p.D = vol ? D : 1; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.nz = vol ? 3 : 1;
+  p.mask = (H % kTile || W % kTile) ? 1 : 0;
+  p.tilesW = (W + kTile - 1) / kTile; p.tilesH = (H + kTile - 1) / kTile;
+  p.tiles = N * p.D * p.tilesW * p.tilesH;
   const int sms = uz::num_sms();
   // output-channel chunking: whole Cout per item unless > 256 or too few items to occupy the SMs
   int bn = Cout;
@@ -371,44 +391,45 @@ namespace uz {
 
 int conv2_stats_rows(int N, int H, int W, int Cin, int Cout) {
   Plan2 pl;
-  if (!make_plan2(N, H, W, Cin, Cout, &pl)) return 0;
+  if (!make_plan2(N, 0, H, W, Cin, Cout, &pl)) return 0;
   return pl.grid;
 }
 
-// returns UZ_OK and sets *handled = 1 when the persistent kernel took the launch
-int conv2_launch(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, void* y, int ldy,
-                 const float* scale, const float* shift, int relu, float* stats_partial, void* stream, int* handled) {
+// returns UZ_OK and sets *handled = 1 when the persistent kernel took the launch.  D == 0: 2-D, 9 taps; D >= 1: 27 taps
+int conv2_launch(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, void* y,
+                 int ldy, const float* scale, const float* shift, int relu, float* stats_partial, void* stream,
+                 int* handled) {
   *handled = 0;
   Plan2 pl;
-  if (!make_plan2(N, H, W, Cin, Cout, &pl)) return UZ_OK;
+  if (!make_plan2(N, D, H, W, Cin, Cout, &pl)) return UZ_OK;
   Conv2Params& p = pl.p;
   p.scale = scale; p.shift = shift; p.relu = relu; p.stats = stats_partial;
   p.dbg = g_conv_debug_flags;
   const uint32_t swz = p.KC * 2;
   CUtensorMap tx, tw, ty;
   {
-    uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
-                        static_cast<uint64_t>(N)};
-    uint64_t strides[3] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(W) * ldx * 2,
-                           static_cast<uint64_t>(H) * W * ldx * 2};
-    uint32_t box[4] = {static_cast<uint32_t>(p.KC), kTile, kTile + 2, 1};
-    int rc = make_tmap_bf16(&tx, x, 4, dims, strides, box, swz);
+    uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(p.D), static_cast<uint64_t>(N)};
+    uint64_t strides[4] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(W) * ldx * 2,
+                           static_cast<uint64_t>(H) * W * ldx * 2, static_cast<uint64_t>(p.D) * H * W * ldx * 2};
+    uint32_t box[5] = {static_cast<uint32_t>(p.KC), kTile, kTile + 2, 1, 1};
+    int rc = make_tmap_bf16(&tx, x, 5, dims, strides, box, swz);
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Cout), 9};
+    uint64_t dims[3] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Cout), static_cast<uint64_t>(9 * p.nz)};
     uint64_t strides[2] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Cout) * Cin * 2};
     uint32_t box[3] = {static_cast<uint32_t>(p.KC), static_cast<uint32_t>(p.BN), 3};
     int rc = make_tmap_bf16(&tw, w_packed, 3, dims, strides, box, swz);
     if (rc) return rc;
   }
   {
-    uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
-                        static_cast<uint64_t>(N)};
-    uint64_t strides[3] = {static_cast<uint64_t>(ldy) * 2, static_cast<uint64_t>(W) * ldy * 2,
-                           static_cast<uint64_t>(H) * W * ldy * 2};
-    uint32_t box[4] = {static_cast<uint32_t>(p.CW), kTile, 8, 1};
-    int rc = make_tmap_bf16(&ty, y, 4, dims, strides, box, p.CW * 2);
+    uint64_t dims[5] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(p.D), static_cast<uint64_t>(N)};
+    uint64_t strides[4] = {static_cast<uint64_t>(ldy) * 2, static_cast<uint64_t>(W) * ldy * 2,
+                           static_cast<uint64_t>(H) * W * ldy * 2, static_cast<uint64_t>(p.D) * H * W * ldy * 2};
+    uint32_t box[5] = {static_cast<uint32_t>(p.CW), kTile, 8, 1, 1};
+    int rc = make_tmap_bf16(&ty, y, 5, dims, strides, box, p.CW * 2);
     if (rc) return rc;
   }
   auto kernel = p.KC == 64 ? conv_tc2_kernel<64> : (p.KC == 32 ? conv_tc2_kernel<32> : conv_tc2_kernel<16>);

@@ -34,7 +34,12 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 //   fwd : bf16 [taps][CoutP][CinP]            wp[t][o][i]  = w[o][i][src(t)]
 //   dgrad: bf16 [taps][CinP2][CoutP2]         wd[t][i][o]  = w[o][i][src(taps-1-t)]   (flipped taps, transposed channels)
 // Packed taps are dx-major, t = kw*3 + kh, so the three dy taps of one dx are contiguous (one TMA box in conv_tc2).
-__device__ __forceinline__ int src_tap(int t, int taps) { return taps == 9 ? (t % 3) * 3 + t / 3 : t; }
+// 27 taps (OIDHW, source s = (kd*3 + kh)*3 + kw): packed t = (kd*3 + kw)*3 + kh, same idea with the z tap outermost.
+__device__ __forceinline__ int src_tap(int t, int taps) {
+  if (taps == 9) return (t % 3) * 3 + t / 3;
+  if (taps == 27) return ((t / 9) * 3 + t % 3) * 3 + (t / 3) % 3;
+  return t;
+}
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, __nv_bfloat16* wp,
                                    int CoutP, int CinP, __nv_bfloat16* wd, int CinP2, int CoutP2) {
   uz::pdl_prologue();
@@ -507,6 +512,155 @@ __global__ void up2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, 
   }
 }
 
+// ---------------------------------------------------------------- volumes: 2x2x2 average pooling, trilinear x2
+// AvgPool3d(2,2,ceil_mode) on even sizes (reference models/phiseg3D.py:100); NDHWC, same vector scheme as the 2-D kernels.
+__global__ void avgpool3_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* out, int ldo, int N,
+                                    int Do, int Ho, int Wo, int C) {
+  uz::pdl_prologue();
+  const int chunks = C / 8;
+  const size_t total = static_cast<size_t>(N) * Do * Ho * Wo * chunks;
+  const size_t W = Wo * 2, HW = static_cast<size_t>(Ho * 2) * W;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(idx % chunks) * 8;
+    const size_t opix = idx / chunks;
+    const int xo = opix % Wo;
+    const int yo = (opix / Wo) % Ho;
+    const int zo = (opix / (static_cast<size_t>(Wo) * Ho)) % Do;
+    const size_t n = opix / (static_cast<size_t>(Wo) * Ho * Do);
+    const size_t ipix = ((n * (Do * 2) + zo * 2) * (Ho * 2) + yo * 2) * W + xo * 2;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a[8];
+      const size_t off = (k & 1) + ((k >> 1) & 1) * W + (k >> 2) * HW;
+      unpack8(*reinterpret_cast<const uint4*>(x + (ipix + off) * ldx + c0), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= 0.125f;
+    *reinterpret_cast<uint4*>(out + opix * ldo + c0) = pack8(acc);
+  }
+}
+
+__global__ void avgpool3_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, __nv_bfloat16* dx, int ldx, int N,
+                                    int Do, int Ho, int Wo, int C) {
+  uz::pdl_prologue();
+  const int chunks = C / 8;
+  const int D = Do * 2, H = Ho * 2, W = Wo * 2;
+  const size_t total = static_cast<size_t>(N) * D * H * W * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(idx % chunks) * 8;
+    const size_t ipix = idx / chunks;
+    const int xi = ipix % W;
+    const int yi = (ipix / W) % H;
+    const int zi = (ipix / (static_cast<size_t>(W) * H)) % D;
+    const size_t n = ipix / (static_cast<size_t>(W) * H * D);
+    const size_t opix = ((n * Do + zi / 2) * Ho + yi / 2) * Wo + xi / 2;
+    float g[8];
+    unpack8(*reinterpret_cast<const uint4*>(dout + opix * ldd + c0), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= 0.125f;
+    *reinterpret_cast<uint4*>(dx + ipix * ldx + c0) = pack8(g);
+  }
+}
+
+// trilinear x2, align_corners=True (reference models/phiseg3D.py:143,291-294,382-386)
+__global__ void up3_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* out, int ldo, int N, int d,
+                               int h, int w, int C) {
+  uz::pdl_prologue();
+  const int chunks = C / 8;
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  const size_t total = static_cast<size_t>(N) * D * H * W * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(idx % chunks) * 8;
+    const size_t opix = idx / chunks;
+    const int xo = opix % W;
+    const int yo = (opix / W) % H;
+    const int zo = (opix / (static_cast<size_t>(W) * H)) % D;
+    const size_t n = opix / (static_cast<size_t>(W) * H * D);
+    int xs[2], ys[2], zs[2];
+    float wx, wy, wz;
+    up2_src(xo, w, 1, xs[0], xs[1], wx);
+    up2_src(yo, h, 1, ys[0], ys[1], wy);
+    up2_src(zo, d, 1, zs[0], zs[1], wz);
+    const size_t base = n * d * h * w;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int kx = k & 1, ky = (k >> 1) & 1, kz = k >> 2;
+      const float cw = (kx ? wx : 1.f - wx) * (ky ? wy : 1.f - wy) * (kz ? wz : 1.f - wz);
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(
+                  x + (base + (static_cast<size_t>(zs[kz]) * h + ys[ky]) * w + xs[kx]) * ldx + c0), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(cw, a[j], acc[j]);
+    }
+    *reinterpret_cast<uint4*>(out + opix * ldo + c0) = pack8(acc);
+  }
+}
+
+// gather form of the transpose, separable weights
+__global__ void up3_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, __nv_bfloat16* dx, int ldx, int N, int d,
+                               int h, int w, int C) {
+  uz::pdl_prologue();
+  const int chunks = C / 8;
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  const size_t total = static_cast<size_t>(N) * d * h * w * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(idx % chunks) * 8;
+    const size_t ipix = idx / chunks;
+    const int xi = ipix % w;
+    const int yi = (ipix / w) % h;
+    const int zi = (ipix / (static_cast<size_t>(w) * h)) % d;
+    const size_t n = ipix / (static_cast<size_t>(w) * h * d);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int zlo = max(2 * zi - 2, 0), zhi = min(2 * zi + 3, D - 1);
+    const int ylo = max(2 * yi - 2, 0), yhi = min(2 * yi + 3, H - 1);
+    const int xlo = max(2 * xi - 2, 0), xhi = min(2 * xi + 3, W - 1);
+    for (int zo = zlo; zo <= zhi; ++zo) {
+      int z0, z1; float wz;
+      up2_src(zo, d, 1, z0, z1, wz);
+      float cz = 0.f;
+      if (z0 == zi) cz += 1.f - wz;
+      if (z1 == zi) cz += wz;
+      if (cz == 0.f) continue;
+      for (int yo = ylo; yo <= yhi; ++yo) {
+        int y0, y1; float wy;
+        up2_src(yo, h, 1, y0, y1, wy);
+        float cy = 0.f;
+        if (y0 == yi) cy += 1.f - wy;
+        if (y1 == yi) cy += wy;
+        if (cy == 0.f) continue;
+        for (int xo = xlo; xo <= xhi; ++xo) {
+          int x0, x1; float wx;
+          up2_src(xo, w, 1, x0, x1, wx);
+          float cx = 0.f;
+          if (x0 == xi) cx += 1.f - wx;
+          if (x1 == xi) cx += wx;
+          if (cx == 0.f) continue;
+          float g[8];
+          unpack8(*reinterpret_cast<const uint4*>(dout + (((n * D + zo) * H + yo) * W + xo) * ldd + c0), g);
+          const float cw = cz * cy * cx;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(cw, g[j], acc[j]);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + ipix * ldx + c0) = pack8(acc);
+  }
+}
+
 // ---------------------------------------------------------------- strided channel copy / add (concat, split, grad sum)
 __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int lds, __nv_bfloat16* dst, int ldd,
                                      size_t npix, int C, int accumulate) {
@@ -814,6 +968,42 @@ extern "C" int uz_upsample2x_bwd(const void* dout, int ldd, void* dx, int ldx, i
   uz::launch(up2_bwd_kernel, ew_blocks(static_cast<size_t>(N) * h * w * (C / 8)), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(dout), ldd, static_cast<__nv_bfloat16*>(dx), ldx, N, h, w, C, align_corners);
   UZ_CHECK_LAUNCH("uz_upsample2x_bwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_avgpool3_fwd(const void* x, int ldx, void* out, int ldo, int N, int Do, int Ho, int Wo, int C,
+                               void* stream) {
+  UZ_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "uz_avgpool3_fwd: bad arguments");
+  uz::launch(avgpool3_fwd_kernel, ew_blocks(static_cast<size_t>(N) * Do * Ho * Wo * (C / 8)), kEwThreads, 0, ST(stream),
+             static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, N, Do, Ho, Wo, C);
+  UZ_CHECK_LAUNCH("uz_avgpool3_fwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_avgpool3_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int Do, int Ho, int Wo, int C,
+                               void* stream) {
+  UZ_CHECK_ARG(dout && dx && C % 8 == 0 && ldx % 8 == 0 && ldd % 8 == 0, "uz_avgpool3_bwd: bad arguments");
+  uz::launch(avgpool3_bwd_kernel, ew_blocks(static_cast<size_t>(N) * Do * Ho * Wo * 8 * (C / 8)), kEwThreads, 0, ST(stream),
+             static_cast<const __nv_bfloat16*>(dout), ldd, static_cast<__nv_bfloat16*>(dx), ldx, N, Do, Ho, Wo, C);
+  UZ_CHECK_LAUNCH("uz_avgpool3_bwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_upsample3d_fwd(const void* x, int ldx, void* out, int ldo, int N, int d, int h, int w, int C,
+                                 void* stream) {
+  UZ_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "uz_upsample3d_fwd: bad arguments");
+  uz::launch(up3_fwd_kernel, ew_blocks(static_cast<size_t>(N) * d * h * w * 8 * (C / 8)), kEwThreads, 0, ST(stream),
+             static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, N, d, h, w, C);
+  UZ_CHECK_LAUNCH("uz_upsample3d_fwd");
+  return UZ_OK;
+}
+
+extern "C" int uz_upsample3d_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int d, int h, int w, int C,
+                                 void* stream) {
+  UZ_CHECK_ARG(dout && dx && C % 8 == 0 && ldx % 8 == 0 && ldd % 8 == 0, "uz_upsample3d_bwd: bad arguments");
+  uz::launch(up3_bwd_kernel, ew_blocks(static_cast<size_t>(N) * d * h * w * (C / 8)), kEwThreads, 0, ST(stream),
+             static_cast<const __nv_bfloat16*>(dout), ldd, static_cast<__nv_bfloat16*>(dx), ldx, N, d, h, w, C);
+  UZ_CHECK_LAUNCH("uz_upsample3d_bwd");
   return UZ_OK;
 }
 

@@ -185,11 +185,13 @@ __global__ void kl_bwd_kernel(const float* __restrict__ mu0, const float* __rest
 // ---------------------------------------------------------------- s_layer: 1x1 conv to logits + nearest upsample
 // one warp per LOW-res pixel; writes the f x f replicated block of the full-res fp32 NCHW output.
 __global__ void slayer_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ w,
-                                  const float* __restrict__ bias, int ncls, int B, int h, int wd, int f, float* out) {
+                                  const float* __restrict__ bias, int ncls, int B, int d, int h, int wd, int f, int fz,
+                                  float* out) {
+  // d = low-res depth (1 for 2-D maps), fz = replication along z (1 for 2-D, f for volumes)
   uz::pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int npix = B * h * wd;
+  const int npix = B * d * h * wd;
   if (warp >= npix) return;
   float acc[kMaxOut];
 #pragma unroll
@@ -205,19 +207,24 @@ __global__ void slayer_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld
 #pragma unroll
   for (int k = 0; k < kMaxOut; ++k)
     if (k < ncls) acc[k] = uz::warp_sum(acc[k]) + bias[k];
-  const int b = warp / (h * wd);
-  const int r = warp - b * h * wd;
+  const int bz = warp / (h * wd);
+  const int b = bz / d, zl = bz - b * d;
+  const int r = warp - bz * h * wd;
   const int yl = r / wd, xl = r - yl * wd;
   const int H = h * f, W = wd * f;
+  const size_t HW = static_cast<size_t>(H) * W;
   for (int k = 0; k < ncls; ++k) {
-    float* o = out + ((static_cast<size_t>(b) * ncls + k) * H + yl * f) * W + xl * f;
-    for (int i = lane; i < f * f; i += 32) o[(i / f) * W + (i % f)] = acc[k];
+    float* o = out + ((static_cast<size_t>(b) * ncls + k) * (d * fz) + zl * fz) * HW + static_cast<size_t>(yl * f) * W + xl * f;
+    for (int i = lane; i < fz * f * f; i += 32) {
+      const int iz = i / (f * f), ir = i - iz * f * f;
+      o[iz * HW + (ir / f) * W + (ir % f)] = acc[k];
+    }
   }
 }
 
 // backward: ds_low = sum over the f x f block of ds_full; dfeat = W^T ds_low; partial dW, db per block.
 __global__ void slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ feat, int ld, int C,
-                                  const float* __restrict__ w, int ncls, int B, int h, int wd, int f,
+                                  const float* __restrict__ w, int ncls, int B, int d, int h, int wd, int f, int fz,
                                   __nv_bfloat16* dfeat, int ldd, float* wpartial /*[blocks][ncls][C]*/,
                                   float* bpartial /*[blocks][ncls]*/) {
   uz::pdl_prologue();
@@ -231,20 +238,26 @@ __global__ void slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfl
 #pragma unroll
   for (int k = 0; k < kMaxOut; ++k) bacc[k] = 0.f;
   __syncwarp();
-  const int npix = B * h * wd;
+  const int npix = B * d * h * wd;
   const int H = h * f, W = wd * f;
+  const size_t HW = static_cast<size_t>(H) * W;
   for (int pix = blockIdx.x * warps + wid; pix < npix; pix += gridDim.x * warps) {
-    const int b = pix / (h * wd);
-    const int r = pix - b * h * wd;
+    const int bz = pix / (h * wd);
+    const int b = bz / d, zl = bz - b * d;
+    const int r = pix - bz * h * wd;
     const int yl = r / wd, xl = r - yl * wd;
     float g[kMaxOut];
 #pragma unroll
     for (int k = 0; k < kMaxOut; ++k) {
       g[k] = 0.f;
       if (k < ncls) {
-        const float* o = dout + ((static_cast<size_t>(b) * ncls + k) * H + yl * f) * W + xl * f;
+        const float* o = dout + ((static_cast<size_t>(b) * ncls + k) * (d * fz) + zl * fz) * HW +
+                         static_cast<size_t>(yl * f) * W + xl * f;
         float t = 0.f;
-        for (int i = lane; i < f * f; i += 32) t += o[(i / f) * W + (i % f)];
+        for (int i = lane; i < fz * f * f; i += 32) {
+          const int iz = i / (f * f), ir = i - iz * f * f;
+          t += o[iz * HW + (ir / f) * W + (ir % f)];
+        }
         g[k] = uz::warp_sum(t);
         bacc[k] += g[k];
       }
@@ -465,17 +478,32 @@ extern "C" int uz_kl_bwd(const float* mu0, const float* s0, const float* mu1, co
   return UZ_OK;
 }
 
-extern "C" int uz_slayer_fwd(const void* feat, int ld, int C, const float* w, const float* bias, int ncls, int B,
-                             int h, int wd, int factor, float* out, void* stream) {
+namespace {
+int slayer_fwd_impl(const void* feat, int ld, int C, const float* w, const float* bias, int ncls, int B, int d, int h,
+                    int wd, int factor, int fz, float* out, void* stream) {
   UZ_CHECK_ARG(feat && w && bias && out, "uz_slayer_fwd: null pointer");
   UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxOut, "uz_slayer_fwd: %d outputs unsupported (max %d)", ncls, kMaxOut);
-  UZ_CHECK_ARG(C % 2 == 0 && ld % 2 == 0 && factor >= 1, "uz_slayer_fwd: bad C/ld/factor");
-  const int npix = B * h * wd;
+  UZ_CHECK_ARG(C % 2 == 0 && ld % 2 == 0 && factor >= 1 && d >= 1, "uz_slayer_fwd: bad C/ld/factor");
+  const long long npix = static_cast<long long>(B) * d * h * wd;
   const int threads = 256;
-  uz::launch(slayer_fwd_kernel, (npix * 32 + threads - 1) / threads, threads, 0, ST(stream), 
-      static_cast<const __nv_bfloat16*>(feat), ld, C, w, bias, ncls, B, h, wd, factor, out);
+  uz::launch(slayer_fwd_kernel, static_cast<unsigned>((npix * 32 + threads - 1) / threads), threads, 0, ST(stream),
+      static_cast<const __nv_bfloat16*>(feat), ld, C, w, bias, ncls, B, d, h, wd, factor, fz, out);
   UZ_CHECK_LAUNCH("uz_slayer_fwd");
   return UZ_OK;
+}
+int slayer_bwd_impl(const float* dout, const void* feat, int ld, int C, const float* w, int ncls, int B, int d, int h,
+                    int wd, int factor, int fz, void* dfeat, int ldd, float* wpartial, float* bpartial, float* dw,
+                    float* db, void* stream);
+}  // namespace
+
+extern "C" int uz_slayer_fwd(const void* feat, int ld, int C, const float* w, const float* bias, int ncls, int B,
+                             int h, int wd, int factor, float* out, void* stream) {
+  return slayer_fwd_impl(feat, ld, C, w, bias, ncls, B, 1, h, wd, factor, 1, out, stream);
+}
+
+extern "C" int uz_slayer3d_fwd(const void* feat, int ld, int C, const float* w, const float* bias, int ncls, int B,
+                               int d, int h, int wd, int factor, float* out, void* stream) {
+  return slayer_fwd_impl(feat, ld, C, w, bias, ncls, B, d, h, wd, factor, factor, out, stream);
 }
 
 extern "C" int uz_slayer_bwd_num_blocks(int B, int h, int wd) {
@@ -485,16 +513,32 @@ extern "C" int uz_slayer_bwd_num_blocks(int B, int h, int wd) {
 extern "C" int uz_slayer_bwd(const float* dout, const void* feat, int ld, int C, const float* w, int ncls, int B, int h,
                              int wd, int factor, void* dfeat, int ldd, float* wpartial, float* bpartial, float* dw,
                              float* db, void* stream) {
+  return slayer_bwd_impl(dout, feat, ld, C, w, ncls, B, 1, h, wd, factor, 1, dfeat, ldd, wpartial, bpartial, dw, db,
+                         stream);
+}
+
+// volumes: feat [B,d,h,wd,C]; dout fp32 [B,ncls,d*f,h*f,wd*f]; workspace rows = uz_slayer_bwd_num_blocks(B * d, h, wd)
+extern "C" int uz_slayer3d_bwd(const float* dout, const void* feat, int ld, int C, const float* w, int ncls, int B,
+                               int d, int h, int wd, int factor, void* dfeat, int ldd, float* wpartial, float* bpartial,
+                               float* dw, float* db, void* stream) {
+  return slayer_bwd_impl(dout, feat, ld, C, w, ncls, B, d, h, wd, factor, factor, dfeat, ldd, wpartial, bpartial, dw,
+                         db, stream);
+}
+
+namespace {
+int slayer_bwd_impl(const float* dout, const void* feat, int ld, int C, const float* w, int ncls, int B, int d, int h,
+                    int wd, int factor, int fz, void* dfeat, int ldd, float* wpartial, float* bpartial, float* dw,
+                    float* db, void* stream) {
   UZ_CHECK_ARG(dout && feat && w && dfeat && wpartial && bpartial && dw && db, "uz_slayer_bwd: null pointer");
   UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxOut, "uz_slayer_bwd: %d outputs unsupported", ncls);
   int warps = static_cast<int>((44 * 1024) / (static_cast<size_t>(ncls) * C * sizeof(float)));
   if (warps > 8) warps = 8;
   UZ_CHECK_ARG(warps >= 1, "uz_slayer_bwd: ncls*C too large for the shared accumulators");
   const int threads = warps * 32;
-  const int blocks = uz_slayer_bwd_num_blocks(B, h, wd);
+  const int blocks = uz_slayer_bwd_num_blocks(B * d, h, wd);
   const size_t smem = static_cast<size_t>(warps) * ncls * C * sizeof(float);
   uz::launch(slayer_bwd_kernel, blocks, threads, smem, ST(stream), dout, static_cast<const __nv_bfloat16*>(feat), ld, C, w, ncls,
-                                                           B, h, wd, factor, static_cast<__nv_bfloat16*>(dfeat), ldd,
+                                                           B, d, h, wd, factor, fz, static_cast<__nv_bfloat16*>(dfeat), ldd,
                                                            wpartial, bpartial);
   UZ_CHECK_LAUNCH("uz_slayer_bwd");
   uz::launch(column_reduce_kernel, (ncls * C + 127) / 128, 128, 0, ST(stream), wpartial, blocks, ncls * C, dw, 1.f);
@@ -502,6 +546,7 @@ extern "C" int uz_slayer_bwd(const float* dout, const void* feat, int ld, int C,
   UZ_CHECK_LAUNCH("uz_slayer_bwd(reduce)");
   return UZ_OK;
 }
+}  // namespace
 
 extern "C" int uz_residual_ce_num_blocks(int B, int hw) {
   return cap_blocks((static_cast<long long>(B) * hw + 255) / 256, 4);

@@ -189,12 +189,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 // taps are MMAs on row-offset views of the slab (MN-major operands: K = pixel rows, a dy shift is 16 rows = 2 swizzle
 // atoms).  Operand traffic drops to ~45 B per tensor-core cycle.  Three [128 x <=128] fp32 accumulators live in TMEM.
 struct Wgrad2Params {
-  int N, H, W, Cin, Cout;
+  int N, D, H, W, Cin, Cout;   // D = 1 for 2-D maps
+  int nz;                      // z taps: 1 (2-D) or 3 (volumes); tensor maps are always 5-D (C, W, H, D, N)
   int tilesW, tilesH, num_tiles;
   int ci_chunks, co_blocks;
   int a_boxes;
   int stages;
-  float* partial;           // [splits][9][Cout][Cin]
+  float* partial;           // [splits][9 * nz][Cout][Cin]
 };
 
 constexpr int kW2Pix = 128;                 // 8 rows x 16 pixels
@@ -214,10 +215,12 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int split = blockIdx.x, splits = gridDim.x;
-  // blockIdx.y -> (co block, dx, ci chunk)
+  // blockIdx.y -> (co block, (dz, dx), ci chunk)
   const int cc = blockIdx.y % p.ci_chunks;
-  const int dx = (blockIdx.y / p.ci_chunks) % 3;
-  const int co0 = (blockIdx.y / (p.ci_chunks * 3)) * 128;
+  const int dxz = (blockIdx.y / p.ci_chunks) % (3 * p.nz);
+  const int dx = dxz % 3, dz = dxz / 3;
+  const int z_off = p.nz >> 1;
+  const int co0 = (blockIdx.y / (p.ci_chunks * 3 * p.nz)) * 128;
   const int ci0 = cc * 128;
   int nch = p.Cin - ci0; if (nch > 128) nch = 128;      // input channels of this CTA (multiple of 16)
   const int b_boxes = (nch + 63) / 64;
@@ -255,15 +258,18 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
       const int tile = split + ti * splits;
       const int x0 = (tile % p.tilesW) * 16;
       const int y0 = ((tile / p.tilesW) % p.tilesH) * 8;
-      const int n = tile / (p.tilesW * p.tilesH);
+      const int zn = tile / (p.tilesW * p.tilesH);
+      const int z0 = zn % p.D;
+      const int n = zn / p.D;
       uz::mbar_wait(&empty_bar[stage], phase ^ 1);
       if (uz::elect_one()) {
         uint8_t* sa = smem + stage * stage_bytes;
         uz::mbar_expect_tx(&full_bar[stage], tx_bytes);
         for (int b = 0; b < p.a_boxes; ++b)
-          uz::tma_load_4d(sa + b * kW2ABox, &tmap_dy, &full_bar[stage], co0 + b * 64, x0, y0, n);
+          uz::tma_load_5d(sa + b * kW2ABox, &tmap_dy, &full_bar[stage], co0 + b * 64, x0, y0, z0, n);
         for (int b = 0; b < b_boxes; ++b)
-          uz::tma_load_4d(sa + a_bytes + b * kW2BBox, &tmap_x, &full_bar[stage], ci0 + b * 64, x0 + dx - 1, y0 - 1, n);
+          uz::tma_load_5d(sa + a_bytes + b * kW2BBox, &tmap_x, &full_bar[stage], ci0 + b * 64, x0 + dx - 1, y0 - 1,
+                          z0 + dz - z_off, n);
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -304,8 +310,8 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
       uz::tc_fence_after();
     }
     for (int dy = 0; dy < 3; ++dy) {
-      const int tap = dy * 3 + dx;      // OIHW order kh*3 + kw
-      float* dst = p.partial + ((static_cast<size_t>(split) * 9 + tap) * p.Cout + co) * p.Cin + ci0;
+      const int tap = (dz * 3 + dy) * 3 + dx;      // OI(D)HW order (kd*3 + kh)*3 + kw; dz == 0 in 2-D
+      float* dst = p.partial + ((static_cast<size_t>(split) * 9 * p.nz + tap) * p.Cout + co) * p.Cin + ci0;
       for (int c = 0; c < nch; c += 16) {
         uint32_t r[16];
         if (my_tiles > 0) {
@@ -340,14 +346,18 @@ struct Plan2 {
   size_t smem;
 };
 
-bool make_plan2(int N, int H, int W, int Cin, int Cout, int taps, Plan2* out) {
-  if (taps != 9 || H % 8 || W % 16 || Cin % 16 || Cout % 16) return false;
-  if (uz::g_conv_debug_flags & 32) return false;
+// D == 0: 2-D map, 9 taps (H % 8 == 0, W % 16 == 0); D >= 1: volume, 27 taps, any H / W (out-of-range dy rows load as zeros)
+bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, int taps, Plan2* out) {
+  const bool vol = D > 0;
+  if (taps != (vol ? 27 : 9) || Cin % 16 || Cout % 16) return false;
+  if (!vol && (H % 8 || W % 16)) return false;
+  if (!vol && (uz::g_conv_debug_flags & 32)) return false;
   Wgrad2Params& p = out->p;
   p = Wgrad2Params{};
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  p.tilesW = W / 16; p.tilesH = H / 8;
-  p.num_tiles = N * p.tilesW * p.tilesH;
+  p.N = N; p.D = vol ? D : 1; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.nz = vol ? 3 : 1;
+  p.tilesW = (W + 15) / 16; p.tilesH = (H + 7) / 8;
+  p.num_tiles = N * p.D * p.tilesW * p.tilesH;
   p.ci_chunks = (Cin + 127) / 128;
   p.co_blocks = (Cout + 127) / 128;
   p.a_boxes = Cout > 64 ? 2 : 1;
@@ -357,7 +367,7 @@ bool make_plan2(int N, int H, int W, int Cin, int Cout, int taps, Plan2* out) {
   if (stages < 2) return false;
   p.stages = stages;
   out->smem = stages * stage_bytes + 1024;
-  const int per_split = p.co_blocks * 3 * p.ci_chunks;
+  const int per_split = p.co_blocks * 3 * p.nz * p.ci_chunks;
   int splits = uz::num_sms() / per_split;
   if (splits > p.num_tiles) splits = p.num_tiles;
   if (splits < 1) splits = 1;
@@ -431,45 +441,71 @@ int make_plan(int N, int H, int W, int Cin, int Cout, int taps, Plan* out) {
 
 }  // namespace
 
+extern "C" long long uz_wgrad3d_workspace_floats(int N, int D, int H, int W, int Cin, int Cout) {
+  Plan2 pl2;
+  if (D > 0 && Cin > 0 && Cout > 0 && make_plan2(N, D, H, W, Cin, Cout, 27, &pl2))
+    return static_cast<long long>(pl2.splits) * 27 * Cout * Cin;
+  return -1;
+}
+
 extern "C" long long uz_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout, int taps) {
   Plan2 pl2;
-  if (Cin > 0 && Cout > 0 && make_plan2(N, H, W, Cin, Cout, taps, &pl2))
+  if (Cin > 0 && Cout > 0 && make_plan2(N, 0, H, W, Cin, Cout, taps, &pl2))
     return static_cast<long long>(pl2.splits) * taps * Cout * Cin;
   Plan pl;
   if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0 || Cin > 512 || make_plan(N, H, W, Cin, Cout, taps, &pl)) return -1;
   return static_cast<long long>(pl.splits) * taps * Cout * Cin;
 }
 
+namespace {
+int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout, int taps,
+               int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream);
+}
+
 // x: bf16 NHWC [N,H,W,Cin] (ldx), dy: bf16 NHWC [N,H,W,Cout] (lddy); dw: fp32 [Cout_logical][Cin_logical][taps].
 extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, int N, int H, int W, int Cin, int Cout,
                              int taps, int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream) {
-  UZ_CHECK_ARG(x && dy && workspace && dw, "uz_conv_wgrad: null pointer");
   UZ_CHECK_ARG(taps == 9 || taps == 1, "uz_conv_wgrad: taps must be 9 or 1");
+  return wgrad_impl(x, ldx, dy, lddy, N, 0, H, W, Cin, Cout, taps, Cin_logical, Cout_logical, workspace, dw, stream);
+}
+
+// volumes: x bf16 NDHWC [N,D,H,W,Cin], dy [N,D,H,W,Cout]; dw fp32 [Cout_logical][Cin_logical][27] (OIDHW)
+extern "C" int uz_conv3d_wgrad(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin,
+                               int Cout, int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream) {
+  UZ_CHECK_ARG(D > 0, "uz_conv3d_wgrad: D must be positive");
+  return wgrad_impl(x, ldx, dy, lddy, N, D, H, W, Cin, Cout, 27, Cin_logical, Cout_logical, workspace, dw, stream);
+}
+
+namespace {
+int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout, int taps,
+               int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream) {
+  UZ_CHECK_ARG(x && dy && workspace && dw, "uz_conv_wgrad: null pointer");
   UZ_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0 && Cin > 0 && Cout > 0 && Cin <= 512,
                "uz_conv_wgrad: channels must be multiples of 16, Cin <= 512 (got %d, %d)", Cin, Cout);
   UZ_CHECK_ARG(ldx % 8 == 0 && lddy % 8 == 0 && ldx >= Cin && lddy >= Cout, "uz_conv_wgrad: bad pixel strides");
   UZ_CHECK_ARG(Cin_logical <= Cin && Cout_logical <= Cout, "uz_conv_wgrad: logical dims exceed stored dims");
   if (uz::g_conv_debug_flags & 256) return UZ_OK;   // measurement knob: step time without the wgrad kernels
   Plan2 pl2;
-  if (make_plan2(N, H, W, Cin, Cout, taps, &pl2)) {
+  if (make_plan2(N, D, H, W, Cin, Cout, taps, &pl2)) {
     pl2.p.partial = workspace;
+    const uint64_t Dd = static_cast<uint64_t>(pl2.p.D);
     CUtensorMap tdy2, tx2;
     {
-      uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+      uint64_t dims[5] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H), Dd,
                           static_cast<uint64_t>(N)};
-      uint64_t strides[3] = {static_cast<uint64_t>(lddy) * 2, static_cast<uint64_t>(W) * lddy * 2,
-                             static_cast<uint64_t>(H) * W * lddy * 2};
-      uint32_t box[4] = {64, 16, 8, 1};
-      int rc2 = uz::make_tmap_bf16(&tdy2, dy, 4, dims, strides, box, 128);
+      uint64_t strides[4] = {static_cast<uint64_t>(lddy) * 2, static_cast<uint64_t>(W) * lddy * 2,
+                             static_cast<uint64_t>(H) * W * lddy * 2, Dd * H * W * lddy * 2};
+      uint32_t box[5] = {64, 16, 8, 1, 1};
+      int rc2 = uz::make_tmap_bf16(&tdy2, dy, 5, dims, strides, box, 128);
       if (rc2) return rc2;
     }
     {
-      uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+      uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H), Dd,
                           static_cast<uint64_t>(N)};
-      uint64_t strides[3] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(W) * ldx * 2,
-                             static_cast<uint64_t>(H) * W * ldx * 2};
-      uint32_t box[4] = {64, 16, 10, 1};
-      int rc2 = uz::make_tmap_bf16(&tx2, x, 4, dims, strides, box, 128);
+      uint64_t strides[4] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(W) * ldx * 2,
+                             static_cast<uint64_t>(H) * W * ldx * 2, Dd * H * W * ldx * 2};
+      uint32_t box[5] = {64, 16, 10, 1, 1};
+      int rc2 = uz::make_tmap_bf16(&tx2, x, 5, dims, strides, box, 128);
       if (rc2) return rc2;
     }
     static size_t attr2 = 0;
@@ -483,7 +519,7 @@ extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, i
       }
       attr2 = pl2.smem;
     }
-    dim3 grid2(pl2.splits, pl2.p.co_blocks * 3 * pl2.p.ci_chunks, 1);
+    dim3 grid2(pl2.splits, pl2.p.co_blocks * 3 * pl2.p.nz * pl2.p.ci_chunks, 1);
     uz::launch(wgrad_tc2_kernel, grid2, kThreads, pl2.smem, static_cast<cudaStream_t>(stream), tdy2, tx2, pl2.p);
     UZ_CHECK_LAUNCH("uz_conv_wgrad(v2)");
     const size_t total2 = static_cast<size_t>(Cout_logical) * Cin_logical * taps;
@@ -494,6 +530,7 @@ extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, i
     UZ_CHECK_LAUNCH("uz_conv_wgrad(v2 reduce)");
     return UZ_OK;
   }
+  UZ_CHECK_ARG(D == 0, "uz_conv3d_wgrad: unsupported shape Cin=%d Cout=%d", Cin, Cout);
   Plan pl;
   int rc = make_plan(N, H, W, Cin, Cout, taps, &pl);
   UZ_CHECK_ARG(rc == UZ_OK, "uz_conv_wgrad: no plan for Cin=%d Cout=%d", Cin, Cout);
@@ -542,3 +579,4 @@ extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, i
   UZ_CHECK_LAUNCH("uz_conv_wgrad(reduce)");
   return UZ_OK;
 }
+}  // namespace

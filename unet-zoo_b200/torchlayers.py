@@ -48,24 +48,30 @@ def _boundary(fn):
 
 
 class Conv2D(nn.Module):
-    """conv(k in {3 (pad 1), 1 (pad 0)}) + bias -> norm(eps 1e-3, momentum 0.01) -> activation."""
+    """conv(k in {3 (pad 1), 1 (pad 0)}) + bias -> norm(eps 1e-3, momentum 0.01) -> activation.
+    ``_conv_cls`` / ``_norm_cls`` / ``_granule`` let models/phiseg3D.py derive its Conv3D from the same code."""
+    _conv_cls = nn.Conv2d
+    _norm_cls = nn.BatchNorm2d
+    _granule = 16            # output channels the tensor-core path stores per group
 
     def __init__(self, input_dim, output_dim, kernel_size=3, stride=1, padding=1, activation=torch.nn.ReLU,
-                 norm=torch.nn.BatchNorm2d, norm_before_activation=True):
+                 norm=None, norm_before_activation=True):
         super(Conv2D, self).__init__()
+        if norm is None:
+            norm = self._norm_cls
         if kernel_size not in (1, 3) or stride != 1:
-            raise NotImplementedError('B200 Conv2D supports the shapes the reference uses: kernel 1 or 3, stride 1')
+            raise NotImplementedError('B200 conv layers support the shapes the reference uses: kernel 1 or 3, stride 1')
         padding = 1 if kernel_size == 3 else 0
-        layers = [nn.Conv2d(input_dim, output_dim, kernel_size=kernel_size, stride=stride, padding=padding)]
+        layers = [self._conv_cls(input_dim, output_dim, kernel_size=kernel_size, stride=stride, padding=padding)]
         if norm_before_activation:
             layers.append(norm(num_features=output_dim, eps=1e-3, momentum=0.01))
             layers.append(activation())
         else:
             raise NotImplementedError('norm_before_activation=False is never used by the reference models')
         self.convolution = nn.Sequential(*layers)
-        if not isinstance(self.convolution[1], (nn.BatchNorm2d, nn.Identity)) or \
+        if not isinstance(self.convolution[1], (self._norm_cls, nn.Identity)) or \
                 not isinstance(self.convolution[2], (nn.ReLU, nn.Identity)):
-            raise NotImplementedError('B200 Conv2D supports norm in {BatchNorm2d, Identity}, activation in {ReLU, Identity}')
+            raise NotImplementedError('B200 conv layers support norm in {BatchNorm, Identity}, activation in {ReLU, Identity}')
         self.input_dim = input_dim
         self.output_dim = output_dim
 
@@ -73,10 +79,10 @@ class Conv2D(nn.Module):
     def forward(self, x):
         conv, bn, act = self.convolution[0], self.convolution[1], self.convolution[2]
         relu = isinstance(act, nn.ReLU)
-        if self.output_dim % 16 != 0:
-            raise NotImplementedError('Conv2D with %d output channels: use the fused logits path '
-                                      '(b200.ops.SLayerNearest)' % self.output_dim)
-        if isinstance(bn, nn.BatchNorm2d):
+        if self.output_dim % self._granule != 0:
+            raise NotImplementedError('%s with %d output channels (needs a multiple of %d): use the fused logits path '
+                                      '(b200.ops.SLayerNearest)' % (type(self).__name__, self.output_dim, self._granule))
+        if isinstance(bn, self._norm_cls):
             if self.training:
                 t = ops.ConvBNAct.apply(x.t, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
                                         bn.running_var, relu, x.c)
@@ -124,9 +130,9 @@ class ReversibleBlock(nn.Module):
 
     def couple(self, x):
         """x: bf16 NHWC [N,H,W,C] -> y of the same shape; no autograd (callers handle gradients by inversion)."""
-        n, h, w, c = x.shape
+        c = x.shape[-1]
         half = c // 2
-        y = kern.new_act(n, h, w, c, x.device)
+        y = kern._like(x, c)
         x1, x2, y1, y2 = x[..., :half], x[..., half:], y[..., :half], y[..., half:]
         fx2 = self.f_block(Act(x2, half)).t
         kern.copy_channels(x1, y1)
@@ -140,10 +146,10 @@ class ReversibleBlock(nn.Module):
         """Inverse recompute (revtorch ReversibleBlock.backward_pass): returns (x, dx); parameter gradients are
         accumulated into ``.grad`` by the inner backward calls, F and G run a second time (BatchNorm running
         statistics receive their second momentum update)."""
-        n, h, w, c = y.shape
+        c = y.shape[-1]
         half = c // 2
-        x = kern.new_act(n, h, w, c, y.device)
-        dx = kern.new_act(n, h, w, c, y.device)
+        x = kern._like(y, c)
+        dx = kern._like(y, c)
         y1, y2, dy1, dy2 = y[..., :half], y[..., half:], dy[..., :half], dy[..., half:]
         x1, x2, dx1, dx2 = x[..., :half], x[..., half:], dx[..., :half], dx[..., half:]
         y1_leaf = y1.detach().requires_grad_(True)
@@ -214,18 +220,22 @@ class ReversibleSequence(nn.Module):
     ``reversible_depth`` additive-coupling blocks whose F and G are 3x3 Conv2D on half the channels.  Only the stack's
     output is kept for backward; inputs are regenerated block by block (activation memory ~ 1/depth)."""
 
+    _conv_layer = Conv2D
+
     def __init__(self, input_dim, output_dim, reversible_depth=3, kernel=3):
         super(ReversibleSequence, self).__init__()
-        if output_dim % 32 != 0:
-            raise NotImplementedError('reversible stacks need channel halves that are multiples of 16 on the B200 path')
+        Conv = self._conv_layer
+        if output_dim % (2 * Conv._granule) != 0:
+            raise NotImplementedError('reversible stacks need channel halves that are multiples of %d on the B200 path'
+                                      % Conv._granule)
         if input_dim != output_dim:
-            self.inital_conv = Conv2D(input_dim, output_dim, kernel_size=1)
+            self.inital_conv = Conv(input_dim, output_dim, kernel_size=1)
         else:
             self.inital_conv = nn.Identity()
         blocks = []
         for i in range(reversible_depth):
-            f_func = nn.Sequential(Conv2D(output_dim // 2, output_dim // 2, kernel_size=kernel, padding=1))
-            g_func = nn.Sequential(Conv2D(output_dim // 2, output_dim // 2, kernel_size=kernel, padding=1))
+            f_func = nn.Sequential(Conv(output_dim // 2, output_dim // 2, kernel_size=kernel, padding=1))
+            g_func = nn.Sequential(Conv(output_dim // 2, output_dim // 2, kernel_size=kernel, padding=1))
             blocks.append(ReversibleBlock(f_func, g_func))
         self.sequence = _RevtorchSequence(nn.ModuleList(blocks))
 

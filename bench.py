@@ -130,9 +130,14 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm), 'power_w_max': max(pw) if pw else None}
 
 
-def synthetic_batches(n_batches, seed):
+def synthetic_batches(n_batches, seed, volume=None):
     from oracle import synth
     out = []
+    if volume is not None:               # BraTS-shaped volumes [1,4,S,S,S] + index labels
+        for i in range(n_batches):
+            vol, lab = synth.brats_like_batch(1, size=volume, seed=seed + i)
+            out.append((vol.pin_memory(), lab.pin_memory(), None))
+        return out
     for i in range(n_batches):
         patch, labels, mask = synth.lidc_like_batch(BATCH, seed=seed + i)
         out.append((patch.pin_memory(), mask.pin_memory(), labels))
@@ -245,7 +250,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='time eager steps instead of CUDA-graph replay')
     ap.add_argument('--skip-eval', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
-    ap.add_argument('--model', default='phiseg', choices=['phiseg', 'revphiseg', 'probunet', 'unet'],
+    ap.add_argument('--volume', type=int, default=128, help='edge of the cubic volume for --model phiseg3d')
+    ap.add_argument('--model', default='phiseg', choices=['phiseg', 'revphiseg', 'probunet', 'unet', 'phiseg3d'],
                     help='phiseg = the headline workload; the others are reported as side information')
     args = ap.parse_args()
 
@@ -265,7 +271,12 @@ def main():
     from oracle import synth
 
     torch.manual_seed(1234 + rank)
-    if args.model == 'phiseg':
+    batch_n, image = BATCH, IMAGE
+    if args.model == 'phiseg3d':
+        from tests.keygrammar import dropin_phiseg3d
+        batch_n, image = 1, (4, args.volume, args.volume, args.volume)     # 4 x 128^3, B = 1 per GPU
+        net = dropin_phiseg3d([32, 64, 128], 3, image)
+    elif args.model == 'phiseg':
         net = dropin_phiseg(FILTERS)
     elif args.model == 'revphiseg':
         net = dropin_phiseg(FILTERS, reversible=True)
@@ -279,8 +290,8 @@ def main():
     net = net.to(device)
     opt = train.make_adam(net, capturable=True)
     dp = dpmod.GradientAllReduce(net.parameters()) if world > 1 else None
-    step = train.TrainStep(net, opt, BATCH, IMAGE, use_graph=not args.no_graph, dp=dp, device=device)
-    batches = synthetic_batches(4, seed=1000 * (rank + 1))
+    step = train.TrainStep(net, opt, batch_n, image, use_graph=not args.no_graph, dp=dp, device=device)
+    batches = synthetic_batches(4, seed=1000 * (rank + 1), volume=args.volume if args.model == 'phiseg3d' else None)
     step.patch.copy_(batches[0][0])
     step.mask.copy_(batches[0][1])
     step.prepare(warmup=3)
@@ -300,7 +311,7 @@ def main():
     eager_launches = _lib.raw('uz_launch_count')() - l0
     gpu_launches = step.launches_per_step * args.steps if step.graph is not None else eager_launches
     ms_step = ms_total / args.steps
-    value = world * BATCH / (ms_step / 1000.0)
+    value = world * batch_n / (ms_step / 1000.0)
 
     # ---- end to end through the public API (pinned host batch in, loss float out)
     losses = []
@@ -316,7 +327,7 @@ def main():
         step.step_device()               # keep the load up for >= ~1.2 s so the 100 ms clock sampler sees it
     torch.cuda.synchronize()
     clk.__exit__()
-    e2e = {'value': world * BATCH / (ms_e2e / 1000.0), 'unit': 'images/s',
+    e2e = {'value': world * batch_n / (ms_e2e / 1000.0), 'unit': 'images/s',
            'h2d_bytes_per_step': int(batches[0][0].numel() * 4 + batches[0][1].numel() * 4), 'd2h_bytes_per_step': 4,
            'ms_per_step': ms_e2e, 'api': 'b200.train.TrainStep.step_host (CUDA-graph replay)' if step.graph is not None
            else 'b200.train.TrainStep.step_host (eager)'}
@@ -329,7 +340,8 @@ def main():
         pass
     peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (measured)' if peaks else 'fallback 1.4 PFLOP/s sustained'
-    side_models = {'revphiseg': 18.318e9, 'probunet': 13.598e9, 'unet': 6.958e9}      # SURVEY.md 8d, forward GFLOP / image
+    side_models = {'revphiseg': 18.318e9, 'probunet': 13.598e9, 'unet': 6.958e9,      # SURVEY.md 8d, forward GFLOP / image
+                   'phiseg3d': 8.146e12 * (args.volume / 128.0) ** 3}                 # per 128^3 volume
     fwd_flops = conv_forward_flops_per_image(net, IMAGE[1]) if args.model == 'phiseg' else side_models[args.model]
     roofline = None      # filled after the evaluation block (the measurement overwrites the weights)
 
@@ -355,10 +367,12 @@ def main():
     # ---- roofline of the tensor-core conv kernels, in situ (differential graph replays)
     if args.model != 'phiseg':
         if rank == 0:
-            print(json.dumps({'metric': '%s LIDC-128^2 train images/s (side information)' % args.model, 'value': value,
+            what = ('PHISeg3D [32,64,128] L=3, 4x%d^3 volumes/s' % args.volume if args.model == 'phiseg3d'
+                    else '%s LIDC-128^2 train images/s' % args.model)
+            print(json.dumps({'metric': what + ' (side information)', 'value': value,
                               'unit': 'images/s', 'n_gpus': world, 'ms_per_step': ms_step, 'e2e': e2e,
-                              'gpu_launches': int(gpu_launches),
-                              'algorithmic_tflops': 3.0 * fwd_flops * BATCH * world / (ms_step / 1000.0) / 1e12}))
+                              'gpu_launches': int(gpu_launches), 'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30,
+                              'algorithmic_tflops': 3.0 * fwd_flops * batch_n * world / (ms_step / 1000.0) / 1e12}))
         sys.stdout.flush()
         if world > 1:
             torch.cuda.synchronize()

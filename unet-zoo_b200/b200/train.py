@@ -24,9 +24,9 @@ class TrainStep:
     def __init__(self, net, optimizer, batch, image_size=(1, 128, 128), use_graph=True, dp=None, device=None):
         self.net, self.opt, self.dp = net, optimizer, dp
         self.device = device or torch.device('cuda', torch.cuda.current_device())
-        c, h, w = image_size
-        self.patch = torch.zeros((batch, c, h, w), dtype=torch.float32, device=self.device)
-        self.mask = torch.zeros((batch, 1, h, w), dtype=torch.float32, device=self.device)
+        c, spatial = image_size[0], tuple(image_size[1:])          # (C,H,W) images or (C,D,H,W) volumes
+        self.patch = torch.zeros((batch, c) + spatial, dtype=torch.float32, device=self.device)
+        self.mask = torch.zeros((batch, 1) + spatial, dtype=torch.float32, device=self.device)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
         self.graph = None

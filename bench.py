@@ -251,7 +251,7 @@ def main():
     ap.add_argument('--skip-eval', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--volume', type=int, default=128, help='edge of the cubic volume for --model phiseg3d')
-    ap.add_argument('--model', default='phiseg', choices=['phiseg', 'revphiseg', 'probunet', 'unet', 'phiseg3d'],
+    ap.add_argument('--model', default='phiseg', choices=['phiseg', 'revphiseg', 'probunet', 'unet', 'phiseg3d', 'revphiseg3d'],
                     help='phiseg = the headline workload; the others are reported as side information')
     args = ap.parse_args()
 
@@ -272,10 +272,10 @@ def main():
 
     torch.manual_seed(1234 + rank)
     batch_n, image = BATCH, IMAGE
-    if args.model == 'phiseg3d':
+    if args.model in ('phiseg3d', 'revphiseg3d'):
         from tests.keygrammar import dropin_phiseg3d
         batch_n, image = 1, (4, args.volume, args.volume, args.volume)     # 4 x 128^3, B = 1 per GPU
-        net = dropin_phiseg3d([32, 64, 128], 3, image)
+        net = dropin_phiseg3d([32, 64, 128], 3, image, reversible=args.model == 'revphiseg3d')
     elif args.model == 'phiseg':
         net = dropin_phiseg(FILTERS)
     elif args.model == 'revphiseg':
@@ -291,7 +291,7 @@ def main():
     opt = train.make_adam(net, capturable=True)
     dp = dpmod.GradientAllReduce(net.parameters()) if world > 1 else None
     step = train.TrainStep(net, opt, batch_n, image, use_graph=not args.no_graph, dp=dp, device=device)
-    batches = synthetic_batches(4, seed=1000 * (rank + 1), volume=args.volume if args.model == 'phiseg3d' else None)
+    batches = synthetic_batches(4, seed=1000 * (rank + 1), volume=args.volume if args.model.endswith('3d') else None)
     step.patch.copy_(batches[0][0])
     step.mask.copy_(batches[0][1])
     step.prepare(warmup=3)
@@ -341,7 +341,8 @@ def main():
     peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (measured)' if peaks else 'fallback 1.4 PFLOP/s sustained'
     side_models = {'revphiseg': 18.318e9, 'probunet': 13.598e9, 'unet': 6.958e9,      # SURVEY.md 8d, forward GFLOP / image
-                   'phiseg3d': 8.146e12 * (args.volume / 128.0) ** 3}                 # per 128^3 volume
+                   'phiseg3d': 8.146e12 * (args.volume / 128.0) ** 3,                 # per 128^3 volume
+                   'revphiseg3d': 2.248e12 * (args.volume / 128.0) ** 3}
     fwd_flops = conv_forward_flops_per_image(net, IMAGE[1]) if args.model == 'phiseg' else side_models[args.model]
     roofline = None      # filled after the evaluation block (the measurement overwrites the weights)
 
@@ -367,7 +368,7 @@ def main():
     # ---- roofline of the tensor-core conv kernels, in situ (differential graph replays)
     if args.model != 'phiseg':
         if rank == 0:
-            what = ('PHISeg3D [32,64,128] L=3, 4x%d^3 volumes/s' % args.volume if args.model == 'phiseg3d'
+            what = ('%s [32,64,128] L=3, 4x%d^3 volumes/s' % (args.model, args.volume) if args.model.endswith('3d')
                     else '%s LIDC-128^2 train images/s' % args.model)
             print(json.dumps({'metric': what + ' (side information)', 'value': value,
                               'unit': 'images/s', 'n_gpus': world, 'ms_per_step': ms_step, 'e2e': e2e,

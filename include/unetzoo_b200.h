@@ -227,7 +227,7 @@ int uz_variance_ncc(const float* probs, const void* gt, int gt_dtype, int N, int
 
 /* nn.Conv3d 3x3x3 pad 1 / 1x1x1 forward (models/phiseg3D.py:24) with the same epilogue contract as uz_conv_fwd
  * (scale/shift/relu fold, or BatchNorm statistics accumulators); with dgrad-packed weights it is the input gradient.
- * taps = 27: w_packed [(kd*3 + kw)*3 + kh][Cout][Cin] as produced by uz_pack_conv_weight(taps = 27); Cout % 32 == 0.
+ * taps = 27: w_packed [(kd*3 + kw)*3 + kh][Cout][Cin] as produced by uz_pack_conv_weight(taps = 27).
  * Same persistent tcgen05 kernel as the 2-D path, the z taps are one more factor of the K loop; any D/H/W. */
 int uz_conv3d_fwd(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, int taps,
                   void* y, int ldy, const float* scale, const float* shift, int relu, float* stats_partial,

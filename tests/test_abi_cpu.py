@@ -67,5 +67,5 @@ def test_dropin_state_dict_and_parameter_count():
     from tests.keygrammar import dropin_phiseg3d
     vol = dropin_phiseg3d([32, 64, 128], 3, (4, 128, 128, 128))
     assert sum(p.numel() for p in vol.parameters()) == 9265121           # PHISeg3D [32,64,128], L = 3
-    with pytest.raises(NotImplementedError):
-        dropin_phiseg3d([32, 64, 128], 3, (4, 128, 128, 128), reversible=True)   # 16-channel halves: not on the B200 path yet
+    rev3 = dropin_phiseg3d([32, 64, 128], 3, (4, 128, 128, 128), reversible=True)
+    assert sum(p.numel() for p in rev3.parameters()) == 2455329         # reversible PHISeg3D (phiseg_brats.py:24)

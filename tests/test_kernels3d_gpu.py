@@ -43,6 +43,9 @@ CONV3D_SHAPES = [
     (1, 5, 12, 20, 96, 32),       # odd sizes, 3 x 32-channel K blocks
     (1, 4, 16, 16, 128, 128),
     (2, 4, 4, 4, 32, 32),
+    (1, 8, 16, 16, 16, 16),       # 16-channel halves of a reversible block: 16-column epilogue, 32-byte store boxes
+    (1, 4, 16, 32, 64, 48),       # odd multiple of 16 output channels
+    (1, 4, 16, 16, 16, 64),       # dgrad towards a padded 2-channel latent has Cout = 16 (here the forward direction)
 ]
 
 

@@ -47,6 +47,8 @@ CONV_SHAPES = [
     (2, 16, 16, 64, 256, 9),
     (2, 32, 32, 224, 128, 1),     # 1x1
     (2, 32, 32, 16, 16, 9),       # dgrad shape towards a padded 2-channel z
+    (2, 32, 32, 64, 48, 9),       # odd multiple of 16 output channels: 16-column epilogue of the persistent kernel
+    (1, 16, 16, 32, 16, 9),
 ]
 
 

@@ -23,7 +23,7 @@ def _rel(a, b):
 
 def _setup(golden_dir, reversible=False):
     g = np.load(os.path.join(golden_dir, 'phiseg3d_small.npz'))
-    filters = [64, 64, 128] if reversible else [int(v) for v in g['filters']]
+    filters = [int(v) for v in g['filters']]          # [32, 64, 64]: reversible halves of 16 channels at full resolution
     L, size, batch = int(g['latent_levels']), int(g['size']), int(g['batch'])
     net = dropin_phiseg3d(filters, L, (4, size, size, size), reversible=reversible)
     sd = synth.synth_state_dict(net.state_dict(), seed=int(g['wseed']))

@@ -45,9 +45,8 @@ def pad16(c):
 
 
 def pad_channels(c, weight_dim=4):
-    """stored channel count: multiples of 16; volumes (5-D weights) use multiples of 32, the granularity the 3x3x3
-    kernel needs for its output channels (a 2-channel latent is stored as 32 channels so its dgrad has a plan)"""
-    return (c + 31) // 32 * 32 if weight_dim == 5 else pad16(c)
+    """stored channel count of an activation / packed weight: the next multiple of 16 (images and volumes alike)"""
+    return pad16(c)
 
 
 def new_act(n, h, w, c, device):

@@ -116,7 +116,6 @@ def to_act(x):
         return x
     if not x.is_cuda:
         raise kern._lib.UnetZooLibError('UNet-Zoo B200 modules need CUDA tensors: there is no CPU fallback path')
-    # volumes store channels in multiples of 32 (kern.pad_channels)
     return Act(ToNHWC.apply(x.float(), kern.pad_channels(x.shape[1], x.dim())), x.shape[1])
 
 

@@ -349,7 +349,7 @@ extern "C" int uz_conv3d_fwd(const void* x, int N, int D, int H, int W, int Cin,
   }
   UZ_CHECK_ARG(x && w_packed && y, "uz_conv3d_fwd: null pointer");
   UZ_CHECK_ARG(Cin % 16 == 0 && Cin > 0, "uz_conv3d_fwd: Cin must be a positive multiple of 16 (got %d)", Cin);
-  UZ_CHECK_ARG(Cout % 32 == 0 && Cout > 0, "uz_conv3d_fwd: Cout must be a positive multiple of 32 (got %d)", Cout);
+  UZ_CHECK_ARG(Cout % 16 == 0 && Cout > 0, "uz_conv3d_fwd: Cout must be a positive multiple of 16 (got %d)", Cout);
   UZ_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= Cin && ldy >= Cout, "uz_conv3d_fwd: bad pixel strides");
   UZ_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,

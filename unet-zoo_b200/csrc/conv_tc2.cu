@@ -40,7 +40,7 @@ struct Conv2Params {
   int stages, nbuf;              // smem pipeline depth, TMEM accumulator buffers (1 or 2)
   int relu;
   uint32_t tmem_cols;
-  uint32_t stage_bytes, a_bytes, out_off;   // smem carve-up
+  uint32_t stage_bytes, a_bytes, b_bytes, out_off;   // smem carve-up (stage_bytes >= a_bytes + b_bytes, 1024-aligned)
   const float* scale;
   const float* shift;
   float* stats;                  // [2][Cout] accumulators (zero on entry) or nullptr
@@ -86,6 +86,76 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
     }
   }
   return v[0];
+}
+
+// 16-column variant: afterwards lanes l and l + 16 hold the total of column l
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// Epilogue of NW (32 or 16) accumulator columns of one row: TMEM -> registers -> scale/shift(/ReLU) -> bf16 -> swizzled
+// staging row; optional BatchNorm statistics of the stored values into this warp's shared accumulators.
+template <int NW>
+__device__ __forceinline__ void epilogue_columns(const Conv2Params& p, uint32_t taddr, int c, int row, int lane,
+                                                 uint32_t xr, uint32_t box_bytes, uint32_t cwb, uint8_t* smem_out,
+                                                 const float* s_scale, const float* s_shift, float* st_sum,
+                                                 float* st_sq, bool in_image) {
+  uint32_t r[NW];
+  if constexpr (NW == 32) tmem_ld32(taddr, r); else uz::tmem_ld16(taddr, r);
+  uz::tmem_ld_wait();
+  float v[NW];
+  uint32_t pk[NW / 2];
+#pragma unroll
+  for (int j = 0; j < NW / 2; ++j) {
+    const int ch = c + 2 * j;
+    float a = fmaf(__uint_as_float(r[2 * j]), s_scale[ch], s_shift[ch]);
+    float b = fmaf(__uint_as_float(r[2 * j + 1]), s_scale[ch + 1], s_shift[ch + 1]);
+    if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    pk[j] = uz::pack_bf16x2(a, b);
+    v[2 * j] = in_image ? uz::bf16lo(pk[j]) : 0.f;          // statistics of the values as stored
+    v[2 * j + 1] = in_image ? uz::bf16hi(pk[j]) : 0.f;
+  }
+  // staging: box (c / CW), this thread's row, 16-byte chunks swizzled
+  {
+    const int cb = c / p.CW;
+    const int j0 = (c % p.CW) / 8;
+    uint8_t* rowp = smem_out + cb * box_bytes + row * cwb;
+#pragma unroll
+    for (int j = 0; j < NW / 8; ++j) {
+      const uint32_t chunk = static_cast<uint32_t>(j0 + j) ^ xr;
+      *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+  }
+  if (p.stats) {
+    float sq[NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) sq[j] = v[j] * v[j];
+    if constexpr (NW == 32) {
+      const float s = transpose_reduce32(v, lane);
+      const float s2 = transpose_reduce32(sq, lane);
+      st_sum[c + lane] += s;
+      st_sq[c + lane] += s2;
+    } else {
+      const float s = transpose_reduce16(v, lane);
+      const float s2 = transpose_reduce16(sq, lane);
+      if (lane < 16) {
+        st_sum[c + lane] += s;
+        st_sq[c + lane] += s2;
+      }
+    }
+  }
 }
 
 template <int KC>
@@ -164,8 +234,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           uz::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * p.stage_bytes;
           if (uz::elect_one()) {
-            uz::mbar_expect_tx(&full_bar[stage],
-                               ((p.dbg & 4) ? 0 : p.a_bytes) + ((p.dbg & 8) ? 0 : p.stage_bytes - p.a_bytes));
+            uz::mbar_expect_tx(&full_bar[stage], ((p.dbg & 4) ? 0 : p.a_bytes) + ((p.dbg & 8) ? 0 : p.b_bytes));
             if (!(p.dbg & 4))
               uz::tma_load_5d(sa, &tmap_x, &full_bar[stage], kb * KC, x0 + dx - 1, y0 - 1, z0 + dz - z_off, n);
             if (!(p.dbg & 8)) tma_load_3d_box(sa + p.a_bytes, &tmap_w, &full_bar[stage], kb * KC, c_out0, r * 3);
@@ -252,43 +321,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const bool in_image = !p.mask || ((x0 + (row & 15) < p.W) && (y0 + 8 * half + (row >> 4) < p.H));
         if (!(p.dbg & 1)) {
-          for (int c = 0; c < p.BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 2 * p.BN + half * p.BN + c, r);
-            uz::tmem_ld_wait();
-            float v[32];
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int ch = c + 2 * j;
-              float a = fmaf(__uint_as_float(r[2 * j]), s_scale[ch], s_shift[ch]);
-              float b = fmaf(__uint_as_float(r[2 * j + 1]), s_scale[ch + 1], s_shift[ch + 1]);
-              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              pk[j] = uz::pack_bf16x2(a, b);
-              v[2 * j] = in_image ? uz::bf16lo(pk[j]) : 0.f;          // statistics of the values as stored
-              v[2 * j + 1] = in_image ? uz::bf16hi(pk[j]) : 0.f;
-            }
-            // staging: box (c / CW), this thread's row, 16-byte chunks swizzled
-            {
-              const int cb = c / p.CW;
-              const int j0 = (c % p.CW) / 8;
-              uint8_t* rowp = smem_out + cb * box_bytes + row * cwb;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t chunk = static_cast<uint32_t>(j0 + j) ^ xr;
-                *reinterpret_cast<uint4*>(rowp + chunk * 16) =
-                    make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-              }
-            }
-            if (p.stats) {
-              float sq[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-              const float s = transpose_reduce32(v, lane);
-              const float s2 = transpose_reduce32(sq, lane);
-              s_stats[ew][0][c + lane] += s;
-              s_stats[ew][1][c + lane] += s2;
-            }
+          const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 2 * p.BN + half * p.BN;
+          if (p.BN % 32 == 0) {
+            for (int c = 0; c < p.BN; c += 32)
+              epilogue_columns<32>(p, tbase + c, c, row, lane, xr, box_bytes, cwb, smem_out, s_scale, s_shift,
+                                   s_stats[ew][0], s_stats[ew][1], in_image);
+          } else {                     // output widths that are odd multiples of 16 (16-channel store boxes)
+            for (int c = 0; c < p.BN; c += 16)
+              epilogue_columns<16>(p, tbase + c, c, row, lane, xr, box_bytes, cwb, smem_out, s_scale, s_shift,
+                                   s_stats[ew][0], s_stats[ew][1], in_image);
           }
         }
         // generic-proxy writes -> visible to the TMA (async proxy), then one thread issues the stores
@@ -333,7 +374,7 @@ struct Plan2 {
 // D == 0: 2-D map (3x3 taps, H and W must be multiples of the tile); D >= 1: volume (3x3x3 taps, any H, W)
 bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
   const bool vol = D > 0;
-  if (Cin % 16 || Cout % 32 || Cout > 4096) return false;
+  if (Cin % 16 || Cout % 16 || Cout > 4096) return false;
   if (!vol && (H % kTile || W % kTile)) return false;
   Conv2Params& p = out->p;
   p = Conv2Params{};
@@ -350,11 +391,11 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
     bn /= 2;
   }
   while (p.tiles * (Cout / bn) < sms && bn % 64 == 0 && bn >= 128) bn /= 2;
-  if (bn % 32) return false;
+  if (bn % 16) return false;
   p.BN = bn;
   p.n_chunks = Cout / bn;
   p.items = p.tiles * p.n_chunks;
-  p.CW = (bn % 64 == 0) ? 64 : 32;
+  p.CW = (bn % 64 == 0) ? 64 : ((bn % 32 == 0) ? 32 : 16);
   p.nbuf = (4 * bn <= 512) ? 2 : 1;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(p.nbuf * 2 * bn)) cols *= 2;
@@ -364,7 +405,7 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
   int best_kc = 0, best_stages = 0;
   for (int kc : {64, 32, 16}) {
     if (Cin % kc) continue;
-    const size_t stage = static_cast<size_t>(kSlabRows + 3 * bn) * kc * 2;
+    const size_t stage = (static_cast<size_t>(kSlabRows + 3 * bn) * kc * 2 + 1023) / 1024 * 1024;
     int stages = static_cast<int>((budget - out_bytes) / stage);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages >= 2) { best_kc = kc; best_stages = stages; break; }
@@ -373,9 +414,10 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
   p.KC = best_kc;
   p.stages = best_stages;
   p.a_bytes = kSlabRows * best_kc * 2;
-  p.stage_bytes = (kSlabRows + 3 * bn) * best_kc * 2;
-  // stage sizes are multiples of 1024 B? slab: 288 rows * rowb (rowb >= 32) = 9216.. ok; weights 3*bn*rowb, bn % 32 == 0
-  if (p.a_bytes % 1024 || p.stage_bytes % 1024) return false;
+  p.b_bytes = 3 * bn * best_kc * 2;
+  p.stage_bytes = (p.a_bytes + p.b_bytes + 1023) / 1024 * 1024;
+  // slab: 288 rows * rowb (rowb >= 32) is a multiple of 1024; the weight taps start bn rows apart = whole swizzle atoms
+  if (p.a_bytes % 1024) return false;
   p.out_off = p.stages * p.stage_bytes;
   out->smem = p.out_off + out_bytes + 1024;
   int slots = sms / p.n_chunks;

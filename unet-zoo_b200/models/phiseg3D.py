@@ -13,9 +13,9 @@ fixed specification, the one the oracle's patched reference (oracle/ref_run.py: 
         (the reference hard-codes nlabels=2 at :253 while reserving num_classes channels at :221);
   (i)   the filter list must satisfy the reference's own channel arithmetic (num_filters[latent_levels-1] ==
         num_filters[-1]); nothing is changed here, inconsistent lists fail like in the reference.
-Channel counts of the B200 path: every 3x3x3 layer needs an output width that is a multiple of 32 (the reference's
-BraTS widths 32/64/128 are).  Reversible blocks (depth 1 everywhere, :103,131,165,339,352) therefore need widths that
-are multiples of 64.
+Channel counts of the B200 path: every conv layer needs an output width that is a multiple of 16 (the reference's
+BraTS widths 32/64/128 are); reversible blocks (depth 1 everywhere, :103,131,165,339,352) split it into two halves, so
+they need multiples of 32.
 """
 import torch
 import torch.nn as nn
@@ -31,7 +31,7 @@ class Conv3D(torchlayers.Conv2D):
     """nn.Conv3d(k in {3 (pad 1), 1}) + bias -> BatchNorm3d(eps 1e-3, momentum 0.01) -> ReLU (models/phiseg3D.py:13-35)"""
     _conv_cls = nn.Conv3d
     _norm_cls = nn.BatchNorm3d
-    _granule = 32
+    _granule = 16
 
 
 class Conv3DSequence(nn.Module):
@@ -361,7 +361,7 @@ class PHISeg3D(PHISeg):
         self.s_out_list_with_softmax = [None] * self.latent_levels
 
     def _packer(self):
-        convs = [m for m in self.modules() if isinstance(m, nn.Conv3d) and m.out_channels % 32 == 0 and m.weight.is_cuda]
+        convs = [m for m in self.modules() if isinstance(m, nn.Conv3d) and m.out_channels % 16 == 0 and m.weight.is_cuda]
         pk = getattr(self, '_weight_packer', None)
         if pk is None or not pk.valid_for(convs[0].weight):
             pk = kern.WeightPacker([m.weight for m in convs])

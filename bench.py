@@ -250,6 +250,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='time eager steps instead of CUDA-graph replay')
     ap.add_argument('--skip-eval', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--debug-flags', type=int, default=0, help='uz_set_debug_flags for A/B measurements')
     ap.add_argument('--volume', type=int, default=128, help='edge of the cubic volume for --model phiseg3d')
     ap.add_argument('--model', default='phiseg', choices=['phiseg', 'revphiseg', 'probunet', 'unet', 'phiseg3d', 'revphiseg3d'],
                     help='phiseg = the headline workload; the others are reported as side information')
@@ -270,6 +271,8 @@ def main():
     from tests.keygrammar import dropin_phiseg
     from oracle import synth
 
+    if args.debug_flags:
+        _lib.call('uz_set_debug_flags', args.debug_flags)
     torch.manual_seed(1234 + rank)
     batch_n, image = BATCH, IMAGE
     if args.model in ('phiseg3d', 'revphiseg3d'):

@@ -376,6 +376,7 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
   const bool vol = D > 0;
   if (Cin % 16 || Cout % 16 || Cout > 4096) return false;
   if (!vol && (H % kTile || W % kTile)) return false;
+  if (!vol && (uz::g_conv_debug_flags & 512) && Cout % 32) return false;   // measurement knob: 16-wide outputs -> generic
   Conv2Params& p = out->p;
   p = Conv2Params{};
   p.N = N; p.D = vol ? D : 1; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;

@@ -64,13 +64,14 @@ __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
   return v[0];
 }
 
+template <int KC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x A][stages x B] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t swz = p.KC * 2;                    // swizzle span in bytes = one smem row
+  constexpr uint32_t swz = KC * 2;                  // swizzle span in bytes = one smem row
   const uint32_t a_bytes = kBlockM * swz;
   const uint32_t b_bytes = p.BN * swz;
   uint8_t* smem_a = smem;
@@ -95,7 +96,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
   const int c_out0 = n_chunk * p.BN;
 
-  const int kblocks = p.Cin / p.KC;
+  const int kblocks = p.Cin / KC;
   const int k_iters = p.taps * kblocks;
 
   if (warp == 0 && lane == 0) {
@@ -136,27 +137,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         if (p.taps == 9) { dx = tap / 3 - 1; dy = tap % 3 - 1; }   // packed taps are dx-major (see uz_pack_conv_weight)
         if (uz::elect_one()) {
           uz::mbar_expect_tx(&full_bar[s], ((p.dbg & 4) ? 0 : a_bytes) + ((p.dbg & 8) ? 0 : b_bytes));
-          if (!(p.dbg & 4)) uz::tma_load_4d(smem_a + s * a_bytes, &tmap_x, &full_bar[s], kb * p.KC, x0 + dx, y0 + dy, n0);
-          if (!(p.dbg & 8)) uz::tma_load_3d(smem_b + s * b_bytes, &tmap_w, &full_bar[s], kb * p.KC, c_out0, tap);
+          if (!(p.dbg & 4)) uz::tma_load_4d(smem_a + s * a_bytes, &tmap_x, &full_bar[s], kb * KC, x0 + dx, y0 + dy, n0);
+          if (!(p.dbg & 8)) uz::tma_load_3d(smem_b + s * b_bytes, &tmap_w, &full_bar[s], kb * KC, c_out0, tap);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Descriptor high words are loop invariant; the KC/16 MMAs of a K step are unrolled with compile-time offsets so every
+    // MMA gets its own uniform registers (a runtime loop made ptxas serialise issue behind a waterfall, ~180 cycles/MMA).
     const uint32_t idesc = uz::umma_idesc_bf16(kBlockM, p.BN, 0, 0);
-    const uint32_t sbo = 8 * swz;
+    constexpr uint32_t sbo = 8 * swz;
+    const uint64_t desc_hi = uz::umma_desc(0, 16, sbo, swz) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = static_cast<uint32_t>(uz::umma_desc(0, 16, sbo, swz) & 0xFFFFFFFFull);
     for (int it = 0; it < k_iters; ++it) {
       const int s = it % p.stages;
       uz::mbar_wait(&full_bar[s], (it / p.stages) & 1);
       uz::tc_fence_after();
-      const uint32_t a_addr = uz::smem_u32(smem_a + s * a_bytes);
-      const uint32_t b_addr = uz::smem_u32(smem_b + s * b_bytes);
+      const uint32_t a_lo = desc_lo0 + (uz::smem_u32(smem_a + s * a_bytes) >> 4);
+      const uint32_t b_lo = desc_lo0 + (uz::smem_u32(smem_b + s * b_bytes) >> 4);
       if (uz::elect_one()) {
-        for (int k = 0; k < ((p.dbg & 2) ? 0 : p.KC / 16); ++k) {
-          const uint64_t adesc = uz::umma_desc(a_addr + k * 32, 16, sbo, swz);
-          const uint64_t bdesc = uz::umma_desc(b_addr + k * 32, 16, sbo, swz);
-          uz::tc_mma_f16(tmem_base, adesc, bdesc, idesc, (it | k) != 0);
+        if (!(p.dbg & 2)) {
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k)
+            uz::tc_mma_f16(tmem_base, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
+                           k == 0 ? static_cast<uint32_t>(it != 0) : 1u);
         }
         uz::tc_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
         if (it == k_iters - 1) uz::tc_commit(&accum_bar);
@@ -269,6 +275,7 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
                               stream, &handled);
     if (rc || handled) return rc;
   }
+  if (uz::g_conv_debug_flags & 2048) return UZ_OK;  // measurement knob: step time without the generic-kernel launches
   ConvParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
   int tiles = 0;
@@ -321,9 +328,11 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
     int rc = uz::make_tmap_bf16(&tw, w_packed, 3, dims, strides, box, swz);
     if (rc) return rc;
   }
-  static size_t attr_bytes = 0;
+  auto kernel = p.KC == 64 ? conv_tc_kernel<64> : (p.KC == 32 ? conv_tc_kernel<32> : conv_tc_kernel<16>);
+  static size_t attr_bytes_kc[3] = {0, 0, 0};
+  size_t& attr_bytes = attr_bytes_kc[p.KC == 64 ? 0 : (p.KC == 32 ? 1 : 2)];
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       uz::set_error("uz_conv_fwd: cannot raise dynamic smem limit to %zu: %s", static_cast<size_t>(smem), cudaGetErrorString(e));
@@ -332,7 +341,7 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
     attr_bytes = smem;
   }
   dim3 grid(tiles, splits, 1);
-  uz::launch(conv_tc_kernel, grid, kThreads, smem, static_cast<cudaStream_t>(stream), tx, tw, p);
+  uz::launch(kernel, grid, kThreads, smem, static_cast<cudaStream_t>(stream), tx, tw, p);
   UZ_CHECK_LAUNCH("uz_conv_fwd");
   return UZ_OK;
 }

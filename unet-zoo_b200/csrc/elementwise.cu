@@ -283,6 +283,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+#pragma unroll 4
     for (size_t pix = static_cast<size_t>(blockIdx.x) * rows + r; pix < npix;
          pix += static_cast<size_t>(gridDim.x) * rows) {
       float g[8], yy[8];
@@ -873,8 +874,7 @@ extern "C" int uz_bn_bwd_reduce_sums(const void* dout, int ldd, const void* y, i
   int threads = 256;
   if (chunks > threads) threads = ((chunks + 31) / 32) * 32;
   const int rows = threads / chunks;
-  int blocks = uz_bn_bwd_num_blocks(npix, C);
-  if (blocks > uz::num_sms()) blocks = uz::num_sms();      // one atomic per block per channel
+  const int blocks = uz_bn_bwd_num_blocks(npix, C);          // <= 4 per SM; one atomic per block per channel
   const size_t smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);
   uz::launch(bn_bwd_reduce_kernel, blocks, threads, smem, ST(stream), static_cast<const __nv_bfloat16*>(dout), ldd,
                                                              static_cast<const __nv_bfloat16*>(y), ldy, scale, shift,

@@ -183,118 +183,189 @@ __global__ void kl_bwd_kernel(const float* __restrict__ mu0, const float* __rest
 }
 
 // ---------------------------------------------------------------- s_layer: 1x1 conv to logits + nearest upsample
-// one warp per LOW-res pixel; writes the f x f replicated block of the full-res fp32 NCHW output.
-__global__ void slayer_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ w,
-                                  const float* __restrict__ bias, int ncls, int B, int d, int h, int wd, int f, int fz,
-                                  float* out) {
-  // d = low-res depth (1 for 2-D maps), fz = replication along z (1 for 2-D, f for volumes)
+// A block owns one LOW-res image row (b, zl, yl) at a time (grid-stride over rows).  The logits of the row's pixels are
+// computed by G lanes per pixel (16-byte feature loads, shuffle reduction), parked in shared memory and then written
+// as the f x f (x fz) replicated block of the full-resolution fp32 NC(D)HW output with consecutive threads on
+// consecutive x => coalesced stores.  d = low-res depth (1 for 2-D maps), fz = replication along z (1 for 2-D).
+constexpr int kSlThreads = 256;
+
+__device__ __forceinline__ int slayer_lanes_per_pixel(int pb, int C) {
+  int g = 1;
+  while (g * 2 <= kSlThreads / pb && g * 2 <= C / 8 && g * 2 <= 32) g *= 2;
+  return g;
+}
+
+__global__ void __launch_bounds__(kSlThreads)
+slayer_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ w,
+                  const float* __restrict__ bias, int ncls, int rows, int d, int h, int wd, int f, int fz, float* out) {
   uz::pdl_prologue();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int npix = B * d * h * wd;
-  if (warp >= npix) return;
-  float acc[kMaxOut];
-#pragma unroll
-  for (int k = 0; k < kMaxOut; ++k) acc[k] = 0.f;
-  const __nv_bfloat16* fp = feat + static_cast<size_t>(warp) * ld;
-  for (int c = lane * 2; c < C; c += 64) {
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(fp + c);
-    const float f0 = uz::bf16lo(v), f1 = uz::bf16hi(v);
-#pragma unroll
-    for (int k = 0; k < kMaxOut; ++k)
-      if (k < ncls) acc[k] = fmaf(f0, w[k * C + c], fmaf(f1, w[k * C + c + 1], acc[k]));
-  }
-#pragma unroll
-  for (int k = 0; k < kMaxOut; ++k)
-    if (k < ncls) acc[k] = uz::warp_sum(acc[k]) + bias[k];
-  const int bz = warp / (h * wd);
-  const int b = bz / d, zl = bz - b * d;
-  const int r = warp - bz * h * wd;
-  const int yl = r / wd, xl = r - yl * wd;
+  extern __shared__ float sm[];            // w_s [ncls][C] | lg [PB][ncls]
+  float* w_s = sm;
+  float* lg = sm + ncls * C;
+  for (int i = threadIdx.x; i < ncls * C; i += kSlThreads) w_s[i] = w[i];
+  int pb = 1;
+  while (pb * 2 <= wd && pb * 2 <= kSlThreads) pb *= 2;
+  if (pb > wd) pb = wd;
+  const int G = slayer_lanes_per_pixel(pb, C);
+  const int chunks = C / 8;
   const int H = h * f, W = wd * f;
   const size_t HW = static_cast<size_t>(H) * W;
-  for (int k = 0; k < ncls; ++k) {
-    float* o = out + ((static_cast<size_t>(b) * ncls + k) * (d * fz) + zl * fz) * HW + static_cast<size_t>(yl * f) * W + xl * f;
-    for (int i = lane; i < fz * f * f; i += 32) {
-      const int iz = i / (f * f), ir = i - iz * f * f;
-      o[iz * HW + (ir / f) * W + (ir % f)] = acc[k];
+  __syncthreads();
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int yl = row % h;
+    const int bz = row / h;
+    const int b = bz / d, zl = bz - b * d;
+    for (int p0 = 0; p0 < wd; p0 += pb) {
+      const int pbc = min(pb, wd - p0);
+      {
+        const int pl = threadIdx.x / G, g = threadIdx.x % G;
+        float acc[kMaxOut];
+#pragma unroll
+        for (int k = 0; k < kMaxOut; ++k) acc[k] = 0.f;
+        if (pl < pbc) {
+          const __nv_bfloat16* fp = feat + (static_cast<size_t>(row) * wd + p0 + pl) * ld;
+          for (int c8 = g; c8 < chunks; c8 += G) {
+            const uint4 v = *reinterpret_cast<const uint4*>(fp + c8 * 8);
+            const float x[8] = {uz::bf16lo(v.x), uz::bf16hi(v.x), uz::bf16lo(v.y), uz::bf16hi(v.y),
+                                uz::bf16lo(v.z), uz::bf16hi(v.z), uz::bf16lo(v.w), uz::bf16hi(v.w)};
+#pragma unroll
+            for (int k = 0; k < kMaxOut; ++k) {
+              if (k < ncls) {
+                const float* wk = w_s + k * C + c8 * 8;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc[k] = fmaf(x[jj], wk[jj], acc[k]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxOut; ++k) {
+          if (k < ncls) {
+            for (int o = G >> 1; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            if (g == 0 && pl < pbc) lg[pl * ncls + k] = acc[k] + bias[k];
+          }
+        }
+      }
+      __syncthreads();
+      const int per_k = fz * f * pbc * f;
+      for (int idx = threadIdx.x; idx < ncls * per_k; idx += kSlThreads) {
+        const int k = idx / per_k;
+        int r = idx - k * per_k;
+        const int ix = r % f; r /= f;
+        const int pl = r % pbc; r /= pbc;
+        const int iy = r % f;
+        const int iz = r / f;
+        out[((static_cast<size_t>(b) * ncls + k) * (d * fz) + zl * fz + iz) * HW + static_cast<size_t>(yl * f + iy) * W +
+            (p0 + pl) * f + ix] = lg[pl * ncls + k];
+      }
+      __syncthreads();
     }
   }
 }
 
-// backward: ds_low = sum over the f x f block of ds_full; dfeat = W^T ds_low; partial dW, db per block.
-__global__ void slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ feat, int ld, int C,
-                                  const float* __restrict__ w, int ncls, int B, int d, int h, int wd, int f, int fz,
-                                  __nv_bfloat16* dfeat, int ldd, float* wpartial /*[blocks][ncls][C]*/,
-                                  float* bpartial /*[blocks][ncls]*/) {
+// backward: g[p][k] = sum over the replicated block of dout; dfeat = W^T g; per-block partial dW = g^T feat, db = sum g.
+__global__ void __launch_bounds__(kSlThreads)
+slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ feat, int ld, int C,
+                  const float* __restrict__ w, int ncls, int rows, int d, int h, int wd, int f, int fz,
+                  __nv_bfloat16* dfeat, int ldd, float* wpartial /*[blocks][ncls][C]*/,
+                  float* bpartial /*[blocks][ncls]*/) {
   uz::pdl_prologue();
-  extern __shared__ float sm[];  // [warps][ncls][C]
-  const int warps = blockDim.x >> 5;
-  const int wid = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  float* acc = sm + static_cast<size_t>(wid) * ncls * C;
-  for (int i = lane; i < ncls * C; i += 32) acc[i] = 0.f;
-  float bacc[kMaxOut];
+  extern __shared__ float sm[];            // w_s [ncls][C] | dw_s [ncls][C] | g_s [PB][ncls] | db_s [ncls]
+  float* w_s = sm;
+  float* dw_s = sm + ncls * C;
+  float* g_s = dw_s + ncls * C;
+  int pb = 1;
+  while (pb * 2 <= wd && pb * 2 <= kSlThreads) pb *= 2;
+  if (pb > wd) pb = wd;
+  float* db_s = g_s + pb * ncls;
+  for (int i = threadIdx.x; i < ncls * C; i += kSlThreads) {
+    w_s[i] = w[i];
+    dw_s[i] = 0.f;
+  }
+  if (threadIdx.x < ncls) db_s[threadIdx.x] = 0.f;
+  const int chunks = C / 8;
+  const int pstride = kSlThreads / chunks;           // pixels processed per pass in phase 2
+  const int c8 = threadIdx.x % chunks, pslot = threadIdx.x / chunks;
+  const bool p2_active = pslot < pstride;
+  constexpr int kRegCls = 4;                          // classes whose dW contribution accumulates in registers
+  float dwr[kRegCls][8];
 #pragma unroll
-  for (int k = 0; k < kMaxOut; ++k) bacc[k] = 0.f;
-  __syncwarp();
-  const int npix = B * d * h * wd;
+  for (int k = 0; k < kRegCls; ++k)
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) dwr[k][jj] = 0.f;
   const int H = h * f, W = wd * f;
   const size_t HW = static_cast<size_t>(H) * W;
-  for (int pix = blockIdx.x * warps + wid; pix < npix; pix += gridDim.x * warps) {
-    const int bz = pix / (h * wd);
+  __syncthreads();
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int yl = row % h;
+    const int bz = row / h;
     const int b = bz / d, zl = bz - b * d;
-    const int r = pix - bz * h * wd;
-    const int yl = r / wd, xl = r - yl * wd;
-    float g[kMaxOut];
-#pragma unroll
-    for (int k = 0; k < kMaxOut; ++k) {
-      g[k] = 0.f;
-      if (k < ncls) {
-        const float* o = dout + ((static_cast<size_t>(b) * ncls + k) * (d * fz) + zl * fz) * HW +
-                         static_cast<size_t>(yl * f) * W + xl * f;
+    for (int p0 = 0; p0 < wd; p0 += pb) {
+      const int pbc = min(pb, wd - p0);
+      for (int i = threadIdx.x; i < pbc * ncls; i += kSlThreads) g_s[i] = 0.f;
+      __syncthreads();
+      const int per_k = fz * f * pbc * f;
+      for (int idx = threadIdx.x; idx < ncls * per_k; idx += kSlThreads) {
+        const int k = idx / per_k;
+        int r = idx - k * per_k;
+        const int ix = r % f; r /= f;
+        const int pl = r % pbc; r /= pbc;
+        const int iy = r % f;
+        const int iz = r / f;
+        const float v = dout[((static_cast<size_t>(b) * ncls + k) * (d * fz) + zl * fz + iz) * HW +
+                             static_cast<size_t>(yl * f + iy) * W + (p0 + pl) * f + ix];
+        if (f == 1 && fz == 1) g_s[pl * ncls + k] = v; else atomicAdd(&g_s[pl * ncls + k], v);
+      }
+      __syncthreads();
+      if (threadIdx.x < ncls) {
         float t = 0.f;
-        for (int i = lane; i < fz * f * f; i += 32) {
-          const int iz = i / (f * f), ir = i - iz * f * f;
-          t += o[iz * HW + (ir / f) * W + (ir % f)];
-        }
-        g[k] = uz::warp_sum(t);
-        bacc[k] += g[k];
+        for (int pl = 0; pl < pbc; ++pl) t += g_s[pl * ncls + threadIdx.x];
+        db_s[threadIdx.x] += t;
       }
-    }
-    const __nv_bfloat16* fp = feat + static_cast<size_t>(pix) * ld;
-    __nv_bfloat16* df = dfeat + static_cast<size_t>(pix) * ldd;
-    for (int c = lane * 2; c < C; c += 64) {
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(fp + c);
-      const float f0 = uz::bf16lo(v), f1 = uz::bf16hi(v);
-      float d0 = 0.f, d1 = 0.f;
+      if (p2_active) {
+        for (int pl = pslot; pl < pbc; pl += pstride) {
+          const size_t pix = static_cast<size_t>(row) * wd + p0 + pl;
+          const uint4 v = *reinterpret_cast<const uint4*>(feat + pix * ld + c8 * 8);
+          const float x[8] = {uz::bf16lo(v.x), uz::bf16hi(v.x), uz::bf16lo(v.y), uz::bf16hi(v.y),
+                              uz::bf16lo(v.z), uz::bf16hi(v.z), uz::bf16lo(v.w), uz::bf16hi(v.w)};
+          float dd[8];
 #pragma unroll
-      for (int k = 0; k < kMaxOut; ++k) {
-        if (k < ncls) {
-          d0 = fmaf(g[k], w[k * C + c], d0);
-          d1 = fmaf(g[k], w[k * C + c + 1], d1);
-          acc[k * C + c] = fmaf(g[k], f0, acc[k * C + c]);
-          acc[k * C + c + 1] = fmaf(g[k], f1, acc[k * C + c + 1]);
+          for (int jj = 0; jj < 8; ++jj) dd[jj] = 0.f;
+#pragma unroll
+          for (int k = 0; k < kMaxOut; ++k) {
+            if (k < ncls) {
+              const float g = g_s[pl * ncls + k];
+              const float* wk = w_s + k * C + c8 * 8;
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) dd[jj] = fmaf(g, wk[jj], dd[jj]);
+              if (k < kRegCls) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) dwr[k][jj] = fmaf(g, x[jj], dwr[k][jj]);
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) atomicAdd(&dw_s[k * C + c8 * 8 + jj], g * x[jj]);
+              }
+            }
+          }
+          *reinterpret_cast<uint4*>(dfeat + pix * ldd + c8 * 8) =
+              make_uint4(uz::pack_bf16x2(dd[0], dd[1]), uz::pack_bf16x2(dd[2], dd[3]), uz::pack_bf16x2(dd[4], dd[5]),
+                         uz::pack_bf16x2(dd[6], dd[7]));
         }
       }
-      *reinterpret_cast<uint32_t*>(df + c) = uz::pack_bf16x2(d0, d1);
+      __syncthreads();
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < ncls * C; i += blockDim.x) {
-    float t = 0.f;
-    for (int ww = 0; ww < warps; ++ww) t += sm[static_cast<size_t>(ww) * ncls * C + i];
-    wpartial[static_cast<size_t>(blockIdx.x) * ncls * C + i] = t;
+  if (p2_active) {
+#pragma unroll
+    for (int k = 0; k < kRegCls; ++k)
+      if (k < ncls)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) atomicAdd(&dw_s[k * C + c8 * 8 + jj], dwr[k][jj]);
   }
-  __shared__ float bsm[32][kMaxOut];
-  if (lane == 0)
-    for (int k = 0; k < ncls; ++k) bsm[wid][k] = bacc[k];
   __syncthreads();
-  if (threadIdx.x < ncls) {
-    float t = 0.f;
-    for (int ww = 0; ww < warps; ++ww) t += bsm[ww][threadIdx.x];
-    bpartial[blockIdx.x * ncls + threadIdx.x] = t;
-  }
+  for (int i = threadIdx.x; i < ncls * C; i += kSlThreads)
+    wpartial[static_cast<size_t>(blockIdx.x) * ncls * C + i] = dw_s[i];
+  if (threadIdx.x < ncls) bpartial[blockIdx.x * ncls + threadIdx.x] = db_s[threadIdx.x];
 }
 
 // ---------------------------------------------------------------- residual multinoulli loss (forward + gradients)
@@ -479,15 +550,24 @@ extern "C" int uz_kl_bwd(const float* mu0, const float* s0, const float* mu1, co
 }
 
 namespace {
+int slayer_pb(int wd) {
+  int pb = 1;
+  while (pb * 2 <= wd && pb * 2 <= kSlThreads) pb *= 2;
+  return pb > wd ? wd : pb;
+}
+
 int slayer_fwd_impl(const void* feat, int ld, int C, const float* w, const float* bias, int ncls, int B, int d, int h,
                     int wd, int factor, int fz, float* out, void* stream) {
   UZ_CHECK_ARG(feat && w && bias && out, "uz_slayer_fwd: null pointer");
   UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxOut, "uz_slayer_fwd: %d outputs unsupported (max %d)", ncls, kMaxOut);
-  UZ_CHECK_ARG(C % 2 == 0 && ld % 2 == 0 && factor >= 1 && d >= 1, "uz_slayer_fwd: bad C/ld/factor");
-  const long long npix = static_cast<long long>(B) * d * h * wd;
-  const int threads = 256;
-  uz::launch(slayer_fwd_kernel, static_cast<unsigned>((npix * 32 + threads - 1) / threads), threads, 0, ST(stream),
-      static_cast<const __nv_bfloat16*>(feat), ld, C, w, bias, ncls, B, d, h, wd, factor, fz, out);
+  UZ_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 8 * kSlThreads && ld % 8 == 0 && factor >= 1 && d >= 1,
+               "uz_slayer_fwd: bad C/ld/factor");
+  const long long rows = static_cast<long long>(B) * d * h;
+  const size_t smem = (static_cast<size_t>(ncls) * C + static_cast<size_t>(slayer_pb(wd)) * ncls) * sizeof(float);
+  UZ_CHECK_ARG(smem <= 48 * 1024, "uz_slayer_fwd: ncls*C too large for the shared weights");
+  uz::launch(slayer_fwd_kernel, cap_blocks(rows, 8), kSlThreads, smem, ST(stream),
+             static_cast<const __nv_bfloat16*>(feat), ld, C, w, bias, ncls, static_cast<int>(rows), d, h, wd, factor, fz,
+             out);
   UZ_CHECK_LAUNCH("uz_slayer_fwd");
   return UZ_OK;
 }
@@ -507,7 +587,8 @@ extern "C" int uz_slayer3d_fwd(const void* feat, int ld, int C, const float* w, 
 }
 
 extern "C" int uz_slayer_bwd_num_blocks(int B, int h, int wd) {
-  return cap_blocks((static_cast<long long>(B) * h * wd + 7) / 8, 2);
+  (void)wd;
+  return cap_blocks(static_cast<long long>(B) * h, 2);       // blocks own low-res rows
 }
 
 extern "C" int uz_slayer_bwd(const float* dout, const void* feat, int ld, int C, const float* w, int ncls, int B, int h,
@@ -531,15 +612,15 @@ int slayer_bwd_impl(const float* dout, const void* feat, int ld, int C, const fl
                     float* db, void* stream) {
   UZ_CHECK_ARG(dout && feat && w && dfeat && wpartial && bpartial && dw && db, "uz_slayer_bwd: null pointer");
   UZ_CHECK_ARG(ncls >= 1 && ncls <= kMaxOut, "uz_slayer_bwd: %d outputs unsupported", ncls);
-  int warps = static_cast<int>((44 * 1024) / (static_cast<size_t>(ncls) * C * sizeof(float)));
-  if (warps > 8) warps = 8;
-  UZ_CHECK_ARG(warps >= 1, "uz_slayer_bwd: ncls*C too large for the shared accumulators");
-  const int threads = warps * 32;
+  UZ_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 8 * kSlThreads && ld % 8 == 0 && ldd % 8 == 0, "uz_slayer_bwd: bad C/ld");
+  const long long rows = static_cast<long long>(B) * d * h;
   const int blocks = uz_slayer_bwd_num_blocks(B * d, h, wd);
-  const size_t smem = static_cast<size_t>(warps) * ncls * C * sizeof(float);
-  uz::launch(slayer_bwd_kernel, blocks, threads, smem, ST(stream), dout, static_cast<const __nv_bfloat16*>(feat), ld, C, w, ncls,
-                                                           B, d, h, wd, factor, fz, static_cast<__nv_bfloat16*>(dfeat), ldd,
-                                                           wpartial, bpartial);
+  const size_t smem =
+      (2 * static_cast<size_t>(ncls) * C + static_cast<size_t>(slayer_pb(wd)) * ncls + ncls) * sizeof(float);
+  UZ_CHECK_ARG(smem <= 48 * 1024, "uz_slayer_bwd: ncls*C too large for the shared accumulators");
+  uz::launch(slayer_bwd_kernel, blocks, kSlThreads, smem, ST(stream), dout, static_cast<const __nv_bfloat16*>(feat), ld, C, w,
+             ncls, static_cast<int>(rows), d, h, wd, factor, fz, static_cast<__nv_bfloat16*>(dfeat), ldd, wpartial,
+             bpartial);
   UZ_CHECK_LAUNCH("uz_slayer_bwd");
   uz::launch(column_reduce_kernel, (ncls * C + 127) / 128, 128, 0, ST(stream), wpartial, blocks, ncls * C, dw, 1.f);
   uz::launch(column_reduce_kernel, 1, 32, 0, ST(stream), bpartial, blocks, ncls, db, 1.f);

@@ -525,7 +525,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
     const size_t total2 = static_cast<size_t>(Cout_logical) * Cin_logical * taps;
     int blocks2 = static_cast<int>((total2 + 255) / 256);
     if (blocks2 > uz::num_sms() * 8) blocks2 = uz::num_sms() * 8;
-    uz::launch(wgrad_reduce_kernel, blocks2, 256, 0, static_cast<cudaStream_t>(stream), workspace, pl2.splits, taps, Cout, Cin,
+    if (!(uz::g_conv_debug_flags & 4096)) uz::launch(wgrad_reduce_kernel, blocks2, 256, 0, static_cast<cudaStream_t>(stream), workspace, pl2.splits, taps, Cout, Cin,
                                                                                Cout_logical, Cin_logical, dw);
     UZ_CHECK_LAUNCH("uz_conv_wgrad(v2 reduce)");
     return UZ_OK;
@@ -574,7 +574,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
   const size_t total = static_cast<size_t>(Cout_logical) * Cin_logical * taps;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > uz::num_sms() * 8) blocks = uz::num_sms() * 8;
-  uz::launch(wgrad_reduce_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), workspace, pl.splits, taps, Cout, Cin,
+  if (!(uz::g_conv_debug_flags & 4096)) uz::launch(wgrad_reduce_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), workspace, pl.splits, taps, Cout, Cin,
                                                                             Cout_logical, Cin_logical, dw);
   UZ_CHECK_LAUNCH("uz_conv_wgrad(reduce)");
   return UZ_OK;

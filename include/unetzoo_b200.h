@@ -85,6 +85,23 @@ typedef struct UzPackDesc {
 } UzPackDesc;
 int uz_pack_conv_weights_batched(const void* descs_device, int n, int blocks_per_layer, void* stream);
 
+/* torch.optim.Adam(lr, betas, eps, weight_decay) -- the reference's optimizer (train_model.py:49: lr 1e-3,
+ * weight_decay 1e-5 added to the gradient) -- for ALL parameters in one launch.  descs_device: device array of UzAdamDesc;
+ * chunk_table_device: int [nchunks][2] = (tensor index, chunk index), one block per uz_adam_chunk_elems() elements;
+ * every parameter has its own fp32 step counter on the device (torch's capturable layout), incremented before the update
+ * (graph capturable; parameters without a gradient are simply not in the table and keep their count). */
+typedef struct UzAdamDesc {
+  void* p;            /* fp32 parameter, updated in place */
+  const void* g;      /* fp32 gradient */
+  void* m;            /* exp_avg */
+  void* v;            /* exp_avg_sq */
+  float* step;        /* this parameter's step counter (device scalar) */
+  long long n;        /* elements */
+} UzAdamDesc;
+int uz_adam_chunk_elems(void);
+int uz_adam_step_batched(const void* descs_device, int ntensors, const int* chunk_table_device, int nchunks, double lr,
+                         double beta1, double beta2, double eps, double weight_decay, void* stream);
+
 /* Training-mode BatchNorm statistics: reduce the conv's per-tile partials, emit scale = gamma*invstd and
  * shift = beta - mean*scale, save mean / invstd, update running stats (momentum, unbiased variance).
  * Replaces nn.BatchNorm2d(eps=1e-3, momentum=0.01) statistics, torchlayers.py:20. */

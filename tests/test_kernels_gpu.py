@@ -434,3 +434,27 @@ def test_ged_full_size_properties():
     sub = mo.generalised_energy_distance(samples[:9].cpu().numpy(), gts.cpu().numpy(), 1, range(1, 2))
     assert float(k.ged(samples[:9], gts, [1])[0]) == sub
     assert np.isfinite(out).all()
+
+
+def test_fused_adam_matches_torch_adam():
+    """b200.optim.FusedAdam (one launch for all parameters) against stock torch.optim.Adam, three steps, odd sizes."""
+    from b200.optim import FusedAdam
+    g = torch.Generator(device='cpu').manual_seed(5)
+    shapes = [(192, 192, 3, 3), (7,), (33, 5, 3, 3), (4097,), (1,), (64, 16, 1, 1)]
+    ref_p = [torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for s in shapes]
+    my_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=1e-5)
+    mine = FusedAdam(my_p, lr=1e-3, weight_decay=1e-5)
+    for it in range(3):
+        grads = [torch.randn(*s, generator=g).to(DEV) * (0.1 + it) for s in shapes]
+        for p, q, gr in zip(ref_p, my_p, grads):
+            p.grad = gr.clone()
+            q.grad = gr.clone() if it != 1 or p.numel() != 7 else None      # a parameter without gradient is skipped
+            if q.grad is None:
+                p.grad = None
+        ref.step()
+        mine.step()
+    for p, q in zip(ref_p, my_p):
+        torch.testing.assert_close(q, p, rtol=2e-6, atol=1e-7)
+    for p, q in zip(ref_p, my_p):
+        torch.testing.assert_close(mine.state[q]['exp_avg_sq'], ref.state[p]['exp_avg_sq'], rtol=1e-5, atol=1e-12)

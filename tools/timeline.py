@@ -51,16 +51,18 @@ def main():
         trace = args.out + '.trace.json'
         prof.export_chrome_trace(trace)
         tr = json.load(open(trace))
-        rows = [(e['ts'], e['dur'], e['name'], e.get('args', {})) for e in tr['traceEvents']
-                if e.get('cat') == 'kernel' and args.list in e['name']]
-        rows.sort()
-        rows = rows[-(len(rows) // 3):]
-        agg = collections.defaultdict(list)
-        for ts, dur, name, a in rows:
-            agg[(tuple(a.get('grid', [])), a.get('shared memory', 0))].append(dur)
-        for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-            print('grid %-16s smem %7s  n=%3d  total %8.1f us  avg %6.1f  min %6.1f max %6.1f' %
-                  (k[0], k[1], len(v), sum(v), sum(v) / len(v), min(v), max(v)))
+        for pat in args.list.split(','):
+            rows = [(e['ts'], e['dur'], e['name'], e.get('args', {})) for e in tr['traceEvents']
+                    if e.get('cat') == 'kernel' and pat in e['name']]
+            rows.sort()
+            rows = rows[-(len(rows) // 3):]
+            agg = collections.defaultdict(list)
+            for ts, dur, name, a in rows:
+                agg[(tuple(a.get('grid', [])), a.get('shared memory', 0))].append(dur)
+            print('== %s: %d launches, %.1f us' % (pat, len(rows), sum(r[1] for r in rows)))
+            for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]))[:14]:
+                print('grid %-16s smem %7s  n=%3d  total %8.1f us  avg %6.1f  min %6.1f max %6.1f' %
+                      (k[0], k[1], len(v), sum(v), sum(v) / len(v), min(v), max(v)))
         os.remove(trace)
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda t: t[0])

@@ -1,0 +1,101 @@
+"""Adam with the reference's semantics (train_model.py:49: torch.optim.Adam(lr=1e-3, weight_decay=1e-5), i.e. L2 added to
+the gradient, bias-corrected moments) as ONE kernel launch for all parameters (uz_adam_step_batched) instead of torch's
+multi-tensor chunks.  Same state layout as torch.optim.Adam(capturable=True) (``step`` device scalar, ``exp_avg``, ``exp_avg_sq`` per parameter), so
+state_dicts interchange; the step counter is a device scalar, the launch is CUDA-graph capturable.
+
+The caller's own torch.optim.Adam keeps working with the drop-in modules -- this class is what b200.train.make_adam
+returns for the step drivers."""
+import struct
+
+import torch
+
+from . import _lib
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._tables = {}            # group index -> [eager, captured] descriptor / chunk tables (pinned host + device)
+
+    def _state(self, p):
+        st = self.state[p]
+        if not st:
+            st['step'] = torch.zeros((), dtype=torch.float32, device=p.device)     # torch's capturable layout
+            st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        elif not (torch.is_tensor(st['step']) and st['step'].is_cuda and st['step'].dtype == torch.float32):
+            st['step'] = torch.as_tensor(float(st['step']), dtype=torch.float32, device=p.device)   # loaded state_dict
+        return st
+
+    def finish_capture(self):
+        """upload the descriptor tables recorded while a CUDA graph was being captured (call after the capture ends)"""
+        for bufs in self._tables.values():
+            tab = bufs[1]
+            if tab.get('dirty'):
+                tab['descs'].copy_(tab['host_d'], non_blocking=True)
+                tab['chunks'].copy_(tab['host_c'], non_blocking=True)
+                tab['dirty'] = False
+        torch.cuda.current_stream().synchronize()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        chunk = _lib.raw('uz_adam_chunk_elems')()
+        for gi, group in enumerate(self.param_groups):
+            live = [p for p in group['params'] if p.grad is not None]
+            if not live:
+                continue
+            dev = live[0].device
+            if not live[0].is_cuda:
+                raise _lib.UnetZooLibError('FusedAdam needs CUDA parameters (no CPU fallback path)')
+            rows, key = [], []
+            for p in live:
+                st = self._state(p)
+                g = p.grad
+                if g.dtype != torch.float32 or not g.is_contiguous() or not p.is_contiguous():
+                    raise _lib.UnetZooLibError('FusedAdam expects dense fp32 parameters and gradients')
+                key.append(g.data_ptr())
+                rows.append((p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
+                             st['step'].data_ptr(), p.numel()))
+            key = tuple(key)
+            # two persistent table sets per group, allocated on first use (never inside a stream capture): one for eager
+            # steps, one for a captured step whose memcpy nodes must keep reading the pointers they were captured with
+            capturing = torch.cuda.is_current_stream_capturing()
+            bufs = self._tables.get(gi)
+            if bufs is None:
+                nparam = len(group['params'])
+                nchunk_max = sum((p.numel() + chunk - 1) // chunk for p in group['params'])
+                bufs = []
+                for _ in range(2):
+                    bufs.append({'key': None, 'n': 0, 'nt': 0,
+                                 'host_d': torch.empty(nparam * 48, dtype=torch.uint8).pin_memory(),
+                                 'host_c': torch.empty(nchunk_max * 2, dtype=torch.int32).pin_memory(),
+                                 'descs': torch.empty(nparam * 48, dtype=torch.uint8, device=dev),
+                                 'chunks': torch.empty(nchunk_max * 2, dtype=torch.int32, device=dev)})
+                self._tables[gi] = bufs
+            tab = bufs[1 if capturing else 0]
+            if tab['key'] != key:
+                raw = b''.join(struct.pack('<QQQQQq', *r) for r in rows)
+                table = []
+                for ti, r in enumerate(rows):
+                    for c in range((r[5] + chunk - 1) // chunk):
+                        table += [ti, c]
+                tab['host_d'][:len(raw)] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+                tab['host_c'][:len(table)] = torch.tensor(table, dtype=torch.int32)
+                tab['key'], tab['n'], tab['nt'] = key, len(table) // 2, len(rows)
+            descs, chunks, nchunks = tab['descs'], tab['chunks'], tab['n']
+            if capturing:
+                # no memcpy nodes inside a captured step (they break the back-to-back kernel scheduling of the graph):
+                # the tables of a capture are static, finish_capture() uploads them once before the first replay
+                tab['dirty'] = True
+            else:
+                descs.copy_(tab['host_d'], non_blocking=True)
+                chunks.copy_(tab['host_c'], non_blocking=True)
+            b1, b2 = group['betas']
+            _lib.call('uz_adam_step_batched', descs.data_ptr(), tab['nt'], chunks.data_ptr(), nchunks,
+                      float(group['lr']), float(b1), float(b2), float(group['eps']), float(group['weight_decay']),
+                      torch.cuda.current_stream().cuda_stream)
+        return loss

@@ -10,11 +10,15 @@ import torch
 from . import _lib, kern
 
 
-def make_adam(net, capturable=True, fused=True):
-    """The reference's optimizer (train_model.py:49: Adam, lr 1e-3, weight_decay 1e-5 as L2 on the gradient) -- stock
-    torch.optim.Adam.  capturable=True lets optimizer.step() live inside a CUDA graph; fused=True selects torch's
-    multi-tensor fused implementation (the default for-each path launches two tiny pow kernels PER PARAMETER for the
-    bias corrections: 1640 launches per PHiSeg step)."""
+def make_adam(net, capturable=True, fused=True, own_kernel=True):
+    """The reference's optimizer (train_model.py:49: Adam, lr 1e-3, weight_decay 1e-5 as L2 on the gradient).
+    own_kernel=True: b200.optim.FusedAdam, one launch for all parameters (graph capturable, same state layout as
+    torch.optim.Adam).  own_kernel=False: stock torch.optim.Adam; capturable=True lets optimizer.step() live inside a CUDA
+    graph, fused=True selects torch's multi-tensor implementation (its default for-each path launches two tiny pow
+    kernels PER PARAMETER for the bias corrections: 1640 launches per PHiSeg step)."""
+    if own_kernel:
+        from .optim import FusedAdam
+        return FusedAdam(net.parameters(), lr=1e-3, weight_decay=1e-5)
     return torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-5, capturable=capturable, fused=fused)
 
 
@@ -64,6 +68,8 @@ class TrainStep:
             with torch.cuda.graph(self.graph):
                 self._body()
             self.launches_per_step = _lib.raw('uz_launch_count')() - n0
+            if hasattr(self.opt, 'finish_capture'):
+                self.opt.finish_capture()
         else:
             n0 = _lib.raw('uz_launch_count')()
             self._body()

@@ -20,6 +20,12 @@ inline int ew_blocks(size_t work, int per_block = kEwThreads) {
   return static_cast<int>(b);
 }
 
+// block size that is a multiple of the number of 8-channel chunks per pixel (<= 256 when possible)
+inline int chunk_aligned_threads(int chunks) {
+  if (chunks >= kEwThreads) return chunks > 1024 ? 1024 / 1 : chunks;
+  return (kEwThreads / chunks) * chunks;
+}
+
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   f[0] = uz::bf16lo(v.x); f[1] = uz::bf16hi(v.x); f[2] = uz::bf16lo(v.y); f[3] = uz::bf16hi(v.y);
   f[4] = uz::bf16lo(v.z); f[5] = uz::bf16hi(v.z); f[6] = uz::bf16lo(v.w); f[7] = uz::bf16hi(v.w);
@@ -64,31 +70,114 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
   }
 }
 
-// all conv layers of a model in ONE launch: blockIdx.y selects the layer descriptor (device table of UzPackDesc)
-__global__ void pack_weight_batched_kernel(const UzPackDesc* __restrict__ descs) {
+// all conv layers of a model in ONE launch: blockIdx.y selects the layer descriptor (device table of UzPackDesc).
+// A work item is a 32 (o) x 32 (i) x 9-tap tile staged through shared memory, so that the fp32 reads (contiguous runs
+// of the OIHW source), the forward stores (i fastest) and the transposed dgrad stores (o fastest) are all coalesced.
+// 27-tap kernels are three 9-tap groups (one per kd): both tap permutations map a group onto itself.
+__global__ void __launch_bounds__(kEwThreads) pack_weight_batched_kernel(const UzPackDesc* __restrict__ descs) {
   uz::pdl_prologue();
+  __shared__ float tile[32][32 * 9 + 1];
   const UzPackDesc d = descs[blockIdx.y];
   const float* __restrict__ w = static_cast<const float*>(d.w);
   __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(d.w_fwd);
   __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d.w_dgrad);
-  const size_t n_fwd = static_cast<size_t>(d.taps) * d.CoutP * d.CinP;
-  const size_t n_bwd = wd ? n_fwd : 0;          // dgrad copy: [taps][CinP][CoutP]
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < n_fwd + n_bwd;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    if (idx < n_fwd) {
-      const int i = idx % d.CinP;
-      const int o = (idx / d.CinP) % d.CoutP;
-      const int t = idx / (static_cast<size_t>(d.CinP) * d.CoutP);
-      float v = (i < d.Cin && o < d.Cout) ? w[(static_cast<size_t>(o) * d.Cin + i) * d.taps + src_tap(t, d.taps)] : 0.f;
-      wp[idx] = __float2bfloat16(v);
-    } else {
-      const size_t j = idx - n_fwd;
-      const int o = j % d.CoutP;
-      const int i = (j / d.CoutP) % d.CinP;
-      const int t = j / (static_cast<size_t>(d.CoutP) * d.CinP);
-      float v = (i < d.Cin && o < d.Cout)
-                    ? w[(static_cast<size_t>(o) * d.Cin + i) * d.taps + src_tap(d.taps - 1 - t, d.taps)] : 0.f;
-      wd[j] = __float2bfloat16(v);
+  const int tg = d.taps >= 9 ? 9 : 1;             // taps per group (taps is 1, 9 or 27)
+  const int groups = d.taps / tg;
+  const int ti = (d.CinP + 31) / 32, to = (d.CoutP + 31) / 32;
+  const int total = to * ti * groups;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int grp = item % groups;
+    const int r = item / groups;
+    const int i0 = (r % ti) * 32, o0 = (r / ti) * 32;
+    const int row = 32 * tg;
+    for (int e = threadIdx.x; e < 32 * row; e += kEwThreads) {
+      const int oo = e / row, rem = e - oo * row;
+      const int ii = rem / tg, sl = rem - ii * tg;
+      const int o = o0 + oo, i = i0 + ii;
+      tile[oo][rem] = (o < d.Cout && i < d.Cin) ? w[(static_cast<size_t>(o) * d.Cin + i) * d.taps + grp * tg + sl] : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < tg * 1024; e += kEwThreads) {
+      const int tl = e >> 10, a = (e >> 5) & 31, b = e & 31;
+      const int sl = tg == 9 ? (tl % 3) * 3 + tl / 3 : 0;            // packed tap tl of the group <- source tap sl
+      {   // forward copy: a = o, b = i (fastest)
+        const int o = o0 + a, i = i0 + b;
+        if (o < d.CoutP && i < d.CinP)
+          wp[(static_cast<size_t>(grp * tg + tl) * d.CoutP + o) * d.CinP + i] = __float2bfloat16(tile[a][b * tg + sl]);
+      }
+      if (wd) {   // dgrad copy: wd[taps-1-u][i][o] = w[o][i][src(u)], u = grp*tg + tl; a = i, b = o (fastest)
+        const int i = i0 + a, o = o0 + b;
+        if (o < d.CoutP && i < d.CinP)
+          wd[(static_cast<size_t>(d.taps - 1 - (grp * tg + tl)) * d.CinP + i) * d.CoutP + o] =
+              __float2bfloat16(tile[b][a * tg + sl]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- Adam, all parameters in one launch
+// torch.optim.Adam(lr, betas, eps, weight_decay as L2 on the gradient) -- the optimizer of the reference
+// (train_model.py:49) -- over a device table of (param, grad, exp_avg, exp_avg_sq, numel) and a chunk table that maps
+// each block to (tensor, 4096-element chunk).  The step counter lives on the device so the launch is graph-capturable.
+__global__ void adam_count_kernel(const UzAdamDesc* __restrict__ descs, int n) {
+  uz::pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) descs[i].step[0] += 1.f;
+}
+
+constexpr int kAdamChunk = 4096;
+__global__ void __launch_bounds__(256) adam_batched_kernel(const UzAdamDesc* __restrict__ descs,
+                                                           const int* __restrict__ chunk_table, double lr_d,
+                                                           double beta1_d, double beta2_d, float eps,
+                                                           float weight_decay) {
+  uz::pdl_prologue();
+  const int tensor = chunk_table[2 * blockIdx.x], chunk = chunk_table[2 * blockIdx.x + 1];
+  const UzAdamDesc d = descs[tensor];
+  float* __restrict__ p = static_cast<float*>(d.p);
+  const float* __restrict__ g = static_cast<const float*>(d.g);
+  float* __restrict__ m = static_cast<float*>(d.m);
+  float* __restrict__ v = static_cast<float*>(d.v);
+  // bias corrections in double like torch's host-side computation (1 - beta^t cancels badly in fp32 for small t)
+  // and 1 - beta in double before rounding to fp32, which is what torch's Python scalars do)
+  const double t = static_cast<double>(d.step[0]);
+  const double bc1 = 1.0 - pow(beta1_d, t);
+  const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(beta2_d, t)));
+  const float step_size = static_cast<float>(lr_d / bc1);
+  const float beta2 = static_cast<float>(beta2_d);
+  const float omb1 = static_cast<float>(1.0 - beta1_d), omb2 = static_cast<float>(1.0 - beta2_d);
+  const long long lo = static_cast<long long>(chunk) * kAdamChunk;
+  const long long hi = min(lo + kAdamChunk, d.n);
+  const bool vec = (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                      reinterpret_cast<uintptr_t>(v)) & 15) == 0);
+  auto update = [&](float& pp, float gg, float& mm, float& vv) {
+    gg = fmaf(weight_decay, pp, gg);
+    mm = fmaf(omb1, gg - mm, mm);                         // lerp(exp_avg, grad, 1 - beta1)
+    vv = fmaf(beta2, vv, omb2 * gg * gg);
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp -= step_size * mm / denom;
+  };
+  if (vec && hi - lo == kAdamChunk) {
+#pragma unroll
+    for (int k = 0; k < kAdamChunk / (256 * 4); ++k) {
+      const long long i = lo + (k * 256 + threadIdx.x) * 4;
+      float4 pp = *reinterpret_cast<const float4*>(p + i);
+      const float4 gg = *reinterpret_cast<const float4*>(g + i);
+      float4 mm = *reinterpret_cast<const float4*>(m + i);
+      float4 vv = *reinterpret_cast<const float4*>(v + i);
+      update(pp.x, gg.x, mm.x, vv.x);
+      update(pp.y, gg.y, mm.y, vv.y);
+      update(pp.z, gg.z, mm.z, vv.z);
+      update(pp.w, gg.w, mm.w, vv.w);
+      *reinterpret_cast<float4*>(p + i) = pp;
+      *reinterpret_cast<float4*>(m + i) = mm;
+      *reinterpret_cast<float4*>(v + i) = vv;
+    }
+  } else {
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+      float pp = p[i], mm = m[i], vv = v[i];
+      update(pp, g[i], mm, vv);
+      p[i] = pp; m[i] = mm; v[i] = vv;
     }
   }
 }
@@ -203,17 +292,22 @@ __global__ void bn_apply_train_kernel(const __nv_bfloat16* __restrict__ y, int l
     }
   }
   __syncthreads();
+  // blockDim.x is a multiple of C/8 (launcher): a thread keeps its 8-channel chunk for the whole loop, so the
+  // coefficients live in registers and the loop has no index division
   const int chunks = C / 8;
-  const size_t total = npix * chunks;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t pix = idx / chunks;
-    const int c0 = static_cast<int>(idx - pix * chunks) * 8;
+  const int c0 = (threadIdx.x % chunks) * 8;
+  const size_t prow = blockDim.x / chunks;
+  const size_t pstride = gridDim.x * prow;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = sm[c0 + j]; sh[j] = sm[C + c0 + j]; }
+#pragma unroll 2
+  for (size_t pix = blockIdx.x * prow + threadIdx.x / chunks; pix < npix; pix += pstride) {
     float f[8];
     unpack8(*reinterpret_cast<const uint4*>(y + pix * ldy + c0), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      f[j] = fmaf(f[j], sm[c0 + j], sm[C + c0 + j]);
+      f[j] = fmaf(f[j], sc[j], sh[j]);
       if (relu) f[j] = fmaxf(f[j], 0.f);
     }
     *reinterpret_cast<uint4*>(out + pix * ldo + c0) = pack8(f);
@@ -246,20 +340,26 @@ __global__ void bn_bwd_apply_train_kernel(const __nv_bfloat16* __restrict__ dout
     }
   }
   __syncthreads();
+  // blockDim.x is a multiple of C/8 (launcher): per-thread coefficients in registers, no index division in the loop
   const int chunks = C / 8;
-  const size_t total = npix * chunks;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t pix = idx / chunks;
-    const int c0 = static_cast<int>(idx - pix * chunks) * 8;
+  const int c0 = (threadIdx.x % chunks) * 8;
+  const size_t prow = blockDim.x / chunks;
+  const size_t pstride = gridDim.x * prow;
+  float ca[8], cb[8], cc[8], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ca[j] = sm[c0 + j]; cb[j] = sm[C + c0 + j]; cc[j] = sm[2 * C + c0 + j];
+    sc[j] = sm[3 * C + c0 + j]; sh[j] = sm[4 * C + c0 + j];
+  }
+#pragma unroll 2
+  for (size_t pix = blockIdx.x * prow + threadIdx.x / chunks; pix < npix; pix += pstride) {
     float g[8], yy[8];
     unpack8(*reinterpret_cast<const uint4*>(dout + pix * ldd + c0), g);
     unpack8(*reinterpret_cast<const uint4*>(y + pix * ldy + c0), yy);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float m = (!relu || fmaf(yy[j], sm[3 * C + c], sm[4 * C + c]) > 0.f) ? g[j] : 0.f;
-      g[j] = fmaf(sm[c], m, fmaf(sm[C + c], yy[j], sm[2 * C + c]));
+      const float m = (!relu || fmaf(yy[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
+      g[j] = fmaf(ca[j], m, fmaf(cb[j], yy[j], cc[j]));
     }
     *reinterpret_cast<uint4*>(dy + pix * lddy + c0) = pack8(g);
   }
@@ -804,6 +904,20 @@ extern "C" int uz_pack_conv_weights_batched(const void* descs_device, int n, int
   return UZ_OK;
 }
 
+extern "C" int uz_adam_chunk_elems(void) { return kAdamChunk; }
+
+extern "C" int uz_adam_step_batched(const void* descs_device, int ntensors, const int* chunk_table_device, int nchunks,
+                                    double lr, double beta1, double beta2, double eps, double weight_decay,
+                                    void* stream) {
+  UZ_CHECK_ARG(descs_device && chunk_table_device && ntensors > 0 && nchunks > 0, "uz_adam_step_batched: bad arguments");
+  uz::launch(adam_count_kernel, (ntensors + 255) / 256, 256, 0, ST(stream), static_cast<const UzAdamDesc*>(descs_device),
+             ntensors);
+  uz::launch(adam_batched_kernel, nchunks, 256, 0, ST(stream), static_cast<const UzAdamDesc*>(descs_device),
+             chunk_table_device, lr, beta1, beta2, static_cast<float>(eps), static_cast<float>(weight_decay));
+  UZ_CHECK_LAUNCH("uz_adam_step_batched");
+  return UZ_OK;
+}
+
 extern "C" int uz_bn_finalize(const float* partial, int tiles, int C, float count, const float* gamma,
                               const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                               float* scale, float* shift, float* mean_out, float* invstd_out, void* stream) {
@@ -888,8 +1002,9 @@ extern "C" int uz_bn_apply_train(const void* y, int ldy, const float* sums, floa
                                  float* scale_out, float* shift_out, float* mean_out, float* invstd_out, int relu,
                                  void* out, int ldo, long long npix, int C, void* stream) {
   UZ_CHECK_ARG(y && sums && scale_out && shift_out && mean_out && invstd_out && out, "uz_bn_apply_train: null pointer");
-  UZ_CHECK_ARG(C % 8 == 0 && ldy % 8 == 0 && ldo % 8 == 0 && npix > 0, "uz_bn_apply_train: bad arguments");
-  uz::launch(bn_apply_train_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 2 * C * sizeof(float), ST(stream), static_cast<const __nv_bfloat16*>(y), ldy, sums, count, gamma, beta, eps,
+  UZ_CHECK_ARG(C % 8 == 0 && C <= 8192 && ldy % 8 == 0 && ldo % 8 == 0 && npix > 0, "uz_bn_apply_train: bad arguments");
+  const int threads = chunk_aligned_threads(C / 8);
+  uz::launch(bn_apply_train_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8), threads), threads, 2 * C * sizeof(float), ST(stream), static_cast<const __nv_bfloat16*>(y), ldy, sums, count, gamma, beta, eps,
                                         momentum, running_mean, running_var, scale_out, shift_out, mean_out, invstd_out,
                                         relu, static_cast<__nv_bfloat16*>(out), ldo, static_cast<size_t>(npix), C);
   UZ_CHECK_LAUNCH("uz_bn_apply_train");
@@ -901,9 +1016,10 @@ extern "C" int uz_bn_bwd_apply_train(const void* dout, int ldd, const void* y, i
                                      const float* mean, const float* invstd, float* dgamma, float* dbeta, void* dy,
                                      int lddy, long long npix, int C, void* stream) {
   UZ_CHECK_ARG(dout && y && scale && shift && sums && mean && invstd && dy, "uz_bn_bwd_apply_train: null pointer");
-  UZ_CHECK_ARG(C % 8 == 0 && ldd % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0 && npix > 0,
+  UZ_CHECK_ARG(C % 8 == 0 && C <= 8192 && ldd % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0 && npix > 0,
                "uz_bn_bwd_apply_train: bad arguments");
-  uz::launch(bn_bwd_apply_train_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 5 * C * sizeof(float), ST(stream), static_cast<const __nv_bfloat16*>(dout), ldd,
+  const int threads = chunk_aligned_threads(C / 8);
+  uz::launch(bn_bwd_apply_train_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8), threads), threads, 5 * C * sizeof(float), ST(stream), static_cast<const __nv_bfloat16*>(dout), ldd,
                                             static_cast<const __nv_bfloat16*>(y), ldy, scale, shift, relu, sums, count,
                                             gamma, mean, invstd, dgamma, dbeta, static_cast<__nv_bfloat16*>(dy), lddy,
                                             static_cast<size_t>(npix), C);

@@ -375,22 +375,45 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, int taps, Plan2* 
   return true;
 }
 
-// dw[o][i][t] (+)= scale * sum_s partial[s][t][o][i]   (fixed order); also emits dbias[o] = sum_pixels dy when asked.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int CoutP, int CinP,
-                                    int Cout, int Cin, float* dw) {
+// dw[o][i][t] = sum_s partial[s][t][o][i], deterministic.  Block = (256 / G) (o, i) pairs x G split groups, blockIdx.y =
+// tap: consecutive threads of a group read consecutive floats of a partial slab (coalesced); the G groups walk the
+// splits in parallel (layers with few channels have up to 49 splits and too few pairs to hide the load latency
+// otherwise) and are combined through shared memory in a fixed order.  G = 1, 2, 4 or 8 so that a thread sums >= ~6 terms.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps,
+                                                           int CoutP, int CinP, int Cout, int Cin, float* dw, int G) {
   uz::pdl_prologue();
-  const size_t total = static_cast<size_t>(Cout) * Cin * taps;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int t = idx % taps;
-    const int i = (idx / taps) % Cin;
-    const int o = idx / (static_cast<size_t>(taps) * Cin);
+  __shared__ float red[256 + 8];
+  const int ppb = 256 / G;                       // pairs per block
+  const int lane = threadIdx.x % ppb, grp = threadIdx.x / ppb;
+  const size_t pairs = static_cast<size_t>(Cout) * Cin;
+  const size_t slab = static_cast<size_t>(CoutP) * CinP;
+  const int t = blockIdx.y;
+  for (size_t base = static_cast<size_t>(blockIdx.x) * ppb; base < pairs; base += static_cast<size_t>(gridDim.x) * ppb) {
+    const size_t idx = base + lane;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s)
-      acc += partial[((static_cast<size_t>(s) * taps + t) * CoutP + o) * CinP + i];
-    dw[idx] = acc;
+    if (idx < pairs) {
+      const int i = static_cast<int>(idx % Cin);
+      const int o = static_cast<int>(idx / Cin);
+      const float* src = partial + static_cast<size_t>(t) * slab + static_cast<size_t>(o) * CinP + i;
+#pragma unroll 4
+      for (int s = grp; s < splits; s += G) acc += src[static_cast<size_t>(s) * taps * slab];
+    }
+    if (G == 1) {
+      if (idx < pairs) dw[idx * taps + t] = acc;
+      continue;
+    }
+    red[grp * (ppb + 1) + lane] = acc;
+    __syncthreads();
+    if (grp == 0 && idx < pairs) {
+      float tot = red[lane];
+      for (int g = 1; g < G; ++g) tot += red[g * (ppb + 1) + lane];
+      dw[idx * taps + t] = tot;
+    }
+    __syncthreads();
   }
 }
+
+inline int reduce_groups(int splits) { return splits >= 32 ? 8 : (splits >= 16 ? 4 : (splits >= 8 ? 2 : 1)); }
 
 int pow2_div_le(int v, int cap) {
   int t = 1;
@@ -522,11 +545,12 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
     dim3 grid2(pl2.splits, pl2.p.co_blocks * 3 * pl2.p.nz * pl2.p.ci_chunks, 1);
     uz::launch(wgrad_tc2_kernel, grid2, kThreads, pl2.smem, static_cast<cudaStream_t>(stream), tdy2, tx2, pl2.p);
     UZ_CHECK_LAUNCH("uz_conv_wgrad(v2)");
-    const size_t total2 = static_cast<size_t>(Cout_logical) * Cin_logical * taps;
-    int blocks2 = static_cast<int>((total2 + 255) / 256);
+    const size_t total2 = static_cast<size_t>(Cout_logical) * Cin_logical;     // one thread per (o, i) pair
+    const int G2 = reduce_groups(pl2.splits);
+    int blocks2 = static_cast<int>((total2 + 256 / G2 - 1) / (256 / G2));
     if (blocks2 > uz::num_sms() * 8) blocks2 = uz::num_sms() * 8;
-    if (!(uz::g_conv_debug_flags & 4096)) uz::launch(wgrad_reduce_kernel, blocks2, 256, 0, static_cast<cudaStream_t>(stream), workspace, pl2.splits, taps, Cout, Cin,
-                                                                               Cout_logical, Cin_logical, dw);
+    if (!(uz::g_conv_debug_flags & 4096)) uz::launch(wgrad_reduce_kernel, dim3(blocks2, taps, 1), 256, 0, static_cast<cudaStream_t>(stream), workspace, pl2.splits, taps, Cout, Cin,
+                                                                               Cout_logical, Cin_logical, dw, G2);
     UZ_CHECK_LAUNCH("uz_conv_wgrad(v2 reduce)");
     return UZ_OK;
   }
@@ -571,11 +595,12 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
   dim3 grid(pl.splits, pl.p.tap_groups * pl.co_blocks, 1);
   uz::launch(kernel, grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream), tdy, tx, pl.p);
   UZ_CHECK_LAUNCH("uz_conv_wgrad");
-  const size_t total = static_cast<size_t>(Cout_logical) * Cin_logical * taps;
-  int blocks = static_cast<int>((total + 255) / 256);
+  const size_t total = static_cast<size_t>(Cout_logical) * Cin_logical;       // one thread per (o, i) pair
+  const int G1 = reduce_groups(pl.splits);
+  int blocks = static_cast<int>((total + 256 / G1 - 1) / (256 / G1));
   if (blocks > uz::num_sms() * 8) blocks = uz::num_sms() * 8;
-  if (!(uz::g_conv_debug_flags & 4096)) uz::launch(wgrad_reduce_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), workspace, pl.splits, taps, Cout, Cin,
-                                                                            Cout_logical, Cin_logical, dw);
+  if (!(uz::g_conv_debug_flags & 4096)) uz::launch(wgrad_reduce_kernel, dim3(blocks, taps, 1), 256, 0, static_cast<cudaStream_t>(stream), workspace, pl.splits, taps, Cout, Cin,
+                                                                            Cout_logical, Cin_logical, dw, G1);
   UZ_CHECK_LAUNCH("uz_conv_wgrad(reduce)");
   return UZ_OK;
 }

@@ -301,8 +301,25 @@ __global__ void bn_apply_train_kernel(const __nv_bfloat16* __restrict__ y, int l
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = sm[c0 + j]; sh[j] = sm[C + c0 + j]; }
-#pragma unroll 2
-  for (size_t pix = blockIdx.x * prow + threadIdx.x / chunks; pix < npix; pix += pstride) {
+  // four independent 16-byte loads in flight per thread before the first use (HBM latency x bandwidth needs ~64 KB per SM)
+  size_t pix = blockIdx.x * prow + threadIdx.x / chunks;
+  for (; pix + 3 * pstride < npix; pix += 4 * pstride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const uint4*>(y + (pix + u * pstride) * ldy + c0));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[j] = fmaf(f[j], sc[j], sh[j]);
+        if (relu) f[j] = fmaxf(f[j], 0.f);
+      }
+      *reinterpret_cast<uint4*>(out + (pix + u * pstride) * ldo + c0) = pack8(f);
+    }
+  }
+  for (; pix < npix; pix += pstride) {
     float f[8];
     unpack8(*reinterpret_cast<const uint4*>(y + pix * ldy + c0), f);
 #pragma unroll
@@ -351,18 +368,30 @@ __global__ void bn_bwd_apply_train_kernel(const __nv_bfloat16* __restrict__ dout
     ca[j] = sm[c0 + j]; cb[j] = sm[C + c0 + j]; cc[j] = sm[2 * C + c0 + j];
     sc[j] = sm[3 * C + c0 + j]; sh[j] = sm[4 * C + c0 + j];
   }
-#pragma unroll 2
-  for (size_t pix = blockIdx.x * prow + threadIdx.x / chunks; pix < npix; pix += pstride) {
+  auto one = [&](const uint4& vg, const uint4& vy, size_t px) {
     float g[8], yy[8];
-    unpack8(*reinterpret_cast<const uint4*>(dout + pix * ldd + c0), g);
-    unpack8(*reinterpret_cast<const uint4*>(y + pix * ldy + c0), yy);
+    unpack8(vg, g);
+    unpack8(vy, yy);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float m = (!relu || fmaf(yy[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
       g[j] = fmaf(ca[j], m, fmaf(cb[j], yy[j], cc[j]));
     }
-    *reinterpret_cast<uint4*>(dy + pix * lddy + c0) = pack8(g);
+    *reinterpret_cast<uint4*>(dy + px * lddy + c0) = pack8(g);
+  };
+  size_t pix = blockIdx.x * prow + threadIdx.x / chunks;
+  for (; pix + 3 * pstride < npix; pix += 4 * pstride) {        // eight independent 16-byte loads in flight per thread
+    uint4 vg[4], vy[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      vg[u] = *reinterpret_cast<const uint4*>(dout + (pix + u * pstride) * ldd + c0);
+      vy[u] = *reinterpret_cast<const uint4*>(y + (pix + u * pstride) * ldy + c0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(vg[u], vy[u], pix + u * pstride);
   }
+  for (; pix < npix; pix += pstride)
+    one(*reinterpret_cast<const uint4*>(dout + pix * ldd + c0), *reinterpret_cast<const uint4*>(y + pix * ldy + c0), pix);
 }
 
 // BN+ReLU backward, pass 1: per-channel sum(g) and sum(g * y) with g = dout * [y*scale+shift > 0]; partial per block.
@@ -383,19 +412,31 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
-#pragma unroll 4
-    for (size_t pix = static_cast<size_t>(blockIdx.x) * rows + r; pix < npix;
-         pix += static_cast<size_t>(gridDim.x) * rows) {
+    auto one = [&](const uint4& vg, const uint4& vy) {
       float g[8], yy[8];
-      unpack8(*reinterpret_cast<const uint4*>(dout + pix * ldd + c0), g);
-      unpack8(*reinterpret_cast<const uint4*>(y + pix * ldy + c0), yy);
+      unpack8(vg, g);
+      unpack8(vy, yy);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float m = (!relu || fmaf(yy[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
         sg[j] += m;
         sgy[j] = fmaf(m, yy[j], sgy[j]);
       }
+    };
+    const size_t pstride = static_cast<size_t>(gridDim.x) * rows;
+    size_t pix = static_cast<size_t>(blockIdx.x) * rows + r;
+    for (; pix + 3 * pstride < npix; pix += 4 * pstride) {      // eight independent 16-byte loads in flight per thread
+      uint4 vg[4], vy[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vg[u] = *reinterpret_cast<const uint4*>(dout + (pix + u * pstride) * ldd + c0);
+        vy[u] = *reinterpret_cast<const uint4*>(y + (pix + u * pstride) * ldy + c0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) one(vg[u], vy[u]);
     }
+    for (; pix < npix; pix += pstride)
+      one(*reinterpret_cast<const uint4*>(dout + pix * ldd + c0), *reinterpret_cast<const uint4*>(y + pix * ldy + c0));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       red[(r * 2) * C + c0 + j] = sg[j];

@@ -393,6 +393,9 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
     bn /= 2;
   }
   while (p.tiles * (Cout / bn) < sms && bn % 64 == 0 && bn >= 128) bn /= 2;
+  // chunks wider than 128 leave room for only ONE accumulator pair in TMEM (no epilogue / MMA overlap): split them once
+  // more so the accumulators are double buffered (192 -> 2 x 96, 256 -> 2 x 128); the slabs are then read twice from L2
+  if (4 * bn > 512 && bn % 32 == 0 && !(uz::g_conv_debug_flags & 16384)) bn /= 2;
   if (bn % 16) return false;
   p.BN = bn;
   p.n_chunks = Cout / bn;

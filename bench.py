@@ -241,6 +241,37 @@ def kernel_family_time(make_step, steps, world, device, lib):
     return out
 
 
+def cupti_kernel_table(step, replays=3):
+    """Per-kernel busy time of one captured step from CUPTI activity records (torch.profiler): name -> (launches, us).
+    Complements the CUDA-event numbers: same step, device timestamps per kernel.  Returns None when CUPTI is unavailable."""
+    try:
+        import collections
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(replays):
+                step.step_device()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        if not evs:
+            return None
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for e in evs:
+            name = e.name.replace('void ', '').replace('(anonymous namespace)::', '')
+            if name.startswith('at::native::'):
+                name = 'torch:' + name[len('at::native::'):].split('<')[0]
+            elif 'conv_tc' in name or 'wgrad_tc' in name:
+                name = name.split('(')[0]
+            else:
+                name = name.split('(')[0].split('<')[0]
+            agg[name][0] += 1
+            agg[name][1] += e.time_range.end - e.time_range.start
+        rows = sorted(((k, v[0] // replays, round(v[1] / replays, 1)) for k, v in agg.items()), key=lambda t: -t[2])
+        return [{'kernel': k, 'launches': c, 'us': u} for k, c, u in rows[:16]]
+    except Exception as exc:        # profiling is side information, never fatal
+        return [{'error': repr(exc)}]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -363,9 +394,10 @@ def main():
         eval_block = {'metric': 'PHiSeg GED-100 eval images/s (100 samples, 4 annotators, GED + NCC)',
                       'value': 1000.0 / t_ms, 'unit': 'images/s', 'ms_per_image': t_ms, 'ged': ged, 'ncc': ncc,
                       'samples_per_rank': ev.counts or [N_SAMPLES],
-                      'path': 'EvalStep.run_host: H2D image+labels, forward(training=False) on this rank\'s share of '
-                              'the 100 copies, accumulate_output(softmax), all-gather of the class probabilities '
-                              '(N>1), argmax, GED, NCC, D2H of two scalars'}
+                      'path': 'EvalStep.run_host: H2D image+labels, forward(training=False, replicate=n) on this '
+                              'rank\'s share of the 100 copies (encoders once, latent sampling + likelihood per copy), '
+                              'accumulate_output(softmax), all-gather of the class probabilities (N>1), argmax, GED, '
+                              'NCC, D2H of two scalars'}
         net.train()
 
     # ---- roofline of the tensor-core conv kernels, in situ (differential graph replays)
@@ -386,6 +418,7 @@ def main():
     fam = kernel_family_time(lambda: train.TrainStep(net, train.make_adam(net), BATCH, IMAGE, use_graph=True, dp=None,
                                                      device=device), max(5, args.steps // 2), 1, device, _lib)
     net.load_state_dict(saved)
+    by_kernel = cupti_kernel_table(step) if rank == 0 else None
     t_all = fam['all']
     t_conv = max(t_all - fam['without conv_tc (fwd+dgrad)'], 1e-6)
     t_wgrad = max(t_all - fam['without wgrad_tc'], 1e-6)
@@ -397,6 +430,7 @@ def main():
                 'algorithmic_flops_per_step': train_flops, 'kernel_ms_per_step': tc_ms,
                 'ms_per_kernel_family': {'conv_tc (fwd+dgrad)': t_conv, 'wgrad_tc (+reduce)': t_wgrad},
                 'step_ms': fam, 'peak_source': peak_src, 'share_of_step': tc_ms / t_all,
+                'by_kernel_cupti_multistream_step': by_kernel,
                 'how': 'CUDA-event time of the captured step, issued on ONE stream (multi-stream overlap off), minus the '
                        'same step with that kernel family elided (uz_set_debug_flags 128 / 256); no gradient '
                        'all-reduce; algorithmic FLOPs = 3 x forward conv FLOPs (SURVEY.md 8d).  The headline value '

@@ -325,3 +325,24 @@ def test_reversible_block_inverse_is_accurate():
     xr, dx = block.backward_pass(y, torch.zeros_like(y))
     assert _rel(xr.float(), x.float()) < 1e-2
     assert float(dx.float().abs().max()) == 0.0
+
+
+def test_replicated_evaluation_matches_repeated_inputs(golden_dir):
+    """forward(replicate=N) (encoders once) == forward on N explicit copies: same logits, same draws."""
+    g, net, sd, patch, mask, eps = _setup('phiseg_small', golden_dir)
+    net.eval()
+    n = 6
+    p1, m1 = patch[:1].cuda(), mask[:1].cuda()
+    with torch.no_grad():
+        torch.manual_seed(11)
+        a = [t.clone() for t in net.forward(p1.repeat(n, 1, 1, 1), m1.repeat(n, 1, 1, 1), training=False)]
+        mu_a = [t.clone() for t in net.prior_mu]
+        torch.manual_seed(11)
+        b = net.forward(p1, m1, training=False, replicate=n)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    for x, y in zip(mu_a, net.prior_mu):
+        assert torch.equal(x, y)
+    assert float((a[0][0] - a[0][1]).abs().max()) > 0          # the copies do differ (independent latent samples)
+    with pytest.raises(ValueError):
+        net.forward(patch.cuda(), mask.cuda(), training=False, replicate=2)

@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--multi-stream', action='store_true')
     ap.add_argument('--debug-flags', type=int, default=0)
+    ap.add_argument('--model', default='phiseg', choices=['phiseg', 'phiseg3d'])
     ap.add_argument('--list', default='', help='substring: print every launch of the matching kernels (grid, us)')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'timeline.json'))
     args = ap.parse_args()
@@ -30,13 +31,20 @@ def main():
     from b200 import _lib
     if args.debug_flags:
         _lib.call('uz_set_debug_flags', args.debug_flags)
-    net = dropin_phiseg(bench.FILTERS)
+    if args.model == 'phiseg3d':
+        from tests.keygrammar import dropin_phiseg3d
+        batch_n, image = 1, (4, 128, 128, 128)
+        net = dropin_phiseg3d([32, 64, 128], 3, image)
+        batches = bench.synthetic_batches(1, seed=1, volume=128)
+    else:
+        batch_n, image = bench.BATCH, bench.IMAGE
+        net = dropin_phiseg(bench.FILTERS)
+        batches = bench.synthetic_batches(1, seed=1)
     net.load_state_dict(synth.synth_state_dict(net.state_dict(), seed=0))
     net = net.to(dev)
     if not args.multi_stream:
         mp._CONCURRENT, ops._AUX_ENABLED = False, False
-    batches = bench.synthetic_batches(1, seed=1)
-    st = train.TrainStep(net, train.make_adam(net), bench.BATCH, bench.IMAGE, use_graph=True, device=dev)
+    st = train.TrainStep(net, train.make_adam(net), batch_n, image, use_graph=True, device=dev)
     st.patch.copy_(batches[0][0])
     st.mask.copy_(batches[0][1])
     st.prepare(warmup=2)

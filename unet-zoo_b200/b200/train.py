@@ -97,8 +97,9 @@ class EvalStep:
     """One validation image like train_model.py:177-205: N copies -> forward(training=False) -> accumulate_output
     (softmax) -> argmax -> GED + NCC against M annotators.  ``shard`` = (rank, world) splits the N samples."""
 
-    def __init__(self, net, n_samples=100, n_classes=2, shard=None):
+    def __init__(self, net, n_samples=100, n_classes=2, shard=None, dedup=True):
         self.net = net
+        self.dedup = dedup
         self.n = n_samples
         self.n_classes = n_classes
         self.counts = None
@@ -122,10 +123,14 @@ class EvalStep:
     def run_device(self, img, lab, utils=None):
         if utils is None:
             import utils
-        patch = img[None, None].repeat(self.n_local, 1, 1, 1)
         masks = lab.permute(2, 0, 1).float()                       # [M,H,W]
-        mask = masks[0][None, None].repeat(self.n_local, 1, 1, 1)
-        s_list = self.net.forward(patch, mask, training=False)
+        if self.dedup:
+            # the N copies are identical: the encoders run once, latent sampling and likelihood on all copies
+            s_list = self.net.forward(img[None, None], masks[0][None, None], training=False, replicate=self.n_local)
+        else:
+            patch = img[None, None].repeat(self.n_local, 1, 1, 1)
+            mask = masks[0][None, None].repeat(self.n_local, 1, 1, 1)
+            s_list = self.net.forward(patch, mask, training=False)
         probs = self.net.accumulate_output(s_list, use_softmax=True)
         if self.counts is not None:                                # this rank's samples -> the full set on every rank
             from . import dp

@@ -401,23 +401,39 @@ class PHISeg(nn.Module):
             object.__setattr__(self, '_weight_packer', pk)
         return pk
 
-    def forward(self, patch, mask, training=True):
+    def forward(self, patch, mask, training=True, replicate=1):
+        """``replicate`` (extension, evaluation only): the N-sample evaluation of the reference feeds N identical copies of
+        one image (train_model.py:177-179).  forward(patch[1,...], mask[1,...], training=False, replicate=N) returns what
+        forward(patch.repeat(N,1,1,1), mask.repeat(N,1,1,1), training=False) returns -- same values, same random draws --
+        but runs the two encoders once instead of N times (their eval-mode outputs are identical for identical inputs)."""
         if not patch.is_cuda:
             raise kern._lib.UnetZooLibError('UNet-Zoo B200 modules need CUDA tensors: there is no CPU fallback path')
+        if replicate != 1 and (training or self.training or patch.shape[0] != 1):
+            raise ValueError('replicate=N needs eval mode, training=False and a batch of one image')
         pk = self._packer()
         pk.refresh()
         kern.zero_arena.reset(patch.device)
         prev = kern.set_active_packer(pk)
         try:
             with deferred_batch_counts():
-                return self._forward(patch, mask, training)
+                return self._forward(patch, mask, training, replicate)
         finally:
             kern.set_active_packer(prev)
 
-    def _forward(self, patch, mask, training=True):
+    @staticmethod
+    def _replicate(x, blocks, n):
+        if n == 1:
+            return x, blocks
+        rep = lambda a: Act(a.t.expand((n,) + tuple(a.t.shape[1:])).contiguous(), a.c)
+        return rep(x), [rep(b) for b in blocks]
+
+    def _forward(self, patch, mask, training=True, replicate=1):
         # posterior and prior encoders are independent (no random draws inside): the prior's runs on a second stream.
         # The latent halves keep the reference's order -- 5 posterior draws, then 5 prior draws (quirk Q4).
-        if _use_streams(patch):
+        if replicate != 1:
+            post_x, post_blocks = self._replicate(*self.posterior.contract(patch, mask), replicate)
+            prior_x, prior_blocks = self._replicate(*self.prior.contract(patch), replicate)
+        elif _use_streams(patch):
             fork = _Fork(patch.device)
             with fork.side():
                 prior_x, prior_blocks = self.prior.contract(patch)

@@ -368,8 +368,10 @@ class PHISeg3D(PHISeg):
             object.__setattr__(self, '_weight_packer', pk)
         return pk
 
-    def _forward(self, patch, mask, training=True):
+    def _forward(self, patch, mask, training=True, replicate=1):
         # volumes fill the GPU on their own: one stream, the reference's order
+        if replicate != 1:
+            raise NotImplementedError('replicate is an evaluation shortcut of the 2-D model')
         post_x, post_blocks = self.posterior.contract(patch, mask)
         self.posterior_latent_space, self.posterior_mu, self.posterior_sigma = self.posterior.latent(post_x, post_blocks)
         del post_x, post_blocks

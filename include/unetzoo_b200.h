@@ -195,8 +195,9 @@ int uz_head_bwd(const void* feat, int ld, int C, const float* wmu, const float* 
 
 /* One level of KL_two_gauss_with_diag_cov (models/phiseg.py:436-453, sigma1*sigma0 quirk) times `weight`
  * (4^level, models/phiseg.py:463): out[0] = weight * mean_b 0.5 * sum(...).  Inputs fp32 [batch][per_sample]. */
+int uz_kl_num_blocks(int batch, int per_sample);
 int uz_kl_fwd(const float* mu0, const float* s0, const float* mu1, const float* s1, int batch, int per_sample,
-              float weight, float* out, void* stream);
+              float weight, float* out, double* partial /* [uz_kl_num_blocks] */, void* stream);
 int uz_kl_bwd(const float* mu0, const float* s0, const float* mu1, const float* s1, int batch, int per_sample,
               float weight, const float* upstream, float* dmu0, float* ds0, float* dmu1, float* ds1, void* stream);
 

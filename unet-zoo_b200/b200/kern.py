@@ -421,7 +421,8 @@ def kl_fwd(mu0, s0, mu1, s1, weight):
     b = mu0.shape[0]
     per = mu0.numel() // b
     out = torch.empty((1,), dtype=torch.float32, device=mu0.device)
-    _lib.call('uz_kl_fwd', _p(mu0), _p(s0), _p(mu1), _p(s1), b, per, float(weight), _p(out), _stream())
+    partial = torch.empty((_lib.raw('uz_kl_num_blocks')(b, per),), dtype=torch.float64, device=mu0.device)
+    _lib.call('uz_kl_fwd', _p(mu0), _p(s0), _p(mu1), _p(s1), b, per, float(weight), _p(out), _p(partial), _stream())
     return out
 
 

@@ -17,41 +17,62 @@ constexpr int kMaxLvl = 8;   // latent levels (5)
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
 // ---------------------------------------------------------------- head forward
-// one warp per pixel: lanes stride over channels (bf16x2 loads), 2*Z dot products reduced with shuffles.
+// G lanes per pixel (G = 1..32, power of two, one 16-byte feature load per lane and step), the 2*Z dot products are
+// combined with xor shuffles; weights sit in shared memory.
+constexpr int kHeadThreads = 256;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&x)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  x[0] = uz::bf16lo(v.x); x[1] = uz::bf16hi(v.x); x[2] = uz::bf16lo(v.y); x[3] = uz::bf16hi(v.y);
+  x[4] = uz::bf16lo(v.z); x[5] = uz::bf16hi(v.z); x[6] = uz::bf16lo(v.w); x[7] = uz::bf16hi(v.w);
+}
+
 template <int Z>
-__global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ wmu,
-                                const float* __restrict__ bmu, const float* __restrict__ wsig,
-                                const float* __restrict__ bsig, const float* __restrict__ eps, int B, int hw, float* mu,
-                                float* sigma, float* z) {
+__global__ void __launch_bounds__(kHeadThreads)
+head_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ wmu,
+                const float* __restrict__ bmu, const float* __restrict__ wsig, const float* __restrict__ bsig,
+                const float* __restrict__ eps, int B, int hw, float* mu, float* sigma, float* z, int G) {
   uz::pdl_prologue();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int npix = B * hw;
-  if (warp >= npix) return;
-  float am[Z], as[Z];
-#pragma unroll
-  for (int k = 0; k < Z; ++k) { am[k] = 0.f; as[k] = 0.f; }
-  const __nv_bfloat16* f = feat + static_cast<size_t>(warp) * ld;
-  for (int c = lane * 2; c < C; c += 64) {
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(f + c);
-    const float f0 = uz::bf16lo(v), f1 = uz::bf16hi(v);
-#pragma unroll
-    for (int k = 0; k < Z; ++k) {
-      am[k] = fmaf(f0, wmu[k * C + c], fmaf(f1, wmu[k * C + c + 1], am[k]));
-      as[k] = fmaf(f0, wsig[k * C + c], fmaf(f1, wsig[k * C + c + 1], as[k]));
-    }
+  extern __shared__ float w_s[];          // [2Z][C]: mu rows then sigma rows
+  for (int i = threadIdx.x; i < Z * C; i += kHeadThreads) {
+    w_s[i] = wmu[i];
+    w_s[Z * C + i] = wsig[i];
   }
+  __syncthreads();
+  const int chunks = C / 8;
+  const int ppb = kHeadThreads / G;
+  const int pl = threadIdx.x / G, g = threadIdx.x % G;
+  const size_t npix = static_cast<size_t>(B) * hw;
+  for (size_t base = static_cast<size_t>(blockIdx.x) * ppb; base < npix; base += static_cast<size_t>(gridDim.x) * ppb) {
+    const size_t pix = base + pl;
+    float acc[2 * Z];
 #pragma unroll
-  for (int k = 0; k < Z; ++k) { am[k] = uz::warp_sum(am[k]); as[k] = uz::warp_sum(as[k]); }
-  if (lane == 0) {
-    const int b = warp / hw, r = warp - b * hw;
+    for (int k = 0; k < 2 * Z; ++k) acc[k] = 0.f;
+    if (pix < npix) {
+      const __nv_bfloat16* f = feat + pix * ld;
+      for (int c8 = g; c8 < chunks; c8 += G) {
+        float x[8];
+        load8(f + c8 * 8, x);
 #pragma unroll
-    for (int k = 0; k < Z; ++k) {
-      const size_t o = (static_cast<size_t>(b) * Z + k) * hw + r;
-      const float m = am[k] + bmu[k];
-      const float s = softplus_f(as[k] + bsig[k]);
-      const float zz = fmaf(s, eps[o], m);
-      mu[o] = m; sigma[o] = s; z[o] = zz;
+        for (int k = 0; k < 2 * Z; ++k) {
+          const float* wk = w_s + k * C + c8 * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k] = fmaf(x[j], wk[j], acc[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * Z; ++k)
+      for (int o = G >> 1; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (g == 0 && pix < npix) {
+      const size_t b = pix / hw, r = pix - b * hw;
+#pragma unroll
+      for (int k = 0; k < Z; ++k) {
+        const size_t o = (b * Z + k) * hw + r;
+        const float m = acc[k] + bmu[k];
+        const float sg = softplus_f(acc[Z + k] + bsig[k]);
+        mu[o] = m; sigma[o] = sg; z[o] = fmaf(sg, eps[o], m);
+      }
     }
   }
 }
@@ -60,77 +81,92 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, 
 // Inputs: upstream grads of mu, sigma, z (fp32 NCHW, any may be null).  dz folds into dmu/dsigma:
 //   dmu_t = dmu + dz ; dsig_t = dsigma + dz*eps ; dpre = dsig_t * sigmoid(pre) where sigma = softplus(pre).
 // Since sigma is saved (not pre): sigmoid(pre) = 1 - exp(-sigma) for pre <= 20, 1 otherwise (sigma = pre > 20).
-// Outputs: dfeat bf16 NHWC [npix][C]; per-block partial weight/bias grads reduced by head_bwd_wreduce_kernel.
+// A block walks chunks of PB pixels: the 2Z upstream values of every pixel are staged in shared memory, then one thread
+// per (pixel slot, 8-channel chunk) writes dfeat (16-byte stores) and keeps its share of dW in registers.
+// Outputs: dfeat bf16 [npix][C]; per-block partial weight / bias grads, reduced in fixed order by column_reduce_kernel.
 template <int Z>
-__global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ wmu,
-                                const float* __restrict__ wsig, const float* __restrict__ eps,
-                                const float* __restrict__ sigma, const float* __restrict__ dmu,
-                                const float* __restrict__ dsigma, const float* __restrict__ dz, int B, int hw,
-                                __nv_bfloat16* dfeat, int ldd, float* wpartial /*[blocks][2Z][C]*/,
-                                float* bpartial /*[blocks][2Z]*/) {
+__global__ void __launch_bounds__(kHeadThreads)
+head_bwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const float* __restrict__ wmu,
+                const float* __restrict__ wsig, const float* __restrict__ eps, const float* __restrict__ sigma,
+                const float* __restrict__ dmu, const float* __restrict__ dsigma, const float* __restrict__ dz, int B,
+                int hw, __nv_bfloat16* dfeat, int ldd, float* wpartial /*[blocks][2Z][C]*/,
+                float* bpartial /*[blocks][2Z]*/) {
   uz::pdl_prologue();
-  extern __shared__ float sm[];  // [warps][2Z][C] accumulators for weight grads
-  const int warps = blockDim.x >> 5;
-  const int wid = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  float* acc = sm + static_cast<size_t>(wid) * 2 * Z * C;
-  for (int i = lane; i < 2 * Z * C; i += 32) acc[i] = 0.f;
-  float bacc[2 * Z];
+  extern __shared__ float sm[];  // w_s [2Z][C] | dw_s [2Z][C] | g_s [PB][2Z] | db_s [2Z]
+  float* w_s = sm;
+  float* dw_s = sm + 2 * Z * C;
+  const int chunks = C / 8;
+  const int pb = kHeadThreads / chunks;                 // pixels per pass
+  float* g_s = dw_s + 2 * Z * C;
+  float* db_s = g_s + pb * 2 * Z;
+  for (int i = threadIdx.x; i < Z * C; i += kHeadThreads) {
+    w_s[i] = wmu[i];
+    w_s[Z * C + i] = wsig[i];
+  }
+  for (int i = threadIdx.x; i < 2 * Z * C; i += kHeadThreads) dw_s[i] = 0.f;
+  if (threadIdx.x < 2 * Z) db_s[threadIdx.x] = 0.f;
+  const int c8 = threadIdx.x % chunks, pslot = threadIdx.x / chunks;
+  const bool active = pslot < pb;
+  float dwr[2 * Z][8];
 #pragma unroll
-  for (int k = 0; k < 2 * Z; ++k) bacc[k] = 0.f;
-  __syncwarp();
-  const int npix = B * hw;
-  for (int pix = blockIdx.x * warps + wid; pix < npix; pix += gridDim.x * warps) {
-    const int b = pix / hw, r = pix - b * hw;
-    float gm[Z], gs[Z];
+  for (int k = 0; k < 2 * Z; ++k)
 #pragma unroll
-    for (int k = 0; k < Z; ++k) {
-      const size_t o = (static_cast<size_t>(b) * Z + k) * hw + r;
+    for (int j = 0; j < 8; ++j) dwr[k][j] = 0.f;
+  const size_t npix = static_cast<size_t>(B) * hw;
+  __syncthreads();
+  for (size_t base = static_cast<size_t>(blockIdx.x) * pb; base < npix; base += static_cast<size_t>(gridDim.x) * pb) {
+    const int pbc = static_cast<int>(min(static_cast<size_t>(pb), npix - base));
+    for (int i = threadIdx.x; i < pbc * Z; i += kHeadThreads) {
+      const int pl = i % pbc, k = i / pbc;                  // consecutive threads -> consecutive pixels (coalesced)
+      const size_t pix = base + pl;
+      const size_t b = pix / hw, r = pix - b * hw;
+      const size_t o = (b * Z + k) * hw + r;
       const float gz = dz ? dz[o] : 0.f;
-      const float s = sigma[o];
-      gm[k] = (dmu ? dmu[o] : 0.f) + gz;
+      const float sg = sigma[o];
+      const float gm = (dmu ? dmu[o] : 0.f) + gz;
       const float gsig = (dsigma ? dsigma[o] : 0.f) + gz * eps[o];
-      const float dsp = s > 20.f ? 1.f : (1.f - expf(-s));
-      gs[k] = gsig * dsp;
-      bacc[k] += gm[k];
-      bacc[Z + k] += gs[k];
+      const float dsp = sg > 20.f ? 1.f : (1.f - expf(-sg));
+      g_s[pl * 2 * Z + k] = gm;
+      g_s[pl * 2 * Z + Z + k] = gsig * dsp;
     }
-    const __nv_bfloat16* f = feat + static_cast<size_t>(pix) * ld;
-    __nv_bfloat16* df = dfeat + static_cast<size_t>(pix) * ldd;
-    for (int c = lane * 2; c < C; c += 64) {
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(f + c);
-      const float f0 = uz::bf16lo(v), f1 = uz::bf16hi(v);
-      float d0 = 0.f, d1 = 0.f;
+    __syncthreads();
+    if (threadIdx.x < 2 * Z) {
+      float t = 0.f;
+      for (int pl = 0; pl < pbc; ++pl) t += g_s[pl * 2 * Z + threadIdx.x];
+      db_s[threadIdx.x] += t;
+    }
+    if (active && pslot < pbc) {
+      const size_t pix = base + pslot;
+      float x[8], dd[8];
+      load8(feat + pix * ld + c8 * 8, x);
 #pragma unroll
-      for (int k = 0; k < Z; ++k) {
-        d0 = fmaf(gm[k], wmu[k * C + c], fmaf(gs[k], wsig[k * C + c], d0));
-        d1 = fmaf(gm[k], wmu[k * C + c + 1], fmaf(gs[k], wsig[k * C + c + 1], d1));
-        acc[k * C + c] = fmaf(gm[k], f0, acc[k * C + c]);
-        acc[k * C + c + 1] = fmaf(gm[k], f1, acc[k * C + c + 1]);
-        acc[(Z + k) * C + c] = fmaf(gs[k], f0, acc[(Z + k) * C + c]);
-        acc[(Z + k) * C + c + 1] = fmaf(gs[k], f1, acc[(Z + k) * C + c + 1]);
+      for (int j = 0; j < 8; ++j) dd[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 2 * Z; ++k) {
+        const float g = g_s[pslot * 2 * Z + k];
+        const float* wk = w_s + k * C + c8 * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dd[j] = fmaf(g, wk[j], dd[j]);
+          dwr[k][j] = fmaf(g, x[j], dwr[k][j]);
+        }
       }
-      *reinterpret_cast<uint32_t*>(df + c) = uz::pack_bf16x2(d0, d1);
+      *reinterpret_cast<uint4*>(dfeat + pix * ldd + c8 * 8) =
+          make_uint4(uz::pack_bf16x2(dd[0], dd[1]), uz::pack_bf16x2(dd[2], dd[3]), uz::pack_bf16x2(dd[4], dd[5]),
+                     uz::pack_bf16x2(dd[6], dd[7]));
     }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * Z * C; i += blockDim.x) {
-    float t = 0.f;
-    for (int w = 0; w < warps; ++w) t += sm[static_cast<size_t>(w) * 2 * Z * C + i];
-    wpartial[static_cast<size_t>(blockIdx.x) * 2 * Z * C + i] = t;
-  }
-  // bias partials: every lane of a warp holds the same bacc (all lanes executed the same pixel loop)
-  __shared__ float bsm[32][2 * Z];
-  if (lane == 0) {
+  if (active) {
 #pragma unroll
-    for (int k = 0; k < 2 * Z; ++k) bsm[wid][k] = bacc[k];
+    for (int k = 0; k < 2 * Z; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&dw_s[k * C + c8 * 8 + j], dwr[k][j]);
   }
   __syncthreads();
-  if (threadIdx.x < 2 * Z) {
-    float t = 0.f;
-    for (int w = 0; w < warps; ++w) t += bsm[w][threadIdx.x];
-    bpartial[blockIdx.x * 2 * Z + threadIdx.x] = t;
-  }
+  for (int i = threadIdx.x; i < 2 * Z * C; i += kHeadThreads)
+    wpartial[static_cast<size_t>(blockIdx.x) * 2 * Z * C + i] = dw_s[i];
+  if (threadIdx.x < 2 * Z) bpartial[blockIdx.x * 2 * Z + threadIdx.x] = db_s[threadIdx.x];
 }
 
 // out[i] = sum_b partial[b][i]   (fixed order, deterministic)
@@ -146,12 +182,15 @@ __global__ void column_reduce_kernel(const float* __restrict__ partial, int nblo
 // ---------------------------------------------------------------- KL (one level)
 // out[0] = weight * mean_b( 0.5 * sum_i[ (s0^2 + d^2)/(s1*s0 + 1e-10) + log(s1*s0 + 1e-10) - log(s0^2 + 1e-10) - 1 ] )
 // single block => deterministic; per-element terms in fp32 like the reference, block reduction in fp64.
-__global__ void kl_fwd_kernel(const float* __restrict__ mu0, const float* __restrict__ s0, const float* __restrict__ mu1,
-                              const float* __restrict__ s1, int n, float scale, float* out) {
+__global__ void __launch_bounds__(1024)
+kl_fwd_kernel(const float* __restrict__ mu0, const float* __restrict__ s0, const float* __restrict__ mu1,
+              const float* __restrict__ s1, long long n, double* partial) {
+  // per-block partial sums in fp64 (fixed grid-stride assignment => deterministic), finished by kl_finish_kernel
   uz::pdl_prologue();
   __shared__ double red[32];
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float a = s0[i], b = s1[i], d = mu1[i] - mu0[i];
     const float v0 = a * a, v1 = b * a;
     acc += static_cast<double>((v0 + d * d) / (v1 + 1e-10f) + logf(v1 + 1e-10f) - logf(v0 + 1e-10f) - 1.f);
@@ -162,8 +201,16 @@ __global__ void kl_fwd_kernel(const float* __restrict__ mu0, const float* __rest
   if (threadIdx.x < 32) {
     double t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
     t = uz::warp_sum_d(t);
-    if (threadIdx.x == 0) out[0] = static_cast<float>(0.5 * t * scale);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
   }
+}
+
+__global__ void kl_finish_kernel(const double* __restrict__ partial, int nblocks, float scale, float* out) {
+  uz::pdl_prologue();
+  double t = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += 32) t += partial[b];
+  t = uz::warp_sum_d(t);
+  if (threadIdx.x == 0) out[0] = static_cast<float>(0.5 * t * scale);
 }
 
 __global__ void kl_bwd_kernel(const float* __restrict__ mu0, const float* __restrict__ s0, const float* __restrict__ mu1,
@@ -495,17 +542,20 @@ extern "C" int uz_head_fwd(const void* feat, int ld, int C, const float* wmu, co
                            float* z, void* stream) {
   UZ_CHECK_ARG(feat && wmu && bmu && wsig && bsig && eps && mu && sigma && z, "uz_head_fwd: null pointer");
   UZ_CHECK_ARG(zdim == 2, "uz_head_fwd: z_dim %d unsupported (reference hard-codes 2, models/phiseg.py:81)", zdim);
-  UZ_CHECK_ARG(C % 2 == 0 && ld % 2 == 0, "uz_head_fwd: C and ld must be even");
-  const int npix = B * hw;
-  const int threads = 256;
-  const int blocks = (npix * 32 + threads - 1) / threads;
-  uz::launch(head_fwd_kernel<2>, blocks, threads, 0, ST(stream), static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, bmu, wsig,
-                                                          bsig, eps, B, hw, mu, sigma, z);
+  UZ_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && ld % 8 == 0, "uz_head_fwd: C and ld must be multiples of 8");
+  const long long npix = static_cast<long long>(B) * hw;
+  int G = 1;
+  while (G * 2 <= 32 && G * 2 <= C / 8) G *= 2;
+  if (npix >= (1ll << 18) && G > 4) G = 4;                         // large maps: fewer shuffles, more pixels per block
+  const int ppb = kHeadThreads / G;
+  const int blocks = cap_blocks((npix + ppb - 1) / ppb, 8);
+  uz::launch(head_fwd_kernel<2>, blocks, kHeadThreads, 4 * C * sizeof(float), ST(stream),
+             static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, bmu, wsig, bsig, eps, B, hw, mu, sigma, z, G);
   UZ_CHECK_LAUNCH("uz_head_fwd");
   return UZ_OK;
 }
 
-extern "C" int uz_head_bwd_num_blocks(int B, int hw) { return cap_blocks((static_cast<long long>(B) * hw + 7) / 8, 1); }
+extern "C" int uz_head_bwd_num_blocks(int B, int hw) { return cap_blocks((static_cast<long long>(B) * hw + 31) / 32, 2); }
 
 // dw: [2*zdim][C] (rows 0..zdim-1 = d mu_conv.weight, rest = d sigma_conv.weight); db: [2*zdim] likewise.
 extern "C" int uz_head_bwd(const void* feat, int ld, int C, const float* wmu, const float* wsig, const float* eps,
@@ -515,12 +565,12 @@ extern "C" int uz_head_bwd(const void* feat, int ld, int C, const float* wmu, co
   UZ_CHECK_ARG(feat && wmu && wsig && eps && sigma && dfeat && wpartial && bpartial && dw && db,
                "uz_head_bwd: null pointer");
   UZ_CHECK_ARG(zdim == 2, "uz_head_bwd: z_dim %d unsupported", zdim);
-  UZ_CHECK_ARG(C % 2 == 0 && ld % 2 == 0 && ldd % 2 == 0, "uz_head_bwd: C and strides must be even");
-  const int threads = 256;  // 8 warps
+  UZ_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 8 * kHeadThreads && ld % 8 == 0 && ldd % 8 == 0,
+               "uz_head_bwd: C and strides must be multiples of 8");
   const int blocks = uz_head_bwd_num_blocks(B, hw);
-  const size_t smem = static_cast<size_t>(threads / 32) * 4 * C * sizeof(float);
+  const size_t smem = (static_cast<size_t>(8) * C + (kHeadThreads / (C / 8)) * 4 + 4) * sizeof(float);
   UZ_CHECK_ARG(smem <= 48 * 1024, "uz_head_bwd: C=%d too large for the shared accumulators", C);
-  uz::launch(head_bwd_kernel<2>, blocks, threads, smem, ST(stream), static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, wsig,
+  uz::launch(head_bwd_kernel<2>, blocks, kHeadThreads, smem, ST(stream), static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, wsig,
                                                             eps, sigma, dmu, dsigma, dz, B, hw,
                                                             static_cast<__nv_bfloat16*>(dfeat), ldd, wpartial, bpartial);
   UZ_CHECK_LAUNCH("uz_head_bwd");
@@ -530,10 +580,17 @@ extern "C" int uz_head_bwd(const void* feat, int ld, int C, const float* wmu, co
   return UZ_OK;
 }
 
+extern "C" int uz_kl_num_blocks(int batch, int per_sample) {
+  return cap_blocks((static_cast<long long>(batch) * per_sample + 4095) / 4096, 1);
+}
+
 extern "C" int uz_kl_fwd(const float* mu0, const float* s0, const float* mu1, const float* s1, int batch,
-                         int per_sample, float weight, float* out, void* stream) {
-  UZ_CHECK_ARG(mu0 && s0 && mu1 && s1 && out && batch > 0, "uz_kl_fwd: bad arguments");
-  uz::launch(kl_fwd_kernel, 1, 1024, 0, ST(stream), mu0, s0, mu1, s1, batch * per_sample, weight / batch, out);
+                         int per_sample, float weight, float* out, double* partial, void* stream) {
+  UZ_CHECK_ARG(mu0 && s0 && mu1 && s1 && out && partial && batch > 0, "uz_kl_fwd: bad arguments");
+  const int blocks = uz_kl_num_blocks(batch, per_sample);
+  uz::launch(kl_fwd_kernel, blocks, 1024, 0, ST(stream), mu0, s0, mu1, s1, static_cast<long long>(batch) * per_sample,
+             partial);
+  uz::launch(kl_finish_kernel, 1, 32, 0, ST(stream), static_cast<const double*>(partial), blocks, weight / batch, out);
   UZ_CHECK_LAUNCH("uz_kl_fwd");
   return UZ_OK;
 }

@@ -48,14 +48,17 @@ def _dense(t):
 import os as _os
 
 _AUX_ENABLED = _os.environ.get('UNETZOO_CONCURRENCY', '1') != '0'
-_aux = {'streams': {}, 'pending': [], 'keep': [], 'callback_queued': False}
+_AUX_STREAMS = max(1, int(_os.environ.get('UNETZOO_AUX_STREAMS', '3')))      # weight-gradient streams (round robin)
+_aux = {'streams': {}, 'pending': [], 'keep': [], 'callback_queued': False, 'next': 0}
 
 
 def _aux_stream(device):
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    if idx not in _aux['streams']:
-        _aux['streams'][idx] = torch.cuda.Stream(device=device)
-    return _aux['streams'][idx]
+    key = (idx, torch.cuda.current_stream(device).cuda_stream, _aux['next'] % _AUX_STREAMS)
+    _aux['next'] += 1
+    if key not in _aux['streams']:
+        _aux['streams'][key] = torch.cuda.Stream(device=device)
+    return _aux['streams'][key]
 
 
 def sync_aux_streams():
@@ -66,6 +69,7 @@ def sync_aux_streams():
     _aux['pending'] = []
     _aux['keep'] = []
     _aux['callback_queued'] = False
+    _aux['next'] = 0
 
 
 def _run_on_aux(fn, keep):

@@ -23,6 +23,8 @@ from torchlayers import Conv2D, Conv2DSequence, ReversibleSequence, _boundary, d
 # Independent sub-graphs (prior vs posterior encoder, the likelihood's per-level branches) are issued on a second CUDA
 # stream: most of their layers are too small to fill 148 SMs on their own.  UNETZOO_CONCURRENCY=0 disables it.
 _CONCURRENT = os.environ.get('UNETZOO_CONCURRENCY', '1') != '0'
+_PRIOR_OVERLAP = os.environ.get('UNETZOO_PRIOR_OVERLAP', '1') != '0'    # prior latent path next to the likelihood
+_LIKELIHOOD_STREAMS = max(1, int(os.environ.get('UNETZOO_LIKELIHOOD_STREAMS', '4')))   # side streams of Likelihood.forward
 _side_streams = {}
 
 
@@ -44,25 +46,30 @@ class _null_ctx:
 
 
 class _Fork:
-    """fork the current stream into a per-device side stream and join it back (CUDA-graph capturable)"""
+    """fork the current stream into per-device side streams and join them back (CUDA-graph capturable)"""
 
-    def __init__(self, device):
+    def __init__(self, device, n=1, tag=''):
         self.main = torch.cuda.current_stream(device)
-        key = (device.index if device.index is not None else torch.cuda.current_device(), self.main.cuda_stream)
-        if key not in _side_streams:
-            _side_streams[key] = torch.cuda.Stream(device=device)
-        self.stream = _side_streams[key]
-        self.stream.wait_stream(self.main)
+        dev = device.index if device.index is not None else torch.cuda.current_device()
+        self.streams = []
+        for k in range(n):
+            key = (dev, self.main.cuda_stream, tag, k)
+            if key not in _side_streams:
+                _side_streams[key] = torch.cuda.Stream(device=device)
+            self.streams.append(_side_streams[key])
+            self.streams[-1].wait_stream(self.main)
+        self.stream = self.streams[0]
 
-    def side(self):
-        return torch.cuda.stream(self.stream)
+    def side(self, k=0):
+        return torch.cuda.stream(self.streams[k % len(self.streams)])
 
     def hand_over(self, *tensors):
         for t in tensors:
             t.record_stream(self.main)
 
     def join(self):
-        self.main.wait_stream(self.stream)
+        for st in self.streams:
+            self.main.wait_stream(st)
 
 
 class DownConvolutionalBlock(nn.Module):
@@ -300,11 +307,12 @@ class Likelihood(nn.Module):
         post_z = [None] * self.latent_levels
         post_c = [None] * self.latent_levels
         # the per-level branches are independent: the small ones run on a second stream next to the full-resolution one
-        fork = _Fork(z[0].device) if (z[0].is_cuda and _use_streams(z[0], self.image_size[1] * self.image_size[2])) else None
+        fork = (_Fork(z[0].device, _LIKELIHOOD_STREAMS)
+                if (z[0].is_cuda and _use_streams(z[0], self.image_size[1] * self.image_size[2])) else None)
         for i in range(self.latent_levels):
             assert z[-i - 1].shape[1] == 2
             assert z[-i - 1].shape[2] == self.image_size[1] * 2 ** (-self.resolution_levels + 1 + i)
-            with (fork.side() if (fork is not None and i != self.latent_levels - 1) else _null_ctx()):
+            with (fork.side(i) if (fork is not None and i != self.latent_levels - 1) else _null_ctx()):
                 x = self.likelihood_ups_path[i](ops.to_act(z[-i - 1]))
                 x = self.likelihood_post_ups_path[i](x)
                 if fork is not None and i != self.latent_levels - 1:
@@ -444,7 +452,18 @@ class PHISeg(nn.Module):
             post_x, post_blocks = self.posterior.contract(patch, mask)
             prior_x, prior_blocks = self.prior.contract(patch)
         self.posterior_latent_space, self.posterior_mu, self.posterior_sigma = self.posterior.latent(post_x, post_blocks)
-        if training:
+        if training and replicate == 1 and _PRIOR_OVERLAP and _use_streams(patch):
+            # teacher forcing: the prior's latent path consumes the POSTERIOR samples, the likelihood too -- they are
+            # independent of each other, so the prior's runs on a side stream next to the likelihood.  Its five random
+            # draws are still issued (host order = Philox offsets) right after the posterior's, before any other draw.
+            fork = _Fork(patch.device, 1, tag='prior')
+            with fork.side():
+                self.prior_latent_space, self.prior_mu, self.prior_sigma = self.prior.latent(
+                    prior_x, prior_blocks, training_prior=True, z_list=self.posterior_latent_space)
+                fork.hand_over(*self.prior_mu, *self.prior_sigma)
+            self.s_out_list = self.likelihood(self.posterior_latent_space)
+            fork.join()
+        elif training:
             self.prior_latent_space, self.prior_mu, self.prior_sigma = self.prior.latent(
                 prior_x, prior_blocks, training_prior=True, z_list=self.posterior_latent_space)
             self.s_out_list = self.likelihood(self.posterior_latent_space)

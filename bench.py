@@ -418,7 +418,8 @@ def main():
     fam = kernel_family_time(lambda: train.TrainStep(net, train.make_adam(net), BATCH, IMAGE, use_graph=True, dp=None,
                                                      device=device), max(5, args.steps // 2), 1, device, _lib)
     net.load_state_dict(saved)
-    by_kernel = cupti_kernel_table(step) if rank == 0 else None
+    # single-GPU only: under data parallelism a replay contains the NCCL all-reduces, which every rank would have to join
+    by_kernel = cupti_kernel_table(step) if world == 1 else None
     t_all = fam['all']
     t_conv = max(t_all - fam['without conv_tc (fwd+dgrad)'], 1e-6)
     t_wgrad = max(t_all - fam['without wgrad_tc'], 1e-6)

@@ -226,7 +226,8 @@ def kernel_family_time(make_step, steps, world, device, lib):
     import models.phiseg as _mp
     from b200 import ops as _ops
     saved_flags = (_mp._CONCURRENT, _ops._AUX_ENABLED)
-    _mp._CONCURRENT, _ops._AUX_ENABLED = False, False
+    _mp._CONCURRENT = False
+    _ops.set_concurrency(False)
     for name, flag in (('all', 0), ('without conv_tc (fwd+dgrad)', 128), ('without wgrad_tc', 256)):
         lib.call('uz_set_debug_flags', flag)
         try:
@@ -237,7 +238,8 @@ def kernel_family_time(make_step, steps, world, device, lib):
             out[name] = timed_region(lambda i: st.step_device(), steps, world, device) / steps
         finally:
             lib.call('uz_set_debug_flags', 0)
-    _mp._CONCURRENT, _ops._AUX_ENABLED = saved_flags
+    _mp._CONCURRENT = saved_flags[0]
+    _ops.set_concurrency(saved_flags[1])
     return out
 
 

@@ -59,6 +59,10 @@ int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx, const void
                 void* y, int ldy, const float* scale, const float* shift, int relu, float* stats_partial,
                 void* stream);
 
+/* Share of the SMs (percent, 5..100, default 100) a 2-D uz_conv_wgrad launch is planned for: callers that overlap
+ * weight gradients with other work (auxiliary streams) ask for fewer pixel splits -> fewer partial slabs to reduce.
+ * Affects uz_wgrad_workspace_floats too: set it before sizing the workspace. */
+int uz_set_wgrad_sm_percent(int percent);
 /* Workspace size (floats) for uz_conv_wgrad, or -1 if the shape is unsupported. */
 long long uz_wgrad_workspace_floats(int N, int H, int W, int Cin, int Cout, int taps);
 

@@ -45,7 +45,8 @@ def main():
     net.load_state_dict(synth.synth_state_dict(net.state_dict(), seed=0))
     net = net.to(dev)
     if not args.multi_stream:
-        mp._CONCURRENT, ops._AUX_ENABLED = False, False
+        mp._CONCURRENT = False
+        ops.set_concurrency(False)
     batches = bench.synthetic_batches(1, seed=1)
 
     def timed(flag, skip, no_adam=False):

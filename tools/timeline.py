@@ -43,7 +43,8 @@ def main():
     net.load_state_dict(synth.synth_state_dict(net.state_dict(), seed=0))
     net = net.to(dev)
     if not args.multi_stream:
-        mp._CONCURRENT, ops._AUX_ENABLED = False, False
+        mp._CONCURRENT = False
+        ops.set_concurrency(False)
     st = train.TrainStep(net, train.make_adam(net), batch_n, image, use_graph=True, device=dev)
     st.patch.copy_(batches[0][0])
     st.mask.copy_(batches[0][1])

@@ -48,6 +48,22 @@ def _dense(t):
 import os as _os
 
 _AUX_ENABLED = _os.environ.get('UNETZOO_CONCURRENCY', '1') != '0'
+_WGRAD_SM_PERCENT = int(_os.environ.get('UNETZOO_WGRAD_SM_PERCENT', '25'))   # planned SM share of an overlapped wgrad
+
+
+def set_concurrency(enabled):
+    """switch the auxiliary weight-gradient streams on / off; an overlapped launch is planned for a quarter of the SMs
+    (fewer split-K partials), a launch that owns the GPU for all of them"""
+    global _AUX_ENABLED
+    _AUX_ENABLED = bool(enabled)
+    _aux['planned_for'] = None
+
+
+def _plan_wgrad_share():
+    if _aux.get('planned_for') is not _AUX_ENABLED:       # applied lazily: importing this module never touches the library
+        kern._lib.call('uz_set_wgrad_sm_percent', _WGRAD_SM_PERCENT if _AUX_ENABLED else 100)
+        _aux['planned_for'] = _AUX_ENABLED
+
 _AUX_STREAMS = max(1, int(_os.environ.get('UNETZOO_AUX_STREAMS', '3')))      # weight-gradient streams (round robin)
 _aux = {'streams': {}, 'pending': [], 'keep': [], 'callback_queued': False, 'next': 0}
 
@@ -74,6 +90,7 @@ def sync_aux_streams():
 
 def _run_on_aux(fn, keep):
     """run fn() on the auxiliary stream after everything already queued on the current stream"""
+    _plan_wgrad_share()
     if not _AUX_ENABLED:
         return fn()
     cur = torch.cuda.current_stream()
@@ -201,7 +218,7 @@ class ConvAffineAct(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx, _ = kern.conv_fwd(dy, wd)
-        dw = kern.conv_wgrad(x, dy, taps, cin, cout).view(ctx.wshape)
+        dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, taps, cin, cout), (x, dy)).view(ctx.wshape)
         dshift = None
         if ctx.bias_is_shift and ctx.needs_input_grad[3]:
             dshift = kern.channel_sum(dy)

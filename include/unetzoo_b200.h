@@ -29,7 +29,8 @@ int uz_device_sm_count(void);
 long long uz_launch_count(void);
 /* profiling knobs for uz_conv_fwd (results become invalid): 1 = skip epilogue body, 2 = skip MMA issue,
  * 4 = skip activation TMA loads, 8 = skip weight TMA loads, 32 = force the generic (non-persistent) kernel,
- * 512 / 1024 / 2048 / 4096 = dispatch and elision knobs of tools/family_times.py,
+ * 512 / 1024 / 2048 / 4096 = dispatch and elision knobs of tools/family_times.py, 8192 = one CTA per SM also for narrow
+ * layers, 16384 = keep output chunks wider than 128 (A/B switches of two plan decisions, see conv_tc2.cu),
  * 128 = uz_conv_fwd returns without launching, 256 = uz_conv_wgrad returns without launching (bench.py times the step
  * with and without a kernel family to get that family's in-situ time).  0 restores normal operation. */
 int uz_set_debug_flags(int flags);

@@ -5,6 +5,8 @@ kernel launches of a PHiSeg step are replayed without Python in the loop.
 The caller-visible semantics are the reference's: stock torch.optim.Adam(lr=1e-3, weight_decay=1e-5) on the fp32
 parameters, loss = net.loss(mask) after net.forward(patch, mask, training=True).
 """
+import os
+
 import torch
 
 from . import _lib, kern
@@ -65,7 +67,11 @@ class TrainStep:
         if self.use_graph:
             self.graph = torch.cuda.CUDAGraph()
             n0 = _lib.raw('uz_launch_count')()
-            with torch.cuda.graph(self.graph):
+            # the capture stream (and the side streams forked from it for the forward / dgrad chains) get a higher
+            # priority than the auxiliary weight-gradient streams: critical-path kernels are scheduled first
+            prio = int(os.environ.get('UNETZOO_MAIN_PRIORITY', '-2'))
+            cap_stream = torch.cuda.Stream(device=self.device, priority=prio)
+            with torch.cuda.graph(self.graph, stream=cap_stream):
                 self._body()
             self.launches_per_step = _lib.raw('uz_launch_count')() - n0
             if hasattr(self.opt, 'finish_capture'):

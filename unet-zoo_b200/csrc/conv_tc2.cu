@@ -433,13 +433,8 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
   if (p.a_bytes % 1024) return false;
   p.out_off = p.stages * p.stage_bytes;
   out->smem = p.out_off + out_bytes + 1024;
-  static int sm_percent = -1;                 // measurement knob: share of the SMs a 2-D launch may occupy
-  if (sm_percent < 0) {
-    const char* e = getenv("UZ_CONV_SM_PERCENT");
-    sm_percent = e ? atoi(e) : 100;
-    if (sm_percent < 10 || sm_percent > 100) sm_percent = 100;
-  }
-  int slots = (vol ? sms : (sms * sm_percent + 99) / 100) * p.ctas_per_sm / p.n_chunks;
+  // (limiting a launch to a share of the SMs so that other streams can run beside it was measured: no gain for the conv)
+  int slots = sms * p.ctas_per_sm / p.n_chunks;
   if (slots > p.tiles) slots = p.tiles;
   if (slots < 1) return false;
   out->grid = slots * p.n_chunks;

@@ -55,7 +55,7 @@ class _Fork:
         for k in range(n):
             key = (dev, self.main.cuda_stream, tag, k)
             if key not in _side_streams:
-                _side_streams[key] = torch.cuda.Stream(device=device)
+                _side_streams[key] = torch.cuda.Stream(device=device, priority=self.main.priority)
             self.streams.append(_side_streams[key])
             self.streams[-1].wait_stream(self.main)
         self.stream = self.streams[0]

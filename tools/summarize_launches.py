@@ -9,7 +9,9 @@ hi = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
 hdr = rows[hi]
 ik, iv = hdr.index('Kernel Name'), hdr.index('Metric Value')
 data = [(r[ik], float(r[iv].replace(',', ''))) for r in rows[hi + 1:] if len(r) > iv]
-step = data[len(data) - len(data) // nsteps:]
+# a training step starts with the batched weight packing: take everything from its last occurrence
+starts = [i for i, (k, _) in enumerate(data) if 'pack_weight_batched_kernel' in k]
+step = data[starts[-1]:] if starts else data[len(data) - len(data) // nsteps:]
 agg = collections.defaultdict(lambda: [0, 0.0])
 for k, v in step:
     k = k.split('(')[0].replace('void ', '').replace('<unnamed>::', '')

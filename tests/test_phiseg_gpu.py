@@ -346,3 +346,40 @@ def test_replicated_evaluation_matches_repeated_inputs(golden_dir):
     assert float((a[0][0] - a[0][1]).abs().max()) > 0          # the copies do differ (independent latent samples)
     with pytest.raises(ValueError):
         net.forward(patch.cuda(), mask.cuda(), training=False, replicate=2)
+
+
+@pytest.mark.parametrize('training', [True, False])
+def test_non_square_image_and_batch_of_one(training):
+    """64 x 192 images (levels down to 1 x 3 maps), batch 1 and 3: shapes outside the benchmark configuration."""
+    filters = [16, 32, 32, 32, 32, 32, 32]
+    for batch in (1, 3):
+        net = dropin_phiseg(filters, image_size=(1, 64, 192))
+        sd = synth.synth_state_dict(net.state_dict(), seed=21)
+        net.load_state_dict(sd)
+        net = net.cuda()
+        net.train(training)
+        rs = np.random.RandomState(batch)
+        patch = torch.from_numpy((rs.standard_normal((batch, 1, 64, 192)) * 0.25).astype(np.float32))
+        mask = torch.from_numpy((rs.uniform(size=(batch, 1, 64, 192)) < 0.2).astype(np.float32))
+        shapes = [(batch, 2, 64 >> (l + 2), 192 >> (l + 2)) for l in (4, 3, 2, 1, 0)] * 2
+        eps = synth.noise_list(shapes, seed=4)
+        with injected_noise(eps), torch.no_grad():
+            s = [t.clone() for t in net.forward(patch.cuda(), mask.cuda(), training=training)]
+            loss = net.loss(mask.cuda())
+        with torch.no_grad():
+            emu = po.phiseg_forward({k: v.clone() for k, v in sd.items()}, patch, mask, eps, training=training,
+                                    rnd=po.Rounding(True))
+            e_emu = po.elbo(emu, mask)
+            ref = po.phiseg_forward({k: v.clone() for k, v in sd.items()}, patch, mask, eps, training=training)
+        acc, acc_emu, acc_ref = sum(t.cpu() for t in s), po.accumulate_output(emu['s']), po.accumulate_output(ref['s'])
+        assert tuple(acc.shape) == (batch, 2, 64, 192)
+        if training:
+            # batch statistics over as few as 1 x 3 x batch values: bf16 rounding alone moves the two ORACLES this far
+            # apart, so the bound is their own distance (the kernels are checked tightly by the eval-mode run)
+            gap = _rel(acc_emu, acc_ref)
+            print('\n[64x192, batch %d, train] cuda vs emu %.3e, emu vs fp32 oracle %.3e' % (batch, _rel(acc, acc_emu), gap))
+            assert _rel(acc, acc_emu) < max(0.1, 2.0 * gap), (batch, _rel(acc, acc_emu), gap)
+            assert float(loss) == pytest.approx(float(e_emu['total']), rel=0.1)
+        else:
+            assert _rel(acc, acc_emu) < 2e-2, (batch, _rel(acc, acc_emu))
+            assert float(loss) == pytest.approx(float(e_emu['total']), rel=1e-2)

@@ -110,3 +110,21 @@ def test_probunet_step(golden_dir, training):
         print('ProbUNet gradient-norm relative deviation from the reference fixture: median %.3e max %.3e' %
               (float(np.median(rel)), max(rel)))
         assert float(np.median(rel)) < 0.15
+
+
+def test_unet_rgb_non_square_input():
+    """3-channel 96 x 160 input, batch 1: generic tile geometry of the small-shape conv kernel, padded input channels."""
+    from models.unet import Unet
+    filters = [16, 32, 32, 48]
+    net = Unet(3, 2, filters)
+    sd = synth.synth_state_dict(net.state_dict(), seed=9)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy((rs.standard_normal((1, 3, 96, 160)) * 0.3).astype(np.float32))
+    with torch.no_grad():
+        got = net.forward(x.cuda()).cpu()
+        ref = uo.unet_forward(sd, x, len(filters), rnd=po.Rounding(True))
+    assert tuple(got.shape) == (1, 2, 96, 160)
+    rel = float((got - ref).norm() / ref.norm())
+    assert rel < 3e-2, rel

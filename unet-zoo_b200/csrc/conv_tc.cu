@@ -34,7 +34,8 @@ struct ConvParams {
   int taps;           // 9 or 1
   int TW, TH, TN;     // pixel box of one tile, TW*TH*TN == 128
   int tilesW, tilesH; // tiles per image row / column
-  int KC;             // channels per K step (16 / 32 / 64)
+  int KC;             // channels per TMA box (16 / 32 / 64)
+  int KB;             // channel blocks per pipeline stage (a stage = KB * KC channels of one tap)
   int BN;             // output channels per CTA (multiple of 16, <= 256)
   int stages;
   int ldy;            // output pixel stride (elements)
@@ -64,7 +65,7 @@ __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
   return v[0];
 }
 
-template <int KC>
+template <int KC, int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const ConvParams p) {
@@ -72,8 +73,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   // carve: [stages x A][stages x B] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t swz = KC * 2;                  // swizzle span in bytes = one smem row
-  const uint32_t a_bytes = kBlockM * swz;
-  const uint32_t b_bytes = p.BN * swz;
+  const uint32_t a_box = kBlockM * swz, b_box = p.BN * swz;       // one channel block of activations / weights
+  const uint32_t a_bytes = a_box * p.KB;
+  const uint32_t b_bytes = b_box * p.KB;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.stages * a_bytes;
   __shared__ uint64_t full_bar[kMaxStages];
@@ -96,8 +98,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
   const int c_out0 = n_chunk * p.BN;
 
-  const int kblocks = p.Cin / KC;
-  const int k_iters = p.taps * kblocks;
+  // a pipeline stage holds KB channel blocks of one tap (KB * KC channels): every stage hand-over costs ~0.2 us of
+  // barrier latency, which -- not the loads -- bounded these small launches when a stage was a single 64-channel block
+  const int kgroups = p.Cin / (KC * KB);
+  const int k_iters = p.taps * kgroups;
 
   if (warp == 0 && lane == 0) {
     uz::tma_prefetch_desc(&tmap_x);
@@ -131,14 +135,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       for (int it = 0; it < k_iters; ++it) {
         const int s = it % p.stages;
         if (it >= p.stages) uz::mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
-        const int tap = it / kblocks;
-        const int kb = it - tap * kblocks;
+        const int tap = it / kgroups;
+        const int kg = it - tap * kgroups;
         int dy = 0, dx = 0;
         if (p.taps == 9) { dx = tap / 3 - 1; dy = tap % 3 - 1; }   // packed taps are dx-major (see uz_pack_conv_weight)
         if (uz::elect_one()) {
           uz::mbar_expect_tx(&full_bar[s], ((p.dbg & 4) ? 0 : a_bytes) + ((p.dbg & 8) ? 0 : b_bytes));
-          if (!(p.dbg & 4)) uz::tma_load_4d(smem_a + s * a_bytes, &tmap_x, &full_bar[s], kb * KC, x0 + dx, y0 + dy, n0);
-          if (!(p.dbg & 8)) uz::tma_load_3d(smem_b + s * b_bytes, &tmap_w, &full_bar[s], kb * KC, c_out0, tap);
+          for (int j = 0; j < KB; ++j) {
+            const int c0 = (kg * KB + j) * KC;
+            if (!(p.dbg & 4)) uz::tma_load_4d(smem_a + s * a_bytes + j * a_box, &tmap_x, &full_bar[s], c0, x0 + dx, y0 + dy, n0);
+            if (!(p.dbg & 8)) uz::tma_load_3d(smem_b + s * b_bytes + j * b_box, &tmap_w, &full_bar[s], c0, c_out0, tap);
+          }
         }
         __syncwarp();
       }
@@ -157,12 +164,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       uz::tc_fence_after();
       const uint32_t a_lo = desc_lo0 + (uz::smem_u32(smem_a + s * a_bytes) >> 4);
       const uint32_t b_lo = desc_lo0 + (uz::smem_u32(smem_b + s * b_bytes) >> 4);
-      if (uz::elect_one()) {
-        if (!(p.dbg & 2)) {
+      const uint32_t a_step = a_box >> 4, b_step = b_box >> 4;
+      if (uz::elect_one()) {                     // ONE election per stage: every extra warp-level instruction in this
+        if (!(p.dbg & 2)) {                      // loop costs ~50 ns per iteration on these latency-bound launches
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k)
-            uz::tc_mma_f16(tmem_base, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
-                           k == 0 ? static_cast<uint32_t>(it != 0) : 1u);
+          for (int j = 0; j < KB; ++j) {
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k)
+              uz::tc_mma_f16(tmem_base, desc_hi | (a_lo + j * a_step + k * 2), desc_hi | (b_lo + j * b_step + k * 2), idesc,
+                             (j == 0 && k == 0) ? static_cast<uint32_t>(it != 0) : 1u);
+          }
         }
         uz::tc_commit(&empty_bar[s]);           // frees the smem slot once these MMAs retire
         if (it == k_iters - 1) uz::tc_commit(&accum_bar);
@@ -299,9 +310,19 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   while (cols < static_cast<uint32_t>(bn)) cols *= 2;
   p.tmem_cols = cols;
   const uint32_t swz = p.KC * 2;
-  const size_t stage_bytes = static_cast<size_t>(kBlockM + bn) * swz;
+  // channel blocks per stage: the largest divisor of Cin / KC (<= 4) that still leaves >= 3 stages
+  const int kblocks = Cin / p.KC;
+  p.KB = 1;
+  for (int kb = 4; kb >= 2; --kb) {
+    if (kblocks % kb == 0 && (196 * 1024) / (static_cast<size_t>(kBlockM + bn) * swz * kb) >= 2 &&
+        !(uz::g_conv_debug_flags & 65536)) {
+      p.KB = kb;
+      break;
+    }
+  }
+  const size_t stage_bytes = static_cast<size_t>(kBlockM + bn) * swz * p.KB;
   const size_t out_bytes = static_cast<size_t>(kBlockM) * (bn * 2 + 16);
-  const int k_iters = taps * (Cin / p.KC);
+  const int k_iters = taps * (kblocks / p.KB);
   int stages = static_cast<int>((196 * 1024) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > k_iters) stages = k_iters;
@@ -328,9 +349,15 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
     int rc = uz::make_tmap_bf16(&tw, w_packed, 3, dims, strides, box, swz);
     if (rc) return rc;
   }
-  auto kernel = p.KC == 64 ? conv_tc_kernel<64> : (p.KC == 32 ? conv_tc_kernel<32> : conv_tc_kernel<16>);
-  static size_t attr_bytes_kc[3] = {0, 0, 0};
-  size_t& attr_bytes = attr_bytes_kc[p.KC == 64 ? 0 : (p.KC == 32 ? 1 : 2)];
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvParams);
+  static const KernelFn table[3][4] = {
+      {conv_tc_kernel<64, 1>, conv_tc_kernel<64, 2>, conv_tc_kernel<64, 3>, conv_tc_kernel<64, 4>},
+      {conv_tc_kernel<32, 1>, conv_tc_kernel<32, 2>, conv_tc_kernel<32, 3>, conv_tc_kernel<32, 4>},
+      {conv_tc_kernel<16, 1>, conv_tc_kernel<16, 2>, conv_tc_kernel<16, 3>, conv_tc_kernel<16, 4>}};
+  const int kci = p.KC == 64 ? 0 : (p.KC == 32 ? 1 : 2);
+  KernelFn kernel = table[kci][p.KB - 1];
+  static size_t attr_bytes_kc[3][4] = {};
+  size_t& attr_bytes = attr_bytes_kc[kci][p.KB - 1];
   if (smem > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {

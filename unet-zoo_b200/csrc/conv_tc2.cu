@@ -393,6 +393,9 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
     if (bn % 64) return false;
     bn /= 2;
   }
+  // (a single-tile CTA runs load -> MMA -> epilogue back to back, nothing overlaps: with fewer items than SMs narrower
+  //  chunks shorten every phase; the slabs are then re-read from L2 by more CTAs)
+  while (2 * p.tiles * (Cout / bn) <= sms && bn % 32 == 0 && bn >= 64 && !(uz::g_conv_debug_flags & 32768)) bn /= 2;
   while (p.tiles * (Cout / bn) < sms && bn % 64 == 0 && bn >= 128) bn /= 2;
   // chunks wider than 128 leave room for only ONE accumulator pair in TMEM (no epilogue / MMA overlap): split them once
   // more so the accumulators are double buffered (192 -> 2 x 96, 256 -> 2 x 128); the slabs are then read twice from L2

@@ -383,3 +383,24 @@ def test_non_square_image_and_batch_of_one(training):
         else:
             assert _rel(acc, acc_emu) < 2e-2, (batch, _rel(acc, acc_emu))
             assert float(loss) == pytest.approx(float(e_emu['total']), rel=1e-2)
+
+
+def test_graph_captured_evaluation_matches_eager(golden_dir):
+    """EvalStep.run_host replays a CUDA graph of the N-sample evaluation; the samples differ from the eager path's (the
+    graph advances the Philox offset on its own), so the comparison is statistical: same image, N = 100 samples each."""
+    from b200 import train
+    g, net, sd, patch, mask, eps = _setup('phiseg_small', golden_dir)
+    _, labels, _ = synth.lidc_like_batch(int(g['batch']), seed=int(g['dseed']))
+    img = patch[0, 0].contiguous().pin_memory()
+    lab = labels[0].contiguous().pin_memory()
+    eager = train.EvalStep(net, 100, 2, use_graph=False)
+    graph = train.EvalStep(net, 100, 2, use_graph=True)
+    torch.manual_seed(3)
+    ge, ne = eager.run_host(img, lab)
+    g1, n1 = graph.run_host(img, lab)
+    g2, n2 = graph.run_host(img, lab)
+    print('\nGED eager %.5f graph %.5f %.5f   NCC eager %.5f graph %.5f %.5f' % (ge, g1, g2, ne, n1, n2))
+    assert all(np.isfinite(v) for v in (ge, g1, g2, ne, n1, n2))
+    assert (g1, n1) != (g2, n2)                       # every replay draws new samples
+    assert abs(g1 - ge) < 0.05 * max(1.0, abs(ge)) + 0.02 and abs(g2 - ge) < 0.05 * max(1.0, abs(ge)) + 0.02
+    assert abs(n1 - ne) < 0.05 and abs(n2 - ne) < 0.05

@@ -101,11 +101,14 @@ class TrainStep:
 
 class EvalStep:
     """One validation image like train_model.py:177-205: N copies -> forward(training=False) -> accumulate_output
-    (softmax) -> argmax -> GED + NCC against M annotators.  ``shard`` = (rank, world) splits the N samples."""
+    (softmax) -> argmax -> GED + NCC against M annotators.  ``shard`` = (rank, world) splits the N samples.
+    ``run_host`` replays a CUDA graph of the whole evaluation (eager it is host-bound: ~350 launches from Python take
+    twice as long as the kernels they start); ``run_device`` is the eager path through the drop-in ``utils`` functions."""
 
-    def __init__(self, net, n_samples=100, n_classes=2, shard=None, dedup=True):
+    def __init__(self, net, n_samples=100, n_classes=2, shard=None, dedup=True, use_graph=True):
         self.net = net
         self.dedup = dedup
+        self.use_graph = use_graph
         self.n = n_samples
         self.n_classes = n_classes
         self.counts = None
@@ -114,22 +117,11 @@ class EvalStep:
             from . import dp
             self.counts = dp.shard_counts(n_samples, shard[1])
             self.n_local = self.counts[shard[0]]
+        self.graph = None
+        self._shape = None
         net.eval()
 
-    @torch.no_grad()
-    def run_host(self, image_pinned, labels_pinned):
-        """image [H,W] fp32, labels [H,W,M] uint8 (host, pinned) -> (ged float, ncc float)"""
-        import utils  # the drop-in second boundary
-        dev = torch.device('cuda', torch.cuda.current_device())
-        img = image_pinned.to(dev, non_blocking=True)
-        lab = labels_pinned.to(dev, non_blocking=True)
-        return self.run_device(img, lab, utils)
-
-    @torch.no_grad()
-    def run_device(self, img, lab, utils=None):
-        if utils is None:
-            import utils
-        masks = lab.permute(2, 0, 1).float()                       # [M,H,W]
+    def _forward_probs(self, img, masks):
         if self.dedup:
             # the N copies are identical: the encoders run once, latent sampling and likelihood on all copies
             s_list = self.net.forward(img[None, None], masks[0][None, None], training=False, replicate=self.n_local)
@@ -141,6 +133,63 @@ class EvalStep:
         if self.counts is not None:                                # this rank's samples -> the full set on every rank
             from . import dp
             probs = dp.gather_samples(probs.contiguous(), self.counts)
+        return probs
+
+    def _device_body(self):
+        """everything on the device, results into self.out (double [2] = GED, NCC); no host synchronisation"""
+        masks = self.lab.permute(2, 0, 1).float()                  # [M,H,W]
+        probs = self._forward_probs(self.img, masks)
+        pred = kern.argmax_classes(probs)                          # torch.argmax(dim=1) of train_model.py:195
+        ged4 = kern.ged(pred, masks, list(range(1, self.n_classes)))
+        ks = torch.arange(self.n_classes, device=masks.device, dtype=masks.dtype).view(1, self.n_classes, 1, 1)
+        onehot = (masks.unsqueeze(1) == ks).long()                 # utils.convert_batch_to_onehot
+        ncc = kern.variance_ncc(probs, onehot)
+        self.out[0:1].copy_(ged4[0:1])
+        self.out[1:2].copy_(ncc)
+
+    def _prepare(self, image, labels):
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.img = torch.zeros(tuple(image.shape), dtype=torch.float32, device=dev)
+        self.lab = torch.zeros(tuple(labels.shape), dtype=labels.dtype, device=dev)
+        self.out = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.out_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self.img.copy_(image)
+        self.lab.copy_(labels)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(2):
+                self._device_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self._device_body()
+        torch.cuda.synchronize()
+        self._shape = (tuple(image.shape), tuple(labels.shape), labels.dtype)
+
+    @torch.no_grad()
+    def run_host(self, image_pinned, labels_pinned):
+        """image [H,W] fp32, labels [H,W,M] uint8 (host, pinned) -> (ged float, ncc float)"""
+        if not self.use_graph:
+            import utils  # the drop-in second boundary
+            dev = torch.device('cuda', torch.cuda.current_device())
+            return self.run_device(image_pinned.to(dev, non_blocking=True), labels_pinned.to(dev, non_blocking=True), utils)
+        if self.graph is None or self._shape != (tuple(image_pinned.shape), tuple(labels_pinned.shape), labels_pinned.dtype):
+            self._prepare(image_pinned, labels_pinned)
+        self.img.copy_(image_pinned, non_blocking=True)
+        self.lab.copy_(labels_pinned, non_blocking=True)
+        self.graph.replay()
+        self.out_host.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.out_host[0]), float(self.out_host[1])
+
+    @torch.no_grad()
+    def run_device(self, img, lab, utils=None):
+        if utils is None:
+            import utils
+        masks = lab.permute(2, 0, 1).float()                       # [M,H,W]
+        probs = self._forward_probs(img, masks)
         pred = kern.argmax_classes(probs)                          # torch.argmax(dim=1) of train_model.py:195
         ged = utils.generalised_energy_distance(pred, masks, nlabels=self.n_classes - 1,
                                                 label_range=range(1, self.n_classes))

@@ -85,26 +85,41 @@ __global__ void pair_distance_kernel(const uint32_t* __restrict__ bits_s, const 
 // Python's builtin sum() over floats: CPython >= 3.12 uses Neumaier compensated summation (Objects/bltinmodule.c),
 // which is what the reference's `sum(d_sy)` executes under this image's Python 3.12.  Reproduced step for step so the
 // GED is bit-identical; __dadd_rn/__dmul_rn keep the compiler from contracting into FMAs.
+__device__ __forceinline__ void py312_step(double x, double& f, double& c) {
+  const double t = __dadd_rn(f, x);
+  if (fabs(f) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dadd_rn(f, -t), x));
+  else c = __dadd_rn(c, __dadd_rn(__dadd_rn(x, -t), f));
+  f = t;
+}
 __device__ double py312_sum(const double* p, int n) {
   double f = 0.0, c = 0.0;
-  for (int k = 0; k < n; ++k) {
-    const double x = p[k];
-    const double t = __dadd_rn(f, x);
-    if (fabs(f) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dadd_rn(f, -t), x));
-    else c = __dadd_rn(c, __dadd_rn(__dadd_rn(x, -t), f));
-    f = t;
+  int k = 0;
+  for (; k + 8 <= n; k += 8) {          // the adds are a serial dependency chain: fetch eight terms ahead of it
+    double x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = p[k + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) py312_step(x[j], f, c);
   }
+  for (; k < n; ++k) py312_step(p[k], f, c);
   if (c != 0.0 && isfinite(c)) f = __dadd_rn(f, c);
   return f;
 }
 
 // out[0] = GED, out[1..3] = sum d_sy, sum d_ss, sum d_yy, in the reference's pair order (utils.py:185-200).
+// Three warps: the three Python sums are independent, each is sequential by definition.
 __global__ void ged_finish_kernel(const double* __restrict__ pair_d, int N, int M, double* out) {
   uz::pdl_prologue();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double sy = py312_sum(pair_d, N * M);
-  const double ss = py312_sum(pair_d + N * M, N * N);
-  const double yy = py312_sum(pair_d + N * M + N * N, M * M);
+  __shared__ double sums[3];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && w < 3) {
+    const double* base = w == 0 ? pair_d : (w == 1 ? pair_d + N * M : pair_d + N * M + N * N);
+    const int n = w == 0 ? N * M : (w == 1 ? N * N : M * M);
+    sums[w] = py312_sum(base, n);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double sy = sums[0], ss = sums[1], yy = sums[2];
   out[1] = sy; out[2] = ss; out[3] = yy;
   const double a = __dmul_rn(2.0 / static_cast<double>(N * M), sy);
   const double b = __dmul_rn(1.0 / static_cast<double>(N * N), ss);
@@ -250,7 +265,7 @@ extern "C" int uz_ged_pairwise(const unsigned int* bits_s, const int* cnt_s, int
   uz::launch(pair_distance_kernel, (total * 32 + 255) / 256, 256, 0, ST(stream), bits_s, cnt_s, N, bits_y, cnt_y, M, nlabels,
                                                                         words, pair_d);
   UZ_CHECK_LAUNCH("uz_ged_pairwise");
-  uz::launch(ged_finish_kernel, 1, 32, 0, ST(stream), pair_d, N, M, out);
+  uz::launch(ged_finish_kernel, 1, 96, 0, ST(stream), pair_d, N, M, out);
   UZ_CHECK_LAUNCH("uz_ged_pairwise(finish)");
   return UZ_OK;
 }

@@ -386,21 +386,32 @@ def test_non_square_image_and_batch_of_one(training):
 
 
 def test_graph_captured_evaluation_matches_eager(golden_dir):
-    """EvalStep.run_host replays a CUDA graph of the N-sample evaluation; the samples differ from the eager path's (the
-    graph advances the Philox offset on its own), so the comparison is statistical: same image, N = 100 samples each."""
+    """EvalStep.run_host replays a CUDA graph of the N-sample evaluation.  With the random draws replaced by a
+    deterministic function of the tensor shape both paths see the same "noise": GED must be bit-identical (integer
+    IoU counts, Python-order sums), NCC equal to fp64 round-off.  With real noise every replay draws new samples."""
     from b200 import train
     g, net, sd, patch, mask, eps = _setup('phiseg_small', golden_dir)
     _, labels, _ = synth.lidc_like_batch(int(g['batch']), seed=int(g['dseed']))
     img = patch[0, 0].contiguous().pin_memory()
     lab = labels[0].contiguous().pin_memory()
-    eager = train.EvalStep(net, 100, 2, use_graph=False)
-    graph = train.EvalStep(net, 100, 2, use_graph=True)
-    torch.manual_seed(3)
-    ge, ne = eager.run_host(img, lab)
-    g1, n1 = graph.run_host(img, lab)
-    g2, n2 = graph.run_host(img, lab)
-    print('\nGED eager %.5f graph %.5f %.5f   NCC eager %.5f graph %.5f %.5f' % (ge, g1, g2, ne, n1, n2))
-    assert all(np.isfinite(v) for v in (ge, g1, g2, ne, n1, n2))
-    assert (g1, n1) != (g2, n2)                       # every replay draws new samples
-    assert abs(g1 - ge) < 0.05 * max(1.0, abs(ge)) + 0.02 and abs(g2 - ge) < 0.05 * max(1.0, abs(ge)) + 0.02
-    assert abs(n1 - ne) < 0.05 and abs(n2 - ne) < 0.05
+    orig = torch.randn_like
+
+    def fake(t, **kw):
+        n = t.numel()
+        return torch.sin(torch.arange(n, device=t.device, dtype=torch.float32) * 12.9898).mul(1.7).reshape(t.shape)
+
+    torch.randn_like = fake
+    try:
+        eager = train.EvalStep(net, 24, 2, use_graph=False)
+        graph = train.EvalStep(net, 24, 2, use_graph=True)
+        ge, ne = eager.run_host(img, lab)
+        g1, n1 = graph.run_host(img, lab)
+        g2, n2 = graph.run_host(img, lab)
+    finally:
+        torch.randn_like = orig
+    print('\nGED eager %.6f graph %.6f %.6f   NCC eager %.6f graph %.6f %.6f' % (ge, g1, g2, ne, n1, n2))
+    assert g1 == ge and g2 == ge
+    assert n1 == pytest.approx(ne, rel=1e-9, abs=1e-12) and n2 == pytest.approx(ne, rel=1e-9, abs=1e-12)
+    real = train.EvalStep(net, 24, 2, use_graph=True)
+    a, b = real.run_host(img, lab), real.run_host(img, lab)
+    assert all(np.isfinite(v) for v in a + b) and a != b        # the graph advances the Philox offset on every replay

@@ -79,14 +79,19 @@ def load():
 SKIP = set()      # measurement aid (tools/family_times.py): entry points whose launches are elided
 
 
+_fn = {}          # entry point name -> bound ctypes function (attribute lookup on the CDLL is not free)
+
+
 def call(name, *args):
     """Invoke an int-status entry point; raises with uz_last_error() on failure."""
     if SKIP and name in SKIP:
         return
-    lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = _fn.get(name)
+    if fn is None:
+        fn = _fn[name] = getattr(load(), name)
+    rc = fn(*args)
     if rc != 0:
-        raise UnetZooLibError('%s failed (%d): %s' % (name, rc, lib.uz_last_error().decode()))
+        raise UnetZooLibError('%s failed (%d): %s' % (name, rc, load().uz_last_error().decode()))
 
 
 def raw(name):

@@ -14,7 +14,10 @@ BN_MOMENTUM = 0.01
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """raw handle of the current CUDA stream.  torch.cuda.current_stream() costs ~14 us of Python per call (device
+    index resolution, availability checks, a Stream object) -- with ~800 launches per eager step that was a third of
+    the host time of the path the unmodified train_model.py takes; the two C calls below cost < 1 us."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _p(t):
@@ -22,21 +25,21 @@ def _p(t):
 
 
 def _check_act(t):
+    """-> (images, H, W, C, pixel stride); a volume [N,D,H,W,C] counts as N*D images.  One shape / stride query each:
+    this runs ~5 times per launch."""
     if not t.is_cuda:
         raise _lib.UnetZooLibError('B200 path needs CUDA tensors (no CPU fallback)')
-    if t.dim() == 5:
-        assert t.dtype == torch.bfloat16 and t.stride(4) == 1, (t.dtype, t.shape, t.stride())
-        n, d, h, w, c = t.shape
-        ld = t.stride(3)
-        assert h == 1 or t.stride(2) == w * ld, t.stride()
-        assert d == 1 or t.stride(1) == h * w * ld, t.stride()
-        assert n == 1 or t.stride(0) == d * h * w * ld, t.stride()
+    sh, st = t.shape, t.stride()
+    if len(sh) == 5:
+        n, d, h, w, c = sh
+        ld = st[3]
+        assert t.dtype == torch.bfloat16 and st[4] == 1, (t.dtype, sh, st)
+        assert (h == 1 or st[2] == w * ld) and (d == 1 or st[1] == h * w * ld) and (n == 1 or st[0] == d * h * w * ld), st
         return n * d, h, w, c, ld
-    assert t.dtype == torch.bfloat16 and t.dim() == 4 and t.stride(3) == 1, (t.dtype, t.shape, t.stride())
-    n, h, w, c = t.shape
-    ld = t.stride(2)
-    assert h == 1 or t.stride(1) == w * ld, t.stride()
-    assert n == 1 or t.stride(0) == h * w * ld, t.stride()
+    assert t.dtype == torch.bfloat16 and len(sh) == 4 and st[3] == 1, (t.dtype, sh, st)
+    n, h, w, c = sh
+    ld = st[2]
+    assert (h == 1 or st[1] == w * ld) and (n == 1 or st[0] == h * w * ld), st
     return n, h, w, c, ld
 
 

@@ -97,5 +97,5 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group['betas']
             _lib.call('uz_adam_step_batched', descs.data_ptr(), tab['nt'], chunks.data_ptr(), nchunks,
                       float(group['lr']), float(b1), float(b2), float(group['eps']), float(group['weight_decay']),
-                      torch.cuda.current_stream().cuda_stream)
+                      torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
         return loss

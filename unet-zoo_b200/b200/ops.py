@@ -59,10 +59,10 @@ def set_concurrency(enabled):
     _aux['planned_for'] = None
 
 
-def _plan_wgrad_share():
-    if _aux.get('planned_for') is not _AUX_ENABLED:       # applied lazily: importing this module never touches the library
-        kern._lib.call('uz_set_wgrad_sm_percent', _WGRAD_SM_PERCENT if _AUX_ENABLED else 100)
-        _aux['planned_for'] = _AUX_ENABLED
+def _plan_wgrad_share(overlapped):
+    if _aux.get('planned_for') is not overlapped:         # applied lazily: importing this module never touches the library
+        kern._lib.call('uz_set_wgrad_sm_percent', _WGRAD_SM_PERCENT if overlapped else 100)
+        _aux['planned_for'] = overlapped
 
 _AUX_STREAMS = max(1, int(_os.environ.get('UNETZOO_AUX_STREAMS', '3')))      # weight-gradient streams (round robin)
 _aux = {'streams': {}, 'pending': [], 'keep': [], 'callback_queued': False, 'next': 0}
@@ -90,8 +90,11 @@ def sync_aux_streams():
 
 def _run_on_aux(fn, keep):
     """run fn() on the auxiliary stream after everything already queued on the current stream"""
-    _plan_wgrad_share()
-    if not _AUX_ENABLED:
+    # Only a captured step is GPU-bound: an eagerly issued step is bound by the host, where the stream switches of this
+    # function (~80 us per layer) cost more than the overlap can return -- eager launches stay on the caller's stream.
+    overlapped = _AUX_ENABLED and torch.cuda.is_current_stream_capturing()
+    _plan_wgrad_share(overlapped)
+    if not overlapped:
         return fn()
     cur = torch.cuda.current_stream()
     st = _aux_stream(keep[0].device)

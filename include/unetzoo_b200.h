@@ -168,6 +168,10 @@ int uz_upsample2x_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int h
  * gradients (models/phiseg.py:71,183,315; models/unet.py:72) and the residual add / inverse of the reversible blocks
  * (revtorch ReversibleBlock: y1 = x1 + F(x2), x2 = y2 - G(y1); torchlayers.py:71-78). */
 int uz_copy_channels(const void* src, int lds, void* dst, int ldd, long long npix, int C, int accumulate, void* stream);
+/* out = a + b (sign >= 0) or a - b (sign < 0) on channel slices in one pass: the coupling y1 = x1 + F(x2) and its inverse
+ * x2 = y2 - G(y1) of the reversible blocks (torchlayers.py:71-78); out may alias a or b. */
+int uz_add_channels(const void* a, int lda, const void* b, int ldb, void* out, int ldo, long long npix, int C, int sign,
+                    void* stream);
 
 /* Global spatial mean [B,hw,C] -> [B,C] (bf16, fp32 accumulation) and its gradient: torch.mean over H then W in front of
  * the ProbUNet Gaussian head (models/probabilistic_unet.py:114-115). */

@@ -23,7 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--multi-stream', action='store_true')
     ap.add_argument('--debug-flags', type=int, default=0)
-    ap.add_argument('--model', default='phiseg', choices=['phiseg', 'phiseg3d'])
+    ap.add_argument('--model', default='phiseg', choices=['phiseg', 'phiseg3d', 'revphiseg'])
     ap.add_argument('--list', default='', help='substring: print every launch of the matching kernels (grid, us)')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'timeline.json'))
     args = ap.parse_args()
@@ -38,7 +38,7 @@ def main():
         batches = bench.synthetic_batches(1, seed=1, volume=128)
     else:
         batch_n, image = bench.BATCH, bench.IMAGE
-        net = dropin_phiseg(bench.FILTERS)
+        net = dropin_phiseg(bench.FILTERS, reversible=args.model == 'revphiseg')
         batches = bench.synthetic_batches(1, seed=1)
     net.load_state_dict(synth.synth_state_dict(net.state_dict(), seed=0))
     net = net.to(dev)

@@ -341,6 +341,16 @@ def copy_channels(src, dst, accumulate=False):
     return dst
 
 
+def add_channels(a, b, out, sign=1):
+    """out = a + b (sign >= 0) or a - b (sign < 0); all three may be channel slices"""
+    n, h, w, c, lda = _check_act(a)
+    ldb = _check_act(b)[4]
+    ldo = _check_act(out)[4]
+    assert a.shape == b.shape == out.shape
+    _lib.call('uz_add_channels', _p(a), lda, _p(b), ldb, _p(out), ldo, n * h * w, c, int(sign), _stream())
+    return out
+
+
 def global_mean_fwd(x):
     n, h, w, c, ldx = _check_act(x)
     out = new_act(n, 1, 1, c, x.device)

@@ -826,6 +826,26 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int 
   }
 }
 
+// out = a + b (sign >= 0) or a - b (sign < 0) on channel slices: the additive coupling of the reversible blocks and its
+// inverse in one pass (y1 = x1 + F(x2), x2 = y2 - G(y1)) instead of a copy followed by an accumulate
+__global__ void add_channels_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b,
+                                    int ldb, __nv_bfloat16* out, int ldo, size_t npix, int C, int sign) {
+  uz::pdl_prologue();
+  const int chunks = C / 8;
+  const size_t total = npix * chunks;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = idx / chunks;
+    const int c0 = static_cast<int>(idx - pix * chunks) * 8;
+    float x[8], y[8];
+    unpack8(*reinterpret_cast<const uint4*>(a + pix * lda + c0), x);
+    unpack8(*reinterpret_cast<const uint4*>(b + pix * ldb + c0), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = sign < 0 ? x[j] - y[j] : x[j] + y[j];
+    *reinterpret_cast<uint4*>(out + pix * ldo + c0) = pack8(x);
+  }
+}
+
 // ---------------------------------------------------------------- global spatial mean (ProbUNet Gaussian heads)
 // out[b][c] = mean over the hw pixels of x[b][:][c]  (torch.mean over H then W, probabilistic_unet.py:114-115)
 __global__ void global_mean_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int hw, int C,
@@ -1173,6 +1193,19 @@ extern "C" int uz_copy_channels(const void* src, int lds, void* dst, int ldd, lo
       static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, static_cast<size_t>(npix), C,
       accumulate);
   UZ_CHECK_LAUNCH("uz_copy_channels");
+  return UZ_OK;
+}
+
+extern "C" int uz_add_channels(const void* a, int lda, const void* b, int ldb, void* out, int ldo, long long npix, int C,
+                               int sign, void* stream) {
+  UZ_CHECK_ARG(a && b && out && C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0 && aligned16(a) &&
+                   aligned16(b) && aligned16(out),
+               "uz_add_channels: bad arguments");
+  if (npix == 0) return UZ_OK;
+  uz::launch(add_channels_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream),
+             static_cast<const __nv_bfloat16*>(a), lda, static_cast<const __nv_bfloat16*>(b), ldb,
+             static_cast<__nv_bfloat16*>(out), ldo, static_cast<size_t>(npix), C, sign);
+  UZ_CHECK_LAUNCH("uz_add_channels");
   return UZ_OK;
 }
 

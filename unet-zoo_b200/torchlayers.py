@@ -135,11 +135,9 @@ class ReversibleBlock(nn.Module):
         y = kern._like(x, c)
         x1, x2, y1, y2 = x[..., :half], x[..., half:], y[..., :half], y[..., half:]
         fx2 = self.f_block(Act(x2, half)).t
-        kern.copy_channels(x1, y1)
-        kern.copy_channels(fx2, y1, accumulate=1)
+        kern.add_channels(x1, fx2, y1)                               # y1 = x1 + F(x2)
         gy1 = self.g_block(Act(y1, half)).t
-        kern.copy_channels(x2, y2)
-        kern.copy_channels(gy1, y2, accumulate=1)
+        kern.add_channels(x2, gy1, y2)                               # y2 = x2 + G(y1)
         return y
 
     def backward_pass(self, y, dy):
@@ -156,18 +154,14 @@ class ReversibleBlock(nn.Module):
         with torch.enable_grad():
             gy1 = self.g_block(Act(y1_leaf, half)).t
         torch.autograd.backward(gy1, dy2)
-        kern.copy_channels(y2, x2)
-        kern.copy_channels(gy1.detach(), x2, accumulate=2)            # x2 = y2 - G(y1)
-        kern.copy_channels(dy1, dx1)
-        kern.copy_channels(ops._dense(y1_leaf.grad), dx1, accumulate=1)   # dx1 = dy1 + dG/dy1
+        kern.add_channels(y2, gy1.detach(), x2, sign=-1)             # x2 = y2 - G(y1)
+        kern.add_channels(dy1, ops._dense(y1_leaf.grad), dx1)        # dx1 = dy1 + dG/dy1
         x2_leaf = x2.detach().requires_grad_(True)
         with torch.enable_grad():
             fx2 = self.f_block(Act(x2_leaf, half)).t
         torch.autograd.backward(fx2, dx1)
-        kern.copy_channels(y1, x1)
-        kern.copy_channels(fx2.detach(), x1, accumulate=2)            # x1 = y1 - F(x2)
-        kern.copy_channels(dy2, dx2)
-        kern.copy_channels(ops._dense(x2_leaf.grad), dx2, accumulate=1)   # dx2 = dy2 + dF/dx2
+        kern.add_channels(y1, fx2.detach(), x1, sign=-1)             # x1 = y1 - F(x2)
+        kern.add_channels(dy2, ops._dense(x2_leaf.grad), dx2)        # dx2 = dy2 + dF/dx2
         return x, dx
 
 

@@ -13,8 +13,7 @@ for (cin, cout, h) in ((128, 128, 128), (192, 192, 64), (32, 32, 128)):
     w = torch.randn(cout, cin, 3, 3, device=dev) * 0.05
     wf, _ = kern.pack_conv_weight(w, need_dgrad=False)
     out = kern.new_act(12, h, h, cout, dev)
-    nt = max(kern.conv_tile_geometry(12, h, h)[3], 148)
-    partial = torch.empty((nt, 2, cout), dtype=torch.float32, device=dev)
+    partial = torch.zeros((2, cout), dtype=torch.float32, device=dev)      # [2][Cout] statistics accumulators
     bias = torch.zeros(cout, device=dev)
     print('shape %d->%d @%d' % (cin, cout, h))
     for flags, name in ((0, 'v2 full'), (1, 'v2 no epilogue'), (2, 'v2 no MMA'), (3, 'v2 no MMA, no epilogue'),

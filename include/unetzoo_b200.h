@@ -168,6 +168,10 @@ int uz_upsample2x_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int h
  * gradients (models/phiseg.py:71,183,315; models/unet.py:72) and the residual add / inverse of the reversible blocks
  * (revtorch ReversibleBlock: y1 = x1 + F(x2), x2 = y2 - G(y1); torchlayers.py:71-78). */
 int uz_copy_channels(const void* src, int lds, void* dst, int ldd, long long npix, int C, int accumulate, void* stream);
+/* dst[p] = src[p % src_npix]: one image's channel slice replicated over a batch of copies (the skip connections of the
+ * N-sample evaluation, whose encoders run once: train_model.py:177-179 feeds N identical copies). */
+int uz_copy_channels_bcast(const void* src, int lds, long long src_npix, void* dst, int ldd, long long npix, int C,
+                           void* stream);
 /* out = a + b (sign >= 0) or a - b (sign < 0) on channel slices in one pass: the coupling y1 = x1 + F(x2) and its inverse
  * x2 = y2 - G(y1) of the reversible blocks (torchlayers.py:71-78); out may alias a or b. */
 int uz_add_channels(const void* a, int lda, const void* b, int ldb, void* out, int ldo, long long npix, int C, int sign,

@@ -335,7 +335,11 @@ def upsample2x_bwd(dout, align_corners=True):
 def copy_channels(src, dst, accumulate=False):
     """accumulate: False/0 copy, True/1 dst += src, 2 dst -= src"""
     n, h, w, c, lds = _check_act(src)
-    ldd = _check_act(dst)[4]
+    nd, _, _, _, ldd = _check_act(dst)
+    if src.shape[0] == 1 and dst.shape[0] > 1 and not accumulate and tuple(src.shape[1:]) == tuple(dst.shape[1:]):
+        # one image replicated over a batch of copies (evaluation with shared encoders)
+        _lib.call('uz_copy_channels_bcast', _p(src), lds, n * h * w, _p(dst), ldd, nd * h * w, c, _stream())
+        return dst
     assert dst.shape == src.shape
     _lib.call('uz_copy_channels', _p(src), lds, _p(dst), ldd, n * h * w, c, int(accumulate), _stream())
     return dst

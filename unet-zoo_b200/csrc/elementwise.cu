@@ -805,7 +805,7 @@ __global__ void up3_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, 
 
 // ---------------------------------------------------------------- strided channel copy / add (concat, split, grad sum)
 __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int lds, __nv_bfloat16* dst, int ldd,
-                                     size_t npix, int C, int accumulate) {
+                                     size_t npix, int C, int accumulate, size_t src_period) {
   uz::pdl_prologue();
   const int chunks = C / 8;
   const size_t total = npix * chunks;
@@ -813,7 +813,8 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, int 
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t pix = idx / chunks;
     const int c0 = static_cast<int>(idx - pix * chunks) * 8;
-    uint4 v = *reinterpret_cast<const uint4*>(src + pix * lds + c0);
+    const size_t spix = src_period ? pix % src_period : pix;     // broadcast of one image over a batch of copies
+    uint4 v = *reinterpret_cast<const uint4*>(src + spix * lds + c0);
     if (accumulate) {          // 1: dst += src, 2: dst -= src
       float a[8], b[8];
       unpack8(v, a);
@@ -1191,8 +1192,21 @@ extern "C" int uz_copy_channels(const void* src, int lds, void* dst, int ldd, lo
   if (npix == 0) return UZ_OK;
   uz::launch(copy_channels_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, static_cast<size_t>(npix), C,
-      accumulate);
+      accumulate, static_cast<size_t>(0));
   UZ_CHECK_LAUNCH("uz_copy_channels");
+  return UZ_OK;
+}
+
+extern "C" int uz_copy_channels_bcast(const void* src, int lds, long long src_npix, void* dst, int ldd, long long npix,
+                                      int C, void* stream) {
+  UZ_CHECK_ARG(src && dst && C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && aligned16(src) && aligned16(dst) &&
+                   src_npix > 0 && npix % src_npix == 0,
+               "uz_copy_channels_bcast: bad arguments");
+  if (npix == 0) return UZ_OK;
+  uz::launch(copy_channels_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8)), kEwThreads, 0, ST(stream),
+      static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, static_cast<size_t>(npix), C, 0,
+      static_cast<size_t>(src_npix));
+  UZ_CHECK_LAUNCH("uz_copy_channels_bcast");
   return UZ_OK;
 }
 

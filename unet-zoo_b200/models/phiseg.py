@@ -432,8 +432,9 @@ class PHISeg(nn.Module):
     def _replicate(x, blocks, n):
         if n == 1:
             return x, blocks
-        rep = lambda a: Act(a.t.expand((n,) + tuple(a.t.shape[1:])).contiguous(), a.c)
-        return rep(x), [rep(b) for b in blocks]
+        # the deepest feature map feeds convolutions and becomes a real batch of n; the skip connections stay single
+        # images -- the concat kernel replicates them while it copies them into the concat buffers (kern.copy_channels)
+        return Act(x.t.expand((n,) + tuple(x.t.shape[1:])).contiguous(), x.c), blocks
 
     def _forward(self, patch, mask, training=True, replicate=1):
         # posterior and prior encoders are independent (no random draws inside): the prior's runs on a second stream.

@@ -211,5 +211,6 @@ if __name__ == '__main__':
     phiseg_case('phiseg_lidc', [32, 64, 128, 192, 192, 192, 192], 2, 2, 4, 6, keep_logits=False)
     phiseg_case('phiseg_rev_small', [32, 64, 64, 64, 64, 64, 64], 4, 1, 3, 5, keep_logits=False, reversible=True)
     phiseg3d_case('phiseg3d_small', [32, 64, 64], 3, 32, 2, 1, 3, 5)
+    phiseg3d_case('phiseg3d_rev_small', [32, 64, 64], 3, 16, 2, 2, 4, 6, reversible=True)
     metrics_case()
     unet_cases()

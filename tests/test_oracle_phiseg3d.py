@@ -13,20 +13,24 @@ from oracle.ref_loader import have_reference
 from tests.keygrammar import dropin_phiseg3d
 
 
-def _case(golden_dir):
-    g = np.load(os.path.join(golden_dir, 'phiseg3d_small.npz'))
+CASES = ['phiseg3d_small', 'phiseg3d_rev_small']
+
+
+def _case(golden_dir, case='phiseg3d_small'):
+    g = np.load(os.path.join(golden_dir, case + '.npz'))
     filters = [int(v) for v in g['filters']]
     L, size, batch = int(g['latent_levels']), int(g['size']), int(g['batch'])
-    net = dropin_phiseg3d(filters, L, (4, size, size, size))
+    net = dropin_phiseg3d(filters, L, (4, size, size, size), reversible=bool(int(g['reversible'])))
     sd = synth.synth_state_dict(net.state_dict(), seed=int(g['wseed']))
     vol, lab = synth.brats_like_batch(batch, size=size, seed=int(g['dseed']))
     eps = synth.noise_list(synth.phiseg3d_noise_shapes(batch, size, L, len(filters)), seed=int(g['nseed']))
     return g, filters, L, sd, vol, lab, eps
 
 
+@pytest.mark.parametrize('case', CASES)
 @pytest.mark.parametrize('training', [True, False])
-def test_oracle_matches_reference_fixture(golden_dir, training):
-    g, filters, L, sd, vol, lab, eps = _case(golden_dir)
+def test_oracle_matches_reference_fixture(golden_dir, training, case):
+    g, filters, L, sd, vol, lab, eps = _case(golden_dir, case)
     key = 'train' if training else 'eval'
     with torch.no_grad():
         out = o3.phiseg3d_forward({k: v.clone() for k, v in sd.items()}, vol, lab, eps, L, len(filters), 3,
@@ -46,8 +50,9 @@ def test_oracle_matches_reference_fixture(golden_dir, training):
     np.testing.assert_allclose(acc[:, :, ::2, ::2, ::2].numpy(), g[key + '_logits_ds2'], rtol=1e-3, atol=2e-4)
 
 
-def test_oracle_gradients_match_reference_fixture(golden_dir):
-    g, filters, L, sd, vol, lab, eps = _case(golden_dir)
+@pytest.mark.parametrize('case', CASES)
+def test_oracle_gradients_match_reference_fixture(golden_dir, case):
+    g, filters, L, sd, vol, lab, eps = _case(golden_dir, case)
     sd2 = {k: v.clone() for k, v in sd.items()}
     params = {k: v.requires_grad_(True) for k, v in sd2.items() if v.dtype == torch.float32 and 'running_' not in k}
     out = o3.phiseg3d_forward(sd2, vol, lab, eps, L, len(filters), 3, training=True)

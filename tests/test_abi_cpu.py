@@ -69,3 +69,28 @@ def test_dropin_state_dict_and_parameter_count():
     assert sum(p.numel() for p in vol.parameters()) == 9265121           # PHISeg3D [32,64,128], L = 3
     rev3 = dropin_phiseg3d([32, 64, 128], 3, (4, 128, 128, 128), reversible=True)
     assert sum(p.numel() for p in rev3.parameters()) == 2455329         # reversible PHISeg3D (phiseg_brats.py:24)
+
+
+def test_fused_adam_state_layout_and_cpu_failure():
+    """b200.optim.FusedAdam keeps torch.optim.Adam's state layout (state_dicts interchange) and, like every product
+    path, refuses CPU parameters instead of falling back."""
+    import torch
+    from tests.gpu_util import PKG  # noqa: F401
+    from b200 import _lib
+    from b200.optim import FusedAdam
+    p_ref = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+    ref = torch.optim.Adam(p_ref, lr=1e-3, weight_decay=1e-5)
+    for p in p_ref:
+        p.grad = torch.randn_like(p)
+    ref.step()
+    p_mine = [torch.nn.Parameter(p.detach().clone()) for p in p_ref]
+    mine = FusedAdam(p_mine, lr=1e-3, weight_decay=1e-5)
+    mine.load_state_dict(ref.state_dict())
+    st = mine.state[p_mine[0]]
+    assert set(st) == {'step', 'exp_avg', 'exp_avg_sq'} and float(st['step']) == 1.0
+    assert torch.equal(st['exp_avg'], ref.state[p_ref[0]]['exp_avg'])
+    assert mine.state_dict()['param_groups'][0]['weight_decay'] == 1e-5
+    for p in p_mine:
+        p.grad = torch.randn_like(p)
+    with pytest.raises(_lib.UnetZooLibError):
+        mine.step()

@@ -46,6 +46,11 @@ class Rounding:
 
 FP32 = Rounding(False)
 
+# baseline arm only (oracle/torch_cuda_arm.py): BatchNorm through torch's own fused kernel (F.batch_norm -> cuDNN / ATen),
+# which is what the reference's nn.BatchNorm2d dispatches to; the default restates it with elementwise ops so that the
+# statistics can be captured and rounding points emulated.
+NATIVE_BN = False
+
 
 def onehot_minus_half(mask, nlabels=2):
     """utils.py:289-311 + models/phiseg.py:176-183: channels k<nlabels = (mask==k) - 0.5."""
@@ -64,6 +69,14 @@ def conv2d_unit(x, sd, prefix, training, rnd=FP32, kernel=3, norm=True, act=True
         beta = sd[prefix + '.convolution.1.bias']
         rm = sd[prefix + '.convolution.1.running_mean']
         rv = sd[prefix + '.convolution.1.running_var']
+        if NATIVE_BN:
+            y = F.batch_norm(y, rm, rv, g, beta, training, BN_MOMENTUM, BN_EPS)
+            if training:
+                nbt = prefix + '.convolution.1.num_batches_tracked'
+                if nbt in sd:
+                    with torch.no_grad():
+                        sd[nbt] += 1
+            return F.relu(y) if act else y
         if training:
             mean = y.mean(dim=(0, 2, 3))
             var = y.var(dim=(0, 2, 3), unbiased=False)

@@ -17,6 +17,33 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}            # group index -> [eager, captured] descriptor / chunk tables (pinned host + device)
 
+    def load_state_dict(self, state_dict):
+        """torch's loader installs NEW tensors in ``self.state``; the descriptor tables (and a captured CUDA graph that
+        replays the launch) hold raw pointers to the old ``exp_avg`` / ``exp_avg_sq`` / ``step`` tensors.  The loaded
+        values are therefore copied INTO the existing state tensors where they exist (pointers stay valid, a captured
+        step keeps working on the restored state); state of parameters that had none yet is new and the eager tables
+        are rebuilt from the pointer key on the next step."""
+        old = {p: dict(st) for p, st in self.state.items() if st}
+        super().load_state_dict(state_dict)
+        for p, st in list(self.state.items()):
+            prev = old.get(p)
+            if not prev or not st:
+                continue
+            for k in ('exp_avg', 'exp_avg_sq', 'step'):
+                if k in st and k in prev and torch.is_tensor(prev[k]) and prev[k].is_cuda:
+                    new = st[k] if torch.is_tensor(st[k]) else torch.as_tensor(float(st[k]))
+                    prev[k].copy_(new.to(device=prev[k].device, dtype=prev[k].dtype).reshape(prev[k].shape))
+                    st[k] = prev[k]
+        for bufs in self._tables.values():
+            bufs[0]['key'] = None              # eager tables: rebuilt on the next step (cheap); captured ones stay valid
+
+    def reset_state(self):
+        """zero the moments and step counters IN PLACE (pointers, hence captured graphs, stay valid)"""
+        for st in self.state.values():
+            for k in ('exp_avg', 'exp_avg_sq', 'step'):
+                if k in st and torch.is_tensor(st[k]):
+                    st[k].zero_()
+
     def _state(self, p):
         st = self.state[p]
         if not st:
@@ -57,9 +84,9 @@ class FusedAdam(torch.optim.Optimizer):
                 g = p.grad
                 if g.dtype != torch.float32 or not g.is_contiguous() or not p.is_contiguous():
                     raise _lib.UnetZooLibError('FusedAdam expects dense fp32 parameters and gradients')
-                key.append(g.data_ptr())
                 rows.append((p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
                              st['step'].data_ptr(), p.numel()))
+                key.append(rows[-1])         # every raw pointer the table holds: a replaced state tensor invalidates it
             key = tuple(key)
             # two persistent table sets per group, allocated on first use (never inside a stream capture): one for eager
             # steps, one for a captured step whose memcpy nodes must keep reading the pointers they were captured with
@@ -78,6 +105,9 @@ class FusedAdam(torch.optim.Optimizer):
                 self._tables[gi] = bufs
             tab = bufs[1 if capturing else 0]
             if tab['key'] != key:
+                if tab.get('uploaded') is not None:
+                    # the previous step's non-blocking upload reads the pinned buffers that are rewritten below
+                    tab['uploaded'].synchronize()
                 raw = b''.join(struct.pack('<QQQQQq', *r) for r in rows)
                 table = []
                 for ti, r in enumerate(rows):
@@ -86,14 +116,22 @@ class FusedAdam(torch.optim.Optimizer):
                 tab['host_d'][:len(raw)] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
                 tab['host_c'][:len(table)] = torch.tensor(table, dtype=torch.int32)
                 tab['key'], tab['n'], tab['nt'] = key, len(table) // 2, len(rows)
+                tab['stale'] = True
             descs, chunks, nchunks = tab['descs'], tab['chunks'], tab['n']
             if capturing:
                 # no memcpy nodes inside a captured step (they break the back-to-back kernel scheduling of the graph):
                 # the tables of a capture are static, finish_capture() uploads them once before the first replay
                 tab['dirty'] = True
-            else:
+            elif tab.get('stale', True):
                 descs.copy_(tab['host_d'], non_blocking=True)
                 chunks.copy_(tab['host_c'], non_blocking=True)
+                if tab.get('uploaded') is None:
+                    tab['uploaded'] = torch.cuda.Event()
+                tab['uploaded'].record()
+                tab['stream'] = torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+                tab['stale'] = False
+            elif tab.get('stream') != torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()):
+                torch.cuda.current_stream().wait_event(tab['uploaded'])      # uploaded on another stream
             b1, b2 = group['betas']
             _lib.call('uz_adam_step_batched', descs.data_ptr(), tab['nt'], chunks.data_ptr(), nchunks,
                       float(group['lr']), float(b1), float(b2), float(group['eps']), float(group['weight_decay']),

@@ -53,8 +53,40 @@ class TrainStep:
         self.opt.step()
         self.loss.copy_(loss.detach())
 
-    def prepare(self, warmup=3):
-        """eager warm-up on a side stream (also sizes every lazily-set kernel attribute), then capture."""
+    def _snapshot(self):
+        """parameters, buffers (BatchNorm running statistics, num_batches_tracked) and optimizer state before the warm-up"""
+        net = {k: v.detach().clone() for k, v in self.net.state_dict().items()}
+        opt = {}
+        for p, st in self.opt.state.items():
+            opt[p] = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+        return net, opt
+
+    def _restore(self, snap):
+        """undo what the warm-up / capture steps did to the model and the optimizer -- IN PLACE, so every pointer a
+        captured graph or a descriptor table holds stays valid.  Optimizer state that did not exist before (first use)
+        is zeroed: the first replayed step is then step 1 from the initial / checkpoint state, like the reference loop."""
+        net, opt = snap
+        with torch.no_grad():
+            for k, v in self.net.state_dict().items():
+                v.copy_(net[k])
+            for p, st in self.opt.state.items():
+                prev = opt.get(p)
+                for k, v in st.items():
+                    if not torch.is_tensor(v):
+                        if prev is not None and k in prev:
+                            st[k] = prev[k]
+                        continue
+                    if prev is not None and k in prev and torch.is_tensor(prev[k]):
+                        v.copy_(prev[k])
+                    else:
+                        v.zero_()
+
+    def prepare(self, warmup=3, keep_state=True):
+        """eager warm-up on a side stream (also sizes every lazily-set kernel attribute), then capture.  The warm-up
+        and capture steps are real optimizer steps on the zero-filled input buffers; with ``keep_state`` (default)
+        the model, its BatchNorm statistics and the optimizer state are restored afterwards, so training starts from
+        the state the caller handed in."""
+        snap = self._snapshot() if keep_state else None
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -81,6 +113,9 @@ class TrainStep:
             self._body()
             self.launches_per_step = _lib.raw('uz_launch_count')() - n0
         torch.cuda.synchronize()
+        if snap is not None:
+            self._restore(snap)
+            torch.cuda.synchronize()
 
     def step_device(self):
         """inputs already resident in self.patch / self.mask"""

@@ -37,6 +37,9 @@ int uz_set_debug_flags(int flags);
 /* Programmatic dependent launch for every kernel of the library (default off; environment UZ_PDL=1 or this call
  * enables it: it helps single-stream execution and hurts the multi-stream overlap the models use, profiles/r01_pdl.md). */
 int uz_set_pdl(int enabled);
+/* Preferred shared-memory carveout (percent of the unified L1 / shared-memory array; -1 = driver default) applied to
+ * every kernel of the library at its next launch.  Environment: UZ_CARVEOUT. */
+int uz_set_smem_carveout(int percent);
 
 /* ---- convolutions on tcgen05 tensor cores (conv_tc.cu, wgrad_tc.cu) ------------------------------------------------ */
 
@@ -59,6 +62,36 @@ int uz_conv_uses_persistent_kernel(int N, int H, int W, int Cin, int Cout, int t
 int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, int taps,
                 void* y, int ldy, const float* scale, const float* shift, int relu, float* stats_partial,
                 void* stream);
+
+/* Optional epilogue extensions of uz_conv_fwd_ex (all fields zero = plain uz_conv_fwd).
+ *  stats_rows   0: stats_partial is [2][Cout], zero on entry, fp32 atomics (summation order across CTAs not fixed);
+ *               1: stats_partial is [uz_conv_stats_rows(...)][2][Cout]; every row is written (not added to) by exactly one
+ *                  CTA and uz_bn_finalize reduces the rows in fixed order -> bit-reproducible training statistics.
+ *  bn_*         fused BatchNorm/ReLU backward of the layer that PRODUCED this conv's forward input (only meaningful when
+ *               the call is an input-gradient, i.e. w_packed is the dgrad packing): with y = that layer's stored
+ *               pre-normalisation output [pixels][Cout] (bn_ldy), a = relu(y*bn_scale + bn_shift) its activation, the
+ *               epilogue stores g = out * [a > 0] (bn_relu) and accumulates sum(g), sum(g*y) per channel into
+ *               bn_sums [2][Cout] (zero on entry) -- the reductions uz_bn_bwd_reduce_sums would compute in a separate
+ *               pass over g and y (reference: autograd of nn.BatchNorm2d + nn.ReLU, torchlayers.py:20-21).
+ *  residual     out = residual + res_sign * value (res_sign = +1 / -1): the additive coupling of a reversible block and
+ *               its inverse, and the gradient accumulation dx1 = dy1 + dF/dx (torchlayers.py:67-82 via revtorch). */
+typedef struct UzConvExtra {
+  int stats_rows;
+  const void* bn_y;
+  int bn_ldy;
+  const float* bn_scale;
+  const float* bn_shift;
+  int bn_relu;
+  float* bn_sums;
+  const void* residual;
+  int ld_res;
+  int res_sign;
+} UzConvExtra;
+int uz_conv_fwd_ex(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, int taps,
+                   void* y, int ldy, const float* scale, const float* shift, int relu, float* stats_partial,
+                   const UzConvExtra* extra, void* stream);
+/* number of statistics rows uz_conv_fwd_ex writes for this shape when extra->stats_rows = 1 */
+int uz_conv_stats_rows(int N, int H, int W, int Cin, int Cout, int taps);
 
 /* Share of the SMs (percent, 5..100, default 100) a 2-D uz_conv_wgrad launch is planned for: callers that overlap
  * weight gradients with other work (auxiliary streams) ask for fewer pixel splits -> fewer partial slabs to reduce.
@@ -252,6 +285,25 @@ int uz_argmax_classes(const float* x, int N, int C, int hw, unsigned char* out, 
  * (0 = int64, 1 = float32, 2 = uint8); work double [(1+M)*hw + M]; out double [1]. */
 int uz_variance_ncc(const float* probs, const void* gt, int gt_dtype, int N, int C, int hw, int M, double* work,
                     double* out, void* stream);
+
+/* Fused N-sample evaluation tail (train_model.py:185-222 after the network), for I images of n samples each (batch index
+ * b = sample * I + image): ONE pass over the L per-level class logits levels[l] = fp32 [n*I][C][(H/f_l)*(W/f_l)] (low
+ * resolution, nearest upsampling by factors[l] is index arithmetic; f = 1 for full-resolution logits) computes
+ * accumulate_output (phiseg.py:428-434, same fp32 order), softmax, argmax -> bit-packed label masks
+ * bits uint32 [I][n][nlabels][ceil(HW/32)] + counts int32 [I][n][nlabels], and sums fp32 [I][2][C][HW] =
+ * (sum_i p_ic, sum_i log(p_ic + 1e-8)) -- everything variance_ncc_dist (utils.py:202-247) needs, additive over samples
+ * and therefore over GPUs (one all-reduce).  part: workspace fp32 [I][uz_eval_sample_groups][2][C][HW].
+ * levels / factors / label_values are [host] arrays. */
+int uz_eval_sample_groups(int n, int I, int hw);
+int uz_eval_sample_stats(const float* const* levels, const int* factors, int L, int n, int I, int C, int H, int W,
+                         const int* label_values, int nlabels, unsigned int* bits, int* counts, float* part,
+                         float* sums, void* stream);
+/* variance_ncc_dist of ONE image from its (all-reduced) sums [2][C][hw] over N samples and the M annotator label maps
+ * gt [M][hw] (dtype 0 = int64, 1 = float32, 2 = uint8; class indices) -> out[0]; with dice_counts != NULL (int32 [3*C]
+ * workspace) also the per-class Dice of argmax_c(mean probs) against annotator `dice_annotator` -> out[1..C]
+ * (train_model.py:207-222 incl. the empty-set conventions; medpy dc).  work: double [(1+M)*hw + M]; out double [1+C]. */
+int uz_ncc_dice_from_sums(const float* sums, const void* gt, int gt_dtype, int N, int C, int hw, int M,
+                          int dice_annotator, double* work, int* dice_counts, double* out, void* stream);
 
 /* ---- volumes: the 3-D clones of models/phiseg3D.py (NDHWC bf16 activations) ------------------------------------------ */
 /* BatchNorm3d, 1x1x1 heads, KL, residual cross-entropy, channel copies and layout conversion are the flat

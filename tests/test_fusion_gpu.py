@@ -1,0 +1,156 @@
+"""Round-2 kernels through the C ABI: the extended conv epilogue (uz_conv_fwd_ex: fused BatchNorm/ReLU-backward
+reduction, residual add, per-CTA statistics rows), deterministic training mode, and the model-level equivalence of the
+fused and unfused backward paths.  Tolerances at each assert."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.gpu_util import bf16r, kern, rel_err, to_nchw, to_nhwc
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# (N, H, W, Cin, Cout): persistent kernel (H, W multiples of 16), generic kernel (small maps), 16-wide epilogue
+EX_SHAPES = [(3, 32, 32, 64, 128), (12, 16, 16, 192, 192), (12, 8, 8, 192, 192), (12, 2, 2, 64, 192), (2, 32, 32, 64, 48),
+             (2, 128, 128, 32, 32)]
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', EX_SHAPES)
+def test_conv_epilogue_fused_bn_backward_sums(N, H, W, Cin, Cout):
+    """dgrad with the producer layer's (y, scale, shift): the stored gradient must equal the plain result times the ReLU
+    mask BIT FOR BIT, and the accumulated (sum g, sum g*y) must match an fp32 reduction of those stored values to 1e-3
+    (fp32 atomics across CTAs: order-dependent rounding only)."""
+    k = kern()
+    dy = to_nhwc(_rand(N, Cin, H, W, seed=1))
+    w = bf16r(_rand(Cin, Cout, 3, 3, seed=2, scale=(2.0 / (Cin * 9)) ** 0.5))      # OIHW of the forward layer Cout -> Cin
+    _, wd = k.pack_conv_weight(w, need_dgrad=True)                                 # dgrad packing [taps][Cout][Cin]
+    y_prev = to_nhwc(_rand(N, Cout, H, W, seed=3))
+    scale, shift = 1 + 0.2 * _rand(Cout, seed=4), 0.3 * _rand(Cout, seed=5)
+    plain, _ = k.conv_fwd(dy, wd)
+    k.zero_arena.reset(dy.device)
+    fused, sums = k.conv_fwd(dy, wd, bn_prev=(y_prev, scale, shift, True))
+    mask = (y_prev.float() * scale + shift) > 0
+    want = torch.where(mask, plain.float(), torch.zeros_like(plain.float()))
+    assert torch.equal(fused.float(), want)
+    s0 = want.sum((0, 1, 2))
+    s1 = (want * y_prev.float()).sum((0, 1, 2))
+    ref_scale = float(want.abs().sum((0, 1, 2)).max())
+    torch.testing.assert_close(sums[0], s0, rtol=1e-3, atol=1e-5 * ref_scale)
+    torch.testing.assert_close(sums[1], s1, rtol=1e-3, atol=1e-5 * ref_scale * float(y_prev.float().abs().max()))
+    # and those sums drive the apply pass to the same dy as the two-launch path
+    gamma = 1 + 0.1 * _rand(Cout, seed=6)
+    mean, invstd = 0.1 * _rand(Cout, seed=7), 1 + 0.1 * _rand(Cout, seed=8).abs()
+    a, da_, db_ = k.bn_relu_bwd_train(fused, y_prev, scale, shift, gamma, mean, invstd, relu=True, sums=sums)
+    b, dg, dbt = k.bn_relu_bwd_train(plain, y_prev, scale, shift, gamma, mean, invstd, relu=True)
+    assert rel_err(a.float(), b.float()) < 2e-3
+    torch.testing.assert_close(da_, dg, rtol=2e-3, atol=2e-3 * float(dg.abs().max()))
+    torch.testing.assert_close(db_, dbt, rtol=2e-3, atol=2e-3 * float(dbt.abs().max()))
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(3, 32, 32, 64, 64), (12, 8, 8, 96, 96)])
+@pytest.mark.parametrize('sign', [1, -1])
+def test_conv_epilogue_residual(N, H, W, Cin, Cout, sign):
+    """out = residual + sign * conv(x): one rounding of the fp32 sum (the unfused path rounds the conv first)."""
+    k = kern()
+    x = bf16r(_rand(N, Cin, H, W, seed=1))
+    w = bf16r(_rand(Cout, Cin, 3, 3, seed=2, scale=(2.0 / (Cin * 9)) ** 0.5))
+    res = bf16r(_rand(N, Cout, H, W, seed=3))
+    wf, _ = k.pack_conv_weight(w, need_dgrad=False)
+    out, _ = k.conv_fwd(to_nhwc(x), wf, residual=to_nhwc(res), res_sign=sign)
+    ref = res + sign * F.conv2d(x, w, padding=1)
+    err = (to_nchw(out) - ref).abs()
+    assert float((err - (ref.abs() * 2 ** -8 + 2e-3 * float(ref.abs().mean()))).max()) <= 0
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(12, 16, 16, 64, 64), (12, 8, 8, 192, 192), (2, 64, 64, 32, 64)])
+def test_deterministic_statistics_rows(N, H, W, Cin, Cout):
+    """per-CTA statistics rows + fixed-order finalize: bit-identical across repeated launches, equal to the atomic
+    accumulators within fp32 rounding."""
+    k = kern()
+    x = to_nhwc(_rand(N, Cin, H, W, seed=1))
+    w = bf16r(_rand(Cout, Cin, 3, 3, seed=2, scale=0.1))
+    wf, _ = k.pack_conv_weight(w, need_dgrad=False)
+    k.zero_arena.reset(x.device)
+    _, acc = k.conv_fwd(x, wf, stats=True)
+    prev = k.set_deterministic(True)
+    try:
+        outs = []
+        for _ in range(3):
+            y, rows = k.conv_fwd(x, wf, stats=True)
+            g, b = torch.ones(Cout, device=DEV), torch.zeros(Cout, device=DEV)
+            outs.append((rows.clone(),) + tuple(t.clone() for t in k.bn_finalize(rows, N * H * W, g, b)))
+    finally:
+        k.set_deterministic(prev)
+    assert outs[0][0].dim() == 3 and outs[0][0].shape[1:] == (2, Cout)
+    for o in outs[1:]:
+        for a, b in zip(o, outs[0]):
+            assert torch.equal(a, b)
+    torch.testing.assert_close(outs[0][0].sum(0), acc[0], rtol=1e-4, atol=1e-2)
+
+
+def _phiseg_step(det, fuse, seed=0, filters=(16, 32, 32, 32, 32, 32, 32), B=4):
+    from b200 import ops, train
+    from oracle import synth
+    from oracle.ref_run import injected_noise
+    from tests.keygrammar import dropin_phiseg
+    k = kern()
+    net = dropin_phiseg(list(filters))
+    net.load_state_dict(synth.synth_state_dict(net.state_dict(), seed=1))
+    net = net.cuda().train()
+    patch, labels, mask = synth.lidc_like_batch(B, seed=3)
+    eps = synth.noise_list(synth.phiseg_noise_shapes(B), seed=5)
+    pd, pf = k.set_deterministic(det), ops.set_fuse_bn_backward(fuse)
+    try:
+        with injected_noise(eps):
+            net.forward(patch.cuda(), mask.cuda(), training=True)
+            loss = net.loss(mask.cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        k.set_deterministic(pd)
+        ops.set_fuse_bn_backward(pf)
+    grads = {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+    stats = {n: b.detach().clone() for n, b in net.named_buffers()}
+    return float(loss), grads, stats
+
+
+def test_deterministic_training_step_is_bit_reproducible():
+    """UNETZOO_DETERMINISTIC: two identical steps give the same loss, gradients and BatchNorm running statistics bit
+    for bit (the atomic path differed by 1.6e-3 run to run)."""
+    l1, g1, s1 = _phiseg_step(True, False)
+    l2, g2, s2 = _phiseg_step(True, False)
+    assert l1 == l2
+    for n in g1:
+        assert torch.equal(g1[n], g2[n]), n
+    for n in s1:
+        assert torch.equal(s1[n], s2[n]), n
+
+
+def test_fused_bn_backward_matches_unfused_step():
+    """model level: the step with the BatchNorm-backward reductions fused into the dgrad epilogues vs the unfused step.
+    Same forward (loss equal to fp32-atomic noise), gradients agree to 2 % relative L2 per tensor (bf16 dgrad chains;
+    the two paths differ only in fp32 summation order of the reductions)."""
+    from b200 import _lib
+    n0 = _lib.raw('uz_launch_count')()
+    l_f, g_f, _ = _phiseg_step(False, True)
+    n1 = _lib.raw('uz_launch_count')()
+    l_u, g_u, _ = _phiseg_step(False, False)
+    n2 = _lib.raw('uz_launch_count')()
+    assert abs(l_f - l_u) <= 2e-3 * abs(l_u)
+    assert (n1 - n0) < (n2 - n1) - 20, 'fusion must remove reduction launches (%d vs %d)' % (n1 - n0, n2 - n1)
+    worst = 0.0
+    for n in g_u:
+        den = float(g_u[n].norm())
+        if den < 1e-6:
+            continue
+        worst = max(worst, float((g_f[n] - g_u[n]).norm()) / den)
+    assert worst < 2e-2, worst

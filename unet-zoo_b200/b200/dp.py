@@ -45,6 +45,22 @@ def shard_counts(n, world):
     return [base + (1 if r < rem else 0) for r in range(world)]
 
 
+def decorrelate_rank_seeds(rank, world, group=None):
+    """Sample-sharded evaluation needs DIFFERENT noise on every rank (identical seeds would evaluate the same samples
+    world times).  If two ranks report the same CUDA generator seed, every rank re-seeds with seed + 7919 * rank."""
+    if world <= 1 or not dist.is_initialized() or not torch.cuda.is_available():
+        return False
+    seed = torch.cuda.initial_seed()
+    t = torch.tensor([seed & 0x7FFFFFFFFFFF], dtype=torch.int64, device='cuda')
+    allv = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allv, t, group=group)
+    seeds = [int(v.item()) for v in allv]
+    if len(set(seeds)) == world:
+        return False
+    torch.cuda.manual_seed(seed + 7919 * rank)
+    return True
+
+
 class _Bucket:
     __slots__ = ('flat', 'params', 'pending', 'work', 'views')
 

@@ -146,8 +146,40 @@ def pack_conv_weight(w, need_dgrad=True):
     return wf, wd
 
 
-def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=False):
-    """x [N,H,W,Cin] bf16, w_packed [taps,Cout,Cin] bf16 -> y [N,H,W,Cout] bf16 (+ stats partial [tiles,2,Cout])."""
+class UzConvExtra(ctypes.Structure):
+    """include/unetzoo_b200.h: UzConvExtra"""
+    _fields_ = [('stats_rows', ctypes.c_int), ('bn_y', ctypes.c_void_p), ('bn_ldy', ctypes.c_int),
+                ('bn_scale', ctypes.c_void_p), ('bn_shift', ctypes.c_void_p), ('bn_relu', ctypes.c_int),
+                ('bn_sums', ctypes.c_void_p), ('residual', ctypes.c_void_p), ('ld_res', ctypes.c_int),
+                ('res_sign', ctypes.c_int)]
+
+
+# Deterministic mode: BatchNorm statistics are written as one row per CTA and reduced in a fixed order (three launches
+# per layer instead of two, no fp32 atomics anywhere in the training step) -> bit-reproducible training.  The default
+# accumulates the statistics with fp32 atomics in CTA-arrival order.  UNETZOO_DETERMINISTIC=1 or set_deterministic(True).
+import os as _os
+_DETERMINISTIC = _os.environ.get('UNETZOO_DETERMINISTIC', '0') == '1'
+
+
+def set_deterministic(enabled):
+    global _DETERMINISTIC
+    prev = _DETERMINISTIC
+    _DETERMINISTIC = bool(enabled)
+    return prev
+
+
+def is_deterministic():
+    return _DETERMINISTIC
+
+
+def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=False, bn_prev=None, residual=None,
+             res_sign=1):
+    """x [N,H,W,Cin] bf16, w_packed [taps,Cout,Cin] bf16 -> y [N,H,W,Cout] bf16 (+ statistics).
+    stats=True: per-channel sum / sum of squares of y, as [1,2,Cout] accumulators or -- deterministic mode -- as one row
+    per CTA [rows,2,Cout].  bn_prev=(y_prev, scale_prev, shift_prev, relu_prev): this call is an input-gradient and its
+    result is the gradient w.r.t. the activation a_prev = relu(y_prev*scale_prev+shift_prev); the epilogue applies that
+    ReLU's mask and accumulates (sum g, sum g*y_prev) -> returned as the second value [2,Cout] (fused BatchNorm backward
+    reduction).  residual: out = residual + res_sign * value."""
     n, h, w, cin, ldx = _check_act(x)
     taps, cout, cin_w = w_packed.shape
     assert cin_w == cin, (cin_w, cin)
@@ -155,8 +187,32 @@ def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=Fa
         out = _like(x, cout)
     _, _, _, _, ldy = _check_act(out)
     partial = None
+    extra = None
     if stats:
-        partial = zero_arena.get(2 * cout, x.device).view(1, 2, cout)      # [2][Cout] accumulators, zero on entry
+        if _DETERMINISTIC and x.dim() == 4:
+            rows = _lib.raw('uz_conv_stats_rows')(n, h, w, cin, cout, taps)
+            partial = torch.empty((rows, 2, cout), dtype=torch.float32, device=x.device)
+            extra = UzConvExtra(stats_rows=1)
+        else:
+            partial = zero_arena.get(2 * cout, x.device).view(1, 2, cout)      # [2][Cout] accumulators, zero on entry
+    keep = None
+    if bn_prev is not None or residual is not None:
+        assert x.dim() == 4 and not stats
+        extra = extra or UzConvExtra()
+        if bn_prev is not None:
+            y_prev, sc_prev, sh_prev, relu_prev = bn_prev
+            assert y_prev.shape[:-1] == out.shape[:-1] and y_prev.shape[-1] >= cout
+            partial = zero_arena.get(2 * cout, x.device).view(2, cout)
+            extra.bn_y, extra.bn_ldy = y_prev.data_ptr(), _check_act(y_prev)[4]
+            extra.bn_scale, extra.bn_shift, extra.bn_relu = sc_prev.data_ptr(), sh_prev.data_ptr(), int(relu_prev)
+            extra.bn_sums = partial.data_ptr()
+        if residual is not None:
+            assert residual.shape == out.shape
+            extra.residual, extra.ld_res, extra.res_sign = residual.data_ptr(), _check_act(residual)[4], int(res_sign)
+    if extra is not None:
+        _lib.call('uz_conv_fwd_ex', _p(x), n, h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy, _p(scale),
+                  _p(shift), int(relu), None if bn_prev is not None else _p(partial), ctypes.byref(extra), _stream())
+        return out, partial
     if x.dim() == 5:
         _lib.call('uz_conv3d_fwd', _p(x), x.shape[0], x.shape[1], h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy,
                   _p(scale), _p(shift), int(relu), _p(partial), _stream())
@@ -214,15 +270,17 @@ def bn_apply_train(y, sums, count, gamma, beta, running_mean, running_var, relu=
     return out, st[0], st[1], st[2], st[3]
 
 
-def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True):
-    """two launches (accumulate, apply) -> dy bf16, dgamma, dbeta"""
+def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True, sums=None):
+    """two launches (accumulate, apply) -> dy bf16, dgamma, dbeta; with ``sums`` ([2,C]: sum g, sum g*y, already
+    accumulated by the dgrad epilogue that produced ``dout``) only the apply pass runs"""
     n, h, w, c, ldd = _check_act(dout)
     ldy = _check_act(y)[4]
     npix = n * h * w
     dev = y.device
-    sums = zero_arena.get(2 * c, dev)
-    _lib.call('uz_bn_bwd_reduce_sums', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), npix, c, _p(sums),
-              _stream())
+    if sums is None:
+        sums = zero_arena.get(2 * c, dev)
+        _lib.call('uz_bn_bwd_reduce_sums', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), npix, c, _p(sums),
+                  _stream())
     dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
     dy = _like(y, c)
     _lib.call('uz_bn_bwd_apply_train', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), _p(sums), float(npix),
@@ -336,8 +394,9 @@ def copy_channels(src, dst, accumulate=False):
     """accumulate: False/0 copy, True/1 dst += src, 2 dst -= src"""
     n, h, w, c, lds = _check_act(src)
     nd, _, _, _, ldd = _check_act(dst)
-    if src.shape[0] == 1 and dst.shape[0] > 1 and not accumulate and tuple(src.shape[1:]) == tuple(dst.shape[1:]):
-        # one image replicated over a batch of copies (evaluation with shared encoders)
+    if dst.shape[0] > src.shape[0] and dst.shape[0] % src.shape[0] == 0 and not accumulate and \
+            tuple(src.shape[1:]) == tuple(dst.shape[1:]):
+        # I images replicated over a batch of copies, dst image index = copy * I + image (evaluation with shared encoders)
         _lib.call('uz_copy_channels_bcast', _p(src), lds, n * h * w, _p(dst), ldd, nd * h * w, c, _stream())
         return dst
     assert dst.shape == src.shape
@@ -543,6 +602,70 @@ def ged(samples, gts, label_values):
     out = torch.empty((4,), dtype=torch.float64, device=dev)
     _lib.call('uz_ged_pairwise', _p(bits_s), _p(cnt_s), n, _p(bits_y), _p(cnt_y), m, nl, hw, _p(pair_d), _p(out),
               _stream())
+    return out
+
+
+def eval_sample_stats(levels, factors, n, images, n_classes, hw_shape, label_values, out=None):
+    """levels: L fp32 tensors [n*images, C, h_l, w_l] (batch index = sample * images + image), factors: H / h_l.
+    -> bits int32 [images, n, nl, words], counts int32 [images, n, nl], sums fp32 [images, 2, C, H*W]
+    (``out`` = (flat int32 buffer holding bits then counts, sums) lets the caller own the buffers, e.g. for collectives)"""
+    H, W = hw_shape
+    hw = H * W
+    nl = len(label_values)
+    words = (hw + 31) // 32
+    dev = levels[0].device
+    levels = [t.contiguous() for t in levels]
+    for t, f in zip(levels, factors):
+        assert t.dtype == torch.float32 and t.shape[0] == n * images and t.shape[1] == n_classes and \
+            t.shape[2] * f == H and t.shape[3] * f == W, (tuple(t.shape), f)
+    if out is None:
+        flat = torch.empty((images * n * nl * (words + 1),), dtype=torch.int32, device=dev)
+        sums = torch.empty((images, 2, n_classes, hw), dtype=torch.float32, device=dev)
+    else:
+        flat, sums = out
+    nb = images * n * nl * words
+    bits = flat[:nb].view(images, n, nl, words)
+    counts = flat[nb:nb + images * n * nl].view(images, n, nl)
+    G = _lib.raw('uz_eval_sample_groups')(n, images, hw)
+    part = torch.empty((images, G, 2, n_classes, hw), dtype=torch.float32, device=dev)
+    lv = (ctypes.c_int * nl)(*[int(v) for v in label_values])
+    fa = (ctypes.c_int * len(factors))(*[int(f) for f in factors])
+    _lib.call('uz_eval_sample_stats', _ptr_array(levels), fa, len(levels), n, images, n_classes, H, W, lv, nl, _p(bits),
+              _p(counts), _p(part), _p(sums), _stream())
+    return bits, counts, sums
+
+
+def ged_from_bits(bits_s, cnt_s, gts, label_values, hw):
+    """bits_s int32 [N, nl, words] / cnt_s [N, nl] (eval_sample_stats) vs ground-truth label maps gts [M, H, W]
+    -> double [4] = GED, sum d_sy, sum d_ss, sum d_yy (bit-identical to the reference's loops)"""
+    n, nl, words = bits_s.shape
+    m = gts.shape[0]
+    dev = bits_s.device
+    gts = gts.contiguous()
+    lv = (ctypes.c_int * nl)(*[int(v) for v in label_values])
+    bits_y = torch.empty((m, nl, words), dtype=torch.int32, device=dev)
+    cnt_y = torch.empty((m, nl), dtype=torch.int32, device=dev)
+    _lib.call('uz_ged_pack_masks', _p(gts), _DTYPE_CODE[gts.dtype], m, hw, lv, nl, _p(bits_y), _p(cnt_y), _stream())
+    pair_d = torch.empty((n * m + n * n + m * m,), dtype=torch.float64, device=dev)
+    out = torch.empty((4,), dtype=torch.float64, device=dev)
+    _lib.call('uz_ged_pairwise', _p(bits_s), _p(cnt_s), n, _p(bits_y), _p(cnt_y), m, nl, hw, _p(pair_d), _p(out),
+              _stream())
+    return out
+
+
+def ncc_dice_from_sums(sums, gts, n_total, dice_annotator=-1, out=None):
+    """sums fp32 [2, C, HW] over n_total samples, gts [M, H, W] label maps -> double [1 + C] = NCC, per-class Dice of
+    argmax(mean probs) vs annotator ``dice_annotator`` (NaN-free only when dice_annotator >= 0)"""
+    _, c, hw = sums.shape
+    m = gts.shape[0]
+    dev = sums.device
+    gts = gts.contiguous()
+    work = torch.empty(((1 + m) * hw + m,), dtype=torch.float64, device=dev)
+    dcnt = torch.empty((3 * c,), dtype=torch.int32, device=dev) if dice_annotator >= 0 else None
+    if out is None:
+        out = torch.zeros((1 + c,), dtype=torch.float64, device=dev)
+    _lib.call('uz_ncc_dice_from_sums', _p(sums), _p(gts), _DTYPE_CODE[gts.dtype], n_total, c, hw, m, int(dice_annotator),
+              _p(work), _p(dcnt), _p(out), _stream())
     return out
 
 

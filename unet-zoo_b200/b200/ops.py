@@ -148,11 +148,42 @@ def from_act(a):
 
 
 # ------------------------------------------------------------------------------------------------ conv (+BN) (+ReLU)
+# Fusing the BatchNorm-backward reduction of layer L into the input-gradient conv of layer L+1 (opt-in: UNETZOO_FUSE_BN_BWD=1;
+# measured on B200 it removes 57 launches from the PHiSeg step but the extra y loads lengthen the epilogue-bound dgrad
+# kernels by more than the removed reductions cost: 5.07 ms vs 4.96 ms per step, profiles/r02_knobs.md):
+# ConvBNAct.forward tags its output tensor with (y, scale, shift, relu); a ConvBNAct that consumes a tagged tensor asks its
+# dgrad launch to mask the result with that ReLU and to accumulate (sum g, sum g*y) in the epilogue, and tags the gradient
+# it returns with those sums.  The producer's backward uses them only if the very same tensor arrives unmodified (autograd
+# accumulates gradients of multi-consumer tensors in place: the version counter tells) -- otherwise it runs the separate
+# reduction kernel as before.  The mask is idempotent, so a masked gradient is always safe to hand on.
+_FUSE_BN_BWD = _os.environ.get('UNETZOO_FUSE_BN_BWD', '0') == '1'
+
+
+def set_fuse_bn_backward(enabled):
+    global _FUSE_BN_BWD
+    prev = _FUSE_BN_BWD
+    _FUSE_BN_BWD = bool(enabled)
+    return prev
+
+
+def _fused_sums_of(da, c):
+    tag = getattr(da, '_uz_sums', None)
+    if tag is None:
+        return None
+    sums, version, ptr = tag
+    if da._version != version or da.data_ptr() != ptr or sums.shape[-1] != c:
+        return None
+    return sums
+
+
 class ConvBNAct(torch.autograd.Function):
     """Conv2D of the reference (torchlayers.py:7-29): conv(k=3 pad 1 | k=1) + bias -> BatchNorm(train) -> ReLU.
 
     forward (training): tcgen05 conv with statistics epilogue -> uz_bn_apply_train (finalize + normalise + ReLU).
-    backward: two-launch BN/ReLU backward -> dgrad (same conv kernel, flipped weights) + tcgen05 wgrad.
+    backward: BN/ReLU backward (reduction fused into the consumer's dgrad epilogue when possible, else its own launch;
+    then the apply pass) -> dgrad (same conv kernel, flipped weights) + tcgen05 wgrad.
+    Deterministic mode (kern.set_deterministic): statistics as per-CTA rows reduced in fixed order by uz_bn_finalize /
+    uz_bn_bwd_finalize, no atomics, no fusion.
     The conv bias gets a zero gradient: BatchNorm removes any per-channel constant, d loss / d bias == 0 exactly.
     """
 
@@ -162,22 +193,47 @@ class ConvBNAct(torch.autograd.Function):
         wf, wd = kern.pack_conv_weight(weight, need_dgrad=need_dx)
         y, sums = kern.conv_fwd(x, wf, shift=bias, stats=True)
         npix = kern._spatial_numel(x.shape[:-1])
-        a, scale, shift, mean, invstd = kern.bn_apply_train(y, sums, npix, gamma, beta, running_mean, running_var,
-                                                            relu=relu)
-        ctx.save_for_backward(x, y, wd, scale, shift, mean, invstd, gamma)
+        ctx.det = kern.is_deterministic() and x.dim() == 4
+        if ctx.det:
+            scale, shift, mean, invstd = kern.bn_finalize(sums, npix, gamma, beta, running_mean, running_var)
+            a = kern.affine_act(y, scale, shift, relu=relu)
+        else:
+            a, scale, shift, mean, invstd = kern.bn_apply_train(y, sums, npix, gamma, beta, running_mean, running_var,
+                                                                relu=relu)
+        src = getattr(x, '_uz_bn', None) if (need_dx and _FUSE_BN_BWD and not ctx.det and x.dim() == 4) else None
+        ctx.fuse_src = src is not None
+        if src is not None:
+            ctx.save_for_backward(x, y, wd, scale, shift, mean, invstd, gamma, src[0], src[1], src[2])
+            ctx.src_relu = src[3]
+        else:
+            ctx.save_for_backward(x, y, wd, scale, shift, mean, invstd, gamma)
         ctx.relu = relu
         ctx.cin_logical = cin_logical
         ctx.wshape = weight.shape
+        if _FUSE_BN_BWD and not ctx.det and x.dim() == 4:
+            a._uz_bn = (y, scale, shift, relu)
         return a
 
     @staticmethod
     def backward(ctx, da):
-        x, y, wd, scale, shift, mean, invstd, gamma = ctx.saved_tensors
-        da = _dense(da)
-        dy, dgamma, dbeta = kern.bn_relu_bwd_train(da, y, scale, shift, gamma, mean, invstd, relu=ctx.relu)
+        if ctx.fuse_src:
+            x, y, wd, scale, shift, mean, invstd, gamma, y_prev, sc_prev, sh_prev = ctx.saved_tensors
+        else:
+            x, y, wd, scale, shift, mean, invstd, gamma = ctx.saved_tensors
+        sums = _fused_sums_of(da, y.shape[-1])
+        if sums is None:
+            da = _dense(da)
+        if ctx.det:
+            dy, dgamma, dbeta = kern.bn_relu_bwd(da, y, scale, shift, gamma, mean, invstd, relu=ctx.relu)
+        else:
+            dy, dgamma, dbeta = kern.bn_relu_bwd_train(da, y, scale, shift, gamma, mean, invstd, relu=ctx.relu, sums=sums)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx, _ = kern.conv_fwd(dy, wd)
+            if ctx.fuse_src:
+                dx, psums = kern.conv_fwd(dy, wd, bn_prev=(y_prev, sc_prev, sh_prev, ctx.src_relu))
+                dx._uz_sums = (psums, dx._version, dx.data_ptr())
+            else:
+                dx, _ = kern.conv_fwd(dy, wd)
         cout, cin = ctx.wshape[0], ctx.wshape[1]
         taps = kern._spatial_numel(ctx.wshape[2:])
         dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, taps, cin, cout), (x, dy)).view(ctx.wshape)

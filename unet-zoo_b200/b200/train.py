@@ -135,27 +135,48 @@ class TrainStep:
 
 
 class EvalStep:
-    """One validation image like train_model.py:177-205: N copies -> forward(training=False) -> accumulate_output
-    (softmax) -> argmax -> GED + NCC against M annotators.  ``shard`` = (rank, world) splits the N samples.
-    ``run_host`` replays a CUDA graph of the whole evaluation (eager it is host-bound: ~350 launches from Python take
-    twice as long as the kernels they start); ``run_device`` is the eager path through the drop-in ``utils`` functions."""
+    """N-sample evaluation like train_model.py:177-222 for I images per call: N copies of every image ->
+    forward(training=False) -> accumulate_output(softmax) -> argmax -> GED + NCC against M annotators + Dice of the mean
+    prediction, as ONE fused tail kernel over the low-resolution level logits (uz_eval_sample_stats: accumulate, softmax,
+    argmax -> bit-packed masks, per-pixel sum p / sum log p).
 
-    def __init__(self, net, n_samples=100, n_classes=2, shard=None, dedup=True, use_graph=True):
+    ``shard`` = (rank, world) splits the N samples of every image over the ranks (13,13,13,13,12,12,12,12 for N=100 on 8
+    GPUs).  The exchange is what the survey specifies: ONE all-gather of the bit-packed masks (+ their
+    pixel counts; 2 KB per sample) and ONE all-reduce of the per-pixel sums (2*C*H*W floats per image); the metrics of
+    image i are then computed by rank i % world only (no redundant work; results stay on the owning rank unless
+    ``gather_results``).  ``images_per_step`` > 1 keeps every GPU busy when N / world is small: the encoders run on I
+    images, the latent / likelihood path on I * N / world samples.  Ranks must draw DIFFERENT noise: the constructor
+    offsets the CUDA generator by the rank when all ranks were seeded alike.
+
+    ``run_host`` replays a CUDA graph of the whole evaluation; ``fused=False`` is the reference-shaped path through the
+    module API and the drop-in ``utils`` functions (full-resolution logits, softmax tensor, argmax)."""
+
+    def __init__(self, net, n_samples=100, n_classes=2, shard=None, dedup=True, use_graph=True, images_per_step=1,
+                 fused=True, gather_results=False):
         self.net = net
         self.dedup = dedup
         self.use_graph = use_graph
+        self.fused = fused and dedup
+        self.gather_results = gather_results
         self.n = n_samples
         self.n_classes = n_classes
+        self.images = images_per_step
         self.counts = None
+        self.rank, self.world = 0, 1
         self.n_local = n_samples
         if shard is not None and shard[1] > 1:
             from . import dp
-            self.counts = dp.shard_counts(n_samples, shard[1])
-            self.n_local = self.counts[shard[0]]
+            self.rank, self.world = shard
+            self.counts = dp.shard_counts(n_samples, self.world)
+            self.n_local = self.counts[self.rank]
+            dp.decorrelate_rank_seeds(self.rank, self.world)
+        if not self.fused and images_per_step != 1:
+            raise ValueError('images_per_step > 1 needs the fused evaluation path')
         self.graph = None
         self._shape = None
         net.eval()
 
+    # ------------------------------------------------------------------------------------------ reference-shaped path
     def _forward_probs(self, img, masks):
         if self.dedup:
             # the N copies are identical: the encoders run once, latent sampling and likelihood on all copies
@@ -170,57 +191,117 @@ class EvalStep:
             probs = dp.gather_samples(probs.contiguous(), self.counts)
         return probs
 
+    # ------------------------------------------------------------------------------------------ fused path
+    def _fused_body(self):
+        """everything on the device; results into self.out [I, 2 + C] doubles (GED, NCC, Dice per class; rows of images
+        owned by other ranks stay NaN unless gather_results); no host synchronisation"""
+        I, C, n = self.images, self.n_classes, self.n_local
+        H, W = self.img.shape[-2:]
+        hw = H * W
+        masks = self.lab.permute(0, 3, 1, 2).contiguous()                 # [I, M, H, W] uint8
+        pairs = self.net.forward(self.img[:, None], masks[:, 0:1].float(), training=False, replicate=n, lowres_logits=True)
+        levels, factors = [p[0] for p in pairs], [p[1] for p in pairs]
+        labels = list(range(1, C))
+        nmax = max(self.counts) if self.counts is not None else n
+        nl = len(labels)
+        words = (hw + 31) // 32
+        bits, cnts, sums = kern.eval_sample_stats(levels, factors, n, I, C, (H, W), labels, out=(self.flat, self.sums))
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.flat_all, self.flat)          # masks + counts: 2 KB per sample
+            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM)               # per-pixel sum p, sum log p
+            nb = I * n * nl * words
+            bl, cl = [], []
+            for r in range(self.world):
+                # every rank laid its buffer out for ITS sample count; the all-gather needs equal sizes, so the buffers
+                # are sized for nmax samples and rank r's rows beyond counts[r] are padding
+                nr = self.counts[r]
+                row = self.flat_all[r]
+                bl.append(row[:I * nr * nl * words].view(I, nr, nl, words))
+                cl.append(row[I * nr * nl * words:I * nr * nl * (words + 1)].view(I, nr, nl))
+            bits, cnts = torch.cat(bl, dim=1), torch.cat(cl, dim=1)
+        self.out.fill_(float('nan'))
+        for i in range(I):
+            if i % self.world != self.rank:
+                continue
+            ged4 = kern.ged_from_bits(bits[i].contiguous(), cnts[i].contiguous(), masks[i], labels, hw)
+            self.out[i, 0:1].copy_(ged4[0:1])
+            kern.ncc_dice_from_sums(self.sums[i], masks[i], self.n, dice_annotator=0, out=self.out[i, 1:])
+        if self.gather_results and self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.out_all, self.out)
+            for i in range(I):
+                self.out[i].copy_(self.out_all[i % self.world, i])
+
     def _device_body(self):
-        """everything on the device, results into self.out (double [2] = GED, NCC); no host synchronisation"""
-        masks = self.lab.permute(2, 0, 1).float()                  # [M,H,W]
-        probs = self._forward_probs(self.img, masks)
+        if self.fused:
+            return self._fused_body()
+        # results into self.out (double [1, 2] = GED, NCC); no host synchronisation
+        masks = self.lab[0].permute(2, 0, 1).float()               # [M,H,W]
+        probs = self._forward_probs(self.img[0], masks)
         pred = kern.argmax_classes(probs)                          # torch.argmax(dim=1) of train_model.py:195
         ged4 = kern.ged(pred, masks, list(range(1, self.n_classes)))
         ks = torch.arange(self.n_classes, device=masks.device, dtype=masks.dtype).view(1, self.n_classes, 1, 1)
         onehot = (masks.unsqueeze(1) == ks).long()                 # utils.convert_batch_to_onehot
         ncc = kern.variance_ncc(probs, onehot)
-        self.out[0:1].copy_(ged4[0:1])
-        self.out[1:2].copy_(ncc)
+        self.out.fill_(float('nan'))
+        self.out[0, 0:1].copy_(ged4[0:1])
+        self.out[0, 1:2].copy_(ncc)
 
     def _prepare(self, image, labels):
         dev = torch.device('cuda', torch.cuda.current_device())
-        self.img = torch.zeros(tuple(image.shape), dtype=torch.float32, device=dev)
-        self.lab = torch.zeros(tuple(labels.shape), dtype=labels.dtype, device=dev)
-        self.out = torch.zeros(2, dtype=torch.float64, device=dev)
-        self.out_host = torch.zeros(2, dtype=torch.float64).pin_memory()
-        self.img.copy_(image)
-        self.lab.copy_(labels)
-        s = torch.cuda.Stream(device=dev)
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s), torch.no_grad():
-            for _ in range(2):
+        I, C = self.images, self.n_classes
+        H, W = image.shape[-2:]
+        self.img = torch.zeros((I, H, W), dtype=torch.float32, device=dev)
+        self.lab = torch.zeros((I, H, W, labels.shape[-1]), dtype=labels.dtype, device=dev)
+        self.out = torch.zeros((I, 2 + C), dtype=torch.float64, device=dev)
+        self.out_all = torch.zeros((self.world, I, 2 + C), dtype=torch.float64, device=dev)
+        self.out_host = torch.zeros((I, 2 + C), dtype=torch.float64).pin_memory()
+        nmax = max(self.counts) if self.counts is not None else self.n_local
+        words = (H * W + 31) // 32
+        per_rank = I * nmax * (C - 1) * (words + 1)
+        self.flat = torch.zeros((per_rank,), dtype=torch.int32, device=dev)
+        self.flat_all = torch.zeros((self.world, per_rank), dtype=torch.int32, device=dev)
+        self.sums = torch.zeros((I, 2, C, H * W), dtype=torch.float32, device=dev)
+        self.img.copy_(image.reshape(I, H, W))
+        self.lab.copy_(labels.reshape(self.lab.shape))
+        if self.use_graph:
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s), torch.no_grad():
+                for _ in range(2):
+                    self._device_body()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.raw('uz_launch_count')()
+            with torch.no_grad(), torch.cuda.graph(self.graph):
                 self._device_body()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
-            self._device_body()
-        torch.cuda.synchronize()
+            self.launches_per_step = _lib.raw('uz_launch_count')() - n0
+            torch.cuda.synchronize()
         self._shape = (tuple(image.shape), tuple(labels.shape), labels.dtype)
 
     @torch.no_grad()
     def run_host(self, image_pinned, labels_pinned):
-        """image [H,W] fp32, labels [H,W,M] uint8 (host, pinned) -> (ged float, ncc float)"""
-        if not self.use_graph:
-            import utils  # the drop-in second boundary
-            dev = torch.device('cuda', torch.cuda.current_device())
-            return self.run_device(image_pinned.to(dev, non_blocking=True), labels_pinned.to(dev, non_blocking=True), utils)
-        if self.graph is None or self._shape != (tuple(image_pinned.shape), tuple(labels_pinned.shape), labels_pinned.dtype):
+        """image [H,W] or [I,H,W] fp32, labels [H,W,M] or [I,H,W,M] uint8 (host, pinned) -> for one image (ged, ncc);
+        for I > 1 a float64 tensor [I, 2 + C] (GED, NCC, Dice per class; NaN rows = images owned by another rank)."""
+        if self._shape != (tuple(image_pinned.shape), tuple(labels_pinned.shape), labels_pinned.dtype):
             self._prepare(image_pinned, labels_pinned)
-        self.img.copy_(image_pinned, non_blocking=True)
-        self.lab.copy_(labels_pinned, non_blocking=True)
-        self.graph.replay()
+        self.img.copy_(image_pinned.reshape(self.img.shape), non_blocking=True)
+        self.lab.copy_(labels_pinned.reshape(self.lab.shape), non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._device_body()
         self.out_host.copy_(self.out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return float(self.out_host[0]), float(self.out_host[1])
+        if image_pinned.dim() == 2:
+            return float(self.out_host[0, 0]), float(self.out_host[0, 1])
+        return self.out_host.clone()
 
     @torch.no_grad()
     def run_device(self, img, lab, utils=None):
+        """eager, through the drop-in ``utils`` functions (the second boundary): one image [H,W], labels [H,W,M]"""
         if utils is None:
             import utils
         masks = lab.permute(2, 0, 1).float()                       # [M,H,W]

@@ -13,7 +13,19 @@
 #define UZ_ERR_CUDA 2
 #define UZ_ERR_DRIVER 3
 
+// Profiling knobs (uz_set_debug_flags): bits that elide loads / MMAs / epilogues / whole launches produce garbage and
+// exist only in builds with -DUZ_PROFILE_KNOBS (make PROFILE=1).  The product library keeps bit 32 alone (route 3x3 layers
+// to the generic kernel: correct results, used by the kernel-vs-kernel parity test).
+#ifdef UZ_PROFILE_KNOBS
+#define UZ_KNOB(bits) (uz::g_conv_debug_flags & (bits))
+#define UZ_DBG(p, bits) ((p).dbg & (bits))
+#else
+#define UZ_KNOB(bits) (uz::g_conv_debug_flags & (bits) & 32)
+#define UZ_DBG(p, bits) 0
+#endif
+
 namespace uz {
+extern int g_conv_debug_flags;
 
 // last error text, readable through uz_last_error()
 void set_error(const char* fmt, ...);
@@ -218,10 +230,12 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // ---------------------------------------------------------------- host side: launches and tensor maps
 namespace uz {
 extern int g_pdl;   // uz_set_pdl(); default from the environment variable UZ_PDL (0)
+void prepare_kernel(const void* fn);   // once per kernel: shared-memory carveout preference (uz_set_smem_carveout)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                           Args&&... args) {
+  prepare_kernel(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -20,7 +20,8 @@ namespace uz {
 int g_conv_debug_flags = 0;
 int conv2_stats_rows(int N, int H, int W, int Cin, int Cout);
 int conv2_launch(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, void* y, int ldy,
-                 const float* scale, const float* shift, int relu, float* stats_partial, void* stream, int* handled);
+                 const float* scale, const float* shift, int relu, float* stats_partial, const UzConvExtra* ex, void* stream,
+                 int* handled);
 }  // namespace uz
 
 namespace {
@@ -45,6 +46,16 @@ struct ConvParams {
   const float* scale;  // [Cout] or nullptr (=1)
   const float* shift;  // [Cout] or nullptr (=0)
   float* stats;        // [2][Cout] accumulators (zero on entry, atomically added to) or nullptr
+  int stats_rows;      // 1: stats is [tiles][2][Cout], row = this CTA's tile, plain stores (fixed summation order)
+  // UzConvExtra: fused BatchNorm/ReLU backward statistics of the producer layer, residual (see conv_tc2.cu)
+  const __nv_bfloat16* bn_y;
+  const float* bn_scale;
+  const float* bn_shift;
+  float* bn_sums;
+  int bn_ldy, bn_relu;
+  const __nv_bfloat16* res;
+  int ld_res;
+  float res_sign;
   int dbg;             // profiling knobs (uz_set_debug_flags): 1 = no epilogue body, 2 = no MMA, 4 = no A loads, 8 = no B loads
 };
 
@@ -63,6 +74,17 @@ __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
     }
   }
   return v[0];
+}
+
+__device__ __forceinline__ void load_row16(const __nv_bfloat16* src, float* out) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + j);
+    out[j * 8 + 0] = uz::bf16lo(q.x); out[j * 8 + 1] = uz::bf16hi(q.x);
+    out[j * 8 + 2] = uz::bf16lo(q.y); out[j * 8 + 3] = uz::bf16hi(q.y);
+    out[j * 8 + 4] = uz::bf16lo(q.z); out[j * 8 + 5] = uz::bf16hi(q.z);
+    out[j * 8 + 6] = uz::bf16lo(q.w); out[j * 8 + 7] = uz::bf16hi(q.w);
+  }
 }
 
 template <int KC, int KB>
@@ -85,6 +107,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   __shared__ float s_scale[256];
   __shared__ float s_shift[256];
   __shared__ float s_stats[4][2][256];
+  __shared__ float s_scale2[256];
+  __shared__ float s_shift2[256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -123,6 +147,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   for (int c = threadIdx.x; c < p.BN; c += kThreads) {
     s_scale[c] = p.scale ? p.scale[c_out0 + c] : 1.f;
     s_shift[c] = p.shift ? p.shift[c_out0 + c] : 0.f;
+    s_scale2[c] = p.bn_y ? p.bn_scale[c_out0 + c] : 1.f;
+    s_shift2[c] = p.bn_y ? p.bn_shift[c_out0 + c] : 0.f;
   }
   uz::tc_fence_before();
   __syncthreads();
@@ -140,11 +166,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         int dy = 0, dx = 0;
         if (p.taps == 9) { dx = tap / 3 - 1; dy = tap % 3 - 1; }   // packed taps are dx-major (see uz_pack_conv_weight)
         if (uz::elect_one()) {
-          uz::mbar_expect_tx(&full_bar[s], ((p.dbg & 4) ? 0 : a_bytes) + ((p.dbg & 8) ? 0 : b_bytes));
+          uz::mbar_expect_tx(&full_bar[s], (UZ_DBG(p, 4) ? 0 : a_bytes) + (UZ_DBG(p, 8) ? 0 : b_bytes));
           for (int j = 0; j < KB; ++j) {
             const int c0 = (kg * KB + j) * KC;
-            if (!(p.dbg & 4)) uz::tma_load_4d(smem_a + s * a_bytes + j * a_box, &tmap_x, &full_bar[s], c0, x0 + dx, y0 + dy, n0);
-            if (!(p.dbg & 8)) uz::tma_load_3d(smem_b + s * b_bytes + j * b_box, &tmap_w, &full_bar[s], c0, c_out0, tap);
+            if (!UZ_DBG(p, 4)) uz::tma_load_4d(smem_a + s * a_bytes + j * a_box, &tmap_x, &full_bar[s], c0, x0 + dx, y0 + dy, n0);
+            if (!UZ_DBG(p, 8)) uz::tma_load_3d(smem_b + s * b_bytes + j * b_box, &tmap_w, &full_bar[s], c0, c_out0, tap);
           }
         }
         __syncwarp();
@@ -166,7 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const uint32_t b_lo = desc_lo0 + (uz::smem_u32(smem_b + s * b_bytes) >> 4);
       const uint32_t a_step = a_box >> 4, b_step = b_box >> 4;
       if (uz::elect_one()) {                     // ONE election per stage: every extra warp-level instruction in this
-        if (!(p.dbg & 2)) {                      // loop costs ~50 ns per iteration on these latency-bound launches
+        if (!UZ_DBG(p, 2)) {                      // loop costs ~50 ns per iteration on these latency-bound launches
 #pragma unroll
           for (int j = 0; j < KB; ++j) {
 #pragma unroll
@@ -190,12 +216,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int row = q * 32 + lane;
     const int box_px = p.TW * p.TH;
     const int xx = row % p.TW, yy = (row / p.TW) % p.TH, nn = row / box_px;
-    const bool valid = (n0 + nn) < p.N && !(p.dbg & 1);
+    const bool valid = (n0 + nn) < p.N && !UZ_DBG(p, 1);
     const size_t pix = (static_cast<size_t>(n0 + nn) * p.H + (y0 + yy)) * p.W + (x0 + xx);
     __nv_bfloat16* dst = p.y + pix * p.ldy + c_out0;
+    const bool bn = p.bn_y != nullptr, rs = p.res != nullptr;
+    const __nv_bfloat16* bn_row = bn ? p.bn_y + pix * p.bn_ldy + c_out0 : nullptr;
+    const __nv_bfloat16* res_row = rs ? p.res + pix * p.ld_res + c_out0 : nullptr;
     uz::mbar_wait(&accum_bar, 0);
     uz::tc_fence_after();
-    for (int c = 0; c < ((p.dbg & 1) ? 0 : p.BN); c += 16) {
+    for (int c = 0; c < (UZ_DBG(p, 1) ? 0 : p.BN); c += 16) {
+      float yv[16], rv[16];
+      if (bn) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) yv[j] = 0.f;
+        if (valid) load_row16(bn_row + c, yv);
+      }
+      if (rs) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rv[j] = 0.f;
+        if (valid) load_row16(res_row + c, rv);
+      }
       uint32_t r[16];
       uz::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       uz::tmem_ld_wait();
@@ -206,6 +246,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         float v0 = fmaf(__uint_as_float(r[2 * j]), s_scale[c + 2 * j], s_shift[c + 2 * j]);
         float v1 = fmaf(__uint_as_float(r[2 * j + 1]), s_scale[c + 2 * j + 1], s_shift[c + 2 * j + 1]);
         if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        if (rs) { v0 = fmaf(p.res_sign, v0, rv[2 * j]); v1 = fmaf(p.res_sign, v1, rv[2 * j + 1]); }
+        if (bn && p.bn_relu) {
+          if (!(fmaf(yv[2 * j], s_scale2[c + 2 * j], s_shift2[c + 2 * j]) > 0.f)) v0 = 0.f;
+          if (!(fmaf(yv[2 * j + 1], s_scale2[c + 2 * j + 1], s_shift2[c + 2 * j + 1]) > 0.f)) v1 = 0.f;
+        }
         packed[j] = uz::pack_bf16x2(v0, v1);
         v[2 * j] = valid ? uz::bf16lo(packed[j]) : 0.f;       // statistics of the stored values, valid rows only
         v[2 * j + 1] = valid ? uz::bf16hi(packed[j]) : 0.f;
@@ -215,10 +260,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
       }
-      if (p.stats) {
+      if (p.stats || bn) {
         float sq[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+        for (int j = 0; j < 16; ++j) sq[j] = v[j] * (bn ? yv[j] : v[j]);
         const float s1 = transpose_reduce16(v, lane);
         const float s2 = transpose_reduce16(sq, lane);
         if (lane < 16) {
@@ -227,14 +272,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
       }
     }
-    if (p.stats) {
+    if (p.stats || p.bn_sums) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int et = threadIdx.x - 64;
+      float* acc = p.stats ? p.stats : p.bn_sums;
       for (int i = et; i < 2 * p.BN; i += 128) {
         const int which = i / p.BN, c = i - which * p.BN;
-        if (!(p.dbg & 1)) {
+        if (!UZ_DBG(p, 1)) {
           const float t = (s_stats[0][which][c] + s_stats[1][which][c]) + (s_stats[2][which][c] + s_stats[3][which][c]);
-          atomicAdd(p.stats + which * p.Cout + c_out0 + c, t);
+          if (p.stats_rows) acc[(static_cast<size_t>(tile) * 2 + which) * p.Cout + c_out0 + c] = t;
+          else atomicAdd(acc + which * p.Cout + c_out0 + c, t);
         }
       }
     }
@@ -271,7 +318,34 @@ extern "C" int uz_conv_tile_geometry(int N, int H, int W, int* TW, int* TH, int*
 extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout,
                            int taps, void* y, int ldy, const float* scale, const float* shift, int relu,
                            float* stats_partial, void* stream) {
+  return uz_conv_fwd_ex(x, N, H, W, Cin, ldx, w_packed, Cout, taps, y, ldy, scale, shift, relu, stats_partial, nullptr,
+                        stream);
+}
+
+extern "C" int uz_conv_stats_rows(int N, int H, int W, int Cin, int Cout, int taps) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return -1;
+  if (taps == 9 && !UZ_KNOB(32)) {
+    const int rows = uz::conv2_stats_rows(N, H, W, Cin, Cout);
+    if (rows > 0) return rows;
+  }
+  int tiles = 0;
+  uz_conv_tile_geometry(N, H, W, nullptr, nullptr, nullptr, &tiles);
+  return tiles;
+}
+
+extern "C" int uz_conv_fwd_ex(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout,
+                              int taps, void* y, int ldy, const float* scale, const float* shift, int relu,
+                              float* stats_partial, const UzConvExtra* ex, void* stream) {
   UZ_CHECK_ARG(x && w_packed && y, "uz_conv_fwd: null pointer");
+  if (ex) {
+    UZ_CHECK_ARG(!ex->bn_y || (ex->bn_scale && ex->bn_shift && ex->bn_sums && ex->bn_ldy % 8 == 0 && ex->bn_ldy >= Cout &&
+                               (reinterpret_cast<uintptr_t>(ex->bn_y) & 15) == 0 && !stats_partial),
+                 "uz_conv_fwd_ex: fused BatchNorm backward needs scale, shift, sums, an aligned y and no forward statistics");
+    UZ_CHECK_ARG(!ex->residual || (ex->ld_res % 8 == 0 && ex->ld_res >= Cout &&
+                                   (reinterpret_cast<uintptr_t>(ex->residual) & 15) == 0),
+                 "uz_conv_fwd_ex: bad residual operand");
+    UZ_CHECK_ARG(!ex->stats_rows || stats_partial, "uz_conv_fwd_ex: stats_rows without a statistics buffer");
+  }
   UZ_CHECK_ARG(taps == 9 || taps == 1, "uz_conv_fwd: taps must be 9 or 1 (got %d)", taps);
   UZ_CHECK_ARG(Cin % 16 == 0 && Cin > 0, "uz_conv_fwd: Cin must be a positive multiple of 16 (got %d)", Cin);
   UZ_CHECK_ARG(Cout % 16 == 0 && Cout > 0, "uz_conv_fwd: Cout must be a positive multiple of 16 (got %d)", Cout);
@@ -279,14 +353,14 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   UZ_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
                "uz_conv_fwd: pointers must be 16-byte aligned");
-  if (uz::g_conv_debug_flags & 128) return UZ_OK;   // measurement knob: step time without the conv kernels
-  if (taps == 9 && !(uz::g_conv_debug_flags & 32)) {
+  if UZ_KNOB(128) return UZ_OK;   // measurement knob: step time without the conv kernels
+  if (taps == 9 && !UZ_KNOB(32)) {
     int handled = 0;
-    int rc = uz::conv2_launch(x, N, 0, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial,
+    int rc = uz::conv2_launch(x, N, 0, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, ex,
                               stream, &handled);
     if (rc || handled) return rc;
   }
-  if (uz::g_conv_debug_flags & 2048) return UZ_OK;  // measurement knob: step time without the generic-kernel launches
+  if UZ_KNOB(2048) return UZ_OK;  // measurement knob: step time without the generic-kernel launches
   ConvParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
   int tiles = 0;
@@ -305,6 +379,13 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   p.ldy = ldy; p.relu = relu;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.scale = scale; p.shift = shift; p.stats = stats_partial;
+  if (ex) {
+    p.stats_rows = ex->stats_rows;
+    p.bn_y = static_cast<const __nv_bfloat16*>(ex->bn_y); p.bn_ldy = ex->bn_ldy;
+    p.bn_scale = ex->bn_scale; p.bn_shift = ex->bn_shift; p.bn_relu = ex->bn_relu; p.bn_sums = ex->bn_sums;
+    p.res = static_cast<const __nv_bfloat16*>(ex->residual); p.ld_res = ex->ld_res;
+    p.res_sign = ex->res_sign < 0 ? -1.f : 1.f;
+  }
   p.dbg = uz::g_conv_debug_flags;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(bn)) cols *= 2;
@@ -315,7 +396,7 @@ extern "C" int uz_conv_fwd(const void* x, int N, int H, int W, int Cin, int ldx,
   p.KB = 1;
   for (int kb = 4; kb >= 2; --kb) {
     if (kblocks % kb == 0 && (196 * 1024) / (static_cast<size_t>(kBlockM + bn) * swz * kb) >= 2 &&
-        !(uz::g_conv_debug_flags & 65536)) {
+        !UZ_KNOB(65536)) {
       p.KB = kb;
       break;
     }
@@ -390,21 +471,25 @@ extern "C" int uz_conv3d_fwd(const void* x, int N, int D, int H, int W, int Cin,
   UZ_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
                "uz_conv3d_fwd: pointers must be 16-byte aligned");
-  if (uz::g_conv_debug_flags & 128) return UZ_OK;
+  if UZ_KNOB(128) return UZ_OK;
   int handled = 0;
-  int rc = uz::conv2_launch(x, N, D, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, stream,
-                            &handled);
+  int rc = uz::conv2_launch(x, N, D, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, nullptr,
+                            stream, &handled);
   if (rc) return rc;
   UZ_CHECK_ARG(handled, "uz_conv3d_fwd: no kernel plan for Cin=%d Cout=%d", Cin, Cout);
   return UZ_OK;
 }
 
 extern "C" int uz_set_debug_flags(int flags) {
+#ifndef UZ_PROFILE_KNOBS
+  UZ_CHECK_ARG((flags & ~32) == 0, "uz_set_debug_flags: this library was built without -DUZ_PROFILE_KNOBS; only bit 32 "
+               "(route 3x3 layers to the generic kernel) is available (got %d)", flags);
+#endif
   uz::g_conv_debug_flags = flags;
   return UZ_OK;
 }
 
 extern "C" int uz_conv_uses_persistent_kernel(int N, int H, int W, int Cin, int Cout, int taps) {
-  if (taps == 9 && !(uz::g_conv_debug_flags & 32)) return uz::conv2_stats_rows(N, H, W, Cin, Cout) > 0 ? 1 : 0;
+  if (taps == 9 && !UZ_KNOB(32)) return uz::conv2_stats_rows(N, H, W, Cin, Cout) > 0 ? 1 : 0;
   return 0;
 }

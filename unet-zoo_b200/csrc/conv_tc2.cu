@@ -46,8 +46,32 @@ struct Conv2Params {
   const float* scale;
   const float* shift;
   float* stats;                  // [2][Cout] accumulators (zero on entry) or nullptr
+  int stats_rows;                // 1: stats is [slots][2][Cout], row = this CTA's slot, plain stores (fixed summation order)
+  // fused BatchNorm/ReLU backward statistics of the layer that produced this conv's forward input (UzConvExtra)
+  const __nv_bfloat16* bn_y;
+  const float* bn_scale;
+  const float* bn_shift;
+  float* bn_sums;                // [2][Cout] accumulators: sum g, sum g*y with g = out * [relu'(y*scale+shift)]
+  int bn_ldy, bn_relu;
+  const __nv_bfloat16* res;      // out = res + res_sign * value
+  int ld_res;
+  float res_sign;
   int dbg;
 };
+
+__device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* src, int n, float* out) {
+  // n (16 or 32) consecutive bf16 of one pixel row -> fp32; 16-byte vector loads
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j * 8 < n) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + j);
+      out[j * 8 + 0] = uz::bf16lo(q.x); out[j * 8 + 1] = uz::bf16hi(q.x);
+      out[j * 8 + 2] = uz::bf16lo(q.y); out[j * 8 + 3] = uz::bf16hi(q.y);
+      out[j * 8 + 4] = uz::bf16lo(q.z); out[j * 8 + 5] = uz::bf16hi(q.z);
+      out[j * 8 + 6] = uz::bf16lo(q.w); out[j * 8 + 7] = uz::bf16hi(q.w);
+    }
+  }
+}
 
 __device__ __forceinline__ void tma_load_3d_box(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   uz::tma_load_3d(smem, m, bar, c0, c1, c2);
@@ -109,11 +133,33 @@ __device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
 
 // Epilogue of NW (32 or 16) accumulator columns of one row: TMEM -> registers -> scale/shift(/ReLU) -> bf16 -> swizzled
 // staging row; optional BatchNorm statistics of the stored values into this warp's shared accumulators.
-template <int NW>
+template <int NW, bool EXT>
 __device__ __forceinline__ void epilogue_columns(const Conv2Params& p, uint32_t taddr, int c, int row, int lane,
                                                  uint32_t xr, uint32_t box_bytes, uint32_t cwb, uint8_t* smem_out,
                                                  const float* s_scale, const float* s_shift, float* st_sum,
-                                                 float* st_sq, bool in_image) {
+                                                 float* st_sq, bool in_image, const float* s_scale2,
+                                                 const float* s_shift2, const __nv_bfloat16* bn_row,
+                                                 const __nv_bfloat16* res_row) {
+  // operands from global memory first (their latency overlaps the TMEM load): the producer layer's pre-normalisation
+  // outputs for the fused BatchNorm/ReLU backward, the residual of a reversible coupling
+  float yv[EXT ? NW : 1], rv[EXT ? NW : 1];
+  const bool bn = EXT && p.bn_y != nullptr, rs = EXT && p.res != nullptr;
+  if constexpr (EXT) {
+    if (bn) {
+      if (in_image) load_row_bf16(bn_row + c, NW, yv);
+      else {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) yv[j] = 0.f;
+      }
+    }
+    if (rs) {
+      if (in_image) load_row_bf16(res_row + c, NW, rv);
+      else {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) rv[j] = 0.f;
+      }
+    }
+  }
   uint32_t r[NW];
   if constexpr (NW == 32) tmem_ld32(taddr, r); else uz::tmem_ld16(taddr, r);
   uz::tmem_ld_wait();
@@ -125,6 +171,13 @@ __device__ __forceinline__ void epilogue_columns(const Conv2Params& p, uint32_t 
     float a = fmaf(__uint_as_float(r[2 * j]), s_scale[ch], s_shift[ch]);
     float b = fmaf(__uint_as_float(r[2 * j + 1]), s_scale[ch + 1], s_shift[ch + 1]);
     if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    if constexpr (EXT) {
+      if (rs) { a = fmaf(p.res_sign, a, rv[2 * j]); b = fmaf(p.res_sign, b, rv[2 * j + 1]); }
+      if (bn && p.bn_relu) {        // gradient of the producer's ReLU: keep where its activation was positive
+        if (!(fmaf(yv[2 * j], s_scale2[ch], s_shift2[ch]) > 0.f)) a = 0.f;
+        if (!(fmaf(yv[2 * j + 1], s_scale2[ch + 1], s_shift2[ch + 1]) > 0.f)) b = 0.f;
+      }
+    }
     pk[j] = uz::pack_bf16x2(a, b);
     v[2 * j] = in_image ? uz::bf16lo(pk[j]) : 0.f;          // statistics of the values as stored
     v[2 * j + 1] = in_image ? uz::bf16hi(pk[j]) : 0.f;
@@ -140,10 +193,13 @@ __device__ __forceinline__ void epilogue_columns(const Conv2Params& p, uint32_t 
       *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     }
   }
-  if (p.stats) {
+  if (p.stats || bn) {
     float sq[NW];
 #pragma unroll
-    for (int j = 0; j < NW; ++j) sq[j] = v[j] * v[j];
+    for (int j = 0; j < NW; ++j) {                // sum y^2 (forward) or sum g*y (fused backward)
+      if constexpr (EXT) sq[j] = v[j] * (bn ? yv[j] : v[j]);
+      else sq[j] = v[j] * v[j];
+    }
     if constexpr (NW == 32) {
       const float s = transpose_reduce32(v, lane);
       const float s2 = transpose_reduce32(sq, lane);
@@ -160,8 +216,8 @@ __device__ __forceinline__ void epilogue_columns(const Conv2Params& p, uint32_t 
   }
 }
 
-template <int KC>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int KC, bool EXT>
+__global__ void __launch_bounds__(kThreads, EXT ? 2 : 1)      // EXT: <= 170 registers so two CTAs still share an SM
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_y, const Conv2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -175,6 +231,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   __shared__ float s_scale[256];
   __shared__ float s_shift[256];
   __shared__ float s_stats[4][2][256];                     // per epilogue warp: sum, sumsq per channel
+  __shared__ float s_scale2[256];                          // folded BatchNorm of the producer layer (fused backward)
+  __shared__ float s_shift2[256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -213,6 +271,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   for (int c = threadIdx.x; c < p.BN; c += kThreads) {
     s_scale[c] = p.scale ? p.scale[c_out0 + c] : 1.f;
     s_shift[c] = p.shift ? p.shift[c_out0 + c] : 0.f;
+    if constexpr (EXT) {
+      s_scale2[c] = p.bn_y ? p.bn_scale[c_out0 + c] : 1.f;
+      s_shift2[c] = p.bn_y ? p.bn_shift[c_out0 + c] : 0.f;
+    }
   }
   for (int i = threadIdx.x; i < 4 * 2 * 256; i += kThreads) (&s_stats[0][0][0])[i] = 0.f;
   uz::tc_fence_before();
@@ -236,10 +298,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           uz::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * p.stage_bytes;
           if (uz::elect_one()) {
-            uz::mbar_expect_tx(&full_bar[stage], ((p.dbg & 4) ? 0 : p.a_bytes) + ((p.dbg & 8) ? 0 : p.b_bytes));
-            if (!(p.dbg & 4))
+            uz::mbar_expect_tx(&full_bar[stage], (UZ_DBG(p, 4) ? 0 : p.a_bytes) + (UZ_DBG(p, 8) ? 0 : p.b_bytes));
+            if (!UZ_DBG(p, 4))
               uz::tma_load_5d(sa, &tmap_x, &full_bar[stage], kb * KC, x0 + dx - 1, y0 - 1, z0 + dz - z_off, n);
-            if (!(p.dbg & 8)) tma_load_3d_box(sa + p.a_bytes, &tmap_w, &full_bar[stage], kb * KC, c_out0, r * 3);
+            if (!UZ_DBG(p, 8)) tma_load_3d_box(sa + p.a_bytes, &tmap_w, &full_bar[stage], kb * KC, c_out0, r * 3);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -270,7 +332,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         {
           const uint32_t a_lo = desc_lo0 + (uz::smem_u32(smem + stage * p.stage_bytes) >> 4);
           const uint32_t b_lo = a_lo + (p.a_bytes >> 4);
-          if (!(p.dbg & 2) && uz::elect_one()) {
+          if (!UZ_DBG(p, 2) && uz::elect_one()) {
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
@@ -322,22 +384,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         if (et == 0) tma_store_wait_read();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const bool in_image = !p.mask || ((x0 + (row & 15) < p.W) && (y0 + 8 * half + (row >> 4) < p.H));
-        if (!(p.dbg & 1)) {
+        // this thread's pixel in the operands read from global memory (fused BatchNorm backward, residual)
+        const size_t pix = ((static_cast<size_t>(n) * p.D + z0) * p.H + (y0 + 8 * half + (row >> 4))) * p.W + x0 + (row & 15);
+        const __nv_bfloat16* bn_row = p.bn_y ? p.bn_y + pix * p.bn_ldy + c_out0 : nullptr;
+        const __nv_bfloat16* res_row = p.res ? p.res + pix * p.ld_res + c_out0 : nullptr;
+        if (!UZ_DBG(p, 1)) {
           const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 2 * p.BN + half * p.BN;
           if (p.BN % 32 == 0) {
             for (int c = 0; c < p.BN; c += 32)
-              epilogue_columns<32>(p, tbase + c, c, row, lane, xr, box_bytes, cwb, smem_out, s_scale, s_shift,
-                                   s_stats[ew][0], s_stats[ew][1], in_image);
+              epilogue_columns<32, EXT>(p, tbase + c, c, row, lane, xr, box_bytes, cwb, smem_out, s_scale, s_shift,
+                                   s_stats[ew][0], s_stats[ew][1], in_image, s_scale2, s_shift2, bn_row, res_row);
           } else {                     // output widths that are odd multiples of 16 (16-channel store boxes)
             for (int c = 0; c < p.BN; c += 16)
-              epilogue_columns<16>(p, tbase + c, c, row, lane, xr, box_bytes, cwb, smem_out, s_scale, s_shift,
-                                   s_stats[ew][0], s_stats[ew][1], in_image);
+              epilogue_columns<16, EXT>(p, tbase + c, c, row, lane, xr, box_bytes, cwb, smem_out, s_scale, s_shift,
+                                   s_stats[ew][0], s_stats[ew][1], in_image, s_scale2, s_shift2, bn_row, res_row);
           }
         }
         // generic-proxy writes -> visible to the TMA (async proxy), then one thread issues the stores
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0 && !(p.dbg & 1)) {
+        if (et == 0 && !UZ_DBG(p, 1)) {
           for (int cb = 0; cb < p.BN / p.CW; ++cb)
             tma_store_5d(&tmap_y, smem_out + cb * box_bytes, c_out0 + cb * p.CW, x0, y0 + 8 * half, z0, n);
           tma_store_commit();
@@ -349,12 +415,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (et == 0) uz::mbar_arrive(&acc_empty[buf]);
     }
     if (et == 0) tma_store_wait_all();
-    if (p.stats) {
+    if (p.stats || p.bn_sums) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* acc = p.stats ? p.stats : p.bn_sums;
       for (int i = et; i < 2 * p.BN; i += 128) {
         const int which = i / p.BN, c = i - which * p.BN;
         const float t = (s_stats[0][which][c] + s_stats[1][which][c]) + (s_stats[2][which][c] + s_stats[3][which][c]);
-        atomicAdd(p.stats + which * p.Cout + c_out0 + c, t);     // one add per CTA per channel
+        if (p.stats_rows)             // one row per CTA slot, reduced in fixed order by uz_bn_finalize (deterministic mode)
+          acc[(static_cast<size_t>(slot) * 2 + which) * p.Cout + c_out0 + c] = t;
+        else
+          atomicAdd(acc + which * p.Cout + c_out0 + c, t);       // one add per CTA per channel
       }
     }
   }
@@ -378,7 +448,7 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
   const bool vol = D > 0;
   if (Cin % 16 || Cout % 16 || Cout > 4096) return false;
   if (!vol && (H % kTile || W % kTile)) return false;
-  if (!vol && (uz::g_conv_debug_flags & 512) && Cout % 32) return false;   // measurement knob: 16-wide outputs -> generic
+  if (!vol && UZ_KNOB(512) && Cout % 32) return false;   // measurement knob: 16-wide outputs -> generic
   Conv2Params& p = out->p;
   p = Conv2Params{};
   p.N = N; p.D = vol ? D : 1; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -395,11 +465,11 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
   }
   // (a single-tile CTA runs load -> MMA -> epilogue back to back, nothing overlaps: with fewer items than SMs narrower
   //  chunks shorten every phase; the slabs are then re-read from L2 by more CTAs)
-  while (2 * p.tiles * (Cout / bn) <= sms && bn % 32 == 0 && bn >= 64 && !(uz::g_conv_debug_flags & 32768)) bn /= 2;
+  while (2 * p.tiles * (Cout / bn) <= sms && bn % 32 == 0 && bn >= 64 && !UZ_KNOB(32768)) bn /= 2;
   while (p.tiles * (Cout / bn) < sms && bn % 64 == 0 && bn >= 128) bn /= 2;
   // chunks wider than 128 leave room for only ONE accumulator pair in TMEM (no epilogue / MMA overlap): split them once
   // more so the accumulators are double buffered (192 -> 2 x 96, 256 -> 2 x 128); the slabs are then read twice from L2
-  if (4 * bn > 512 && bn % 32 == 0 && !(uz::g_conv_debug_flags & 16384)) bn /= 2;
+  if (4 * bn > 512 && bn % 32 == 0 && !UZ_KNOB(16384)) bn /= 2;
   if (bn % 16) return false;
   p.BN = bn;
   p.n_chunks = Cout / bn;
@@ -413,10 +483,10 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, Plan2* out) {
   // Narrow layers (a single chunk of <= 64 output channels) are bound by the per-tile epilogue and by the latency of
   // their few K steps, not by the tensor pipe: they run TWO CTAs per SM (half the shared memory each, TMEM columns
   // 2 x <= 256), which doubles epilogue throughput and overlaps one CTA's loads with the other's stores.
-  const bool dual = p.n_chunks == 1 && bn <= 64 && !(uz::g_conv_debug_flags & 8192);
+  const bool dual = p.n_chunks == 1 && bn <= 64 && !UZ_KNOB(8192);
   int best_kc = 0, best_stages = 0;
   for (int pass = dual ? 0 : 1; pass < 2 && !best_kc; ++pass) {
-    const size_t budget = pass == 0 ? 100 * 1024 : 214 * 1024;
+    const size_t budget = pass == 0 ? 97 * 1024 : 211 * 1024;   // + ~13 KB of static shared memory per CTA
     for (int kc : {64, 32, 16}) {
       if (Cin % kc) continue;
       const size_t stage = (static_cast<size_t>(kSlabRows + 3 * bn) * kc * 2 + 1023) / 1024 * 1024;
@@ -451,19 +521,26 @@ namespace uz {
 int conv2_stats_rows(int N, int H, int W, int Cin, int Cout) {
   Plan2 pl;
   if (!make_plan2(N, 0, H, W, Cin, Cout, &pl)) return 0;
-  return pl.grid;
+  return pl.grid / pl.p.n_chunks;          // CTA slots: every slot writes one statistics row (all its output-channel chunks)
 }
 
 // returns UZ_OK and sets *handled = 1 when the persistent kernel took the launch.  D == 0: 2-D, 9 taps; D >= 1: 27 taps
 int conv2_launch(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, void* y,
-                 int ldy, const float* scale, const float* shift, int relu, float* stats_partial, void* stream,
-                 int* handled) {
+                 int ldy, const float* scale, const float* shift, int relu, float* stats_partial, const UzConvExtra* ex,
+                 void* stream, int* handled) {
   *handled = 0;
   Plan2 pl;
   if (!make_plan2(N, D, H, W, Cin, Cout, &pl)) return UZ_OK;
-  if (g_conv_debug_flags & 1024) { *handled = 1; return UZ_OK; }   // measurement knob: persistent-kernel launches elided
+  if UZ_KNOB(1024) { *handled = 1; return UZ_OK; }   // measurement knob: persistent-kernel launches elided
   Conv2Params& p = pl.p;
   p.scale = scale; p.shift = shift; p.relu = relu; p.stats = stats_partial;
+  if (ex) {
+    p.stats_rows = ex->stats_rows;
+    p.bn_y = static_cast<const __nv_bfloat16*>(ex->bn_y); p.bn_ldy = ex->bn_ldy;
+    p.bn_scale = ex->bn_scale; p.bn_shift = ex->bn_shift; p.bn_relu = ex->bn_relu; p.bn_sums = ex->bn_sums;
+    p.res = static_cast<const __nv_bfloat16*>(ex->residual); p.ld_res = ex->ld_res;
+    p.res_sign = ex->res_sign < 0 ? -1.f : 1.f;
+  }
   p.dbg = g_conv_debug_flags;
   const uint32_t swz = p.KC * 2;
   CUtensorMap tx, tw, ty;
@@ -492,9 +569,11 @@ int conv2_launch(const void* x, int N, int D, int H, int W, int Cin, int ldx, co
     int rc = make_tmap_bf16(&ty, y, 5, dims, strides, box, p.CW * 2);
     if (rc) return rc;
   }
-  auto kernel = p.KC == 64 ? conv_tc2_kernel<64> : (p.KC == 32 ? conv_tc2_kernel<32> : conv_tc2_kernel<16>);
-  static size_t attr_bytes[3] = {0, 0, 0};
-  size_t& ab = attr_bytes[p.KC == 64 ? 0 : (p.KC == 32 ? 1 : 2)];
+  const bool ext = p.bn_y != nullptr || p.res != nullptr;
+  auto kernel = ext ? (p.KC == 64 ? conv_tc2_kernel<64, true> : (p.KC == 32 ? conv_tc2_kernel<32, true> : conv_tc2_kernel<16, true>))
+                    : (p.KC == 64 ? conv_tc2_kernel<64, false> : (p.KC == 32 ? conv_tc2_kernel<32, false> : conv_tc2_kernel<16, false>));
+  static size_t attr_bytes[6] = {0, 0, 0, 0, 0, 0};
+  size_t& ab = attr_bytes[(p.KC == 64 ? 0 : (p.KC == 32 ? 1 : 2)) + (ext ? 3 : 0)];
   if (pl.smem > ab) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
     if (e != cudaSuccess) {

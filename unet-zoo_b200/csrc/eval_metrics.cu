@@ -223,6 +223,150 @@ __global__ void ncc_finish_kernel(const double* __restrict__ ncc_j, int M, doubl
   out[0] = (1.0 / M) * s;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused N-sample evaluation (train_model.py:185-222 after the network): ONE pass over the per-level class logits does
+// accumulate_output (phiseg.py:428-434, same fp32 summation order), softmax, argmax -> bit-packed label masks, and the
+// two per-pixel sums sum_i p_ic and sum_i log(p_ic + 1e-8) that variance_ncc_dist needs (the
+// single-pass form of utils.py:202-247).  The levels may be low-resolution logits (nearest upsampling by factor f,
+// phiseg.py:321, is index arithmetic here) so the five full-resolution fp32 tensors are never written.
+// Both sums are additive over samples -> over GPUs: one all-reduce of [2][C][HW]; the masks are 2 KB per sample.
+constexpr int kEvalMaxLevels = 8;
+constexpr int kEvalMaxClasses = 4;
+struct EvalLevels {
+  const float* s[kEvalMaxLevels];   // fp32 [B][C][(H/f) * (W/f)], B = n * I with batch index b = sample * I + image
+  int f[kEvalMaxLevels];
+  int L;
+};
+
+// grid (ceil(HW/256), G sample groups, I images); thread = pixel, warp = one 32-pixel mask word.
+// part: fp32 [I][G][2][C][HW] (sum p, sum log(p+1e-8) over the group's samples, fixed order)
+__global__ void __launch_bounds__(256)
+eval_sample_stats_kernel(EvalLevels lv, int n, int I, int C, int H, int W, LabelSet ls, uint32_t* bits /*[I][n][nl][words]*/,
+                         int* counts /*[I][n][nl], zero on entry*/, float* part) {
+  uz::pdl_prologue();
+  const int HW = H * W, words = (HW + 31) / 32;
+  const int px = blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.y, G = gridDim.y, img = blockIdx.z;
+  const int per = (n + G - 1) / G;
+  const int s0 = g * per, s1 = min(n, s0 + per);
+  const bool inside = px < HW;
+  const int y = inside ? px / W : 0, x = inside ? px - y * W : 0;
+  int off[kEvalMaxLevels], plane[kEvalMaxLevels];
+  for (int l = 0; l < lv.L; ++l) {
+    const int f = lv.f[l], wl = W / f, hl = H / f;
+    off[l] = (y / f) * wl + x / f;
+    plane[l] = hl * wl;
+  }
+  float ps[kEvalMaxClasses], lsum[kEvalMaxClasses];
+#pragma unroll
+  for (int c = 0; c < kEvalMaxClasses; ++c) { ps[c] = 0.f; lsum[c] = 0.f; }
+  for (int smp = s0; smp < s1; ++smp) {
+    const size_t b = static_cast<size_t>(smp) * I + img;
+    float acc[kEvalMaxClasses];
+#pragma unroll
+    for (int c = 0; c < kEvalMaxClasses; ++c) {
+      acc[c] = 0.f;
+      if (c < C && inside) {
+        // s_accum = list[-1]; s_accum += list[0], list[1], ... (phiseg.py:429-431): the reference's fp32 order
+        float a = lv.s[lv.L - 1][(b * C + c) * plane[lv.L - 1] + off[lv.L - 1]];
+        for (int l = 0; l < lv.L - 1; ++l) a += lv.s[l][(b * C + c) * plane[l] + off[l]];
+        acc[c] = a;
+      }
+    }
+    float m = acc[0];
+#pragma unroll
+    for (int c = 1; c < kEvalMaxClasses; ++c) if (c < C) m = fmaxf(m, acc[c]);
+    float e[kEvalMaxClasses], den = 0.f;
+#pragma unroll
+    for (int c = 0; c < kEvalMaxClasses; ++c) { e[c] = c < C ? expf(acc[c] - m) : 0.f; den += e[c]; }
+    int arg = 0;
+    float best = -1.f;
+#pragma unroll
+    for (int c = 0; c < kEvalMaxClasses; ++c) {
+      if (c < C) {
+        const float p = e[c] / den;
+        if (p > best) { best = p; arg = c; }              // first maximal index, like torch.argmax
+        ps[c] += p;
+        lsum[c] += logf(p + 1e-8f);
+      }
+    }
+    for (int l = 0; l < ls.n; ++l) {
+      const uint32_t word = __ballot_sync(0xffffffffu, inside && arg == ls.v[l]);
+      if (lane == 0 && (px >> 5) < words) {
+        const size_t row = (static_cast<size_t>(img) * n + smp) * ls.n + l;
+        bits[row * words + (px >> 5)] = word;
+        if (word) atomicAdd(&counts[row], __popc(word));    // integer: order independent
+      }
+    }
+  }
+  if (inside) {
+    float* dst = part + ((static_cast<size_t>(img) * G + g) * 2) * C * HW + px;
+    for (int c = 0; c < C; ++c) {
+      dst[static_cast<size_t>(c) * HW] = ps[c];
+      dst[static_cast<size_t>(C + c) * HW] = lsum[c];
+    }
+  }
+}
+
+// sums [I][2][C][HW] = sum over the G groups in fixed order
+__global__ void eval_stats_reduce_kernel(const float* __restrict__ part, int I, int G, size_t per_image, float* sums) {
+  uz::pdl_prologue();
+  const size_t total = static_cast<size_t>(I) * per_image;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t img = idx / per_image, r = idx - img * per_image;
+    float t = 0.f;
+    for (int g = 0; g < G; ++g) t += part[(img * G + g) * per_image + r];
+    sums[idx] = t;
+  }
+}
+
+// per pixel from the (all-reduced) sums of ONE image: E_ss = -sum_c (P_c/N)(L_c/N), E_sy[j] = -sum_c [gt_j == c] L_c/N
+// (utils.py:219-238), and the Dice counts of argmax_c(mean probs) against one annotator (train_model.py:207-222).
+template <typename GT>
+__global__ void ncc_from_sums_kernel(const float* __restrict__ sums /*[2][C][HW]*/, const GT* __restrict__ gt /*[M][HW]*/,
+                                     int N, int C, int hw, int M, int dice_annotator, double* e_ss, double* e_sy,
+                                     int* dice_counts /*[C][3]: |pred|, |gt|, |both|; zero on entry*/) {
+  uz::pdl_prologue();
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= hw) return;
+  const float inv = 1.f / static_cast<float>(N);
+  float lbar[kEvalMaxClasses];
+  double ss = 0.0;
+  int arg = 0;
+  float best = -1.f;
+  for (int c = 0; c < C; ++c) {
+    const float psum = sums[static_cast<size_t>(c) * hw + px];
+    lbar[c] = sums[static_cast<size_t>(C + c) * hw + px] * inv;
+    ss -= static_cast<double>(psum * inv) * static_cast<double>(lbar[c]);
+    if (psum > best) { best = psum; arg = c; }
+  }
+  e_ss[px] = ss;
+  for (int j = 0; j < M; ++j) {
+    const int lbl = static_cast<int>(gt[static_cast<size_t>(j) * hw + px]);
+    e_sy[static_cast<size_t>(j) * hw + px] = (lbl >= 0 && lbl < C) ? -static_cast<double>(lbar[lbl]) : 0.0;
+  }
+  if (dice_counts && dice_annotator >= 0) {
+    const int lbl = static_cast<int>(gt[static_cast<size_t>(dice_annotator) * hw + px]);
+    atomicAdd(&dice_counts[arg * 3 + 0], 1);
+    if (lbl >= 0 && lbl < C) {
+      atomicAdd(&dice_counts[lbl * 3 + 1], 1);
+      if (lbl == arg) atomicAdd(&dice_counts[arg * 3 + 2], 1);
+    }
+  }
+}
+
+// per label: both empty -> 1, exactly one empty -> 0, else medpy dc = 2|A&B| / (|A| + |B|)  (train_model.py:211-222)
+__global__ void dice_finish_kernel(const int* __restrict__ counts, int C, double* dice) {
+  uz::pdl_prologue();
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const int np = counts[c * 3], ng = counts[c * 3 + 1], nb = counts[c * 3 + 2];
+  dice[c] = (np == 0 && ng == 0) ? 1.0 : ((np == 0 || ng == 0) ? 0.0 : 2.0 * nb / static_cast<double>(np + ng));
+}
+
 }  // namespace
 
 #define ST(s) static_cast<cudaStream_t>(s)
@@ -305,5 +449,78 @@ extern "C" int uz_variance_ncc(const float* probs, const void* gt, int gt_dtype,
   UZ_CHECK_LAUNCH("uz_variance_ncc(corr)");
   uz::launch(ncc_finish_kernel, 1, 32, 0, ST(stream), ncc_j, M, out);
   UZ_CHECK_LAUNCH("uz_variance_ncc(finish)");
+  return UZ_OK;
+}
+
+
+// ---- fused N-sample evaluation -------------------------------------------------------------------------------------
+extern "C" int uz_eval_sample_groups(int n, int I, int hw) {
+  // enough blocks for ~2 waves: (hw / 256) * G * I >= 2 * SMs, at least 4 samples per group
+  if (n <= 0 || I <= 0 || hw <= 0) return -1;
+  const int per_g = (hw + 255) / 256 * I;
+  int G = (2 * uz::num_sms() + per_g - 1) / per_g;
+  if (G > (n + 3) / 4) G = (n + 3) / 4;
+  if (G < 1) G = 1;
+  return G;
+}
+
+extern "C" int uz_eval_sample_stats(const float* const* levels, const int* factors, int L, int n, int I, int C, int H,
+                                    int W, const int* label_values, int nlabels, unsigned int* bits, int* counts,
+                                    float* part, float* sums, void* stream) {
+  UZ_CHECK_ARG(levels && factors && label_values && bits && counts && part && sums, "uz_eval_sample_stats: null pointer");
+  UZ_CHECK_ARG(L >= 1 && L <= kEvalMaxLevels && C >= 1 && C <= kEvalMaxClasses && nlabels >= 1 && nlabels <= kMaxLabels,
+               "uz_eval_sample_stats: L=%d C=%d nlabels=%d unsupported", L, C, nlabels);
+  EvalLevels lv{};
+  lv.L = L;
+  for (int l = 0; l < L; ++l) {
+    UZ_CHECK_ARG(levels[l] && factors[l] >= 1 && H % factors[l] == 0 && W % factors[l] == 0,
+                 "uz_eval_sample_stats: level %d: factor must divide the image size", l);
+    lv.s[l] = levels[l];
+    lv.f[l] = factors[l];
+  }
+  LabelSet ls{};
+  ls.n = nlabels;
+  for (int l = 0; l < nlabels; ++l) ls.v[l] = label_values[l];
+  const int hw = H * W;
+  const int G = uz_eval_sample_groups(n, I, hw);
+  cudaMemsetAsync(counts, 0, sizeof(int) * static_cast<size_t>(I) * n * nlabels, ST(stream));
+  uz::launch(eval_sample_stats_kernel, dim3((hw + 255) / 256, G, I), 256, 0, ST(stream), lv, n, I, C, H, W, ls, bits, counts,
+             part);
+  UZ_CHECK_LAUNCH("uz_eval_sample_stats");
+  const size_t per_image = static_cast<size_t>(2) * C * hw;
+  int blocks = static_cast<int>((per_image * I + 255) / 256);
+  if (blocks > uz::num_sms() * 8) blocks = uz::num_sms() * 8;
+  uz::launch(eval_stats_reduce_kernel, blocks, 256, 0, ST(stream), part, I, G, per_image, sums);
+  UZ_CHECK_LAUNCH("uz_eval_sample_stats(reduce)");
+  return UZ_OK;
+}
+
+extern "C" int uz_ncc_dice_from_sums(const float* sums, const void* gt, int gt_dtype, int N, int C, int hw, int M,
+                                     int dice_annotator, double* work, int* dice_counts, double* out, void* stream) {
+  UZ_CHECK_ARG(sums && gt && work && out, "uz_ncc_dice_from_sums: null pointer");
+  UZ_CHECK_ARG(C >= 1 && C <= kEvalMaxClasses && M >= 1 && M <= 16 && N >= 1 && dice_annotator < M,
+               "uz_ncc_dice_from_sums: C=%d M=%d unsupported", C, M);
+  double* e_ss = work;
+  double* e_sy = work + hw;
+  double* ncc_j = work + static_cast<size_t>(1 + M) * hw;
+  if (dice_counts) cudaMemsetAsync(dice_counts, 0, sizeof(int) * 3 * C, ST(stream));
+  const int blocks = (hw + 127) / 128;
+  if (gt_dtype == 1)
+    uz::launch(ncc_from_sums_kernel<float>, blocks, 128, 0, ST(stream), sums, static_cast<const float*>(gt), N, C, hw, M,
+               dice_annotator, e_ss, e_sy, dice_counts);
+  else if (gt_dtype == 2)
+    uz::launch(ncc_from_sums_kernel<uint8_t>, blocks, 128, 0, ST(stream), sums, static_cast<const uint8_t*>(gt), N, C, hw,
+               M, dice_annotator, e_ss, e_sy, dice_counts);
+  else if (gt_dtype == 0)
+    uz::launch(ncc_from_sums_kernel<long long>, blocks, 128, 0, ST(stream), sums, static_cast<const long long*>(gt), N, C,
+               hw, M, dice_annotator, e_ss, e_sy, dice_counts);
+  else
+    UZ_CHECK_ARG(false, "uz_ncc_dice_from_sums: gt dtype %d unsupported", gt_dtype);
+  UZ_CHECK_LAUNCH("uz_ncc_dice_from_sums(pixel)");
+  uz::launch(ncc_corr_kernel, M, 1024, 0, ST(stream), e_ss, e_sy, hw, ncc_j);
+  UZ_CHECK_LAUNCH("uz_ncc_dice_from_sums(corr)");
+  uz::launch(ncc_finish_kernel, 1, 32, 0, ST(stream), ncc_j, M, out);
+  if (dice_counts) uz::launch(dice_finish_kernel, 1, 32, 0, ST(stream), dice_counts, C, out + 1);
+  UZ_CHECK_LAUNCH("uz_ncc_dice_from_sums(finish)");
   return UZ_OK;
 }

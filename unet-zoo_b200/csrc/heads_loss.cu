@@ -157,13 +157,23 @@ head_bwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const flo
     }
     __syncthreads();
   }
-  if (active) {
+  // the pb pixel slots of a channel chunk are summed in slot order through a [pb][C] staging area (no shared-memory
+  // atomics: the result does not depend on thread scheduling)
+  float* tmp_s = db_s + 2 * Z;
 #pragma unroll
-    for (int k = 0; k < 2 * Z; ++k)
+  for (int k = 0; k < 2 * Z; ++k) {
+    if (active) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&dw_s[k * C + c8 * 8 + j], dwr[k][j]);
+      for (int j = 0; j < 8; ++j) tmp_s[pslot * C + c8 * 8 + j] = dwr[k][j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += kHeadThreads) {
+      float t = 0.f;
+      for (int sl = 0; sl < pb; ++sl) t += tmp_s[sl * C + i];
+      dw_s[k * C + i] = t;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int i = threadIdx.x; i < 2 * Z * C; i += kHeadThreads)
     wpartial[static_cast<size_t>(blockIdx.x) * 2 * Z * C + i] = dw_s[i];
   if (threadIdx.x < 2 * Z) bpartial[blockIdx.x * 2 * Z + threadIdx.x] = db_s[threadIdx.x];
@@ -311,6 +321,7 @@ slayer_fwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const f
 }
 
 // backward: g[p][k] = sum over the replicated block of dout; dfeat = W^T g; per-block partial dW = g^T feat, db = sum g.
+template <int kRegCls>       // upper bound of ncls: every class accumulates its dW share in registers
 __global__ void __launch_bounds__(kSlThreads)
 slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ feat, int ld, int C,
                   const float* __restrict__ w, int ncls, int rows, int d, int h, int wd, int f, int fz,
@@ -325,6 +336,8 @@ slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restric
   while (pb * 2 <= wd && pb * 2 <= kSlThreads) pb *= 2;
   if (pb > wd) pb = wd;
   float* db_s = g_s + pb * ncls;
+  float* rs_s = db_s + ncls;                          // [pb][ncls][fz * f] replica-row sums
+  float* tmp_s = rs_s + pb * ncls * fz * f;           // [pixel slots][C] staging of the dW reduction
   for (int i = threadIdx.x; i < ncls * C; i += kSlThreads) {
     w_s[i] = w[i];
     dw_s[i] = 0.f;
@@ -334,7 +347,6 @@ slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restric
   const int pstride = kSlThreads / chunks;           // pixels processed per pass in phase 2
   const int c8 = threadIdx.x % chunks, pslot = threadIdx.x / chunks;
   const bool p2_active = pslot < pstride;
-  constexpr int kRegCls = 4;                          // classes whose dW contribution accumulates in registers
   float dwr[kRegCls][8];
 #pragma unroll
   for (int k = 0; k < kRegCls; ++k)
@@ -349,19 +361,26 @@ slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restric
     const int b = bz / d, zl = bz - b * d;
     for (int p0 = 0; p0 < wd; p0 += pb) {
       const int pbc = min(pb, wd - p0);
-      for (int i = threadIdx.x; i < pbc * ncls; i += kSlThreads) g_s[i] = 0.f;
+      // upstream gradient of a low-resolution pixel = sum over its f x f (x fz) replicas: one thread per (class, z, y
+      // replica row, pixel) sums the f contiguous values of that row, then the rows are added in fixed order
+      const int rows_pp = fz * f;                       // replica rows per pixel
+      for (int idx = threadIdx.x; idx < ncls * rows_pp * pbc; idx += kSlThreads) {
+        const int pl = idx % pbc;
+        int r = idx / pbc;
+        const int iy = r % f; r /= f;
+        const int iz = r % fz;
+        const int k = r / fz;
+        const float* src = dout + ((static_cast<size_t>(b) * ncls + k) * (d * fz) + zl * fz + iz) * HW +
+                           static_cast<size_t>(yl * f + iy) * W + (p0 + pl) * f;
+        float t = 0.f;
+        for (int ix = 0; ix < f; ++ix) t += src[ix];
+        rs_s[(pl * ncls + k) * rows_pp + iz * f + iy] = t;
+      }
       __syncthreads();
-      const int per_k = fz * f * pbc * f;
-      for (int idx = threadIdx.x; idx < ncls * per_k; idx += kSlThreads) {
-        const int k = idx / per_k;
-        int r = idx - k * per_k;
-        const int ix = r % f; r /= f;
-        const int pl = r % pbc; r /= pbc;
-        const int iy = r % f;
-        const int iz = r / f;
-        const float v = dout[((static_cast<size_t>(b) * ncls + k) * (d * fz) + zl * fz + iz) * HW +
-                             static_cast<size_t>(yl * f + iy) * W + (p0 + pl) * f + ix];
-        if (f == 1 && fz == 1) g_s[pl * ncls + k] = v; else atomicAdd(&g_s[pl * ncls + k], v);
+      for (int i = threadIdx.x; i < pbc * ncls; i += kSlThreads) {
+        float t = 0.f;
+        for (int rr = 0; rr < rows_pp; ++rr) t += rs_s[i * rows_pp + rr];
+        g_s[i] = t;
       }
       __syncthreads();
       if (threadIdx.x < ncls) {
@@ -379,19 +398,14 @@ slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restric
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) dd[jj] = 0.f;
 #pragma unroll
-          for (int k = 0; k < kMaxOut; ++k) {
+          for (int k = 0; k < kRegCls; ++k) {
             if (k < ncls) {
               const float g = g_s[pl * ncls + k];
               const float* wk = w_s + k * C + c8 * 8;
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) dd[jj] = fmaf(g, wk[jj], dd[jj]);
-              if (k < kRegCls) {
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) dwr[k][jj] = fmaf(g, x[jj], dwr[k][jj]);
-              } else {
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) atomicAdd(&dw_s[k * C + c8 * 8 + jj], g * x[jj]);
-              }
+              for (int jj = 0; jj < 8; ++jj) dwr[k][jj] = fmaf(g, x[jj], dwr[k][jj]);
             }
           }
           *reinterpret_cast<uint4*>(dfeat + pix * ldd + c8 * 8) =
@@ -402,14 +416,23 @@ slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restric
       __syncthreads();
     }
   }
-  if (p2_active) {
+  // fixed-order sum over the pixel slots (no shared-memory atomics)
 #pragma unroll
-    for (int k = 0; k < kRegCls; ++k)
-      if (k < ncls)
+  for (int k = 0; k < kRegCls; ++k) {
+    if (k < ncls) {
+      if (p2_active) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) atomicAdd(&dw_s[k * C + c8 * 8 + jj], dwr[k][jj]);
+        for (int jj = 0; jj < 8; ++jj) tmp_s[pslot * C + c8 * 8 + jj] = dwr[k][jj];
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < C; i += kSlThreads) {
+        float t = 0.f;
+        for (int sl = 0; sl < pstride; ++sl) t += tmp_s[sl * C + i];
+        dw_s[k * C + i] = t;
+      }
+      __syncthreads();
+    }
   }
-  __syncthreads();
   for (int i = threadIdx.x; i < ncls * C; i += kSlThreads)
     wpartial[static_cast<size_t>(blockIdx.x) * ncls * C + i] = dw_s[i];
   if (threadIdx.x < ncls) bpartial[blockIdx.x * ncls + threadIdx.x] = db_s[threadIdx.x];
@@ -568,7 +591,8 @@ extern "C" int uz_head_bwd(const void* feat, int ld, int C, const float* wmu, co
   UZ_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 8 * kHeadThreads && ld % 8 == 0 && ldd % 8 == 0,
                "uz_head_bwd: C and strides must be multiples of 8");
   const int blocks = uz_head_bwd_num_blocks(B, hw);
-  const size_t smem = (static_cast<size_t>(8) * C + (kHeadThreads / (C / 8)) * 4 + 4) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(8) * C + (kHeadThreads / (C / 8)) * 4 + 4 +
+                       static_cast<size_t>(kHeadThreads / (C / 8)) * C) * sizeof(float);     // + [pb][C] staging
   UZ_CHECK_ARG(smem <= 48 * 1024, "uz_head_bwd: C=%d too large for the shared accumulators", C);
   uz::launch(head_bwd_kernel<2>, blocks, kHeadThreads, smem, ST(stream), static_cast<const __nv_bfloat16*>(feat), ld, C, wmu, wsig,
                                                             eps, sigma, dmu, dsigma, dz, B, hw,
@@ -672,12 +696,13 @@ int slayer_bwd_impl(const float* dout, const void* feat, int ld, int C, const fl
   UZ_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 8 * kSlThreads && ld % 8 == 0 && ldd % 8 == 0, "uz_slayer_bwd: bad C/ld");
   const long long rows = static_cast<long long>(B) * d * h;
   const int blocks = uz_slayer_bwd_num_blocks(B * d, h, wd);
-  const size_t smem =
-      (2 * static_cast<size_t>(ncls) * C + static_cast<size_t>(slayer_pb(wd)) * ncls + ncls) * sizeof(float);
+  const size_t smem = (2 * static_cast<size_t>(ncls) * C + static_cast<size_t>(slayer_pb(wd)) * ncls + ncls +
+                       static_cast<size_t>(slayer_pb(wd)) * ncls * fz * factor +
+                       static_cast<size_t>(kSlThreads / (C / 8)) * C) * sizeof(float);
   UZ_CHECK_ARG(smem <= 48 * 1024, "uz_slayer_bwd: ncls*C too large for the shared accumulators");
-  uz::launch(slayer_bwd_kernel, blocks, kSlThreads, smem, ST(stream), dout, static_cast<const __nv_bfloat16*>(feat), ld, C, w,
-             ncls, static_cast<int>(rows), d, h, wd, factor, fz, static_cast<__nv_bfloat16*>(dfeat), ldd, wpartial,
-             bpartial);
+  uz::launch(ncls <= 4 ? slayer_bwd_kernel<4> : slayer_bwd_kernel<kMaxOut>, blocks, kSlThreads, smem, ST(stream), dout,
+             static_cast<const __nv_bfloat16*>(feat), ld, C, w, ncls, static_cast<int>(rows), d, h, wd, factor, fz,
+             static_cast<__nv_bfloat16*>(dfeat), ldd, wpartial, bpartial);
   UZ_CHECK_LAUNCH("uz_slayer_bwd");
   uz::launch(column_reduce_kernel, (ncls * C + 127) / 128, 128, 0, ST(stream), wpartial, blocks, ncls * C, dw, 1.f);
   uz::launch(column_reduce_kernel, 1, 32, 0, ST(stream), bpartial, blocks, ncls, db, 1.f);

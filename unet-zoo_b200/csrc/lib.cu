@@ -3,6 +3,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <unordered_set>
 #include "common.cuh"
 #include "unetzoo_b200.h"
 
@@ -36,6 +38,25 @@ int g_pdl = [] {
   const char* e = getenv("UZ_PDL");
   return (e && e[0] == '1') ? 1 : 0;
 }();
+
+// Shared-memory carveout preference applied to EVERY kernel of the library on its first launch (UZ_CARVEOUT = percent of
+// the unified L1/shared array, -1 = leave the driver default).  With the default policy every kernel gets the smallest
+// carveout that fits it, so a step that alternates 0-KB elementwise kernels with 100-200 KB tensor-core kernels makes the
+// SMs re-partition between launches and keeps kernels of different streams from sharing an SM.
+int g_carveout = [] {
+  const char* e = getenv("UZ_CARVEOUT");
+  return e ? atoi(e) : -1;
+}();
+static std::mutex g_prep_mutex;
+static std::unordered_set<const void*> g_prepared;
+void prepare_kernel(const void* fn) {
+  if (g_carveout < 0) return;
+  std::lock_guard<std::mutex> lock(g_prep_mutex);
+  if (g_prepared.insert(fn).second) {
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout) != cudaSuccess)
+      (void)cudaGetLastError();
+  }
+}
 
 void count_launch() { ++g_launches; }
 
@@ -96,6 +117,14 @@ extern "C" int uz_abi_version(void) { return UZ_ABI_VERSION; }
 extern "C" int uz_device_sm_count(void) { return uz::num_sms(); }
 
 extern "C" long long uz_launch_count(void) { return g_launches; }
+
+extern "C" int uz_set_smem_carveout(int percent) {
+  UZ_CHECK_ARG(percent >= -1 && percent <= 100, "uz_set_smem_carveout: %d outside [-1, 100]", percent);
+  std::lock_guard<std::mutex> lock(uz::g_prep_mutex);
+  uz::g_carveout = percent;
+  uz::g_prepared.clear();
+  return UZ_OK;
+}
 
 extern "C" int uz_set_pdl(int enabled) {
   uz::g_pdl = enabled ? 1 : 0;

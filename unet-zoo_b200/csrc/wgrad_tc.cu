@@ -361,7 +361,7 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, int taps, Plan2* 
   const bool vol = D > 0;
   if (taps != (vol ? 27 : 9) || Cin % 16 || Cout % 16) return false;
   if (!vol && (H % 8 || W % 16)) return false;
-  if (!vol && (uz::g_conv_debug_flags & 32)) return false;
+  if (!vol && UZ_KNOB(32)) return false;
   Wgrad2Params& p = out->p;
   p = Wgrad2Params{};
   p.N = N; p.D = vol ? D : 1; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -523,7 +523,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
                "uz_conv_wgrad: channels must be multiples of 16, Cin <= 512 (got %d, %d)", Cin, Cout);
   UZ_CHECK_ARG(ldx % 8 == 0 && lddy % 8 == 0 && ldx >= Cin && lddy >= Cout, "uz_conv_wgrad: bad pixel strides");
   UZ_CHECK_ARG(Cin_logical <= Cin && Cout_logical <= Cout, "uz_conv_wgrad: logical dims exceed stored dims");
-  if (uz::g_conv_debug_flags & 256) return UZ_OK;   // measurement knob: step time without the wgrad kernels
+  if UZ_KNOB(256) return UZ_OK;   // measurement knob: step time without the wgrad kernels
   Plan2 pl2;
   if (make_plan2(N, D, H, W, Cin, Cout, taps, &pl2)) {
     pl2.p.partial = workspace;
@@ -565,7 +565,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
     const int G2 = reduce_groups(pl2.splits);
     int blocks2 = static_cast<int>((total2 + 256 / G2 - 1) / (256 / G2));
     if (blocks2 > uz::num_sms() * 8) blocks2 = uz::num_sms() * 8;
-    if (!(uz::g_conv_debug_flags & 4096)) uz::launch(wgrad_reduce_kernel, dim3(blocks2, taps, 1), 256, 0, static_cast<cudaStream_t>(stream), workspace, pl2.splits, taps, Cout, Cin,
+    if (!UZ_KNOB(4096)) uz::launch(wgrad_reduce_kernel, dim3(blocks2, taps, 1), 256, 0, static_cast<cudaStream_t>(stream), workspace, pl2.splits, taps, Cout, Cin,
                                                                                Cout_logical, Cin_logical, dw, G2);
     UZ_CHECK_LAUNCH("uz_conv_wgrad(v2 reduce)");
     return UZ_OK;
@@ -615,7 +615,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
   const int G1 = reduce_groups(pl.splits);
   int blocks = static_cast<int>((total + 256 / G1 - 1) / (256 / G1));
   if (blocks > uz::num_sms() * 8) blocks = uz::num_sms() * 8;
-  if (!(uz::g_conv_debug_flags & 4096)) uz::launch(wgrad_reduce_kernel, dim3(blocks, taps, 1), 256, 0, static_cast<cudaStream_t>(stream), workspace, pl.splits, taps, Cout, Cin,
+  if (!UZ_KNOB(4096)) uz::launch(wgrad_reduce_kernel, dim3(blocks, taps, 1), 256, 0, static_cast<cudaStream_t>(stream), workspace, pl.splits, taps, Cout, Cin,
                                                                             Cout_logical, Cin_logical, dw, G1);
   UZ_CHECK_LAUNCH("uz_conv_wgrad(reduce)");
   return UZ_OK;

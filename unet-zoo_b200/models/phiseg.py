@@ -301,8 +301,11 @@ class Likelihood(nn.Module):
             self.s_layer.append(Conv2DSequence(input_dim=input, output_dim=output, depth=1, kernel=1,
                                                activation=torch.nn.Identity, norm=torch.nn.Identity))
 
-    def forward(self, z):
-        """z: list of latent tensors [B,2,r,r] fp32 (index = latent level) -> list of full-resolution logits."""
+    def forward(self, z, lowres=False):
+        """z: list of latent tensors [B,2,r,r] fp32 (index = latent level) -> list of full-resolution logits.
+        ``lowres`` (extension, evaluation): return the logits at the resolution of their feature maps together with the
+        nearest-upsampling factors, [(s_in [B,C,h,w], factor), ...] -- the fused evaluation kernel (b200.train.EvalStep)
+        does the replication of models/phiseg.py:321 as index arithmetic instead of reading five full-size tensors."""
         s = [None] * self.latent_levels
         post_z = [None] * self.latent_levels
         post_c = [None] * self.latent_levels
@@ -334,7 +337,10 @@ class Likelihood(nn.Module):
             conv = block.convolution[0].convolution[0]
             factor = self.image_size[1] // feat.t.shape[1]
             assert factor * feat.t.shape[1] == self.image_size[1] and factor * feat.t.shape[2] == self.image_size[2]
-            s[-i - 1] = ops.SLayerNearest.apply(feat.t, conv.weight, conv.bias, factor)
+            if lowres:
+                s[-i - 1] = (ops.SLayerNearest.apply(feat.t, conv.weight, conv.bias, 1), factor)
+            else:
+                s[-i - 1] = ops.SLayerNearest.apply(feat.t, conv.weight, conv.bias, factor)
         return s
 
 
@@ -409,22 +415,24 @@ class PHISeg(nn.Module):
             object.__setattr__(self, '_weight_packer', pk)
         return pk
 
-    def forward(self, patch, mask, training=True, replicate=1):
+    def forward(self, patch, mask, training=True, replicate=1, lowres_logits=False):
         """``replicate`` (extension, evaluation only): the N-sample evaluation of the reference feeds N identical copies of
-        one image (train_model.py:177-179).  forward(patch[1,...], mask[1,...], training=False, replicate=N) returns what
-        forward(patch.repeat(N,1,1,1), mask.repeat(N,1,1,1), training=False) returns -- same values, same random draws --
-        but runs the two encoders once instead of N times (their eval-mode outputs are identical for identical inputs)."""
+        one image (train_model.py:177-179).  forward(patch[I,...], mask[I,...], training=False, replicate=N) returns what
+        forward(patch.repeat(N,1,1,1), mask.repeat(N,1,1,1), training=False) returns -- same values, same random draws
+        (batch index = copy * I + image) -- but runs the two encoders once per image instead of N times (their eval-mode
+        outputs are identical for identical inputs).  ``lowres_logits``: see Likelihood.forward (evaluation only; the
+        returned list then holds (tensor, factor) pairs and ``s_out_list`` is not updated)."""
         if not patch.is_cuda:
             raise kern._lib.UnetZooLibError('UNet-Zoo B200 modules need CUDA tensors: there is no CPU fallback path')
-        if replicate != 1 and (training or self.training or patch.shape[0] != 1):
-            raise ValueError('replicate=N needs eval mode, training=False and a batch of one image')
+        if (replicate != 1 or lowres_logits) and (training or self.training):
+            raise ValueError('replicate=N / lowres_logits need eval mode and training=False')
         pk = self._packer()
         pk.refresh()
         kern.zero_arena.reset(patch.device)
         prev = kern.set_active_packer(pk)
         try:
             with deferred_batch_counts():
-                return self._forward(patch, mask, training, replicate)
+                return self._forward(patch, mask, training, replicate, lowres_logits)
         finally:
             kern.set_active_packer(prev)
 
@@ -432,11 +440,12 @@ class PHISeg(nn.Module):
     def _replicate(x, blocks, n):
         if n == 1:
             return x, blocks
-        # the deepest feature map feeds convolutions and becomes a real batch of n; the skip connections stay single
-        # images -- the concat kernel replicates them while it copies them into the concat buffers (kern.copy_channels)
-        return Act(x.t.expand((n,) + tuple(x.t.shape[1:])).contiguous(), x.c), blocks
+        # the deepest feature map feeds convolutions and becomes a real batch of n copies (copy-major: index = copy * I +
+        # image); the skip connections stay single images -- the concat kernel replicates them while it copies them into
+        # the concat buffers (kern.copy_channels)
+        return Act(x.t.repeat((n,) + (1,) * (x.t.dim() - 1)), x.c), blocks
 
-    def _forward(self, patch, mask, training=True, replicate=1):
+    def _forward(self, patch, mask, training=True, replicate=1, lowres_logits=False):
         # posterior and prior encoders are independent (no random draws inside): the prior's runs on a second stream.
         # The latent halves keep the reference's order -- 5 posterior draws, then 5 prior draws (quirk Q4).
         if replicate != 1:
@@ -470,6 +479,8 @@ class PHISeg(nn.Module):
             self.s_out_list = self.likelihood(self.posterior_latent_space)
         else:
             self.prior_latent_space, self.prior_mu, self.prior_sigma = self.prior.latent(prior_x, prior_blocks)
+            if lowres_logits:
+                return self.likelihood(self.prior_latent_space, lowres=True)
             self.s_out_list = self.likelihood(self.prior_latent_space)
         return self.s_out_list
 

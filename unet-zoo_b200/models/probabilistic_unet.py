@@ -119,16 +119,6 @@ class Fcomb(nn.Module):
                 self.layers.apply(init_weights)
                 self.last_layer.apply(init_weights)
 
-    def tile(self, a, dim, n_tile):
-        """tf.tile equivalent kept for API completeness (the device path broadcasts z without materialising tiles)."""
-        init_dim = a.size(dim)
-        repeat_idx = [1] * a.dim()
-        repeat_idx[dim] = n_tile
-        a = a.repeat(*(repeat_idx))
-        order_index = torch.LongTensor(np.concatenate([init_dim * np.arange(n_tile) + i for i in range(init_dim)])).to(
-            a.device)
-        return torch.index_select(a, dim, order_index)
-
     def forward(self, feature_map, z):
         """feature_map: NHWC Act or NCHW tensor [B,C,H,W]; z: [B, latent_dim] -> class logits fp32 NCHW."""
         if self.use_tile:
@@ -200,11 +190,23 @@ class ProbabilisticUnet(nn.Module):
                     self.posterior_latent_space = self.posterior.forward(patch, segm)
                 self.prior_latent_space = self.prior.forward(patch)
                 object.__setattr__(self, '_unet_features', self.unet.features(patch))
+            conv = self.last_conv.convolution[0]
+            return ops.SLayerNearest.apply(self._unet_features.t, conv.weight, conv.bias, 1)
         finally:
-            kern.set_active_packer(pk)
-        # packed weights stay active for sample()/reconstruct()/elbo() of this step
-        conv = self.last_conv.convolution[0]
-        return ops.SLayerNearest.apply(self._unet_features.t, conv.weight, conv.bias, 1)
+            kern.set_active_packer(prev)
+
+    def _with_packer(self, fn, refresh):
+        """sample() / reconstruct() / elbo() run 1x1 convs outside forward(): they activate the model's packed weights
+        themselves and restore whatever was active before (nothing stays installed process-wide).  ``refresh`` re-packs
+        first -- needed when the parameters may have changed since forward() (sample() after an optimizer step)."""
+        pk = self._packer()
+        if refresh:
+            pk.refresh()
+        prev = kern.set_active_packer(pk)
+        try:
+            return fn()
+        finally:
+            kern.set_active_packer(prev)
 
     def sample(self, testing=False):
         if testing is False:
@@ -212,14 +214,14 @@ class ProbabilisticUnet(nn.Module):
         else:
             z_prior = self.prior_latent_space.sample()
         self.z_prior_sample = z_prior
-        return self.fcomb.forward(self._unet_features, z_prior)
+        return self._with_packer(lambda: self.fcomb.forward(self._unet_features, z_prior), refresh=True)
 
     def reconstruct(self, use_posterior_mean=False, calculate_posterior=False, z_posterior=None):
         if use_posterior_mean:
             z_posterior = self.posterior_latent_space.loc
         elif calculate_posterior:
             z_posterior = self.posterior_latent_space.rsample()
-        return self.fcomb.forward(self._unet_features, z_posterior)
+        return self._with_packer(lambda: self.fcomb.forward(self._unet_features, z_posterior), refresh=False)
 
     def accumulate_output(self, output_list, use_softmax=False):
         s_accum = output_list
@@ -259,5 +261,4 @@ class ProbabilisticUnet(nn.Module):
         reg_loss = l2_regularisation(self.posterior) + l2_regularisation(self.prior) + l2_regularisation(
             self.fcomb.layers)
         loss = -elbo + 1e-5 * reg_loss
-        kern.set_active_packer(None)
         return loss

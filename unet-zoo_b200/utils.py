@@ -28,6 +28,13 @@ def generalised_energy_distance(sample_arr, gt_arr, nlabels=1, **kwargs):
     """reference utils.py:148-200.  sample_arr [N,X,Y], gt_arr [M,X,Y]; returns a python float, bit-identical to the
     reference's nested loops (integer IoU counts, fp64 ratios, Python-order sums)."""
     label_range = list(kwargs.get('label_range', range(nlabels)))
+    if len(label_range) != nlabels:
+        # the reference divides the summed IoUs by ``nlabels`` whatever the length of ``label_range`` (utils.py:170); the
+        # kernel divides by the number of labels it walks.  The two agree for every call site of the reference
+        # (train_model.py:198-200,398-400: nlabels = n_classes - 1, label_range = range(1, n_classes)).
+        raise NotImplementedError('generalised_energy_distance: len(label_range) = %d != nlabels = %d is not supported '
+                                  'by the B200 kernel (the reference call sites always pass matching values)'
+                                  % (len(label_range), nlabels))
     sample_arr = _as_cuda_labels(sample_arr)
     gt_arr = _as_cuda_labels(gt_arr).to(sample_arr.device)
     out = kern.ged(sample_arr, gt_arr, label_range)

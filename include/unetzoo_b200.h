@@ -24,6 +24,9 @@ extern "C" {
 
 const char* uz_last_error(void);
 int uz_abi_version(void);
+/* storage type of activations / packed weights this library was built for: 0 = bf16 (libunetzoo_b200.so), 1 = IEEE half
+ * (libunetzoo_b200_fp16.so, -DUZ_ACT_FP16: 10-bit mantissa like TF32, the tolerance-matched parity mode) */
+int uz_storage_dtype(void);
 int uz_device_sm_count(void);
 /* number of kernel launches issued by this library so far in this process (bench.py's gpu_launches) */
 long long uz_launch_count(void);

@@ -33,13 +33,19 @@ BN_MOMENTUM = 0.01
 
 
 class Rounding:
-    """fp32 (reference arithmetic) or bf16-storage emulation of the CUDA path."""
+    """fp32 (reference arithmetic) or storage-precision emulation of the CUDA path: bf16 (product library) or IEEE half
+    (libunetzoo_b200_fp16.so, the tolerance-matched parity mode)."""
 
-    def __init__(self, bf16=False):
+    def __init__(self, bf16=False, fp16=False):
         self.bf16 = bf16
+        self.fp16 = fp16
 
     def act(self, x):
-        return x.to(torch.bfloat16).to(torch.float32) if self.bf16 else x
+        if self.bf16:
+            return x.to(torch.bfloat16).to(torch.float32)
+        if self.fp16:
+            return x.to(torch.float16).to(torch.float32)
+        return x
 
     weight = act
 

@@ -11,7 +11,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(_HERE)
 REPO_ROOT = os.path.dirname(PKG_ROOT)
 HEADER = os.path.join(REPO_ROOT, 'include', 'unetzoo_b200.h')
-LIB_PATH = os.path.join(PKG_ROOT, 'libunetzoo_b200.so')
+# Two builds of the same sources: bf16 storage (the product) and IEEE-half storage (10-bit mantissa like TF32: the
+# tolerance-matched parity mode).  UNETZOO_PRECISION=fp16 or set_precision('fp16') selects the second one.
+_LIBS = {'bf16': 'libunetzoo_b200.so', 'fp16': 'libunetzoo_b200_fp16.so'}
+PRECISION = os.environ.get('UNETZOO_PRECISION', 'bf16')
+if PRECISION not in _LIBS:
+    raise ValueError('UNETZOO_PRECISION must be bf16 or fp16 (got %r)' % PRECISION)
+LIB_PATH = os.path.join(PKG_ROOT, _LIBS[PRECISION])
 
 _SCALARS = {
     'int': ctypes.c_int,
@@ -54,6 +60,28 @@ class UnetZooLibError(RuntimeError):
 
 _lib = None
 _protos = None
+_loaded = {}
+
+
+def act_dtype():
+    """torch dtype of activations / packed weights for the selected library"""
+    import torch
+    return torch.float16 if PRECISION == 'fp16' else torch.bfloat16
+
+
+def set_precision(name):
+    """switch the active library ('bf16' | 'fp16'); tensors produced under one precision must not be fed to the other.
+    Returns the previous name."""
+    global PRECISION, LIB_PATH, _lib
+    if name not in _LIBS:
+        raise ValueError('precision must be bf16 or fp16 (got %r)' % (name,))
+    prev = PRECISION
+    if name != prev:
+        PRECISION = name
+        LIB_PATH = os.path.join(PKG_ROOT, _LIBS[name])
+        _lib = _loaded.get(name)
+        _fn.clear()
+    return prev
 
 
 def load():
@@ -62,7 +90,7 @@ def load():
         return _lib
     if not os.path.isfile(LIB_PATH):
         raise UnetZooLibError(
-            'libunetzoo_b200.so not found at %s -- build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            'library not found at %s -- build it with `python -c "import __graft_entry__ as g; g.build()"` '
             'or `make -C unet-zoo_b200/csrc`; there is no fallback path.' % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     _protos = parse_header()
@@ -72,7 +100,10 @@ def load():
         fn.argtypes = [t for t, _ in argl]
     if lib.uz_abi_version() != 1:
         raise UnetZooLibError('ABI version mismatch')
+    if lib.uz_storage_dtype() != (1 if PRECISION == 'fp16' else 0):
+        raise UnetZooLibError('%s was not built for %s storage' % (LIB_PATH, PRECISION))
     _lib = lib
+    _loaded[PRECISION] = lib
     return lib
 
 

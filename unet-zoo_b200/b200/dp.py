@@ -1,10 +1,10 @@
 """One-process-per-GPU data parallelism for the drop-in models (the reference has none).
 
-Training: batch data-parallel.  Parameters are grouped into a few flat fp32 buckets in reverse registration
-(~ reverse autograd) order; a post-accumulate hook counts arrivals and, when a bucket is complete, gathers its gradients
-with one multi-tensor copy, re-points ``.grad`` at views of the flat buffer and issues ONE NCCL all-reduce (average).  torch.distributed's NCCL process group runs the collective on its own stream
-after the producing kernels and ``finish()`` makes the compute stream wait for it, so communication overlaps the rest
-of backward.  Parameters that never receive a gradient (``{posterior,prior}.upsampling_path.4.*``)
+Training: batch data-parallel.  Parameters are grouped into a few flat fp32 buckets in the order their gradients are
+produced (recorded during the warm-up steps), with a small tail bucket for the last arrivals; the tensor-core weight
+gradients are written straight into the buckets (``grad_view_for``), the few remaining gradients are gathered with one
+multi-tensor copy, ``.grad`` is re-pointed at views of the flat buffer and ONE NCCL all-reduce (average) per bucket is
+issued from a side stream.  ``finish()`` makes the compute stream wait, so communication overlaps the rest of backward.  Parameters that never receive a gradient (``{posterior,prior}.upsampling_path.4.*``)
 keep ``grad is None`` exactly like in the reference, so stock Adam skips them.
 
 Evaluation: the N samples of an image are sharded over ranks; the per-rank class probabilities are exchanged with a
@@ -68,19 +68,40 @@ class _Bucket:
         self.flat, self.params, self.pending, self.work = flat, params, 0, None
 
 
+# parameter -> fp32 view into its flat bucket.  b200.ops hands the view to the weight-gradient kernel as its output, so
+# the gradient is PRODUCED inside the bucket and ``.grad`` becomes that view without a gather copy.
+_grad_views = {}
+
+
+def grad_view_for(param):
+    return _grad_views.get(id(param))
+
+
 class GradientAllReduce:
     """Bucketed, overlapped gradient averaging.  Usage per step:
          dp.zero_grad(); loss.backward(); dp.finish(); optimizer.step()
-    The first steps (before ``freeze_buckets``) use a plain post-backward all-reduce and discover which parameters
-    actually receive gradients."""
+    The first steps (before ``freeze_buckets``) use a plain post-backward all-reduce and record the ORDER in which the
+    gradients are produced; ``freeze_buckets`` then builds the flat buckets in that order -- large ones first, a small
+    tail (``tail_bytes``) for the parameters whose gradients arrive last, so that the only all-reduce that cannot hide
+    behind backward is short.  A completed bucket is handed to NCCL from a side stream that waits for the producing
+    streams (the compute stream is never stalled by communication set-up); ``finish()`` joins."""
 
-    def __init__(self, params, group=None, bucket_bytes=32 << 20):
+    def __init__(self, params, group=None, bucket_bytes=24 << 20, tail_bytes=2 << 20):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.bucket_bytes = bucket_bytes
+        self.tail_bytes = tail_bytes
         self.buckets = None
         self._hooks = []
+        self._order = []
+        self._comm_stream = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        for p in self.params:                              # discovery: the order gradients become available in
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._record_order))
+
+    def _record_order(self, param):
+        if self.buckets is None:
+            self._order.append(id(param))
 
     # -- discovery phase ------------------------------------------------------------------------------------------
     def _finish_unbucketed(self):
@@ -98,7 +119,18 @@ class GradientAllReduce:
     def freeze_buckets(self):
         """Call after at least one backward: builds the flat buckets over the parameters that have gradients."""
         live = [p for p in self.params if p.grad is not None]
-        live.reverse()                                     # last-registered parameters finish backward first
+        seen = {}
+        for k, pid in enumerate(self._order):              # last recorded backward wins
+            seen[pid] = k
+        if len(seen) >= len(live):
+            live.sort(key=lambda p: seen.get(id(p), -1))    # production order of the last discovery step
+        else:
+            live.reverse()                                  # no hook information: last-registered parameters finish first
+        # split off the tail: the parameters produced last, up to tail_bytes
+        tail, tb = [], 0
+        while len(live) > 1 and tb + live[-1].numel() * 4 <= self.tail_bytes:
+            tb += live[-1].numel() * 4
+            tail.insert(0, live.pop())
         groups, cur, cur_bytes = [], [], 0
         for p in live:
             cur.append(p)
@@ -108,6 +140,11 @@ class GradientAllReduce:
                 cur, cur_bytes = [], 0
         if cur:
             groups.append(cur)
+        if tail:
+            groups.append(tail)
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
         self.buckets = []
         for plist in groups:
             flat = torch.zeros(sum(p.numel() for p in plist), dtype=torch.float32, device=plist[0].device)
@@ -116,27 +153,49 @@ class GradientAllReduce:
             off = 0
             for p in plist:
                 b.views.append(flat[off:off + p.numel()].view_as(p))
+                _grad_views[id(p)] = b.views[-1]
                 off += p.numel()
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
             self.buckets.append(b)
+        if live and live[0].is_cuda:
+            self._comm_stream = torch.cuda.Stream(device=live[0].device)
         self.zero_grad()
 
     def _make_hook(self, bucket):
         def hook(param):
             bucket.pending -= 1
             if bucket.pending == 0:
-                # gather the bucket's freshly produced gradients into its flat buffer with ONE multi-tensor copy and
-                # re-point .grad at the views: the all-reduce then averages the gradients in place
-                if bucket.flat.is_cuda:
-                    from . import ops
-                    ops.sync_aux_streams()          # weight gradients are produced on the auxiliary stream
-                torch._foreach_copy_(bucket.views, [p.grad for p in bucket.params])
-                for p, v in zip(bucket.params, bucket.views):
-                    p.grad = v
-                if self.world > 1:
-                    bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG if bucket.flat.is_cuda
-                                                  else dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._launch(bucket)
         return hook
+
+    def _launch(self, bucket):
+        """bucket complete: gather what was not produced in place, then ONE all-reduce (average)"""
+        cuda = bucket.flat.is_cuda
+        if cuda:
+            from . import ops
+            cur = torch.cuda.current_stream()
+            side = self._comm_stream
+            side.wait_stream(cur)
+            for st in ops.pending_aux_streams():           # weight gradients are produced on the auxiliary streams
+                side.wait_stream(st)
+            ctx = torch.cuda.stream(side)
+        else:
+            ctx = _NullCtx()
+        with ctx:
+            src, dst = [], []
+            for p, v in zip(bucket.params, bucket.views):
+                if p.grad.data_ptr() != v.data_ptr():      # conv weight gradients already live in the bucket
+                    src.append(p.grad)
+                    dst.append(v)
+            if dst:
+                torch._foreach_copy_(dst, src)
+            for p, v in zip(bucket.params, bucket.views):
+                p.grad = v
+            if self.world > 1:
+                bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG if cuda else dist.ReduceOp.SUM,
+                                              group=self.group, async_op=True)
+            elif cuda:
+                bucket.work = side                         # single rank: only the gather has to be joined
 
     # -- per step -------------------------------------------------------------------------------------------------
     def zero_grad(self):
@@ -153,15 +212,31 @@ class GradientAllReduce:
             return
         for b in self.buckets:
             if b.work is not None:
-                b.work.wait()                             # compute stream waits for the NCCL stream (no host sync on CUDA)
-                if not b.flat.is_cuda:
-                    b.flat.div_(self.world)               # gloo has no AVG
+                if isinstance(b.work, torch.cuda.Stream):
+                    torch.cuda.current_stream().wait_stream(b.work)
+                else:
+                    b.work.wait()                         # compute stream waits for the NCCL stream (no host sync on CUDA)
+                    if b.flat.is_cuda:
+                        torch.cuda.current_stream().wait_stream(self._comm_stream)
+                    else:
+                        b.flat.div_(self.world)           # gloo has no AVG
                 b.work = None
 
     def remove(self):
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        for b in self.buckets or []:
+            for p in b.params:
+                _grad_views.pop(id(p), None)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
 
 
 def gather_samples(local, counts, group=None):

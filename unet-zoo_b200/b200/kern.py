@@ -33,10 +33,10 @@ def _check_act(t):
     if len(sh) == 5:
         n, d, h, w, c = sh
         ld = st[3]
-        assert t.dtype == torch.bfloat16 and st[4] == 1, (t.dtype, sh, st)
+        assert t.dtype == _lib.act_dtype() and st[4] == 1, (t.dtype, sh, st)
         assert (h == 1 or st[2] == w * ld) and (d == 1 or st[1] == h * w * ld) and (n == 1 or st[0] == d * h * w * ld), st
         return n * d, h, w, c, ld
-    assert t.dtype == torch.bfloat16 and len(sh) == 4 and st[3] == 1, (t.dtype, sh, st)
+    assert t.dtype == _lib.act_dtype() and len(sh) == 4 and st[3] == 1, (t.dtype, sh, st)
     n, h, w, c = sh
     ld = st[2]
     assert (h == 1 or st[1] == w * ld) and (n == 1 or st[0] == h * w * ld), st
@@ -53,12 +53,12 @@ def pad_channels(c, weight_dim=4):
 
 
 def new_act(n, h, w, c, device):
-    return torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+    return torch.empty((n, h, w, c), dtype=_lib.act_dtype(), device=device)
 
 
 def _like(x, c):
     """fresh dense activation with x's batch / spatial dims and c channels"""
-    return torch.empty(tuple(x.shape[:-1]) + (c,), dtype=torch.bfloat16, device=x.device)
+    return torch.empty(tuple(x.shape[:-1]) + (c,), dtype=_lib.act_dtype(), device=x.device)
 
 
 def _taps(w):
@@ -97,8 +97,8 @@ class WeightPacker:
             cout, cin = w.shape[0], w.shape[1]
             taps = _taps(w)
             coutp, cinp = pad_channels(cout, w.dim()), pad_channels(cin, w.dim())
-            wf = torch.empty((taps, coutp, cinp), dtype=torch.bfloat16, device=dev)
-            wd = torch.empty((taps, cinp, coutp), dtype=torch.bfloat16, device=dev)
+            wf = torch.empty((taps, coutp, cinp), dtype=_lib.act_dtype(), device=dev)
+            wd = torch.empty((taps, cinp, coutp), dtype=_lib.act_dtype(), device=dev)
             self.packed[w.data_ptr()] = (wf, wd)
             rows.append(struct.pack('<QQQiiiiii', w.data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, cin, taps, coutp,
                                     cinp, 0))
@@ -106,10 +106,11 @@ class WeightPacker:
         raw = b''.join(rows)
         self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         self.ptr0 = self.weights[0].data_ptr()
+        self.dtype = _lib.act_dtype()
         self.versions = None
 
     def valid_for(self, weights_first):
-        return weights_first.data_ptr() == self.ptr0
+        return weights_first.data_ptr() == self.ptr0 and self.dtype == _lib.act_dtype()
 
     def refresh(self):
         blocks = min(64, max(1, (self.max_elems + 255) // 256 // 4))
@@ -139,8 +140,8 @@ def pack_conv_weight(w, need_dgrad=True):
     cout, cin = w.shape[0], w.shape[1]
     taps = _taps(w)
     coutp, cinp = pad_channels(cout, w.dim()), pad_channels(cin, w.dim())
-    wf = torch.empty((taps, coutp, cinp), dtype=torch.bfloat16, device=w.device)
-    wd = torch.empty((taps, cinp, coutp), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
+    wf = torch.empty((taps, coutp, cinp), dtype=_lib.act_dtype(), device=w.device)
+    wd = torch.empty((taps, cinp, coutp), dtype=_lib.act_dtype(), device=w.device) if need_dgrad else None
     _lib.call('uz_pack_conv_weight', _p(w.contiguous()), cout, cin, taps, _p(wf), coutp, cinp, _p(wd), cinp, coutp,
               _stream())
     return wf, wd
@@ -222,8 +223,12 @@ def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=Fa
     return out, partial
 
 
-def conv_wgrad(x, dy, taps, cin_logical, cout_logical):
-    """-> dw fp32 [cout_logical, cin_logical, taps]"""
+def conv_wgrad(x, dy, taps, cin_logical, cout_logical, out=None):
+    """-> dw fp32 [cout_logical, cin_logical, taps] (written into ``out``, any contiguous fp32 tensor of that size, when
+    given: data-parallel training lets the kernel produce the gradient inside its all-reduce bucket)"""
+    if out is not None:
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == cout_logical * cin_logical * taps
+        out = out.view(cout_logical, cin_logical, taps)
     n, h, w, cin, ldx = _check_act(x)
     _, _, _, cout, lddy = _check_act(dy)
     if x.dim() == 5 and taps == 27:
@@ -232,7 +237,7 @@ def conv_wgrad(x, dy, taps, cin_logical, cout_logical):
         if ws < 0:
             raise _lib.UnetZooLibError('uz_conv3d_wgrad: unsupported shape Cin=%d Cout=%d' % (cin, cout))
         work = torch.empty((ws,), dtype=torch.float32, device=x.device)
-        dw = torch.empty((cout_logical, cin_logical, taps), dtype=torch.float32, device=x.device)
+        dw = out if out is not None else torch.empty((cout_logical, cin_logical, taps), dtype=torch.float32, device=x.device)
         _lib.call('uz_conv3d_wgrad', _p(x), ldx, _p(dy), lddy, nb, d, h, w, cin, cout, cin_logical, cout_logical,
                   _p(work), _p(dw), _stream())
         return dw
@@ -240,7 +245,7 @@ def conv_wgrad(x, dy, taps, cin_logical, cout_logical):
     if ws < 0:
         raise _lib.UnetZooLibError('uz_conv_wgrad: unsupported shape Cin=%d Cout=%d' % (cin, cout))
     work = torch.empty((ws,), dtype=torch.float32, device=x.device)
-    dw = torch.empty((cout_logical, cin_logical, taps), dtype=torch.float32, device=x.device)
+    dw = out if out is not None else torch.empty((cout_logical, cin_logical, taps), dtype=torch.float32, device=x.device)
     _lib.call('uz_conv_wgrad', _p(x), ldx, _p(dy), lddy, n, h, w, cin, cout, taps, cin_logical, cout_logical, _p(work),
               _p(dw), _stream())
     return dw
@@ -341,7 +346,7 @@ def avgpool2_fwd(x):
     n, h, w, c, ldx = _check_act(x)
     if x.dim() == 5:
         nb, d = x.shape[0], x.shape[1]
-        out = torch.empty((nb, d // 2, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((nb, d // 2, h // 2, w // 2, c), dtype=_lib.act_dtype(), device=x.device)
         _lib.call('uz_avgpool3_fwd', _p(x), ldx, _p(out), c, nb, d // 2, h // 2, w // 2, c, _stream())
         return out
     out = new_act(n, h // 2, w // 2, c, x.device)
@@ -353,7 +358,7 @@ def avgpool2_bwd(dout):
     n, ho, wo, c, ldd = _check_act(dout)
     if dout.dim() == 5:
         nb, do = dout.shape[0], dout.shape[1]
-        dx = torch.empty((nb, do * 2, ho * 2, wo * 2, c), dtype=torch.bfloat16, device=dout.device)
+        dx = torch.empty((nb, do * 2, ho * 2, wo * 2, c), dtype=_lib.act_dtype(), device=dout.device)
         _lib.call('uz_avgpool3_bwd', _p(dout), ldd, _p(dx), c, nb, do, ho, wo, c, _stream())
         return dx
     dx = new_act(n, ho * 2, wo * 2, c, dout.device)
@@ -367,7 +372,7 @@ def upsample2x_fwd(x, align_corners=True, out=None):
         assert align_corners
         nb, d = x.shape[0], x.shape[1]
         if out is None:
-            out = torch.empty((nb, 2 * d, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+            out = torch.empty((nb, 2 * d, 2 * h, 2 * w, c), dtype=_lib.act_dtype(), device=x.device)
         ldo = _check_act(out)[4]
         _lib.call('uz_upsample3d_fwd', _p(x), ldx, _p(out), ldo, nb, d, h, w, c, _stream())
         return out
@@ -382,7 +387,7 @@ def upsample2x_bwd(dout, align_corners=True):
     n, hh, ww, c, ldd = _check_act(dout)
     if dout.dim() == 5:
         nb, dd = dout.shape[0], dout.shape[1]
-        dx = torch.empty((nb, dd // 2, hh // 2, ww // 2, c), dtype=torch.bfloat16, device=dout.device)
+        dx = torch.empty((nb, dd // 2, hh // 2, ww // 2, c), dtype=_lib.act_dtype(), device=dout.device)
         _lib.call('uz_upsample3d_bwd', _p(dout), ldd, _p(dx), c, nb, dd // 2, hh // 2, ww // 2, c, _stream())
         return dx
     dx = new_act(n, hh // 2, ww // 2, c, dout.device)
@@ -433,7 +438,7 @@ def input_pack(patch, mask, nlabels=2, cp=16):
     b, cimg = patch.shape[0], patch.shape[1]
     sp = tuple(patch.shape[2:])
     assert cimg + (nlabels if mask is not None else 0) <= cp
-    out = torch.empty((b,) + sp + (cp,), dtype=torch.bfloat16, device=patch.device)
+    out = torch.empty((b,) + sp + (cp,), dtype=_lib.act_dtype(), device=patch.device)
     patch = patch.contiguous().float()
     if mask is not None:
         mask = mask.contiguous().float()
@@ -447,7 +452,7 @@ def nchw_to_nhwc(x, ld=None):
     b, c = x.shape[0], x.shape[1]
     sp = tuple(x.shape[2:])
     ld = ld or pad16(c)
-    out = torch.empty((b,) + sp + (ld,), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((b,) + sp + (ld,), dtype=_lib.act_dtype(), device=x.device)
     _lib.call('uz_nchw_to_nhwc', _p(x.contiguous().float()), b, c, _spatial_numel(sp), _p(out), ld, _stream())
     return out
 

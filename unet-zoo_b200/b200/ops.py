@@ -77,6 +77,11 @@ def _aux_stream(device):
     return _aux['streams'][key]
 
 
+def pending_aux_streams():
+    """auxiliary streams with launches that nobody has joined yet (the dp bucket hooks make their side stream wait)"""
+    return list(_aux['pending'])
+
+
 def sync_aux_streams():
     """make the current stream wait for every outstanding auxiliary-stream launch"""
     cur = torch.cuda.current_stream()
@@ -176,6 +181,12 @@ def _fused_sums_of(da, c):
     return sums
 
 
+def _bucket_view(weight):
+    """data-parallel training: the flat-bucket view this parameter's gradient is all-reduced in (b200.dp), or None"""
+    from . import dp
+    return dp.grad_view_for(weight)
+
+
 class ConvBNAct(torch.autograd.Function):
     """Conv2D of the reference (torchlayers.py:7-29): conv(k=3 pad 1 | k=1) + bias -> BatchNorm(train) -> ReLU.
 
@@ -210,6 +221,7 @@ class ConvBNAct(torch.autograd.Function):
         ctx.relu = relu
         ctx.cin_logical = cin_logical
         ctx.wshape = weight.shape
+        ctx.weight_ref = weight
         if _FUSE_BN_BWD and not ctx.det and x.dim() == 4:
             a._uz_bn = (y, scale, shift, relu)
         return a
@@ -236,7 +248,8 @@ class ConvBNAct(torch.autograd.Function):
                 dx, _ = kern.conv_fwd(dy, wd)
         cout, cin = ctx.wshape[0], ctx.wshape[1]
         taps = kern._spatial_numel(ctx.wshape[2:])
-        dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, taps, cin, cout), (x, dy)).view(ctx.wshape)
+        dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, taps, cin, cout, out=_bucket_view(ctx.weight_ref)),
+                         (x, dy)).view(ctx.wshape)
         dbias = kern.zero_arena.get(cout, dy.device)
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None
 
@@ -314,7 +327,7 @@ class Concat(torch.autograd.Function):
     def forward(ctx, a, b, up_a, up_b, align_corners):
         ca, cb = a.shape[-1], b.shape[-1]
         sp = tuple(k * (2 if up_a else 1) for k in a.shape[1:-1])
-        out = torch.empty((a.shape[0],) + sp + (ca + cb,), dtype=torch.bfloat16, device=a.device)
+        out = torch.empty((a.shape[0],) + sp + (ca + cb,), dtype=kern._lib.act_dtype(), device=a.device)
         for src, up, sl in ((a, up_a, out[..., :ca]), (b, up_b, out[..., ca:])):
             if up:
                 kern.upsample2x_fwd(src, align_corners, out=sl)

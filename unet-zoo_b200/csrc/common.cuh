@@ -3,10 +3,18 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <utility>
+
+// kind::f16 operand format of the tcgen05 instruction descriptor: 1 = BF16 (default build), 0 = F16 (-DUZ_ACT_FP16)
+#ifdef UZ_ACT_FP16
+#define UZ_MMA_OPERAND_FORMAT 0u
+#else
+#define UZ_MMA_OPERAND_FORMAT 1u
+#endif
 
 #define UZ_OK 0
 #define UZ_ERR_ARG 1
@@ -198,8 +206,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
   uint32_t d = 0;
   d |= 1u << 4;   // D format fp32
-  d |= 1u << 7;   // A bf16
-  d |= 1u << 10;  // B bf16
+  d |= UZ_MMA_OPERAND_FORMAT << 7;   // A: bf16, or f16 in the UZ_ACT_FP16 build
+  d |= UZ_MMA_OPERAND_FORMAT << 10;  // B likewise
   d |= (a_mn_major & 1u) << 15;
   d |= (b_mn_major & 1u) << 16;
   d |= (N >> 3) << 17;
@@ -207,12 +215,39 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint
   return d;
 }
 
+// Storage type of activations and packed weights: bf16 (default build), or -- build with -DUZ_ACT_FP16 ->
+// libunetzoo_b200_fp16.so -- IEEE half: 10 mantissa bits like TF32 (8x finer than bf16) for the tolerance-matched parity
+// mode.  Both are 2 bytes, so every layout, tensor map and kernel is shared; only these conversions and the operand
+// format field of the tcgen05 instruction descriptor differ.  The C++ element type stays __nv_bfloat16 as an opaque
+// 2-byte container; the names below keep "bf16" for the default build.
+#ifdef UZ_ACT_FP16
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16lo(uint32_t v) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFFu)));
+}
+__device__ __forceinline__ float bf16hi(uint32_t v) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16)));
+}
+__device__ __forceinline__ __nv_bfloat16 f2act(float v) {
+  const unsigned short b = __half_as_ushort(__float2half_rn(v));
+  return *reinterpret_cast<const __nv_bfloat16*>(&b);
+}
+__device__ __forceinline__ float act2f(__nv_bfloat16 x) {
+  return __half2float(__ushort_as_half(*reinterpret_cast<const unsigned short*>(&x)));
+}
+#else
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ __nv_bfloat16 f2act(float v) { return __float2bfloat16(v); }
+__device__ __forceinline__ float act2f(__nv_bfloat16 x) { return __bfloat162float(x); }
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -293,7 +293,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int z0 = zn % p.D;
         const int n = zn / p.D;
         for (int ks = 0; ks < k_steps; ++ks) {
-          const int kb = ks / taps_xz, r = ks - kb * taps_xz;
+          // K order = (dz, dx) outer, channel block inner, and inside a step 16-channel sub-block outer, dy inner: the
+          // fp32 accumulation order of an output element is then (tap column, channel ascending, dy) whatever KC the plan
+          // picked -- results do not depend on the batch size (sample-sharded evaluation == single-rank, bit for bit)
+          const int r = ks / kblocks, kb = ks - r * kblocks;
           const int dz = r / 3, dx = r - dz * 3;
           uz::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * p.stage_bytes;
@@ -334,11 +337,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           const uint32_t b_lo = a_lo + (p.a_bytes >> 4);
           if (!UZ_DBG(p, 2) && uz::elect_one()) {
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
+            for (int k = 0; k < KC / 16; ++k) {
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
+              for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
+                for (int half = 0; half < 2; ++half) {
                   constexpr uint32_t kTileRowUnits = (kTile * rowb) >> 4;
                   const uint64_t adesc = desc_hi | (a_lo + (dy + 8 * half) * kTileRowUnits + k * 2);
                   const uint64_t bdesc = desc_hi | (b_lo + dy * b_tap_units + k * 2);

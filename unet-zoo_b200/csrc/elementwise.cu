@@ -58,14 +58,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
       const int o = (idx / CinP) % CoutP;
       const int t = idx / (static_cast<size_t>(CinP) * CoutP);
       float v = (i < Cin && o < Cout) ? w[(static_cast<size_t>(o) * Cin + i) * taps + src_tap(t, taps)] : 0.f;
-      wp[idx] = __float2bfloat16(v);
+      wp[idx] = uz::f2act(v);
     } else {
       const size_t j = idx - n_fwd;
       const int o = j % CoutP2;
       const int i = (j / CoutP2) % CinP2;
       const int t = j / (static_cast<size_t>(CoutP2) * CinP2);
       float v = (i < Cin && o < Cout) ? w[(static_cast<size_t>(o) * Cin + i) * taps + src_tap(taps - 1 - t, taps)] : 0.f;
-      wd[j] = __float2bfloat16(v);
+      wd[j] = uz::f2act(v);
     }
   }
 }
@@ -103,13 +103,13 @@ __global__ void __launch_bounds__(kEwThreads) pack_weight_batched_kernel(const U
       {   // forward copy: a = o, b = i (fastest)
         const int o = o0 + a, i = i0 + b;
         if (o < d.CoutP && i < d.CinP)
-          wp[(static_cast<size_t>(grp * tg + tl) * d.CoutP + o) * d.CinP + i] = __float2bfloat16(tile[a][b * tg + sl]);
+          wp[(static_cast<size_t>(grp * tg + tl) * d.CoutP + o) * d.CinP + i] = uz::f2act(tile[a][b * tg + sl]);
       }
       if (wd) {   // dgrad copy: wd[taps-1-u][i][o] = w[o][i][src(u)], u = grp*tg + tl; a = i, b = o (fastest)
         const int i = i0 + a, o = o0 + b;
         if (o < d.CoutP && i < d.CinP)
           wd[(static_cast<size_t>(d.taps - 1 - (grp * tg + tl)) * d.CinP + i) * d.CoutP + o] =
-              __float2bfloat16(tile[b][a * tg + sl]);
+              uz::f2act(tile[b][a * tg + sl]);
       }
     }
     __syncthreads();
@@ -871,7 +871,7 @@ __global__ void global_mean_fwd_kernel(const __nv_bfloat16* __restrict__ x, int 
   if (threadIdx.x < 64 && cg + threadIdx.x < C) {
     float t = 0.f;
     for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-    out[static_cast<size_t>(b) * ldo + cg + threadIdx.x] = __float2bfloat16(t / hw);
+    out[static_cast<size_t>(b) * ldo + cg + threadIdx.x] = uz::f2act(t / hw);
   }
 }
 __global__ void global_mean_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, int hw, int C,
@@ -906,12 +906,12 @@ __global__ void input_pack_kernel(const float* __restrict__ patch, const float* 
     const size_t b = pix / hw, r = pix - b * hw;
     __nv_bfloat16* o = out + pix * CP;
     int c = 0;
-    for (; c < Cimg; ++c) o[c] = __float2bfloat16(patch[(b * Cimg + c) * hw + r]);
+    for (; c < Cimg; ++c) o[c] = uz::f2act(patch[(b * Cimg + c) * hw + r]);
     if (mask) {
       const float m = mask[b * hw + r];
-      for (int k = 0; k < nlabels; ++k, ++c) o[c] = __float2bfloat16((m == static_cast<float>(k) ? 1.f : 0.f) - 0.5f);
+      for (int k = 0; k < nlabels; ++k, ++c) o[c] = uz::f2act((m == static_cast<float>(k) ? 1.f : 0.f) - 0.5f);
     }
-    for (; c < CP; ++c) o[c] = __float2bfloat16(0.f);
+    for (; c < CP; ++c) o[c] = uz::f2act(0.f);
   }
 }
 
@@ -924,7 +924,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int B, int C,
     const int c = idx % ld;
     const size_t pix = idx / ld;
     const size_t b = pix / hw, r = pix - b * hw;
-    dst[idx] = __float2bfloat16(c < C ? src[(b * C + c) * hw + r] : 0.f);
+    dst[idx] = uz::f2act(c < C ? src[(b * C + c) * hw + r] : 0.f);
   }
 }
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int ld, int B, int C, size_t hw, float* dst) {
@@ -935,7 +935,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int l
     const size_t r = idx % hw;
     const int c = (idx / hw) % C;
     const size_t b = idx / (hw * C);
-    dst[idx] = __bfloat162float(src[(b * hw + r) * ld + c]);
+    dst[idx] = uz::act2f(src[(b * hw + r) * ld + c]);
   }
 }
 

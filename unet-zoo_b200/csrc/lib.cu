@@ -113,6 +113,13 @@ int num_sms() {
 extern "C" const char* uz_last_error(void) { return g_err; }
 
 extern "C" int uz_abi_version(void) { return UZ_ABI_VERSION; }
+extern "C" int uz_storage_dtype(void) {
+#ifdef UZ_ACT_FP16
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 extern "C" int uz_device_sm_count(void) { return uz::num_sms(); }
 

@@ -37,6 +37,9 @@ long long uz_launch_count(void);
  * 128 = uz_conv_fwd returns without launching, 256 = uz_conv_wgrad returns without launching (bench.py times the step
  * with and without a kernel family to get that family's in-situ time).  0 restores normal operation. */
 int uz_set_debug_flags(int flags);
+/* profiling build only (libunetzoo_b200_prof.so, -DUZ_PROFILE_KNOBS): device buffer of 16 uint64 that CTA 0 of the
+ * small-shape tensor-core kernels fills with %globaltimer phase timestamps (tools/phase_trace.py); NULL switches it off */
+int uz_set_trace_buffer(void* device_ptr);
 /* Programmatic dependent launch for every kernel of the library (default off; environment UZ_PDL=1 or this call
  * enables it: it helps single-stream execution and hurts the multi-stream overlap the models use, profiles/r01_pdl.md). */
 int uz_set_pdl(int enabled);
@@ -157,10 +160,24 @@ int uz_bn_apply_train(const void* y, int ldy, const float* sums, float count, co
                       float eps, float momentum, float* running_mean, float* running_var, float* scale_out,
                       float* shift_out, float* mean_out, float* invstd_out, int relu, void* out, int ldo,
                       long long npix, int C, void* stream);
+/* uz_bn_apply_train with (a) an additive-coupling residual: out = residual + res_sign * act(...)  (reversible blocks,
+ * torchlayers.py:67-75 via revtorch: y1 = x1 + F(x2) written straight into the block output) and (b) stat_updates
+ * momentum updates of the running statistics in one go (2 for reversible blocks, whose F and G run a second time in
+ * backward on the same batch: SURVEY.md quirk Q7). */
+int uz_bn_apply_train_ex(const void* y, int ldy, const float* sums, float count, const float* gamma, const float* beta,
+                         float eps, float momentum, float* running_mean, float* running_var, float* scale_out,
+                         float* shift_out, float* mean_out, float* invstd_out, int relu, void* out, int ldo,
+                         long long npix, int C, const void* residual, int ld_res, int res_sign, int stat_updates,
+                         void* stream);
 /* BatchNorm(+ReLU) backward in two launches: accumulate sum(g), sum(g*y) into [2][C] (zero on entry, fp32 atomics), then
  * dy = A*g + B*y + Cc with the coefficients derived per block; dgamma / dbeta are written by the second kernel. */
 int uz_bn_bwd_reduce_sums(const void* dout, int ldd, const void* y, int ldy, const float* scale, const float* shift,
                           int relu, long long npix, int C, float* sums, void* stream);
+/* uz_bn_bwd_reduce_sums that also inverts a reversible block's coupling in the same pass over the recomputed y:
+ * inv_out = inv_in - act(y*scale + shift)   (x2 = y2 - G(y1), x1 = y1 - F(x2); revtorch backward_pass). */
+int uz_bn_bwd_reduce_sums_ex(const void* dout, int ldd, const void* y, int ldy, const float* scale, const float* shift,
+                             int relu, long long npix, int C, float* sums, const void* inv_in, int ld_inv_in,
+                             void* inv_out, int ld_inv_out, void* stream);
 int uz_bn_bwd_apply_train(const void* dout, int ldd, const void* y, int ldy, const float* scale, const float* shift,
                           int relu, const float* sums, float count, const float* gamma, const float* mean,
                           const float* invstd, float* dgamma, float* dbeta, void* dy, int lddy, long long npix, int C,
@@ -308,6 +325,13 @@ int uz_eval_sample_stats(const float* const* levels, const int* factors, int L, 
 int uz_ncc_dice_from_sums(const float* sums, const void* gt, int gt_dtype, int N, int C, int hw, int M,
                           int dice_annotator, double* work, int* dice_counts, double* out, void* stream);
 
+/* Synthetic LIDC-shaped batch generated on the device (the data plug-in's device path; replaces the
+ * per-image host work of data/batch_provider.py:43-67,131-137 for synthetic runs): patch fp32 [B,1,S,S], labels uint8
+ * [B,S,S,annotators], mask fp32 [B,1,S,S] (one random annotator per image).  A pure function of `seed` (counter-based
+ * hash RNG); unet-zoo_b200/b200/data.py holds the numpy restatement the tests compare with. */
+int uz_synth_lidc_batch(unsigned int seed, int B, int size, int annotators, float* patch, unsigned char* labels,
+                        float* mask, void* stream);
+
 /* ---- volumes: the 3-D clones of models/phiseg3D.py (NDHWC bf16 activations) ------------------------------------------ */
 /* BatchNorm3d, 1x1x1 heads, KL, residual cross-entropy, channel copies and layout conversion are the flat
  * [pixels][channels] entry points above with pixels = N*D*H*W (hw = D*H*W for the fp32 NCDHW sides). */
@@ -319,6 +343,11 @@ int uz_ncc_dice_from_sums(const float* sums, const void* gt, int gt_dtype, int N
 int uz_conv3d_fwd(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, int taps,
                   void* y, int ldy, const float* scale, const float* shift, int relu, float* stats_partial,
                   void* stream);
+/* uz_conv3d_fwd with the epilogue extensions of uz_conv_fwd_ex (fused BatchNorm-backward sums, residual; no statistics
+ * rows) */
+int uz_conv3d_fwd_ex(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, int taps,
+                     void* y, int ldy, const float* scale, const float* shift, int relu, float* stats_partial,
+                     const UzConvExtra* extra, void* stream);
 /* conv3d weight gradient: dw fp32 [Cout_logical][Cin_logical][27] (OIDHW).  Workspace from uz_wgrad3d_workspace_floats. */
 long long uz_wgrad3d_workspace_floats(int N, int D, int H, int W, int Cin, int Cout);
 int uz_conv3d_wgrad(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout,

@@ -159,3 +159,75 @@ def test_fused_bn_backward_matches_unfused_step():
     floor, fused = med(g_u, g_v), med(g_f, g_u)
     print('\nmedian gradient rel-L2: unfused vs unfused %.3e, fused vs unfused %.3e' % (floor, fused))
     assert fused <= 1.5 * floor + 1e-3
+
+
+def _torch_reversible_reference(seq, x0, g0):
+    """fp32 autograd of the same ReversibleSequence with stock torch ops (plain forward: gradients of the additive
+    coupling equal those of the inverse-recompute backward)"""
+    import copy
+    x = x0.clone().requires_grad_(True)
+    params = {}
+    cur = x
+    for bi, block in enumerate(seq.sequence.reversible_blocks):
+        x1, x2 = torch.chunk(cur, 2, dim=1)
+
+        def unit(m, inp, tag):
+            conv, bn = m.convolution[0], m.convolution[1]
+            w = conv.weight.detach().to(torch.bfloat16).float().requires_grad_(True)     # kernels round the weights to bf16
+            g, b = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+            params['%d.%s.w' % (bi, tag)], params['%d.%s.g' % (bi, tag)], params['%d.%s.b' % (bi, tag)] = w, g, b
+            y = F.conv2d(inp, w, conv.bias.detach(), padding=1)
+            return F.relu(F.batch_norm(y, None, None, g, b, True, 0.01, 1e-3))
+
+        y1 = x1 + unit(block.f_block[0], x2, 'f')
+        y2 = x2 + unit(block.g_block[0], y1, 'g')
+        cur = torch.cat([y1, y2], dim=1)
+    cur.backward(g0)
+    return cur.detach(), x.grad.detach(), params
+
+
+@pytest.mark.parametrize('shape', [(3, 32, 32, 64), (12, 8, 8, 128)])
+def test_fused_reversible_sequence_matches_nested_autograd_path(shape):
+    """ReversibleSequence forward + inverse-recompute backward: the fused kernels (coupling add inside the BatchNorm pass,
+    coupling inverse inside the BatchNorm-backward reduction, gradient add in the dgrad epilogue) and the autograd-nested
+    path (separate add launches) against fp32 torch autograd of the same stack.  The fused path rounds once less per
+    coupling, so it must be at least as close to fp32 as the nested one (x1.5 + bf16 floor); running statistics (two
+    momentum updates, quirk Q7) equal to fp32 rounding between the two paths."""
+    import torchlayers
+    n, h, w, c = shape
+    torch.manual_seed(0)
+    seq_a = torchlayers.ReversibleSequence(c, c, reversible_depth=2).cuda().train()
+    seq_b = torchlayers.ReversibleSequence(c, c, reversible_depth=2).cuda().train()
+    seq_b.load_state_dict(seq_a.state_dict())
+    x0 = bf16r(_rand(n, c, h, w, seed=3))
+    g0 = bf16r(_rand(n, c, h, w, seed=4))
+    y_ref, dx_ref, p_ref = _torch_reversible_reference(seq_a, x0, g0)
+    outs = []
+    for seq, fused in ((seq_a, True), (seq_b, False)):
+        prev = torchlayers.set_fused_reversible(fused)
+        try:
+            x = x0.clone().requires_grad_(True)
+            y = seq(x)
+            y.backward(g0)
+            torch.cuda.synchronize()
+        finally:
+            torchlayers.set_fused_reversible(prev)
+        outs.append((y.detach(), x.grad.detach(), {k: p.grad.detach() for k, p in seq.named_parameters()},
+                     {k: b.detach().clone() for k, b in seq.named_buffers()}))
+    (ya, dxa, ga, ba), (yb, dxb, gb, bb) = outs
+    ey = (rel_err(ya, y_ref), rel_err(yb, y_ref))
+    ed = (rel_err(dxa, dx_ref), rel_err(dxb, dx_ref))
+    print('\nreversible stack %s: y rel-L2 vs fp32 fused %.3e nested %.3e; dx fused %.3e nested %.3e' % (shape, ey[0], ey[1], ed[0], ed[1]))
+    assert ey[0] < 1.5 * ey[1] + 2e-3
+    assert ed[0] < 1.5 * ed[1] + 1e-2
+    wf = ga['sequence.reversible_blocks.0.f_block.0.convolution.0.weight']
+    wn = gb['sequence.reversible_blocks.0.f_block.0.convolution.0.weight']
+    assert rel_err(wf, p_ref['0.f.w'].grad) < 1.5 * rel_err(wn, p_ref['0.f.w'].grad) + 1e-2
+    gf = ga['sequence.reversible_blocks.1.g_block.0.convolution.1.weight']
+    gn = gb['sequence.reversible_blocks.1.g_block.0.convolution.1.weight']
+    assert rel_err(gf, p_ref['1.g.g'].grad) < 1.5 * rel_err(gn, p_ref['1.g.g'].grad) + 1e-2
+    for k in bb:
+        if k.endswith('num_batches_tracked'):
+            assert int(ba[k]) == int(bb[k]) == 2
+        else:
+            torch.testing.assert_close(ba[k], bb[k], rtol=2e-3, atol=1e-5)

@@ -345,7 +345,17 @@ def test_replicated_evaluation_matches_repeated_inputs(golden_dir):
         assert torch.equal(x, y)
     assert float((a[0][0] - a[0][1]).abs().max()) > 0          # the copies do differ (independent latent samples)
     with pytest.raises(ValueError):
-        net.forward(patch.cuda(), mask.cuda(), training=False, replicate=2)
+        net.forward(p1, m1, training=True, replicate=2)             # an evaluation-only shortcut
+    # several images at once: copy-major batch (index = copy * I + image), encoders once per image
+    I = patch.shape[0]
+    with torch.no_grad():
+        torch.manual_seed(12)
+        c = [t.clone() for t in net.forward(patch.cuda().repeat(3, 1, 1, 1), mask.cuda().repeat(3, 1, 1, 1), training=False)]
+        torch.manual_seed(12)
+        d = net.forward(patch.cuda(), mask.cuda(), training=False, replicate=3)
+    assert d[0].shape[0] == 3 * I
+    for x, y in zip(c, d):
+        assert torch.equal(x, y)
 
 
 @pytest.mark.parametrize('training', [True, False])

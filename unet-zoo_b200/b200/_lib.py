@@ -13,10 +13,11 @@ REPO_ROOT = os.path.dirname(PKG_ROOT)
 HEADER = os.path.join(REPO_ROOT, 'include', 'unetzoo_b200.h')
 # Two builds of the same sources: bf16 storage (the product) and IEEE-half storage (10-bit mantissa like TF32: the
 # tolerance-matched parity mode).  UNETZOO_PRECISION=fp16 or set_precision('fp16') selects the second one.
-_LIBS = {'bf16': 'libunetzoo_b200.so', 'fp16': 'libunetzoo_b200_fp16.so'}
+_LIBS = {'bf16': 'libunetzoo_b200.so', 'fp16': 'libunetzoo_b200_fp16.so',
+         'prof': 'libunetzoo_b200_prof.so'}      # prof: bf16 + profiling knobs / phase traces (`make prof`, tools only)
 PRECISION = os.environ.get('UNETZOO_PRECISION', 'bf16')
 if PRECISION not in _LIBS:
-    raise ValueError('UNETZOO_PRECISION must be bf16 or fp16 (got %r)' % PRECISION)
+    raise ValueError('UNETZOO_PRECISION must be bf16, fp16 or prof (got %r)' % PRECISION)
 LIB_PATH = os.path.join(PKG_ROOT, _LIBS[PRECISION])
 
 _SCALARS = {
@@ -74,7 +75,7 @@ def set_precision(name):
     Returns the previous name."""
     global PRECISION, LIB_PATH, _lib
     if name not in _LIBS:
-        raise ValueError('precision must be bf16 or fp16 (got %r)' % (name,))
+        raise ValueError('precision must be bf16, fp16 or prof (got %r)' % (name,))
     prev = PRECISION
     if name != prev:
         PRECISION = name

@@ -198,7 +198,7 @@ def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=Fa
             partial = zero_arena.get(2 * cout, x.device).view(1, 2, cout)      # [2][Cout] accumulators, zero on entry
     keep = None
     if bn_prev is not None or residual is not None:
-        assert x.dim() == 4 and not stats
+        assert not stats
         extra = extra or UzConvExtra()
         if bn_prev is not None:
             y_prev, sc_prev, sh_prev, relu_prev = bn_prev
@@ -211,8 +211,13 @@ def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=Fa
             assert residual.shape == out.shape
             extra.residual, extra.ld_res, extra.res_sign = residual.data_ptr(), _check_act(residual)[4], int(res_sign)
     if extra is not None:
-        _lib.call('uz_conv_fwd_ex', _p(x), n, h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy, _p(scale),
-                  _p(shift), int(relu), None if bn_prev is not None else _p(partial), ctypes.byref(extra), _stream())
+        if x.dim() == 5:
+            _lib.call('uz_conv3d_fwd_ex', _p(x), x.shape[0], x.shape[1], h, w, cin, ldx, _p(w_packed), cout, taps, _p(out),
+                      ldy, _p(scale), _p(shift), int(relu), None if bn_prev is not None else _p(partial),
+                      ctypes.byref(extra), _stream())
+        else:
+            _lib.call('uz_conv_fwd_ex', _p(x), n, h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy, _p(scale),
+                      _p(shift), int(relu), None if bn_prev is not None else _p(partial), ctypes.byref(extra), _stream())
         return out, partial
     if x.dim() == 5:
         _lib.call('uz_conv3d_fwd', _p(x), x.shape[0], x.shape[1], h, w, cin, ldx, _p(w_packed), cout, taps, _p(out), ldy,
@@ -263,29 +268,48 @@ def bn_finalize(partial, count, gamma, beta, running_mean=None, running_var=None
     return scale, shift, mean, invstd
 
 
-def bn_apply_train(y, sums, count, gamma, beta, running_mean, running_var, relu=True, eps=BN_EPS, momentum=BN_MOMENTUM):
-    """finalize + normalise + ReLU in one launch -> (a, scale, shift, mean, invstd)"""
+def bn_apply_train(y, sums, count, gamma, beta, running_mean, running_var, relu=True, eps=BN_EPS, momentum=BN_MOMENTUM,
+                   residual=None, res_sign=1, out=None, stat_updates=1):
+    """finalize + normalise + ReLU in one launch -> (a, scale, shift, mean, invstd).  ``residual``: a = residual +
+    res_sign * act(...) (reversible coupling, written into ``out`` -- e.g. a channel slice of the block output);
+    ``stat_updates``: momentum updates of the running statistics (2 for reversible blocks, quirk Q7)."""
     n, h, w, c, ldy = _check_act(y)
     dev = y.device
     st = torch.empty((4, c), dtype=torch.float32, device=dev)
-    out = _like(y, c)
-    _lib.call('uz_bn_apply_train', _p(y), ldy, _p(sums), float(count), _p(gamma), _p(beta), eps, momentum,
-              _p(running_mean), _p(running_var), _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), int(relu), _p(out), c,
-              n * h * w, c, _stream())
+    if out is None:
+        out = _like(y, c)
+    ldo = _check_act(out)[4]
+    if residual is None and stat_updates == 1:
+        _lib.call('uz_bn_apply_train', _p(y), ldy, _p(sums), float(count), _p(gamma), _p(beta), eps, momentum,
+                  _p(running_mean), _p(running_var), _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), int(relu), _p(out), ldo,
+                  n * h * w, c, _stream())
+    else:
+        ldr = _check_act(residual)[4] if residual is not None else 0
+        _lib.call('uz_bn_apply_train_ex', _p(y), ldy, _p(sums), float(count), _p(gamma), _p(beta), eps, momentum,
+                  _p(running_mean), _p(running_var), _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), int(relu), _p(out), ldo,
+                  n * h * w, c, _p(residual), ldr, int(res_sign), int(stat_updates), _stream())
     return out, st[0], st[1], st[2], st[3]
 
 
-def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True, sums=None):
+def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True, sums=None, inverse=None):
     """two launches (accumulate, apply) -> dy bf16, dgamma, dbeta; with ``sums`` ([2,C]: sum g, sum g*y, already
-    accumulated by the dgrad epilogue that produced ``dout``) only the apply pass runs"""
+    accumulated by the dgrad epilogue that produced ``dout``) only the apply pass runs.  ``inverse`` = (inv_in, inv_out):
+    the accumulate pass also writes inv_out = inv_in - act(y*scale+shift) (inverse of a reversible coupling)."""
     n, h, w, c, ldd = _check_act(dout)
     ldy = _check_act(y)[4]
     npix = n * h * w
     dev = y.device
     if sums is None:
         sums = zero_arena.get(2 * c, dev)
-        _lib.call('uz_bn_bwd_reduce_sums', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), npix, c, _p(sums),
-                  _stream())
+        if inverse is None:
+            _lib.call('uz_bn_bwd_reduce_sums', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), npix, c,
+                      _p(sums), _stream())
+        else:
+            inv_in, inv_out = inverse
+            _lib.call('uz_bn_bwd_reduce_sums_ex', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), npix, c,
+                      _p(sums), _p(inv_in), _check_act(inv_in)[4], _p(inv_out), _check_act(inv_out)[4], _stream())
+    else:
+        assert inverse is None
     dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
     dy = _like(y, c)
     _lib.call('uz_bn_bwd_apply_train', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), _p(sums), float(npix),

@@ -34,6 +34,20 @@
 
 namespace uz {
 extern int g_conv_debug_flags;
+#ifdef UZ_PROFILE_KNOBS
+// phase timestamps (globaltimer, ns) of CTA 0 of the traced kernels: uz_set_trace_buffer(ptr to 16 x uint64, device)
+extern unsigned long long* g_trace;
+#define UZ_TRACE(ptr, slot)                                                                   \
+  do {                                                                                        \
+    if ((ptr) && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) {             \
+      unsigned long long t__;                                                                 \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                 \
+      (ptr)[slot] = t__;                                                                      \
+    }                                                                                         \
+  } while (0)
+#else
+#define UZ_TRACE(ptr, slot) do { } while (0)
+#endif
 
 // last error text, readable through uz_last_error()
 void set_error(const char* fmt, ...);

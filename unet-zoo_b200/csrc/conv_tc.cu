@@ -57,6 +57,7 @@ struct ConvParams {
   int ld_res;
   float res_sign;
   int dbg;             // profiling knobs (uz_set_debug_flags): 1 = no epilogue body, 2 = no MMA, 4 = no A loads, 8 = no B loads
+  unsigned long long* trace;   // profiling build: phase timestamps of CTA 0
 };
 
 // sum over the 32 lanes of v[j], j < 16; afterwards lanes l and l + 16 hold the total of column l
@@ -127,6 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   const int kgroups = p.Cin / (KC * KB);
   const int k_iters = p.taps * kgroups;
 
+  UZ_TRACE(p.trace, warp == 0 ? 0 : 15);
   if (warp == 0 && lane == 0) {
     uz::tma_prefetch_desc(&tmap_x);
     uz::tma_prefetch_desc(&tmap_w);
@@ -141,7 +143,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       uz::fence_barrier_init();
     }
     __syncwarp();
+    UZ_TRACE(p.trace, 1);
     uz::tmem_alloc(&tmem_base_slot, p.tmem_cols);
+    UZ_TRACE(p.trace, 2);
   }
   uz::pdl_prologue();   // everything above is independent of the previous kernel's output
   for (int c = threadIdx.x; c < p.BN; c += kThreads) {
@@ -154,6 +158,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   __syncthreads();
   uz::tc_fence_after();
   const uint32_t tmem_base = uz::uniform_u32(tmem_base_slot);
+  UZ_TRACE(p.trace, warp == 0 ? 3 : 15);
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
@@ -188,6 +193,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       const int s = it % p.stages;
       uz::mbar_wait(&full_bar[s], (it / p.stages) & 1);
       uz::tc_fence_after();
+      if (it == 0) UZ_TRACE(p.trace, 4);
+      if (it == k_iters - 1) UZ_TRACE(p.trace, 5);
       const uint32_t a_lo = desc_lo0 + (uz::smem_u32(smem_a + s * a_bytes) >> 4);
       const uint32_t b_lo = desc_lo0 + (uz::smem_u32(smem_b + s * b_bytes) >> 4);
       const uint32_t a_step = a_box >> 4, b_step = b_box >> 4;
@@ -224,6 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const __nv_bfloat16* res_row = rs ? p.res + pix * p.ld_res + c_out0 : nullptr;
     uz::mbar_wait(&accum_bar, 0);
     uz::tc_fence_after();
+    UZ_TRACE(p.trace, warp == 2 ? 6 : 15);
     for (int c = 0; c < (UZ_DBG(p, 1) ? 0 : p.BN); c += 16) {
       float yv[16], rv[16];
       if (bn) {
@@ -287,8 +295,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     }
   }
 
+  UZ_TRACE(p.trace, warp == 2 ? 7 : 15);
   uz::tc_fence_before();
   __syncthreads();
+  UZ_TRACE(p.trace, warp == 0 ? 8 : 15);
   if (warp == 1) {
     uz::tc_fence_after();
     uz::tmem_dealloc(tmem_base, p.tmem_cols);
@@ -387,6 +397,9 @@ extern "C" int uz_conv_fwd_ex(const void* x, int N, int H, int W, int Cin, int l
     p.res_sign = ex->res_sign < 0 ? -1.f : 1.f;
   }
   p.dbg = uz::g_conv_debug_flags;
+#ifdef UZ_PROFILE_KNOBS
+  p.trace = uz::g_trace;
+#endif
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(bn)) cols *= 2;
   p.tmem_cols = cols;
@@ -458,12 +471,21 @@ extern "C" int uz_conv_fwd_ex(const void* x, int N, int H, int W, int Cin, int l
 extern "C" int uz_conv3d_fwd(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout,
                              int taps, void* y, int ldy, const float* scale, const float* shift, int relu,
                              float* stats_partial, void* stream) {
+  return uz_conv3d_fwd_ex(x, N, D, H, W, Cin, ldx, w_packed, Cout, taps, y, ldy, scale, shift, relu, stats_partial, nullptr,
+                          stream);
+}
+
+extern "C" int uz_conv3d_fwd_ex(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed,
+                                int Cout, int taps, void* y, int ldy, const float* scale, const float* shift, int relu,
+                                float* stats_partial, const UzConvExtra* ex, void* stream) {
   UZ_CHECK_ARG(taps == 27 || taps == 1, "uz_conv3d_fwd: taps must be 27 or 1 (got %d)", taps);
   UZ_CHECK_ARG(D > 0, "uz_conv3d_fwd: D must be positive");
   if (taps == 1) {   // pointwise: a volume is N*D images
     UZ_CHECK_ARG(static_cast<long long>(N) * D < (1ll << 30), "uz_conv3d_fwd: batch too large");
-    return uz_conv_fwd(x, N * D, H, W, Cin, ldx, w_packed, Cout, 1, y, ldy, scale, shift, relu, stats_partial, stream);
+    return uz_conv_fwd_ex(x, N * D, H, W, Cin, ldx, w_packed, Cout, 1, y, ldy, scale, shift, relu, stats_partial, ex,
+                          stream);
   }
+  UZ_CHECK_ARG(!ex || !ex->stats_rows, "uz_conv3d_fwd_ex: per-CTA statistics rows are a 2-D feature");
   UZ_CHECK_ARG(x && w_packed && y, "uz_conv3d_fwd: null pointer");
   UZ_CHECK_ARG(Cin % 16 == 0 && Cin > 0, "uz_conv3d_fwd: Cin must be a positive multiple of 16 (got %d)", Cin);
   UZ_CHECK_ARG(Cout % 16 == 0 && Cout > 0, "uz_conv3d_fwd: Cout must be a positive multiple of 16 (got %d)", Cout);
@@ -473,7 +495,7 @@ extern "C" int uz_conv3d_fwd(const void* x, int N, int D, int H, int W, int Cin,
                "uz_conv3d_fwd: pointers must be 16-byte aligned");
   if UZ_KNOB(128) return UZ_OK;
   int handled = 0;
-  int rc = uz::conv2_launch(x, N, D, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, nullptr,
+  int rc = uz::conv2_launch(x, N, D, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, ex,
                             stream, &handled);
   if (rc) return rc;
   UZ_CHECK_ARG(handled, "uz_conv3d_fwd: no kernel plan for Cin=%d Cout=%d", Cin, Cout);

@@ -267,7 +267,11 @@ __global__ void bn_apply_train_kernel(const __nv_bfloat16* __restrict__ y, int l
                                       float count, const float* __restrict__ gamma, const float* __restrict__ beta,
                                       float eps, float momentum, float* running_mean, float* running_var,
                                       float* scale_out, float* shift_out, float* mean_out, float* invstd_out, int relu,
-                                      __nv_bfloat16* out, int ldo, size_t npix, int C) {
+                                      __nv_bfloat16* out, int ldo, size_t npix, int C,
+                                      const __nv_bfloat16* __restrict__ res, int ldr, float res_sign, int updates) {
+  // res != nullptr: out = res + res_sign * act(...) (additive coupling of a reversible block written straight into the
+  // block output); updates: momentum updates of the running statistics (2 for reversible blocks: their F and G run a
+  // second time in backward with the same batch, torchlayers.py:71-78 via revtorch)
   uz::pdl_prologue();
   extern __shared__ float sm[];          // [2][C]: scale, shift
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -286,8 +290,13 @@ __global__ void bn_apply_train_kernel(const __nv_bfloat16* __restrict__ y, int l
       invstd_out[c] = invstd;
       if (running_mean) {
         const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        float rm = running_mean[c], rv = running_var[c];
+        for (int u = 0; u < updates; ++u) {
+          rm = (1.f - momentum) * rm + momentum * mean;
+          rv = (1.f - momentum) * rv + momentum * unbiased;
+        }
+        running_mean[c] = rm;
+        running_var[c] = rv;
       }
     }
   }
@@ -303,20 +312,22 @@ __global__ void bn_apply_train_kernel(const __nv_bfloat16* __restrict__ y, int l
   for (int j = 0; j < 8; ++j) { sc[j] = sm[c0 + j]; sh[j] = sm[C + c0 + j]; }
   // four independent 16-byte loads in flight per thread before the first use (HBM latency x bandwidth needs ~64 KB per SM)
   size_t pix = blockIdx.x * prow + threadIdx.x / chunks;
-  for (; pix + 3 * pstride < npix; pix += 4 * pstride) {
-    uint4 v[4];
+  if (res == nullptr) {
+    for (; pix + 3 * pstride < npix; pix += 4 * pstride) {
+      uint4 v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const uint4*>(y + (pix + u * pstride) * ldy + c0));
+      for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const uint4*>(y + (pix + u * pstride) * ldy + c0));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float f[8];
-      unpack8(v[u], f);
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        f[j] = fmaf(f[j], sc[j], sh[j]);
-        if (relu) f[j] = fmaxf(f[j], 0.f);
+        for (int j = 0; j < 8; ++j) {
+          f[j] = fmaf(f[j], sc[j], sh[j]);
+          if (relu) f[j] = fmaxf(f[j], 0.f);
+        }
+        *reinterpret_cast<uint4*>(out + (pix + u * pstride) * ldo + c0) = pack8(f);
       }
-      *reinterpret_cast<uint4*>(out + (pix + u * pstride) * ldo + c0) = pack8(f);
     }
   }
   for (; pix < npix; pix += pstride) {
@@ -326,6 +337,12 @@ __global__ void bn_apply_train_kernel(const __nv_bfloat16* __restrict__ y, int l
     for (int j = 0; j < 8; ++j) {
       f[j] = fmaf(f[j], sc[j], sh[j]);
       if (relu) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (res != nullptr) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(res + pix * ldr + c0), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(res_sign, f[j], r[j]);
     }
     *reinterpret_cast<uint4*>(out + pix * ldo + c0) = pack8(f);
   }
@@ -398,7 +415,10 @@ __global__ void bn_bwd_apply_train_kernel(const __nv_bfloat16* __restrict__ dout
 // block = (C/8 channel chunks) x rows; grid-stride over pixel rows; block result -> partial[block][2][C].
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, const __nv_bfloat16* __restrict__ y,
                                      int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
-                                     int relu, size_t npix, int C, float* partial, int atomic_out) {
+                                     int relu, size_t npix, int C, float* partial, int atomic_out,
+                                     const __nv_bfloat16* __restrict__ inv_in, int ldi, __nv_bfloat16* inv_out, int ldo) {
+  // inv_in != nullptr: also inv_out = inv_in - act(y*scale+shift): the inverse of a reversible block's additive coupling
+  // (x2 = y2 - G(y1)) computed in the pass that reads the recomputed y anyway
   uz::pdl_prologue();
   extern __shared__ float red[];  // [rows][2][C]
   const int chunks = C / 8;
@@ -425,18 +445,34 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int
     };
     const size_t pstride = static_cast<size_t>(gridDim.x) * rows;
     size_t pix = static_cast<size_t>(blockIdx.x) * rows + r;
-    for (; pix + 3 * pstride < npix; pix += 4 * pstride) {      // eight independent 16-byte loads in flight per thread
-      uint4 vg[4], vy[4];
+    if (inv_in == nullptr) {
+      for (; pix + 3 * pstride < npix; pix += 4 * pstride) {      // eight independent 16-byte loads in flight per thread
+        uint4 vg[4], vy[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        vg[u] = *reinterpret_cast<const uint4*>(dout + (pix + u * pstride) * ldd + c0);
-        vy[u] = *reinterpret_cast<const uint4*>(y + (pix + u * pstride) * ldy + c0);
+        for (int u = 0; u < 4; ++u) {
+          vg[u] = *reinterpret_cast<const uint4*>(dout + (pix + u * pstride) * ldd + c0);
+          vy[u] = *reinterpret_cast<const uint4*>(y + (pix + u * pstride) * ldy + c0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) one(vg[u], vy[u]);
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) one(vg[u], vy[u]);
     }
-    for (; pix < npix; pix += pstride)
-      one(*reinterpret_cast<const uint4*>(dout + pix * ldd + c0), *reinterpret_cast<const uint4*>(y + pix * ldy + c0));
+    for (; pix < npix; pix += pstride) {
+      const uint4 vy = *reinterpret_cast<const uint4*>(y + pix * ldy + c0);
+      one(*reinterpret_cast<const uint4*>(dout + pix * ldd + c0), vy);
+      if (inv_in != nullptr) {
+        float yy[8], r[8];
+        unpack8(vy, yy);
+        unpack8(*reinterpret_cast<const uint4*>(inv_in + pix * ldi + c0), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = fmaf(yy[j], sc[j], sh[j]);
+          if (relu) a = fmaxf(a, 0.f);
+          r[j] -= a;
+        }
+        *reinterpret_cast<uint4*>(inv_out + pix * ldo + c0) = pack8(r);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       red[(r * 2) * C + c0 + j] = sg[j];
@@ -1037,14 +1073,25 @@ extern "C" int uz_bn_bwd_reduce(const void* dout, int ldd, const void* y, int ld
   const size_t smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);
   uz::launch(bn_bwd_reduce_kernel, blocks, threads, smem, ST(stream), static_cast<const __nv_bfloat16*>(dout), ldd,
                                                              static_cast<const __nv_bfloat16*>(y), ldy, scale, shift,
-                                                             relu, static_cast<size_t>(npix), C, partial, 0);
+                                                             relu, static_cast<size_t>(npix), C, partial, 0,
+                                                             static_cast<const __nv_bfloat16*>(nullptr), 0,
+                                                             static_cast<__nv_bfloat16*>(nullptr), 0);
   UZ_CHECK_LAUNCH("uz_bn_bwd_reduce");
   return UZ_OK;
 }
 
 extern "C" int uz_bn_bwd_reduce_sums(const void* dout, int ldd, const void* y, int ldy, const float* scale,
                                      const float* shift, int relu, long long npix, int C, float* sums, void* stream) {
+  return uz_bn_bwd_reduce_sums_ex(dout, ldd, y, ldy, scale, shift, relu, npix, C, sums, nullptr, 0, nullptr, 0, stream);
+}
+
+extern "C" int uz_bn_bwd_reduce_sums_ex(const void* dout, int ldd, const void* y, int ldy, const float* scale,
+                                        const float* shift, int relu, long long npix, int C, float* sums,
+                                        const void* inv_in, int ld_inv_in, void* inv_out, int ld_inv_out, void* stream) {
   UZ_CHECK_ARG(dout && y && scale && shift && sums, "uz_bn_bwd_reduce_sums: null pointer");
+  UZ_CHECK_ARG((inv_in == nullptr) == (inv_out == nullptr) &&
+                   (!inv_in || (ld_inv_in % 8 == 0 && ld_inv_out % 8 == 0 && aligned16(inv_in) && aligned16(inv_out))),
+               "uz_bn_bwd_reduce_sums_ex: bad inverse-coupling operands");
   UZ_CHECK_ARG(C % 8 == 0 && ldd % 8 == 0 && ldy % 8 == 0, "uz_bn_bwd_reduce_sums: alignment");
   const int chunks = C / 8;
   int threads = 256;
@@ -1054,7 +1101,9 @@ extern "C" int uz_bn_bwd_reduce_sums(const void* dout, int ldd, const void* y, i
   const size_t smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);
   uz::launch(bn_bwd_reduce_kernel, blocks, threads, smem, ST(stream), static_cast<const __nv_bfloat16*>(dout), ldd,
                                                              static_cast<const __nv_bfloat16*>(y), ldy, scale, shift,
-                                                             relu, static_cast<size_t>(npix), C, sums, 1);
+                                                             relu, static_cast<size_t>(npix), C, sums, 1,
+                                                             static_cast<const __nv_bfloat16*>(inv_in), ld_inv_in,
+                                                             static_cast<__nv_bfloat16*>(inv_out), ld_inv_out);
   UZ_CHECK_LAUNCH("uz_bn_bwd_reduce_sums");
   return UZ_OK;
 }
@@ -1063,12 +1112,25 @@ extern "C" int uz_bn_apply_train(const void* y, int ldy, const float* sums, floa
                                  const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                  float* scale_out, float* shift_out, float* mean_out, float* invstd_out, int relu,
                                  void* out, int ldo, long long npix, int C, void* stream) {
+  return uz_bn_apply_train_ex(y, ldy, sums, count, gamma, beta, eps, momentum, running_mean, running_var, scale_out,
+                              shift_out, mean_out, invstd_out, relu, out, ldo, npix, C, nullptr, 0, 1, 1, stream);
+}
+
+extern "C" int uz_bn_apply_train_ex(const void* y, int ldy, const float* sums, float count, const float* gamma,
+                                    const float* beta, float eps, float momentum, float* running_mean,
+                                    float* running_var, float* scale_out, float* shift_out, float* mean_out,
+                                    float* invstd_out, int relu, void* out, int ldo, long long npix, int C,
+                                    const void* residual, int ld_res, int res_sign, int stat_updates, void* stream) {
   UZ_CHECK_ARG(y && sums && scale_out && shift_out && mean_out && invstd_out && out, "uz_bn_apply_train: null pointer");
+  UZ_CHECK_ARG(!residual || (ld_res % 8 == 0 && aligned16(residual)), "uz_bn_apply_train_ex: bad residual operand");
+  UZ_CHECK_ARG(stat_updates >= 0 && stat_updates <= 4, "uz_bn_apply_train_ex: stat_updates %d", stat_updates);
   UZ_CHECK_ARG(C % 8 == 0 && C <= 8192 && ldy % 8 == 0 && ldo % 8 == 0 && npix > 0, "uz_bn_apply_train: bad arguments");
   const int threads = chunk_aligned_threads(C / 8);
   uz::launch(bn_apply_train_kernel, ew_blocks(static_cast<size_t>(npix) * (C / 8), threads), threads, 2 * C * sizeof(float), ST(stream), static_cast<const __nv_bfloat16*>(y), ldy, sums, count, gamma, beta, eps,
                                         momentum, running_mean, running_var, scale_out, shift_out, mean_out, invstd_out,
-                                        relu, static_cast<__nv_bfloat16*>(out), ldo, static_cast<size_t>(npix), C);
+                                        relu, static_cast<__nv_bfloat16*>(out), ldo, static_cast<size_t>(npix), C,
+                                        static_cast<const __nv_bfloat16*>(residual), ld_res, res_sign < 0 ? -1.f : 1.f,
+                                        stat_updates);
   UZ_CHECK_LAUNCH("uz_bn_apply_train");
   return UZ_OK;
 }
@@ -1264,5 +1326,95 @@ extern "C" int uz_nhwc_to_nchw(const void* src, int ld, int B, int C, long long 
   uz::launch(nhwc_to_nchw_kernel, ew_blocks(static_cast<size_t>(B) * C * hw), kEwThreads, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(src), ld, B, C, static_cast<size_t>(hw), dst);
   UZ_CHECK_LAUNCH("uz_nhwc_to_nchw");
+  return UZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Synthetic LIDC-shaped batches generated ON THE DEVICE (the reference's BatchProvider is per-image
+// host code, data/batch_provider.py:43-67,131-137; this is the data plug-in's device path).  Counter-based RNG: every
+// value is a hash of (seed, image, stream, index), so a batch is a pure function of its seed -- reproducible, no state.
+//   patch  fp32 [B,1,S,S]   clip(N(0,1) * 0.25, -0.5, 0.5) + 0.2 * mean_m(labels)   (images are [0,1] - 0.5 in the reference)
+//   labels uint8 [B,S,S,M]  M annotators: jittered filled ellipses, each empty with probability 1/4
+//   mask   fp32 [B,1,S,S]   the labels of one random annotator per image (train_model.py:103-106)
+namespace {
+__host__ __device__ inline uint32_t uz_mix32(uint32_t h) {      // murmur3 finaliser
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__host__ __device__ inline uint32_t uz_hash4(uint32_t seed, uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t h = uz_mix32(seed ^ 0x9E3779B9u);
+  h = uz_mix32(h ^ (a * 0x85EBCA6Bu + 0x27D4EB2Fu));
+  h = uz_mix32(h ^ (b * 0xC2B2AE35u + 0x165667B1u));
+  h = uz_mix32(h ^ (c * 0x9E3779B1u + 0x85EBCA77u));
+  return h;
+}
+__host__ __device__ inline float uz_u01(uint32_t h) { return (static_cast<float>(h >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+struct SynthImage {          // per-image ellipse parameters, derived by thread 0 of the block's image
+  float cy[8], cx[8], ry[8], rx[8];
+  int empty[8];
+  int pick;
+};
+
+__device__ inline float uz_normal(uint32_t seed, uint32_t a, uint32_t b, uint32_t c) {
+  const float u1 = uz_u01(uz_hash4(seed, a, b, c)), u2 = uz_u01(uz_hash4(seed, a, b, c + 0x40000000u));
+  return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+__global__ void __launch_bounds__(256)
+synth_lidc_kernel(uint32_t seed, int B, int S, int M, float* __restrict__ patch, uint8_t* __restrict__ labels,
+                  float* __restrict__ mask) {
+  uz::pdl_prologue();
+  __shared__ SynthImage im;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    // explicit single-rounding operations (no FMA contraction): b200/data.py restates this arithmetic in numpy fp32
+    const float fs = static_cast<float>(S);
+    auto lin = [](float a, float k, float u) { return __fadd_rn(a, __fmul_rn(k, u)); };
+    const float cy = __fmul_rn(lin(0.3f, 0.4f, uz_u01(uz_hash4(seed, b, 1, 0))), fs);
+    const float cx = __fmul_rn(lin(0.3f, 0.4f, uz_u01(uz_hash4(seed, b, 1, 1))), fs);
+    const float ry = __fmul_rn(lin(0.06f, 0.12f, uz_u01(uz_hash4(seed, b, 1, 2))), fs);
+    const float rx = __fmul_rn(lin(0.06f, 0.12f, uz_u01(uz_hash4(seed, b, 1, 3))), fs);
+    for (int m = 0; m < M; ++m) {
+      im.empty[m] = uz_u01(uz_hash4(seed, b, 2, m)) < 0.25f;
+      im.cy[m] = __fadd_rn(cy, __fmul_rn(__fmul_rn(0.02f, fs), uz_normal(seed, b, 3, m)));
+      im.cx[m] = __fadd_rn(cx, __fmul_rn(__fmul_rn(0.02f, fs), uz_normal(seed, b, 4, m)));
+      im.ry[m] = __fmul_rn(ry, lin(0.8f, 0.45f, uz_u01(uz_hash4(seed, b, 5, m))));
+      im.rx[m] = __fmul_rn(rx, lin(0.8f, 0.45f, uz_u01(uz_hash4(seed, b, 6, m))));
+    }
+    im.pick = static_cast<int>(uz_hash4(seed, b, 7, 0) % static_cast<uint32_t>(M));
+  }
+  __syncthreads();
+  const int hw = S * S;
+  for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < hw; px += gridDim.x * blockDim.x) {
+    const int y = px / S, x = px - y * S;
+    float v = 0.25f * uz_normal(seed, b, 8, static_cast<uint32_t>(px));
+    v = fminf(fmaxf(v, -0.5f), 0.5f);
+    int count = 0, picked = 0;
+    for (int m = 0; m < M; ++m) {
+      int inside = 0;
+      if (!im.empty[m]) {
+        const float dy = __fdiv_rn(__fsub_rn(static_cast<float>(y), im.cy[m]), im.ry[m]);
+        const float dx = __fdiv_rn(__fsub_rn(static_cast<float>(x), im.cx[m]), im.rx[m]);
+        inside = __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)) <= 1.0f;
+      }
+      labels[(static_cast<size_t>(b) * hw + px) * M + m] = static_cast<uint8_t>(inside);
+      count += inside;
+      if (m == im.pick) picked = inside;
+    }
+    patch[static_cast<size_t>(b) * hw + px] = v + 0.2f * (static_cast<float>(count) / static_cast<float>(M));
+    mask[static_cast<size_t>(b) * hw + px] = static_cast<float>(picked);
+  }
+}
+}  // namespace
+
+extern "C" int uz_synth_lidc_batch(unsigned int seed, int B, int size, int annotators, float* patch,
+                                   unsigned char* labels, float* mask, void* stream) {
+  UZ_CHECK_ARG(patch && labels && mask && B > 0 && size > 0 && annotators >= 1 && annotators <= 8,
+               "uz_synth_lidc_batch: bad arguments");
+  int bx = (size * size + 255) / 256;
+  if (bx > 64) bx = 64;
+  uz::launch(synth_lidc_kernel, dim3(bx, B, 1), 256, 0, ST(stream), seed, B, size, annotators, patch, labels, mask);
+  UZ_CHECK_LAUNCH("uz_synth_lidc_batch");
   return UZ_OK;
 }

@@ -133,6 +133,19 @@ extern "C" int uz_set_smem_carveout(int percent) {
   return UZ_OK;
 }
 
+#ifdef UZ_PROFILE_KNOBS
+namespace uz { unsigned long long* g_trace = nullptr; }
+#endif
+extern "C" int uz_set_trace_buffer(void* device_ptr) {
+#ifdef UZ_PROFILE_KNOBS
+  uz::g_trace = static_cast<unsigned long long*>(device_ptr);
+  return UZ_OK;
+#else
+  UZ_CHECK_ARG(device_ptr == nullptr, "uz_set_trace_buffer: this library was built without -DUZ_PROFILE_KNOBS");
+  return UZ_OK;
+#endif
+}
+
 extern "C" int uz_set_pdl(int enabled) {
   uz::g_pdl = enabled ? 1 : 0;
   return UZ_OK;

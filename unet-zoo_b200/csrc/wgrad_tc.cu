@@ -31,11 +31,91 @@ struct WgradParams {
   int TW, TH, TN;
   int tilesW, tilesH, num_tiles;
   int taps_per_cta, tap_groups;
-  int a_boxes, b_boxes;     // 64-channel boxes per stage for dy (<=2) and x
+  int a_boxes, b_boxes;     // 64-channel boxes per stage for dy (<=2) and x (of this CTA's input-channel chunk)
+  int ci_w, ci_chunks;      // input channels per CTA (Cin, or 64 for tiny layers) and number of such chunks
+  int co_blocks;
   int stages;
   uint32_t tmem_cols;
   float* partial;           // [splits][taps][Cout][Cin]
+  unsigned long long* trace;   // profiling build: phase timestamps of CTA 0
 };
+
+
+// Epilogue of the weight-gradient kernels.  The accumulator block [128 rows (TMEM lanes) x ncols] fp32 used to leave one
+// row per thread: every 16-byte store instruction of a warp touched 32 different 32-byte sectors, the LSU -- not the
+// tensor core, not HBM -- bounded the small launches (phase trace, profiles/r02_phase_trace.md: 11 of 14 us of a
+// 192 -> 192 launch were these stores).  Now the block is staged in the (by then idle) pipeline shared memory, rows
+// padded by 16 bytes so the row-per-thread 16-byte writes are bank-conflict free, and written out with consecutive
+// threads on consecutive 16 bytes: 512 contiguous bytes per warp store.
+__device__ __forceinline__ void store_acc_block(uint32_t taddr, int ncols, bool have_acc, float* stage, float* dst,
+                                                size_t ld, int valid_rows, int row, int et,
+                                                unsigned long long* trace = nullptr) {
+  const int pitch = ncols + 4;
+  float* srow = stage + static_cast<size_t>(row) * pitch;
+  int c = 0;
+  for (; c + 32 <= ncols; c += 32) {            // two TMEM loads in flight per wait
+    uint32_t r[16], r2[16];
+    if (have_acc) {
+      uz::tmem_ld16(taddr + c, r);
+      uz::tmem_ld16(taddr + c + 16, r2);
+      uz::tmem_ld_wait();
+      if (c == 0) UZ_TRACE(trace, et == 0 ? 9 : 15);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { r[j] = 0u; r2[j] = 0u; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(srow + c + 4 * j) =
+          make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                      __uint_as_float(r[4 * j + 3]));
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(srow + c + 16 + 4 * j) =
+          make_float4(__uint_as_float(r2[4 * j]), __uint_as_float(r2[4 * j + 1]), __uint_as_float(r2[4 * j + 2]),
+                      __uint_as_float(r2[4 * j + 3]));
+  }
+  for (; c < ncols; c += 16) {
+    uint32_t r[16];
+    if (have_acc) {
+      uz::tmem_ld16(taddr + c, r);
+      uz::tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(srow + c + 4 * j) =
+          make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                      __uint_as_float(r[4 * j + 3]));
+  }
+  UZ_TRACE(trace, et == 0 ? 10 : 15);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  UZ_TRACE(trace, et == 0 ? 11 : 15);
+  // copy-out: a warp writes whole rows (lane = 16-byte column chunk, ncols <= 128 -> one chunk per lane), eight rows per
+  // iteration with all loads issued before the stores -- with four warps per SM nothing else hides the shared-memory
+  // latency (a one-float4-per-iteration loop ran at ~160 cycles per iteration: 24 GB/s per SM)
+  const int n4 = ncols >> 2;
+  const int ew = et >> 5, el = et & 31;
+  if (el < n4) {
+    for (int r0 = ew; r0 < valid_rows; r0 += 32) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int rr = r0 + 4 * u;
+        if (rr < valid_rows) v[u] = *reinterpret_cast<const float4*>(stage + static_cast<size_t>(rr) * pitch + 4 * el);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int rr = r0 + 4 * u;
+        if (rr < valid_rows) *reinterpret_cast<float4*>(dst + static_cast<size_t>(rr) * ld + 4 * el) = v[u];
+      }
+    }
+  }
+  UZ_TRACE(trace, et == 0 ? 12 : 15);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
 
 template <int PIX>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -56,13 +136,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int split = blockIdx.x, splits = gridDim.x;
   const int group = blockIdx.y % p.tap_groups;
-  const int co0 = (blockIdx.y / p.tap_groups) * 128;
+  const int co0 = ((blockIdx.y / p.tap_groups) % p.co_blocks) * 128;
+  const int ci0 = (blockIdx.y / (p.tap_groups * p.co_blocks)) * p.ci_w;     // this CTA's input-channel chunk
+  int ncin = p.Cin - ci0; if (ncin > p.ci_w) ncin = p.ci_w;
   const int tap0 = group * p.taps_per_cta;
   int ntaps = p.taps - tap0; if (ntaps > p.taps_per_cta) ntaps = p.taps_per_cta;
 
   int my_tiles = 0;
   if (split < p.num_tiles) my_tiles = (p.num_tiles - split + splits - 1) / splits;
   const int iters = my_tiles * ntaps;
+  UZ_TRACE(p.trace, warp == 0 ? 0 : 15);
 
   if (warp == 0 && lane == 0) {
     uz::tma_prefetch_desc(&tmap_dy);
@@ -78,13 +161,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
       uz::fence_barrier_init();
     }
     __syncwarp();
+    UZ_TRACE(p.trace, 1);
     uz::tmem_alloc(&tmem_base_slot, p.tmem_cols);
+    UZ_TRACE(p.trace, 2);
   }
   uz::pdl_prologue();   // everything above is independent of the previous kernel's output
   uz::tc_fence_before();
   __syncthreads();
   uz::tc_fence_after();
   const uint32_t tmem_base = uz::uniform_u32(tmem_base_slot);
+  UZ_TRACE(p.trace, warp == 0 ? 3 : 15);
 
   if (warp == 0) {
     {
@@ -106,8 +192,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
           uz::mbar_expect_tx(&full_bar[s], stage_bytes);
           for (int b = 0; b < p.a_boxes; ++b)
             uz::tma_load_4d(sa + b * box_bytes, &tmap_dy, &full_bar[s], co0 + b * 64, x0, y0, n0);
-          for (int b = 0; b < p.b_boxes; ++b)
-            uz::tma_load_4d(sb + b * box_bytes, &tmap_x, &full_bar[s], b * 64, x0 + dx, y0 + dy, n0);
+          for (int b = 0; b < p.b_boxes; ++b)      // boxes past Cin are zero-filled by TMA (the last chunk may be narrower)
+            uz::tma_load_4d(sb + b * box_bytes, &tmap_x, &full_bar[s], ci0 + b * 64, x0 + dx, y0 + dy, n0);
         }
         __syncwarp();
       }
@@ -117,19 +203,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     // are invariant; the PIX/16 K steps are unrolled so every MMA owns its uniform registers (see conv_tc2.cu).
     const uint64_t desc_hi = uz::umma_desc(0, box_bytes, 1024, 128) & 0xFFFFFFFF00000000ull;
     const uint32_t desc_lo0 = static_cast<uint32_t>(uz::umma_desc(0, box_bytes, 1024, 128) & 0xFFFFFFFFull);
-    const int n0 = p.Cin < 256 ? p.Cin : 256;          // first N chunk
-    const int n1 = p.Cin - n0;                         // second N chunk (Cin in (256, 512]) or 0
+    const int n0 = ncin < 256 ? ncin : 256;            // first N chunk
+    const int n1 = ncin - n0;                          // second N chunk (channels in (256, 512]) or 0
     const uint32_t idesc0 = uz::umma_idesc_bf16(128, n0, 1, 1);
     const uint32_t idesc1 = uz::umma_idesc_bf16(128, n1 > 0 ? n1 : 16, 1, 1);
     for (int it = 0; it < iters; ++it) {
       const int s = it % p.stages;
       uz::mbar_wait(&full_bar[s], (it / p.stages) & 1);
       uz::tc_fence_after();
+      if (it == 0) UZ_TRACE(p.trace, 4);
+      if (it == iters - 1) UZ_TRACE(p.trace, 5);
       const int ti = it / ntaps;
       const int tl = it - ti * ntaps;  // local tap index -> accumulator slot
       const uint32_t a_lo = desc_lo0 + (uz::smem_u32(smem + s * stage_bytes) >> 4);
       const uint32_t b_lo = a_lo + (a_bytes >> 4);
-      const uint32_t dcol = tmem_base + tl * p.Cin;
+      const uint32_t dcol = tmem_base + tl * p.ci_w;
       if (uz::elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < PIX / 16; ++ks) {
@@ -147,35 +235,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;            // co within the block
-    const int co = co0 + row;
     if (iters > 0) {
       uz::mbar_wait(&accum_bar, 0);
       uz::tc_fence_after();
     }
+    UZ_TRACE(p.trace, warp == 2 ? 6 : 15);
+    int valid_rows = p.Cout - co0;
+    if (valid_rows > 128) valid_rows = 128;
+    float* stage = reinterpret_cast<float*>(smem);          // pipeline buffers: idle once the accumulators are complete
     for (int tl = 0; tl < ntaps; ++tl) {
-      float* dst = p.partial + ((static_cast<size_t>(split) * p.taps + tap0 + tl) * p.Cout + co) * p.Cin;
-      for (int c = 0; c < p.Cin; c += 16) {
-        uint32_t r[16];
-        if (iters > 0) {
-          uz::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tl * p.Cin + c, r);
-          uz::tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = 0u;
-        }
-        if (co < p.Cout) {
-          float4* d4 = reinterpret_cast<float4*>(dst + c);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                __uint_as_float(r[4 * j + 3]));
-        }
+      float* dst = p.partial + ((static_cast<size_t>(split) * p.taps + tap0 + tl) * p.Cout + co0) * p.Cin + ci0;
+      for (int c0 = 0; c0 < ncin; c0 += 128) {             // column blocks of <= 128 (staging: 128 x 132 floats)
+        const int ncols = ncin - c0 < 128 ? ncin - c0 : 128;
+        store_acc_block(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tl * p.ci_w + c0, ncols, iters > 0, stage,
+                        dst + c0, p.Cin, valid_rows, row, threadIdx.x - 64,
+#ifdef UZ_PROFILE_KNOBS
+                        (tl == 0 && c0 == 0) ? p.trace : nullptr
+#else
+                        nullptr
+#endif
+        );
       }
     }
   }
 
+  UZ_TRACE(p.trace, warp == 2 ? 7 : 15);
   uz::tc_fence_before();
   __syncthreads();
+  UZ_TRACE(p.trace, warp == 0 ? 8 : 15);
   if (warp == 1) {
     uz::tc_fence_after();
     uz::tmem_dealloc(tmem_base, p.tmem_cols);
@@ -203,6 +290,7 @@ struct Wgrad2Params {
   int nz;                      // z taps: 1 (2-D) or 3 (volumes); tensor maps are always 5-D (C, W, H, D, N)
   int tilesW, tilesH, num_tiles;
   int ci_chunks, co_blocks;
+  int ci_w;                    // input channels per CTA: 128, or 64 when the layer has few pixel tiles (output-bound)
   int a_boxes;
   int stages;
   float* partial;           // [splits][9 * nz][Cout][Cin]
@@ -231,8 +319,8 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
   const int dx = dxz % 3, dz = dxz / 3;
   const int z_off = p.nz >> 1;
   const int co0 = (blockIdx.y / (p.ci_chunks * 3 * p.nz)) * 128;
-  const int ci0 = cc * 128;
-  int nch = p.Cin - ci0; if (nch > 128) nch = 128;      // input channels of this CTA (multiple of 16)
+  const int ci0 = cc * p.ci_w;
+  int nch = p.Cin - ci0; if (nch > p.ci_w) nch = p.ci_w;   // input channels of this CTA (multiple of 16)
   const int b_boxes = (nch + 63) / 64;
   const uint32_t a_bytes = p.a_boxes * kW2ABox;
   const uint32_t stage_bytes = a_bytes + 2 * kW2BBox;     // slab area sized for two boxes
@@ -314,31 +402,18 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
     }
   } else {
     const int q = warp & 3;
-    const int co = co0 + q * 32 + lane;
     if (my_tiles > 0) {
       uz::mbar_wait(&accum_bar, 0);
       uz::tc_fence_after();
     }
+    int valid_rows = p.Cout - co0;
+    if (valid_rows > 128) valid_rows = 128;
+    float* stage = reinterpret_cast<float*>(smem);          // pipeline buffers: idle once the accumulators are complete
     for (int dy = 0; dy < 3; ++dy) {
       const int tap = (dz * 3 + dy) * 3 + dx;      // OI(D)HW order (kd*3 + kh)*3 + kw; dz == 0 in 2-D
-      float* dst = p.partial + ((static_cast<size_t>(split) * 9 * p.nz + tap) * p.Cout + co) * p.Cin + ci0;
-      for (int c = 0; c < nch; c += 16) {
-        uint32_t r[16];
-        if (my_tiles > 0) {
-          uz::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + dy * 128 + c, r);
-          uz::tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = 0u;
-        }
-        if (co < p.Cout) {
-          float4* d4 = reinterpret_cast<float4*>(dst + c);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                __uint_as_float(r[4 * j + 3]));
-        }
-      }
+      float* dst = p.partial + ((static_cast<size_t>(split) * 9 * p.nz + tap) * p.Cout + co0) * p.Cin + ci0;
+      store_acc_block(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + dy * 128, nch, my_tiles > 0, stage, dst, p.Cin,
+                      valid_rows, q * 32 + lane, threadIdx.x - 64);
     }
   }
 
@@ -368,7 +443,8 @@ bool make_plan2(int N, int D, int H, int W, int Cin, int Cout, int taps, Plan2* 
   p.nz = vol ? 3 : 1;
   p.tilesW = (W + 15) / 16; p.tilesH = (H + 7) / 8;
   p.num_tiles = N * p.D * p.tilesW * p.tilesH;
-  p.ci_chunks = (Cin + 127) / 128;
+  p.ci_w = (!vol && p.num_tiles <= 32 && Cin > 64) ? 64 : 128;      // few tiles: more, narrower CTAs (see make_plan)
+  p.ci_chunks = (Cin + p.ci_w - 1) / p.ci_w;
   p.co_blocks = (Cout + 127) / 128;
   p.a_boxes = Cout > 64 ? 2 : 1;
   const size_t stage_bytes = static_cast<size_t>(p.a_boxes) * kW2ABox + 2 * kW2BBox;
@@ -447,15 +523,21 @@ int make_plan(int N, int H, int W, int Cin, int Cout, int taps, Plan* out) {
   p.TN = p.PIX / (p.TW * p.TH);
   p.tilesW = W / p.TW; p.tilesH = H / p.TH;
   p.num_tiles = p.tilesW * p.tilesH * ((N + p.TN - 1) / p.TN);
-  int tpc = 512 / Cin; if (tpc < 1) return UZ_ERR_ARG;
+  // Tiny layers (a handful of pixel tiles) are bound by WRITING their [tap][co][ci] result through one SM's store path
+  // (~35 GB/s per SM measured, profiles/r02_phase_trace.md), not by the MMAs: they get one tap and 64 input channels
+  // per CTA (9 x more, 3 x narrower CTAs: every CTA writes 32 KB instead of 196 KB) and no pixel split.
+  const bool tiny = taps == 9 && p.num_tiles <= 8 && Cin > 64;
+  p.ci_w = tiny ? 64 : Cin;
+  p.ci_chunks = (Cin + p.ci_w - 1) / p.ci_w;
+  int tpc = tiny ? 1 : 512 / Cin; if (tpc < 1) return UZ_ERR_ARG;
   if (tpc > taps) tpc = taps;
   if (taps == 9 && tpc >= 3 && tpc < 9) tpc = 3;   // balanced groups of three
   p.taps_per_cta = tpc;
   p.tap_groups = (taps + tpc - 1) / tpc;
   p.a_boxes = Cout > 64 ? 2 : 1;
-  p.b_boxes = (Cin + 63) / 64;
+  p.b_boxes = (p.ci_w + 63) / 64;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(tpc * Cin)) cols *= 2;
+  while (cols < static_cast<uint32_t>(tpc * p.ci_w)) cols *= 2;
   p.tmem_cols = cols;
   const size_t stage_bytes = static_cast<size_t>(p.a_boxes + p.b_boxes) * p.PIX * 128;
   int stages = static_cast<int>((196 * 1024) / stage_bytes);
@@ -464,8 +546,9 @@ int make_plan(int N, int H, int W, int Cin, int Cout, int taps, Plan* out) {
   p.stages = stages;
   out->smem = stages * stage_bytes + 1024;
   out->co_blocks = (Cout + 127) / 128;
-  const int per_split = p.tap_groups * out->co_blocks;
-  int splits = (wgrad_target_ctas(false) + per_split - 1) / per_split;
+  p.co_blocks = out->co_blocks;
+  const int per_split = p.tap_groups * out->co_blocks * p.ci_chunks;
+  int splits = tiny ? 1 : (wgrad_target_ctas(false) + per_split - 1) / per_split;
   if (splits > p.num_tiles) splits = p.num_tiles;
   if (splits < 1) splits = 1;
   out->splits = splits;
@@ -575,6 +658,9 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
   int rc = make_plan(N, H, W, Cin, Cout, taps, &pl);
   UZ_CHECK_ARG(rc == UZ_OK, "uz_conv_wgrad: no plan for Cin=%d Cout=%d", Cin, Cout);
   pl.p.partial = workspace;
+#ifdef UZ_PROFILE_KNOBS
+  pl.p.trace = uz::g_trace;
+#endif
   CUtensorMap tdy, tx;
   {
     uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
@@ -608,7 +694,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
     }
     attr_bytes = pl.smem;
   }
-  dim3 grid(pl.splits, pl.p.tap_groups * pl.co_blocks, 1);
+  dim3 grid(pl.splits, pl.p.tap_groups * pl.co_blocks * pl.p.ci_chunks, 1);
   uz::launch(kernel, grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream), tdy, tx, pl.p);
   UZ_CHECK_LAUNCH("uz_conv_wgrad");
   const size_t total = static_cast<size_t>(Cout_logical) * Cin_logical;       // one thread per (o, i) pair

@@ -368,10 +368,10 @@ class PHISeg3D(PHISeg):
             object.__setattr__(self, '_weight_packer', pk)
         return pk
 
-    def _forward(self, patch, mask, training=True, replicate=1):
+    def _forward(self, patch, mask, training=True, replicate=1, lowres_logits=False):
         # volumes fill the GPU on their own: one stream, the reference's order
-        if replicate != 1:
-            raise NotImplementedError('replicate is an evaluation shortcut of the 2-D model')
+        if replicate != 1 or lowres_logits:
+            raise NotImplementedError('replicate / lowres_logits are evaluation shortcuts of the 2-D model')
         post_x, post_blocks = self.posterior.contract(patch, mask)
         self.posterior_latent_space, self.posterior_mu, self.posterior_sigma = self.posterior.latent(post_x, post_blocks)
         del post_x, post_blocks

@@ -32,7 +32,13 @@ class deferred_batch_counts:
             if self.prev is not None:
                 self.prev.extend(counts)
             else:
-                torch._foreach_add_(counts, 1)
+                # a counter may appear more than once (reversible blocks run F and G twice per step): one add per
+                # multiplicity, every tensor at most once per multi-tensor launch
+                seen = {}
+                for t in counts:
+                    seen.setdefault(id(t), [t, 0])[1] += 1
+                for mult in sorted(set(n for _, n in seen.values())):
+                    torch._foreach_add_([t for t, n in seen.values() if n == mult], mult)
         return False
 
 
@@ -119,6 +125,35 @@ class Conv2DSequence(nn.Module):
         return x
 
 
+# Fused reversible path (UNETZOO_FUSED_REVERSIBLE=0 selects the autograd-nested path below, which deterministic mode
+# also uses): per F / G unit
+#   forward   conv (+ statistics)  ->  ONE pass: BatchNorm + ReLU + coupling add written straight into the block output
+#   backward  conv (recompute)     ->  ONE pass: BatchNorm-backward sums + coupling inverse (x2 = y2 - G(y1))
+#             -> BatchNorm-backward apply -> dgrad whose epilogue adds the incoming gradient (dx1 = dy1 + dG/dy1)
+#             -> wgrad (auxiliary stream)
+# i.e. 2 launches forward and 4 on the backward chain per unit instead of 3 and 7, no nested torch.autograd.backward, no
+# intermediate F(x2) / G(y1) tensors.  The BatchNorm statistics of the recomputation are the forward pass's (the inputs
+# are the same up to bf16 reconstruction rounding); the second momentum update of the running statistics that revtorch's
+# recomputation causes is applied together with the first.
+import os as _os
+_FUSED_REVERSIBLE = _os.environ.get('UNETZOO_FUSED_REVERSIBLE', '1') != '0'
+
+
+def set_fused_reversible(enabled):
+    global _FUSED_REVERSIBLE
+    prev = _FUSED_REVERSIBLE
+    _FUSED_REVERSIBLE = bool(enabled)
+    return prev
+
+
+def _count_batches(bn, n):
+    for _ in range(n):
+        if _deferred_counts is not None:
+            _deferred_counts.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked.add_(1)
+
+
 class ReversibleBlock(nn.Module):
     """Additive coupling of revtorch 0.2.0 (reference torchlayers.py:67-75): y1 = x1 + F(x2), y2 = x2 + G(y1) on the two
     channel halves.  Sub-module names ``f_block`` / ``g_block`` are revtorch's (state_dict keys)."""
@@ -128,6 +163,77 @@ class ReversibleBlock(nn.Module):
         self.f_block = f_block
         self.g_block = g_block
 
+    # ------------------------------------------------------------------------------------------ fused path
+    def fusable(self):
+        if not _FUSED_REVERSIBLE or kern.is_deterministic():
+            return False
+        for seq in (self.f_block, self.g_block):
+            if len(seq) != 1 or not isinstance(seq[0], Conv2D):
+                return False
+            m = seq[0]
+            if not isinstance(m.convolution[1], m._norm_cls) or not isinstance(m.convolution[2], nn.ReLU):
+                return False
+        return True
+
+    @staticmethod
+    def _unit_forward(m, xin, res, out, updates):
+        """out = res + ReLU(BatchNorm(conv(xin))); returns the statistics the backward pass needs (training mode)"""
+        conv, bn = m.convolution[0], m.convolution[1]
+        wf, _ = kern.pack_conv_weight(conv.weight, need_dgrad=True)
+        if m.training:
+            y, sums = kern.conv_fwd(xin, wf, shift=conv.bias, stats=True)
+            npix = kern._spatial_numel(xin.shape[:-1])
+            _, scale, shift, mean, invstd = kern.bn_apply_train(y, sums, npix, bn.weight, bn.bias, bn.running_mean,
+                                                                bn.running_var, relu=True, residual=res, res_sign=1,
+                                                                out=out, stat_updates=updates)
+            _count_batches(bn, updates)
+            return scale, shift, mean, invstd
+        scale, shift = kern.bn_eval_fold(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        kern.conv_fwd(xin, wf, out=out, scale=scale, shift=shift, relu=True, residual=res, res_sign=1)
+        return None
+
+    def couple_fused(self, x, updates=1):
+        c = x.shape[-1]
+        half = c // 2
+        y = kern._like(x, c)
+        x1, x2, y1, y2 = x[..., :half], x[..., half:], y[..., :half], y[..., half:]
+        sf = self._unit_forward(self.f_block[0], x2, x1, y1, updates)           # y1 = x1 + F(x2)
+        sg = self._unit_forward(self.g_block[0], y1, x2, y2, updates)           # y2 = x2 + G(y1)
+        return y, (sf, sg)
+
+    @staticmethod
+    def _unit_backward(m, xin, stats, g, inv, dres, grads):
+        """unit u = ReLU(BatchNorm(conv(xin))) with upstream gradient g: recompute, inv[1] = inv[0] - u(xin),
+        dres[1] = dres[0] + du/dxin, parameter gradients into ``grads``"""
+        conv, bn = m.convolution[0], m.convolution[1]
+        scale, shift, mean, invstd = stats
+        wf, wd = kern.pack_conv_weight(conv.weight, need_dgrad=True)
+        y, _ = kern.conv_fwd(xin, wf, shift=conv.bias)
+        dy, dgamma, dbeta = kern.bn_relu_bwd_train(g, y, scale, shift, bn.weight, mean, invstd, relu=True, inverse=inv)
+        kern.conv_fwd(dy, wd, out=dres[1], residual=dres[0], res_sign=1)
+        wshape = conv.weight.shape
+        cout, cin = wshape[0], wshape[1]
+        taps = kern._spatial_numel(wshape[2:])
+        dw = ops._run_on_aux(lambda: kern.conv_wgrad(xin, dy, taps, cin, cout, out=ops._bucket_view(conv.weight)),
+                             (xin, dy)).view(wshape)
+        grads[id(conv.weight)] = dw
+        grads[id(conv.bias)] = kern.zero_arena.get(cout, dy.device)      # exactly zero in front of BatchNorm
+        grads[id(bn.weight)] = dgamma
+        grads[id(bn.bias)] = dbeta
+
+    def backward_fused(self, y, dy, stats, grads):
+        c = y.shape[-1]
+        half = c // 2
+        x = kern._like(y, c)
+        dx = kern._like(y, c)
+        y1, y2, dy1, dy2 = y[..., :half], y[..., half:], dy[..., :half], dy[..., half:]
+        x1, x2, dx1, dx2 = x[..., :half], x[..., half:], dx[..., :half], dx[..., half:]
+        sf, sg = stats
+        self._unit_backward(self.g_block[0], y1, sg, dy2, (y2, x2), (dy1, dx1), grads)     # x2 = y2 - G(y1); dx1 = dy1 + ...
+        self._unit_backward(self.f_block[0], x2, sf, dx1, (y1, x1), (dy2, dx2), grads)     # x1 = y1 - F(x2); dx2 = dy2 + ...
+        return x, dx
+
+    # ------------------------------------------------------------------------------------------ autograd-nested path
     def couple(self, x):
         """x: bf16 NHWC [N,H,W,C] -> y of the same shape; no autograd (callers handle gradients by inversion)."""
         c = x.shape[-1]
@@ -171,9 +277,16 @@ class _ReversibleFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, blocks, *params):
         y = x
+        ctx.fused = all(b.fusable() for b in blocks) and all(b.f_block[0].training for b in blocks)
+        ctx.stats = []
         for block in blocks:
-            y = block.couple(y)
+            if ctx.fused:
+                y, st = block.couple_fused(y, updates=2)
+                ctx.stats.append(st)
+            else:
+                y = block.couple(y)
         ctx.blocks = blocks
+        ctx.params = params
         ctx.y = y
         ctx.packer = kern._active_packer          # weights do not change between forward and backward of a step
         return y
@@ -184,12 +297,17 @@ class _ReversibleFunction(torch.autograd.Function):
         del ctx.y
         dy = ops._dense(dy)
         prev = kern.set_active_packer(ctx.packer)
+        grads = {}
         try:
-            for block in list(ctx.blocks)[::-1]:
-                y, dy = block.backward_pass(y, dy)
+            blocks = list(ctx.blocks)
+            for k in range(len(blocks) - 1, -1, -1):
+                if ctx.fused:
+                    y, dy = blocks[k].backward_fused(y, dy, ctx.stats[k], grads)
+                else:
+                    y, dy = blocks[k].backward_pass(y, dy)
         finally:
             kern.set_active_packer(prev)
-        return (dy, None) + tuple(None for _ in ctx.blocks.parameters())
+        return (dy, None) + tuple(grads.get(id(p)) for p in ctx.params)
 
 
 class _RevtorchSequence(nn.Module):
@@ -205,7 +323,10 @@ class _RevtorchSequence(nn.Module):
         else:
             t = x.t
             for block in self.reversible_blocks:
-                t = block.couple(t)
+                if block.fusable():
+                    t, _ = block.couple_fused(t, updates=1)
+                else:
+                    t = block.couple(t)
         return Act(t, x.c)
 
 

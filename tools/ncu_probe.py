@@ -45,7 +45,55 @@ def bn(c, h):
     return run
 
 
+def eval_tail():
+    """the fused evaluation tail at GED-100 size: 100 samples, 2 classes, 128^2, low-resolution level logits"""
+    n, C, H = 100, 2, 128
+    levels = [torch.randn(n, C, H >> l, H >> l, device='cuda') for l in range(5)]
+    factors = [1 << l for l in range(5)]
+    gts = (torch.rand(4, H, H, device='cuda') < 0.05).to(torch.uint8)
+
+    def run():
+        bits, cnts, sums = kern.eval_sample_stats(levels, factors, n, 1, C, (H, H), [1])
+        kern.ged_from_bits(bits[0], cnts[0], gts, [1], H * H)
+        kern.ncc_dice_from_sums(sums[0], gts, n, dice_annotator=0)
+    return run
+
+
+def heads():
+    """latent head, logits layer and residual cross-entropy at batch 12 (forward + backward kernels)"""
+    feat = act(32, 192)
+    wmu, wsig = torch.randn(2, 192, device='cuda') * 0.05, torch.randn(2, 192, device='cuda') * 0.05
+    bmu, bsig = torch.zeros(2, device='cuda'), torch.zeros(2, device='cuda')
+    eps = torch.randn(B, 2, 32, 32, device='cuda')
+    f128 = act(128, 128)
+    ws, bs = torch.randn(2, 128, device='cuda') * 0.05, torch.zeros(2, device='cuda')
+    target = (torch.rand(B, 1, 128, 128, device='cuda') < 0.05).float()
+
+    def run():
+        mu, sigma, z = kern.head_fwd(feat, wmu, bmu, wsig, bsig, eps)
+        kern.head_bwd(feat, wmu, wsig, eps, sigma, torch.ones_like(mu), torch.ones_like(mu), torch.ones_like(mu))
+        s0 = kern.slayer_fwd(f128, ws, bs, 1)
+        kern.slayer_bwd(torch.ones_like(s0), f128, ws, 1)
+        s_list = [s0] + [torch.randn_like(s0) for _ in range(4)]
+        kern.residual_ce(s_list, target, need_grad=True, upstream=torch.ones(1, device='cuda'))
+        kern.kl_fwd(mu, sigma, mu * 0.9, sigma * 1.1, 4.0)
+    return run
+
+
+def memops():
+    x64, x128 = act(64, 64), act(128, 32)
+
+    def run():
+        kern.avgpool2_fwd(x128)
+        kern.upsample2x_fwd(x64, True)
+        kern.upsample2x_bwd(act(128, 64), True)
+    return run
+
+
 PROBES = {
+    'eval_tail': eval_tail,
+    'heads': heads,
+    'memops': memops,
     'wgrad_tiny': lambda: wgrad(192, 192, 4),
     'wgrad_small': lambda: wgrad(192, 192, 16),
     'wgrad_mid': lambda: wgrad(128, 128, 32),

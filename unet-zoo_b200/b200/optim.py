@@ -36,6 +36,7 @@ class FusedAdam(torch.optim.Optimizer):
                     st[k] = prev[k]
         for bufs in self._tables.values():
             bufs[0]['key'] = None              # eager tables: rebuilt on the next step (cheap); captured ones stay valid
+        self.__dict__['_state_gen'] = self.__dict__.get('_state_gen', 0) + 1
 
     def reset_state(self):
         """zero the moments and step counters IN PLACE (pointers, hence captured graphs, stay valid)"""
@@ -78,16 +79,28 @@ class FusedAdam(torch.optim.Optimizer):
             dev = live[0].device
             if not live[0].is_cuda:
                 raise _lib.UnetZooLibError('FusedAdam needs CUDA parameters (no CPU fallback path)')
-            rows, key = [], []
-            for p in live:
-                st = self._state(p)
-                g = p.grad
-                if g.dtype != torch.float32 or not g.is_contiguous() or not p.is_contiguous():
-                    raise _lib.UnetZooLibError('FusedAdam expects dense fp32 parameters and gradients')
-                rows.append((p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
-                             st['step'].data_ptr(), p.numel()))
-                key.append(rows[-1])         # every raw pointer the table holds: a replaced state tensor invalidates it
-            key = tuple(key)
+            # cheap key first: the gradient pointers (new view objects every step, same buffers) + the identity of the state
+            # tensors (replaced only by load_state_dict / reset); the full rows are rebuilt only when it changes
+            gen = self.__dict__.setdefault('_state_gen', 0)
+            state = self.state
+            quick = (gen, tuple(p.grad.data_ptr() for p in live),
+                     tuple(id(state[p].get('exp_avg')) if p in state else 0 for p in live))
+            cache = self.__dict__.setdefault('_row_cache', {})
+            hit = cache.get(gi)
+            if hit is not None and hit[0] == quick:
+                rows, key = hit[1], hit[2]
+            else:
+                rows, key = [], []
+                for p in live:
+                    st = self._state(p)
+                    g = p.grad
+                    if g.dtype != torch.float32 or not g.is_contiguous() or not p.is_contiguous():
+                        raise _lib.UnetZooLibError('FusedAdam expects dense fp32 parameters and gradients')
+                    rows.append((p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
+                                 st['step'].data_ptr(), p.numel()))
+                    key.append(rows[-1])     # every raw pointer the table holds: a replaced state tensor invalidates it
+                key = tuple(key)
+                cache[gi] = (quick, rows, key)
             # two persistent table sets per group, allocated on first use (never inside a stream capture): one for eager
             # steps, one for a captured step whose memcpy nodes must keep reading the pointers they were captured with
             capturing = torch.cuda.is_current_stream_capturing()

@@ -106,14 +106,40 @@ def _attach_data_parallel():
     torch.optim.Adam.step = step
 
 
+def _install_fused_adam():
+    """--graph: the caller's ``torch.optim.Adam(net.parameters(), lr=, weight_decay=)`` (train_model.py:49) resolves to
+    b200.optim.FusedAdam -- same update rule and state_dict layout, ONE launch for all parameters instead of ~100
+    multi-tensor launches and per-parameter Python work (which would leave the graph-replayed step host-bound)."""
+    import torch
+    from b200.optim import FusedAdam
+    stock = torch.optim.Adam
+
+    class Adam(FusedAdam):
+        def __new__(cls, params, *a, **k):
+            params = list(params)
+            if params and all(torch.is_tensor(p) and p.is_cuda for p in params) and not k.get('amsgrad', False):
+                return object.__new__(cls)
+            return stock(params, *a, **k)
+
+        def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, **unused):
+            FusedAdam.__init__(self, params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+
+    torch.optim.Adam = Adam
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reference', default=os.environ.get('UNETZOO_REFERENCE_ROOT'),
                     help='path to a checkout of gigantenbein/UNet-Zoo (unmodified)')
     ap.add_argument('--script', default='train_model.py')
     ap.add_argument('--log-root', default=os.environ.get('UNETZOO_LOG_ROOT', os.path.join(os.getcwd(), 'unetzoo_logs')))
+    ap.add_argument('--graph', action='store_true',
+                    help='transparent CUDA-graph capture of the training step behind net.forward / loss.backward '
+                         '(UNETZOO_TRANSPARENT_GRAPH=1): the unmodified loop stops being host-bound')
     ap.add_argument('script_args', nargs=argparse.REMAINDER)
     args = ap.parse_args()
+    if args.graph:
+        os.environ['UNETZOO_TRANSPARENT_GRAPH'] = '1'    # read when models.phiseg is imported by the experiment file
     if not args.reference or not os.path.isfile(os.path.join(args.reference, args.script)):
         raise SystemExit('launch.py: --reference must point at a UNet-Zoo checkout containing %s' % args.script)
     ref = os.path.abspath(args.reference)
@@ -125,6 +151,8 @@ def main():
     _patch_scheduler()
     _inject_sys_config(os.path.abspath(args.log_root), ref)
     _attach_data_parallel()
+    if args.graph and int(os.environ.get('WORLD_SIZE', '1')) == 1:
+        _install_fused_adam()
     script_args = [a for a in args.script_args if a != '--']
     sys.argv = [os.path.join(ref, args.script)] + script_args
     runpy.run_path(os.path.join(ref, args.script), run_name='__main__')

@@ -26,6 +26,43 @@ _CONCURRENT = os.environ.get('UNETZOO_CONCURRENCY', '1') != '0'
 _PRIOR_OVERLAP = os.environ.get('UNETZOO_PRIOR_OVERLAP', '1') != '0'    # prior latent path next to the likelihood
 _LIKELIHOOD_STREAMS = max(1, int(os.environ.get('UNETZOO_LIKELIHOOD_STREAMS', '4')))   # side streams of Likelihood.forward
 _side_streams = {}
+# Transparent CUDA-graph capture of the training step for the UNMODIFIED caller (train_model.py:100-134 issues
+# net.forward(training=True) -> net.loss(mask) -> optimizer.zero_grad() -> loss.backward() -> optimizer.step() eagerly,
+# ~900 launches from Python: host-bound at ~400 images/s).  With UNETZOO_TRANSPARENT_GRAPH=1 (or net.transparent_graph =
+# True; launch.py --graph sets it) the third identically-shaped training forward captures forward + ELBO + backward as ONE
+# graph (exactly what b200.train.TrainStep captures, minus the optimizer); net.forward() replays it, net.loss() hands out
+# a tensor whose backward() just returns the gradients the replay left in static buffers, and the caller's own optimizer
+# keeps running eagerly on them.  Needs optimizer.zero_grad() to set gradients to None (the torch >= 2.0 default).
+_TRANSPARENT = os.environ.get('UNETZOO_TRANSPARENT_GRAPH', '0') == '1'
+_TRANSPARENT_WARMUP = 2
+_TG_ATTRS = ('posterior_latent_space', 'posterior_mu', 'posterior_sigma', 'prior_latent_space', 'prior_mu', 'prior_sigma',
+             's_out_list', 'loss_dict', 'loss_tot', 'kl_divergence_loss', 'reconstruction_loss')
+
+
+class _GraphLoss(torch.autograd.Function):
+    """The loss tensor handed to the caller in transparent-graph mode: the captured step already computed the parameter
+    gradients into static buffers, backward() returns them."""
+
+    @staticmethod
+    def forward(ctx, loss_static, state, *params):
+        ctx.state = state
+        return loss_static.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        st = ctx.state
+        scale = float(g)                       # the caller's loop synchronises every iteration anyway (scheduler.step(loss))
+        out = []
+        for p, gr in zip(st['params'], st['grads']):
+            if gr is None:
+                out.append(None)
+                continue
+            if p.grad is not None and p.grad.data_ptr() == gr.data_ptr():
+                raise RuntimeError('transparent-graph mode: .grad still aliases the captured gradient buffer -- call '
+                                   'optimizer.zero_grad(set_to_none=True) (the default) before loss.backward()')
+            v = gr.view_as(gr)                 # a fresh handle on the static buffer: AccumulateGrad adopts it without a copy
+            out.append(v if scale == 1.0 else v * scale)
+        return (None, None) + tuple(out)
 
 
 def _use_streams(t, hw=None):
@@ -426,6 +463,14 @@ class PHISeg(nn.Module):
             raise kern._lib.UnetZooLibError('UNet-Zoo B200 modules need CUDA tensors: there is no CPU fallback path')
         if (replicate != 1 or lowres_logits) and (training or self.training):
             raise ValueError('replicate=N / lowres_logits need eval mode and training=False')
+        object.__setattr__(self, '_tg_active', None)
+        if training and self.training and torch.is_grad_enabled() and mask is not None and \
+                (_TRANSPARENT or getattr(self, 'transparent_graph', False)) and \
+                not torch.cuda.is_current_stream_capturing():
+            return self._transparent_forward(patch, mask)
+        return self._plain_forward(patch, mask, training, replicate, lowres_logits)
+
+    def _plain_forward(self, patch, mask, training=True, replicate=1, lowres_logits=False):
         pk = self._packer()
         pk.refresh()
         kern.zero_arena.reset(patch.device)
@@ -548,4 +593,69 @@ class PHISeg(nn.Module):
         return self.loss_tot
 
     def loss(self, segm):
+        st = getattr(self, '_tg_active', None)
+        if st is not None and torch.is_grad_enabled():
+            if segm.data_ptr() != st['mask_ptr'] and not torch.equal(segm.reshape(st['mask'].shape).float(), st['mask']):
+                raise RuntimeError('transparent-graph mode: loss(mask) must receive the mask the preceding '
+                                   'forward(patch, mask, training=True) was given (reference train_model.py:111-112)')
+            out = _GraphLoss.apply(st['loss'], st, *st['params'])
+            # quirk Q1: the three loss handles are one tensor
+            self.loss_tot = out
+            self.kl_divergence_loss = out
+            self.reconstruction_loss = out
+            object.__setattr__(self, '_tg_active', None)
+            return out
         return self.elbo(segm)
+
+    # ---------------------------------------------------------------- transparent graph capture (unmodified caller)
+    def _transparent_forward(self, patch, mask):
+        params = [p for p in self.parameters() if p.requires_grad]
+        key = (tuple(patch.shape), tuple(mask.shape), patch.device.index, params[0].data_ptr())
+        table = self.__dict__.setdefault('_tg', {})
+        st = table.setdefault(key, {'calls': 0})
+        if 'graph_fwd' not in st:
+            st['calls'] += 1
+            if st['calls'] <= _TRANSPARENT_WARMUP:
+                return self._plain_forward(patch, mask, True)           # eager: the caller's first steps run as before
+            self._transparent_capture(st, patch, mask, params)
+        st['patch'].copy_(patch)
+        st['mask'].copy_(mask.reshape(st['mask'].shape))
+        st['mask_ptr'] = mask.data_ptr()
+        st['graph_fwd'].replay()
+        for k, v in st['attrs'].items():
+            setattr(self, k, v)
+        object.__setattr__(self, '_tg_active', st)
+        return self.s_out_list
+
+    def _swap_parameters(self, mapping):
+        for m in self.modules():
+            for name, p in list(m._parameters.items()):
+                if p is not None and id(p) in mapping:
+                    m._parameters[name] = mapping[id(p)]
+
+    def _transparent_capture(self, st, patch, mask, params):
+        dev = patch.device
+        st['patch'] = patch.detach().float().clone()
+        st['mask'] = mask.detach().float().clone()
+        torch.cuda.synchronize(dev)
+        cap = torch.cuda.Stream(device=dev, priority=int(os.environ.get('UNETZOO_MAIN_PRIORITY', '-2')))
+        graph = torch.cuda.CUDAGraph()
+        # The capture runs on ALIASES of the parameters (new leaf tensors on the same storage): the caller's eager
+        # warm-up steps created the parameters' AccumulateGrad nodes on the legacy default stream and the caller still
+        # holds the previous loss (hence those nodes) -- gradients accumulated there would tie the legacy stream to the
+        # capture and invalidate it.  Fresh leaves get fresh nodes on the capture stream.
+        alias = {id(p): nn.Parameter(p.detach(), requires_grad=True) for p in params}
+        back = {id(a): p for p, a in ((p, alias[id(p)]) for p in params)}
+        self._swap_parameters(alias)
+        try:
+            with torch.cuda.graph(graph, stream=cap):
+                self._plain_forward(st['patch'], st['mask'], True)
+                loss = self.elbo(st['mask'])
+                st['attrs'] = {k: getattr(self, k) for k in _TG_ATTRS}
+                st['attrs']['loss_dict'] = dict(self.loss_dict)
+                loss.backward()
+            grads = [alias[id(p)].grad for p in params]
+        finally:
+            self._swap_parameters(back)         # the caller's Parameter objects (and its optimizer's references) are back
+        torch.cuda.synchronize(dev)
+        st.update(graph_fwd=graph, loss=loss.detach(), grads=grads, params=params)

@@ -129,6 +129,20 @@ typedef struct UzPackDesc {
 } UzPackDesc;
 int uz_pack_conv_weights_batched(const void* descs_device, int n, int blocks_per_layer, void* stream);
 
+/* Eval-mode BatchNorm fold (uz_bn_eval_fold) for every layer of a model in ONE launch: scale = gamma / sqrt(rv + eps),
+ * shift = beta + (conv_bias - rm) * scale.  descs_device: device array of n UzFoldDesc. */
+typedef struct UzFoldDesc {
+  const float* conv_bias;
+  const float* gamma;
+  const float* beta;
+  const float* running_mean;
+  const float* running_var;
+  float* scale;
+  float* shift;
+  long long C;
+} UzFoldDesc;
+int uz_bn_eval_fold_batched(const void* descs_device, int n, int max_channels, float eps, void* stream);
+
 /* torch.optim.Adam(lr, betas, eps, weight_decay) -- the reference's optimizer (train_model.py:49: lr 1e-3,
  * weight_decay 1e-5 added to the gradient) -- for ALL parameters in one launch.  descs_device: device array of UzAdamDesc;
  * chunk_table_device: int [nchunks][2] = (tensor index, chunk index), one block per uz_adam_chunk_elems() elements;

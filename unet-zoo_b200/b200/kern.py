@@ -317,7 +317,51 @@ def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True, sum
     return dy, dgb[0], dgb[1]
 
 
+class BNFolder:
+    """Eval-mode BatchNorm folds (scale, shift per layer) of ALL conv units of a model with ONE launch per forward
+    (uz_bn_eval_fold_batched) instead of one tiny launch per layer (106 for PHiSeg: 160 us of a 5.7 ms evaluation)."""
+
+    def __init__(self, units):
+        """units: list of (conv_bias, gamma, beta, running_mean, running_var) tensors (fp32, same device)"""
+        dev = units[0][3].device
+        total = sum(u[3].numel() for u in units)
+        self.buf = torch.empty((2, total), dtype=torch.float32, device=dev)
+        self.views = {}
+        rows, off, self.maxc = [], 0, 0
+        for bias, gamma, beta, rm, rv in units:
+            c = rm.numel()
+            sc, sh = self.buf[0, off:off + c], self.buf[1, off:off + c]
+            self.views[rm.data_ptr()] = (sc, sh)
+            rows.append(struct.pack('<QQQQQQQq', _p(bias) or 0, _p(gamma) or 0, _p(beta) or 0, rm.data_ptr(), rv.data_ptr(),
+                                    sc.data_ptr(), sh.data_ptr(), c))
+            off += c
+            self.maxc = max(self.maxc, c)
+        self.n = len(units)
+        self.table = torch.frombuffer(bytearray(b''.join(rows)), dtype=torch.uint8).to(dev)
+        self.ptr0 = units[0][3].data_ptr()
+
+    def valid_for(self, rm_first):
+        return rm_first.data_ptr() == self.ptr0
+
+    def refresh(self, eps=BN_EPS):
+        _lib.call('uz_bn_eval_fold_batched', _p(self.table), self.n, self.maxc, eps, _stream())
+
+
+_active_folder = None
+
+
+def set_active_folder(folder):
+    global _active_folder
+    prev = _active_folder
+    _active_folder = folder
+    return prev
+
+
 def bn_eval_fold(conv_bias, gamma, beta, rm, rv, eps=BN_EPS):
+    if _active_folder is not None:
+        hit = _active_folder.views.get(rm.data_ptr())
+        if hit is not None:
+            return hit
     c = rm.numel()
     scale = torch.empty(c, dtype=torch.float32, device=rm.device)
     shift = torch.empty_like(scale)

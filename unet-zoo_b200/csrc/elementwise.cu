@@ -5,6 +5,7 @@
 // All activations are [pixels][channels] with a pixel stride `ld` (elements, multiple of 8) so producers can write into
 // and consumers can read from channel slices of wider (concat) buffers without copies.  Every thread moves 16-byte
 // vectors (8 bf16 channels); consecutive threads touch consecutive 16-byte chunks of a pixel => fully coalesced.
+#include <cstdlib>
 #include "common.cuh"
 #include "unetzoo_b200.h"
 
@@ -12,9 +13,21 @@ namespace {
 
 constexpr int kEwThreads = 256;
 
+// Grid of a grid-stride elementwise kernel.  `per_thread` work items per thread (env UZ_EW_PER_THREAD, default 16; measured single-stream step 8.54 / 8.38 / 8.28 / 7.90 ms for 1 / 4 / 8 / 16): the
+// streaming loops keep four 16-byte loads in flight only if a thread HAS four items -- with one item per thread (the
+// old sizing: up to 16 blocks per SM) every load was a dependent round trip to HBM and the 128^2-map BatchNorm passes
+// ran at 0.2 of the HBM roofline (profiles/r02_ncu_kernels.md).  At least two blocks per SM while there is work for them.
+int g_ew_per_thread = [] {
+  const char* e = getenv("UZ_EW_PER_THREAD");
+  const int v = e ? atoi(e) : 16;
+  return v < 1 ? 1 : v;
+}();
 inline int ew_blocks(size_t work, int per_block = kEwThreads) {
-  size_t b = (work + per_block - 1) / per_block;
-  size_t cap = static_cast<size_t>(uz::num_sms()) * 16;
+  const size_t sms = static_cast<size_t>(uz::num_sms());
+  size_t b1 = (work + per_block - 1) / per_block;                       // one item per thread
+  size_t b = (work + static_cast<size_t>(per_block) * g_ew_per_thread - 1) / (static_cast<size_t>(per_block) * g_ew_per_thread);
+  if (b < 2 * sms) b = b1 < 2 * sms ? b1 : 2 * sms;
+  const size_t cap = sms * 16;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return static_cast<int>(b);
@@ -616,33 +629,38 @@ __device__ __forceinline__ void up2_src(int o, int in, int align, int& i0, int& 
   w1 = s - i0;
 }
 
+// one block per output row (n, yo): the row's source rows / weight are computed once, threads walk (xo, 8-channel
+// chunk) with 32-bit arithmetic.  (The first version decoded a flat 64-bit index per element -- five 64-bit divisions
+// per 16-byte store: 720 us of a 5.7 ms GED-100 evaluation, 0.14 of the HBM roofline.)
 __global__ void up2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* out, int ldo, int N, int h,
                                int w, int C, int align) {
   uz::pdl_prologue();
   const int chunks = C / 8;
   const int H = 2 * h, W = 2 * w;
-  const size_t total = static_cast<size_t>(N) * H * W * chunks;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(idx % chunks) * 8;
-    const size_t opix = idx / chunks;
-    const int xo = opix % W;
-    const int yo = (opix / W) % H;
-    const size_t n = opix / (static_cast<size_t>(W) * H);
-    int x0, x1, y0, y1;
-    float wx, wy;
-    up2_src(xo, w, align, x0, x1, wx);
+  const int rows = N * H, per_row = W * chunks;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / H, yo = row - n * H;
+    int y0, y1;
+    float wy;
     up2_src(yo, h, align, y0, y1, wy);
-    const size_t base = n * h * w;
-    float a[8], b[8], c[8], d[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + (base + static_cast<size_t>(y0) * w + x0) * ldx + c0), a);
-    unpack8(*reinterpret_cast<const uint4*>(x + (base + static_cast<size_t>(y0) * w + x1) * ldx + c0), b);
-    unpack8(*reinterpret_cast<const uint4*>(x + (base + static_cast<size_t>(y1) * w + x0) * ldx + c0), c);
-    unpack8(*reinterpret_cast<const uint4*>(x + (base + static_cast<size_t>(y1) * w + x1) * ldx + c0), d);
-    const float w00 = (1.f - wy) * (1.f - wx), w01 = (1.f - wy) * wx, w10 = wy * (1.f - wx), w11 = wy * wx;
+    const __nv_bfloat16* r0 = x + (static_cast<size_t>(n) * h + y0) * w * ldx;
+    const __nv_bfloat16* r1 = x + (static_cast<size_t>(n) * h + y1) * w * ldx;
+    __nv_bfloat16* o = out + static_cast<size_t>(row) * W * ldo;
+    for (int i = threadIdx.x; i < per_row; i += blockDim.x) {
+      const int xo = i / chunks, c0 = (i - xo * chunks) * 8;
+      int x0, x1;
+      float wx;
+      up2_src(xo, w, align, x0, x1, wx);
+      float a[8], b[8], c[8], d[8];
+      unpack8(*reinterpret_cast<const uint4*>(r0 + static_cast<size_t>(x0) * ldx + c0), a);
+      unpack8(*reinterpret_cast<const uint4*>(r0 + static_cast<size_t>(x1) * ldx + c0), b);
+      unpack8(*reinterpret_cast<const uint4*>(r1 + static_cast<size_t>(x0) * ldx + c0), c);
+      unpack8(*reinterpret_cast<const uint4*>(r1 + static_cast<size_t>(x1) * ldx + c0), d);
+      const float w00 = (1.f - wy) * (1.f - wx), w01 = (1.f - wy) * wx, w10 = wy * (1.f - wx), w11 = wy * wx;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = w00 * a[j] + w01 * b[j] + w10 * c[j] + w11 * d[j];
-    *reinterpret_cast<uint4*>(out + opix * ldo + c0) = pack8(a);
+      for (int j = 0; j < 8; ++j) a[j] = w00 * a[j] + w01 * b[j] + w10 * c[j] + w11 * d[j];
+      *reinterpret_cast<uint4*>(o + static_cast<size_t>(xo) * ldo + c0) = pack8(a);
+    }
   }
 }
 
@@ -652,14 +670,13 @@ __global__ void up2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ldd, 
   uz::pdl_prologue();
   const int chunks = C / 8;
   const int H = 2 * h, W = 2 * w;
-  const size_t total = static_cast<size_t>(N) * h * w * chunks;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(idx % chunks) * 8;
-    const size_t ipix = idx / chunks;
-    const int xi = ipix % w;
-    const int yi = (ipix / w) % h;
-    const size_t n = ipix / (static_cast<size_t>(w) * h);
+  const int rows = N * h, per_row = w * chunks;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x)
+  for (int i = threadIdx.x; i < per_row; i += blockDim.x) {
+    const size_t n = row / h;
+    const int yi = row - static_cast<int>(n) * h;
+    const int xi = i / chunks, c0 = (i - xi * chunks) * 8;
+    const size_t ipix = static_cast<size_t>(row) * w + xi;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -1002,6 +1019,27 @@ extern "C" int uz_pack_conv_weights_batched(const void* descs_device, int n, int
   return UZ_OK;
 }
 
+namespace {
+// eval-mode BatchNorm folds of ALL layers of a model in one launch (blockIdx.y = layer): see bn_eval_fold_kernel
+__global__ void bn_eval_fold_batched_kernel(const UzFoldDesc* __restrict__ descs, float eps) {
+  uz::pdl_prologue();
+  const UzFoldDesc d = descs[blockIdx.y];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d.C; c += gridDim.x * blockDim.x) {
+    const float sc = (d.gamma ? d.gamma[c] : 1.f) * rsqrtf(d.running_var[c] + eps);
+    d.scale[c] = sc;
+    d.shift[c] = (d.beta ? d.beta[c] : 0.f) + ((d.conv_bias ? d.conv_bias[c] : 0.f) - d.running_mean[c]) * sc;
+  }
+}
+}  // namespace
+
+extern "C" int uz_bn_eval_fold_batched(const void* descs_device, int n, int max_channels, float eps, void* stream) {
+  UZ_CHECK_ARG(descs_device && n > 0 && max_channels > 0, "uz_bn_eval_fold_batched: bad arguments");
+  dim3 grid((max_channels + 127) / 128, n, 1);
+  uz::launch(bn_eval_fold_batched_kernel, grid, 128, 0, ST(stream), static_cast<const UzFoldDesc*>(descs_device), eps);
+  UZ_CHECK_LAUNCH("uz_bn_eval_fold_batched");
+  return UZ_OK;
+}
+
 extern "C" int uz_adam_chunk_elems(void) { return kAdamChunk; }
 
 extern "C" int uz_adam_step_batched(const void* descs_device, int ntensors, const int* chunk_table_device, int nchunks,
@@ -1196,7 +1234,10 @@ extern "C" int uz_avgpool2_bwd(const void* dout, int ldd, void* dx, int ldx, int
 extern "C" int uz_upsample2x_fwd(const void* x, int ldx, void* out, int ldo, int N, int h, int w, int C,
                                  int align_corners, void* stream) {
   UZ_CHECK_ARG(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "uz_upsample2x_fwd: bad arguments");
-  uz::launch(up2_fwd_kernel, ew_blocks(static_cast<size_t>(N) * h * w * 4 * (C / 8)), kEwThreads, 0, ST(stream), 
+  UZ_CHECK_ARG(static_cast<long long>(N) * 2 * h < (1ll << 31), "uz_upsample2x_fwd: too many rows");
+  const int rows_f = N * 2 * h;
+  uz::launch(up2_fwd_kernel, rows_f < uz::num_sms() * 16 ? rows_f : uz::num_sms() * 16,
+             2 * w * (C / 8) >= 256 ? 256 : ((2 * w * (C / 8) + 31) / 32) * 32, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, N, h, w, C, align_corners);
   UZ_CHECK_LAUNCH("uz_upsample2x_fwd");
   return UZ_OK;
@@ -1205,7 +1246,10 @@ extern "C" int uz_upsample2x_fwd(const void* x, int ldx, void* out, int ldo, int
 extern "C" int uz_upsample2x_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int h, int w, int C,
                                  int align_corners, void* stream) {
   UZ_CHECK_ARG(dout && dx && C % 8 == 0 && ldx % 8 == 0 && ldd % 8 == 0, "uz_upsample2x_bwd: bad arguments");
-  uz::launch(up2_bwd_kernel, ew_blocks(static_cast<size_t>(N) * h * w * (C / 8)), kEwThreads, 0, ST(stream), 
+  UZ_CHECK_ARG(static_cast<long long>(N) * h < (1ll << 31), "uz_upsample2x_bwd: too many rows");
+  const int rows_b = N * h;
+  uz::launch(up2_bwd_kernel, rows_b < uz::num_sms() * 16 ? rows_b : uz::num_sms() * 16,
+             w * (C / 8) >= 256 ? 256 : ((w * (C / 8) + 31) / 32) * 32, 0, ST(stream), 
       static_cast<const __nv_bfloat16*>(dout), ldd, static_cast<__nv_bfloat16*>(dx), ldx, N, h, w, C, align_corners);
   UZ_CHECK_LAUNCH("uz_upsample2x_bwd");
   return UZ_OK;

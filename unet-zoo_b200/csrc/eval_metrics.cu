@@ -91,31 +91,42 @@ __device__ __forceinline__ void py312_step(double x, double& f, double& c) {
   else c = __dadd_rn(c, __dadd_rn(__dadd_rn(x, -t), f));
   f = t;
 }
-__device__ double py312_sum(const double* p, int n) {
+// sequential by definition (every step depends on the previous running sum); the block stages the terms in shared memory
+// in chunks so the one summing thread never waits for global memory
+constexpr int kGedChunk = 512;
+__device__ double py312_sum_staged(const double* __restrict__ p, int n, double* stage /*[2][kGedChunk]*/, int lane) {
   double f = 0.0, c = 0.0;
-  int k = 0;
-  for (; k + 8 <= n; k += 8) {          // the adds are a serial dependency chain: fetch eight terms ahead of it
-    double x[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = p[k + j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) py312_step(x[j], f, c);
+  for (int i = lane; i < min(n, kGedChunk); i += 32) stage[i] = p[i];
+  __syncwarp();
+  for (int base = 0, buf = 0; base < n; base += kGedChunk, buf ^= 1) {
+    const int cnt = min(kGedChunk, n - base);
+    const int nxt = base + kGedChunk;
+    // lanes 1..31 fetch the next chunk while lane 0 walks this one
+    if (lane != 0) {
+      for (int i = lane - 1; i < min(kGedChunk, n - nxt); i += 31) stage[(buf ^ 1) * kGedChunk + i] = p[nxt + i];
+    } else {
+      const double* x = stage + buf * kGedChunk;
+#pragma unroll 4
+      for (int k = 0; k < cnt; ++k) py312_step(x[k], f, c);
+    }
+    __syncwarp();
   }
-  for (; k < n; ++k) py312_step(p[k], f, c);
   if (c != 0.0 && isfinite(c)) f = __dadd_rn(f, c);
   return f;
 }
 
 // out[0] = GED, out[1..3] = sum d_sy, sum d_ss, sum d_yy, in the reference's pair order (utils.py:185-200).
 // Three warps: the three Python sums are independent, each is sequential by definition.
-__global__ void ged_finish_kernel(const double* __restrict__ pair_d, int N, int M, double* out) {
+__global__ void __launch_bounds__(96) ged_finish_kernel(const double* __restrict__ pair_d, int N, int M, double* out) {
   uz::pdl_prologue();
   __shared__ double sums[3];
-  const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0 && w < 3) {
+  __shared__ double stage[3][2 * kGedChunk];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (w < 3) {
     const double* base = w == 0 ? pair_d : (w == 1 ? pair_d + N * M : pair_d + N * M + N * N);
     const int n = w == 0 ? N * M : (w == 1 ? N * N : M * M);
-    sums[w] = py312_sum(base, n);
+    const double r = py312_sum_staged(base, n, stage[w], lane);
+    if (lane == 0) sums[w] = r;
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -455,11 +466,13 @@ extern "C" int uz_variance_ncc(const float* probs, const void* gt, int gt_dtype,
 
 // ---- fused N-sample evaluation -------------------------------------------------------------------------------------
 extern "C" int uz_eval_sample_groups(int n, int I, int hw) {
-  // enough blocks for ~2 waves: (hw / 256) * G * I >= 2 * SMs, at least 4 samples per group
+  // ~8 blocks of 256 threads per SM: a thread's samples are a serial chain of dependent-latency loads, the loads in flight
+  // come from the number of resident warps (first version: 2 blocks per SM, 59 us = 0.05 of the HBM roofline at N = 100);
+  // at least 2 samples per group so the partial sums stay small
   if (n <= 0 || I <= 0 || hw <= 0) return -1;
   const int per_g = (hw + 255) / 256 * I;
-  int G = (2 * uz::num_sms() + per_g - 1) / per_g;
-  if (G > (n + 3) / 4) G = (n + 3) / 4;
+  int G = (8 * uz::num_sms() + per_g - 1) / per_g;
+  if (G > (n + 1) / 2) G = (n + 1) / 2;
   if (G < 1) G = 1;
   return G;
 }

@@ -50,7 +50,9 @@ struct WgradParams {
 __device__ __forceinline__ void store_acc_block(uint32_t taddr, int ncols, bool have_acc, float* stage, float* dst,
                                                 size_t ld, int valid_rows, int row, int et,
                                                 unsigned long long* trace = nullptr) {
-  const int pitch = ncols + 4;
+  // fixed pitch (128 columns + 16 bytes: bank-conflict-free 16-byte row writes): a thread's staging row is the same
+  // private region for every block, so its own wait_group is all the synchronisation the reuse needs
+  constexpr int pitch = 128 + 4;
   float* srow = stage + static_cast<size_t>(row) * pitch;
   int c = 0;
   for (; c + 32 <= ncols; c += 32) {            // two TMEM loads in flight per wait
@@ -91,30 +93,20 @@ __device__ __forceinline__ void store_acc_block(uint32_t taddr, int ncols, bool 
                       __uint_as_float(r[4 * j + 3]));
   }
   UZ_TRACE(trace, et == 0 ? 10 : 15);
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  // copy-out: every thread hands the row it just staged to the TMA engine as ONE bulk copy (cp.async.bulk shared ->
+  // global, ncols * 4 contiguous bytes on both sides).  No block barrier is needed -- a thread only ever touches its own
+  // staging row -- and the stores no longer go through the four epilogue warps' LSU path (row-per-thread st.global ran at
+  // ~24 GB/s per SM, a coalesced eight-rows-in-flight loop at ~35 GB/s: profiles/r02_phase_trace.md).
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   UZ_TRACE(trace, et == 0 ? 11 : 15);
-  // copy-out: a warp writes whole rows (lane = 16-byte column chunk, ncols <= 128 -> one chunk per lane), eight rows per
-  // iteration with all loads issued before the stores -- with four warps per SM nothing else hides the shared-memory
-  // latency (a one-float4-per-iteration loop ran at ~160 cycles per iteration: 24 GB/s per SM)
-  const int n4 = ncols >> 2;
-  const int ew = et >> 5, el = et & 31;
-  if (el < n4) {
-    for (int r0 = ew; r0 < valid_rows; r0 += 32) {
-      float4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int rr = r0 + 4 * u;
-        if (rr < valid_rows) v[u] = *reinterpret_cast<const float4*>(stage + static_cast<size_t>(rr) * pitch + 4 * el);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int rr = r0 + 4 * u;
-        if (rr < valid_rows) *reinterpret_cast<float4*>(dst + static_cast<size_t>(rr) * ld + 4 * el) = v[u];
-      }
-    }
+  if (row < valid_rows) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + static_cast<size_t>(row) * ld),
+                 "r"(uz::smem_u32(srow)), "r"(static_cast<uint32_t>(ncols * 4))
+                 : "memory");
   }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the staging row may be overwritten again
   UZ_TRACE(trace, et == 0 ? 12 : 15);
-  asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
 template <int PIX>
@@ -259,6 +251,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     }
   }
 
+  if (warp >= 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // bulk stores of the epilogue have landed
   UZ_TRACE(p.trace, warp == 2 ? 7 : 15);
   uz::tc_fence_before();
   __syncthreads();
@@ -417,6 +410,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
     }
   }
 
+  if (warp >= 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // bulk stores of the epilogue have landed
   uz::tc_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -51,8 +51,7 @@ class _GraphLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         st = ctx.state
-        scale = float(g)                       # the caller's loop synchronises every iteration anyway (scheduler.step(loss))
-        out = []
+        out, live = [], []
         for p, gr in zip(st['params'], st['grads']):
             if gr is None:
                 out.append(None)
@@ -61,7 +60,11 @@ class _GraphLoss(torch.autograd.Function):
                 raise RuntimeError('transparent-graph mode: .grad still aliases the captured gradient buffer -- call '
                                    'optimizer.zero_grad(set_to_none=True) (the default) before loss.backward()')
             v = gr.view_as(gr)                 # a fresh handle on the static buffer: AccumulateGrad adopts it without a copy
-            out.append(v if scale == 1.0 else v * scale)
+            out.append(v)
+            live.append(v)
+        # upstream gradient (1 for loss.backward()): applied on the device, in place, without reading it on the host --
+        # a host read here would serialise the caller's remaining per-step work behind the whole replayed step
+        torch._foreach_mul_(live, g)
         return (None, None) + tuple(out)
 
 
@@ -470,16 +473,34 @@ class PHISeg(nn.Module):
             return self._transparent_forward(patch, mask)
         return self._plain_forward(patch, mask, training, replicate, lowres_logits)
 
+    def _folder(self):
+        # eval mode: the BatchNorm folds of every conv unit in one launch
+        from torchlayers import Conv2D as _C2D
+        units = [m for m in self.modules() if isinstance(m, _C2D) and isinstance(m.convolution[1], m._norm_cls)]
+        fd = getattr(self, '_bn_folder', None)
+        if fd is None or not fd.valid_for(units[0].convolution[1].running_mean):
+            fd = kern.BNFolder([(m.convolution[0].bias, m.convolution[1].weight, m.convolution[1].bias,
+                                 m.convolution[1].running_mean, m.convolution[1].running_var) for m in units])
+            object.__setattr__(self, '_bn_folder', fd)
+        return fd
+
     def _plain_forward(self, patch, mask, training=True, replicate=1, lowres_logits=False):
         pk = self._packer()
         pk.refresh()
         kern.zero_arena.reset(patch.device)
         prev = kern.set_active_packer(pk)
+        prev_f = None
+        if not self.training:
+            fd = self._folder()
+            fd.refresh()
+            prev_f = kern.set_active_folder(fd)
         try:
             with deferred_batch_counts():
                 return self._forward(patch, mask, training, replicate, lowres_logits)
         finally:
             kern.set_active_packer(prev)
+            if not self.training:
+                kern.set_active_folder(prev_f)
 
     @staticmethod
     def _replicate(x, blocks, n):

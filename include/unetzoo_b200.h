@@ -196,6 +196,14 @@ int uz_bn_bwd_apply_train(const void* dout, int ldd, const void* y, int ldy, con
                           int relu, const float* sums, float count, const float* gamma, const float* mean,
                           const float* invstd, float* dgamma, float* dbeta, void* dy, int lddy, long long npix, int C,
                           void* stream);
+/* The same backward (reference torchlayers.py:18-21 through nn.BatchNorm2d / nn.ReLU) as ONE launch on thread-block
+ * clusters: a cluster owns 16 channels, its CTAs split the pixels, stage (g, y) in shared memory, exchange the partial
+ * sums through distributed shared memory in a fixed order (deterministic, no atomics) and write dy from the staged copy.
+ * uz_bn_bwd_fused_supported: 1 if this size has a plan (npix <= 49152, C a multiple of 16). */
+int uz_bn_bwd_fused_supported(long long npix, int C);
+int uz_bn_bwd_fused(const void* dout, int ldd, const void* y, int ldy, const float* scale, const float* shift, int relu,
+                    float count, const float* gamma, const float* mean, const float* invstd, float* dgamma,
+                    float* dbeta, void* dy, int lddy, long long npix, int C, void* stream);
 
 /* Eval-mode fold of conv bias + BatchNorm running stats into the conv epilogue's scale / shift (train_model.py:139). */
 int uz_bn_eval_fold(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,

@@ -147,12 +147,18 @@ def test_fused_bn_backward_matches_unfused_step():
         v = [float((a[n] - b[n]).norm()) / float(b[n].norm()) for n in b if float(b[n].norm()) > 1e-6]
         return float(np.median(v))
 
-    n0 = _lib.raw('uz_launch_count')()
-    l_f, g_f, _ = _phiseg_step(False, True)
-    n1 = _lib.raw('uz_launch_count')()
-    l_u, g_u, _ = _phiseg_step(False, False)
-    n2 = _lib.raw('uz_launch_count')()
-    l_v, g_v, _ = _phiseg_step(False, False)
+    k = kern()
+    prev = k._BN_BWD_FUSED          # the launch-count comparison is between the dgrad-epilogue sums and the reduce + apply pair
+    k._BN_BWD_FUSED = False
+    try:
+        n0 = _lib.raw('uz_launch_count')()
+        l_f, g_f, _ = _phiseg_step(False, True)
+        n1 = _lib.raw('uz_launch_count')()
+        l_u, g_u, _ = _phiseg_step(False, False)
+        n2 = _lib.raw('uz_launch_count')()
+        l_v, g_v, _ = _phiseg_step(False, False)
+    finally:
+        k._BN_BWD_FUSED = prev
     assert (n1 - n0) < (n2 - n1) - 20, 'fusion must remove reduction launches (%d vs %d)' % (n1 - n0, n2 - n1)
     floor_loss = abs(l_u - l_v) / abs(l_v)
     assert abs(l_f - l_u) / abs(l_u) <= max(3 * floor_loss, 2e-3)
@@ -231,3 +237,47 @@ def test_fused_reversible_sequence_matches_nested_autograd_path(shape):
             assert int(ba[k]) == int(bb[k]) == 2
         else:
             torch.testing.assert_close(ba[k], bb[k], rtol=2e-3, atol=1e-5)
+
+
+# (N, H, W, C, channel-slice stride): K = 1 / 2 / 8 pixel slices per cluster, staged and re-read plans, odd pixel counts
+BN_CLUSTER_SHAPES = [(12, 2, 2, 192, 192), (12, 4, 4, 192, 256), (5, 4, 4, 48, 48), (12, 8, 8, 256, 256),
+                     (12, 16, 16, 64, 64), (12, 32, 32, 192, 192), (12, 64, 64, 64, 96), (3, 20, 12, 32, 32)]
+
+
+@pytest.mark.parametrize('N,H,W,C,ld', BN_CLUSTER_SHAPES)
+def test_bn_backward_cluster_kernel(N, H, W, C, ld):
+    """uz_bn_bwd_fused (one launch on thread-block clusters, partial sums through distributed shared memory) against
+    autograd through F.batch_norm(training=True) + ReLU in fp32 on the same stored values, against the two-launch path,
+    and bit-reproducible run to run (fixed summation order)."""
+    k = kern()
+    assert k._lib.raw('uz_bn_bwd_fused_supported')(N * H * W, C) == 1
+    ybuf = to_nhwc(bf16r(_rand(N, ld, H, W, seed=11)))               # y is a channel slice of a wider buffer
+    y = ybuf[..., :C]
+    gamma = (1 + 0.1 * _rand(C, seed=3)).requires_grad_(True)
+    beta = (0.1 * _rand(C, seed=4)).requires_grad_(True)
+    yq = to_nchw(y.contiguous()).requires_grad_(True)
+    ref = F.relu(F.batch_norm(yq, None, None, gamma, beta, True, 0.01, 1e-3))
+    da = bf16r(_rand(N, C, H, W, seed=7))
+    ref.backward(da)
+    mean = yq.detach().mean((0, 2, 3))
+    var = yq.detach().var((0, 2, 3), unbiased=False)
+    invstd = (var + 1e-3).rsqrt()
+    scale = gamma.detach() * invstd
+    shift = beta.detach() - mean * scale
+    dout = to_nhwc(da)
+    prev, prev_max = k._BN_BWD_FUSED, k._BN_BWD_FUSED_MAX_PIX
+    try:
+        k._BN_BWD_FUSED, k._BN_BWD_FUSED_MAX_PIX = True, 1 << 30      # the kernel's whole range, not only the routed sizes
+        dy, dgamma, dbeta = k.bn_relu_bwd_train(dout, y, scale, shift, gamma.detach(), mean, invstd)
+        dy_b, dgamma_b, dbeta_b = k.bn_relu_bwd_train(dout, y, scale, shift, gamma.detach(), mean, invstd)
+        k._BN_BWD_FUSED = False
+        dy_u, dgamma_u, dbeta_u = k.bn_relu_bwd_train(dout, y, scale, shift, gamma.detach(), mean, invstd)
+    finally:
+        k._BN_BWD_FUSED, k._BN_BWD_FUSED_MAX_PIX = prev, prev_max
+    assert torch.equal(dy, dy_b) and torch.equal(dgamma, dgamma_b) and torch.equal(dbeta, dbeta_b)   # deterministic
+    assert rel_err(to_nchw(dy), yq.grad) < 6e-3                       # bf16 storage of dy: 2^-9 rms
+    torch.testing.assert_close(dgamma, gamma.grad, rtol=1e-4, atol=1e-4 * float(gamma.grad.abs().max()))
+    torch.testing.assert_close(dbeta, beta.grad, rtol=1e-4, atol=1e-4 * float(beta.grad.abs().max()))
+    # the two-launch path sums with atomics in arrival order: equal up to fp32 summation order
+    torch.testing.assert_close(dgamma, dgamma_u, rtol=1e-4, atol=1e-4 * float(dgamma_u.abs().max()))
+    assert float((dy.float() - dy_u.float()).abs().max()) <= 2 ** -7 * float(dy_u.float().abs().max())

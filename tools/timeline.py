@@ -26,6 +26,7 @@ def main():
     ap.add_argument('--model', default='phiseg', choices=['phiseg', 'phiseg3d', 'revphiseg'])
     ap.add_argument('--list', default='', help='substring: print every launch of the matching kernels (grid, us)')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'timeline.json'))
+    ap.add_argument('--raw', default='', help='write every kernel of the last replay (start, duration, stream, grid) here')
     args = ap.parse_args()
     dev = torch.device('cuda', 0)
     from b200 import _lib
@@ -56,6 +57,17 @@ def main():
         for _ in range(3):
             st.step_device()
         torch.cuda.synchronize()
+    if args.raw:
+        trace = args.raw + '.trace.json'
+        prof.export_chrome_trace(trace)
+        tr = json.load(open(trace))
+        rows = sorted((e['ts'], e['dur'], e['name'].replace('void ', '').replace('(anonymous namespace)::', '').split('(')[0][:60],
+                       e.get('args', {}).get('stream'), e.get('args', {}).get('grid'), e.get('args', {}).get('block'),
+                       e.get('args', {}).get('shared memory')) for e in tr['traceEvents'] if e.get('cat') == 'kernel')
+        rows = rows[-(len(rows) // 3):]
+        t0 = rows[0][0]
+        json.dump([[round(r[0] - t0, 3)] + list(r[1:]) for r in rows], open(args.raw, 'w'))
+        os.remove(trace)
     if args.list:
         trace = args.out + '.trace.json'
         prof.export_chrome_trace(trace)

@@ -1,7 +1,8 @@
 """One-process-per-GPU data parallelism for the drop-in models (the reference has none).
 
 Training: batch data-parallel.  Parameters are grouped into a few flat fp32 buckets in the order their gradients are
-produced (recorded during the warm-up steps), with a small tail bucket for the last arrivals; the tensor-core weight
+produced (recorded during the warm-up steps), sized geometrically from a small tail bucket for the last arrivals up to
+``bucket_bytes`` for the early ones; the tensor-core weight
 gradients are written straight into the buckets (``grad_view_for``), the few remaining gradients are gathered with one
 multi-tensor copy, ``.grad`` is re-pointed at views of the flat buffer and ONE NCCL all-reduce (average) per bucket is
 issued from a side stream.  ``finish()`` makes the compute stream wait, so communication overlaps the rest of backward.  Parameters that never receive a gradient (``{posterior,prior}.upsampling_path.4.*``)
@@ -62,10 +63,12 @@ def decorrelate_rank_seeds(rank, world, group=None):
 
 
 class _Bucket:
-    __slots__ = ('flat', 'params', 'pending', 'work', 'views')
+    __slots__ = ('flat', 'params', 'pending', 'work', 'views', 'streams', 'index')
 
     def __init__(self, flat, params):
         self.flat, self.params, self.pending, self.work = flat, params, 0, None
+        self.streams = {}          # compute streams the gradients of this bucket were accumulated on (this step)
+        self.index = 0
 
 
 # parameter -> fp32 view into its flat bucket.  b200.ops hands the view to the weight-gradient kernel as its output, so
@@ -84,11 +87,19 @@ class GradientAllReduce:
     gradients are produced; ``freeze_buckets`` then builds the flat buckets in that order -- large ones first, a small
     tail (``tail_bytes``) for the parameters whose gradients arrive last, so that the only all-reduce that cannot hide
     behind backward is short.  A completed bucket is handed to NCCL from a side stream that waits for the producing
-    streams (the compute stream is never stalled by communication set-up); ``finish()`` joins."""
+    streams (the compute stream is never stalled by communication set-up); ``finish()`` joins.
 
-    def __init__(self, params, group=None, bucket_bytes=24 << 20, tail_bytes=2 << 20):
+    ``optimizer`` (a b200.optim.FusedAdam) moves the parameter update into the bucket pipeline as well: as soon as a
+    bucket is complete (and averaged), its parameters are stepped (``optimizer.step_params``) and -- with ``packer``, the
+    model's kern.WeightPacker -- their bf16 tensor-core copies re-packed, on the side stream, next to the rest of backward.
+    Only the last (small) bucket's update remains on the critical path; the per-forward weight packing disappears.  The
+    caller then skips ``optimizer.step()`` (``owns_optimizer``).  Works with a single rank (no process group) too."""
+
+    def __init__(self, params, group=None, bucket_bytes=24 << 20, tail_bytes=2 << 20, optimizer=None, packer=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.optimizer = optimizer
+        self.packer = packer
         self.bucket_bytes = bucket_bytes
         self.tail_bytes = tail_bytes
         self.buckets = None
@@ -102,6 +113,11 @@ class GradientAllReduce:
     def _record_order(self, param):
         if self.buckets is None:
             self._order.append(id(param))
+
+    @property
+    def owns_optimizer(self):
+        """True once the buckets exist and the parameter update runs inside the bucket pipeline"""
+        return self.optimizer is not None and self.buckets is not None
 
     # -- discovery phase ------------------------------------------------------------------------------------------
     def _finish_unbucketed(self):
@@ -126,22 +142,22 @@ class GradientAllReduce:
             live.sort(key=lambda p: seen.get(id(p), -1))    # production order of the last discovery step
         else:
             live.reverse()                                  # no hook information: last-registered parameters finish first
-        # split off the tail: the parameters produced last, up to tail_bytes
-        tail, tb = [], 0
-        while len(live) > 1 and tb + live[-1].numel() * 4 <= self.tail_bytes:
-            tb += live[-1].numel() * 4
-            tail.insert(0, live.pop())
+        # Buckets are cut from the END of the production order with doubling sizes (tail_bytes, 2x, 4x, ... capped at
+        # bucket_bytes): whatever completes late in backward sits in a small bucket, so the work that cannot hide behind
+        # backward any more (the last all-reduces; with ``optimizer`` also the last updates and re-packs) is short, while
+        # the early, well-hidden part of the model uses few large buckets.
         groups, cur, cur_bytes = [], [], 0
-        for p in live:
-            cur.append(p)
-            cur_bytes += p.numel() * 4
-            if cur_bytes >= self.bucket_bytes:
-                groups.append(cur)
+        limit = min(self.tail_bytes, self.bucket_bytes)
+        for p in reversed(live):
+            nbytes = p.numel() * 4
+            if cur and cur_bytes + nbytes > limit:
+                groups.insert(0, cur)
                 cur, cur_bytes = [], 0
+                limit = min(limit * 2, self.bucket_bytes)
+            cur.insert(0, p)
+            cur_bytes += nbytes
         if cur:
-            groups.append(cur)
-        if tail:
-            groups.append(tail)
+            groups.insert(0, cur)
         for h in self._hooks:
             h.remove()
         self._hooks = []
@@ -156,13 +172,23 @@ class GradientAllReduce:
                 _grad_views[id(p)] = b.views[-1]
                 off += p.numel()
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
+            b.index = len(self.buckets)
             self.buckets.append(b)
+            if self.packer is not None:
+                self.packer.make_subset(('bucket', b.index), plist)
         if live and live[0].is_cuda:
             self._comm_stream = torch.cuda.Stream(device=live[0].device)
+        if self.packer is not None and self.optimizer is not None:
+            # from now on the packed copies are refreshed per bucket right after the update: bring them up to date once
+            self.packer.refresh(force=True)
+            self.packer.external = True
         self.zero_grad()
 
     def _make_hook(self, bucket):
         def hook(param):
+            if param.is_cuda:
+                st = torch.cuda.current_stream()           # the accumulation stream has waited for the producing kernels
+                bucket.streams[st.cuda_stream] = st
             bucket.pending -= 1
             if bucket.pending == 0:
                 self._launch(bucket)
@@ -176,6 +202,8 @@ class GradientAllReduce:
             cur = torch.cuda.current_stream()
             side = self._comm_stream
             side.wait_stream(cur)
+            for st in bucket.streams.values():             # every stream a gradient of this bucket was accumulated on: the
+                side.wait_stream(st)                       # layer's dgrad (reads the packed weights) precedes it there
             for st in ops.pending_aux_streams():           # weight gradients are produced on the auxiliary streams
                 side.wait_stream(st)
             ctx = torch.cuda.stream(side)
@@ -196,6 +224,15 @@ class GradientAllReduce:
                                               group=self.group, async_op=True)
             elif cuda:
                 bucket.work = side                         # single rank: only the gather has to be joined
+            if self.optimizer is not None:
+                if self.world > 1:
+                    bucket.work.wait()                     # the side stream waits for the average (no host sync on CUDA)
+                    if not cuda:
+                        bucket.flat.div_(self.world)       # gloo has no AVG
+                self.optimizer.step_params(bucket.params, ('bucket', bucket.index))
+                if self.packer is not None:
+                    self.packer.refresh_subset(('bucket', bucket.index))
+                bucket.work = side if cuda else None
 
     # -- per step -------------------------------------------------------------------------------------------------
     def zero_grad(self):
@@ -205,6 +242,7 @@ class GradientAllReduce:
             for b in self.buckets:
                 b.pending = len(b.params)
                 b.work = None
+                b.streams = {}
 
     def finish(self):
         if self.buckets is None:

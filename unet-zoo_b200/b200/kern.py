@@ -91,7 +91,7 @@ class WeightPacker:
         self.weights = [w for w in weights]
         dev = self.weights[0].device
         self.packed = {}
-        rows = []
+        self.rows = {}
         self.max_elems = 0
         for w in self.weights:
             cout, cin = w.shape[0], w.shape[1]
@@ -100,21 +100,45 @@ class WeightPacker:
             wf = torch.empty((taps, coutp, cinp), dtype=_lib.act_dtype(), device=dev)
             wd = torch.empty((taps, cinp, coutp), dtype=_lib.act_dtype(), device=dev)
             self.packed[w.data_ptr()] = (wf, wd)
-            rows.append(struct.pack('<QQQiiiiii', w.data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, cin, taps, coutp,
-                                    cinp, 0))
+            self.rows[w.data_ptr()] = (struct.pack('<QQQiiiiii', w.data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, cin, taps,
+                                                   coutp, cinp, 0), 2 * taps * coutp * cinp)
             self.max_elems = max(self.max_elems, 2 * taps * coutp * cinp)
-        raw = b''.join(rows)
+        raw = b''.join(self.rows[w.data_ptr()][0] for w in self.weights)
         self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         self.ptr0 = self.weights[0].data_ptr()
         self.dtype = _lib.act_dtype()
         self.versions = None
+        # external=True: somebody else (the overlapped optimizer of b200.dp: Adam + re-pack per gradient bucket during
+        # backward) keeps the packed copies current; the per-forward refresh() is then a no-op unless forced
+        self.external = False
+        self.subsets = {}
 
     def valid_for(self, weights_first):
         return weights_first.data_ptr() == self.ptr0 and self.dtype == _lib.act_dtype()
 
-    def refresh(self):
+    def refresh(self, force=False):
+        if self.external and not force:
+            return
         blocks = min(64, max(1, (self.max_elems + 255) // 256 // 4))
         _lib.call('uz_pack_conv_weights_batched', _p(self.table), len(self.weights), blocks, _stream())
+
+    def make_subset(self, key, params):
+        """descriptor table for the packed layers among ``params`` (allocate outside a stream capture)"""
+        rows = [self.rows[p.data_ptr()] for p in params if p.data_ptr() in self.rows]
+        if not rows:
+            self.subsets[key] = None
+            return
+        raw = b''.join(r[0] for r in rows)
+        self.subsets[key] = (torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.table.device), len(rows),
+                             max(r[1] for r in rows))
+
+    def refresh_subset(self, key):
+        sub = self.subsets.get(key)
+        if sub is None:
+            return
+        table, n, max_elems = sub
+        blocks = min(64, max(1, (max_elems + 255) // 256 // 4))
+        _lib.call('uz_pack_conv_weights_batched', _p(table), n, blocks, _stream())
 
     def lookup(self, w):
         return self.packed.get(w.data_ptr())
@@ -291,6 +315,12 @@ def bn_apply_train(y, sums, count, gamma, beta, running_mean, running_var, relu=
     return out, st[0], st[1], st[2], st[3]
 
 
+_BN_BWD_FUSED = _os.environ.get('UNETZOO_BN_BWD_FUSED', '1') != '0'
+# in the captured step (gpurun_out/r2c_tl_*.json) the cluster kernel wins up to 16x16x12 pixels (4.9 vs 6.1 us at 2x2,
+# 7.3 vs 8.9 us at 16x16) and loses from 32x32x12 on (13-15 vs 11.6 us)
+_BN_BWD_FUSED_MAX_PIX = int(_os.environ.get('UNETZOO_BN_BWD_FUSED_MAX_PIX', '3072'))
+
+
 def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True, sums=None, inverse=None):
     """two launches (accumulate, apply) -> dy bf16, dgamma, dbeta; with ``sums`` ([2,C]: sum g, sum g*y, already
     accumulated by the dgrad epilogue that produced ``dout``) only the apply pass runs.  ``inverse`` = (inv_in, inv_out):
@@ -299,6 +329,14 @@ def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True, sum
     ldy = _check_act(y)[4]
     npix = n * h * w
     dev = y.device
+    if sums is None and inverse is None and _BN_BWD_FUSED and npix <= _BN_BWD_FUSED_MAX_PIX and \
+            _lib.raw('uz_bn_bwd_fused_supported')(npix, c):
+        # one launch on thread-block clusters (csrc/bn_cluster.cu): sums exchanged through distributed shared memory
+        dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+        dy = _like(y, c)
+        _lib.call('uz_bn_bwd_fused', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), float(npix), _p(gamma),
+                  _p(mean), _p(invstd), _p(dgb[0]), _p(dgb[1]), _p(dy), c, npix, c, _stream())
+        return dy, dgb[0], dgb[1]
     if sums is None:
         sums = zero_arena.get(2 * c, dev)
         if inverse is None:

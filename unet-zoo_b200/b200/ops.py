@@ -93,12 +93,23 @@ def sync_aux_streams():
     _aux['next'] = 0
 
 
-def _run_on_aux(fn, keep):
-    """run fn() on the auxiliary stream after everything already queued on the current stream"""
+_BIG_MAP_PIXELS = int(_os.environ.get('UNETZOO_WGRAD_BIG_PIXELS', str(12 * 128 * 128)))
+_BIG_MAP_PERCENT = int(_os.environ.get('UNETZOO_WGRAD_BIG_PERCENT', '25'))
+
+
+def _run_on_aux(fn, keep, last=False):
+    """run fn() on the auxiliary stream after everything already queued on the current stream.  ``last``: nothing follows
+    this layer on its backward chain (the first layer of a network: no input gradient) -- its weight gradient is the tail
+    of the step and is planned for the whole GPU on the chain's own stream."""
     # Only a captured step is GPU-bound: an eagerly issued step is bound by the host, where the stream switches of this
     # function (~80 us per layer) cost more than the overlap can return -- eager launches stay on the caller's stream.
-    overlapped = _AUX_ENABLED and torch.cuda.is_current_stream_capturing()
-    _plan_wgrad_share(overlapped)
+    overlapped = _AUX_ENABLED and torch.cuda.is_current_stream_capturing() and not last
+    if overlapped and _BIG_MAP_PERCENT != _WGRAD_SM_PERCENT and keep[0].numel() // keep[0].shape[-1] >= _BIG_MAP_PIXELS:
+        # the largest maps are processed at the end of backward, when little else is left to overlap with
+        kern._lib.call('uz_set_wgrad_sm_percent', _BIG_MAP_PERCENT)
+        _aux['planned_for'] = None
+    else:
+        _plan_wgrad_share(overlapped)
     if not overlapped:
         return fn()
     cur = torch.cuda.current_stream()
@@ -249,7 +260,7 @@ class ConvBNAct(torch.autograd.Function):
         cout, cin = ctx.wshape[0], ctx.wshape[1]
         taps = kern._spatial_numel(ctx.wshape[2:])
         dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, taps, cin, cout, out=_bucket_view(ctx.weight_ref)),
-                         (x, dy)).view(ctx.wshape)
+                         (x, dy), last=not ctx.needs_input_grad[0]).view(ctx.wshape)
         dbias = kern.zero_arena.get(cout, dy.device)
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None
 

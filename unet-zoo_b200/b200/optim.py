@@ -71,82 +71,101 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        chunk = _lib.raw('uz_adam_chunk_elems')()
         for gi, group in enumerate(self.param_groups):
             live = [p for p in group['params'] if p.grad is not None]
-            if not live:
-                continue
-            dev = live[0].device
-            if not live[0].is_cuda:
-                raise _lib.UnetZooLibError('FusedAdam needs CUDA parameters (no CPU fallback path)')
-            # cheap key first: the gradient pointers (new view objects every step, same buffers) + the identity of the state
-            # tensors (replaced only by load_state_dict / reset); the full rows are rebuilt only when it changes
-            gen = self.__dict__.setdefault('_state_gen', 0)
-            state = self.state
-            quick = (gen, tuple(p.grad.data_ptr() for p in live),
-                     tuple(id(state[p].get('exp_avg')) if p in state else 0 for p in live))
-            cache = self.__dict__.setdefault('_row_cache', {})
-            hit = cache.get(gi)
-            if hit is not None and hit[0] == quick:
-                rows, key = hit[1], hit[2]
-            else:
-                rows, key = [], []
-                for p in live:
-                    st = self._state(p)
-                    g = p.grad
-                    if g.dtype != torch.float32 or not g.is_contiguous() or not p.is_contiguous():
-                        raise _lib.UnetZooLibError('FusedAdam expects dense fp32 parameters and gradients')
-                    rows.append((p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
-                                 st['step'].data_ptr(), p.numel()))
-                    key.append(rows[-1])     # every raw pointer the table holds: a replaced state tensor invalidates it
-                key = tuple(key)
-                cache[gi] = (quick, rows, key)
-            # two persistent table sets per group, allocated on first use (never inside a stream capture): one for eager
-            # steps, one for a captured step whose memcpy nodes must keep reading the pointers they were captured with
-            capturing = torch.cuda.is_current_stream_capturing()
-            bufs = self._tables.get(gi)
-            if bufs is None:
-                nparam = len(group['params'])
-                nchunk_max = sum((p.numel() + chunk - 1) // chunk for p in group['params'])
-                bufs = []
-                for _ in range(2):
-                    bufs.append({'key': None, 'n': 0, 'nt': 0,
-                                 'host_d': torch.empty(nparam * 48, dtype=torch.uint8).pin_memory(),
-                                 'host_c': torch.empty(nchunk_max * 2, dtype=torch.int32).pin_memory(),
-                                 'descs': torch.empty(nparam * 48, dtype=torch.uint8, device=dev),
-                                 'chunks': torch.empty(nchunk_max * 2, dtype=torch.int32, device=dev)})
-                self._tables[gi] = bufs
-            tab = bufs[1 if capturing else 0]
-            if tab['key'] != key:
-                if tab.get('uploaded') is not None:
-                    # the previous step's non-blocking upload reads the pinned buffers that are rewritten below
-                    tab['uploaded'].synchronize()
-                raw = b''.join(struct.pack('<QQQQQq', *r) for r in rows)
-                table = []
-                for ti, r in enumerate(rows):
-                    for c in range((r[5] + chunk - 1) // chunk):
-                        table += [ti, c]
-                tab['host_d'][:len(raw)] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
-                tab['host_c'][:len(table)] = torch.tensor(table, dtype=torch.int32)
-                tab['key'], tab['n'], tab['nt'] = key, len(table) // 2, len(rows)
-                tab['stale'] = True
-            descs, chunks, nchunks = tab['descs'], tab['chunks'], tab['n']
-            if capturing:
-                # no memcpy nodes inside a captured step (they break the back-to-back kernel scheduling of the graph):
-                # the tables of a capture are static, finish_capture() uploads them once before the first replay
-                tab['dirty'] = True
-            elif tab.get('stale', True):
-                descs.copy_(tab['host_d'], non_blocking=True)
-                chunks.copy_(tab['host_c'], non_blocking=True)
-                if tab.get('uploaded') is None:
-                    tab['uploaded'] = torch.cuda.Event()
-                tab['uploaded'].record()
-                tab['stream'] = torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
-                tab['stale'] = False
-            elif tab.get('stream') != torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()):
-                torch.cuda.current_stream().wait_event(tab['uploaded'])      # uploaded on another stream
-            b1, b2 = group['betas']
-            _lib.call('uz_adam_step_batched', descs.data_ptr(), tab['nt'], chunks.data_ptr(), nchunks,
-                      float(group['lr']), float(b1), float(b2), float(group['eps']), float(group['weight_decay']),
-                      torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+            if live:
+                self._step_list(gi, group, live, len(group['params']),
+                                sum((p.numel() + self._chunk() - 1) // self._chunk() for p in group['params']))
         return loss
+
+    @staticmethod
+    def _chunk():
+        return _lib.raw('uz_adam_chunk_elems')()
+
+    @torch.no_grad()
+    def step_params(self, params, key):
+        """Adam step for a SUBSET of the parameters (those of ``params`` that have a gradient) with its own descriptor
+        table ``key``: b200.dp runs it per gradient bucket as soon as the bucket is complete, next to the rest of backward
+        (reference train_model.py:119 optimizer.step(), executed piecewise; every parameter is still updated exactly once
+        per step with its complete gradient).  Hyper-parameters come from the parameter group of params[0]."""
+        live = [p for p in params if p.grad is not None]
+        if not live:
+            return
+        group = next(g for g in self.param_groups if any(q is live[0] for q in g['params']))
+        chunk = self._chunk()
+        self._step_list(('subset', key), group, live, len(params), sum((p.numel() + chunk - 1) // chunk for p in params))
+
+    def _step_list(self, gi, group, live, nparam_max, nchunk_max):
+        chunk = self._chunk()
+        dev = live[0].device
+        if not live[0].is_cuda:
+            raise _lib.UnetZooLibError('FusedAdam needs CUDA parameters (no CPU fallback path)')
+        # cheap key first: the gradient pointers (new view objects every step, same buffers) + the identity of the state
+        # tensors (replaced only by load_state_dict / reset); the full rows are rebuilt only when it changes
+        gen = self.__dict__.setdefault('_state_gen', 0)
+        state = self.state
+        quick = (gen, tuple(p.grad.data_ptr() for p in live),
+                 tuple(id(state[p].get('exp_avg')) if p in state else 0 for p in live))
+        cache = self.__dict__.setdefault('_row_cache', {})
+        hit = cache.get(gi)
+        if hit is not None and hit[0] == quick:
+            rows, key = hit[1], hit[2]
+        else:
+            rows, key = [], []
+            for p in live:
+                st = self._state(p)
+                g = p.grad
+                if g.dtype != torch.float32 or not g.is_contiguous() or not p.is_contiguous():
+                    raise _lib.UnetZooLibError('FusedAdam expects dense fp32 parameters and gradients')
+                rows.append((p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
+                             st['step'].data_ptr(), p.numel()))
+                key.append(rows[-1])     # every raw pointer the table holds: a replaced state tensor invalidates it
+            key = tuple(key)
+            cache[gi] = (quick, rows, key)
+        # two persistent table sets per group, allocated on first use (never inside a stream capture): one for eager
+        # steps, one for a captured step whose memcpy nodes must keep reading the pointers they were captured with
+        capturing = torch.cuda.is_current_stream_capturing()
+        bufs = self._tables.get(gi)
+        if bufs is None:
+            nparam = nparam_max
+            bufs = []
+            for _ in range(2):
+                bufs.append({'key': None, 'n': 0, 'nt': 0,
+                             'host_d': torch.empty(nparam * 48, dtype=torch.uint8).pin_memory(),
+                             'host_c': torch.empty(nchunk_max * 2, dtype=torch.int32).pin_memory(),
+                             'descs': torch.empty(nparam * 48, dtype=torch.uint8, device=dev),
+                             'chunks': torch.empty(nchunk_max * 2, dtype=torch.int32, device=dev)})
+            self._tables[gi] = bufs
+        tab = bufs[1 if capturing else 0]
+        if tab['key'] != key:
+            if tab.get('uploaded') is not None:
+                # the previous step's non-blocking upload reads the pinned buffers that are rewritten below
+                tab['uploaded'].synchronize()
+            raw = b''.join(struct.pack('<QQQQQq', *r) for r in rows)
+            table = []
+            for ti, r in enumerate(rows):
+                for c in range((r[5] + chunk - 1) // chunk):
+                    table += [ti, c]
+            tab['host_d'][:len(raw)] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+            tab['host_c'][:len(table)] = torch.tensor(table, dtype=torch.int32)
+            tab['key'], tab['n'], tab['nt'] = key, len(table) // 2, len(rows)
+            tab['stale'] = True
+        descs, chunks, nchunks = tab['descs'], tab['chunks'], tab['n']
+        if capturing:
+            # no memcpy nodes inside a captured step (they break the back-to-back kernel scheduling of the graph):
+            # the tables of a capture are static, finish_capture() uploads them once before the first replay
+            tab['dirty'] = True
+        elif tab.get('stale', True):
+            descs.copy_(tab['host_d'], non_blocking=True)
+            chunks.copy_(tab['host_c'], non_blocking=True)
+            if tab.get('uploaded') is None:
+                tab['uploaded'] = torch.cuda.Event()
+            tab['uploaded'].record()
+            tab['stream'] = torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+            tab['stale'] = False
+        elif tab.get('stream') != torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()):
+            torch.cuda.current_stream().wait_event(tab['uploaded'])      # uploaded on another stream
+        b1, b2 = group['betas']
+        _lib.call('uz_adam_step_batched', descs.data_ptr(), tab['nt'], chunks.data_ptr(), nchunks,
+                  float(group['lr']), float(b1), float(b2), float(group['eps']), float(group['weight_decay']),
+                  torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))

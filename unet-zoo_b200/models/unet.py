@@ -105,6 +105,14 @@ class Unet(nn.Module):
     def sample(self, testing=True):
         return self.prediction
 
+    def _packer(self):
+        ws = [m.weight for m in self.modules() if isinstance(m, nn.Conv2d) and m.out_channels % 16 == 0]
+        pk = getattr(self, '_weight_packer', None)
+        if pk is None or not pk.valid_for(ws[0]):
+            pk = kern.WeightPacker(ws)
+            object.__setattr__(self, '_weight_packer', pk)
+        return pk
+
     def features(self, x):
         """encoder-decoder up to (not including) last_layer; returns the NHWC activation handle"""
         if not x.is_cuda:
@@ -114,10 +122,7 @@ class Unet(nn.Module):
         if outer is not None and outer.lookup(ws[0]) is not None:
             pk = outer                                   # an enclosing model (ProbabilisticUnet) already packed them
         else:
-            pk = getattr(self, '_weight_packer', None)
-            if pk is None or not pk.valid_for(ws[0]):
-                pk = kern.WeightPacker(ws)
-                object.__setattr__(self, '_weight_packer', pk)
+            pk = self._packer()
             pk.refresh()
         prev = kern.set_active_packer(pk)
         try:

@@ -205,6 +205,18 @@ int uz_bn_bwd_fused(const void* dout, int ldd, const void* y, int ldy, const flo
                     float count, const float* gamma, const float* mean, const float* invstd, float* dgamma,
                     float* dbeta, void* dy, int lddy, long long npix, int C, void* stream);
 
+/* Conv2D of the reference in training mode as ONE launch (torchlayers.py:18-21: conv + bias -> BatchNorm2d with batch
+ * statistics -> ReLU) for maps whose pixel tiles fit one thread-block cluster (N*H*W <= 1024: the 2x2 ... 8x8 levels at
+ * batch 12): y = conv(x) + bias (bf16, kept for backward); the per-channel sums of the stored y are exchanged between the
+ * tile CTAs through distributed shared memory in a fixed order (deterministic, no atomics, no second launch);
+ * a = act(y*scale + shift) is written from the accumulators still in TMEM.  scale / shift / mean / invstd [Cout]: the
+ * coefficients backward needs; running statistics get stat_updates momentum updates (unbiased variance). */
+int uz_conv_bn_fused_supported(int N, int H, int W, int Cin, int Cout, int taps);
+int uz_conv_bn_act_fused(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, int taps,
+                         const float* bias, const float* gamma, const float* beta, float eps, float momentum,
+                         float* running_mean, float* running_var, int stat_updates, int relu, void* y, int ldy, void* a,
+                         int lda, float* scale_out, float* shift_out, float* mean_out, float* invstd_out, void* stream);
+
 /* Eval-mode fold of conv bias + BatchNorm running stats into the conv epilogue's scale / shift (train_model.py:139). */
 int uz_bn_eval_fold(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
                     const float* running_var, float eps, int C, float* scale, float* shift, void* stream);
@@ -288,6 +300,20 @@ int uz_kl_fwd(const float* mu0, const float* s0, const float* mu1, const float* 
               float weight, float* out, double* partial /* [uz_kl_num_blocks] */, void* stream);
 int uz_kl_bwd(const float* mu0, const float* s0, const float* mu1, const float* s1, int batch, int per_sample,
               float weight, const float* upstream, float* dmu0, float* ds0, float* dmu1, float* ds1, void* stream);
+
+/* The whole hierarchical KL term of PHiSeg (models/phiseg.py:463-472: one KL_two_gauss_with_diag_cov per latent level and
+ * the running `loss_tot += kl_weight * level`) in two launches instead of four per level: levels_out[l] = level_weight[l] *
+ * KL_l, total_out[0] = sum over l = L-1 ... 0 of total_weight * levels_out[l] (fp32, the reference's order).  Arrays of L
+ * host pointers / element counts; partial: L * uz_kl_hierarchy_num_blocks(max numel) doubles.  Backward: 4 * L gradient
+ * pointers ([l*4 + 0..3] = d mu0, d sigma0, d mu1, d sigma1), upstream = d loss / d total_out (device scalar). */
+int uz_kl_hierarchy_num_blocks(long long max_numel);
+int uz_kl_hierarchy_fwd(const float* const* mu0, const float* const* s0, const float* const* mu1, const float* const* s1,
+                        const long long* numel, const float* level_weight, int L, int batch, float total_weight,
+                        double* partial, float* levels_out, float* total_out, void* stream);
+int uz_kl_hierarchy_bwd(const float* const* mu0, const float* const* s0, const float* const* mu1, const float* const* s1,
+                        const long long* numel, const float* level_weight, int L, int batch, float total_weight,
+                        const float* upstream, float* const* grads, void* stream);
+
 
 /* Likelihood.s_layer (1x1 conv to n_classes, no norm / activation) fused with the nearest upsample to full resolution
  * (models/phiseg.py:283-284,319-321): out fp32 NCHW [B,ncls,h*factor,wd*factor]. */
@@ -374,6 +400,28 @@ int uz_conv3d_fwd_ex(const void* x, int N, int D, int H, int W, int Cin, int ldx
 long long uz_wgrad3d_workspace_floats(int N, int D, int H, int W, int Cin, int Cout);
 int uz_conv3d_wgrad(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout,
                     int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream);
+
+/* Deferred split-K reduction: uz_conv_wgrad_partial runs the tensor-core kernel only (partial slabs
+ * [splits][taps][Cout][Cin] fp32 stay in `workspace`, *splits reports their number; D == 0 images, D > 0 volumes with 27
+ * taps), and ONE uz_wgrad_reduce_batched launch later sums the splits of many layers in fixed order and writes their
+ * OIHW gradients dw[Cout][Cin][taps] (the per-layer reduction of uz_conv_wgrad costs a launch per layer and writes with a
+ * stride of `taps` floats).  Rows of the (host) table, at most UZ_WGRAD_REDUCE_MAX_ROWS per launch -- they travel as launch
+ * parameters, so a captured CUDA graph holds them by value: */
+#define UZ_WGRAD_REDUCE_MAX_ROWS 64
+typedef struct UzWgradReduceDesc {
+  const float* partial; /* workspace of the layer */
+  float* dw;            /* fp32 [Cout][Cin][taps] */
+  int splits, taps;
+  int CoutP, CinP;      /* stored (padded) channel counts of the slabs */
+  int Cout, Cin;        /* logical channel counts of dw */
+  int unit_begin;       /* filled in by the library */
+  int reserved;
+} UzWgradReduceDesc;
+int uz_conv_wgrad_partial(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout,
+                          int taps, float* workspace, int* splits, void* stream);
+int uz_wgrad_reduce_units(int Cout_logical, int Cin_logical);
+int uz_wgrad_reduce_batched(const UzWgradReduceDesc* descs, int n, void* stream);
+
 /* nn.AvgPool3d(2, 2, ceil_mode=True) on even sizes (models/phiseg3D.py:100) and its gradient. */
 int uz_avgpool3_fwd(const void* x, int ldx, void* out, int ldo, int N, int Do, int Ho, int Wo, int C, void* stream);
 int uz_avgpool3_bwd(const void* dout, int ldd, void* dx, int ldx, int N, int Do, int Ho, int Wo, int C, void* stream);

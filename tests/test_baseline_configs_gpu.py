@@ -93,7 +93,9 @@ def test_probunet_baseline_size():
           '(rel %.2e), KL %.5g vs %.5g' % (r_rec, r_gap, float(loss), float(ref['loss']), l_err,
                                            float(net.kl_divergence_loss), float(ref['kl'])))
     assert r_rec < 2.0 * r_gap + 5e-3
-    assert l_err < 5e-3
+    # random-weight fixture: the yardstick is the distance of the same-rounding oracle from the fp32 one
+    l_gap = abs(float(emu['loss']) - float(ref['loss'])) / abs(float(ref['loss']))
+    assert l_err < 2.0 * l_gap + 5e-3
 
 
 @pytest.mark.parametrize('reversible', [False, True])

@@ -281,3 +281,88 @@ def test_bn_backward_cluster_kernel(N, H, W, C, ld):
     # the two-launch path sums with atomics in arrival order: equal up to fp32 summation order
     torch.testing.assert_close(dgamma, dgamma_u, rtol=1e-4, atol=1e-4 * float(dgamma_u.abs().max()))
     assert float((dy.float() - dy_u.float()).abs().max()) <= 2 ** -7 * float(dy_u.float().abs().max())
+
+
+def test_deferred_batched_wgrad_reduction():
+    """uz_conv_wgrad_partial + ONE uz_wgrad_reduce_batched launch for a mix of layers (persistent and generic plans, 1x1,
+    padded logical channels, a 3x3x3 volume layer) against the per-layer uz_conv_wgrad: same partial slabs; the batched
+    kernel sums the splits strictly in order, the per-layer one in up to 8 interleaved groups => equal up to fp32
+    summation order (1e-5), and bit-reproducible run to run."""
+    k = kern()
+    cases = [  # N, H, W, Cin, Cout, taps, Cin_logical, Cout_logical
+        (12, 16, 16, 192, 192, 9, 192, 192), (12, 2, 2, 192, 192, 9, 192, 192), (3, 32, 32, 64, 128, 9, 64, 128),
+        (2, 64, 64, 32, 32, 9, 32, 32), (2, 32, 32, 224, 128, 1, 224, 128), (2, 32, 32, 16, 32, 9, 3, 32),
+        (12, 8, 8, 80, 64, 9, 66, 64), (4, 128, 128, 32, 32, 9, 32, 32)]
+    ref, got, keep = [], [], []
+    for i, (N, H, W, Cin, Cout, taps, cil, col) in enumerate(cases):
+        x = to_nhwc(bf16r(_rand(N, Cin, H, W, seed=20 + i)))
+        dy = to_nhwc(bf16r(_rand(N, Cout, H, W, seed=40 + i)))
+        ref.append(k.conv_wgrad(x, dy, taps, cil, col))
+        got.append(k.conv_wgrad(x, dy, taps, cil, col, defer=True))
+        keep.append((x, dy))
+    xv = bf16r(_rand(1, 32, 8, 16, 16, seed=3)).permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    dv = bf16r(_rand(1, 48, 8, 16, 16, seed=4)).permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    ref.append(k.conv_wgrad(xv, dv, 27, 32, 48))
+    got.append(k.conv_wgrad(xv, dv, 27, 32, 48, defer=True))
+    assert len(k.wgrad_reducer.items) == len(cases) + 1
+    k.wgrad_reducer.flush()
+    assert not k.wgrad_reducer.items
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(got, ref)):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5 * float(b.abs().max()), msg='layer %d' % i)
+    again = [k.conv_wgrad(x, dy, c[5], c[6], c[7], defer=True) for (x, dy), c in zip(keep, cases)]
+    k.wgrad_reducer.flush()
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(again, got)):
+        assert torch.equal(a, b), 'layer %d not reproducible' % i
+
+
+# N, H, W, Cin, Cout, taps: 1 / 2 / 6 pixel tiles per cluster, Cout chunks of 48 / 64 / 32, a 1x1 layer, padded inputs
+CONV_BN_FUSED_SHAPES = [(12, 2, 2, 192, 192, 9), (12, 4, 4, 192, 192, 9), (12, 8, 8, 192, 192, 9), (12, 8, 8, 256, 256, 9),
+                        (5, 4, 4, 256, 256, 9), (12, 8, 8, 64, 64, 9), (12, 2, 2, 16, 64, 9), (3, 8, 8, 64, 48, 9),
+                        (12, 8, 8, 192, 32, 1), (16, 8, 8, 32, 32, 9)]
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,taps', CONV_BN_FUSED_SHAPES)
+def test_conv_bn_relu_cluster_kernel(N, H, W, Cin, Cout, taps):
+    """uz_conv_bn_act_fused (conv + batch statistics through the cluster's distributed shared memory + normalise + ReLU in
+    one launch) against the conv -> uz_bn_finalize -> uz_affine_act path and against torch fp32 F.batch_norm on the
+    stored conv output; bit-reproducible run to run."""
+    k = kern()
+    ks = 3 if taps == 9 else 1
+    x = to_nhwc(bf16r(_rand(N, Cin, H, W, seed=1)))
+    w = bf16r(_rand(Cout, Cin, ks, ks, seed=2, scale=0.05))
+    bias = 0.1 * _rand(Cout, seed=8)
+    gamma, beta = 1 + 0.1 * _rand(Cout, seed=3), 0.1 * _rand(Cout, seed=4)
+    rm0, rv0 = 0.1 * _rand(Cout, seed=5), _rand(Cout, seed=6).abs() + 0.5
+    wf, _ = k.pack_conv_weight(w, need_dgrad=False)
+    assert k.conv_bn_fused_supported(x, wf)
+    rm, rv = rm0.clone(), rv0.clone()
+    a, y, scale, shift, mean, invstd = k.conv_bn_act_fused(x, wf, bias, gamma, beta, rm, rv, relu=True)
+    rm_b, rv_b = rm0.clone(), rv0.clone()
+    a_b, y_b, scale_b, _, _, _ = k.conv_bn_act_fused(x, wf, bias, gamma, beta, rm_b, rv_b, relu=True)
+    assert torch.equal(a, a_b) and torch.equal(y, y_b) and torch.equal(scale, scale_b) and torch.equal(rm, rm_b)
+    # split path: same conv kernel (statistics rows reduced in fixed order), then finalize + affine
+    prev = k.set_deterministic(True)
+    try:
+        y2, partial = k.conv_fwd(x, wf, shift=bias, stats=True)
+    finally:
+        k.set_deterministic(prev)
+    rm2, rv2 = rm0.clone(), rv0.clone()
+    scale2, shift2, mean2, invstd2 = k.bn_finalize(partial, N * H * W, gamma, beta, rm2, rv2)
+    a2 = k.affine_act(y2, scale2, shift2, relu=True)
+    assert torch.equal(y, y2)                                              # the stored conv output is the same kernel math
+    torch.testing.assert_close(mean, mean2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(invstd, invstd2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(scale, scale2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(shift, shift2, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rm, rm2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rv, rv2, rtol=1e-5, atol=1e-6)
+    assert float((a.float() - a2.float()).abs().max()) <= 2 ** -7 * float(a2.float().abs().max())     # one bf16 ulp
+    # torch fp32 on the stored y
+    yq = to_nchw(y)
+    ref = F.relu(F.batch_norm(yq, rm0.clone(), rv0.clone(), gamma, beta, True, 0.01, 1e-3))
+    err = (to_nchw(a) - ref).abs()
+    assert float(err.max()) <= 2 ** -7 * float(ref.abs().max()) + 1e-3
+    conv_ref = F.conv2d(to_nchw(x), w, bias, padding=ks // 2)
+    assert rel_err(yq, conv_ref) < 5e-3

@@ -458,3 +458,31 @@ def test_fused_adam_matches_torch_adam():
         torch.testing.assert_close(q, p, rtol=2e-6, atol=1e-7)
     for p, q in zip(ref_p, my_p):
         torch.testing.assert_close(mine.state[q]['exp_avg_sq'], ref.state[p]['exp_avg_sq'], rtol=1e-5, atol=1e-12)
+
+
+def test_kl_hierarchy_matches_per_level_kernels():
+    """uz_kl_hierarchy_fwd / _bwd (all latent levels in one launch, models/phiseg.py:463-472) against the per-level
+    kernels: level values bit-identical (same per-block fp64 partial sums), total = fp32 sum in the reference's order
+    (level L-1 first), gradients bit-identical for an upstream of 1 and scaled for any other."""
+    k = kern()
+    B, L = 12, 5
+    lw = [4.0 ** i for i in range(L)]
+    levels = []
+    for l in range(L):
+        r = 4 << l
+        mk = lambda s, pos: ((_rand(B, 2, r, r, seed=s).abs() + 0.1) if pos else _rand(B, 2, r, r, seed=s)).contiguous()
+        levels.append((mk(10 * l, False), mk(10 * l + 1, True), mk(10 * l + 2, False), mk(10 * l + 3, True)))
+    total, per = k.kl_hierarchy_fwd(levels, lw, 0.5)
+    ref = [k.kl_fwd(*levels[l], lw[l]) for l in range(L)]
+    for l in range(L):
+        assert torch.equal(per[l:l + 1], ref[l]), l
+    want = torch.zeros((), device=DEV)
+    for l in reversed(range(L)):
+        want = want + 0.5 * ref[l][0] if l != L - 1 else 0.5 * ref[l][0]
+    torch.testing.assert_close(total[0], want, rtol=1e-6, atol=0)
+    up = torch.full((1,), 0.75, device=DEV)
+    grads = k.kl_hierarchy_bwd(levels, lw, 0.5, up)
+    for l in range(L):
+        g_ref = k.kl_bwd(*levels[l], lw[l], torch.full((1,), 0.75 * 0.5, device=DEV))
+        for a, b in zip(grads[4 * l:4 * l + 4], g_ref):
+            torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-30)

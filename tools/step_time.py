@@ -46,9 +46,14 @@ def main():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--model', default='phiseg')
     ap.add_argument('--tag', default='')
+    ap.add_argument('--debug-flags', type=int, default=0, help='profiling knobs (needs UNETZOO_PRECISION=prof)')
+    ap.add_argument('--multi-only', action='store_true')
     args = ap.parse_args()
+    if args.debug_flags:
+        from b200 import _lib
+        _lib.call('uz_set_debug_flags', args.debug_flags)
     out = {'tag': args.tag, 'env': {k: v for k, v in os.environ.items() if k.startswith('UZ_') or k.startswith('UNETZOO_')}}
-    for multi in (True, False):
+    for multi in ((True,) if args.multi_only else (True, False)):
         ms, launches, loss = run(multi, args.steps, reversible=args.model == 'revphiseg')
         out['multi_stream' if multi else 'single_stream'] = {'ms': round(ms, 3), 'images_per_s': round(bench.BATCH / ms * 1e3, 1),
                                                             'launches': launches, 'loss': loss}

@@ -210,6 +210,9 @@ class GradientAllReduce:
         else:
             ctx = _NullCtx()
         with ctx:
+            if cuda:
+                from . import kern
+                kern.wgrad_reducer.flush()                 # deferred split-K reductions of the weight gradients so far
             src, dst = [], []
             for p, v in zip(bucket.params, bucket.views):
                 if p.grad.data_ptr() != v.data_ptr():      # conv weight gradients already live in the bucket

@@ -252,32 +252,107 @@ def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=Fa
     return out, partial
 
 
-def conv_wgrad(x, dy, taps, cin_logical, cout_logical, out=None):
+class WgradReducer:
+    """Deferred split-K reductions of the weight gradients (uz_conv_wgrad_partial + uz_wgrad_reduce_batched): the
+    tensor-core kernels of many layers leave their partial slabs behind, ONE launch per <= 64 layers reduces / transposes
+    them into the OIHW gradient tensors.  ``flush()`` must run on a stream that is ordered after every producing launch
+    (b200.ops joins the auxiliary streams first).  The descriptor rows are launch parameters: nothing to upload, a
+    captured CUDA graph holds them by value."""
+    MAX_ROWS = 64
+
+    def __init__(self):
+        self.items = []
+        self.pending_bytes = 0
+        self.keep = []             # slabs / gradient tensors referenced by captured launches
+
+    def add(self, work, splits, taps, coutp, cinp, cout, cin, dw):
+        self.items.append((work, splits, taps, coutp, cinp, cout, cin, dw))
+        self.pending_bytes += work.numel() * 4
+
+    def flush(self):
+        if not self.items:
+            return
+        items, self.items, self.pending_bytes = self.items, [], 0
+        cur = torch.cuda.current_stream(items[0][0].device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        for k in range(0, len(items), self.MAX_ROWS):
+            part = items[k:k + self.MAX_ROWS]
+            raw = b''.join(struct.pack('<QQiiiiiiii', work.data_ptr(), dw.data_ptr(), splits, taps, coutp, cinp, cout,
+                                       cin, 0, 0) for work, splits, taps, coutp, cinp, cout, cin, dw in part)
+            buf = ctypes.create_string_buffer(raw, len(raw))
+            _lib.call('uz_wgrad_reduce_batched', ctypes.cast(buf, ctypes.c_void_p), len(part), _stream())
+        if capturing:
+            self.keep.append(items)
+        else:
+            for it in items:
+                it[0].record_stream(cur)           # slabs may have been allocated on an auxiliary stream
+                it[7].record_stream(cur)
+
+
+wgrad_reducer = WgradReducer()
+
+
+def conv_wgrad(x, dy, taps, cin_logical, cout_logical, out=None, defer=False):
     """-> dw fp32 [cout_logical, cin_logical, taps] (written into ``out``, any contiguous fp32 tensor of that size, when
-    given: data-parallel training lets the kernel produce the gradient inside its all-reduce bucket)"""
+    given: data-parallel training lets the kernel produce the gradient inside its all-reduce bucket).  ``defer``: only
+    the tensor-core kernel runs now; dw is filled by the next ``wgrad_reducer.flush()`` (one launch for many layers)."""
     if out is not None:
         assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == cout_logical * cin_logical * taps
         out = out.view(cout_logical, cin_logical, taps)
     n, h, w, cin, ldx = _check_act(x)
     _, _, _, cout, lddy = _check_act(dy)
-    if x.dim() == 5 and taps == 27:
+    vol = x.dim() == 5 and taps == 27
+    if vol:
         nb, d = x.shape[0], x.shape[1]
         ws = _lib.raw('uz_wgrad3d_workspace_floats')(nb, d, h, w, cin, cout)
-        if ws < 0:
-            raise _lib.UnetZooLibError('uz_conv3d_wgrad: unsupported shape Cin=%d Cout=%d' % (cin, cout))
-        work = torch.empty((ws,), dtype=torch.float32, device=x.device)
-        dw = out if out is not None else torch.empty((cout_logical, cin_logical, taps), dtype=torch.float32, device=x.device)
-        _lib.call('uz_conv3d_wgrad', _p(x), ldx, _p(dy), lddy, nb, d, h, w, cin, cout, cin_logical, cout_logical,
-                  _p(work), _p(dw), _stream())
-        return dw
-    ws = _lib.raw('uz_wgrad_workspace_floats')(n, h, w, cin, cout, taps)
+    else:
+        nb, d = n, 0
+        ws = _lib.raw('uz_wgrad_workspace_floats')(n, h, w, cin, cout, taps)
     if ws < 0:
         raise _lib.UnetZooLibError('uz_conv_wgrad: unsupported shape Cin=%d Cout=%d' % (cin, cout))
     work = torch.empty((ws,), dtype=torch.float32, device=x.device)
     dw = out if out is not None else torch.empty((cout_logical, cin_logical, taps), dtype=torch.float32, device=x.device)
+    if defer:
+        splits = ctypes.c_int(0)
+        _lib.call('uz_conv_wgrad_partial', _p(x), ldx, _p(dy), lddy, nb, d, h, w, cin, cout, taps, _p(work),
+                  ctypes.byref(splits), _stream())
+        wgrad_reducer.add(work, splits.value, taps, cout, cin, cout_logical, cin_logical, dw)
+        return dw
+    if vol:
+        _lib.call('uz_conv3d_wgrad', _p(x), ldx, _p(dy), lddy, nb, d, h, w, cin, cout, cin_logical, cout_logical,
+                  _p(work), _p(dw), _stream())
+        return dw
     _lib.call('uz_conv_wgrad', _p(x), ldx, _p(dy), lddy, n, h, w, cin, cout, taps, cin_logical, cout_logical, _p(work),
               _p(dw), _stream())
     return dw
+
+
+_CONV_BN_FUSED = _os.environ.get('UNETZOO_CONV_BN_FUSED', '1') != '0'
+
+
+def conv_bn_fused_supported(x, w_packed):
+    if not _CONV_BN_FUSED or x.dim() != 4:
+        return False
+    n, h, w, cin, _ = _check_act(x)
+    taps, cout, _ = w_packed.shape
+    return bool(_lib.raw('uz_conv_bn_fused_supported')(n, h, w, cin, cout, taps))
+
+
+def conv_bn_act_fused(x, w_packed, bias, gamma, beta, running_mean, running_var, relu=True, eps=None, momentum=None,
+                      stat_updates=1):
+    """Conv2D (training) in one launch on a thread-block cluster -> (a, y, scale, shift, mean, invstd); see
+    uz_conv_bn_act_fused.  Only for layers with conv_bn_fused_supported()."""
+    n, h, w, cin, ldx = _check_act(x)
+    taps, cout, cin_w = w_packed.shape
+    assert cin_w == cin, (cin_w, cin)
+    y = new_act(n, h, w, cout, x.device)
+    a = new_act(n, h, w, cout, x.device)
+    st = torch.empty((4, cout), dtype=torch.float32, device=x.device)
+    _lib.call('uz_conv_bn_act_fused', _p(x), n, h, w, cin, ldx, _p(w_packed), cout, taps, _p(bias), _p(gamma), _p(beta),
+              BN_EPS if eps is None else eps, BN_MOMENTUM if momentum is None else momentum, _p(running_mean),
+              _p(running_var), int(stat_updates), int(relu), _p(y), cout, _p(a), cout, _p(st[0]), _p(st[1]), _p(st[2]),
+              _p(st[3]), _stream())
+    return a, y, st[0], st[1], st[2], st[3]
 
 
 def bn_finalize(partial, count, gamma, beta, running_mean=None, running_var=None, eps=BN_EPS, momentum=BN_MOMENTUM):
@@ -622,6 +697,34 @@ def kl_bwd(mu0, s0, mu1, s1, weight, upstream):
     return g
 
 
+def _kl_args(levels, level_weights):
+    L = len(levels)
+    cols = [[t[k] for t in levels] for k in range(4)]
+    numel = (ctypes.c_longlong * L)(*[t[0].numel() for t in levels])
+    wts = (ctypes.c_float * L)(*[float(w) for w in level_weights])
+    return L, [_ptr_array(c) for c in cols], numel, wts
+
+
+def kl_hierarchy_fwd(levels, level_weights, total_weight):
+    """levels: L tuples (mu0, sigma0, mu1, sigma1) of contiguous fp32 tensors -> (total fp32 [1], per-level fp32 [L])"""
+    L, ptrs, numel, wts = _kl_args(levels, level_weights)
+    dev = levels[0][0].device
+    nb = _lib.raw('uz_kl_hierarchy_num_blocks')(max(t[0].numel() for t in levels))
+    partial = torch.empty((L * nb,), dtype=torch.float64, device=dev)
+    out = torch.empty((L + 1,), dtype=torch.float32, device=dev)
+    _lib.call('uz_kl_hierarchy_fwd', ptrs[0], ptrs[1], ptrs[2], ptrs[3], numel, wts, L, levels[0][0].shape[0],
+              float(total_weight), _p(partial), _p(out[:L]), _p(out[L:]), _stream())
+    return out[L:], out[:L]
+
+
+def kl_hierarchy_bwd(levels, level_weights, total_weight, upstream):
+    L, ptrs, numel, wts = _kl_args(levels, level_weights)
+    grads = [torch.empty_like(t) for lv in levels for t in lv]
+    _lib.call('uz_kl_hierarchy_bwd', ptrs[0], ptrs[1], ptrs[2], ptrs[3], numel, wts, L, levels[0][0].shape[0],
+              float(total_weight), _p(upstream), _ptr_array(grads), _stream())
+    return grads
+
+
 def slayer_fwd(feat, w, bias, factor):
     n, h, wd, c, ld = _check_act(feat)
     ncls = w.shape[0]
@@ -659,6 +762,17 @@ def _ptr_array(tensors):
     for i, t in enumerate(tensors):
         arr[i] = None if t is None else t.data_ptr()
     return arr
+
+
+_ones = {}
+
+
+def one_scalar(device):
+    """a cached fp32 device scalar 1.0 (created outside any stream capture on first use)"""
+    key = (device.type, device.index)
+    if key not in _ones:
+        _ones[key] = torch.ones((1,), dtype=torch.float32, device=device)
+    return _ones[key]
 
 
 def residual_ce(s_list, target, need_grad=True, upstream=None):

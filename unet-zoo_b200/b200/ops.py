@@ -83,14 +83,44 @@ def pending_aux_streams():
 
 
 def sync_aux_streams():
-    """make the current stream wait for every outstanding auxiliary-stream launch"""
+    """make the current stream wait for every outstanding auxiliary-stream launch, then reduce the weight-gradient
+    partials that are still pending (one launch)"""
     cur = torch.cuda.current_stream()
     for st in _aux['pending']:
         cur.wait_stream(st)
     _aux['pending'] = []
+    kern.wgrad_reducer.flush()
     _aux['keep'] = []
     _aux['callback_queued'] = False
     _aux['next'] = 0
+
+
+# Weight gradients leave their split-K partial slabs behind; one batched launch per ~_FLUSH_BYTES of slabs (on an
+# auxiliary stream, next to the dgrad chain) and one at the end of backward reduce them into the OIHW gradients.  The
+# per-layer reduction kernels were ~0.7 ms of a 8.3 ms single-stream PHiSeg step (106 launches writing with a 36-byte
+# stride).  UNETZOO_DEFER_WGRAD_REDUCE=0 restores them.
+_DEFER_REDUCE = _os.environ.get('UNETZOO_DEFER_WGRAD_REDUCE', '1') != '0'
+_FLUSH_BYTES = int(_os.environ.get('UNETZOO_WGRAD_FLUSH_MB', '64')) << 20
+
+
+def _can_defer(weight):
+    """the gradient tensor is handed to autograd before it is filled: only safe when nothing reads it before the end of
+    backward -- no accumulation into an existing .grad, no tensor hooks on the parameter"""
+    return _DEFER_REDUCE and weight.grad is None and not weight._backward_hooks
+
+
+def _flush_partials_if_large():
+    if kern.wgrad_reducer.pending_bytes < _FLUSH_BYTES or not _aux['pending']:
+        return
+    dev = kern.wgrad_reducer.items[0][0].device
+    st = _aux_stream(dev)
+    for other in _aux['pending']:
+        if other is not st:
+            st.wait_stream(other)
+    with torch.cuda.stream(st):
+        kern.wgrad_reducer.flush()
+    if st not in _aux['pending']:
+        _aux['pending'].append(st)
 
 
 _BIG_MAP_PIXELS = int(_os.environ.get('UNETZOO_WGRAD_BIG_PIXELS', str(12 * 128 * 128)))
@@ -110,6 +140,9 @@ def _run_on_aux(fn, keep, last=False):
         _aux['planned_for'] = None
     else:
         _plan_wgrad_share(overlapped)
+    if not _aux['callback_queued'] and torch._C._current_graph_task_id() != -1:
+        _aux['callback_queued'] = True          # also joins / flushes when nothing ran on an auxiliary stream
+        torch.autograd.Variable._execution_engine.queue_callback(sync_aux_streams)
     if not overlapped:
         return fn()
     cur = torch.cuda.current_stream()
@@ -120,9 +153,7 @@ def _run_on_aux(fn, keep, last=False):
     _aux['keep'].append((keep, out))          # inputs stay referenced until the join: no early reuse of their memory
     if st not in _aux['pending']:
         _aux['pending'].append(st)
-    if not _aux['callback_queued']:
-        _aux['callback_queued'] = True
-        torch.autograd.Variable._execution_engine.queue_callback(sync_aux_streams)
+    _flush_partials_if_large()
     return out
 
 
@@ -201,7 +232,9 @@ def _bucket_view(weight):
 class ConvBNAct(torch.autograd.Function):
     """Conv2D of the reference (torchlayers.py:7-29): conv(k=3 pad 1 | k=1) + bias -> BatchNorm(train) -> ReLU.
 
-    forward (training): tcgen05 conv with statistics epilogue -> uz_bn_apply_train (finalize + normalise + ReLU).
+    forward (training): tcgen05 conv with statistics epilogue -> uz_bn_apply_train (finalize + normalise + ReLU); maps of
+    up to 1024 pixels (2x2 ... 8x8 at batch 12) take ONE launch (uz_conv_bn_act_fused: statistics exchanged through the
+    distributed shared memory of a thread-block cluster).
     backward: BN/ReLU backward (reduction fused into the consumer's dgrad epilogue when possible, else its own launch;
     then the apply pass) -> dgrad (same conv kernel, flipped weights) + tcgen05 wgrad.
     Deterministic mode (kern.set_deterministic): statistics as per-CTA rows reduced in fixed order by uz_bn_finalize /
@@ -213,15 +246,21 @@ class ConvBNAct(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, relu, cin_logical):
         need_dx = ctx.needs_input_grad[0]
         wf, wd = kern.pack_conv_weight(weight, need_dgrad=need_dx)
-        y, sums = kern.conv_fwd(x, wf, shift=bias, stats=True)
-        npix = kern._spatial_numel(x.shape[:-1])
         ctx.det = kern.is_deterministic() and x.dim() == 4
-        if ctx.det:
-            scale, shift, mean, invstd = kern.bn_finalize(sums, npix, gamma, beta, running_mean, running_var)
-            a = kern.affine_act(y, scale, shift, relu=relu)
+        npix = kern._spatial_numel(x.shape[:-1])
+        if kern.conv_bn_fused_supported(x, wf):
+            # small maps: conv + batch statistics (exchanged inside a thread-block cluster, fixed order) + normalise + ReLU
+            # in ONE launch
+            a, y, scale, shift, mean, invstd = kern.conv_bn_act_fused(x, wf, bias, gamma, beta, running_mean, running_var,
+                                                                      relu=relu)
         else:
-            a, scale, shift, mean, invstd = kern.bn_apply_train(y, sums, npix, gamma, beta, running_mean, running_var,
-                                                                relu=relu)
+            y, sums = kern.conv_fwd(x, wf, shift=bias, stats=True)
+            if ctx.det:
+                scale, shift, mean, invstd = kern.bn_finalize(sums, npix, gamma, beta, running_mean, running_var)
+                a = kern.affine_act(y, scale, shift, relu=relu)
+            else:
+                a, scale, shift, mean, invstd = kern.bn_apply_train(y, sums, npix, gamma, beta, running_mean, running_var,
+                                                                    relu=relu)
         src = getattr(x, '_uz_bn', None) if (need_dx and _FUSE_BN_BWD and not ctx.det and x.dim() == 4) else None
         ctx.fuse_src = src is not None
         if src is not None:
@@ -259,7 +298,8 @@ class ConvBNAct(torch.autograd.Function):
                 dx, _ = kern.conv_fwd(dy, wd)
         cout, cin = ctx.wshape[0], ctx.wshape[1]
         taps = kern._spatial_numel(ctx.wshape[2:])
-        dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, taps, cin, cout, out=_bucket_view(ctx.weight_ref)),
+        defer = _can_defer(ctx.weight_ref)
+        dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, taps, cin, cout, out=_bucket_view(ctx.weight_ref), defer=defer),
                          (x, dy), last=not ctx.needs_input_grad[0]).view(ctx.wshape)
         dbias = kern.zero_arena.get(cout, dy.device)
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None
@@ -280,6 +320,7 @@ class ConvAffineAct(torch.autograd.Function):
         ctx.relu = relu
         ctx.cin_logical = cin_logical
         ctx.wshape = weight.shape
+        ctx.weight_ref = weight
         ctx.bias_is_shift = bias_is_shift
         return a
 
@@ -301,7 +342,8 @@ class ConvAffineAct(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx, _ = kern.conv_fwd(dy, wd)
-        dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, taps, cin, cout), (x, dy)).view(ctx.wshape)
+        dw = _run_on_aux(lambda: kern.conv_wgrad(x, dy, taps, cin, cout, defer=_can_defer(ctx.weight_ref)),
+                         (x, dy)).view(ctx.wshape)
         dshift = None
         if ctx.bias_is_shift and ctx.needs_input_grad[3]:
             dshift = kern.channel_sum(dy)
@@ -416,6 +458,29 @@ class KLLevel(torch.autograd.Function):
         return g[0], g[1], g[2], g[3], None
 
 
+class KLHierarchy(torch.autograd.Function):
+    """calculate_hierarchical_KL_div_loss (models/phiseg.py:463-472) for all latent levels at once: returns
+    (sum_l total_weight * w_l * KL_l  -- added in the reference's order l = L-1 ... 0 --, per-level w_l * KL_l for the
+    loss dictionary).  Two launches forward, one backward, instead of four / two per level."""
+
+    @staticmethod
+    def forward(ctx, level_weights, total_weight, *tensors):
+        ts = [t.contiguous() for t in tensors]
+        levels = [tuple(ts[i:i + 4]) for i in range(0, len(ts), 4)]
+        total, per_level = kern.kl_hierarchy_fwd(levels, level_weights, total_weight)
+        ctx.save_for_backward(*ts)
+        ctx.cfg = (tuple(level_weights), float(total_weight))
+        ctx.mark_non_differentiable(per_level)
+        return total.reshape(()), per_level
+
+    @staticmethod
+    def backward(ctx, up, _unused):
+        ts = ctx.saved_tensors
+        levels = [tuple(ts[i:i + 4]) for i in range(0, len(ts), 4)]
+        grads = kern.kl_hierarchy_bwd(levels, ctx.cfg[0], ctx.cfg[1], up.reshape(1).contiguous().float())
+        return (None, None) + tuple(grads)
+
+
 class SLayerNearest(torch.autograd.Function):
     """1x1 conv to class logits + nearest upsample to the image size (models/phiseg.py:319-321)."""
 
@@ -445,14 +510,19 @@ class ResidualCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, target, *s_list):
         s_list = [s.contiguous() for s in s_list]
-        ce, _ = kern.residual_ce(s_list, target, need_grad=False)
-        ctx.save_for_backward(target, *s_list)
+        need = any(ctx.needs_input_grad[1:])
+        if need:
+            # ONE pass: the gradients for an upstream of 1 come out of the same kernel run as the values (they cost 8 B per
+            # logit to keep); backward only scales them.  The second, gradient-only run sat alone on the step's critical
+            # path between forward and backward (~55 us of an otherwise idle GPU).
+            ce, grads = kern.residual_ce(s_list, target, need_grad=True, upstream=kern.one_scalar(s_list[0].device))
+            ctx.grads = grads
+        else:
+            ce, _ = kern.residual_ce(s_list, target, need_grad=False)
         total = ce.sum()
         ctx.mark_non_differentiable(ce)
         return total, ce
 
     @staticmethod
     def backward(ctx, up, _unused):
-        target, *s_list = ctx.saved_tensors
-        _, grads = kern.residual_ce(list(s_list), target, need_grad=True, upstream=up.reshape(1).contiguous().float())
-        return (None,) + tuple(grads)
+        return (None,) + tuple(torch._foreach_mul(ctx.grads, up.reshape(()).float()))

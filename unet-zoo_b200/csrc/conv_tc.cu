@@ -56,6 +56,21 @@ struct ConvParams {
   const __nv_bfloat16* res;
   int ld_res;
   float res_sign;
+  // fused training-mode BatchNorm + ReLU (uz_conv_bn_act_fused): the CTAs of all pixel tiles form a thread-block cluster
+  // and exchange their per-channel sums through distributed shared memory; y keeps the conv output, a the activation
+  int fuse_bn;
+  float bn_count, bn_eps, bn_momentum;
+  const float* bn_gamma;
+  const float* bn_beta;
+  float* bn_running_mean;
+  float* bn_running_var;
+  int bn_updates, bn_act_relu;
+  float* bn_scale_out;
+  float* bn_shift_out;
+  float* bn_mean_out;
+  float* bn_invstd_out;
+  __nv_bfloat16* a_out;
+  int lda;
   int dbg;             // profiling knobs (uz_set_debug_flags): 1 = no epilogue body, 2 = no MMA, 4 = no A loads, 8 = no B loads
   unsigned long long* trace;   // profiling build: phase timestamps of CTA 0
 };
@@ -110,6 +125,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   __shared__ float s_stats[4][2][256];
   __shared__ float s_scale2[256];
   __shared__ float s_shift2[256];
+  __shared__ float s_cta[2][256];     // fused BatchNorm: this CTA's (tile's) per-channel sum / sum of squares
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -268,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
       }
-      if (p.stats || bn) {
+      if (p.stats || bn || p.fuse_bn) {
         float sq[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) sq[j] = v[j] * (bn ? yv[j] : v[j]);
@@ -280,7 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
       }
     }
-    if (p.stats || p.bn_sums) {
+    if (p.stats || p.bn_sums || p.fuse_bn) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int et = threadIdx.x - 64;
       float* acc = p.stats ? p.stats : p.bn_sums;
@@ -288,8 +304,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const int which = i / p.BN, c = i - which * p.BN;
         if (!UZ_DBG(p, 1)) {
           const float t = (s_stats[0][which][c] + s_stats[1][which][c]) + (s_stats[2][which][c] + s_stats[3][which][c]);
-          if (p.stats_rows) acc[(static_cast<size_t>(tile) * 2 + which) * p.Cout + c_out0 + c] = t;
+          if (p.fuse_bn) s_cta[which][c] = t;
+          else if (p.stats_rows) acc[(static_cast<size_t>(tile) * 2 + which) * p.Cout + c_out0 + c] = t;
           else atomicAdd(acc + which * p.Cout + c_out0 + c, t);
+        }
+      }
+    }
+  }
+
+  if (p.fuse_bn) {
+    // ===================== BatchNorm statistics across the cluster (all threads of all CTAs take part in the barriers)
+    uz::tc_fence_before();
+    uz::cluster_sync_all();                      // every tile's s_cta is complete and visible cluster-wide
+    if (warp >= 2) {
+      const int et = threadIdx.x - 64;
+      const uint32_t ntiles = uz::cluster_nctarank();
+      for (int c = et; c < p.BN; c += 128) {
+        float s1 = 0.f, s2 = 0.f;
+        for (uint32_t r = 0; r < ntiles; ++r) {  // fixed rank order: run-to-run deterministic
+          s1 += uz::cluster_ld_f32(uz::cluster_map(&s_cta[0][c], r));
+          s2 += uz::cluster_ld_f32(uz::cluster_map(&s_cta[1][c], r));
+        }
+        const int cg = c_out0 + c;
+        const float mean = s1 / p.bn_count;
+        const float var = fmaxf(s2 / p.bn_count - mean * mean, 0.f);
+        const float invstd = rsqrtf(var + p.bn_eps);
+        const float sc = (p.bn_gamma ? p.bn_gamma[cg] : 1.f) * invstd;
+        const float sh = (p.bn_beta ? p.bn_beta[cg] : 0.f) - mean * sc;
+        s_scale2[c] = sc;
+        s_shift2[c] = sh;
+        if (uz::cluster_ctarank() == 0) {
+          p.bn_scale_out[cg] = sc;
+          p.bn_shift_out[cg] = sh;
+          p.bn_mean_out[cg] = mean;
+          p.bn_invstd_out[cg] = invstd;
+          if (p.bn_running_mean) {
+            const float unbiased = p.bn_count > 1.f ? var * p.bn_count / (p.bn_count - 1.f) : var;
+            float rm = p.bn_running_mean[cg], rv = p.bn_running_var[cg];
+            for (int u = 0; u < p.bn_updates; ++u) {
+              rm = (1.f - p.bn_momentum) * rm + p.bn_momentum * mean;
+              rv = (1.f - p.bn_momentum) * rv + p.bn_momentum * unbiased;
+            }
+            p.bn_running_mean[cg] = rm;
+            p.bn_running_var[cg] = rv;
+          }
+        }
+      }
+    }
+    uz::cluster_sync_all();                      // nobody reads remote shared memory any more; s_scale2 / s_shift2 visible
+    if (warp >= 2) {
+      // second pass over the accumulators still in TMEM: a = act(BatchNorm(y)) from the bf16-rounded y that was stored
+      uz::tc_fence_after();
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int box_px = p.TW * p.TH;
+      const int xx = row % p.TW, yy = (row / p.TW) % p.TH, nn = row / box_px;
+      const bool valid = (n0 + nn) < p.N;
+      const size_t pix = (static_cast<size_t>(n0 + nn) * p.H + (y0 + yy)) * p.W + (x0 + xx);
+      __nv_bfloat16* dst = p.a_out + pix * p.lda + c_out0;
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t r[16];
+        uz::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+        uz::tmem_ld_wait();
+        uint32_t packed[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t yq = uz::pack_bf16x2(fmaf(__uint_as_float(r[2 * j]), s_scale[c + 2 * j], s_shift[c + 2 * j]),
+                                              fmaf(__uint_as_float(r[2 * j + 1]), s_scale[c + 2 * j + 1], s_shift[c + 2 * j + 1]));
+          float v0 = fmaf(uz::bf16lo(yq), s_scale2[c + 2 * j], s_shift2[c + 2 * j]);
+          float v1 = fmaf(uz::bf16hi(yq), s_scale2[c + 2 * j + 1], s_shift2[c + 2 * j + 1]);
+          if (p.bn_act_relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          packed[j] = uz::pack_bf16x2(v0, v1);
+        }
+        if (valid) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+          d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
         }
       }
     }
@@ -343,9 +433,76 @@ extern "C" int uz_conv_stats_rows(int N, int H, int W, int Cin, int Cout, int ta
   return tiles;
 }
 
+namespace {
+// training-mode BatchNorm + activation fused into the generic kernel (one thread-block cluster over the pixel tiles)
+struct FusedBn {
+  float count, eps, momentum;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  int updates, relu;
+  float* scale_out;
+  float* shift_out;
+  float* mean_out;
+  float* invstd_out;
+  void* a;
+  int lda;
+};
+constexpr int kMaxClusterTiles = 8;     // portable cluster size
+
+int conv_fwd_impl(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, int taps, void* y,
+                  int ldy, const float* scale, const float* shift, int relu, float* stats_partial, const UzConvExtra* ex,
+                  const FusedBn* fb, void* stream);
+}  // namespace
+
 extern "C" int uz_conv_fwd_ex(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout,
                               int taps, void* y, int ldy, const float* scale, const float* shift, int relu,
                               float* stats_partial, const UzConvExtra* ex, void* stream) {
+  return conv_fwd_impl(x, N, H, W, Cin, ldx, w_packed, Cout, taps, y, ldy, scale, shift, relu, stats_partial, ex, nullptr,
+                       stream);
+}
+
+// 1 if uz_conv_bn_act_fused has a plan: a layer of the generic kernel (maps that the persistent kernel does not take)
+// whose pixel tiles fit one portable cluster
+extern "C" int uz_conv_bn_fused_supported(int N, int H, int W, int Cin, int Cout, int taps) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || Cin % 16 || Cout % 16 || (taps != 9 && taps != 1)) return 0;
+  if (taps == 9 && !UZ_KNOB(32) && uz::conv2_stats_rows(N, H, W, Cin, Cout) > 0) return 0;
+  int tiles = 0;
+  uz_conv_tile_geometry(N, H, W, nullptr, nullptr, nullptr, &tiles);
+  int bn = Cout;
+  while (bn > 256) { if (bn % 32) return 0; bn /= 2; }
+  return tiles <= kMaxClusterTiles ? 1 : 0;
+}
+
+// Conv2D of the reference in training mode as ONE launch (torchlayers.py:18-21: conv + bias -> BatchNorm2d(batch
+// statistics, eps, momentum) -> ReLU): y = conv(x) + bias (bf16, kept for backward), per-channel statistics of the stored
+// y exchanged between the pixel-tile CTAs of a cluster through distributed shared memory (fixed order: deterministic),
+// a = act(y * scale + shift) written from the accumulators still in TMEM.  scale / shift / mean / invstd [Cout] are the
+// coefficients backward needs; running statistics get `stat_updates` momentum updates (unbiased variance).
+extern "C" int uz_conv_bn_act_fused(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout,
+                                    int taps, const float* bias, const float* gamma, const float* beta, float eps,
+                                    float momentum, float* running_mean, float* running_var, int stat_updates, int relu,
+                                    void* y, int ldy, void* a, int lda, float* scale_out, float* shift_out,
+                                    float* mean_out, float* invstd_out, void* stream) {
+  UZ_CHECK_ARG(uz_conv_bn_fused_supported(N, H, W, Cin, Cout, taps), "uz_conv_bn_act_fused: no plan for this layer");
+  UZ_CHECK_ARG(a && scale_out && shift_out && mean_out && invstd_out, "uz_conv_bn_act_fused: null pointer");
+  UZ_CHECK_ARG(lda % 8 == 0 && lda >= Cout && (reinterpret_cast<uintptr_t>(a) & 15) == 0, "uz_conv_bn_act_fused: bad a");
+  UZ_CHECK_ARG(stat_updates >= 0 && stat_updates <= 4, "uz_conv_bn_act_fused: stat_updates %d", stat_updates);
+  FusedBn fb{};
+  fb.count = static_cast<float>(static_cast<double>(N) * H * W);
+  fb.eps = eps; fb.momentum = momentum; fb.gamma = gamma; fb.beta = beta;
+  fb.running_mean = running_mean; fb.running_var = running_mean ? running_var : nullptr;
+  fb.updates = stat_updates; fb.relu = relu;
+  fb.scale_out = scale_out; fb.shift_out = shift_out; fb.mean_out = mean_out; fb.invstd_out = invstd_out;
+  fb.a = a; fb.lda = lda;
+  return conv_fwd_impl(x, N, H, W, Cin, ldx, w_packed, Cout, taps, y, ldy, nullptr, bias, 0, nullptr, nullptr, &fb, stream);
+}
+
+namespace {
+int conv_fwd_impl(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, int taps, void* y,
+                  int ldy, const float* scale, const float* shift, int relu, float* stats_partial, const UzConvExtra* ex,
+                  const FusedBn* fb, void* stream) {
   UZ_CHECK_ARG(x && w_packed && y, "uz_conv_fwd: null pointer");
   if (ex) {
     UZ_CHECK_ARG(!ex->bn_y || (ex->bn_scale && ex->bn_shift && ex->bn_sums && ex->bn_ldy % 8 == 0 && ex->bn_ldy >= Cout &&
@@ -364,7 +521,7 @@ extern "C" int uz_conv_fwd_ex(const void* x, int N, int H, int W, int Cin, int l
                    (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
                "uz_conv_fwd: pointers must be 16-byte aligned");
   if UZ_KNOB(128) return UZ_OK;   // measurement knob: step time without the conv kernels
-  if (taps == 9 && !UZ_KNOB(32)) {
+  if (taps == 9 && !UZ_KNOB(32) && !fb) {
     int handled = 0;
     int rc = uz::conv2_launch(x, N, 0, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, ex,
                               stream, &handled);
@@ -395,6 +552,16 @@ extern "C" int uz_conv_fwd_ex(const void* x, int N, int H, int W, int Cin, int l
     p.bn_scale = ex->bn_scale; p.bn_shift = ex->bn_shift; p.bn_relu = ex->bn_relu; p.bn_sums = ex->bn_sums;
     p.res = static_cast<const __nv_bfloat16*>(ex->residual); p.ld_res = ex->ld_res;
     p.res_sign = ex->res_sign < 0 ? -1.f : 1.f;
+  }
+  if (fb) {
+    p.fuse_bn = 1;
+    p.bn_count = fb->count; p.bn_eps = fb->eps; p.bn_momentum = fb->momentum;
+    p.bn_gamma = fb->gamma; p.bn_beta = fb->beta;
+    p.bn_running_mean = fb->running_mean; p.bn_running_var = fb->running_var;
+    p.bn_updates = fb->updates; p.bn_act_relu = fb->relu;
+    p.bn_scale_out = fb->scale_out; p.bn_shift_out = fb->shift_out;
+    p.bn_mean_out = fb->mean_out; p.bn_invstd_out = fb->invstd_out;
+    p.a_out = static_cast<__nv_bfloat16*>(fb->a); p.lda = fb->lda;
   }
   p.dbg = uz::g_conv_debug_flags;
 #ifdef UZ_PROFILE_KNOBS
@@ -462,10 +629,12 @@ extern "C" int uz_conv_fwd_ex(const void* x, int N, int H, int W, int Cin, int l
     attr_bytes = smem;
   }
   dim3 grid(tiles, splits, 1);
-  uz::launch(kernel, grid, kThreads, smem, static_cast<cudaStream_t>(stream), tx, tw, p);
+  if (fb) uz::launch_cluster(kernel, grid, kThreads, smem, static_cast<cudaStream_t>(stream), dim3(tiles, 1, 1), tx, tw, p);
+  else uz::launch(kernel, grid, kThreads, smem, static_cast<cudaStream_t>(stream), tx, tw, p);
   UZ_CHECK_LAUNCH("uz_conv_fwd");
   return UZ_OK;
 }
+}  // namespace
 
 // volumes: x bf16 NDHWC [N,D,H,W,Cin]; taps 27 (3x3x3, pad 1; packed [(kd*3+kw)*3+kh][Cout][Cin]) or 1 (1x1x1)
 extern "C" int uz_conv3d_fwd(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout,

@@ -179,14 +179,50 @@ head_bwd_kernel(const __nv_bfloat16* __restrict__ feat, int ld, int C, const flo
   if (threadIdx.x < 2 * Z) bpartial[blockIdx.x * 2 * Z + threadIdx.x] = db_s[threadIdx.x];
 }
 
-// out[i] = sum_b partial[b][i]   (fixed order, deterministic)
-__global__ void column_reduce_kernel(const float* __restrict__ partial, int nblocks, int n, float* out, float scale) {
+// out[i] = scale * sum_b partial[b][i] for up to two segments (weight and bias partials of one layer) in ONE launch.
+// A block is 32 columns x 32 row groups: group g sums rows g, g+32, ... (four loads in flight), the groups are combined
+// through shared memory in a fixed order => deterministic.  The first version walked all rows with one thread per
+// column: a chain of up to 768 dependent L2 loads, 8-16 us per launch on the loss / head backward chains.
+struct ColSeg {
+  const float* partial;
+  float* out;
+  int n;        // columns
+  int blocks;   // thread blocks of this segment = ceil(n / 32)
+};
+
+__global__ void __launch_bounds__(1024) column_reduce_kernel(const ColSeg a, const ColSeg b, int nrows, float scale) {
   uz::pdl_prologue();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  __shared__ float red[32][33];
+  const bool second = static_cast<int>(blockIdx.x) >= a.blocks;
+  const ColSeg sg = second ? b : a;
+  const int col = (static_cast<int>(blockIdx.x) - (second ? a.blocks : 0)) * 32 + (threadIdx.x & 31);
+  const int g = threadIdx.x >> 5;
   float t = 0.f;
-  for (int b = 0; b < nblocks; ++b) t += partial[static_cast<size_t>(b) * n + i];
-  out[i] = t * scale;
+  if (col < sg.n) {
+    const float* src = sg.partial + col;
+    int r = g;
+    for (; r + 96 < nrows; r += 128) {
+      const float v0 = src[static_cast<size_t>(r) * sg.n], v1 = src[static_cast<size_t>(r + 32) * sg.n];
+      const float v2 = src[static_cast<size_t>(r + 64) * sg.n], v3 = src[static_cast<size_t>(r + 96) * sg.n];
+      t = (((t + v0) + v1) + v2) + v3;
+    }
+    for (; r < nrows; r += 32) t += src[static_cast<size_t>(r) * sg.n];
+  }
+  red[g][threadIdx.x & 31] = t;
+  __syncthreads();
+  if (g == 0 && col < sg.n) {
+    float tot = red[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 32; ++k) tot += red[k][threadIdx.x];
+    sg.out[col] = tot * scale;
+  }
+}
+
+static inline cudaError_t launch_column_reduce(cudaStream_t st, const float* p0, int n0, float* o0, const float* p1, int n1,
+                                               float* o1, int nrows, float scale) {
+  ColSeg a{p0, o0, n0, (n0 + 31) / 32};
+  ColSeg b{p1, o1, p1 ? n1 : 0, p1 ? (n1 + 31) / 32 : 0};
+  return uz::launch(column_reduce_kernel, a.blocks + b.blocks, 1024, 0, st, a, b, nrows, scale);
 }
 
 // ---------------------------------------------------------------- KL (one level)
@@ -229,6 +265,94 @@ __global__ void kl_bwd_kernel(const float* __restrict__ mu0, const float* __rest
   uz::pdl_prologue();
   const float g = upstream[0] * scale;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float a = s0[i], b = s1[i], d = mu1[i] - mu0[i];
+    const float t = b * a + 1e-10f, u = a * a + 1e-10f, num = a * a + d * d;
+    const float it = 1.f / t;
+    dmu0[i] = -g * d * it;
+    dmu1[i] = g * d * it;
+    ds1[i] = 0.5f * g * (a * it - num * a * it * it);
+    ds0[i] = 0.5f * g * (2.f * a * it - num * b * it * it + b * it - 2.f * a / u);
+  }
+}
+
+// ---------------------------------------------------------------- KL, all latent levels of the hierarchy in one launch
+// (reference models/phiseg.py:463-472 calculate_hierarchical_KL_div_loss: five KL_two_gauss_with_diag_cov calls and a
+// running `loss_tot += weight * KL`): blockIdx.y = level.  levels_out[l] = w_l * KL_l; total_out = sum of
+// total_weight * levels_out[l] over l = L-1 ... 0 in fp32, the order the reference adds them in.
+struct KlLevels {
+  const float* mu0[kMaxLvl];
+  const float* s0[kMaxLvl];
+  const float* mu1[kMaxLvl];
+  const float* s1[kMaxLvl];
+  float* g[kMaxLvl][4];      // backward: dmu0, ds0, dmu1, ds1
+  long long n[kMaxLvl];
+  float scale[kMaxLvl];      // level weight / batch
+  int L;
+};
+
+__global__ void __launch_bounds__(1024) kl_fwd_batched_kernel(const KlLevels p, int blocks_per_level, double* partial) {
+  uz::pdl_prologue();
+  __shared__ double red[32];
+  const int l = blockIdx.y;
+  const float* __restrict__ mu0 = p.mu0[l];
+  const float* __restrict__ s0 = p.s0[l];
+  const float* __restrict__ mu1 = p.mu1[l];
+  const float* __restrict__ s1 = p.s1[l];
+  const long long n = p.n[l];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float a = s0[i], b = s1[i], d = mu1[i] - mu0[i];
+    const float v0 = a * a, v1 = b * a;
+    acc += static_cast<double>((v0 + d * d) / (v1 + 1e-10f) + logf(v1 + 1e-10f) - logf(v0 + 1e-10f) - 1.f);
+  }
+  acc = uz::warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    t = uz::warp_sum_d(t);
+    if (threadIdx.x == 0) partial[l * blocks_per_level + blockIdx.x] = t;
+  }
+}
+
+__global__ void kl_finish_batched_kernel(const KlLevels p, const double* __restrict__ partial, int blocks_per_level,
+                                         float total_weight, float* levels_out, float* total_out) {
+  uz::pdl_prologue();
+  __shared__ float lv[kMaxLvl];
+  const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (l < p.L) {
+    double t = 0.0;
+    for (int b = lane; b < blocks_per_level; b += 32) t += partial[l * blocks_per_level + b];
+    t = uz::warp_sum_d(t);
+    if (lane == 0) {
+      lv[l] = static_cast<float>(0.5 * t * p.scale[l]);
+      levels_out[l] = lv[l];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = total_weight * lv[p.L - 1];
+    for (int k = p.L - 2; k >= 0; --k) tot += total_weight * lv[k];
+    total_out[0] = tot;
+  }
+}
+
+__global__ void kl_bwd_batched_kernel(const KlLevels p, float total_weight, const float* __restrict__ upstream) {
+  uz::pdl_prologue();
+  const int l = blockIdx.y;
+  const float* __restrict__ mu0 = p.mu0[l];
+  const float* __restrict__ s0 = p.s0[l];
+  const float* __restrict__ mu1 = p.mu1[l];
+  const float* __restrict__ s1 = p.s1[l];
+  float* dmu0 = p.g[l][0];
+  float* ds0 = p.g[l][1];
+  float* dmu1 = p.g[l][2];
+  float* ds1 = p.g[l][3];
+  const float g = (upstream[0] * total_weight) * p.scale[l];
+  const long long n = p.n[l];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float a = s0[i], b = s1[i], d = mu1[i] - mu0[i];
     const float t = b * a + 1e-10f, u = a * a + 1e-10f, num = a * a + d * d;
     const float it = 1.f / t;
@@ -598,8 +722,7 @@ extern "C" int uz_head_bwd(const void* feat, int ld, int C, const float* wmu, co
                                                             eps, sigma, dmu, dsigma, dz, B, hw,
                                                             static_cast<__nv_bfloat16*>(dfeat), ldd, wpartial, bpartial);
   UZ_CHECK_LAUNCH("uz_head_bwd");
-  uz::launch(column_reduce_kernel, (4 * C + 127) / 128, 128, 0, ST(stream), wpartial, blocks, 4 * C, dw, 1.f);
-  uz::launch(column_reduce_kernel, 1, 32, 0, ST(stream), bpartial, blocks, 4, db, 1.f);
+  launch_column_reduce(ST(stream), wpartial, 4 * C, dw, bpartial, 4, db, blocks, 1.f);
   UZ_CHECK_LAUNCH("uz_head_bwd(reduce)");
   return UZ_OK;
 }
@@ -627,6 +750,70 @@ extern "C" int uz_kl_bwd(const float* mu0, const float* s0, const float* mu1, co
   uz::launch(kl_bwd_kernel, cap_blocks((n + 255) / 256, 4), 256, 0, ST(stream), mu0, s0, mu1, s1, n, weight / batch, upstream,
                                                                        dmu0, ds0, dmu1, ds1);
   UZ_CHECK_LAUNCH("uz_kl_bwd");
+  return UZ_OK;
+}
+
+namespace {
+int kl_fill(KlLevels* p, const float* const* mu0, const float* const* s0, const float* const* mu1, const float* const* s1,
+            const long long* numel, const float* level_weight, int L, int batch) {
+  UZ_CHECK_ARG(mu0 && s0 && mu1 && s1 && numel && level_weight && L >= 1 && L <= kMaxLvl && batch > 0,
+               "uz_kl_hierarchy: bad arguments (L = %d, at most %d levels)", L, kMaxLvl);
+  *p = KlLevels{};
+  p->L = L;
+  for (int l = 0; l < L; ++l) {
+    UZ_CHECK_ARG(mu0[l] && s0[l] && mu1[l] && s1[l] && numel[l] > 0, "uz_kl_hierarchy: null pointer at level %d", l);
+    p->mu0[l] = mu0[l]; p->s0[l] = s0[l]; p->mu1[l] = mu1[l]; p->s1[l] = s1[l];
+    p->n[l] = numel[l];
+    p->scale[l] = level_weight[l] / batch;
+  }
+  return UZ_OK;
+}
+}  // namespace
+
+extern "C" int uz_kl_hierarchy_num_blocks(long long max_numel) {
+  return cap_blocks((max_numel + 4095) / 4096, 1);
+}
+
+// levels_out[l] = level_weight[l] * KL_l (batch mean, sigma1*sigma0 quirk of the reference), total_out[0] =
+// sum_{l = L-1..0} total_weight * levels_out[l]; partial: L * uz_kl_hierarchy_num_blocks(max numel) doubles.
+extern "C" int uz_kl_hierarchy_fwd(const float* const* mu0, const float* const* s0, const float* const* mu1,
+                                   const float* const* s1, const long long* numel, const float* level_weight, int L,
+                                   int batch, float total_weight, double* partial, float* levels_out, float* total_out,
+                                   void* stream) {
+  UZ_CHECK_ARG(partial && levels_out && total_out, "uz_kl_hierarchy_fwd: null pointer");
+  KlLevels p;
+  int rc = kl_fill(&p, mu0, s0, mu1, s1, numel, level_weight, L, batch);
+  if (rc) return rc;
+  long long mx = 0;
+  for (int l = 0; l < L; ++l) mx = numel[l] > mx ? numel[l] : mx;
+  const int bpl = uz_kl_hierarchy_num_blocks(mx);
+  uz::launch(kl_fwd_batched_kernel, dim3(bpl, L, 1), 1024, 0, ST(stream), p, bpl, partial);
+  uz::launch(kl_finish_batched_kernel, 1, 32 * kMaxLvl, 0, ST(stream), p, static_cast<const double*>(partial), bpl,
+             total_weight, levels_out, total_out);
+  UZ_CHECK_LAUNCH("uz_kl_hierarchy_fwd");
+  return UZ_OK;
+}
+
+// grads: 4 * L pointers, [l*4 + 0..3] = d mu0, d s0, d mu1, d s1 of level l; upstream: d loss / d total_out (device scalar)
+extern "C" int uz_kl_hierarchy_bwd(const float* const* mu0, const float* const* s0, const float* const* mu1,
+                                   const float* const* s1, const long long* numel, const float* level_weight, int L,
+                                   int batch, float total_weight, const float* upstream, float* const* grads,
+                                   void* stream) {
+  UZ_CHECK_ARG(upstream && grads, "uz_kl_hierarchy_bwd: null pointer");
+  KlLevels p;
+  int rc = kl_fill(&p, mu0, s0, mu1, s1, numel, level_weight, L, batch);
+  if (rc) return rc;
+  long long mx = 0;
+  for (int l = 0; l < L; ++l) {
+    for (int k = 0; k < 4; ++k) {
+      UZ_CHECK_ARG(grads[l * 4 + k], "uz_kl_hierarchy_bwd: null gradient pointer");
+      p.g[l][k] = grads[l * 4 + k];
+    }
+    mx = numel[l] > mx ? numel[l] : mx;
+  }
+  uz::launch(kl_bwd_batched_kernel, dim3(cap_blocks((mx + 255) / 256, 2), L, 1), 256, 0, ST(stream), p, total_weight,
+             upstream);
+  UZ_CHECK_LAUNCH("uz_kl_hierarchy_bwd");
   return UZ_OK;
 }
 
@@ -704,8 +891,7 @@ int slayer_bwd_impl(const float* dout, const void* feat, int ld, int C, const fl
              static_cast<const __nv_bfloat16*>(feat), ld, C, w, ncls, static_cast<int>(rows), d, h, wd, factor, fz,
              static_cast<__nv_bfloat16*>(dfeat), ldd, wpartial, bpartial);
   UZ_CHECK_LAUNCH("uz_slayer_bwd");
-  uz::launch(column_reduce_kernel, (ncls * C + 127) / 128, 128, 0, ST(stream), wpartial, blocks, ncls * C, dw, 1.f);
-  uz::launch(column_reduce_kernel, 1, 32, 0, ST(stream), bpartial, blocks, ncls, db, 1.f);
+  launch_column_reduce(ST(stream), wpartial, ncls * C, dw, bpartial, ncls, db, blocks, 1.f);
   UZ_CHECK_LAUNCH("uz_slayer_bwd(reduce)");
   return UZ_OK;
 }
@@ -730,7 +916,7 @@ extern "C" int uz_residual_ce(const float* const* s, float* const* ds, const flo
   const int blocks = uz_residual_ce_num_blocks(B, hw);
   uz::launch(residual_ce_kernel, blocks, 256, 0, ST(stream), p, L, ncls, target, B, hw, 1.f / B, upstream, partial);
   UZ_CHECK_LAUNCH("uz_residual_ce");
-  uz::launch(column_reduce_kernel, 1, 32, 0, ST(stream), partial, blocks, L, ce_levels, 1.f / B);
+  launch_column_reduce(ST(stream), partial, L, ce_levels, nullptr, 0, nullptr, blocks, 1.f / B);
   UZ_CHECK_LAUNCH("uz_residual_ce(reduce)");
   return UZ_OK;
 }

@@ -493,6 +493,53 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// The same reduction for MANY layers in one launch (uz_wgrad_reduce_batched): a work unit is one output channel o and a
+// block of 64 input channels; the block's 64 lanes x 4 tap groups read the [split][tap][o][i] partials (256-byte rows,
+// fully coalesced), sum the splits in a fixed order, transpose through shared memory and write the unit's contiguous
+// run dw[o][i0 .. i0+63][0 .. taps-1] coalesced (the per-layer kernel above writes every float with a stride of `taps`).
+// The descriptor rows travel as a kernel PARAMETER (<= 64 rows = 3 KB): a captured CUDA graph keeps them by value, no
+// device table to upload or keep alive.
+struct ReduceBatch {
+  UzWgradReduceDesc d[UZ_WGRAD_REDUCE_MAX_ROWS];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const __grid_constant__ ReduceBatch b) {
+  uz::pdl_prologue();
+  __shared__ float tile[64 * 27];
+  int lo = 0, hi = b.n - 1;                      // last descriptor whose first unit is <= blockIdx.x (block-uniform)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (b.d[mid].unit_begin <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+  }
+  const UzWgradReduceDesc d = b.d[lo];
+  const int unit = blockIdx.x - d.unit_begin;
+  const int chunks = (d.Cin + 63) / 64;
+  const int o = unit / chunks, i0 = (unit - o * chunks) * 64;
+  const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int i = i0 + lane;
+  const size_t slab = static_cast<size_t>(d.CoutP) * d.CinP;
+  const size_t split_stride = static_cast<size_t>(d.taps) * slab;
+  if (i < d.Cin) {
+    for (int t = grp; t < d.taps; t += 4) {
+      const float* src = d.partial + static_cast<size_t>(t) * slab + static_cast<size_t>(o) * d.CinP + i;
+      float acc = 0.f;
+      int s = 0;
+      for (; s + 4 <= d.splits; s += 4) {        // four loads in flight, summed in split order
+        const float a0 = src[static_cast<size_t>(s) * split_stride], a1 = src[static_cast<size_t>(s + 1) * split_stride];
+        const float a2 = src[static_cast<size_t>(s + 2) * split_stride], a3 = src[static_cast<size_t>(s + 3) * split_stride];
+        acc = (((acc + a0) + a1) + a2) + a3;
+      }
+      for (; s < d.splits; ++s) acc += src[static_cast<size_t>(s) * split_stride];
+      tile[lane * d.taps + t] = acc;
+    }
+  }
+  __syncthreads();
+  const int ni = d.Cin - i0 < 64 ? d.Cin - i0 : 64;
+  float* dst = d.dw + (static_cast<size_t>(o) * d.Cin + i0) * d.taps;
+  for (int e = threadIdx.x; e < ni * d.taps; e += 256) dst[e] = tile[e];
+}
+
 inline int reduce_groups(int splits) { return splits >= 32 ? 8 : (splits >= 16 ? 4 : (splits >= 8 ? 2 : 1)); }
 
 int pow2_div_le(int v, int cap) {
@@ -575,8 +622,46 @@ extern "C" long long uz_wgrad_workspace_floats(int N, int H, int W, int Cin, int
 
 namespace {
 int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout, int taps,
-               int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream);
+               int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream, int* splits_out = nullptr);
 }
+
+// The tensor-core part alone: writes the split-K partial slabs [splits][taps][Cout][Cin] fp32 into `workspace`
+// (uz_wgrad_workspace_floats) and reports the number of splits.  The slabs of many layers are then reduced, transposed to
+// OIHW and written to their gradient tensors by ONE uz_wgrad_reduce_batched launch.  D == 0: images, D > 0: volumes (27 taps).
+extern "C" int uz_conv_wgrad_partial(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W,
+                                     int Cin, int Cout, int taps, float* workspace, int* splits, void* stream) {
+  UZ_CHECK_ARG(splits, "uz_conv_wgrad_partial: null pointer");
+  UZ_CHECK_ARG(D == 0 ? (taps == 9 || taps == 1) : taps == 27, "uz_conv_wgrad_partial: taps %d with D %d", taps, D);
+  return wgrad_impl(x, ldx, dy, lddy, N, D, H, W, Cin, Cout, taps, Cin, Cout, workspace, nullptr, stream, splits);
+}
+
+extern "C" int uz_wgrad_reduce_units(int Cout_logical, int Cin_logical) {
+  return Cout_logical * ((Cin_logical + 63) / 64);
+}
+
+// descs: n <= UZ_WGRAD_REDUCE_MAX_ROWS rows in HOST memory (copied into the launch parameters); unit_begin is filled in
+// here.  Deterministic (fixed split order).
+extern "C" int uz_wgrad_reduce_batched(const UzWgradReduceDesc* descs, int n, void* stream) {
+  UZ_CHECK_ARG(descs && n > 0 && n <= UZ_WGRAD_REDUCE_MAX_ROWS, "uz_wgrad_reduce_batched: 1..%d rows (got %d)",
+               UZ_WGRAD_REDUCE_MAX_ROWS, n);
+  if UZ_KNOB(4096) return UZ_OK;
+  ReduceBatch b;
+  b.n = n;
+  int units = 0;
+  for (int k = 0; k < n; ++k) {
+    b.d[k] = descs[k];
+    UZ_CHECK_ARG(b.d[k].partial && b.d[k].dw && b.d[k].splits > 0 && b.d[k].taps > 0 && b.d[k].taps <= 27 &&
+                     b.d[k].Cout > 0 && b.d[k].Cin > 0 && b.d[k].Cout <= b.d[k].CoutP && b.d[k].Cin <= b.d[k].CinP,
+                 "uz_wgrad_reduce_batched: bad row %d", k);
+    b.d[k].unit_begin = units;
+    units += uz_wgrad_reduce_units(b.d[k].Cout, b.d[k].Cin);
+  }
+  uz::launch(wgrad_reduce_batched_kernel, dim3(units, 1, 1), 256, 0, static_cast<cudaStream_t>(stream), b);
+  UZ_CHECK_LAUNCH("uz_wgrad_reduce_batched");
+  return UZ_OK;
+}
+
+
 
 // x: bf16 NHWC [N,H,W,Cin] (ldx), dy: bf16 NHWC [N,H,W,Cout] (lddy); dw: fp32 [Cout_logical][Cin_logical][taps].
 extern "C" int uz_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, int N, int H, int W, int Cin, int Cout,
@@ -593,9 +678,10 @@ extern "C" int uz_conv3d_wgrad(const void* x, int ldx, const void* dy, int lddy,
 }
 
 namespace {
+// splits_out != nullptr: only the tensor-core kernel runs; the partial slabs stay in `workspace` for uz_wgrad_reduce_batched
 int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout, int taps,
-               int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream) {
-  UZ_CHECK_ARG(x && dy && workspace && dw, "uz_conv_wgrad: null pointer");
+               int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream, int* splits_out) {
+  UZ_CHECK_ARG(x && dy && workspace && (dw || splits_out), "uz_conv_wgrad: null pointer");
   UZ_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0 && Cin > 0 && Cout > 0 && Cin <= 512,
                "uz_conv_wgrad: channels must be multiples of 16, Cin <= 512 (got %d, %d)", Cin, Cout);
   UZ_CHECK_ARG(ldx % 8 == 0 && lddy % 8 == 0 && ldx >= Cin && lddy >= Cout, "uz_conv_wgrad: bad pixel strides");
@@ -638,6 +724,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
     dim3 grid2(pl2.splits, pl2.p.co_blocks * 3 * pl2.p.nz * pl2.p.ci_chunks, 1);
     uz::launch(wgrad_tc2_kernel, grid2, kThreads, pl2.smem, static_cast<cudaStream_t>(stream), tdy2, tx2, pl2.p);
     UZ_CHECK_LAUNCH("uz_conv_wgrad(v2)");
+    if (splits_out) { *splits_out = pl2.splits; return UZ_OK; }
     const size_t total2 = static_cast<size_t>(Cout_logical) * Cin_logical;     // one thread per (o, i) pair
     const int G2 = reduce_groups(pl2.splits);
     int blocks2 = static_cast<int>((total2 + 256 / G2 - 1) / (256 / G2));
@@ -691,6 +778,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
   dim3 grid(pl.splits, pl.p.tap_groups * pl.co_blocks * pl.p.ci_chunks, 1);
   uz::launch(kernel, grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream), tdy, tx, pl.p);
   UZ_CHECK_LAUNCH("uz_conv_wgrad");
+  if (splits_out) { *splits_out = pl.splits; return UZ_OK; }
   const size_t total = static_cast<size_t>(Cout_logical) * Cin_logical;       // one thread per (o, i) pair
   const int G1 = reduce_groups(pl.splits);
   int blocks = static_cast<int>((total + 256 / G1 - 1) / (256 / G1));

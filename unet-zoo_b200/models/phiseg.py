@@ -577,11 +577,16 @@ class PHISeg(nn.Module):
             level_weights = [self.exponential_weight ** i for i in list(range(self.latent_levels))]
         else:
             level_weights = [1] * self.latent_levels
+        # all levels in one fused op: total = sum over ii = L-1 ... 0 of kl_weight * w_ii * KL_ii (the reference's order of
+        # `loss_tot += ...`), per-level values for the loss dictionary
+        flat = []
+        for ii in range(self.latent_levels):
+            flat += [self.posterior_mu[ii], self.posterior_sigma[ii], self.prior_mu[ii], self.prior_sigma[ii]]
+        total, levels = ops.KLHierarchy.apply(tuple(float(w) for w in level_weights),
+                                              float(self.kl_divergence_loss_weight), *flat)
         for ii in reversed(range(self.latent_levels)):
-            self.loss_dict['KL_divergence_loss_lvl%d' % ii] = ops.KLLevel.apply(
-                self.posterior_mu[ii], self.posterior_sigma[ii], self.prior_mu[ii], self.prior_sigma[ii],
-                float(level_weights[ii]))
-            self._loss_add(self.kl_divergence_loss_weight * self.loss_dict['KL_divergence_loss_lvl%d' % ii])
+            self.loss_dict['KL_divergence_loss_lvl%d' % ii] = levels[ii]
+        self._loss_add(total)
         return self.loss_tot
 
     def _loss_add(self, term):

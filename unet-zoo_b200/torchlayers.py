@@ -214,8 +214,9 @@ class ReversibleBlock(nn.Module):
         wshape = conv.weight.shape
         cout, cin = wshape[0], wshape[1]
         taps = kern._spatial_numel(wshape[2:])
-        dw = ops._run_on_aux(lambda: kern.conv_wgrad(xin, dy, taps, cin, cout, out=ops._bucket_view(conv.weight)),
-                             (xin, dy)).view(wshape)
+        defer = ops._can_defer(conv.weight)
+        dw = ops._run_on_aux(lambda: kern.conv_wgrad(xin, dy, taps, cin, cout, out=ops._bucket_view(conv.weight),
+                                                     defer=defer), (xin, dy)).view(wshape)
         grads[id(conv.weight)] = dw
         grads[id(conv.bias)] = kern.zero_arena.get(cout, dy.device)      # exactly zero in front of BatchNorm
         grads[id(bn.weight)] = dgamma

@@ -160,6 +160,23 @@ int uz_adam_chunk_elems(void);
 int uz_adam_step_batched(const void* descs_device, int ntensors, const int* chunk_table_device, int nchunks, double lr,
                          double beta1, double beta2, double eps, double weight_decay, void* stream);
 
+/* Adam and the bf16 weight packing in ONE pass for the conv weights: the update of a 32 x 32 x 9-tap tile stays in shared
+ * memory and both packed copies (uz_pack_conv_weight layouts) are written from there -- the separate packing pass at the
+ * head of the next step (100 MB read + 100 MB written, alone on the GPU) disappears.  packs_device: UzAdamPackDesc rows
+ * (tensor = row of descs_device); item_table_device: int [nitems][2] = (pack row, tile), uz_adam_pack_items tiles per
+ * layer.  Tensors in the chunk table get the plain update; the step counters of all ntensors rows are incremented. */
+typedef struct UzAdamPackDesc {
+  void* w_fwd;        /* bf16 [taps][CoutP][CinP] */
+  void* w_dgrad;      /* bf16 [taps][CinP][CoutP] or NULL */
+  int tensor;         /* row of the UzAdamDesc table */
+  int Cout, Cin, taps, CoutP, CinP;
+} UzAdamPackDesc;
+int uz_adam_pack_items(int CoutP, int CinP, int taps);
+int uz_adam_pack_step(const void* descs_device, int ntensors, const int* chunk_table_device, int nchunks,
+                      const void* packs_device, const int* item_table_device, int nitems, double lr, double beta1,
+                      double beta2, double eps, double weight_decay, void* stream);
+
+
 /* Training-mode BatchNorm statistics: reduce the conv's per-tile partials, emit scale = gamma*invstd and
  * shift = beta - mean*scale, save mean / invstd, update running stats (momentum, unbiased variance).
  * Replaces nn.BatchNorm2d(eps=1e-3, momentum=0.01) statistics, torchlayers.py:20. */

@@ -486,3 +486,38 @@ def test_kl_hierarchy_matches_per_level_kernels():
         g_ref = k.kl_bwd(*levels[l], lw[l], torch.full((1,), 0.75 * 0.5, device=DEV))
         for a, b in zip(grads[4 * l:4 * l + 4], g_ref):
             torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-30)
+
+
+def test_fused_adam_with_weight_packing_matches_separate_passes():
+    """uz_adam_pack_step: Adam on the conv weights with the bf16 forward / dgrad copies rewritten in the same pass, against
+    the plain fused Adam followed by the packing kernel -- parameters, moments and packed copies bit for bit -- for 3x3,
+    1x1 and 3x3x3 layers with odd channel counts, next to unpacked tensors in the same optimizer."""
+    from b200.optim import FusedAdam
+    k = kern()
+    g = torch.Generator(device='cpu').manual_seed(9)
+    shapes = [(192, 192, 3, 3), (32, 1, 3, 3), (48, 33, 3, 3), (64, 16, 1, 1), (32, 16, 3, 3, 3), (7,), (4097,)]
+    a_p = [torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for s in shapes]
+    b_p = [torch.nn.Parameter(p.detach().clone()) for p in a_p]
+    pk_a = k.WeightPacker([p for p in a_p if p.dim() >= 4])
+    pk_b = k.WeightPacker([p for p in b_p if p.dim() >= 4])
+    opt_a = FusedAdam(a_p, lr=1e-3, weight_decay=1e-5)
+    opt_a.attach_packer(pk_a)
+    opt_b = FusedAdam(b_p, lr=1e-3, weight_decay=1e-5)
+    assert pk_a.external and not pk_b.external
+    for it in range(3):
+        grads = [torch.randn(*s, generator=g).to(DEV) * (0.1 + it) for s in shapes]
+        for p, q, gr in zip(a_p, b_p, grads):
+            p.grad, q.grad = gr.clone(), gr.clone()
+        opt_a.step()                     # update + re-pack
+        pk_a.refresh()                   # no-op: the optimizer keeps the copies current
+        opt_b.step()
+        pk_b.refresh()                   # separate packing pass
+        torch.cuda.synchronize()
+        for p, q in zip(a_p, b_p):
+            assert torch.equal(p, q)
+            assert torch.equal(opt_a.state[p]['exp_avg'], opt_b.state[q]['exp_avg'])
+            assert torch.equal(opt_a.state[p]['exp_avg_sq'], opt_b.state[q]['exp_avg_sq'])
+            assert torch.equal(opt_a.state[p]['step'], opt_b.state[q]['step'])
+            if p.dim() >= 4:
+                (fa, da), (fb, db) = pk_a.lookup(p), pk_b.lookup(q)
+                assert torch.equal(fa, fb) and torch.equal(da, db), tuple(p.shape)

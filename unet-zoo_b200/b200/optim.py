@@ -16,6 +16,19 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}            # group index -> [eager, captured] descriptor / chunk tables (pinned host + device)
+        self.packer = None           # kern.WeightPacker whose bf16 copies this optimizer keeps current (attach_packer)
+
+    def attach_packer(self, packer):
+        """From now on the conv weights known to ``packer`` are updated by the fused Adam + packing kernel
+        (uz_adam_pack_step): their bf16 tensor-core copies are rewritten from the new values in the same pass, and the
+        per-forward packing launch becomes a no-op (``packer.external``).  The copies are brought up to date once here;
+        whoever changes parameters behind the optimizer's back afterwards must call ``packer.refresh(force=True)``."""
+        self.packer = packer
+        if packer is not None:
+            packer.refresh(force=True)
+            packer.external = True
+        self._tables = {}            # re-created with tile tables on the next (eager) step
+        self.__dict__['_state_gen'] = self.__dict__.get('_state_gen', 0) + 1
 
     def load_state_dict(self, state_dict):
         """torch's loader installs NEW tensors in ``self.state``; the descriptor tables (and a captured CUDA graph that
@@ -62,6 +75,9 @@ class FusedAdam(torch.optim.Optimizer):
             if tab.get('dirty'):
                 tab['descs'].copy_(tab['host_d'], non_blocking=True)
                 tab['chunks'].copy_(tab['host_c'], non_blocking=True)
+                if tab['ni']:
+                    tab['packs'].copy_(tab['host_p'], non_blocking=True)
+                    tab['items'].copy_(tab['host_i'], non_blocking=True)
                 tab['dirty'] = False
         torch.cuda.current_stream().synchronize()
 
@@ -128,13 +144,24 @@ class FusedAdam(torch.optim.Optimizer):
         bufs = self._tables.get(gi)
         if bufs is None:
             nparam = nparam_max
+            nitem_max = 0
+            if self.packer is not None:
+                for q in group['params']:
+                    hit = self.packer.rows.get(q.data_ptr())
+                    if hit is not None:
+                        f = struct.unpack('<QQQiiiiii', hit[0])
+                        nitem_max += _lib.raw('uz_adam_pack_items')(f[6], f[7], f[5])
             bufs = []
             for _ in range(2):
-                bufs.append({'key': None, 'n': 0, 'nt': 0,
+                bufs.append({'key': None, 'n': 0, 'nt': 0, 'ni': 0,
                              'host_d': torch.empty(nparam * 48, dtype=torch.uint8).pin_memory(),
                              'host_c': torch.empty(nchunk_max * 2, dtype=torch.int32).pin_memory(),
+                             'host_p': torch.empty(nparam * 40, dtype=torch.uint8).pin_memory(),
                              'descs': torch.empty(nparam * 48, dtype=torch.uint8, device=dev),
-                             'chunks': torch.empty(nchunk_max * 2, dtype=torch.int32, device=dev)})
+                             'chunks': torch.empty(nchunk_max * 2, dtype=torch.int32, device=dev),
+                             'packs': torch.empty(nparam * 40, dtype=torch.uint8, device=dev),
+                             'host_i': torch.empty(max(2 * nitem_max, 2), dtype=torch.int32).pin_memory(),
+                             'items': torch.empty(max(2 * nitem_max, 2), dtype=torch.int32, device=dev)})
             self._tables[gi] = bufs
         tab = bufs[1 if capturing else 0]
         if tab['key'] != key:
@@ -142,13 +169,27 @@ class FusedAdam(torch.optim.Optimizer):
                 # the previous step's non-blocking upload reads the pinned buffers that are rewritten below
                 tab['uploaded'].synchronize()
             raw = b''.join(struct.pack('<QQQQQq', *r) for r in rows)
-            table = []
+            table, prow, items = [], [], []
+            pk_rows = self.packer.rows if self.packer is not None else {}
             for ti, r in enumerate(rows):
+                hit = pk_rows.get(r[0])
+                if hit is not None:
+                    # conv weight with packed copies: fused update + re-pack, one block per 32 x 32 x 9-tap tile
+                    _, wf, wd, cout, cin, taps, coutp, cinp, _ = struct.unpack('<QQQiiiiii', hit[0])
+                    for it in range(_lib.raw('uz_adam_pack_items')(coutp, cinp, taps)):
+                        items += [len(prow), it]
+                    prow.append(struct.pack('<QQiiiiii', wf, wd, ti, cout, cin, taps, coutp, cinp))
+                    continue
                 for c in range((r[5] + chunk - 1) // chunk):
                     table += [ti, c]
             tab['host_d'][:len(raw)] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
-            tab['host_c'][:len(table)] = torch.tensor(table, dtype=torch.int32)
-            tab['key'], tab['n'], tab['nt'] = key, len(table) // 2, len(rows)
+            if table:
+                tab['host_c'][:len(table)] = torch.tensor(table, dtype=torch.int32)
+            if prow:
+                praw = b''.join(prow)
+                tab['host_p'][:len(praw)] = torch.frombuffer(bytearray(praw), dtype=torch.uint8)
+                tab['host_i'][:len(items)] = torch.tensor(items, dtype=torch.int32)
+            tab['key'], tab['n'], tab['nt'], tab['ni'] = key, len(table) // 2, len(rows), len(items) // 2
             tab['stale'] = True
         descs, chunks, nchunks = tab['descs'], tab['chunks'], tab['n']
         if capturing:
@@ -158,6 +199,9 @@ class FusedAdam(torch.optim.Optimizer):
         elif tab.get('stale', True):
             descs.copy_(tab['host_d'], non_blocking=True)
             chunks.copy_(tab['host_c'], non_blocking=True)
+            if tab['ni']:
+                tab['packs'].copy_(tab['host_p'], non_blocking=True)
+                tab['items'].copy_(tab['host_i'], non_blocking=True)
             if tab.get('uploaded') is None:
                 tab['uploaded'] = torch.cuda.Event()
             tab['uploaded'].record()
@@ -166,6 +210,11 @@ class FusedAdam(torch.optim.Optimizer):
         elif tab.get('stream') != torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()):
             torch.cuda.current_stream().wait_event(tab['uploaded'])      # uploaded on another stream
         b1, b2 = group['betas']
+        if tab['ni']:
+            _lib.call('uz_adam_pack_step', descs.data_ptr(), tab['nt'], chunks.data_ptr(), nchunks, tab['packs'].data_ptr(),
+                      tab['items'].data_ptr(), tab['ni'], float(group['lr']), float(b1), float(b2), float(group['eps']),
+                      float(group['weight_decay']), torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+            return
         _lib.call('uz_adam_step_batched', descs.data_ptr(), tab['nt'], chunks.data_ptr(), nchunks,
                   float(group['lr']), float(b1), float(b2), float(group['eps']), float(group['weight_decay']),
                   torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))

@@ -44,6 +44,13 @@ class TrainStep:
             overlap_optimizer = os.environ.get('UNETZOO_OVERLAP_OPT', '0') == '1'
         from .optim import FusedAdam
         self.packer = None
+        if isinstance(optimizer, FusedAdam) and hasattr(net, '_packer') and not overlap_optimizer and \
+                os.environ.get('UNETZOO_ADAM_PACK', '1') != '0':
+            # the optimizer re-packs the bf16 tensor-core weight copies while it updates them (uz_adam_pack_step): no
+            # packing pass at the head of the step
+            self.packer = net._packer()
+            optimizer.attach_packer(self.packer)
+            net.register_load_state_dict_post_hook(lambda module, incompatible: self.refresh_weights())
         if overlap_optimizer and isinstance(optimizer, FusedAdam) and len(optimizer.param_groups) == 1:
             self.packer = net._packer() if hasattr(net, '_packer') else None
             if self.dp is None:

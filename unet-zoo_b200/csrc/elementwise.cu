@@ -83,6 +83,29 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
   }
 }
 
+// second phase of the packing kernels: tile[32 o][32 i x tg taps] (fp32, new weights) -> both packed bf16 copies, two
+// channels per thread (4-byte stores; CoutP / CinP are multiples of 16 and tiles start at multiples of 32, so a pair never
+// straddles the padded extent)
+__device__ __forceinline__ void pack_tile_stores(const float (*tile)[32 * 9 + 1], int tg, int grp, int taps, int o0, int i0,
+                                                 int CoutP, int CinP, __nv_bfloat16* wp, __nv_bfloat16* wd) {
+  for (int e = threadIdx.x; e < tg * 512; e += kEwThreads) {
+    const int tl = e >> 9, a = (e >> 4) & 31, b = (e & 15) * 2;
+    const int sl = tg == 9 ? (tl % 3) * 3 + tl / 3 : 0;            // packed tap tl of the group <- source tap sl
+    {   // forward copy: a = o, b = i (fastest)
+      const int o = o0 + a, i = i0 + b;
+      if (o < CoutP && i < CinP)
+        *reinterpret_cast<uint32_t*>(wp + (static_cast<size_t>(grp * tg + tl) * CoutP + o) * CinP + i) =
+            uz::pack_bf16x2(tile[a][b * tg + sl], tile[a][(b + 1) * tg + sl]);
+    }
+    if (wd) {   // dgrad copy: wd[taps-1-u][i][o] = w[o][i][src(u)], u = grp*tg + tl; a = i, b = o (fastest)
+      const int i = i0 + a, o = o0 + b;
+      if (o < CoutP && i < CinP)
+        *reinterpret_cast<uint32_t*>(wd + (static_cast<size_t>(taps - 1 - (grp * tg + tl)) * CinP + i) * CoutP + o) =
+            uz::pack_bf16x2(tile[b][a * tg + sl], tile[b + 1][a * tg + sl]);
+    }
+  }
+}
+
 // all conv layers of a model in ONE launch: blockIdx.y selects the layer descriptor (device table of UzPackDesc).
 // A work item is a 32 (o) x 32 (i) x 9-tap tile staged through shared memory, so that the fp32 reads (contiguous runs
 // of the OIHW source), the forward stores (i fastest) and the transposed dgrad stores (o fastest) are all coalesced.
@@ -110,21 +133,7 @@ __global__ void __launch_bounds__(kEwThreads) pack_weight_batched_kernel(const U
       tile[oo][rem] = (o < d.Cout && i < d.Cin) ? w[(static_cast<size_t>(o) * d.Cin + i) * d.taps + grp * tg + sl] : 0.f;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < tg * 1024; e += kEwThreads) {
-      const int tl = e >> 10, a = (e >> 5) & 31, b = e & 31;
-      const int sl = tg == 9 ? (tl % 3) * 3 + tl / 3 : 0;            // packed tap tl of the group <- source tap sl
-      {   // forward copy: a = o, b = i (fastest)
-        const int o = o0 + a, i = i0 + b;
-        if (o < d.CoutP && i < d.CinP)
-          wp[(static_cast<size_t>(grp * tg + tl) * d.CoutP + o) * d.CinP + i] = uz::f2act(tile[a][b * tg + sl]);
-      }
-      if (wd) {   // dgrad copy: wd[taps-1-u][i][o] = w[o][i][src(u)], u = grp*tg + tl; a = i, b = o (fastest)
-        const int i = i0 + a, o = o0 + b;
-        if (o < d.CoutP && i < d.CinP)
-          wd[(static_cast<size_t>(d.taps - 1 - (grp * tg + tl)) * d.CinP + i) * d.CoutP + o] =
-              uz::f2act(tile[b][a * tg + sl]);
-      }
-    }
+    pack_tile_stores(tile, tg, grp, d.taps, o0, i0, d.CoutP, d.CinP, wp, wd);
     __syncthreads();
   }
 }
@@ -193,6 +202,121 @@ __global__ void __launch_bounds__(256) adam_batched_kernel(const UzAdamDesc* __r
       p[i] = pp; m[i] = mm; v[i] = vv;
     }
   }
+}
+
+// ---------------------------------------------------------------- Adam + weight packing in one pass (conv weights)
+// The tensor-core kernels read bf16 copies of the conv weights in two tap-major layouts (pack_weight_batched_kernel above).
+// Re-packing after every optimizer step was a pass of its own at the head of the next step: 100 MB fp32 read again,
+// 100 MB bf16 written, alone on the GPU.  Here the Adam update of a 32 (o) x 32 (i) x 9-tap tile keeps the new fp32
+// weights in shared memory and writes both packed copies from there: the parameters are read once per step.
+// item_table: int [nitems][2] = (row of the pack table, tile index inside the layer).
+__global__ void __launch_bounds__(kEwThreads) adam_pack_kernel(const UzAdamDesc* __restrict__ descs,
+                                                               const UzAdamPackDesc* __restrict__ packs,
+                                                               const int* __restrict__ item_table, double lr_d,
+                                                               double beta1_d, double beta2_d, float eps,
+                                                               float weight_decay) {
+  uz::pdl_prologue();
+  __shared__ float tile[32][32 * 9 + 1];
+  const UzAdamPackDesc pk = packs[item_table[2 * blockIdx.x]];
+  const int item = item_table[2 * blockIdx.x + 1];
+  const UzAdamDesc d = descs[pk.tensor];
+  float* __restrict__ p = static_cast<float*>(d.p);
+  const float* __restrict__ g = static_cast<const float*>(d.g);
+  float* __restrict__ m = static_cast<float*>(d.m);
+  float* __restrict__ v = static_cast<float*>(d.v);
+  __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(pk.w_fwd);
+  __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(pk.w_dgrad);
+  const double t = static_cast<double>(d.step[0]);
+  const double bc1 = 1.0 - pow(beta1_d, t);
+  const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(beta2_d, t)));
+  const float step_size = static_cast<float>(lr_d / bc1);
+  const float beta2 = static_cast<float>(beta2_d);
+  const float omb1 = static_cast<float>(1.0 - beta1_d), omb2 = static_cast<float>(1.0 - beta2_d);
+  auto update = [&](float& pp, float gg, float& mm, float& vv) {       // identical to adam_batched_kernel
+    gg = fmaf(weight_decay, pp, gg);
+    mm = fmaf(omb1, gg - mm, mm);
+    vv = fmaf(beta2, vv, omb2 * gg * gg);
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp -= step_size * mm / denom;
+  };
+  const int tg = pk.taps >= 9 ? 9 : 1;
+  const int groups = pk.taps / tg;
+  const int ti = (pk.CinP + 31) / 32;
+  const int grp = item % groups;
+  const int r = item / groups;
+  const int i0 = (r % ti) * 32, o0 = (r / ti) * 32;
+  const int row = 32 * tg;
+  const bool full = o0 + 32 <= pk.Cout && i0 + 32 <= pk.Cin && tg == 9 && pk.taps == 9 && (pk.Cin & 3) == 0 &&
+                    (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 15) == 0);
+  if (full) {
+    // a row of the tile = 288 contiguous, 16-byte aligned floats of the OIHW tensor: 72 float4 per row, 2304 per tile,
+    // 9 per thread in three batches of 3 x 4 independent 16-byte loads
+    constexpr int U = 3;
+    for (int e0 = threadIdx.x; e0 < 32 * 72; e0 += kEwThreads * U) {
+      size_t idx[U];
+      int oo[U], c4[U];
+      float4 pp[U], gg[U], mm[U], vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * kEwThreads;
+        oo[u] = e / 72;
+        c4[u] = e - oo[u] * 72;
+        idx[u] = (static_cast<size_t>(o0 + oo[u]) * pk.Cin + i0) * 9 + c4[u] * 4;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pp[u] = *reinterpret_cast<const float4*>(p + idx[u]);
+        gg[u] = *reinterpret_cast<const float4*>(g + idx[u]);
+        mm[u] = *reinterpret_cast<const float4*>(m + idx[u]);
+        vv[u] = *reinterpret_cast<const float4*>(v + idx[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        update(pp[u].x, gg[u].x, mm[u].x, vv[u].x);
+        update(pp[u].y, gg[u].y, mm[u].y, vv[u].y);
+        update(pp[u].z, gg[u].z, mm[u].z, vv[u].z);
+        update(pp[u].w, gg[u].w, mm[u].w, vv[u].w);
+        *reinterpret_cast<float4*>(p + idx[u]) = pp[u];
+        *reinterpret_cast<float4*>(m + idx[u]) = mm[u];
+        *reinterpret_cast<float4*>(v + idx[u]) = vv[u];
+        float* trow = &tile[oo[u]][c4[u] * 4];
+        trow[0] = pp[u].x; trow[1] = pp[u].y; trow[2] = pp[u].z; trow[3] = pp[u].w;
+      }
+    }
+  } else {
+    constexpr int U = 4;
+    for (int e0 = threadIdx.x; e0 < 32 * row; e0 += kEwThreads * U) {
+      size_t idx[U];
+      bool ok[U];
+      int oo[U], rem[U];
+      float pp[U], gg[U], mm[U], vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * kEwThreads;
+        oo[u] = e / row;
+        rem[u] = e - oo[u] * row;
+        const int ii = rem[u] / tg, sl = rem[u] - ii * tg;
+        const int o = o0 + oo[u], i = i0 + ii;
+        ok[u] = e < 32 * row && o < pk.Cout && i < pk.Cin;
+        idx[u] = (static_cast<size_t>(o) * pk.Cin + i) * pk.taps + grp * tg + sl;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (ok[u]) { pp[u] = p[idx[u]]; gg[u] = g[idx[u]]; mm[u] = m[idx[u]]; vv[u] = v[idx[u]]; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (ok[u]) {
+          update(pp[u], gg[u], mm[u], vv[u]);
+          p[idx[u]] = pp[u]; m[idx[u]] = mm[u]; v[idx[u]] = vv[u];
+        }
+        if (e0 + u * kEwThreads < 32 * row) tile[oo[u]][rem[u]] = ok[u] ? pp[u] : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  pack_tile_stores(tile, tg, grp, pk.taps, o0, i0, pk.CoutP, pk.CinP, wp, wd);
 }
 
 // ---------------------------------------------------------------- BatchNorm statistics
@@ -1051,6 +1175,36 @@ extern "C" int uz_adam_step_batched(const void* descs_device, int ntensors, cons
   uz::launch(adam_batched_kernel, nchunks, 256, 0, ST(stream), static_cast<const UzAdamDesc*>(descs_device),
              chunk_table_device, lr, beta1, beta2, static_cast<float>(eps), static_cast<float>(weight_decay));
   UZ_CHECK_LAUNCH("uz_adam_step_batched");
+  return UZ_OK;
+}
+
+extern "C" int uz_adam_pack_items(int CoutP, int CinP, int taps) {
+  return ((CoutP + 31) / 32) * ((CinP + 31) / 32) * (taps >= 9 ? taps / 9 : 1);
+}
+
+// Adam for all tensors of `descs_device`: the step counters of ALL of them are incremented, tensors covered by the chunk
+// table get the plain update (uz_adam_step_batched's kernel), conv weights listed in `packs_device` get the update AND
+// their bf16 forward / dgrad copies re-packed from the new values in the same pass.
+extern "C" int uz_adam_pack_step(const void* descs_device, int ntensors, const int* chunk_table_device, int nchunks,
+                                 const void* packs_device, const int* item_table_device, int nitems, double lr,
+                                 double beta1, double beta2, double eps, double weight_decay, void* stream) {
+  UZ_CHECK_ARG(descs_device && ntensors > 0 && nchunks >= 0 && nitems >= 0, "uz_adam_pack_step: bad arguments");
+  UZ_CHECK_ARG((nchunks == 0 || chunk_table_device) && (nitems == 0 || (packs_device && item_table_device)),
+               "uz_adam_pack_step: null table");
+  uz::launch(adam_count_kernel, (ntensors + 255) / 256, 256, 0, ST(stream), static_cast<const UzAdamDesc*>(descs_device),
+             ntensors);
+  UZ_CHECK_LAUNCH("uz_adam_pack_step(count)");
+  if (nchunks > 0) {
+    uz::launch(adam_batched_kernel, nchunks, 256, 0, ST(stream), static_cast<const UzAdamDesc*>(descs_device),
+               chunk_table_device, lr, beta1, beta2, static_cast<float>(eps), static_cast<float>(weight_decay));
+    UZ_CHECK_LAUNCH("uz_adam_pack_step(adam)");
+  }
+  if (nitems > 0) {
+    uz::launch(adam_pack_kernel, nitems, kEwThreads, 0, ST(stream), static_cast<const UzAdamDesc*>(descs_device),
+               static_cast<const UzAdamPackDesc*>(packs_device), item_table_device, lr, beta1, beta2,
+               static_cast<float>(eps), static_cast<float>(weight_decay));
+    UZ_CHECK_LAUNCH("uz_adam_pack_step(adam+pack)");
+  }
   return UZ_OK;
 }
 

@@ -569,41 +569,56 @@ struct LevelPtrs {
 };
 // For level l (processed L-1 .. 0): acc_l = sum_{k>=l} s_k ; CE_l(pixel) = logsumexp(acc_l) - acc_l[target].
 // Per-block partial sums per level -> partial[block][L]; gradients d s_k = (1/B) * sum_{l<=k} (softmax(acc_l) - onehot).
-__global__ void residual_ce_kernel(LevelPtrs ptrs, int L, int ncls, const float* __restrict__ target, int B, int hw,
-                                   float inv_batch, const float* __restrict__ upstream, float* partial) {
+// NC / NL > 0: compile-time class / level counts (2 x 5 for LIDC, 3 x 5 for UZH): every logit of the pixel is loaded before
+// the first use (NC * NL independent loads in flight) and the level loops carry no run-time guards -- the generic
+// instance (NC = NL = 0, run-time counts up to kMaxCls x kMaxLvl) took 44 us for 12 x 128^2 pixels, alone on the step's
+// critical path between forward and backward.
+template <int NC, int NL>
+__global__ void __launch_bounds__(256) residual_ce_kernel(LevelPtrs ptrs, int L_rt, int ncls_rt,
+                                                          const float* __restrict__ target, int B, int hw, float inv_batch,
+                                                          const float* __restrict__ upstream, float* partial) {
   uz::pdl_prologue();
+  constexpr int MC = NC > 0 ? NC : kMaxCls;
+  constexpr int ML = NL > 0 ? NL : kMaxLvl;
+  const int ncls = NC > 0 ? NC : ncls_rt;
+  const int L = NL > 0 ? NL : L_rt;
   if (upstream) inv_batch *= upstream[0];
   __shared__ float red[32][kMaxLvl];
-  float lsum[kMaxLvl];
+  float lsum[ML];
 #pragma unroll
-  for (int l = 0; l < kMaxLvl; ++l) lsum[l] = 0.f;
+  for (int l = 0; l < ML; ++l) lsum[l] = 0.f;
   const size_t npix = static_cast<size_t>(B) * hw;
   for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < npix;
        pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t b = pix / hw, r = pix - b * hw;
+    float v[ML][MC];
+#pragma unroll
+    for (int l = 0; l < ML; ++l)
+#pragma unroll
+      for (int k = 0; k < MC; ++k) v[l][k] = (l < L && k < ncls) ? ptrs.s[l][(b * ncls + k) * hw + r] : 0.f;
     const int tgt = static_cast<int>(target[pix]);
-    float acc[kMaxCls], grad[kMaxCls];
+    float acc[MC], grad[MC];
 #pragma unroll
-    for (int k = 0; k < kMaxCls; ++k) { acc[k] = 0.f; grad[k] = 0.f; }
-    float gl[kMaxLvl][kMaxCls];
+    for (int k = 0; k < MC; ++k) { acc[k] = 0.f; grad[k] = 0.f; }
+    float gl[ML][MC];
 #pragma unroll
-    for (int l = kMaxLvl - 1; l >= 0; --l) {
+    for (int l = ML - 1; l >= 0; --l) {
       if (l < L) {
         float mx = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < kMaxCls; ++k)
+        for (int k = 0; k < MC; ++k)
           if (k < ncls) {
-            acc[k] += ptrs.s[l][(b * ncls + k) * hw + r];
+            acc[k] += v[l][k];
             mx = fmaxf(mx, acc[k]);
           }
-        float se = 0.f, e[kMaxCls];
+        float se = 0.f, e[MC];
 #pragma unroll
-        for (int k = 0; k < kMaxCls; ++k)
+        for (int k = 0; k < MC; ++k)
           if (k < ncls) { e[k] = expf(acc[k] - mx); se += e[k]; }
         const float lse = mx + logf(se);
         float at = 0.f;
 #pragma unroll
-        for (int k = 0; k < kMaxCls; ++k)
+        for (int k = 0; k < MC; ++k)
           if (k < ncls) {
             if (k == tgt) at = acc[k];
             gl[l][k] = (e[k] / se - (k == tgt ? 1.f : 0.f)) * inv_batch;
@@ -613,10 +628,10 @@ __global__ void residual_ce_kernel(LevelPtrs ptrs, int L, int ncls, const float*
     }
     // d s_k = sum_{l<=k} gl[l]  (prefix over levels from 0 upwards)
 #pragma unroll
-    for (int l = 0; l < kMaxLvl; ++l) {
+    for (int l = 0; l < ML; ++l) {
       if (l < L) {
 #pragma unroll
-        for (int k = 0; k < kMaxCls; ++k)
+        for (int k = 0; k < MC; ++k)
           if (k < ncls) {
             grad[k] += gl[l][k];
             if (ptrs.ds[l]) ptrs.ds[l][(b * ncls + k) * hw + r] = grad[k];
@@ -626,7 +641,7 @@ __global__ void residual_ce_kernel(LevelPtrs ptrs, int L, int ncls, const float*
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int l = 0; l < kMaxLvl; ++l) {
+  for (int l = 0; l < ML; ++l) {
     const float t = uz::warp_sum(lsum[l]);
     if (lane == 0) red[wid][l] = t;
   }
@@ -914,7 +929,12 @@ extern "C" int uz_residual_ce(const float* const* s, float* const* ds, const flo
     p.ds[l] = ds ? ds[l] : nullptr;
   }
   const int blocks = uz_residual_ce_num_blocks(B, hw);
-  uz::launch(residual_ce_kernel, blocks, 256, 0, ST(stream), p, L, ncls, target, B, hw, 1.f / B, upstream, partial);
+  auto kernel = residual_ce_kernel<0, 0>;
+  if (L == 5 && ncls == 2) kernel = residual_ce_kernel<2, 5>;
+  else if (L == 5 && ncls == 3) kernel = residual_ce_kernel<3, 5>;
+  else if (L == 3 && ncls == 3) kernel = residual_ce_kernel<3, 3>;
+  else if (L == 1 && ncls == 2) kernel = residual_ce_kernel<2, 1>;
+  uz::launch(kernel, blocks, 256, 0, ST(stream), p, L, ncls, target, B, hw, 1.f / B, upstream, partial);
   UZ_CHECK_LAUNCH("uz_residual_ce");
   launch_column_reduce(ST(stream), partial, L, ce_levels, nullptr, 0, nullptr, blocks, 1.f / B);
   UZ_CHECK_LAUNCH("uz_residual_ce(reduce)");

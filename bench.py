@@ -38,7 +38,8 @@ ANNOTATORS = 4
 METRIC = 'PHiSeg-7/5 LIDC-128^2 train images/s'
 # forward conv GFLOP per image / volume; training = 3 x forward
 FWD_FLOPS = {'revphiseg': 18.318e9, 'probunet': 13.598e9, 'unet': 6.958e9, 'phiseg3d': 8.146e12, 'revphiseg3d': 2.248e12}
-TENSOR_KERNELS = ('conv_tc2_kernel', 'conv_tc_kernel', 'wgrad_tc2_kernel', 'wgrad_tc_kernel', 'wgrad_reduce_kernel')
+TENSOR_KERNELS = ('conv_tc2_kernel', 'conv_tc_kernel', 'wgrad_tc2_kernel', 'wgrad_tc_kernel', 'wgrad_reduce_kernel',
+                  'wgrad_reduce_batched_kernel')
 
 
 def conv_forward_flops_per_image(net, hw=128):
@@ -309,6 +310,7 @@ _HBM_BYTES = {
     'uz_bn_apply_train': ('bn_apply_train_kernel', lambda a: a[17] * a[18] * 4),          # read y, write a (bf16)
     'uz_bn_bwd_reduce_sums': ('bn_bwd_reduce_kernel', lambda a: a[7] * a[8] * 4),         # read dout, y
     'uz_bn_bwd_apply_train': ('bn_bwd_apply_train_kernel', lambda a: a[16] * a[17] * 6),  # read dout, y, write dy
+    'uz_bn_bwd_fused': ('bn_bwd_cluster_kernel', lambda a: a[15] * a[16] * 6),            # the same in one launch
 }
 
 
@@ -317,9 +319,10 @@ def single_stream_profile(net, device, hbm_peak):
     and replayed under CUPTI: busy time of the tensor-core families and GB/s of the BatchNorm passes."""
     import models.phiseg as _mp
     from b200 import _lib, ops as _ops, train
-    saved = (_mp._CONCURRENT, _ops._AUX_ENABLED)
+    saved = (_mp._CONCURRENT, _ops._AUX_ENABLED, _lib.raw('uz_get_pdl')())
     _mp._CONCURRENT = False
     _ops.set_concurrency(False)
+    _lib.call('uz_set_pdl', 0)      # programmatic dependent launch off: an early-launched kernel's record includes its wait
     bytes_by_kernel = collections.defaultdict(float)
     orig = _lib.call
 
@@ -341,6 +344,7 @@ def single_stream_profile(net, device, hbm_peak):
         _lib.call = orig
         _mp._CONCURRENT = saved[0]
         _ops.set_concurrency(saved[1])
+        _lib.call('uz_set_pdl', saved[2])
     del st
     if not rows or 'error' in rows[0]:
         return None
@@ -553,7 +557,8 @@ def main():
                     ncu = None
             roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                         'frac': achieved / peak_tf, 'traffic': traffic,
-                        'kernel': 'conv_tc2_kernel / conv_tc_kernel (fwd + dgrad) + wgrad_tc2_kernel / wgrad_tc_kernel (+ wgrad_reduce_kernel)',
+                        'kernel': 'conv_tc2_kernel / conv_tc_kernel (fwd + dgrad, the latter incl. the cluster-fused BatchNorm epilogue) + '
+                                  'wgrad_tc2_kernel / wgrad_tc_kernel (+ wgrad_reduce_batched_kernel)',
                         'algorithmic_flops_per_step': train_flops, 'kernel_ms_per_step': tc_ms,
                         'peak_source': peak_src, 'single_stream_step_us': prof['span_us'],
                         'share_of_step': (prof['tensor_us'] / prof['span_us']) if prof['span_us'] else None,

@@ -40,9 +40,11 @@ int uz_set_debug_flags(int flags);
 /* profiling build only (libunetzoo_b200_prof.so, -DUZ_PROFILE_KNOBS): device buffer of 16 uint64 that CTA 0 of the
  * small-shape tensor-core kernels fills with %globaltimer phase timestamps (tools/phase_trace.py); NULL switches it off */
 int uz_set_trace_buffer(void* device_ptr);
-/* Programmatic dependent launch for every kernel of the library (default off; environment UZ_PDL=1 or this call
- * enables it: it helps single-stream execution and hurts the multi-stream overlap the models use, profiles/r01_pdl.md). */
+/* Programmatic dependent launch: 0 off, 1 every kernel, 2 only the light (elementwise / reduction) kernels, 3 only the
+ * tensor-core kernels (default; environment UZ_PDL): their barrier / TMEM / descriptor prologue then overlaps the tail of
+ * the preceding kernel.  Measured on the PHiSeg-7/5 step: off 4.32 ms, 1: 4.27, 2: 4.48, 3: 4.23 (profiles/README.md). */
 int uz_set_pdl(int enabled);
+int uz_get_pdl(void);
 /* Preferred shared-memory carveout (percent of the unified L1 / shared-memory array; -1 = driver default) applied to
  * every kernel of the library at its next launch.  Environment: UZ_CARVEOUT. */
 int uz_set_smem_carveout(int percent);

@@ -323,7 +323,9 @@ inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  // g_pdl: 1 = every launch, 2 = only light kernels (<= 48 KB dynamic shared memory: the elementwise / reduction
+  // kernels), 3 = only the tensor-core kernels (their barrier / TMEM / descriptor prologue overlaps the predecessor's tail)
+  cfg.numAttrs = (g_pdl == 1 || (g_pdl == 2 && smem <= 48 * 1024) || (g_pdl == 3 && smem > 48 * 1024)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -345,7 +347,7 @@ inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 2 : 1;
+  cfg.numAttrs = (g_pdl == 1 || (g_pdl == 2 && smem <= 48 * 1024) || (g_pdl == 3 && smem > 48 * 1024)) ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

@@ -33,10 +33,14 @@ int load_encode() {
 
 namespace uz {
 int g_pdl = [] {
-  // Measured on the PHiSeg training step (profiles/r01_pdl.md): +4 % on a single stream, -3.5 % with the three-stream
-  // overlap the models use (early-scheduled dependents hold SM resources other streams could use) => opt-in.
+  // Programmatic dependent launch.  Round 1 (profiles/r01_pdl.md): on for every kernel it gained 4 % on a single stream
+  // and LOST 3.5 % with the multi-stream overlap the models use (early-scheduled dependents hold SM resources other
+  // streams could use).  Round 2, restructured step (PHiSeg-7/5 B=12, ms per step): off 4.32, every kernel 4.26-4.28,
+  // light kernels only 4.48, tensor-core kernels only 4.20-4.26 -- their barrier / TMEM / descriptor prologue is what
+  // overlaps the predecessor's tail -- hence default 3.  UZ_PDL=0/1/2/3 selects.
   const char* e = getenv("UZ_PDL");
-  return (e && e[0] == '1') ? 1 : 0;
+  if (!e) return 3;
+  return (e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
 }();
 
 // Shared-memory carveout preference applied to EVERY kernel of the library on its first launch (UZ_CARVEOUT = percent of
@@ -146,7 +150,9 @@ extern "C" int uz_set_trace_buffer(void* device_ptr) {
 #endif
 }
 
+extern "C" int uz_get_pdl(void) { return uz::g_pdl; }
+
 extern "C" int uz_set_pdl(int enabled) {
-  uz::g_pdl = enabled ? 1 : 0;
+  uz::g_pdl = enabled < 0 ? 0 : (enabled > 3 ? 1 : enabled);   // 0 off, 1 all kernels, 2 light / 3 tensor-core kernels only
   return UZ_OK;
 }

@@ -351,13 +351,24 @@ def test_conv_bn_relu_cluster_kernel(N, H, W, Cin, Cout, taps):
     rm2, rv2 = rm0.clone(), rv0.clone()
     scale2, shift2, mean2, invstd2 = k.bn_finalize(partial, N * H * W, gamma, beta, rm2, rv2)
     a2 = k.affine_act(y2, scale2, shift2, relu=True)
-    assert torch.equal(y, y2)                                              # the stored conv output is the same kernel math
-    torch.testing.assert_close(mean, mean2, rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(invstd, invstd2, rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(scale, scale2, rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(shift, shift2, rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(rm, rm2, rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(rv, rv2, rtol=1e-5, atol=1e-6)
+    import os
+    small = os.environ.get('UZ_CONV_SMALL') == '1' and H <= 4 and W <= 4 and N * H * W <= 64 and Cin % 64 == 0 and \
+        taps == 9                     # then served by the opt-in CUDA-core small-map kernel (conv_small.cu)
+    if small:
+        # different fp32 summation order than the tensor-core kernel: a few stored values differ by one bf16 ulp
+        d = (y.float() - y2.float()).abs()
+        assert float(d.max()) <= 2 ** -7 * float(y2.float().abs().max())
+        assert float((d > 0).float().mean()) < 0.05
+        tol = 2e-3
+    else:
+        assert torch.equal(y, y2)                                          # the stored conv output is the same kernel math
+        tol = 1e-5
+    torch.testing.assert_close(mean, mean2, rtol=tol, atol=tol * float(mean2.abs().max()))
+    torch.testing.assert_close(invstd, invstd2, rtol=tol, atol=1e-6)
+    torch.testing.assert_close(scale, scale2, rtol=tol, atol=1e-6)
+    torch.testing.assert_close(shift, shift2, rtol=10 * tol, atol=tol * float(shift2.abs().max()))
+    torch.testing.assert_close(rm, rm2, rtol=tol, atol=tol * float(rm2.abs().max()))
+    torch.testing.assert_close(rv, rv2, rtol=tol, atol=1e-6)
     assert float((a.float() - a2.float()).abs().max()) <= 2 ** -7 * float(a2.float().abs().max())     # one bf16 ulp
     # torch fp32 on the stored y
     yq = to_nchw(y)

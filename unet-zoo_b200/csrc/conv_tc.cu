@@ -22,6 +22,18 @@ int conv2_stats_rows(int N, int H, int W, int Cin, int Cout);
 int conv2_launch(const void* x, int N, int D, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, void* y, int ldy,
                  const float* scale, const float* shift, int relu, float* stats_partial, const UzConvExtra* ex, void* stream,
                  int* handled);
+// conv_small.cu: CUDA-core kernel for maps of at most 4x4 pixels (latency-bound layers)
+struct SmallBn {
+  float count, eps, momentum;
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var;
+  int updates, relu;
+  float* scale_out; float* shift_out; float* mean_out; float* invstd_out;
+  void* a; int lda;
+};
+int conv_small_supported(int N, int H, int W, int Cin, int Cout);
+int conv_small_launch(const void* x, int N, int H, int W, int Cin, int ldx, const void* w_packed, int Cout, void* y,
+                      int ldy, const float* scale, const float* shift, int relu, const SmallBn* fb, void* stream);
 }  // namespace uz
 
 namespace {
@@ -521,6 +533,17 @@ int conv_fwd_impl(const void* x, int N, int H, int W, int Cin, int ldx, const vo
                    (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
                "uz_conv_fwd: pointers must be 16-byte aligned");
   if UZ_KNOB(128) return UZ_OK;   // measurement knob: step time without the conv kernels
+  if (taps == 9 && !stats_partial && !(ex && (ex->bn_y || ex->residual)) && uz::conv_small_supported(N, H, W, Cin, Cout)) {
+    // 2x2 ... 4x4 maps: latency-bound, CUDA-core kernel with the BatchNorm fusion inside one CTA (conv_small.cu)
+    uz::SmallBn sb{};
+    if (fb) {
+      sb.count = fb->count; sb.eps = fb->eps; sb.momentum = fb->momentum; sb.gamma = fb->gamma; sb.beta = fb->beta;
+      sb.running_mean = fb->running_mean; sb.running_var = fb->running_var; sb.updates = fb->updates; sb.relu = fb->relu;
+      sb.scale_out = fb->scale_out; sb.shift_out = fb->shift_out; sb.mean_out = fb->mean_out;
+      sb.invstd_out = fb->invstd_out; sb.a = fb->a; sb.lda = fb->lda;
+    }
+    return uz::conv_small_launch(x, N, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, fb ? &sb : nullptr, stream);
+  }
   if (taps == 9 && !UZ_KNOB(32) && !fb) {
     int handled = 0;
     int rc = uz::conv2_launch(x, N, 0, H, W, Cin, ldx, w_packed, Cout, y, ldy, scale, shift, relu, stats_partial, ex,

@@ -507,10 +507,13 @@ slayer_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restric
         g_s[i] = t;
       }
       __syncthreads();
-      if (threadIdx.x < ncls) {
+      // bias gradient: warp k sums class k over the row's pixels (lanes + shuffle tree: fixed order; a single thread per
+      // class walking up to 128 pixels kept the whole block waiting ~2 us per row at the next barrier)
+      for (int k = threadIdx.x >> 5; k < ncls; k += kSlThreads / 32) {
         float t = 0.f;
-        for (int pl = 0; pl < pbc; ++pl) t += g_s[pl * ncls + threadIdx.x];
-        db_s[threadIdx.x] += t;
+        for (int pl = threadIdx.x & 31; pl < pbc; pl += 32) t += g_s[pl * ncls + k];
+        t = uz::warp_sum(t);
+        if ((threadIdx.x & 31) == 0) db_s[k] += t;
       }
       if (p2_active) {
         for (int pl = pslot; pl < pbc; pl += pstride) {
@@ -871,7 +874,7 @@ extern "C" int uz_slayer3d_fwd(const void* feat, int ld, int C, const float* w, 
 
 extern "C" int uz_slayer_bwd_num_blocks(int B, int h, int wd) {
   (void)wd;
-  return cap_blocks(static_cast<long long>(B) * h, 2);       // blocks own low-res rows
+  return cap_blocks(static_cast<long long>(B) * h, 4);       // blocks own low-res rows
 }
 
 extern "C" int uz_slayer_bwd(const float* dout, const void* feat, int ld, int C, const float* w, int ncls, int B, int h,

@@ -23,6 +23,7 @@ from torchlayers import Conv2D, Conv2DSequence, ReversibleSequence, _boundary, d
 # Independent sub-graphs (prior vs posterior encoder, the likelihood's per-level branches) are issued on a second CUDA
 # stream: most of their layers are too small to fill 148 SMs on their own.  UNETZOO_CONCURRENCY=0 disables it.
 _CONCURRENT = os.environ.get('UNETZOO_CONCURRENCY', '1') != '0'
+_EARLY_LOGITS = os.environ.get('UNETZOO_EARLY_LOGITS', '1') != '0'
 _PRIOR_OVERLAP = os.environ.get('UNETZOO_PRIOR_OVERLAP', '1') != '0'    # prior latent path next to the likelihood
 _LIKELIHOOD_STREAMS = max(1, int(os.environ.get('UNETZOO_LIKELIHOOD_STREAMS', '4')))   # side streams of Likelihood.forward
 _side_streams = {}
@@ -365,22 +366,39 @@ class Likelihood(nn.Module):
             post_z[-i - 1] = x
         if fork is not None:
             fork.join()
+        # The class logits of a level (1x1 conv + nearest upsampling, models/phiseg.py:319-321) depend only on that level's
+        # post_c: they are issued as soon as it exists, the low-resolution ones on side streams next to the top-down chain
+        # (five of them back to back after the chain were 75 us at the tail of forward -- and, replayed by autograd on the
+        # same streams, 130 us at the head of backward).
+        sfork = _Fork(z[0].device, self.latent_levels - 1, tag='slayer') if (fork is not None and _EARLY_LOGITS) else None
+
+        def emit_logits(lvl):
+            feat = post_c[lvl]
+            conv = self.s_layer[self.latent_levels - 1 - lvl].convolution[0].convolution[0]
+            factor = self.image_size[1] // feat.t.shape[1]
+            assert factor * feat.t.shape[1] == self.image_size[1] and factor * feat.t.shape[2] == self.image_size[2]
+            if sfork is not None and lvl != 0:
+                st = sfork.streams[lvl - 1]
+                st.wait_stream(sfork.main)
+                feat.t.record_stream(st)
+                with torch.cuda.stream(st):
+                    out = ops.SLayerNearest.apply(feat.t, conv.weight, conv.bias, 1 if lowres else factor)
+                sfork.hand_over(out)
+            else:
+                out = ops.SLayerNearest.apply(feat.t, conv.weight, conv.bias, 1 if lowres else factor)
+            s[lvl] = (out, factor) if lowres else out
+
         post_c[self.latent_levels - 1] = post_z[self.latent_levels - 1]
+        emit_logits(self.latent_levels - 1)
         for i in reversed(range(self.latent_levels - 1)):
             below = post_c[i + 1]
             assert post_z[i].t.shape[1] == 2 * below.t.shape[1] and post_z[i].t.shape[2] == 2 * below.t.shape[2]
             # bilinear x2 of the level below written straight into the concat buffer (no intermediate tensor)
             concat = Act(ops.Concat.apply(post_z[i].t, below.t, False, True, True), post_z[i].c + below.c)
             post_c[i] = self.likelihood_post_c_path[i](concat)
-        for i, block in enumerate(self.s_layer):
-            feat = post_c[-i - 1]
-            conv = block.convolution[0].convolution[0]
-            factor = self.image_size[1] // feat.t.shape[1]
-            assert factor * feat.t.shape[1] == self.image_size[1] and factor * feat.t.shape[2] == self.image_size[2]
-            if lowres:
-                s[-i - 1] = (ops.SLayerNearest.apply(feat.t, conv.weight, conv.bias, 1), factor)
-            else:
-                s[-i - 1] = ops.SLayerNearest.apply(feat.t, conv.weight, conv.bias, factor)
+            emit_logits(i)
+        if sfork is not None:
+            sfork.join()
         return s
 
 

@@ -172,6 +172,10 @@ typedef struct UzAdamPackDesc {
   void* w_dgrad;      /* bf16 [taps][CinP][CoutP] or NULL */
   int tensor;         /* row of the UzAdamDesc table */
   int Cout, Cin, taps, CoutP, CinP;
+  const float* slab;  /* NULL: gradient = the g of the UzAdamDesc row; else the split-K slabs [splits][taps][CoutP][CinP] of
+                         uz_conv_wgrad_partial, summed over the splits in order while the tile is loaded (no separate
+                         uz_wgrad_reduce_batched pass, no OIHW gradient tensor) */
+  int splits, reserved;
 } UzAdamPackDesc;
 int uz_adam_pack_items(int CoutP, int CinP, int taps);
 int uz_adam_pack_step(const void* descs_device, int ntensors, const int* chunk_table_device, int nchunks,
@@ -424,7 +428,9 @@ int uz_conv3d_wgrad(const void* x, int ldx, const void* dy, int lddy, int N, int
  * [splits][taps][Cout][Cin] fp32 stay in `workspace`, *splits reports their number; D == 0 images, D > 0 volumes with 27
  * taps), and ONE uz_wgrad_reduce_batched launch later sums the splits of many layers in fixed order and writes their
  * OIHW gradients dw[Cout][Cin][taps] (the per-layer reduction of uz_conv_wgrad costs a launch per layer and writes with a
- * stride of `taps` floats).  Rows of the (host) table, at most UZ_WGRAD_REDUCE_MAX_ROWS per launch -- they travel as launch
+ * stride of `taps` floats).  accumulate = 1: the split-K CTAs ADD their blocks into ONE slab [taps][Cout][Cin] (workspace
+ * zero on entry, taps*Cout*Cin floats; bulk reduce-add stores, the reduction happens in L2; *splits = 1; fp32 summation
+ * order then depends on scheduling -- accumulate = 0 keeps the fixed-order slabs).  Rows of the (host) table, at most UZ_WGRAD_REDUCE_MAX_ROWS per launch -- they travel as launch
  * parameters, so a captured CUDA graph holds them by value: */
 #define UZ_WGRAD_REDUCE_MAX_ROWS 64
 typedef struct UzWgradReduceDesc {
@@ -437,8 +443,8 @@ typedef struct UzWgradReduceDesc {
   int reserved;
 } UzWgradReduceDesc;
 int uz_conv_wgrad_partial(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout,
-                          int taps, float* workspace, int* splits, void* stream);
-int uz_wgrad_reduce_units(int Cout_logical, int Cin_logical);
+                          int taps, float* workspace, int accumulate, int* splits, void* stream);
+int uz_wgrad_reduce_units(int Cout_logical, int Cin_logical, int taps);
 int uz_wgrad_reduce_batched(const UzWgradReduceDesc* descs, int n, void* stream);
 
 /* nn.AvgPool3d(2, 2, ceil_mode=True) on even sizes (models/phiseg3D.py:100) and its gradient. */

@@ -283,38 +283,47 @@ def test_bn_backward_cluster_kernel(N, H, W, C, ld):
     assert float((dy.float() - dy_u.float()).abs().max()) <= 2 ** -7 * float(dy_u.float().abs().max())
 
 
-def test_deferred_batched_wgrad_reduction():
+@pytest.mark.parametrize('accumulate', [True, False])
+def test_deferred_batched_wgrad_reduction(accumulate):
     """uz_conv_wgrad_partial + ONE uz_wgrad_reduce_batched launch for a mix of layers (persistent and generic plans, 1x1,
-    padded logical channels, a 3x3x3 volume layer) against the per-layer uz_conv_wgrad: same partial slabs; the batched
-    kernel sums the splits strictly in order, the per-layer one in up to 8 interleaved groups => equal up to fp32
-    summation order (1e-5), and bit-reproducible run to run."""
+    padded logical channels, a 3x3x3 volume layer) against the per-layer uz_conv_wgrad.  accumulate: the split-K CTAs add
+    into one slab through L2 (bulk reduce-add stores) -- equal up to fp32 summation order; slab mode (what the
+    deterministic mode uses): splits summed strictly in order, bit-reproducible run to run."""
     k = kern()
     cases = [  # N, H, W, Cin, Cout, taps, Cin_logical, Cout_logical
         (12, 16, 16, 192, 192, 9, 192, 192), (12, 2, 2, 192, 192, 9, 192, 192), (3, 32, 32, 64, 128, 9, 64, 128),
         (2, 64, 64, 32, 32, 9, 32, 32), (2, 32, 32, 224, 128, 1, 224, 128), (2, 32, 32, 16, 32, 9, 3, 32),
         (12, 8, 8, 80, 64, 9, 66, 64), (4, 128, 128, 32, 32, 9, 32, 32)]
-    ref, got, keep = [], [], []
-    for i, (N, H, W, Cin, Cout, taps, cil, col) in enumerate(cases):
-        x = to_nhwc(bf16r(_rand(N, Cin, H, W, seed=20 + i)))
-        dy = to_nhwc(bf16r(_rand(N, Cout, H, W, seed=40 + i)))
-        ref.append(k.conv_wgrad(x, dy, taps, cil, col))
-        got.append(k.conv_wgrad(x, dy, taps, cil, col, defer=True))
-        keep.append((x, dy))
-    xv = bf16r(_rand(1, 32, 8, 16, 16, seed=3)).permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
-    dv = bf16r(_rand(1, 48, 8, 16, 16, seed=4)).permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
-    ref.append(k.conv_wgrad(xv, dv, 27, 32, 48))
-    got.append(k.conv_wgrad(xv, dv, 27, 32, 48, defer=True))
-    assert len(k.wgrad_reducer.items) == len(cases) + 1
-    k.wgrad_reducer.flush()
-    assert not k.wgrad_reducer.items
-    torch.cuda.synchronize()
-    for i, (a, b) in enumerate(zip(got, ref)):
-        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5 * float(b.abs().max()), msg='layer %d' % i)
-    again = [k.conv_wgrad(x, dy, c[5], c[6], c[7], defer=True) for (x, dy), c in zip(keep, cases)]
-    k.wgrad_reducer.flush()
-    torch.cuda.synchronize()
-    for i, (a, b) in enumerate(zip(again, got)):
-        assert torch.equal(a, b), 'layer %d not reproducible' % i
+    prev_acc, prev_det = k._WGRAD_ACCUMULATE, k.set_deterministic(not accumulate)
+    k._WGRAD_ACCUMULATE = accumulate
+    try:
+        ref, got, keep = [], [], []
+        for i, (N, H, W, Cin, Cout, taps, cil, col) in enumerate(cases):
+            x = to_nhwc(bf16r(_rand(N, Cin, H, W, seed=20 + i)))
+            dy = to_nhwc(bf16r(_rand(N, Cout, H, W, seed=40 + i)))
+            ref.append(k.conv_wgrad(x, dy, taps, cil, col))
+            got.append(k.conv_wgrad(x, dy, taps, cil, col, defer=True))
+            keep.append((x, dy))
+        xv = bf16r(_rand(1, 32, 8, 16, 16, seed=3)).permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+        dv = bf16r(_rand(1, 48, 8, 16, 16, seed=4)).permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+        ref.append(k.conv_wgrad(xv, dv, 27, 32, 48))
+        got.append(k.conv_wgrad(xv, dv, 27, 32, 48, defer=True))
+        assert len(k.wgrad_reducer.items) == len(cases) + 1
+        assert all((it[1] == 1) == accumulate or it[1] == 1 for it in k.wgrad_reducer.items)
+        k.wgrad_reducer.flush()
+        assert not k.wgrad_reducer.items
+        torch.cuda.synchronize()
+        for i, (a, b) in enumerate(zip(got, ref)):
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5 * float(b.abs().max()), msg='layer %d' % i)
+        if not accumulate:
+            again = [k.conv_wgrad(x, dy, c[5], c[6], c[7], defer=True) for (x, dy), c in zip(keep, cases)]
+            k.wgrad_reducer.flush()
+            torch.cuda.synchronize()
+            for i, (a, b) in enumerate(zip(again, got)):
+                assert torch.equal(a, b), 'layer %d not reproducible' % i
+    finally:
+        k._WGRAD_ACCUMULATE = prev_acc
+        k.set_deterministic(prev_det)
 
 
 # N, H, W, Cin, Cout, taps: 1 / 2 / 6 pixel tiles per cluster, Cout chunks of 48 / 64 / 32, a 1x1 layer, padded inputs

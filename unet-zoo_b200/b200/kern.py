@@ -264,13 +264,39 @@ class WgradReducer:
         self.items = []
         self.pending_bytes = 0
         self.keep = []             # slabs / gradient tensors referenced by captured launches
+        # hold: the end-of-backward flush is skipped -- the optimizer that follows reads the slabs itself
+        # (FusedAdam with an attached packer: uz_adam_pack_step sums the splits while it loads a tile's gradients), takes
+        # the items it can use with ``take`` and flushes the rest
+        self.hold = False
+
+    def take(self, dw_ptrs):
+        """-> {dw data_ptr: (slab tensor, splits, coutp, cinp)} for the pending items whose gradient tensor is in
+        ``dw_ptrs``; they leave the pending list (the caller consumes the slabs directly)"""
+        want = set(dw_ptrs)
+        out, rest = {}, []
+        for it in self.items:
+            ptr = it[7].data_ptr()
+            if ptr in want and ptr not in out:
+                out[ptr] = (it[0], it[1], it[3], it[4])
+            else:
+                rest.append(it)
+        self.items = rest
+        self.pending_bytes = sum(it[0].numel() * 4 for it in rest)
+        if out:
+            cur = torch.cuda.current_stream(next(iter(out.values()))[0].device)
+            if torch.cuda.is_current_stream_capturing():
+                self.keep.append(list(out.values()))
+            else:
+                for v in out.values():
+                    v[0].record_stream(cur)
+        return out
 
     def add(self, work, splits, taps, coutp, cinp, cout, cin, dw):
         self.items.append((work, splits, taps, coutp, cinp, cout, cin, dw))
         self.pending_bytes += work.numel() * 4
 
-    def flush(self):
-        if not self.items:
+    def flush(self, force=True):
+        if not self.items or (self.hold and not force):
             return
         items, self.items, self.pending_bytes = self.items, [], 0
         cur = torch.cuda.current_stream(items[0][0].device)
@@ -290,6 +316,7 @@ class WgradReducer:
 
 
 wgrad_reducer = WgradReducer()
+_WGRAD_ACCUMULATE = _os.environ.get('UNETZOO_WGRAD_ACCUMULATE', '1') != '0'
 
 
 def conv_wgrad(x, dy, taps, cin_logical, cout_logical, out=None, defer=False):
@@ -310,14 +337,18 @@ def conv_wgrad(x, dy, taps, cin_logical, cout_logical, out=None, defer=False):
         ws = _lib.raw('uz_wgrad_workspace_floats')(n, h, w, cin, cout, taps)
     if ws < 0:
         raise _lib.UnetZooLibError('uz_conv_wgrad: unsupported shape Cin=%d Cout=%d' % (cin, cout))
-    work = torch.empty((ws,), dtype=torch.float32, device=x.device)
     dw = out if out is not None else torch.empty((cout_logical, cin_logical, taps), dtype=torch.float32, device=x.device)
     if defer:
+        # split-K CTAs add into ONE slab through L2 (bulk reduce-add) unless the run has to be bit-reproducible
+        acc = _WGRAD_ACCUMULATE and not _DETERMINISTIC
+        work = torch.zeros((taps * cout * cin,), dtype=torch.float32, device=x.device) if acc else \
+            torch.empty((ws,), dtype=torch.float32, device=x.device)
         splits = ctypes.c_int(0)
-        _lib.call('uz_conv_wgrad_partial', _p(x), ldx, _p(dy), lddy, nb, d, h, w, cin, cout, taps, _p(work),
+        _lib.call('uz_conv_wgrad_partial', _p(x), ldx, _p(dy), lddy, nb, d, h, w, cin, cout, taps, _p(work), int(acc),
                   ctypes.byref(splits), _stream())
         wgrad_reducer.add(work, splits.value, taps, cout, cin, cout_logical, cin_logical, dw)
         return dw
+    work = torch.empty((ws,), dtype=torch.float32, device=x.device)
     if vol:
         _lib.call('uz_conv3d_wgrad', _p(x), ldx, _p(dy), lddy, nb, d, h, w, cin, cout, cin_logical, cout_logical,
                   _p(work), _p(dw), _stream())

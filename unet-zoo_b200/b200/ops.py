@@ -89,7 +89,7 @@ def sync_aux_streams():
     for st in _aux['pending']:
         cur.wait_stream(st)
     _aux['pending'] = []
-    kern.wgrad_reducer.flush()
+    kern.wgrad_reducer.flush(force=False)      # unless an optimizer that reads the slabs itself follows (TrainStep)
     _aux['keep'] = []
     _aux['callback_queued'] = False
     _aux['next'] = 0

@@ -120,8 +120,18 @@ class FusedAdam(torch.optim.Optimizer):
         # tensors (replaced only by load_state_dict / reset); the full rows are rebuilt only when it changes
         gen = self.__dict__.setdefault('_state_gen', 0)
         state = self.state
+        # weight gradients still sitting in their split-K slabs (kern.wgrad_reducer on hold): the fused update + packing
+        # kernel sums the splits itself, the OIHW gradient tensor is never written
+        slabs = {}
+        if self.packer is not None:
+            from . import kern
+            if kern.wgrad_reducer.hold and kern.wgrad_reducer.items:
+                slabs = kern.wgrad_reducer.take([p.grad.data_ptr() for p in live if p.data_ptr() in self.packer.rows])
+                kern.wgrad_reducer.flush()                       # whatever the packer does not cover
+        slab_key = tuple((slabs[p.grad.data_ptr()][0].data_ptr(), slabs[p.grad.data_ptr()][1])
+                         if p.grad.data_ptr() in slabs else (0, 0) for p in live) if slabs else ()
         quick = (gen, tuple(p.grad.data_ptr() for p in live),
-                 tuple(id(state[p].get('exp_avg')) if p in state else 0 for p in live))
+                 tuple(id(state[p].get('exp_avg')) if p in state else 0 for p in live), slab_key)
         cache = self.__dict__.setdefault('_row_cache', {})
         hit = cache.get(gi)
         if hit is not None and hit[0] == quick:
@@ -136,7 +146,7 @@ class FusedAdam(torch.optim.Optimizer):
                 rows.append((p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
                              st['step'].data_ptr(), p.numel()))
                 key.append(rows[-1])     # every raw pointer the table holds: a replaced state tensor invalidates it
-            key = tuple(key)
+            key = tuple(key) + (slab_key,)
             cache[gi] = (quick, rows, key)
         # two persistent table sets per group, allocated on first use (never inside a stream capture): one for eager
         # steps, one for a captured step whose memcpy nodes must keep reading the pointers they were captured with
@@ -156,10 +166,10 @@ class FusedAdam(torch.optim.Optimizer):
                 bufs.append({'key': None, 'n': 0, 'nt': 0, 'ni': 0,
                              'host_d': torch.empty(nparam * 48, dtype=torch.uint8).pin_memory(),
                              'host_c': torch.empty(nchunk_max * 2, dtype=torch.int32).pin_memory(),
-                             'host_p': torch.empty(nparam * 40, dtype=torch.uint8).pin_memory(),
+                             'host_p': torch.empty(nparam * 56, dtype=torch.uint8).pin_memory(),
                              'descs': torch.empty(nparam * 48, dtype=torch.uint8, device=dev),
                              'chunks': torch.empty(nchunk_max * 2, dtype=torch.int32, device=dev),
-                             'packs': torch.empty(nparam * 40, dtype=torch.uint8, device=dev),
+                             'packs': torch.empty(nparam * 56, dtype=torch.uint8, device=dev),
                              'host_i': torch.empty(max(2 * nitem_max, 2), dtype=torch.int32).pin_memory(),
                              'items': torch.empty(max(2 * nitem_max, 2), dtype=torch.int32, device=dev)})
             self._tables[gi] = bufs
@@ -178,7 +188,12 @@ class FusedAdam(torch.optim.Optimizer):
                     _, wf, wd, cout, cin, taps, coutp, cinp, _ = struct.unpack('<QQQiiiiii', hit[0])
                     for it in range(_lib.raw('uz_adam_pack_items')(coutp, cinp, taps)):
                         items += [len(prow), it]
-                    prow.append(struct.pack('<QQiiiiii', wf, wd, ti, cout, cin, taps, coutp, cinp))
+                    sl = slabs.get(r[1])
+                    if sl is not None and (sl[2], sl[3]) != (coutp, cinp):
+                        raise _lib.UnetZooLibError('FusedAdam: weight-gradient slab and packed weight disagree on the padded '
+                                                   'channel counts')
+                    prow.append(struct.pack('<QQiiiiiiQii', wf, wd, ti, cout, cin, taps, coutp, cinp,
+                                            sl[0].data_ptr() if sl is not None else 0, sl[1] if sl is not None else 0, 0))
                     continue
                 for c in range((r[5] + chunk - 1) // chunk):
                     table += [ti, c]

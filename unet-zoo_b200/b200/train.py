@@ -12,6 +12,9 @@ import torch
 from . import _lib, kern
 
 
+_CONSUME_SLABS = os.environ.get('UNETZOO_ADAM_FROM_SLABS', '1') != '0'
+
+
 def make_adam(net, capturable=True, fused=True, own_kernel=True):
     """The reference's optimizer (train_model.py:49: Adam, lr 1e-3, weight_decay 1e-5 as L2 on the gradient).
     own_kernel=True: b200.optim.FusedAdam, one launch for all parameters (graph capturable, same state layout as
@@ -77,11 +80,20 @@ class TrainStep:
             self.opt.zero_grad(set_to_none=True)
         self.net.forward(self.patch, self.mask, training=True)
         loss = self.net.loss(self.mask)
-        loss.backward()
-        if self.dp is not None:
-            self.dp.finish()
-        if self.dp is None or not self.dp.owns_optimizer:
-            self.opt.step()
+        # single GPU, fused optimizer with an attached packer: the optimizer reads the weight-gradient slabs itself
+        # (no reduction pass, no OIHW gradient tensors -- nobody else looks at .grad inside this step)
+        hold = self.dp is None and self.packer is not None and getattr(self.opt, 'packer', None) is self.packer and \
+            _CONSUME_SLABS
+        kern.wgrad_reducer.hold = hold
+        try:
+            loss.backward()
+            if self.dp is not None:
+                self.dp.finish()
+            if self.dp is None or not self.dp.owns_optimizer:
+                self.opt.step()
+        finally:
+            kern.wgrad_reducer.hold = False
+            kern.wgrad_reducer.flush()
         self.loss.copy_(loss.detach())
 
     def refresh_weights(self):

@@ -246,6 +246,40 @@ __global__ void __launch_bounds__(kEwThreads) adam_pack_kernel(const UzAdamDesc*
   const int r = item / groups;
   const int i0 = (r % ti) * 32, o0 = (r / ti) * 32;
   const int row = 32 * tg;
+  // Gradient straight from the weight-gradient kernels' split-K slabs [split][tap][CoutP][CinP] (pk.slab != NULL): the tile
+  // of gradients is summed over the splits and transposed into shared memory first -- rows of 32 input channels, 128
+  // contiguous bytes per (tap, o) -- so the separate reduction pass (read slabs, write OIHW, read again here) disappears.
+  const float* __restrict__ slab = pk.slab;
+  if (slab != nullptr) {
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const size_t plane = static_cast<size_t>(pk.CoutP) * pk.CinP;
+    const size_t split_stride = plane * pk.taps;
+    const int i = i0 + lane;
+    constexpr int U = 9;                                           // independent 128-byte row loads in flight per warp
+    constexpr int W = kEwThreads / 32;
+    for (int rt0 = wrp; rt0 < 32 * tg; rt0 += W * U) {             // (o row, tap of the group) pairs
+      float a[U];
+      int oo[U], sl[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int rt = rt0 + u * W;
+        oo[u] = rt / tg;
+        sl[u] = rt - oo[u] * tg;
+        a[u] = 0.f;
+        const int o = o0 + oo[u];
+        if (rt < 32 * tg && o < pk.Cout && i < pk.Cin) {
+          const float* src = slab + static_cast<size_t>(grp * tg + sl[u]) * plane + static_cast<size_t>(o) * pk.CinP + i;
+          float t = src[0];
+          for (int sp = 1; sp < pk.splits; ++sp) t += src[static_cast<size_t>(sp) * split_stride];   // fixed order
+          a[u] = t;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (rt0 + u * W < 32 * tg) tile[oo[u]][lane * tg + sl[u]] = a[u];
+    }
+    __syncthreads();
+  }
   const bool full = o0 + 32 <= pk.Cout && i0 + 32 <= pk.Cin && tg == 9 && pk.taps == 9 && (pk.Cin & 3) == 0 &&
                     (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                        reinterpret_cast<uintptr_t>(v)) & 15) == 0);
@@ -267,7 +301,12 @@ __global__ void __launch_bounds__(kEwThreads) adam_pack_kernel(const UzAdamDesc*
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         pp[u] = *reinterpret_cast<const float4*>(p + idx[u]);
-        gg[u] = *reinterpret_cast<const float4*>(g + idx[u]);
+        if (slab != nullptr) {
+          const float* trow = &tile[oo[u]][c4[u] * 4];
+          gg[u] = make_float4(trow[0], trow[1], trow[2], trow[3]);
+        } else {
+          gg[u] = *reinterpret_cast<const float4*>(g + idx[u]);
+        }
         mm[u] = *reinterpret_cast<const float4*>(m + idx[u]);
         vv[u] = *reinterpret_cast<const float4*>(v + idx[u]);
       }
@@ -303,7 +342,12 @@ __global__ void __launch_bounds__(kEwThreads) adam_pack_kernel(const UzAdamDesc*
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (ok[u]) { pp[u] = p[idx[u]]; gg[u] = g[idx[u]]; mm[u] = m[idx[u]]; vv[u] = v[idx[u]]; }
+        if (ok[u]) {
+          pp[u] = p[idx[u]];
+          gg[u] = slab != nullptr ? tile[oo[u]][rem[u]] : g[idx[u]];
+          mm[u] = m[idx[u]];
+          vv[u] = v[idx[u]];
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {

@@ -37,6 +37,7 @@ struct WgradParams {
   int stages;
   uint32_t tmem_cols;
   float* partial;           // [splits][taps][Cout][Cin]
+  int accumulate;           // 1: every split ADDS into slab 0 (zero on entry) with bulk reduce-add stores
   unsigned long long* trace;   // profiling build: phase timestamps of CTA 0
 };
 
@@ -47,9 +48,13 @@ struct WgradParams {
 // 192 -> 192 launch were these stores).  Now the block is staged in the (by then idle) pipeline shared memory, rows
 // padded by 16 bytes so the row-per-thread 16-byte writes are bank-conflict free, and written out with consecutive
 // threads on consecutive 16 bytes: 512 contiguous bytes per warp store.
+// accumulate: the rows are ADDED to global memory (cp.reduce.async.bulk ... .add.f32: the reduction happens in L2) -- all
+// split-K CTAs of a layer then share ONE [tap][Cout][Cin] slab instead of writing `splits` of them for a later pass
+// to read back (0.8 GB per PHiSeg step, a 0.22 ms reduction alone at the end of backward); a CTA without work skips.
 __device__ __forceinline__ void store_acc_block(uint32_t taddr, int ncols, bool have_acc, float* stage, float* dst,
-                                                size_t ld, int valid_rows, int row, int et,
+                                                size_t ld, int valid_rows, int row, int et, bool accumulate,
                                                 unsigned long long* trace = nullptr) {
+  if (accumulate && !have_acc) return;
   // fixed pitch (128 columns + 16 bytes: bank-conflict-free 16-byte row writes): a thread's staging row is the same
   // private region for every block, so its own wait_group is all the synchronisation the reuse needs
   constexpr int pitch = 128 + 4;
@@ -100,9 +105,15 @@ __device__ __forceinline__ void store_acc_block(uint32_t taddr, int ncols, bool 
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   UZ_TRACE(trace, et == 0 ? 11 : 15);
   if (row < valid_rows) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + static_cast<size_t>(row) * ld),
-                 "r"(uz::smem_u32(srow)), "r"(static_cast<uint32_t>(ncols * 4))
-                 : "memory");
+    if (accumulate)
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                       dst + static_cast<size_t>(row) * ld),
+                   "r"(uz::smem_u32(srow)), "r"(static_cast<uint32_t>(ncols * 4))
+                   : "memory");
+    else
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + static_cast<size_t>(row) * ld),
+                   "r"(uz::smem_u32(srow)), "r"(static_cast<uint32_t>(ncols * 4))
+                   : "memory");
   }
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the staging row may be overwritten again
@@ -236,11 +247,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     if (valid_rows > 128) valid_rows = 128;
     float* stage = reinterpret_cast<float*>(smem);          // pipeline buffers: idle once the accumulators are complete
     for (int tl = 0; tl < ntaps; ++tl) {
-      float* dst = p.partial + ((static_cast<size_t>(split) * p.taps + tap0 + tl) * p.Cout + co0) * p.Cin + ci0;
+      float* dst = p.partial + ((static_cast<size_t>(p.accumulate ? 0 : split) * p.taps + tap0 + tl) * p.Cout + co0) * p.Cin + ci0;
       for (int c0 = 0; c0 < ncin; c0 += 128) {             // column blocks of <= 128 (staging: 128 x 132 floats)
         const int ncols = ncin - c0 < 128 ? ncin - c0 : 128;
         store_acc_block(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tl * p.ci_w + c0, ncols, iters > 0, stage,
-                        dst + c0, p.Cin, valid_rows, row, threadIdx.x - 64,
+                        dst + c0, p.Cin, valid_rows, row, threadIdx.x - 64, p.accumulate != 0,
 #ifdef UZ_PROFILE_KNOBS
                         (tl == 0 && c0 == 0) ? p.trace : nullptr
 #else
@@ -287,6 +298,7 @@ struct Wgrad2Params {
   int a_boxes;
   int stages;
   float* partial;           // [splits][9 * nz][Cout][Cin]
+  int accumulate;           // 1: every split ADDS into slab 0 (zero on entry) with bulk reduce-add stores
 };
 
 constexpr int kW2Pix = 128;                 // 8 rows x 16 pixels
@@ -404,9 +416,9 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
     float* stage = reinterpret_cast<float*>(smem);          // pipeline buffers: idle once the accumulators are complete
     for (int dy = 0; dy < 3; ++dy) {
       const int tap = (dz * 3 + dy) * 3 + dx;      // OI(D)HW order (kd*3 + kh)*3 + kw; dz == 0 in 2-D
-      float* dst = p.partial + ((static_cast<size_t>(split) * 9 * p.nz + tap) * p.Cout + co0) * p.Cin + ci0;
+      float* dst = p.partial + ((static_cast<size_t>(p.accumulate ? 0 : split) * 9 * p.nz + tap) * p.Cout + co0) * p.Cin + ci0;
       store_acc_block(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + dy * 128, nch, my_tiles > 0, stage, dst, p.Cin,
-                      valid_rows, q * 32 + lane, threadIdx.x - 64);
+                      valid_rows, q * 32 + lane, threadIdx.x - 64, p.accumulate != 0);
     }
   }
 
@@ -504,40 +516,61 @@ struct ReduceBatch {
   int n;
 };
 
+// rows (output channels) per work unit: enough bytes per block to amortise its start-up (a unit of one row moved 2.3 KB
+// and the 43 712 blocks of a PHiSeg step ran at 1.3 TB/s), bounded by the shared-memory tile for 27-tap volume layers
+__host__ __device__ inline int reduce_rows_per_unit(int taps) { return taps <= 9 ? 8 : 2; }
+
 __global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const __grid_constant__ ReduceBatch b) {
   uz::pdl_prologue();
-  __shared__ float tile[64 * 27];
+  __shared__ float tile[8 * 64 * 9];             // [rows][64 ci][taps]; 2 rows x 27 taps fits as well
   int lo = 0, hi = b.n - 1;                      // last descriptor whose first unit is <= blockIdx.x (block-uniform)
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (b.d[mid].unit_begin <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
   }
   const UzWgradReduceDesc d = b.d[lo];
+  const int R = reduce_rows_per_unit(d.taps);
   const int unit = blockIdx.x - d.unit_begin;
   const int chunks = (d.Cin + 63) / 64;
-  const int o = unit / chunks, i0 = (unit - o * chunks) * 64;
+  const int o0 = (unit / chunks) * R, i0 = (unit % chunks) * 64;
   const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int i = i0 + lane;
   const size_t slab = static_cast<size_t>(d.CoutP) * d.CinP;
   const size_t split_stride = static_cast<size_t>(d.taps) * slab;
+  const int nrows = d.Cout - o0 < R ? d.Cout - o0 : R;
+  const int ni = d.Cin - i0 < 64 ? d.Cin - i0 : 64;
   if (i < d.Cin) {
-    for (int t = grp; t < d.taps; t += 4) {
-      const float* src = d.partial + static_cast<size_t>(t) * slab + static_cast<size_t>(o) * d.CinP + i;
-      float acc = 0.f;
-      int s = 0;
-      for (; s + 4 <= d.splits; s += 4) {        // four loads in flight, summed in split order
-        const float a0 = src[static_cast<size_t>(s) * split_stride], a1 = src[static_cast<size_t>(s + 1) * split_stride];
-        const float a2 = src[static_cast<size_t>(s + 2) * split_stride], a3 = src[static_cast<size_t>(s + 3) * split_stride];
-        acc = (((acc + a0) + a1) + a2) + a3;
+    constexpr int U = 6;                         // (row, tap) pairs in flight per thread: the loads are 600 ns apiece
+    const int total = nrows * d.taps;
+    for (int rt0 = grp; rt0 < total; rt0 += 4 * U) {
+      float acc[U];
+      int dstidx[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int rt = rt0 + 4 * u;
+        acc[u] = 0.f;
+        dstidx[u] = -1;
+        if (rt < total) {
+          const int r = rt / d.taps, t = rt - r * d.taps;
+          const float* src = d.partial + static_cast<size_t>(t) * slab + static_cast<size_t>(o0 + r) * d.CinP + i;
+          dstidx[u] = (r * ni + lane) * d.taps + t;
+          float a = src[0];                      // splits summed strictly in order
+          for (int s = 1; s < d.splits; ++s) a += src[static_cast<size_t>(s) * split_stride];
+          acc[u] = a;
+        }
       }
-      for (; s < d.splits; ++s) acc += src[static_cast<size_t>(s) * split_stride];
-      tile[lane * d.taps + t] = acc;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (dstidx[u] >= 0) tile[dstidx[u]] = acc[u];
     }
   }
   __syncthreads();
-  const int ni = d.Cin - i0 < 64 ? d.Cin - i0 : 64;
-  float* dst = d.dw + (static_cast<size_t>(o) * d.Cin + i0) * d.taps;
-  for (int e = threadIdx.x; e < ni * d.taps; e += 256) dst[e] = tile[e];
+  // row r of the unit is the contiguous run dw[o0 + r][i0 .. i0 + ni - 1][0 .. taps - 1]
+  const int run = ni * d.taps;
+  for (int e = threadIdx.x; e < nrows * run; e += 256) {
+    const int r = e / run, k = e - r * run;
+    d.dw[(static_cast<size_t>(o0 + r) * d.Cin + i0) * d.taps + k] = tile[e];
+  }
 }
 
 inline int reduce_groups(int splits) { return splits >= 32 ? 8 : (splits >= 16 ? 4 : (splits >= 8 ? 2 : 1)); }
@@ -622,21 +655,25 @@ extern "C" long long uz_wgrad_workspace_floats(int N, int H, int W, int Cin, int
 
 namespace {
 int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout, int taps,
-               int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream, int* splits_out = nullptr);
+               int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream, int* splits_out = nullptr,
+               int accumulate = 0);
 }
 
 // The tensor-core part alone: writes the split-K partial slabs [splits][taps][Cout][Cin] fp32 into `workspace`
 // (uz_wgrad_workspace_floats) and reports the number of splits.  The slabs of many layers are then reduced, transposed to
 // OIHW and written to their gradient tensors by ONE uz_wgrad_reduce_batched launch.  D == 0: images, D > 0: volumes (27 taps).
 extern "C" int uz_conv_wgrad_partial(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W,
-                                     int Cin, int Cout, int taps, float* workspace, int* splits, void* stream) {
+                                     int Cin, int Cout, int taps, float* workspace, int accumulate, int* splits,
+                                     void* stream) {
   UZ_CHECK_ARG(splits, "uz_conv_wgrad_partial: null pointer");
   UZ_CHECK_ARG(D == 0 ? (taps == 9 || taps == 1) : taps == 27, "uz_conv_wgrad_partial: taps %d with D %d", taps, D);
-  return wgrad_impl(x, ldx, dy, lddy, N, D, H, W, Cin, Cout, taps, Cin, Cout, workspace, nullptr, stream, splits);
+  return wgrad_impl(x, ldx, dy, lddy, N, D, H, W, Cin, Cout, taps, Cin, Cout, workspace, nullptr, stream, splits,
+                    accumulate ? 1 : 0);
 }
 
-extern "C" int uz_wgrad_reduce_units(int Cout_logical, int Cin_logical) {
-  return Cout_logical * ((Cin_logical + 63) / 64);
+extern "C" int uz_wgrad_reduce_units(int Cout_logical, int Cin_logical, int taps) {
+  const int R = reduce_rows_per_unit(taps);
+  return ((Cout_logical + R - 1) / R) * ((Cin_logical + 63) / 64);
 }
 
 // descs: n <= UZ_WGRAD_REDUCE_MAX_ROWS rows in HOST memory (copied into the launch parameters); unit_begin is filled in
@@ -654,7 +691,7 @@ extern "C" int uz_wgrad_reduce_batched(const UzWgradReduceDesc* descs, int n, vo
                      b.d[k].Cout > 0 && b.d[k].Cin > 0 && b.d[k].Cout <= b.d[k].CoutP && b.d[k].Cin <= b.d[k].CinP,
                  "uz_wgrad_reduce_batched: bad row %d", k);
     b.d[k].unit_begin = units;
-    units += uz_wgrad_reduce_units(b.d[k].Cout, b.d[k].Cin);
+    units += uz_wgrad_reduce_units(b.d[k].Cout, b.d[k].Cin, b.d[k].taps);
   }
   uz::launch(wgrad_reduce_batched_kernel, dim3(units, 1, 1), 256, 0, static_cast<cudaStream_t>(stream), b);
   UZ_CHECK_LAUNCH("uz_wgrad_reduce_batched");
@@ -680,8 +717,10 @@ extern "C" int uz_conv3d_wgrad(const void* x, int ldx, const void* dy, int lddy,
 namespace {
 // splits_out != nullptr: only the tensor-core kernel runs; the partial slabs stay in `workspace` for uz_wgrad_reduce_batched
 int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, int H, int W, int Cin, int Cout, int taps,
-               int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream, int* splits_out) {
+               int Cin_logical, int Cout_logical, float* workspace, float* dw, void* stream, int* splits_out,
+               int accumulate) {
   UZ_CHECK_ARG(x && dy && workspace && (dw || splits_out), "uz_conv_wgrad: null pointer");
+  UZ_CHECK_ARG(!accumulate || splits_out, "uz_conv_wgrad: accumulation needs the deferred reduction");
   UZ_CHECK_ARG(Cin % 16 == 0 && Cout % 16 == 0 && Cin > 0 && Cout > 0 && Cin <= 512,
                "uz_conv_wgrad: channels must be multiples of 16, Cin <= 512 (got %d, %d)", Cin, Cout);
   UZ_CHECK_ARG(ldx % 8 == 0 && lddy % 8 == 0 && ldx >= Cin && lddy >= Cout, "uz_conv_wgrad: bad pixel strides");
@@ -690,6 +729,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
   Plan2 pl2;
   if (make_plan2(N, D, H, W, Cin, Cout, taps, &pl2)) {
     pl2.p.partial = workspace;
+    pl2.p.accumulate = accumulate;
     const uint64_t Dd = static_cast<uint64_t>(pl2.p.D);
     CUtensorMap tdy2, tx2;
     {
@@ -724,7 +764,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
     dim3 grid2(pl2.splits, pl2.p.co_blocks * 3 * pl2.p.nz * pl2.p.ci_chunks, 1);
     uz::launch(wgrad_tc2_kernel, grid2, kThreads, pl2.smem, static_cast<cudaStream_t>(stream), tdy2, tx2, pl2.p);
     UZ_CHECK_LAUNCH("uz_conv_wgrad(v2)");
-    if (splits_out) { *splits_out = pl2.splits; return UZ_OK; }
+    if (splits_out) { *splits_out = accumulate ? 1 : pl2.splits; return UZ_OK; }
     const size_t total2 = static_cast<size_t>(Cout_logical) * Cin_logical;     // one thread per (o, i) pair
     const int G2 = reduce_groups(pl2.splits);
     int blocks2 = static_cast<int>((total2 + 256 / G2 - 1) / (256 / G2));
@@ -739,6 +779,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
   int rc = make_plan(N, H, W, Cin, Cout, taps, &pl);
   UZ_CHECK_ARG(rc == UZ_OK, "uz_conv_wgrad: no plan for Cin=%d Cout=%d", Cin, Cout);
   pl.p.partial = workspace;
+  pl.p.accumulate = accumulate;
 #ifdef UZ_PROFILE_KNOBS
   pl.p.trace = uz::g_trace;
 #endif
@@ -778,7 +819,7 @@ int wgrad_impl(const void* x, int ldx, const void* dy, int lddy, int N, int D, i
   dim3 grid(pl.splits, pl.p.tap_groups * pl.co_blocks * pl.p.ci_chunks, 1);
   uz::launch(kernel, grid, kThreads, pl.smem, static_cast<cudaStream_t>(stream), tdy, tx, pl.p);
   UZ_CHECK_LAUNCH("uz_conv_wgrad");
-  if (splits_out) { *splits_out = pl.splits; return UZ_OK; }
+  if (splits_out) { *splits_out = accumulate ? 1 : pl.splits; return UZ_OK; }
   const size_t total = static_cast<size_t>(Cout_logical) * Cin_logical;       // one thread per (o, i) pair
   const int G1 = reduce_groups(pl.splits);
   int blocks = static_cast<int>((total + 256 / G1 - 1) / (256 / G1));

@@ -136,7 +136,9 @@ def test_conditioned_forward_and_loss_terms(training, precision):
         assert rel_logits < 4e-3 and rel_logits < 1.5 * gap + 5e-4
         assert tot_err < 3e-3
         assert kl_err < 1e-2 and ce_err < 1e-2
-    assert rel_emu < 4e-3
+    # distance to the oracle that rounds where the kernels round: 2.0e-3 ... 5.0e-3 (bf16), 2.0e-4 ... 2.5e-4 (fp16) over
+    # several conditioning runs (the oracle's own cuDNN training of the fixture is not bit-reproducible)
+    assert rel_emu < (7e-3 if precision == 'bf16' else 1e-3)
 
 
 def test_conditioned_gradients():

@@ -339,8 +339,9 @@ def conv_wgrad(x, dy, taps, cin_logical, cout_logical, out=None, defer=False):
         raise _lib.UnetZooLibError('uz_conv_wgrad: unsupported shape Cin=%d Cout=%d' % (cin, cout))
     dw = out if out is not None else torch.empty((cout_logical, cin_logical, taps), dtype=torch.float32, device=x.device)
     if defer:
-        # split-K CTAs add into ONE slab through L2 (bulk reduce-add) unless the run has to be bit-reproducible
-        acc = _WGRAD_ACCUMULATE and not _DETERMINISTIC
+        # split-K CTAs add into ONE slab through L2 (bulk reduce-add) unless the run has to be bit-reproducible; volumes
+        # keep the slabs (few parameters, thousands of pixel tiles: 45.8 ms per PHISeg3D step with slabs, 46.9 ms without)
+        acc = _WGRAD_ACCUMULATE and not _DETERMINISTIC and not vol
         work = torch.zeros((taps * cout * cin,), dtype=torch.float32, device=x.device) if acc else \
             torch.empty((ws,), dtype=torch.float32, device=x.device)
         splits = ctypes.c_int(0)

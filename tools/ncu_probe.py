@@ -90,7 +90,62 @@ def memops():
     return run
 
 
+def fused_small(h):
+    """conv + BatchNorm + ReLU in one cluster launch (uz_conv_bn_act_fused), 192 -> 192 at h x h x 12"""
+    x = act(h, 192)
+    w = torch.randn(192, 192, 3, 3, device='cuda') * 0.05
+    wf, _ = kern.pack_conv_weight(w, need_dgrad=False)
+    z, o = torch.zeros(192, device='cuda'), torch.ones(192, device='cuda')
+    rm, rv = torch.zeros(192, device='cuda'), torch.ones(192, device='cuda')
+    return lambda: kern.conv_bn_act_fused(x, wf, z, o, z, rm, rv)
+
+
+def bn_cluster(c, h):
+    """BatchNorm + ReLU backward in one cluster launch (uz_bn_bwd_fused)"""
+    y, d = act(h, c), act(h, c)
+    g, b = torch.ones(c, device='cuda'), torch.zeros(c, device='cuda')
+    return lambda: kern.bn_relu_bwd_train(d, y, g, b, g, b, g)
+
+
+def optimizer():
+    """fused Adam + bf16 weight packing (uz_adam_pack_step) on 16 layers of 192 -> 192 x 3 x 3, gradients from split-K
+    slabs reduced by the batched kernel (uz_wgrad_reduce_batched) for half of them"""
+    from b200.optim import FusedAdam
+    ws = [torch.nn.Parameter(torch.randn(192, 192, 3, 3, device='cuda') * 0.05) for _ in range(16)]
+    pk = kern.WeightPacker(ws)
+    opt = FusedAdam(ws, lr=1e-3, weight_decay=1e-5)
+    opt.attach_packer(pk)
+    x, dy = act(16, 192), act(16, 192)
+
+    def run():
+        for k, w in enumerate(ws):
+            w.grad = kern.conv_wgrad(x, dy, 9, 192, 192, defer=True).view(192, 192, 3, 3)
+        kern.wgrad_reducer.flush()
+        opt.step()
+    return run
+
+
+def kl_hier():
+    lv = []
+    for l in range(5):
+        r = 4 << l
+        mk = lambda pos: (torch.rand(B, 2, r, r, device='cuda') + 0.1) if pos else torch.randn(B, 2, r, r, device='cuda')
+        lv.append((mk(False), mk(True), mk(False), mk(True)))
+    up = torch.ones(1, device='cuda')
+
+    def run():
+        kern.kl_hierarchy_fwd(lv, [4.0 ** i for i in range(5)], 1.0)
+        kern.kl_hierarchy_bwd(lv, [4.0 ** i for i in range(5)], 1.0, up)
+    return run
+
+
 PROBES = {
+    'fused_8x8': lambda: fused_small(8),
+    'fused_2x2': lambda: fused_small(2),
+    'bn_cluster_16': lambda: bn_cluster(192, 16),
+    'bn_cluster_4': lambda: bn_cluster(192, 4),
+    'optimizer': optimizer,
+    'kl_hier': kl_hier,
     'eval_tail': eval_tail,
     'heads': heads,
     'memops': memops,

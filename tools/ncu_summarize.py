@@ -99,7 +99,7 @@ def main(paths):
                                             'sm__cycles_elapsed.max (counts UTCHMMA)'}
     json.dump(out, open(os.path.join(ROOT, 'profiles', 'r02_ncu_summary.json'), 'w'), indent=1)
     open(os.path.join(ROOT, 'profiles', 'r02_ncu_kernels.md'), 'w').write(
-        '# ncu --set full, one warm launch per kernel family (round 2)\n\n`bash tools/gpu_probe_r2b.sh` on a B200; batch 12 shapes of '
+        '# ncu --set full, one warm launch per kernel family (round 2)\n\n`bash tools/gpu_probe_r2c.sh` on a B200 (final round-2 code); batch 12 shapes of '
         'PHiSeg-7/5 (tools/ncu_probe.py).  Durations under ncu are cold-cache and serialised (clock control off): use them '
         'for DRAM bytes / counters, the in-step times are in `r02_layer_times_singlestream.txt` and the bench line.\n'
         'Tensor pipe active = `sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg` / 4 / `sm__cycles_elapsed.max` '

@@ -9,9 +9,14 @@ hi = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
 hdr = rows[hi]
 ik, iv = hdr.index('Kernel Name'), hdr.index('Metric Value')
 data = [(r[ik], float(r[iv].replace(',', ''))) for r in rows[hi + 1:] if len(r) > iv]
-# a training step starts with the batched weight packing: take everything from its last occurrence
-starts = [i for i, (k, _) in enumerate(data) if 'pack_weight_batched_kernel' in k]
-step = data[starts[-1]:] if starts else data[len(data) - len(data) // nsteps:]
+# a training step ends with the fused optimizer launch (adam_pack_kernel; adam_batched_kernel before round 2c): take the
+# launches between the last two of them
+ends = [i for i, (k, _) in enumerate(data) if 'adam_pack_kernel' in k] or \
+    [i for i, (k, _) in enumerate(data) if 'adam_batched_kernel' in k]
+if len(ends) >= 2:
+    step = data[ends[-2] + 1:ends[-1] + 1]
+else:
+    step = data[len(data) - len(data) // nsteps:]
 agg = collections.defaultdict(lambda: [0, 0.0])
 for k, v in step:
     k = k.split('(')[0].replace('void ', '').replace('<unnamed>::', '')

@@ -131,9 +131,10 @@ def test_conditioned_forward_and_loss_terms(training, precision):
         assert tot_err < 1e-3
         assert kl_err < 1e-3 and ce_err < 1e-3
     else:
-        # bf16 storage, measured over several conditioning runs: logits 1.6e-3 ... 2.3e-3, ELBO 1.7e-4 ... 1.3e-3, level terms
-        # <= 5.4e-3 -- the rounding-emulating ORACLE is as far from fp32 as the kernels are (``gap``)
-        assert rel_logits < 4e-3 and rel_logits < 1.5 * gap + 5e-4
+        # bf16 storage, measured over several conditioning runs: logits 1.5e-3 ... 1.8e-3 (train), 2.3e-3 ... 4.1e-3 (eval), ELBO
+        # 1.7e-4 ... 1.3e-3, level terms <= 5.4e-3 -- the rounding-emulating ORACLE is as far from fp32 as the kernels are
+        # (``gap``: 1.6e-3 train, 2.4e-3 ... 3.6e-3 eval); the binding criterion is the one relative to that gap
+        assert rel_logits < 6e-3 and rel_logits < 1.5 * gap + 5e-4
         assert tot_err < 3e-3
         assert kl_err < 1e-2 and ce_err < 1e-2
     # distance to the oracle that rounds where the kernels round: 2.0e-3 ... 5.0e-3 (bf16), 2.0e-4 ... 2.5e-4 (fp16) over

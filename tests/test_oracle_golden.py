@@ -140,3 +140,29 @@ def test_reversible_oracle_gradients_and_double_running_stat_update(golden_dir):
     k = str(g['train_running_var_probe_key'])
     np.testing.assert_allclose(sd[k].detach().numpy(), g['train_running_var_probe'], rtol=1e-5)
     assert int(sd[k.replace('running_var', 'num_batches_tracked')]) == int(g['train_num_batches_tracked_probe']) == 5
+
+
+@pytest.mark.skipif(not have_reference(), reason='/root/reference only exists in the build container')
+@pytest.mark.parametrize('reversible', [False, True])
+def test_checkpoint_round_trip_with_the_reference(tmp_path, reversible):
+    """a `.pth` written by the reference (`torch.save(net.state_dict())`, train_model.py:558-564) loads
+    into the drop-in module with strict=True, and a checkpoint written by the drop-in loads back into the reference --
+    same keys, shapes, dtypes and values in both directions (host-side: no kernel involved)."""
+    from oracle.ref_run import build_reference_phiseg
+    from tests.keygrammar import dropin_phiseg
+    filters = [32, 64, 96, 32, 64, 32, 64]      # reversible halves must be multiples of 16 on the B200 path
+    ref = build_reference_phiseg(filters, reversible=reversible)
+    ref.load_state_dict(synth.synth_state_dict(ref.state_dict(), seed=21))
+    path = tmp_path / 'reference.pth'
+    torch.save(ref.state_dict(), path)
+    ours = dropin_phiseg(filters, reversible=reversible)
+    missing, unexpected = ours.load_state_dict(torch.load(path), strict=True)
+    assert not missing and not unexpected
+    for (k, v), (k2, v2) in zip(ref.state_dict().items(), ours.state_dict().items()):
+        assert k == k2 and v.dtype == v2.dtype and torch.equal(v, v2), k
+    back = tmp_path / 'dropin.pth'
+    torch.save(ours.state_dict(), back)
+    ref2 = build_reference_phiseg(filters, reversible=reversible)
+    ref2.load_state_dict(torch.load(back), strict=True)
+    for (k, v), (_, v2) in zip(ref.state_dict().items(), ref2.state_dict().items()):
+        assert torch.equal(v, v2), k

@@ -240,6 +240,12 @@ int uz_conv_bn_act_fused(const void* x, int N, int H, int W, int Cin, int ldx, c
                          float* running_mean, float* running_var, int stat_updates, int relu, void* y, int ldy, void* a,
                          int lda, float* scale_out, float* shift_out, float* mean_out, float* invstd_out, void* stream);
 
+/* The same backward for LARGE maps as one COOPERATIVE launch: a single-wave grid accumulates the sums (fp32 atomics into
+ * sums[2][C], zero on entry), crosses a grid-wide barrier and writes dy, re-reading dout / y from L2. */
+int uz_bn_bwd_coop(const void* dout, int ldd, const void* y, int ldy, const float* scale, const float* shift, int relu,
+                   float* sums, float count, const float* gamma, const float* mean, const float* invstd, float* dgamma,
+                   float* dbeta, void* dy, int lddy, long long npix, int C, void* stream);
+
 /* Eval-mode fold of conv bias + BatchNorm running stats into the conv epilogue's scale / shift (train_model.py:139). */
 int uz_bn_eval_fold(const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
                     const float* running_var, float eps, int C, float* scale, float* shift, void* stream);

@@ -389,3 +389,36 @@ def test_conv_bn_relu_cluster_kernel(N, H, W, Cin, Cout, taps):
     assert float(err.max()) <= 2 ** -7 * float(ref.abs().max()) + 1e-3
     conv_ref = F.conv2d(to_nchw(x), w, bias, padding=ks // 2)
     assert rel_err(yq, conv_ref) < 5e-3
+
+
+@pytest.mark.parametrize('N,H,W,C,ld', [(12, 64, 64, 64, 96), (12, 128, 128, 32, 32), (2, 128, 128, 128, 128), (3, 70, 66, 48, 48)])
+def test_bn_backward_cooperative_kernel(N, H, W, C, ld):
+    """uz_bn_bwd_coop (sums + grid-wide barrier + apply in ONE cooperative launch, large maps) against autograd through
+    F.batch_norm(training=True) + ReLU in fp32 and against the two-launch path."""
+    k = kern()
+    ybuf = to_nhwc(bf16r(_rand(N, ld, H, W, seed=11)))
+    y = ybuf[..., :C]
+    gamma = (1 + 0.1 * _rand(C, seed=3)).requires_grad_(True)
+    beta = (0.1 * _rand(C, seed=4)).requires_grad_(True)
+    yq = to_nchw(y.contiguous()).requires_grad_(True)
+    ref = F.relu(F.batch_norm(yq, None, None, gamma, beta, True, 0.01, 1e-3))
+    da = bf16r(_rand(N, C, H, W, seed=7))
+    ref.backward(da)
+    mean = yq.detach().mean((0, 2, 3))
+    invstd = (yq.detach().var((0, 2, 3), unbiased=False) + 1e-3).rsqrt()
+    scale = gamma.detach() * invstd
+    shift = beta.detach() - mean * scale
+    dout = to_nhwc(da)
+    prev, prev_min = k._BN_BWD_COOP, k._BN_BWD_COOP_MIN_PIX
+    try:
+        k._BN_BWD_COOP, k._BN_BWD_COOP_MIN_PIX = True, 1
+        dy, dgamma, dbeta = k.bn_relu_bwd_train(dout, y, scale, shift, gamma.detach(), mean, invstd)
+        k._BN_BWD_COOP = False
+        dy_u, dgamma_u, dbeta_u = k.bn_relu_bwd_train(dout, y, scale, shift, gamma.detach(), mean, invstd)
+    finally:
+        k._BN_BWD_COOP, k._BN_BWD_COOP_MIN_PIX = prev, prev_min
+    assert rel_err(to_nchw(dy), yq.grad) < 6e-3
+    torch.testing.assert_close(dgamma, gamma.grad, rtol=2e-4, atol=2e-4 * float(gamma.grad.abs().max()))
+    torch.testing.assert_close(dbeta, beta.grad, rtol=2e-4, atol=2e-4 * float(beta.grad.abs().max()))
+    torch.testing.assert_close(dgamma, dgamma_u, rtol=2e-4, atol=2e-4 * float(dgamma_u.abs().max()))
+    assert float((dy.float() - dy_u.float()).abs().max()) <= 2 ** -7 * float(dy_u.float().abs().max())

@@ -426,6 +426,10 @@ _BN_BWD_FUSED = _os.environ.get('UNETZOO_BN_BWD_FUSED', '1') != '0'
 # in the captured step (gpurun_out/r2c_tl_*.json) the cluster kernel wins up to 16x16x12 pixels (4.9 vs 6.1 us at 2x2,
 # 7.3 vs 8.9 us at 16x16) and loses from 32x32x12 on (13-15 vs 11.6 us)
 _BN_BWD_FUSED_MAX_PIX = int(_os.environ.get('UNETZOO_BN_BWD_FUSED_MAX_PIX', '3072'))
+# one cooperative launch (sums, grid-wide barrier, apply) for large maps: correct, but a cooperative grid waits until the
+# whole GPU can take it -- in the multi-stream step that serialises the backward streams: 4.33 vs 4.08 ms -> opt-in
+_BN_BWD_COOP = _os.environ.get('UNETZOO_BN_BWD_COOP', '0') == '1'
+_BN_BWD_COOP_MIN_PIX = int(_os.environ.get('UNETZOO_BN_BWD_COOP_MIN_PIX', '49152'))
 
 
 def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True, sums=None, inverse=None):
@@ -443,6 +447,14 @@ def bn_relu_bwd_train(dout, y, scale, shift, gamma, mean, invstd, relu=True, sum
         dy = _like(y, c)
         _lib.call('uz_bn_bwd_fused', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), float(npix), _p(gamma),
                   _p(mean), _p(invstd), _p(dgb[0]), _p(dgb[1]), _p(dy), c, npix, c, _stream())
+        return dy, dgb[0], dgb[1]
+    if sums is None and inverse is None and _BN_BWD_COOP and npix >= _BN_BWD_COOP_MIN_PIX and c <= 1024:
+        # large maps: sums + apply in one cooperative launch (grid-wide barrier in between)
+        sums = zero_arena.get(2 * c, dev)
+        dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+        dy = _like(y, c)
+        _lib.call('uz_bn_bwd_coop', _p(dout), ldd, _p(y), ldy, _p(scale), _p(shift), int(relu), _p(sums), float(npix),
+                  _p(gamma), _p(mean), _p(invstd), _p(dgb[0]), _p(dgb[1]), _p(dy), c, npix, c, _stream())
         return dy, dgb[0], dgb[1]
     if sums is None:
         sums = zero_arena.get(2 * c, dev)

@@ -247,3 +247,185 @@ extern "C" int uz_bn_bwd_fused(const void* dout, int ldd, const void* y, int ldy
   UZ_CHECK_LAUNCH("uz_bn_bwd_fused");
   return UZ_OK;
 }
+
+
+// ---------------------------------------------------------------- large maps: one COOPERATIVE launch
+// Maps too large for a cluster (64x64x12 pixels and up) used two launches -- sums, then apply -- each of them a 6-12 us
+// kernel that streams 25-50 MB: mostly launch + ramp-up + tail.  Here a single-wave cooperative grid does both passes with
+// a grid-wide barrier in between; the second pass re-reads dout / y from L2 (the tensors of all but the 128-channel layers
+// fit).  The per-channel sums are accumulated with fp32 atomics like in the two-launch path.
+namespace {
+
+struct BnCoopParams {
+  const __nv_bfloat16* dout; int ldd;
+  const __nv_bfloat16* y; int ldy;
+  const float* scale; const float* shift;
+  const float* gamma; const float* mean; const float* invstd;
+  float* sums;                 // [2][C], zero on entry
+  float* dgamma; float* dbeta;
+  __nv_bfloat16* dy; int lddy;
+  int relu, C;
+  long long npix;
+  float count;
+};
+
+// <= 64 registers: two of these grids (2 blocks per SM each) are co-resident, e.g. the two encoders' backward streams
+__global__ void __launch_bounds__(256, 4) bn_bwd_coop_kernel(const BnCoopParams p) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ float sm[];                       // pass 1: [rows][2][C] partial sums; pass 2: [3][C] coefficients
+  const int C = p.C;
+  const int chunks = C / 8;
+  const int rows = blockDim.x / chunks;
+  const int r = threadIdx.x / chunks;
+  const int c0 = (threadIdx.x - r * chunks) * 8;
+  const bool active = r < rows;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = active ? p.scale[c0 + j] : 0.f; sh[j] = active ? p.shift[c0 + j] : 0.f; }
+  const size_t npix = static_cast<size_t>(p.npix);
+  const size_t pstride = static_cast<size_t>(gridDim.x) * rows;
+  // ---- pass 1: sum g, sum g*y with g = dout * [ReLU active]
+  {
+    float sg[8], sgy[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sgy[j] = 0.f; }
+    if (active) {
+      auto one = [&](const uint4& vg, const uint4& vy) {
+        float g[8], yy[8];
+        unpack8(vg, g);
+        unpack8(vy, yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float m = (!p.relu || fmaf(yy[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
+          sg[j] += m;
+          sgy[j] = fmaf(m, yy[j], sgy[j]);
+        }
+      };
+      size_t pix = static_cast<size_t>(blockIdx.x) * rows + r;
+      for (; pix + 3 * pstride < npix; pix += 4 * pstride) {
+        uint4 vg[4], vy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          vg[u] = *reinterpret_cast<const uint4*>(p.dout + (pix + u * pstride) * p.ldd + c0);
+          vy[u] = *reinterpret_cast<const uint4*>(p.y + (pix + u * pstride) * p.ldy + c0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) one(vg[u], vy[u]);
+      }
+      for (; pix < npix; pix += pstride)
+        one(*reinterpret_cast<const uint4*>(p.dout + pix * p.ldd + c0), *reinterpret_cast<const uint4*>(p.y + pix * p.ldy + c0));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sm[(r * 2) * C + c0 + j] = sg[j];
+        sm[(r * 2 + 1) * C + c0 + j] = sgy[j];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float acc = 0.f;
+      for (int rr = 0; rr < rows; ++rr) acc += sm[rr * 2 * C + i];
+      atomicAdd(p.sums + i, acc);
+    }
+  }
+  __threadfence();
+  grid.sync();
+  // ---- pass 2: dy = A*g + B*y + Cc
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float tsg = __ldcg(p.sums + c), tsgy = __ldcg(p.sums + C + c);
+    const float mu = p.mean[c], is = p.invstd[c], gm = p.gamma ? p.gamma[c] : 1.f;
+    const float sgx = (tsgy - mu * tsg) * is;
+    const float mg = tsg / p.count, mgx = sgx / p.count;
+    sm[c] = gm * is;
+    sm[C + c] = -gm * is * is * mgx;
+    sm[2 * C + c] = -gm * is * mg + gm * is * is * mgx * mu;
+    if (blockIdx.x == 0) {
+      if (p.dgamma) p.dgamma[c] = sgx;
+      if (p.dbeta) p.dbeta[c] = tsg;
+    }
+  }
+  __syncthreads();
+  if (active) {
+    float ca[8], cb[8], cc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ca[j] = sm[c0 + j]; cb[j] = sm[C + c0 + j]; cc[j] = sm[2 * C + c0 + j]; }
+    auto two = [&](const uint4& vg, const uint4& vy, size_t px) {
+      float g[8], yy[8];
+      unpack8(vg, g);
+      unpack8(vy, yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float m = (!p.relu || fmaf(yy[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
+        g[j] = fmaf(ca[j], m, fmaf(cb[j], yy[j], cc[j]));
+      }
+      *reinterpret_cast<uint4*>(p.dy + px * p.lddy + c0) = pack8(g);
+    };
+    // same pixel assignment as pass 1: a block re-reads what it just read (L2, partly L1)
+    size_t pix = static_cast<size_t>(blockIdx.x) * rows + r;
+    for (; pix + 3 * pstride < npix; pix += 4 * pstride) {
+      uint4 vg[4], vy[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vg[u] = *reinterpret_cast<const uint4*>(p.dout + (pix + u * pstride) * p.ldd + c0);
+        vy[u] = *reinterpret_cast<const uint4*>(p.y + (pix + u * pstride) * p.ldy + c0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) two(vg[u], vy[u], pix + u * pstride);
+    }
+    for (; pix < npix; pix += pstride)
+      two(*reinterpret_cast<const uint4*>(p.dout + pix * p.ldd + c0), *reinterpret_cast<const uint4*>(p.y + pix * p.ldy + c0), pix);
+  }
+}
+
+}  // namespace
+
+// BatchNorm(train)+ReLU backward of a LARGE map in one cooperative launch; sums: [2][C] floats, zero on entry.
+extern "C" int uz_bn_bwd_coop(const void* dout, int ldd, const void* y, int ldy, const float* scale, const float* shift,
+                              int relu, float* sums, float count, const float* gamma, const float* mean,
+                              const float* invstd, float* dgamma, float* dbeta, void* dy, int lddy, long long npix, int C,
+                              void* stream) {
+  UZ_CHECK_ARG(dout && y && scale && shift && sums && mean && invstd && dy, "uz_bn_bwd_coop: null pointer");
+  UZ_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && ldd % 8 == 0 && ldy % 8 == 0 && lddy % 8 == 0 && npix > 0,
+               "uz_bn_bwd_coop: bad arguments");
+  UZ_CHECK_ARG(((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0,
+               "uz_bn_bwd_coop: pointers must be 16-byte aligned");
+  BnCoopParams p{};
+  p.dout = static_cast<const __nv_bfloat16*>(dout); p.ldd = ldd;
+  p.y = static_cast<const __nv_bfloat16*>(y); p.ldy = ldy;
+  p.scale = scale; p.shift = shift; p.gamma = gamma; p.mean = mean; p.invstd = invstd;
+  p.sums = sums; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.dy = static_cast<__nv_bfloat16*>(dy); p.lddy = lddy;
+  p.relu = relu; p.C = C; p.npix = npix; p.count = count;
+  const int chunks = C / 8;
+  int threads = 256;
+  if (chunks > threads) threads = ((chunks + 31) / 32) * 32;
+  const int rows = threads / chunks;
+  size_t smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);
+  if (smem < static_cast<size_t>(3) * C * sizeof(float)) smem = static_cast<size_t>(3) * C * sizeof(float);
+  UZ_CHECK_ARG(smem <= 48 * 1024 && threads <= 256, "uz_bn_bwd_coop: C = %d too wide", C);
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_coop_kernel, threads, smem);
+  if (e != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    uz::set_error("uz_bn_bwd_coop: occupancy query failed");
+    return UZ_ERR_CUDA;
+  }
+  if (per_sm > 2) per_sm = 2;
+  long long blocks = static_cast<long long>(per_sm) * uz::num_sms();
+  const long long need = (npix + rows - 1) / rows;
+  if (blocks > need) blocks = need;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(blocks), 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, bn_bwd_coop_kernel, p);
+  (void)e;
+  UZ_CHECK_LAUNCH("uz_bn_bwd_coop");
+  return UZ_OK;
+}

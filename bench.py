@@ -504,6 +504,13 @@ def main():
             res = ev.run_host(img, lab)
         k_eval = max(3, min(args.steps, 10))
         t_ms = timed_region(lambda i: ev.run_host(img, lab), k_eval, world, device) / k_eval
+        # the same with the weight packing / BatchNorm folds hoisted out of the per-image call (a validation pass runs many
+        # images on unchanged parameters, train_model.py:150-222): reported beside the per-call number, not instead of it
+        ev_s = train.EvalStep(net_e, N_SAMPLES, 2, shard=(rank, world), images_per_step=world, static_weights=True)
+        for _ in range(2):
+            ev_s.run_host(img, lab)
+        t_ms_static = timed_region(lambda i: ev_s.run_host(img, lab), k_eval, world, device) / k_eval
+        del ev_s
         fg = None
         if rank == 0:
             # foreground fraction of the argmax masks of image 0 (a degenerate all-background set would skip the popcounts)
@@ -513,6 +520,7 @@ def main():
             fg = float(cnt.float().mean().item()) / (IMAGE[1] * IMAGE[2])
         eval_block = {'metric': 'PHiSeg GED-100 eval images/s (100 samples, 4 annotators, GED + NCC + Dice)',
                       'value': world * 1000.0 / t_ms, 'unit': 'images/s', 'ms_per_call': t_ms, 'images_per_call': world,
+                      'value_static_weights': world * 1000.0 / t_ms_static, 'ms_per_call_static_weights': t_ms_static,
                       'ged': float(res[0, 0]), 'ncc': float(res[0, 1]), 'dice': [float(v) for v in res[0, 2:]],
                       'foreground_fraction_of_samples': fg, 'samples_per_rank': ev.counts or [N_SAMPLES],
                       'launches_per_call': int(getattr(ev, 'launches_per_step', 0)),

@@ -96,6 +96,24 @@ def test_fused_equals_unfused_evalstep():
         torch.randn_like = orig
     assert a[0] == b[0] == c[0]
     assert abs(a[1] - b[1]) < 1e-5 and a[1] == c[1]
+    # static_weights: weight packing / BatchNorm folds once instead of per call -- same numbers; after the parameters
+    # change, refresh_weights() brings the copies up to date
+    torch.randn_like = _fake_noise()
+    try:
+        st = train.EvalStep(net, 16, 2, use_graph=True, fused=True, static_weights=True)
+        d = st.run_host(img, lab)
+        assert d == c
+        with torch.no_grad():
+            for p in net.parameters():
+                p.mul_(1.01)
+        st.refresh_weights()
+        torch.randn_like = _fake_noise()
+        e = st.run_host(img, lab)
+        torch.randn_like = _fake_noise()
+        f = train.EvalStep(net, 16, 2, use_graph=True, fused=True).run_host(img, lab)
+    finally:
+        torch.randn_like = orig
+    assert e == f and e != d
 
 
 def _rank_main(rank, world, port, q):

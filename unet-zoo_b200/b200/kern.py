@@ -496,11 +496,14 @@ class BNFolder:
         self.n = len(units)
         self.table = torch.frombuffer(bytearray(b''.join(rows)), dtype=torch.uint8).to(dev)
         self.ptr0 = units[0][3].data_ptr()
+        self.external = False       # True: somebody (EvalStep with static weights) refreshes explicitly; per-forward no-op
 
     def valid_for(self, rm_first):
         return rm_first.data_ptr() == self.ptr0
 
-    def refresh(self, eps=BN_EPS):
+    def refresh(self, eps=BN_EPS, force=False):
+        if self.external and not force:
+            return
         _lib.call('uz_bn_eval_fold_batched', _p(self.table), self.n, self.maxc, eps, _stream())
 
 

@@ -208,8 +208,12 @@ class EvalStep:
     module API and the drop-in ``utils`` functions (full-resolution logits, softmax tensor, argmax)."""
 
     def __init__(self, net, n_samples=100, n_classes=2, shard=None, dedup=True, use_graph=True, images_per_step=1,
-                 fused=True, gather_results=False):
+                 fused=True, gather_results=False, static_weights=False):
         self.net = net
+        # static_weights: the parameters do not change between calls (one validation pass over many images,
+        # train_model.py:150-222): the bf16 weight packing and the BatchNorm folds run ONCE (``refresh_weights()``, also
+        # called by the first run) instead of inside every call; call ``refresh_weights()`` again after an optimizer step
+        self.static_weights = static_weights and hasattr(net, '_packer') and hasattr(net, '_folder')
         self.dedup = dedup
         self.use_graph = use_graph
         self.fused = fused and dedup
@@ -289,7 +293,24 @@ class EvalStep:
             for i in range(I):
                 self.out[i].copy_(self.out_all[i % self.world, i])
 
+    def refresh_weights(self):
+        """re-pack the bf16 tensor-core weight copies and re-fold the BatchNorm running statistics (static_weights mode)"""
+        if self.static_weights:
+            self.net._packer().refresh(force=True)
+            self.net._folder().refresh(force=True)
+
     def _device_body(self):
+        if not self.static_weights:
+            return self._device_body_inner()
+        pk, fd = self.net._packer(), self.net._folder()
+        prev = (pk.external, fd.external)
+        pk.external, fd.external = True, True          # refreshed by refresh_weights(), not by every forward
+        try:
+            return self._device_body_inner()
+        finally:
+            pk.external, fd.external = prev
+
+    def _device_body_inner(self):
         if self.fused:
             return self._fused_body()
         # results into self.out (double [1, 2] = GED, NCC); no host synchronisation
@@ -321,6 +342,7 @@ class EvalStep:
         self.sums = torch.zeros((I, 2, C, H * W), dtype=torch.float32, device=dev)
         self.img.copy_(image.reshape(I, H, W))
         self.lab.copy_(labels.reshape(self.lab.shape))
+        self.refresh_weights()
         if self.use_graph:
             s = torch.cuda.Stream(device=dev)
             s.wait_stream(torch.cuda.current_stream())

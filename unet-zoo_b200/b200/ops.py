@@ -48,9 +48,9 @@ def _dense(t):
 import os as _os
 
 _AUX_ENABLED = _os.environ.get('UNETZOO_CONCURRENCY', '1') != '0'
-# planned SM share of an overlapped wgrad: 50 % (25 % while every split cost a slab to write and reduce; with the splits
-# accumulated in L2 more of them are free: 4.105 / 4.091 / 4.172 ms at 25 / 50 / 100 %)
-_WGRAD_SM_PERCENT = int(_os.environ.get('UNETZOO_WGRAD_SM_PERCENT', '50'))
+# planned SM share of an overlapped wgrad: measured with the splits accumulated in L2 and the full-resolution maps at
+# 100 %: 25 / 28 / 30 / 32 / 35 % -> 4.03-4.04 ms, 40 / 45 / 50 / 70 % -> 4.08 ms, 100 % -> 4.17 ms
+_WGRAD_SM_PERCENT = int(_os.environ.get('UNETZOO_WGRAD_SM_PERCENT', '30'))
 
 
 def set_concurrency(enabled):

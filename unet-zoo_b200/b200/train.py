@@ -159,8 +159,13 @@ class TrainStep:
             # priority than the auxiliary weight-gradient streams: critical-path kernels are scheduled first
             prio = int(os.environ.get('UNETZOO_MAIN_PRIORITY', '-2'))
             cap_stream = torch.cuda.Stream(device=self.device, priority=prio)
+            mark = len(kern.wgrad_reducer.keep)
             with torch.cuda.graph(self.graph, stream=cap_stream):
                 self._body()
+            # the weight-gradient slabs the captured launches point at live (and die) with this object, not with the
+            # process-wide reducer
+            self._slabs = kern.wgrad_reducer.keep[mark:]
+            del kern.wgrad_reducer.keep[mark:]
             self.launches_per_step = _lib.raw('uz_launch_count')() - n0
             if hasattr(self.opt, 'finish_capture'):
                 self.opt.finish_capture()

@@ -692,6 +692,7 @@ class PHISeg(nn.Module):
         back = {id(a): p for p, a in ((p, alias[id(p)]) for p in params)}
         self._swap_parameters(alias)
         try:
+            mark = len(kern.wgrad_reducer.keep)
             with torch.cuda.graph(graph, stream=cap):
                 self._plain_forward(st['patch'], st['mask'], True)
                 loss = self.elbo(st['mask'])
@@ -702,4 +703,6 @@ class PHISeg(nn.Module):
         finally:
             self._swap_parameters(back)         # the caller's Parameter objects (and its optimizer's references) are back
         torch.cuda.synchronize(dev)
-        st.update(graph_fwd=graph, loss=loss.detach(), grads=grads, params=params)
+        st.update(graph_fwd=graph, loss=loss.detach(), grads=grads, params=params,
+                  slabs=kern.wgrad_reducer.keep[mark:])        # weight-gradient slabs of the captured launches
+        del kern.wgrad_reducer.keep[mark:]

@@ -11,8 +11,6 @@
 // algorithmic minimum (read dout, y once; write dy once).
 #include <cooperative_groups.h>
 
-#include <cstdlib>
-
 #include "common.cuh"
 #include "unetzoo_b200.h"
 
@@ -193,11 +191,9 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_cluster_kernel(const BnBwdPar
 
 // pixel slices per cluster: enough CTAs to keep a slice short, at most the portable cluster size
 inline int plan_cluster(long long npix, int* pix_per_cta, int* staged) {
-  static const int forced = [] { const char* e = getenv("UZ_BN_CLUSTER_K"); return e ? atoi(e) : 0; }();
-  static const int target = [] { const char* e = getenv("UZ_BN_CLUSTER_PIX"); return e ? atoi(e) : 512; }();
+  // <= 512 pixels per CTA (measured: 128 or 512 make no difference up to 16x16x12; one CTA for everything is 2x slower)
   int K = 1;
-  while (K < 8 && (npix + K - 1) / K > target) K *= 2;
-  if (forced > 0) K = forced;
+  while (K < 8 && (npix + K - 1) / K > 512) K *= 2;
   long long ppc = (npix + K - 1) / K;
   ppc = (ppc + 7) / 8 * 8;
   *pix_per_cta = static_cast<int>(ppc);

@@ -58,7 +58,8 @@ class TrainStep:
             self.packer = net._packer() if hasattr(net, '_packer') else None
             if self.dp is None:
                 from . import dp as _dp
-                self.dp = _dp.GradientAllReduce(net.parameters(), optimizer=optimizer, packer=self.packer)
+                self.dp = _dp.GradientAllReduce(net.parameters(), optimizer=optimizer, packer=self.packer,
+                                                tail_bytes=2 << 20)    # the last update cannot hide: keep it short
             elif self.dp.optimizer is None and self.dp.buckets is None:
                 self.dp.optimizer, self.dp.packer = optimizer, self.packer
             if self.packer is not None:

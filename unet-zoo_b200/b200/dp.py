@@ -1,8 +1,8 @@
 """One-process-per-GPU data parallelism for the drop-in models (the reference has none).
 
 Training: batch data-parallel.  Parameters are grouped into a few flat fp32 buckets in the order their gradients are
-produced (recorded during the warm-up steps), sized geometrically from a small tail bucket for the last arrivals up to
-``bucket_bytes`` for the early ones; the tensor-core weight
+produced (recorded during the warm-up steps), cut from the end of backward (``tail_bytes`` for the last arrivals, doubling
+up to ``bucket_bytes``; by default both are 24 MB: few collectives beat a short last one); the tensor-core weight
 gradients are written straight into the buckets (``grad_view_for``), the few remaining gradients are gathered with one
 multi-tensor copy, ``.grad`` is re-pointed at views of the flat buffer and ONE NCCL all-reduce (average) per bucket is
 issued from a side stream.  ``finish()`` makes the compute stream wait, so communication overlaps the rest of backward.  Parameters that never receive a gradient (``{posterior,prior}.upsampling_path.4.*``)
@@ -84,9 +84,8 @@ class GradientAllReduce:
     """Bucketed, overlapped gradient averaging.  Usage per step:
          dp.zero_grad(); loss.backward(); dp.finish(); optimizer.step()
     The first steps (before ``freeze_buckets``) use a plain post-backward all-reduce and record the ORDER in which the
-    gradients are produced; ``freeze_buckets`` then builds the flat buckets in that order -- large ones first, a small
-    tail (``tail_bytes``) for the parameters whose gradients arrive last, so that the only all-reduce that cannot hide
-    behind backward is short.  A completed bucket is handed to NCCL from a side stream that waits for the producing
+    gradients are produced; ``freeze_buckets`` then builds the flat buckets in that order, counted from the END of
+    backward (``tail_bytes`` for the parameters whose gradients arrive last, doubling up to ``bucket_bytes``).  A completed bucket is handed to NCCL from a side stream that waits for the producing
     streams (the compute stream is never stalled by communication set-up); ``finish()`` joins.
 
     ``optimizer`` (a b200.optim.FusedAdam) moves the parameter update into the bucket pipeline as well: as soon as a

@@ -254,8 +254,10 @@ def conv_fwd(x, w_packed, out=None, scale=None, shift=None, relu=False, stats=Fa
 
 class WgradReducer:
     """Deferred split-K reductions of the weight gradients (uz_conv_wgrad_partial + uz_wgrad_reduce_batched): the
-    tensor-core kernels of many layers leave their partial slabs behind, ONE launch per <= 64 layers reduces / transposes
-    them into the OIHW gradient tensors.  ``flush()`` must run on a stream that is ordered after every producing launch
+    tensor-core kernels of many layers leave their partial slabs behind (one slab per layer when the splits accumulate in
+    L2, one per split in deterministic mode and for volumes), ONE launch per <= 64 layers reduces / transposes them into
+    the OIHW gradient tensors -- or nobody does: the fused optimizer of a single-GPU TrainStep reads the slabs itself
+    (``hold`` / ``take``).  ``flush()`` must run on a stream that is ordered after every producing launch
     (b200.ops joins the auxiliary streams first).  The descriptor rows are launch parameters: nothing to upload, a
     captured CUDA graph holds them by value."""
     MAX_ROWS = 64

@@ -76,3 +76,40 @@ def test_shard_counts_match_survey():
     assert dp.shard_counts(100, 8) == [13, 13, 13, 13, 12, 12, 12, 12]
     assert dp.shard_counts(100, 1) == [100]
     assert sum(dp.shard_counts(16, 3)) == 16
+
+
+def test_buckets_are_cut_from_the_end_of_the_production_order():
+    """single process, no process group: the bucket layout only depends on the order the gradients were produced in
+    (recorded by the hooks) and on tail_bytes / bucket_bytes -- tail first from the END, doubling up to the cap, production
+    order preserved inside and across buckets; parameters without a gradient stay outside"""
+    sys.path.insert(0, PKG)
+    from b200 import dp
+    sizes = [40, 10, 30, 20, 50, 5, 60, 15]                    # floats; forward order
+    params = [torch.nn.Parameter(torch.randn(n)) for n in sizes]
+    unused = torch.nn.Parameter(torch.ones(7))
+    ar = dp.GradientAllReduce(params + [unused], bucket_bytes=100 * 4, tail_bytes=20 * 4)
+    ar.zero_grad()
+    loss = sum((k + 1) * p.sum() for k, p in enumerate(params))
+    loss.backward()                                            # one backward: the hooks record the production order
+    ar.finish()
+    produced = list(ar._order)
+    assert len(produced) == len(params)
+    ar.freeze_buckets()
+    flat_order = [id(p) for b in ar.buckets for p in b.params]
+    assert flat_order == produced                              # production order, nothing lost, nothing duplicated
+    assert all(id(unused) != pid for pid in flat_order) and unused.grad is None
+    by_id = {id(p): p.numel() for p in params}
+    bucket_floats = [sum(by_id[id(p)] for p in b.params) for b in ar.buckets]
+    # counted from the end: the last bucket holds at most tail_bytes (or one oversized parameter), the limits double
+    limit = 20
+    for nfl, b in zip(reversed(bucket_floats), reversed(ar.buckets)):
+        assert nfl <= limit or len(b.params) == 1, (bucket_floats, limit)
+        limit = min(2 * limit, 100)
+    # a second step through the frozen buckets: gradients land in the flat buffers (views), values unchanged
+    ar.zero_grad()
+    sum((k + 1) * p.sum() for k, p in enumerate(params)).backward()
+    ar.finish()
+    for k, p in enumerate(params):
+        assert torch.equal(p.grad, torch.full_like(p, float(k + 1)))
+        assert p.grad.data_ptr() == dp.grad_view_for(p).data_ptr()
+    ar.remove()

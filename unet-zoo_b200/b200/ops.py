@@ -67,7 +67,7 @@ def _plan_wgrad_share(overlapped):
         _aux['planned_for'] = overlapped
 
 _AUX_STREAMS = max(1, int(_os.environ.get('UNETZOO_AUX_STREAMS', '3')))      # weight-gradient streams (round robin)
-_aux = {'streams': {}, 'pending': [], 'keep': [], 'callback_queued': False, 'next': 0}
+_aux = {'streams': {}, 'pending': [], 'keep': [], 'callback_task': None, 'next': 0}
 
 
 def _aux_stream(device):
@@ -93,7 +93,7 @@ def sync_aux_streams():
     _aux['pending'] = []
     kern.wgrad_reducer.flush(force=False)      # unless an optimizer that reads the slabs itself follows (TrainStep)
     _aux['keep'] = []
-    _aux['callback_queued'] = False
+    _aux['callback_task'] = None
     _aux['next'] = 0
 
 
@@ -145,8 +145,11 @@ def _run_on_aux(fn, keep, last=False):
         _aux['planned_for'] = None
     else:
         _plan_wgrad_share(overlapped)
-    if not _aux['callback_queued'] and torch._C._current_graph_task_id() != -1:
-        _aux['callback_queued'] = True          # also joins / flushes when nothing ran on an auxiliary stream
+    task = torch._C._current_graph_task_id()
+    if task != -1 and _aux['callback_task'] != task:
+        # once per backward pass (keyed by its graph-task id, so a pass that died with an exception cannot leave the flag
+        # set); also joins / flushes when nothing ran on an auxiliary stream
+        _aux['callback_task'] = task
         torch.autograd.Variable._execution_engine.queue_callback(sync_aux_streams)
     if not overlapped:
         return fn()
